@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py — hitbox updates/s + pair TOI solves/s of the bulk step (BASELINE.json metric).
+
+A "step" = one cb200_bulk_update over the whole scene: every hitbox rebased to T, re-binned into the grid,
+every candidate pair's collide_time solved (plus separate_time for the overlapping pairs), next event
+min-reduced.  Workload at N=1: config 3 (1M mixed circles/rects, uniform density 0.025/unit^2, cell 4,
+padding 0.01, bulk step every 0.1 time units).  N>1: weak scaling, one 1M-hitbox column strip per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n HITBOXES] [--workload c3|c3_dense|c5]
+
+Prints ONE JSON line (rank 0).  `value` = device-resident whole-job throughput; `e2e` = the same metric with
+new velocities coming from pinned HOST arrays each step and the sorted event list read back (H2D + D2H inside
+the timed region); `roofline` = dominant kernel vs the measured HBM peak; `cpu_baseline` = the oracle (C++
+restatement of the reference; Rust toolchain absent) on one host core, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DT = 0.1  # bulk step period (config 2/3)
+METRIC = "hitbox updates/sec (full re-bin + pair TOI solve + next-event min per bulk step)"
+UNIT = "hitbox updates/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def make_workload(scenes, name: str, n: int, rank: int, world: int):
+    """Per-rank scene.  Weak scaling: rank r owns the column strip [r*W, (r+1)*W) of a world `world` strips wide."""
+    if name == "c3":
+        side = math.sqrt(n / 0.025)
+        s = scenes.make_scene(n, side, side, seed=scenes.SEED_BASE + 3 + 1000 * rank, x0=side * rank)
+    elif name == "c3_dense":
+        side = math.sqrt(n / 1.0)
+        s = scenes.make_scene(n, side, side, seed=scenes.SEED_BASE + 3 + 1000 * rank, x0=side * rank)
+    elif name == "c5":
+        s = scenes.c5(n)
+        s["pos_x"] = s["pos_x"] + math.sqrt(n / 0.025) * rank
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    s["id"] = s["id"] + np.uint64(rank) * np.uint64(n)
+    return s
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+
+    def run(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def oracle_timing(scene_fn, n_sample: int, steps: int, warmup: int):
+    """The reference's CPU implementation of the path (C++ restatement; Rust toolchain absent): the ascending
+    set_hitbox_vel loop per step, single-threaded like the reference.  Returns (updates/s, solves/s, ms/step, stats)."""
+    from oracle import oracle_py as oracle
+
+    s = scene_fn(n_sample)
+    orc = oracle.Collider(4.0, 0.01)
+    orc.add_hitboxes(s)
+    T = 0.0
+    for _ in range(warmup):
+        orc.bulk_update(end_time=T + DT)
+        T = min(T + DT, orc.next_time())
+        orc.set_time(T)
+    orc.stats(reset=True)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        orc.bulk_update(end_time=T + DT)
+        done += 1
+        T = min(T + DT, orc.next_time())  # stay within the reference's set_time contract without draining events
+        orc.set_time(T)
+    el = time.perf_counter() - t0
+    st = orc.stats()
+    return n_sample * done / el, (st["collide_solves"] + st["separate_solves"]) / el, el / done * 1e3, st
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = min(args.n, args.ref_sample)
+    scenes = importlib.import_module("collider-rs_b200.scenes")
+    ups, sps, ms, st = oracle_timing(lambda m: make_workload(scenes, args.workload, m, 0, 1), n_sample, args.steps, max(1, min(args.warmup, 1)))
+    sample = f"{n_sample} hitboxes of the {args.workload} scene (same density), {args.steps} bulk-equivalent steps (ascending set_hitbox_vel loop)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {args.n} mixed circles/rects, cell_width 4, padding 0.01, bulk step every {DT}", "cpu_sample_hitboxes": n_sample},
+        "pair_solves_per_s": sps,
+        "cpu_baseline": {"value": ups, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "note": "C++17 restatement of the reference (oracle/); the Rust crate cannot be built here (no rustc/cargo)"},
+        "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores_available": os.cpu_count(),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000, help="hitboxes per GPU")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c3_dense", "c5"])
+    ap.add_argument("--ref-sample", type=int, default=200_000, help="hitboxes in the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cb = importlib.import_module("collider-rs_b200")
+    scenes = importlib.import_module("collider-rs_b200.scenes")
+    hbm_peak, peak_kind = load_peaks()
+
+    n = args.n
+    scene = make_workload(scenes, args.workload, n, rank, world)
+    eng = cb.Engine(scenes.CELL_WIDTH, scenes.PADDING, device=local_rank)
+    eng.upload_state(**scene)
+    # first step: pairs already in contact at T = 0 come back as Collide events at T; they become the overlap set
+    # (what add_hitbox's immediate-overlap list does in the reference, collider.rs:355-365)
+    res = eng.bulk_update(0.0, end_time=DT)
+    ev = eng.fetch_events()
+    touching = ev[(ev["kind"] == cb.EV_COLLIDE) & (ev["time"] == 0.0)]
+    eng.set_overlaps(touching["a"], touching["b"])
+    step_no = [0]
+
+    def device_step():
+        step_no[0] += 1
+        T = step_no[0] * DT
+        return eng.bulk_update(T, end_time=T + DT)
+
+    for _ in range(args.warmup):
+        res = device_step()
+    launches0 = eng.launch_count()
+    eng.reset_timing()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    solves = 0
+    entries = cells = events = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = device_step()
+        solves += res.n_collide_solves + res.n_separate_solves
+        entries += res.n_entries
+        cells += res.n_cells
+        events += res.n_events
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = eng.launch_count() - launches0
+    dev_ms, stage_ms = eng.step_timing()
+
+    # e2e: new velocities arrive from pinned host arrays every step, sorted events are read back
+    pvx, pvy = cb.PinnedArray(n, np.float64), cb.PinnedArray(n, np.float64)
+    pvx.array[:] = scene["vel_x"]
+    pvy.array[:] = scene["vel_y"]
+
+    def e2e_step():
+        step_no[0] += 1
+        T = step_no[0] * DT
+        r = eng.bulk_update(T, end_time=T + DT, vel_x=pvx.array, vel_y=pvy.array)
+        evs = eng.fetch_events()
+        return r, evs
+
+    for _ in range(3):
+        e2e_step()
+    d2h = 0
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        r, evs = e2e_step()
+        d2h += evs.nbytes + C_sizeof_result(cb)
+    barrier()
+    e2e_wall = time.perf_counter() - t1
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    times = torch.tensor([wall, e2e_wall, dev_ms], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([float(solves), float(entries), float(cells), float(events)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    wall_max, e2e_max, dev_ms_max = times.tolist()
+    solves_all, entries_all, cells_all, events_all = sums.tolist()
+
+    if rank == 0:
+        K = args.steps
+        E, Cc, V, P = entries / K, cells / K, events / K, solves / K
+        lw, lh = eng.get_grid()
+        n_slots = 1 << (lw + lh)
+        # algorithmic bytes per launch of each kernel (DESIGN.md "bytes per unit")
+        alg = {
+            "stage_a": 242.0 * n + 8.0 * E,
+            "scan": 8.0 * n_slots,
+            "scatter": 32.0 * n + 16.0 * E,
+            "pairs": 12.0 * E + 64.0 * min(E, 2.0 * P) + 128.0 * P + 16.0 * V,
+        }
+        dom = max(("stage_a", "scan", "scatter", "pairs"), key=lambda k: stage_ms[k])
+        achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        step_bytes = sum(alg.values())
+        line = {
+            "metric": METRIC, "value": n * world * K / wall_max, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": wall_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"{args.workload}: {n} mixed circles/rects per GPU, uniform density, cell_width 4, padding 0.01, bulk step every {DT} "
+                            f"(full re-bin + pair TOI solve + next-event min)",
+                "hitboxes_per_gpu": n, "grid_slots": n_slots, "l2": "working set per step (SoA state + HbRec + slot table + entries) > 126 MB L2; no flush",
+                "timing": "wall clock around K synchronous C-ABI calls bracketed by barrier+cuda sync, max over ranks; device_ms_per_step = CUDA events on the engine stream",
+            },
+            "pair_solves_per_s": solves_all / wall_max,
+            "device_ms_per_step": dev_ms_max,
+            "stage_ms": stage_ms,
+            "per_step": {"cell_entries": E, "cells": Cc, "pair_solves": P, "events": V},
+            "gpu_launches": int(launches),
+            "e2e": {"value": n * world * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(16 * n), "d2h_bytes_per_step": int(d2h / K),
+                    "ms_per_step": e2e_max / K * 1e3},
+            "roofline": {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_kind": peak_kind,
+                         "whole_step": {"bytes": step_bytes, "achieved": step_bytes / (dev_ms_max * 1e-3) / 1e9,
+                                        "frac": step_bytes / (dev_ms_max * 1e-3) / 1e9 / hbm_peak}},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            n_sample = min(n, args.ref_sample)
+            ups, sps, ms, st = oracle_timing(lambda m: make_workload(scenes, args.workload, m, 0, 1), n_sample, 3, 1)
+            line["cpu_baseline"] = {"value": ups, "unit": UNIT, "cores": 1, "kind": "port", "pair_solves_per_s": sps,
+                                    "sample": f"{n_sample} hitboxes of the same scene density, 3 bulk-equivalent steps (ascending set_hitbox_vel loop), single thread",
+                                    "host_cores_available": os.cpu_count()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def C_sizeof_result(cb):
+    import ctypes
+
+    return ctypes.sizeof(cb.StepResult)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,308 @@
+"""collider-rs_b200 — B200-native engine for collider-rs's data-parallel hot path.
+
+This package is the Python-side loader/binding of ``lib/libcollider_b200.so`` (the C ABI declared in
+``include/collider_b200.h``).  It holds no algorithm of its own: every call below forwards to the
+CUDA library, and importing the binding fails loudly if the library has not been built
+(``python collider-rs_b200/build.py``) — there is no CPU fallback.
+
+Import with ``importlib.import_module("collider-rs_b200")`` (the directory name carries a hyphen).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcollider_b200.so")
+
+KIND_CIRCLE, KIND_RECT = 0, 1
+GROUP_NONE = 0xFFFFFFFF
+EV_REITERATE, EV_COLLIDE, EV_SEPARATE = 0, 1, 2
+E_ARG, E_CUDA, E_CONTRACT, E_STATE = -1, -2, -3, -4
+N_STAGES = 6
+STAGE_NAMES = ("pre", "stage_a", "scan", "scatter", "pairs", "tail")
+INF = math.inf
+
+
+class ColliderError(RuntimeError):
+    """A failed C-ABI call; ``code`` is the CB200_E_* value.  E_CONTRACT restates a reference panic."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class StateView(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("id", C.c_void_p)] + [
+        (k, C.c_void_p)
+        for k in ("pos_x", "pos_y", "dim_x", "dim_y", "vel_x", "vel_y", "rsz_x", "rsz_y", "start_time", "end_time", "pub_end_time",
+                  "kind", "group", "interact_mask")
+    ]
+
+
+class StateOut(C.Structure):
+    _fields_ = [("n", C.c_uint64)] + [
+        (k, C.c_void_p) for k in ("pos_x", "pos_y", "dim_x", "dim_y", "vel_x", "vel_y", "rsz_x", "rsz_y", "start_time", "end_time", "pub_end_time")
+    ]
+
+
+class VelView(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("vel_x", "vel_y", "rsz_x", "rsz_y", "end_time")]
+
+
+class Event(C.Structure):
+    _fields_ = [("time", C.c_double), ("a", C.c_uint64), ("b", C.c_uint64), ("kind", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+EVENT_DTYPE = np.dtype([("time", "<f8"), ("a", "<u8"), ("b", "<u8"), ("kind", "<u4"), ("_pad", "<u4")])
+
+
+class StepResult(C.Structure):
+    _fields_ = [
+        ("next_time", C.c_double),
+        ("next_event", Event),
+        ("n_hitboxes", C.c_uint64),
+        ("n_entries", C.c_uint64),
+        ("n_cells", C.c_uint64),
+        ("n_collide_solves", C.c_uint64),
+        ("n_separate_solves", C.c_uint64),
+        ("n_events", C.c_uint64),
+        ("n_solitaire", C.c_uint64),
+        ("error_flags", C.c_uint32),
+        ("_pad", C.c_uint32),
+        ("error_slot", C.c_uint64),
+    ]
+
+
+EXPORTS = (
+    "cb200_abi_version", "cb200_create", "cb200_destroy", "cb200_last_error", "cb200_set_grid", "cb200_get_grid",
+    "cb200_host_alloc", "cb200_host_free", "cb200_upload_state", "cb200_download_state", "cb200_set_overlaps",
+    "cb200_bulk_update", "cb200_fetch_events", "cb200_fetch_candidate_pairs", "cb200_fetch_cell_entries",
+    "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
+    "cb200_last_step_timing", "cb200_reset_timing",
+)
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the CUDA library.  Raises if it is missing — the product has no other path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is not built: run `python collider-rs_b200/build.py` (nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, dbl, i32 = C.c_void_p, C.c_uint64, C.c_double, C.c_int
+    L.cb200_abi_version.restype = i32
+    L.cb200_create.argtypes = [dbl, dbl, i32, C.POINTER(vp)]
+    L.cb200_destroy.argtypes = [vp]
+    L.cb200_destroy.restype = None
+    L.cb200_last_error.argtypes = [vp]
+    L.cb200_last_error.restype = C.c_char_p
+    L.cb200_set_grid.argtypes = [vp, i32, i32]
+    L.cb200_get_grid.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.cb200_host_alloc.argtypes = [u64]
+    L.cb200_host_alloc.restype = vp
+    L.cb200_host_free.argtypes = [vp]
+    L.cb200_host_free.restype = None
+    L.cb200_upload_state.argtypes = [vp, C.POINTER(StateView)]
+    L.cb200_download_state.argtypes = [vp, C.POINTER(StateOut)]
+    L.cb200_set_overlaps.argtypes = [vp, vp, vp, u64]
+    L.cb200_bulk_update.argtypes = [vp, dbl, C.POINTER(VelView), dbl, C.POINTER(StepResult)]
+    L.cb200_fetch_events.argtypes = [vp, vp, u64, u64, C.POINTER(u64)]
+    L.cb200_fetch_candidate_pairs.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
+    L.cb200_fetch_cell_entries.argtypes = [vp, vp, vp, vp, u64, C.POINTER(u64)]
+    L.cb200_fetch_index_rects.argtypes = [vp, vp, u64]
+    L.cb200_collide_time_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+    L.cb200_separate_time_batch.argtypes = [vp, u64, vp, vp, vp, vp, dbl, vp]
+    L.cb200_launch_count.argtypes = [vp]
+    L.cb200_launch_count.restype = u64
+    L.cb200_last_step_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), i32]
+    L.cb200_reset_timing.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _col(a, dtype, n):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if a.shape != (n,):
+        raise ValueError(f"column has shape {a.shape}, expected ({n},)")
+    return a
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory from cb200_host_alloc."""
+
+    def __init__(self, shape, dtype):
+        self._L = load_library()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        self._p = self._L.cb200_host_alloc(max(1, n * dtype.itemsize))
+        if not self._p:
+            raise MemoryError("cb200_host_alloc failed")
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            self._L.cb200_host_free(self._p)
+            self._p = None
+
+
+class Engine:
+    """One device context: the hitbox table, the cell table and the event buffer of one `Collider`."""
+
+    def __init__(self, cell_width: float, padding: float, device: int = 0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.cb200_create(cell_width, padding, device, C.byref(h))
+        if rc != 0:
+            raise ColliderError(rc, self._L.cb200_last_error(None).decode())
+        self._h = h
+        self.cell_width, self.padding, self.device = cell_width, padding, device
+        self.n = 0
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cb200_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ColliderError(rc, self._L.cb200_last_error(self._h).decode())
+
+    def set_grid(self, log2_w: int, log2_h: int):
+        self._check(self._L.cb200_set_grid(self._h, log2_w, log2_h))
+
+    def get_grid(self):
+        a, b = C.c_int(), C.c_int()
+        self._check(self._L.cb200_get_grid(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def upload_state(self, *, id, pos_x, pos_y, dim_x, dim_y, vel_x, vel_y, kind, rsz_x=None, rsz_y=None, start_time=None, end_time=None,
+                     pub_end_time=None, group=None, interact_mask=None):
+        n = len(id)
+        z = np.zeros(n)
+        cols = dict(
+            id=_col(id, np.uint64, n),
+            pos_x=_col(pos_x, np.float64, n), pos_y=_col(pos_y, np.float64, n),
+            dim_x=_col(dim_x, np.float64, n), dim_y=_col(dim_y, np.float64, n),
+            vel_x=_col(vel_x, np.float64, n), vel_y=_col(vel_y, np.float64, n),
+            rsz_x=_col(z if rsz_x is None else rsz_x, np.float64, n), rsz_y=_col(z if rsz_y is None else rsz_y, np.float64, n),
+            start_time=_col(z if start_time is None else start_time, np.float64, n),
+            end_time=_col(np.full(n, INF) if end_time is None else end_time, np.float64, n),
+            pub_end_time=_col(np.full(n, INF) if pub_end_time is None else pub_end_time, np.float64, n),
+            kind=_col(kind, np.uint8, n),
+            group=_col(np.zeros(n, np.uint32) if group is None else group, np.uint32, n),
+            interact_mask=_col(np.ones(n, np.uint32) if interact_mask is None else interact_mask, np.uint32, n),
+        )
+        v = StateView()
+        v.n = n
+        for k, a in cols.items():
+            setattr(v, k, a.ctypes.data)
+        self._check(self._L.cb200_upload_state(self._h, C.byref(v)))
+        self.n = n
+
+    def download_state(self):
+        n = self.n
+        names = ("pos_x", "pos_y", "dim_x", "dim_y", "vel_x", "vel_y", "rsz_x", "rsz_y", "start_time", "end_time", "pub_end_time")
+        out = {k: np.zeros(n) for k in names}
+        o = StateOut()
+        o.n = n
+        for k in names:
+            setattr(o, k, out[k].ctypes.data)
+        self._check(self._L.cb200_download_state(self._h, C.byref(o)))
+        return out
+
+    def set_overlaps(self, id_a, id_b):
+        a = np.ascontiguousarray(id_a, dtype=np.uint64)
+        b = np.ascontiguousarray(id_b, dtype=np.uint64)
+        if a.shape != b.shape:
+            raise ValueError("id_a / id_b length mismatch")
+        self._check(self._L.cb200_set_overlaps(self._h, _ptr(a), _ptr(b), a.size))
+
+    def bulk_update(self, time: float, end_time: float = INF, vel_x=None, vel_y=None, rsz_x=None, rsz_y=None, end_time_arr=None) -> StepResult:
+        """cb200_bulk_update.  Arrays are host arrays of length n (numpy, or PinnedArray.array)."""
+        arrs = [vel_x, vel_y, rsz_x, rsz_y, end_time_arr]
+        res = StepResult()
+        if all(a is None for a in arrs):
+            rc = self._L.cb200_bulk_update(self._h, time, None, end_time, C.byref(res))
+        else:
+            keep = [None if a is None else _col(a, np.float64, self.n) for a in arrs]
+            v = VelView(*[None if a is None else a.ctypes.data for a in keep])
+            rc = self._L.cb200_bulk_update(self._h, time, C.byref(v), end_time, C.byref(res))
+        self.last_result = res
+        self._check(rc)
+        return res
+
+    def fetch_events(self, offset: int = 0, cap: int | None = None) -> np.ndarray:
+        if cap is None:
+            cap = max(0, int(self.last_result.n_events) - offset)
+        buf = np.zeros(cap, dtype=EVENT_DTYPE)
+        got = C.c_uint64()
+        self._check(self._L.cb200_fetch_events(self._h, _ptr(buf), cap, offset, C.byref(got)))
+        return buf[: got.value]
+
+    def fetch_candidate_pairs(self):
+        n = C.c_uint64()
+        self._check(self._L.cb200_fetch_candidate_pairs(self._h, None, None, 0, C.byref(n)))
+        hi = np.zeros(n.value, dtype=np.uint64)
+        lo = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            self._check(self._L.cb200_fetch_candidate_pairs(self._h, _ptr(hi), _ptr(lo), n.value, C.byref(n)))
+        return hi, lo
+
+    def fetch_cell_entries(self):
+        n = C.c_uint64()
+        self._check(self._L.cb200_fetch_cell_entries(self._h, None, None, None, 0, C.byref(n)))
+        x = np.zeros(n.value, dtype=np.int32)
+        y = np.zeros(n.value, dtype=np.int32)
+        i = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            self._check(self._L.cb200_fetch_cell_entries(self._h, _ptr(x), _ptr(y), _ptr(i), n.value, C.byref(n)))
+        return x, y, i
+
+    def fetch_index_rects(self) -> np.ndarray:
+        r = np.zeros((self.n, 4), dtype=np.int32)
+        self._check(self._L.cb200_fetch_index_rects(self._h, _ptr(r), self.n))
+        return r
+
+    def _batch(self, fn, a, ka, b, kb, *extra):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1, 9)
+        b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1, 9)
+        ka = np.ascontiguousarray(ka, dtype=np.uint8).reshape(-1)
+        kb = np.ascontiguousarray(kb, dtype=np.uint8).reshape(-1)
+        out = np.zeros(a.shape[0])
+        self._check(fn(self._h, a.shape[0], _ptr(a), _ptr(ka), _ptr(b), _ptr(kb), *extra, _ptr(out)))
+        return out
+
+    def collide_time_batch(self, a, ka, b, kb):
+        return self._batch(self._L.cb200_collide_time_batch, a, ka, b, kb)
+
+    def separate_time_batch(self, a, ka, b, kb, padding):
+        return self._batch(self._L.cb200_separate_time_batch, a, ka, b, kb, C.c_double(padding))
+
+    def launch_count(self) -> int:
+        return int(self._L.cb200_launch_count(self._h))
+
+    def reset_timing(self):
+        self._check(self._L.cb200_reset_timing(self._h))
+
+    def step_timing(self):
+        total = C.c_float()
+        stages = (C.c_float * N_STAGES)()
+        self._check(self._L.cb200_last_step_timing(self._h, C.byref(total), stages, N_STAGES))
+        return total.value, dict(zip(STAGE_NAMES, [float(s) for s in stages]))

@@ -1,0 +1,198 @@
+// Shared device-side types and helpers of the B200 engine (sm_100a only).
+//
+// Vocabulary follows the reference (SergiusIW/collider-rs 0.3.1): hitbox, DurHitbox, IndexRect, grid
+// cell, HbEvent.  A *slot* is one element of the device cell table: cell (x, y) folded modulo the grid
+// period (2^lw x 2^lh).  Aliasing between cells that share a slot costs time, never correctness (see
+// pair ownership in kernels.cuh).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "narrowphase.cuh"
+
+namespace cb200 {
+
+// ---- error flags (mirrors include/collider_b200.h CB200_F_*) ----
+constexpr uint32_t kFInvalidTime = 1u << 0, kFEndTime = 1u << 1, kFCircleResize = 1u << 2, kFTooSmall = 1u << 3,
+                   kFEmptyRect = 1u << 4, kFRectSpan = 1u << 5, kFNan = 1u << 6, kFHighTime = 1u << 7,
+                   kFIdNotFound = 1u << 8;
+
+constexpr uint32_t kGroupNone = 0xFFFFFFFFu;
+constexpr uint32_t kCollideBit = 0x80000000u;  // in PairEvent.b_kind: 1 = Collide, 0 = Separate
+constexpr uint64_t kPairClass = 0x8000000000000000ull;
+
+// The DurHitbox a hitbox presents to the pair stage at the step time (core/dur_hitbox/mod.rs:27-70)
+// plus its IndexRect (index_rect.rs:17-31) and profile bits: 96 B = three 32-B sectors.  Sector 0 is
+// all the ownership / group test needs; sectors 1-2 are fetched only for pairs that are solved.
+struct alignas(32) HbRec {
+    int32_t sx, sy, ex, ey;  // IndexRect, half-open
+    double dur;              // internal end_time - T
+    uint32_t kgb;            // bit0 kind (0 circle, 1 rect), bit1 binned (has a group and a valid rect), bits 8..15 group
+    uint32_t mask;           // interact_groups as a bit mask
+    double px, py, w, h;
+    double vx, vy, rw, rh;
+};
+static_assert(sizeof(HbRec) == 96, "HbRec must be three sectors");
+
+struct RecHead {  // sector 0 of HbRec
+    int32_t sx, sy, ex, ey;
+    double dur;
+    uint32_t kgb, mask;
+};
+
+__device__ __forceinline__ RecHead load_head(const HbRec* __restrict__ rec, uint32_t i) {
+    const int4* p = reinterpret_cast<const int4*>(rec + i);
+    const int4 a = __ldg(p), b = __ldg(p + 1);
+    RecHead h;
+    h.sx = a.x; h.sy = a.y; h.ex = a.z; h.ey = a.w;
+    h.dur = __hiloint2double(b.y, b.x);
+    h.kgb = (uint32_t)b.z;
+    h.mask = (uint32_t)b.w;
+    return h;
+}
+
+__device__ __forceinline__ DurHb load_body(const HbRec* __restrict__ rec, uint32_t i, const RecHead& h) {
+    const double2* p = reinterpret_cast<const double2*>(rec + i);
+    const double2 a = __ldg(p + 2), b = __ldg(p + 3), c = __ldg(p + 4), d = __ldg(p + 5);
+    DurHb r;
+    r.px = a.x; r.py = a.y; r.w = b.x; r.h = b.y;
+    r.vx = c.x; r.vy = c.y; r.rw = d.x; r.rh = d.y;
+    r.dur = h.dur;
+    r.kind = (int)(h.kgb & 1u);
+    return r;
+}
+
+// One pair event queued by a step: time, creator (higher slot), partner (lower slot) | kind bit.
+struct alignas(16) PairEvent {
+    double time;
+    uint32_t a;
+    uint32_t b_kind;
+};
+
+// Total order of the event queue (events.rs:28-68 + SURVEY.md 8c canonical tie-break):
+// t = order-preserving bits of the time; tie = class | hi << 32 | kind << 31 | lo  (solitaire: slot).
+struct MinKey {
+    uint64_t t, tie;
+};
+__device__ __forceinline__ bool key_less(const MinKey& a, const MinKey& b) { return a.t < b.t || (a.t == b.t && a.tie < b.tie); }
+__host__ __device__ __forceinline__ uint64_t time_key(double t) {
+#if defined(__CUDA_ARCH__)
+    const uint64_t b = (uint64_t)__double_as_longlong(t);
+#else
+    uint64_t b;
+    memcpy(&b, &t, 8);
+#endif
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double key_time(uint64_t k) {
+    const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double t;
+    memcpy(&t, &b, 8);
+    return t;
+#endif
+}
+constexpr uint64_t kKeyMax = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ MinKey warp_min(MinKey k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MinKey other;
+        other.t = __shfl_xor_sync(0xffffffffu, k.t, o);
+        other.tie = __shfl_xor_sync(0xffffffffu, k.tie, o);
+        if (key_less(other, k)) k = other;
+    }
+    return k;
+}
+
+// Block-wide min of a MinKey; the result is valid in thread 0.  blockDim.x must be a multiple of 32, <= 1024.
+__device__ __forceinline__ MinKey block_min(MinKey k) {
+    __shared__ MinKey s_part[32];
+    k = warp_min(k);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_part[warp] = k;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        k = lane < nw ? s_part[lane] : MinKey{kKeyMax, kKeyMax};
+        k = warp_min(k);
+    }
+    return k;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Block-wide sum; valid in thread 0.
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long v) {
+    __shared__ unsigned long long s_sum[32];
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_sum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        v = lane < nw ? s_sum[lane] : 0ull;
+        v = warp_sum(v);
+    }
+    return v;
+}
+
+// Device-resident step counters (zeroed at the start of every step).
+struct Counters {
+    unsigned long long n_entries;      // E, written by the scan
+    unsigned long long n_cells;        // non-empty slots
+    unsigned long long n_collide;      // collide_time evaluations
+    unsigned long long n_separate;     // separate_time evaluations
+    unsigned long long n_pair_events;  // pair events with time < 1e50 (may exceed the buffer capacity -> overflow)
+    unsigned long long n_solitaire;    // Reiterate events
+    unsigned long long err_slot;       // lowest slot that reported an error
+    unsigned int err_flags;
+    unsigned int scan_ticket;
+    unsigned int overflow_entries;
+    unsigned int n_captured;           // debug capture cursor
+    unsigned long long diff_hi, diff_lo;  // sort: OR of key differences
+    unsigned long long n_sort_keys;
+};
+
+__device__ __forceinline__ void report_error(Counters* ctr, uint32_t flags, uint64_t slot) {
+    atomicOr(&ctr->err_flags, flags);
+    atomicMin(&ctr->err_slot, (unsigned long long)slot);
+}
+
+// Grid fold: cell (x, y) -> slot.
+struct GridGeom {
+    int lw, lh;
+    __host__ __device__ __forceinline__ uint32_t slot(int32_t x, int32_t y) const {
+        return ((uint32_t)x & ((1u << lw) - 1u)) | (((uint32_t)y & ((1u << lh) - 1u)) << lw);
+    }
+    __host__ __device__ __forceinline__ uint32_t n_slots() const { return 1u << (lw + lh); }
+};
+
+// Warp-aggregated append: the lanes that call this together claim consecutive positions with one atomic.
+__device__ __forceinline__ unsigned long long warp_agg_claim(unsigned long long* counter) {
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+}
+__device__ __forceinline__ unsigned int warp_agg_claim32(unsigned int* counter) {
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + (unsigned int)__popc(m & ((1u << lane) - 1u));
+}
+
+}  // namespace cb200

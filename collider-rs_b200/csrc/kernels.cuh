@@ -1,0 +1,504 @@
+// The bulk-step kernels: stage A (rebase + solitaire check + swept bounds + IndexRect + cell count),
+// cell scatter, pair stage (candidate generation + collide_time + event emit + min-reduce), separate
+// stage (overlapping pairs), finalize.  sm_100a, FMA contraction off (-fmad=false).
+//
+// Reference-equivalent definition of one bulk step at time T:
+//     for id in ascending HbId: Collider::internal_update_hitbox(id, Some(vel_id))   src/core/collider.rs:231-250
+// which leaves, for every pair whose NEW index rects share a cell, one event created by the higher id
+// against the lower id already rebased to T.  Each kernel cites the reference lines whose results it reproduces.
+#pragma once
+#include "common.cuh"
+
+namespace cb200 {
+
+constexpr int kThreads = 256;
+
+struct StateCols {  // SoA hitbox table, slot order == ascending HbId
+    double *px, *py, *w, *h, *vx, *vy, *rw, *rh, *start, *end, *pub_end;
+    uint8_t* kind;
+    uint32_t *group, *mask;
+    uint8_t* reit;  // 1 = a Reiterate event is queued at `end` (collider.rs:441-447)
+};
+
+struct StepArgs {
+    uint32_t n;
+    int rebase;  // 0 = re-run of binning on an already-rebased table (after a buffer grew): skip the advance
+    double T, cell_width, padding, end_scalar;
+    StateCols s;
+    const double *nvx, *nvy, *nrw, *nrh, *nend;  // optional new velocity columns (device), null = keep
+    HbRec* rec;
+    uint32_t* slot_count;
+    GridGeom geom;
+    Counters* ctr;
+    MinKey* partial;  // [gridDim.x] solitaire minima
+};
+
+__device__ __forceinline__ bool is_finite(double x) { return fabs(x) < cb_inf(); }
+
+// Rust `f64 as i32`: saturating, NaN -> 0 — exactly cvt.rzi.s32.f64.
+__device__ __forceinline__ int32_t f64_as_i32(double v) { return __double2int_rz(v); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Stage A: per hitbox, the part of internal_update_hitbox that touches only that hitbox.
+//   rebase        HitboxInfo::pub_hitbox_at_time (collider.rs:488-497), PlacedShape::advance (shape/mod.rs:260-265)
+//   install vel   collider.rs:237-240, Hitbox::validate (core/mod.rs:146-162)
+//   solitaire     Collider::solitaire_event_check, release build (collider.rs:420-448); Grid::cell_period
+//                 (grid.rs:61-72); PlacedBounds::max_edge over the velocity bounds (shape/mod.rs:294-300,
+//                 core/mod.rs:109-116); Hitbox::time_until_too_small (core/mod.rs:164-175)
+//   DurHitbox     Hitbox::to_dur_hitbox (core/mod.rs:177-187)
+//   swept bounds  DurHitbox::bounding_box (dur_hitbox/mod.rs:88-99)
+//   IndexRect     Grid::index_bounds (grid.rs:101-113)
+//   cell count    first half of the counting sort that replaces Grid::update_area (grid.rs:137-175)
+// Reads the SoA columns coalesced, writes the rebased columns back and the 96-B HbRec for the pair stage.
+__global__ void __launch_bounds__(kThreads) k_stage_a(const StepArgs a) {
+    MinKey best{kKeyMax, kKeyMax};
+    unsigned long long n_sol = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        double px = a.s.px[i], py = a.s.py[i], w = a.s.w[i], h = a.s.h[i];
+        double vx = a.s.vx[i], vy = a.s.vy[i], rw = a.s.rw[i], rh = a.s.rh[i];
+        const double start = a.s.start[i], pub_end_old = a.s.pub_end[i];
+        const uint32_t kind = a.s.kind[i], group = a.s.group[i], mask = a.s.mask[i];
+        const double T = a.T;
+        uint32_t err = 0;
+
+        // pub_hitbox_at_time(T): assert start <= T <= pub_end, then advance by T - start.
+        if (!(T >= start && T <= pub_end_old)) err |= kFInvalidTime;
+        const double dt = T - start;
+        if (!(dt < kHighTime)) err |= kFHighTime;
+        if (a.rebase) {
+            px = px + vx * dt;
+            py = py + vy * dt;
+            w = w + rw * dt;
+            h = h + rh * dt;
+        }
+
+        // install the new velocity, validate
+        if (a.nvx) vx = a.nvx[i];
+        if (a.nvy) vy = a.nvy[i];
+        if (a.nrw) rw = a.nrw[i];
+        if (a.nrh) rh = a.nrh[i];
+        const double user_end = a.nend ? a.nend[i] : a.end_scalar;
+        if (!(user_end >= T)) err |= kFEndTime;  // also catches NaN
+        if (kind == (uint32_t)kCircle && !(rw == rh)) err |= kFCircleResize;
+        if (!(w >= a.padding && h >= a.padding)) err |= kFTooSmall;
+        if (!(is_finite(px) && is_finite(py) && is_finite(w) && is_finite(h) && is_finite(vx) && is_finite(vy) && is_finite(rw) &&
+              is_finite(rh)))
+            err |= kFNan;
+
+        // solitaire_event_check (release build)
+        const bool has_group = group != kGroupNone;
+        double period = cb_inf();
+        if (has_group) {
+            const double speed = fmax(fmax(fabs(vx - rw * 0.5), fabs(vy - rh * 0.5)), fmax(fabs(vx + rw * 0.5), fabs(vy + rh * 0.5)));
+            if (!(speed <= 0.0)) period = a.cell_width / speed;
+        }
+        double r_time = T + period;
+        bool reit = true;
+        if (user_end < r_time) {
+            r_time = user_end;
+            reit = false;
+        }
+        {
+            const double min_size = a.padding * 0.9;
+            if (!(w > min_size && h > min_size)) err |= kFTooSmall;
+            double tus = cb_inf();
+            if (rw < 0.0) tus = fmin(tus, (min_size - w) / rw);
+            if (rh < 0.0) tus = fmin(tus, (min_size - h) / rh);
+            const double small_end = T + tus;
+            if (small_end < r_time) {
+                r_time = small_end;
+                reit = false;
+            }
+        }
+        reit = reit && (r_time < kHighTime);  // EventManager::new_event_key drops time >= 1e50 (events.rs:156-159)
+        const double dur = r_time - T;
+
+        // swept bounds + IndexRect (only hitboxes with a group enter the grid, collider.rs:328)
+        HbRec rec;
+        rec.sx = rec.sy = 0;
+        rec.ex = rec.ey = 0;
+        bool binned = false;
+        if (has_group && err == 0) {
+            DurHb d;
+            d.px = px; d.py = py; d.w = w; d.h = h; d.vx = vx; d.vy = vy; d.rw = rw; d.rh = rh; d.dur = dur; d.kind = (int)kind;
+            const Box4 bb = swept_bounds(d, dur);
+            if (!bb.ok) {
+                err |= (dur < kHighTime) ? kFNan : kFHighTime;
+            } else {
+                const double min_x = bb.cx - bb.w * 0.5, max_x = bb.cx + bb.w * 0.5;
+                const double min_y = bb.cy - bb.h * 0.5, max_y = bb.cy + bb.h * 0.5;
+                const int32_t sx = f64_as_i32(floor(min_x / a.cell_width));
+                const int32_t sy = f64_as_i32(floor(min_y / a.cell_width));
+                const int32_t ex = max(f64_as_i32(ceil(max_x / a.cell_width)), (int32_t)((uint32_t)sx + 1u));
+                const int32_t ey = max(f64_as_i32(ceil(max_y / a.cell_width)), (int32_t)((uint32_t)sy + 1u));
+                const int64_t nx = (int64_t)ex - sx, ny = (int64_t)ey - sy;
+                if (nx <= 0 || ny <= 0) {
+                    err |= kFEmptyRect;  // IndexRect::new (index_rect.rs:26-29)
+                } else if (nx > (1ll << a.geom.lw) || ny > (1ll << a.geom.lh)) {
+                    err |= kFRectSpan;
+                } else {
+                    rec.sx = sx; rec.sy = sy; rec.ex = ex; rec.ey = ey;
+                    binned = true;
+                    for (int32_t x = sx; x != ex; ++x)
+                        for (int32_t y = sy; y != ey; ++y) atomicAdd(&a.slot_count[a.geom.slot(x, y)], 1u);
+                }
+            }
+        }
+        if (err) report_error(a.ctr, err, i);
+
+        // write back: state columns + pair-stage record
+        a.s.px[i] = px; a.s.py[i] = py; a.s.w[i] = w; a.s.h[i] = h;
+        if (a.nvx) a.s.vx[i] = vx;
+        if (a.nvy) a.s.vy[i] = vy;
+        if (a.nrw) a.s.rw[i] = rw;
+        if (a.nrh) a.s.rh[i] = rh;
+        a.s.start[i] = T;
+        a.s.end[i] = r_time;
+        a.s.pub_end[i] = user_end;
+        a.s.reit[i] = reit ? 1 : 0;
+
+        rec.dur = dur;
+        rec.kgb = (kind & 1u) | (binned ? 2u : 0u) | ((has_group ? (group & 0xffu) : 0xffu) << 8);
+        rec.mask = mask;
+        rec.px = px; rec.py = py; rec.w = w; rec.h = h;
+        rec.vx = vx; rec.vy = vy; rec.rw = rw; rec.rh = rh;
+        {
+            int4* out = reinterpret_cast<int4*>(a.rec + i);
+            const int4* in = reinterpret_cast<const int4*>(&rec);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) out[k] = in[k];
+        }
+
+        if (reit) {
+            ++n_sol;
+            const MinKey k{time_key(r_time), (uint64_t)i};
+            if (key_less(k, best)) best = k;
+        }
+    }
+    best = block_min(best);
+    const unsigned long long tot = block_sum(n_sol);
+    if (threadIdx.x == 0) {
+        a.partial[blockIdx.x] = best;
+        if (tot) atomicAdd(&a.ctr->n_solitaire, tot);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Exclusive scan of the slot counts (single pass, decoupled look-back).  n is a multiple of the tile size.
+// tile_state[t]: bits 63..62 = flag (0 invalid, 1 tile aggregate, 2 inclusive prefix), low 32 bits value.
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kThreads * kScanItems;
+
+__global__ void __launch_bounds__(kThreads) k_scan_slots(uint32_t* __restrict__ data, uint32_t n, unsigned long long* tile_state,
+                                                         Counters* ctr) {
+    __shared__ uint32_t s_tile, s_prefix;
+    __shared__ uint32_t s_warp[kThreads / 32];
+    if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->scan_ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    uint4* p = reinterpret_cast<uint4*>(data + (size_t)tile * kScanTile + (size_t)threadIdx.x * kScanItems);
+    uint32_t v[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems / 4; ++k) {
+        const uint4 q = p[k];
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+    uint32_t sum = 0, nonzero = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        sum += v[k];
+        nonzero += v[k] != 0;
+    }
+    // block exclusive scan of the per-thread sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t ws = lane < kThreads / 32 ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < kThreads / 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= o) ws += t;
+        }
+        if (lane < kThreads / 32) s_warp[lane] = ws;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t block_total = s_warp[kThreads / 32 - 1];
+    const uint32_t thread_excl = inc - sum + (warp ? s_warp[warp - 1] : 0);
+
+    if (threadIdx.x == 0) {
+        uint32_t prefix = 0;
+        if (tile == 0) {
+            atomicExch(&tile_state[0], (2ull << 62) | block_total);
+        } else {
+            atomicExch(&tile_state[tile], (1ull << 62) | block_total);
+            int64_t j = (int64_t)tile - 1;
+            for (;;) {
+                unsigned long long st;
+                do {
+                    st = *reinterpret_cast<volatile unsigned long long*>(&tile_state[j]);
+                } while ((st >> 62) == 0);
+                prefix += (uint32_t)st;
+                if ((st >> 62) == 2) break;
+                --j;
+            }
+            atomicExch(&tile_state[tile], (2ull << 62) | (uint32_t)(prefix + block_total));
+        }
+        s_prefix = prefix;
+        if ((size_t)(tile + 1) * kScanTile >= n) ctr->n_entries = (unsigned long long)prefix + block_total;
+    }
+    const unsigned long long nz = block_sum(nonzero);  // contains the __syncthreads that publishes s_prefix
+    if (threadIdx.x == 0 && nz) atomicAdd(&ctr->n_cells, nz);
+    uint32_t run = s_prefix + thread_excl;
+#pragma unroll
+    for (int k = 0; k < kScanItems / 4; ++k) {
+        uint4 q;
+        q.x = run; run += v[4 * k];
+        q.y = run; run += v[4 * k + 1];
+        q.z = run; run += v[4 * k + 2];
+        q.w = run; run += v[4 * k + 3];
+        p[k] = q;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Scatter: second half of the counting sort.  offsets[s] enters as the start of slot s and leaves as its end
+// (so afterwards start(s) = s ? offsets[s-1] : 0).  entries[pos] = (hitbox slot index, grid slot).
+__global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const HbRec* __restrict__ rec, uint32_t* offsets, uint2* entries,
+                                                      uint32_t cap_entries, GridGeom geom, Counters* ctr) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const RecHead h = load_head(rec, i);
+        if (!(h.kgb & 2u)) continue;
+        for (int32_t x = h.sx; x != h.ex; ++x)
+            for (int32_t y = h.sy; y != h.ey; ++y) {
+                const uint32_t s = geom.slot(x, y);
+                const uint32_t pos = atomicAdd(&offsets[s], 1u);
+                if (pos < cap_entries) entries[pos] = make_uint2(i, s);
+                else ctr->overflow_entries = 1u;
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Overlap set (HitboxInfo.overlaps, collider.rs:463) as an open-addressing hash set of (hi << 32 | lo).
+struct OverlapSet {
+    const unsigned long long* table;  // kKeyMax = empty
+    uint32_t cap_mask;                // capacity - 1 (power of two); 0 = no overlaps at all
+};
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ bool overlap_contains(const OverlapSet& ov, uint32_t hi, uint32_t lo) {
+    const unsigned long long key = ((unsigned long long)hi << 32) | lo;
+    uint32_t p = (uint32_t)mix64(key) & ov.cap_mask;
+    for (;;) {
+        const unsigned long long k = __ldg(ov.table + p);
+        if (k == key) return true;
+        if (k == kKeyMax) return false;
+        p = (p + 1) & ov.cap_mask;
+    }
+}
+__global__ void k_overlap_insert(const uint2* __restrict__ pairs, uint32_t n_pairs, unsigned long long* table, uint32_t cap_mask) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const uint2 pr = pairs[i];
+    const unsigned long long key = ((unsigned long long)pr.x << 32) | pr.y;
+    uint32_t p = (uint32_t)mix64(key) & cap_mask;
+    for (;;) {
+        const unsigned long long prev = atomicCAS(&table[p], kKeyMax, key);
+        if (prev == kKeyMax || prev == key) return;
+        p = (p + 1) & cap_mask;
+    }
+}
+// ids -> slots (binary search in the ascending id column); pairs out as (hi slot, lo slot).
+__global__ void k_overlap_map_ids(const uint64_t* __restrict__ ids, uint32_t n, const uint64_t* __restrict__ id_a,
+                                  const uint64_t* __restrict__ id_b, uint32_t n_pairs, uint2* pairs, Counters* ctr) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    uint32_t s[2];
+    const uint64_t want[2] = {id_a[i], id_b[i]};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (ids[mid] < want[k]) lo = mid + 1;
+            else hi = mid;
+        }
+        if (lo >= n || ids[lo] != want[k]) {
+            report_error(ctr, kFIdNotFound, i);
+            lo = 0;
+        }
+        s[k] = lo;
+    }
+    if (s[0] == s[1]) report_error(ctr, kFIdNotFound, i);
+    pairs[i] = make_uint2(max(s[0], s[1]), min(s[0], s[1]));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pair stage: one thread per cell entry, paired with the entries that precede it in the same slot.
+//   candidates   Grid::overlapping_ids (grid.rs:115-135) restricted to the surviving (hi, lo) pairs; the
+//                hash-set de-duplication is replaced by pair ownership: a pair is handled only in the slot of
+//                cell (max(sx_i, sx_j), max(sy_i, sy_j)) — the min corner of the rect intersection — so every
+//                pair sharing >= 1 cell is produced exactly once, and aliased slot-mates are rejected.
+//   filters      lo.group in hi.interact_groups (grid.rs:122, key group); not already overlapping (collider.rs:351)
+//   solve        hi.collide_time(lo rebased to T) (collider.rs:354 -> solvers.rs:25-34)
+//   queue        add_pair_event(T + delay, Collide(hi, lo)), dropped when >= 1e50 (collider.rs:367-372, events.rs:156-159)
+//   min          EventManager::peek_time under the canonical order (events.rs:171-173)
+struct PairArgs {
+    const uint2* entries;
+    const uint32_t* offsets;  // end of each slot
+    const HbRec* rec;
+    GridGeom geom;
+    double T;
+    OverlapSet ov;
+    PairEvent* events;
+    uint32_t cap_events;
+    Counters* ctr;
+    MinKey* partial;   // [gridDim.x]
+    uint2* capture;    // CAPTURE mode: candidate pairs (hi, lo)
+    uint32_t cap_capture;
+};
+
+template <bool CAPTURE>
+__global__ void __launch_bounds__(kThreads) k_pairs(const PairArgs a) {
+    MinKey best{kKeyMax, kKeyMax};
+    unsigned long long n_solved = 0;
+    const uint32_t n_entries = (uint32_t)a.ctr->n_entries;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += stride) {
+        const uint2 en = a.entries[e];
+        const uint32_t i = en.x, slot = en.y;
+        const uint32_t first = slot ? __ldg(a.offsets + slot - 1) : 0u;
+        if (e == first) continue;
+        const RecHead hi_ = load_head(a.rec, i);
+        DurHb body_i;
+        bool have_i = false;
+        for (uint32_t f = first; f < e; ++f) {
+            const uint32_t j = a.entries[f].x;
+            const RecHead hj = load_head(a.rec, j);
+            // ownership: min corner of the rect intersection must be this slot's cell
+            const int32_t ox = max(hi_.sx, hj.sx), oy = max(hi_.sy, hj.sy);
+            if (ox >= min(hi_.ex, hj.ex) || oy >= min(hi_.ey, hj.ey)) continue;
+            if (a.geom.slot(ox, oy) != slot) continue;
+            const bool i_is_hi = i > j;
+            const uint32_t hi = i_is_hi ? i : j, lo = i_is_hi ? j : i;
+            const uint32_t mask_hi = i_is_hi ? hi_.mask : hj.mask;
+            const uint32_t group_lo = ((i_is_hi ? hj.kgb : hi_.kgb) >> 8) & 0xffu;
+            if (!((mask_hi >> group_lo) & 1u)) continue;
+            if (a.ov.cap_mask && overlap_contains(a.ov, hi, lo)) continue;
+            ++n_solved;
+            if (CAPTURE) {
+                const uint32_t pos = warp_agg_claim32(&a.ctr->n_captured);
+                if (pos < a.cap_capture) a.capture[pos] = make_uint2(hi, lo);
+                continue;
+            }
+            if (!have_i) {
+                body_i = load_body(a.rec, i, hi_);
+                have_i = true;
+            }
+            const DurHb body_j = load_body(a.rec, j, hj);
+            // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486): advanced by T - start = 0
+            const DurHb A = i_is_hi ? body_i : body_j;
+            const DurHb B = advanced(i_is_hi ? body_j : body_i, 0.0);
+            const double delay = collide_time(A, B);
+            if (delay != delay) report_error(a.ctr, kFNan, hi);
+            const double t = a.T + delay;
+            if (t < kHighTime) {
+                const unsigned long long pos = warp_agg_claim(&a.ctr->n_pair_events);
+                if (pos < a.cap_events) a.events[pos] = PairEvent{t, hi, lo | kCollideBit};
+                const MinKey k{time_key(t), kPairClass | ((uint64_t)hi << 32) | kCollideBit | lo};
+                if (key_less(k, best)) best = k;
+            }
+        }
+    }
+    best = block_min(best);
+    const unsigned long long tot = block_sum(n_solved);
+    if (threadIdx.x == 0) {
+        a.partial[blockIdx.x] = best;
+        if (tot) atomicAdd(&a.ctr->n_collide, tot);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Separate stage: one thread per currently-overlapping pair (collider.rs:329-339):
+//   hi.separate_time(lo rebased to T, padding) -> add_pair_event(T + delay, Separate(hi, lo)).
+__global__ void __launch_bounds__(kThreads) k_separate(const uint2* __restrict__ pairs, uint32_t n_pairs, const HbRec* __restrict__ rec,
+                                                       double T, double padding, PairEvent* events, uint32_t cap_events, Counters* ctr,
+                                                       MinKey* partial) {
+    MinKey best{kKeyMax, kKeyMax};
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) {
+        const uint2 pr = pairs[p];
+        const RecHead hh = load_head(rec, pr.x), hl = load_head(rec, pr.y);
+        const DurHb A = load_body(rec, pr.x, hh);
+        const DurHb B = advanced(load_body(rec, pr.y, hl), 0.0);
+        const double delay = separate_time(A, B, padding);
+        if (delay != delay) report_error(ctr, kFNan, pr.x);
+        const double t = T + delay;
+        if (t < kHighTime) {
+            const unsigned long long pos = warp_agg_claim(&ctr->n_pair_events);
+            if (pos < cap_events) events[pos] = PairEvent{t, pr.x, pr.y};
+            const MinKey k{time_key(t), kPairClass | ((uint64_t)pr.x << 32) | pr.y};
+            if (key_less(k, best)) best = k;
+        }
+    }
+    best = block_min(best);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = best;
+        if (blockIdx.x == 0) atomicAdd(&ctr->n_separate, (unsigned long long)n_pairs);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Finalize: reduce the per-block minima of the three stages into the step result (device copy).
+struct StepResultDev {
+    double next_time;
+    uint64_t next_tie;  // MinKey.tie of the minimum (kKeyMax if none)
+    Counters ctr;
+};
+__global__ void __launch_bounds__(kThreads) k_finalize(const MinKey* __restrict__ partial, uint32_t n_partial, const Counters* ctr,
+                                                       StepResultDev* out) {
+    MinKey best{kKeyMax, kKeyMax};
+    for (uint32_t i = threadIdx.x; i < n_partial; i += blockDim.x) {
+        const MinKey k = partial[i];
+        if (key_less(k, best)) best = k;
+    }
+    best = block_min(best);
+    if (threadIdx.x == 0) {
+        out->next_time = best.t == kKeyMax && best.tie == kKeyMax ? cb_inf() : key_time(best.t);
+        out->next_tie = best.tie;
+        out->ctr = *ctr;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batched narrowphase on explicit DurHitbox pairs (n x 9 doubles: px,py,dw,dh,vx,vy,rw,rh,duration).
+__device__ __forceinline__ DurHb load_dur9(const double* __restrict__ r, uint8_t kind) {
+    DurHb d;
+    d.px = r[0]; d.py = r[1]; d.w = r[2]; d.h = r[3]; d.vx = r[4]; d.vy = r[5]; d.rw = r[6]; d.rh = r[7]; d.dur = r[8];
+    d.kind = kind;
+    return d;
+}
+__global__ void k_collide_batch(uint64_t n, const double* __restrict__ a, const uint8_t* __restrict__ ka, const double* __restrict__ b,
+                                const uint8_t* __restrict__ kb, double* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = collide_time(load_dur9(a + 9 * i, ka[i]), load_dur9(b + 9 * i, kb[i]));
+}
+__global__ void k_separate_batch(uint64_t n, const double* __restrict__ a, const uint8_t* __restrict__ ka, const double* __restrict__ b,
+                                 const uint8_t* __restrict__ kb, double padding, double* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = separate_time(load_dur9(a + 9 * i, ka[i]), load_dur9(b + 9 * i, kb[i]), padding);
+}
+
+}  // namespace cb200

@@ -1,0 +1,225 @@
+// Narrowphase: circle/rect time-of-collision and time-of-separation, f64, FMA-free.
+//
+// Device arithmetic for SURVEY.md §8 rows a-10 … a-15.  Each function names the reference code whose
+// *results* it must reproduce bit-for-bit (paths under the reference's src/).  The structure is not the
+// reference's: shapes are flat register structs, the four-cardinal interval sweep is fully unrolled and
+// exits through a single predicate, and the rect/circle corner stage re-uses the quadratic solve with
+// the corner folded in as a zero-diameter circle.
+//
+// Bit-exactness rules (DESIGN.md §"f64 contract"): compile with -fmad=false (no contraction), keep
+// every product/sum in the reference's association order, use true f64 `/` and `sqrt` (IEEE
+// round-to-nearest on sm_100a), never a reciprocal.
+//
+// CB_HD marks functions that are also compiled for the host *only by tests/host_narrowphase_check.cpp*
+// (a pre-GPU logic check of this very source against the oracle); the product library never calls the
+// host instantiation.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CB_HD __host__ __device__ __forceinline__
+#else
+#define CB_HD inline
+#endif
+
+namespace cb200 {
+
+constexpr double kHighTime = 1e50;  // core/mod.rs:28
+constexpr int kCircle = 0;
+constexpr int kRect = 1;
+
+// A hitbox at the solve time: placed shape + velocity + remaining duration (DurHitbox,
+// core/dur_hitbox/mod.rs:27-70), flattened.
+struct DurHb {
+    double px, py, w, h, vx, vy, rw, rh, dur;
+    int kind;
+};
+
+CB_HD double cb_inf() {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(0x7ff0000000000000LL);
+#else
+    return INFINITY;
+#endif
+}
+CB_HD double cb_nan() {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(0x7ff8000000000000LL);
+#else
+    return NAN;
+#endif
+}
+
+// PlacedShape::advance (geom/shape/mod.rs:260-265, 99-101): product rounded, then sum rounded.
+CB_HD DurHb advanced(const DurHb& s, double t) {
+    DurHb r = s;
+    r.px = s.px + s.vx * t;
+    r.py = s.py + s.vy * t;
+    r.w = s.w + s.rw * t;
+    r.h = s.h + s.rh * t;
+    return r;
+}
+
+// Four-cardinal interval sweep of two moving boxes: results of solvers::rect_rect_time
+// (core/dur_hitbox/solvers.rs:60-86) with PlacedBounds::card_overlap (geom/shape/mod.rs:285-304) in
+// Card::values order MinusX, MinusY, PlusX, PlusY (geom/card.rs:47-49).
+//   card_overlap(a, b, c) = b.edge(c) + a.edge(flip c); with edge(-X) = -left the sum (-l_b) + r_a is
+//   the same IEEE operation as r_a - l_b, so each card is one subtraction of two edges.
+// The reference leaves the loop at the first card that decides the answer; every early exit returns the
+// same sentinel (inf for collide, 0 for separate) and the running window only shrinks, so evaluating
+// all four cards and testing once at the end selects the same value.
+CB_HD double box_sweep_time(const DurHb& a, const DurHb& b, bool for_collide) {
+    const double a_l = a.px - a.w * 0.5, a_r = a.px + a.w * 0.5, a_b = a.py - a.h * 0.5, a_t = a.py + a.h * 0.5;
+    const double b_l = b.px - b.w * 0.5, b_r = b.px + b.w * 0.5, b_b = b.py - b.h * 0.5, b_t = b.py + b.h * 0.5;
+    const double av_l = a.vx - a.rw * 0.5, av_r = a.vx + a.rw * 0.5, av_b = a.vy - a.rh * 0.5, av_t = a.vy + a.rh * 0.5;
+    const double bv_l = b.vx - b.rw * 0.5, bv_r = b.vx + b.rw * 0.5, bv_b = b.vy - b.rh * 0.5, bv_t = b.vy + b.rh * 0.5;
+    const double o[4] = {a_r - b_l, a_t - b_b, b_r - a_l, b_t - a_b};
+    const double ov[4] = {av_r - bv_l, av_t - bv_b, bv_r - av_l, bv_t - av_b};
+    double start = 0.0, end = cb_inf();
+    bool decided = false;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const bool apart = o[c] < 0.0;
+        if (apart) {
+            if (!for_collide || ov[c] <= 0.0) decided = true;
+            else start = fmax(start, -o[c] / ov[c]);
+        } else if (ov[c] < 0.0) {
+            end = fmin(end, -o[c] / ov[c]);
+        }
+    }
+    if (decided || start >= end) return for_collide ? cb_inf() : 0.0;
+    return for_collide ? start : end;
+}
+
+// util::quad_root_ascending (util.rs:23-32) + the `Some(result) if result >= 0.0` filter of
+// solvers::circle_circle_time (solvers.rs:105-108).
+CB_HD double first_root_or_inf(double a, double b, double c) {
+    const double det = b * b - a * c * 4.0;
+    if (det <= 0.0) return cb_inf();
+    const double r = (b >= 0.0) ? (c * 2.0) / (-b - sqrt(det)) : (-b + sqrt(det)) / (a * 2.0);
+    return (r >= 0.0) ? r : cb_inf();
+}
+
+// solvers::circle_circle_time (solvers.rs:88-109) on raw scalars so the rect-corner stage can call it
+// with a zero-diameter "circle" (solvers.rs:153-165).
+CB_HD double disc_sweep_time(double a_px, double a_py, double a_d, double a_vx, double a_vy, double a_rd,  //
+                             double b_px, double b_py, double b_d, double b_vx, double b_vy, double b_rd, bool for_collide) {
+    const double sign = for_collide ? 1.0 : -1.0;
+    const double net_rad = (a_d + b_d) * 0.5;
+    const double dx = a_px - b_px, dy = a_py - b_py;
+    const double coeff_c = sign * (net_rad * net_rad - (dx * dx + dy * dy));
+    if (coeff_c > 0.0) return 0.0;
+    const double net_rad_vel = (a_rd + b_rd) * 0.5;
+    const double dvx = a_vx - b_vx, dvy = a_vy - b_vy;
+    const double coeff_a = sign * (net_rad_vel * net_rad_vel - (dvx * dvx + dvy * dvy));
+    const double coeff_b = sign * 2.0 * (net_rad * net_rad_vel - (dx * dvx + dy * dvy));
+    return first_root_or_inf(coeff_a, coeff_b, coeff_c);
+}
+
+// solvers::rebased_rect_circle_collide_time (solvers.rs:153-165): if the circle centre lies in a corner
+// sector of the box (geom/shape/mod.rs:239-243, 330-353), sweep the circle against that moving corner
+// (corner of the velocity bounds = corner velocity, geom/shape/mod.rs:306-318).
+CB_HD double corner_stage_time(const DurHb& box, const DurHb& disc) {
+    const double l = box.px - box.w * 0.5, r = box.px + box.w * 0.5;
+    const double b = box.py - box.h * 0.5, t = box.py + box.h * 0.5;
+    const int sx = disc.px < l ? -1 : (disc.px > r ? 1 : 0);
+    const int sy = disc.py < b ? -1 : (disc.py > t ? 1 : 0);
+    if (sx == 0 || sy == 0) return 0.0;
+    const double cx = sx < 0 ? l : r, cy = sy < 0 ? b : t;
+    const double cvx = sx < 0 ? box.vx - box.rw * 0.5 : box.vx + box.rw * 0.5;
+    const double cvy = sy < 0 ? box.vy - box.rh * 0.5 : box.vy + box.rh * 0.5;
+    return disc_sweep_time(cx, cy, 0.0, cvx, cvy, 0.0, disc.px, disc.py, disc.w, disc.vx, disc.vy, disc.rw, true);
+}
+
+// solvers::rect_circle_collide_time (solvers.rs:119-131)
+CB_HD double box_disc_collide(const DurHb& box, const DurHb& disc, double duration) {
+    const double base = box_sweep_time(box, disc, true);
+    if (base >= duration) return cb_inf();
+    return base + corner_stage_time(advanced(box, base), advanced(disc, base));
+}
+
+// solvers::rect_circle_separate_time (solvers.rs:133-151): time-reversed corner stage from base_time.
+CB_HD double box_disc_separate(const DurHb& box, const DurHb& disc) {
+    const double base = box_sweep_time(box, disc, false);
+    if (base == 0.0) return 0.0;
+    if (base >= kHighTime) return cb_inf();
+    DurHb bx = advanced(box, base), dc = advanced(disc, base);
+    bx.vx = -bx.vx; bx.vy = -bx.vy; bx.rw = -bx.rw; bx.rh = -bx.rh;  // DurHbVel::negate, dur_hitbox/mod.rs:47-53
+    dc.vx = -dc.vx; dc.vy = -dc.vy; dc.rw = -dc.rw; dc.rh = -dc.rh;
+    return fmax(base - corner_stage_time(bx, dc), 0.0);
+}
+
+// solvers::time_unpadded (solvers.rs:46-58)
+CB_HD double sweep_unpadded(const DurHb& a, const DurHb& b, bool for_collide, double duration) {
+    double result;
+    if (a.kind == kRect && b.kind == kRect) {
+        result = box_sweep_time(a, b, for_collide);
+    } else if (a.kind == kCircle && b.kind == kCircle) {
+        result = disc_sweep_time(a.px, a.py, a.w, a.vx, a.vy, a.rw, b.px, b.py, b.w, b.vx, b.vy, b.rw, for_collide);
+    } else {
+        const DurHb& box = (a.kind == kRect) ? a : b;
+        const DurHb& disc = (a.kind == kRect) ? b : a;
+        result = for_collide ? box_disc_collide(box, disc, duration) : box_disc_separate(box, disc);
+    }
+    return (result >= duration) ? cb_inf() : result;
+}
+
+// Swept bounds of a hitbox over `duration`: DurHitbox::bounding_box_for (dur_hitbox/mod.rs:92-99) =
+// as_rect when still (DurHbVel::is_still :43-45), else PlacedShape::bounding_box of start and end shapes
+// (geom/shape/mod.rs:249-258) — note the centre is recomputed as left + w*0.5, and the edges used
+// afterwards are centre -/+ w*0.5 again, so the round trip is kept.
+struct Box4 {
+    double cx, cy, w, h;
+    bool ok;  // false where the reference would panic (duration >= 1e50 while moving; negative dims)
+};
+CB_HD Box4 swept_bounds(const DurHb& s, double duration) {
+    Box4 o;
+    if (s.vx == 0.0 && s.vy == 0.0 && s.rw == 0.0 && s.rh == 0.0) {
+        o.cx = s.px; o.cy = s.py; o.w = s.w; o.h = s.h;
+        o.ok = (s.w >= 0.0 && s.h >= 0.0);
+        return o;
+    }
+    const DurHb e = advanced(s, duration);
+    const double right = fmax(s.px + s.w * 0.5, e.px + e.w * 0.5);
+    const double top = fmax(s.py + s.h * 0.5, e.py + e.h * 0.5);
+    const double left = fmin(s.px - s.w * 0.5, e.px - e.w * 0.5);
+    const double bottom = fmin(s.py - s.h * 0.5, e.py - e.h * 0.5);
+    o.w = right - left;
+    o.h = top - bottom;
+    o.cx = left + o.w * 0.5;
+    o.cy = bottom + o.h * 0.5;
+    o.ok = (duration < kHighTime) && (o.w >= 0.0) && (o.h >= 0.0);
+    return o;
+}
+
+// PlacedShape::overlaps for two boxes = min over the four card overlaps >= 0
+// (geom/shape/mod.rs:154-156 -> normals.rs:22-30).
+CB_HD bool boxes_touch(const Box4& a, const Box4& b) {
+    const double a_l = a.cx - a.w * 0.5, a_r = a.cx + a.w * 0.5, a_b = a.cy - a.h * 0.5, a_t = a.cy + a.h * 0.5;
+    const double b_l = b.cx - b.w * 0.5, b_r = b.cx + b.w * 0.5, b_b = b.cy - b.h * 0.5, b_t = b.cy + b.h * 0.5;
+    return (a_r - b_l >= 0.0) && (a_t - b_b >= 0.0) && (b_r - a_l >= 0.0) && (b_t - a_b >= 0.0);
+}
+
+// solvers::collide_time (solvers.rs:25-34).  NaN where the reference would panic.
+CB_HD double collide_time(const DurHb& a, const DurHb& b) {
+    const double duration = fmin(a.dur, b.dur);
+    const Box4 ba = swept_bounds(a, duration), bb = swept_bounds(b, duration);
+    if (!(ba.ok && bb.ok)) return cb_nan();
+    if (!boxes_touch(ba, bb)) return cb_inf();
+    return sweep_unpadded(a, b, true, duration);
+}
+
+// solvers::separate_time (solvers.rs:36-44): the circle of a (rect, circle) pair goes first, and only the
+// first shape is inflated by 2*padding — the result is not symmetric in (a, b) bit-for-bit.
+CB_HD double separate_time(const DurHb& a_in, const DurHb& b_in, double padding) {
+    const bool swap = (a_in.kind == kRect && b_in.kind == kCircle);
+    DurHb a = swap ? b_in : a_in;
+    const DurHb& b = swap ? a_in : b_in;
+    a.w = a.w + padding * 2.0;
+    a.h = a.h + padding * 2.0;
+    if (!(a.w >= 0.0 && a.h >= 0.0)) return cb_nan();  // Shape::new, geom/shape/mod.rs:44-47
+    return sweep_unpadded(a, b, false, fmin(a.dur, b.dur));
+}
+
+}  // namespace cb200

@@ -1,0 +1,192 @@
+/* collider_b200.h — C ABI of the B200 device engine behind collider-rs's `Collider<P: HbProfile>`.
+ *
+ * This is the drop-in boundary.  The reference (SergiusIW/collider-rs 0.3.1, pure Rust)
+ * has no FFI of its own; the cut is made at the three internal seams its orchestrator calls:
+ *   (1) Grid::update_hitbox -> candidate ids           src/core/grid.rs:79-92   (called collider.rs:266-272,340-349)
+ *   (2) DurHitbox::{collide_time, separate_time}       src/core/dur_hitbox/mod.rs:101-107 (called collider.rs:151-153,188-190,331-332,354)
+ *   (3) EventManager::{peek_time, add_*_event}         src/core/events.rs:115-173 (called collider.rs:86,154,191,333,367,442)
+ * and the per-hitbox driver around them, Collider::internal_update_hitbox / update_hitbox_tracking /
+ * solitaire_event_check (src/core/collider.rs:231-250, 320-381, 420-448), executed for ALL hitboxes in one
+ * device pass by cb200_bulk_update.
+ *
+ * Plain pointers and sizes only.  Every function returns 0 on success, a negative CB200_E_* code on
+ * failure; cb200_last_error() gives the message (the Rust wrapper re-raises it as panic!, preserving the
+ * reference's contract-panic behaviour — see INTEGRATION.md).  A context is single-threaded like the
+ * reference's `&mut self` API: one caller at a time, one CUDA stream per context.
+ *
+ * There is no CPU fallback: every entry point that computes runs CUDA kernels on `device`; if no CUDA
+ * device is usable, cb200_create fails with CB200_E_CUDA.
+ */
+#ifndef COLLIDER_B200_H
+#define COLLIDER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_ABI_VERSION 1
+
+enum {
+    CB200_OK = 0,
+    CB200_E_ARG = -1,      /* bad argument (null pointer, ids not ascending, ...) */
+    CB200_E_CUDA = -2,     /* CUDA runtime failure */
+    CB200_E_CONTRACT = -3, /* a reference contract assertion failed on the device (see error_flags) */
+    CB200_E_STATE = -4     /* call sequence error (e.g. bulk_update before upload_state) */
+};
+
+/* Contract violations detected on the device; names follow the reference's panics. */
+enum {
+    CB200_F_INVALID_TIME = 1u << 0,   /* "invalid time": T outside [start_time, pub_end_time]   collider.rs:489-492 */
+    CB200_F_END_TIME = 1u << 1,       /* "end time must exceed present time"                      core/mod.rs:147-150 */
+    CB200_F_CIRCLE_RESIZE = 1u << 2,  /* "circle resize velocity must maintain aspect ratio"      core/mod.rs:151-156 */
+    CB200_F_TOO_SMALL = 1u << 3,      /* "shape width/height must be at least {padding}"          core/mod.rs:157-161,166 */
+    CB200_F_EMPTY_RECT = 1u << 4,     /* "IndexRect contains no elements"                         index_rect.rs:26-29 */
+    CB200_F_RECT_SPAN = 1u << 5,      /* index rect wider than the device grid period (engine limit, not a reference panic) */
+    CB200_F_NAN = 1u << 6,            /* "unexpected NaN"                                         float.rs:31 */
+    CB200_F_HIGH_TIME = 1u << 7,      /* "requires time < 1e50"                                   core/mod.rs:142 */
+    CB200_F_ID_NOT_FOUND = 1u << 8    /* "hitbox id {} not found"                                 collider.rs:235,260,283,294 */
+};
+
+#define CB200_KIND_CIRCLE 0 /* ShapeKind::Circle, geom/shape/mod.rs:27-31 */
+#define CB200_KIND_RECT 1   /* ShapeKind::Rect */
+#define CB200_GROUP_NONE 0xFFFFFFFFu /* HbProfile::group() == None: never binned, no events (collider.rs:328) */
+
+/* InternalEvent kinds (events.rs:74-82, release build) */
+#define CB200_EV_REITERATE 0
+#define CB200_EV_COLLIDE 1
+#define CB200_EV_SEPARATE 2
+
+typedef struct cb200_ctx cb200_ctx;
+
+/* Host SoA view of the hitbox table: HitboxInfo fields (collider.rs:457-464) column by column.
+ * `id` must be strictly ascending (slot order == HbId order; the canonical tie-break of SURVEY.md §8c
+ * relies on it).  group: HbProfile::group() value in 0..31 or CB200_GROUP_NONE; interact_mask: bit g set
+ * iff g is in HbProfile::interact_groups() (core/mod.rs:218-231). */
+typedef struct cb200_state_view {
+    uint64_t n;
+    const uint64_t* id;
+    const double* pos_x;        /* Hitbox.value.pos          core/mod.rs:119-130 */
+    const double* pos_y;
+    const double* dim_x;        /* Hitbox.value.shape.dims */
+    const double* dim_y;
+    const double* vel_x;        /* Hitbox.vel.value          core/mod.rs:34-59 */
+    const double* vel_y;
+    const double* rsz_x;        /* Hitbox.vel.resize */
+    const double* rsz_y;
+    const double* start_time;   /* HitboxInfo.start_time */
+    const double* end_time;     /* internal Hitbox.vel.end_time (collider.rs:440) */
+    const double* pub_end_time; /* HitboxInfo.pub_end_time */
+    const uint8_t* kind;        /* CB200_KIND_* */
+    const uint32_t* group;
+    const uint32_t* interact_mask;
+} cb200_state_view;
+
+typedef struct cb200_state_out {
+    uint64_t n; /* capacity of every array below, in hitboxes */
+    double *pos_x, *pos_y, *dim_x, *dim_y, *vel_x, *vel_y, *rsz_x, *rsz_y, *start_time, *end_time, *pub_end_time;
+} cb200_state_out;
+
+/* New velocities for a bulk step; any pointer may be NULL (= keep the current component). */
+typedef struct cb200_vel_view {
+    const double* vel_x;
+    const double* vel_y;
+    const double* rsz_x;
+    const double* rsz_y;
+    const double* end_time; /* per-hitbox HbVel.end_time; NULL = use the scalar argument */
+} cb200_vel_view;
+
+/* One queued event as the host's EventManager would hold it (events.rs:28-100): `a` is the hitbox that
+ * was being updated when the event was created (always the higher HbId after a bulk step),
+ * `b` the partner (0 for Reiterate). */
+typedef struct cb200_event {
+    double time;
+    uint64_t a;
+    uint64_t b;
+    uint32_t kind; /* CB200_EV_* */
+    uint32_t _pad;
+} cb200_event;
+
+typedef struct cb200_step_result {
+    double next_time;       /* EventManager::peek_time (events.rs:171-173): min event time or +inf */
+    cb200_event next_event; /* the minimum under the canonical order (time, class, hi, kind, lo); kind/ids 0 if none */
+    uint64_t n_hitboxes;    /* N: hitboxes updated (a-2 … a-7 each) */
+    uint64_t n_entries;     /* E: (hitbox, cell) entries binned */
+    uint64_t n_cells;       /* C: grid slots touched (non-empty) */
+    uint64_t n_collide_solves;  /* unique candidate pairs, one collide_time each (a-10) */
+    uint64_t n_separate_solves; /* overlapping pairs, one separate_time each (a-11) */
+    uint64_t n_events;      /* V: events emitted (time < 1e50), solitaire included */
+    uint64_t n_solitaire;   /* Reiterate events among them */
+    uint32_t error_flags;   /* CB200_F_* */
+    uint32_t _pad;
+    uint64_t error_slot;    /* lowest-numbered reporting slot's id, when error_flags != 0 */
+} cb200_step_result;
+
+/* Collider::new (collider.rs:59-69): requires cell_width > padding > 0 (else CB200_E_ARG with the
+ * reference's message).  `device` is the CUDA ordinal.  *out receives the context. */
+int cb200_create(double cell_width, double padding, int device, cb200_ctx** out);
+void cb200_destroy(cb200_ctx* ctx);
+/* Message of the last failure on `ctx` (or of the last failed cb200_create when ctx == NULL). */
+const char* cb200_last_error(const cb200_ctx* ctx);
+int cb200_abi_version(void);
+
+/* Device grid period (slots = 2^log2_w x 2^log2_h, cells folded modulo the period; aliasing costs time,
+ * never correctness).  0,0 = choose from the uploaded extent (default). */
+int cb200_set_grid(cb200_ctx* ctx, int log2_w, int log2_h);
+int cb200_get_grid(cb200_ctx* ctx, int* log2_w, int* log2_h);
+
+/* Pinned (page-locked) host memory for the arrays handed to upload_state / bulk_update / fetch_events, so that
+ * the H2D / D2H copies inside those calls run at full PCIe speed.  Plain malloc'd memory is accepted too. */
+void* cb200_host_alloc(uint64_t bytes);
+void cb200_host_free(void* p);
+
+/* Replace the device-resident hitbox table (H2D).  Replaces FnvHashMap<HbId, HitboxInfo> (collider.rs:31). */
+int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* view);
+/* Read the table back (D2H) — Collider::get_hitbox's data source (collider.rs:200-202). */
+int cb200_download_state(cb200_ctx* ctx, const cb200_state_out* out);
+
+/* Replace the set of currently-overlapping pairs (HitboxInfo.overlaps, collider.rs:463) as id pairs. */
+int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_b, uint64_t n_pairs);
+
+/* The bulk advance/rebuild entry point.  Reference-equivalent definition: at `time`,
+ *   for id in ascending HbId: Collider::internal_update_hitbox(id, Some(vel_id))   (collider.rs:231-250)
+ * i.e. rebase, clear every queued event, solitaire_event_check, re-bin into the grid, candidate pairs,
+ * collide_time / separate_time per pair, queue the events; then EventManager::peek_time.
+ * `vel` may be NULL (keep velocities); `end_time` is the HbVel.end_time installed when vel->end_time is NULL. */
+int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, cb200_step_result* out);
+
+/* Events queued by the last bulk step, sorted by the canonical order (time, class, hi id, kind, lo id)
+ * (events.rs:60-68 with SURVEY.md §8c tie-break).  Copies events [offset, offset+cap) into buf. */
+int cb200_fetch_events(cb200_ctx* ctx, cb200_event* buf, uint64_t cap, uint64_t offset, uint64_t* n_out);
+
+/* Parity/debug views of the last bulk step.
+ * Candidate pairs: (hi id, lo id) for every collide_time evaluated (unsorted).  Grid::overlapping_ids, grid.rs:115-135. */
+int cb200_fetch_candidate_pairs(cb200_ctx* ctx, uint64_t* id_hi, uint64_t* id_lo, uint64_t cap, uint64_t* n_out);
+/* Cell entries: (cell x, cell y, id) for every (hitbox, cell) binned (unsorted).  Grid.map, grid.rs:48-51. */
+int cb200_fetch_cell_entries(cb200_ctx* ctx, int32_t* cell_x, int32_t* cell_y, uint64_t* id, uint64_t cap, uint64_t* n_out);
+/* Per-hitbox IndexRect (sx, sy, ex, ey) x n.  Grid::index_bounds, grid.rs:101-113. */
+int cb200_fetch_index_rects(cb200_ctx* ctx, int32_t* rects, uint64_t cap_hitboxes);
+
+/* Batched narrowphase on explicit DurHitbox pairs (host arrays, n x 9 doubles each:
+ * px,py,dw,dh,vx,vy,rw,rh,duration; kinds n bytes each).  DurHitbox::collide_time / separate_time,
+ * dur_hitbox/mod.rs:101-107.  NaN is written where the reference would panic. */
+int cb200_collide_time_batch(cb200_ctx* ctx, uint64_t n, const double* a, const uint8_t* kind_a, const double* b, const uint8_t* kind_b,
+                             double* out);
+int cb200_separate_time_batch(cb200_ctx* ctx, uint64_t n, const double* a, const uint8_t* kind_a, const double* b, const uint8_t* kind_b,
+                              double padding, double* out);
+
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+uint64_t cb200_launch_count(const cb200_ctx* ctx);
+/* Device-side duration of cb200_bulk_update and of each of its stages in milliseconds (CUDA events on the
+ * context's stream).  For bench.py's roofline. */
+/* Averages since the last cb200_reset_timing.  Stages: 0 pre (H2D velocities + table zeroing), 1 stage A,
+ * 2 slot scan, 3 scatter, 4 pair stage, 5 tail (separate stage + finalize + result D2H). */
+#define CB200_N_STAGES 6
+int cb200_last_step_timing(cb200_ctx* ctx, float* total_ms, float* stage_ms, int n_stages);
+int cb200_reset_timing(cb200_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLLIDER_B200_H */

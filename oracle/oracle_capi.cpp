@@ -229,6 +229,56 @@ int64_t orc_dump_grid(void* hp, int32_t* x, int32_t* y, uint32_t* group, uint64_
     return (int64_t)v.size();
 }
 
+// ---- bulk helpers for large parity scenes (avoid one ctypes call per hitbox) ----
+// cols: 9 columns of n doubles, column k at cols + k*n: px,py,dw,dh,vx,vy,rw,rh,end_time.  group 0xFFFFFFFF = None.
+int orc_add_hitboxes(void* hp, uint64_t n, const uint64_t* ids, const double* cols, const uint8_t* kind, const uint32_t* group,
+                     const uint32_t* mask) {
+    auto* h = (Handle*)hp;
+    return guard(h, [&] {
+        for (uint64_t i = 0; i < n; ++i) {
+            Hitbox hitbox;
+            hitbox.value = placed(v2(cols[0 * n + i], cols[1 * n + i]), (ShapeKind)kind[i], v2(cols[2 * n + i], cols[3 * n + i]));
+            hitbox.vel = HbVel{v2(cols[4 * n + i], cols[5 * n + i]), v2(cols[6 * n + i], cols[7 * n + i]), cols[8 * n + i]};
+            int64_t g = group[i] == 0xFFFFFFFFu ? -1 : (int64_t)group[i];
+            h->c->add_hitbox(make_profile(ids[i], g, mask[i]), hitbox);
+        }
+    });
+}
+// ids ascending; cols: 11 columns of cap doubles (px,py,dw,dh,vx,vy,rw,rh,start_time,internal end_time,pub_end_time)
+int64_t orc_dump_state(void* hp, uint64_t* ids, double* cols, uint8_t* kind, uint32_t* group, uint32_t* mask, uint64_t cap) {
+    auto* h = (Handle*)hp;
+    std::vector<HbId> all = h->c->ids();
+    for (size_t r = 0; r < all.size() && r < cap; ++r) {
+        const HitboxInfo& i = h->c->info(all[r]);
+        ids[r] = all[r];
+        const double v[11] = {i.hitbox.value.pos.x, i.hitbox.value.pos.y, i.hitbox.value.dims.x, i.hitbox.value.dims.y,
+                              i.hitbox.vel.value.x, i.hitbox.vel.value.y, i.hitbox.vel.resize.x, i.hitbox.vel.resize.y,
+                              i.start_time, i.hitbox.vel.end_time, i.pub_end_time};
+        for (int k = 0; k < 11; ++k) cols[(size_t)k * cap + r] = v[k];
+        kind[r] = (uint8_t)i.hitbox.value.kind;
+        group[r] = i.profile.has_group ? i.profile.group : 0xFFFFFFFFu;
+        uint32_t m = 0;
+        for (HbGroup g : i.profile.interact_groups) m |= 1u << g;
+        mask[r] = m;
+    }
+    return (int64_t)all.size();
+}
+// every overlapping pair once, as (a < b)
+int64_t orc_dump_overlaps(void* hp, uint64_t* a, uint64_t* b, uint64_t cap) {
+    auto* h = (Handle*)hp;
+    int64_t n = 0;
+    for (HbId id : h->c->ids())
+        for (HbId other : h->c->info(id).overlaps.v)
+            if (id < other) {
+                if ((uint64_t)n < cap) {
+                    a[n] = id;
+                    b[n] = other;
+                }
+                ++n;
+            }
+    return n;
+}
+
 // ---- scalar / batched primitives for KATs and narrowphase parity ----
 // a, b: n x 9 doubles (px,py,dw,dh,vx,vy,rw,rh,duration); kinds: n bytes each.  NaN-free inputs assumed;
 // a panic inside one pair writes NaN for that pair.

@@ -86,6 +86,11 @@ def lib():
         L.orc_shape_overlaps.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_swept_rect.argtypes = [C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_set_can_interact.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_add_hitboxes.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 5
+        L.orc_dump_state.restype = C.c_int64
+        L.orc_dump_state.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_uint64]
+        L.orc_dump_overlaps.restype = C.c_int64
+        L.orc_dump_overlaps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
 
@@ -274,6 +279,42 @@ class Collider:
 
     def len(self):
         return int(self._L.orc_len(self._h))
+
+    # ---- bulk helpers for large scenes (one call instead of one per hitbox) ----
+    def add_hitboxes(self, scene: dict, end_time=INF):
+        """add_hitbox for every row of a scene dict (id, pos_x, pos_y, dim_x, dim_y, vel_x, vel_y, kind[, rsz_x, rsz_y, group, interact_mask])."""
+        n = len(scene["id"])
+        z = np.zeros(n)
+        cols = np.ascontiguousarray(np.stack([
+            scene["pos_x"], scene["pos_y"], scene["dim_x"], scene["dim_y"], scene["vel_x"], scene["vel_y"],
+            scene.get("rsz_x", z), scene.get("rsz_y", z), np.broadcast_to(np.asarray(end_time, dtype=np.float64), (n,)),
+        ]), dtype=np.float64)
+        ids = np.ascontiguousarray(scene["id"], dtype=np.uint64)
+        kind = np.ascontiguousarray(scene["kind"], dtype=np.uint8)
+        group = np.ascontiguousarray(scene.get("group", np.zeros(n, np.uint32)), dtype=np.uint32)
+        mask = np.ascontiguousarray(scene.get("interact_mask", np.ones(n, np.uint32)), dtype=np.uint32)
+        self._check(self._L.orc_add_hitboxes(self._h, n, _p(ids), _p(cols), _p(kind), _p(group), _p(mask)))
+
+    def dump_state(self) -> dict:
+        """Raw internal table in ascending id order, as the columns cb200_upload_state takes."""
+        n = self.len()
+        ids = np.zeros(n, dtype=np.uint64)
+        cols = np.zeros((11, n))
+        kind = np.zeros(n, dtype=np.uint8)
+        group = np.zeros(n, dtype=np.uint32)
+        mask = np.zeros(n, dtype=np.uint32)
+        self._L.orc_dump_state(self._h, _p(ids), _p(cols), _p(kind), _p(group), _p(mask), n)
+        names = ("pos_x", "pos_y", "dim_x", "dim_y", "vel_x", "vel_y", "rsz_x", "rsz_y", "start_time", "end_time", "pub_end_time")
+        out = {k: cols[i].copy() for i, k in enumerate(names)}
+        out.update(id=ids, kind=kind, group=group, interact_mask=mask)
+        return out
+
+    def dump_overlaps(self):
+        n = self._L.orc_dump_overlaps(self._h, None, None, 0)
+        a = np.zeros(n, dtype=np.uint64)
+        b = np.zeros(n, dtype=np.uint64)
+        self._L.orc_dump_overlaps(self._h, _p(a), _p(b), n)
+        return a, b
 
     # ---- bulk step + introspection (not in the reference API) ----
     def bulk_update(self, end_time=INF, vx=None, vy=None, rw=None, rh=None, end_time_arr=None, record_candidates=False):

@@ -1,0 +1,237 @@
+"""GPU parity: cb200_bulk_update (CUDA, through the C ABI) against the CPU oracle on the same seeded scenes.
+
+Bar: identical candidate-pair set, identical cell membership, identical (kind, id, id) event
+sequence under the canonical order, event times and rebased state bit-equal (the north_star allows 1e-9
+relative for times; the f64 contract of DESIGN.md makes them bit-equal, and that is what is asserted).
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+cb = importlib.import_module("collider-rs_b200")
+scenes = importlib.import_module("collider-rs_b200.scenes")
+
+CW, PAD = scenes.CELL_WIDTH, scenes.PADDING
+STATE_COLS = ("pos_x", "pos_y", "dim_x", "dim_y", "vel_x", "vel_y", "rsz_x", "rsz_y", "start_time", "end_time", "pub_end_time")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def oracle_events(orc):
+    t, idx, kind, a, b = orc.dump_events()
+    return t, kind, a, b
+
+
+def assert_step_parity(orc, eng, res, check_grid=True):
+    """Compare everything the last bulk step produced on both sides."""
+    # event queue, in order
+    t, kind, a, b = oracle_events(orc)
+    ev = eng.fetch_events()
+    assert len(ev) == len(t) == res.n_events
+    np.testing.assert_array_equal(ev["kind"], kind)
+    np.testing.assert_array_equal(ev["a"], a)
+    np.testing.assert_array_equal(ev["b"], np.where(kind == 0, 0, b))
+    np.testing.assert_array_equal(bits(ev["time"]), bits(t))
+    # min-reduction
+    assert res.next_time == orc.next_time()
+    if len(t):
+        assert (res.next_event.kind, res.next_event.a) == (kind[0], a[0])
+        assert bits([res.next_event.time])[0] == bits(t[:1])[0]
+        if kind[0] != 0:
+            assert res.next_event.b == b[0]
+    # candidate-pair set
+    ohi, olo = orc.bulk_candidates()
+    dhi, dlo = eng.fetch_candidate_pairs()
+    assert res.n_collide_solves == len(ohi) == len(dhi)
+    okey = np.sort(ohi.astype(np.uint64) << np.uint64(32) | olo)
+    dkey = np.sort(dhi << np.uint64(32) | dlo)
+    np.testing.assert_array_equal(dkey, okey)
+    assert len(np.unique(dkey)) == len(dkey), "a pair was produced twice"
+    # rebased table
+    st = eng.download_state()
+    ost = orc.dump_state()
+    for k in STATE_COLS:
+        np.testing.assert_array_equal(bits(st[k]), bits(ost[k]), err_msg=k)
+    if check_grid:
+        gx, gy, gg, gi = orc.dump_grid()
+        dx, dy, di = eng.fetch_cell_entries()
+        assert res.n_entries == len(gx) == len(dx)
+        o = np.lexsort((gy, gx, gi))
+        d = np.lexsort((dy, dx, di))
+        np.testing.assert_array_equal(dx[d], gx[o])
+        np.testing.assert_array_equal(dy[d], gy[o])
+        np.testing.assert_array_equal(di[d], gi[o])
+
+
+def seeded(oracle, scene, end_time=cb.INF):
+    orc = oracle.Collider(CW, PAD)
+    orc.add_hitboxes(scene, end_time=end_time)
+    eng = cb.Engine(CW, PAD)
+    st = orc.dump_state()
+    eng.upload_state(**st)
+    a, b = orc.dump_overlaps()
+    eng.set_overlaps(a, b)
+    return orc, eng
+
+
+def drain_until(orc, t_stop):
+    """The user loop of README.md:66-80 without velocity changes: process every event up to t_stop."""
+    n = 0
+    while True:
+        t = min(orc.next_time(), t_stop)
+        orc.set_time(t)
+        while orc.next() is not None:
+            n += 1
+        if t >= t_stop:
+            return n
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 20000])
+def test_bulk_step_parity_uniform(oracle, n):
+    scene = scenes.uniform_density(n)
+    orc, eng = seeded(oracle, scene)
+    orc.bulk_update(end_time=0.1, record_candidates=True)
+    res = eng.bulk_update(0.0, end_time=0.1)
+    assert res.n_hitboxes == n
+    assert_step_parity(orc, eng, res)
+
+
+def test_bulk_step_parity_full_cell_sweeps(oracle):
+    """end_time = +inf: every moving hitbox sweeps one cell period and queues a Reiterate (a-3)."""
+    scene = scenes.c1()
+    orc, eng = seeded(oracle, scene)
+    orc.bulk_update(end_time=cb.INF, record_candidates=True)
+    res = eng.bulk_update(0.0, end_time=cb.INF)
+    assert res.n_solitaire == 1000
+    assert_step_parity(orc, eng, res)
+
+
+def test_bulk_chain_with_events_between_steps(oracle):
+    """Config 2 shape: bulk step every 0.1, Collide/Separate events processed in between (they change the overlap
+    sets, which the host re-uploads); device state is carried across steps without re-upload."""
+    scene = scenes.uniform_density(5000, seed=scenes.SEED_BASE + 2)
+    orc, eng = seeded(oracle, scene)
+    T = 0.0
+    for step in range(8):
+        orc.bulk_update(end_time=T + 0.1, record_candidates=True)
+        res = eng.bulk_update(T, end_time=T + 0.1)
+        assert_step_parity(orc, eng, res, check_grid=(step % 3 == 0))
+        T = T + 0.1
+        drain_until(orc, T)
+        a, b = orc.dump_overlaps()
+        eng.set_overlaps(a, b)
+
+
+def test_bulk_new_velocities(oracle):
+    """The bulk entry point installs new velocities (reference-equivalent: set_hitbox_vel for every id ascending)."""
+    n = 3000
+    scene = scenes.uniform_density(n, seed=77)
+    orc, eng = seeded(oracle, scene)
+    T = 0.0
+    for step in range(3):
+        vx = scenes.uniform(1000 + step, n, 1, -3.0, 3.0)
+        vy = scenes.uniform(1000 + step, n, 2, -3.0, 3.0)
+        orc.bulk_update(end_time=T + 0.25, vx=vx, vy=vy, record_candidates=True)
+        res = eng.bulk_update(T, end_time=T + 0.25, vel_x=vx, vel_y=vy)
+        assert_step_parity(orc, eng, res)
+        T += 0.25
+        drain_until(orc, T)
+        eng.set_overlaps(*orc.dump_overlaps())
+
+
+def test_resizing_groups_and_negative_coordinates(oracle):
+    """Rows the reference leaves untested: resize velocities, several groups with asymmetric
+    interact_groups, group None, coordinates around the origin (floor toward -inf in index_bounds)."""
+    n = 4000
+    s = scenes.make_scene(n, 300.0, seed=4242, x0=-150.0)
+    s["pos_y"] = s["pos_y"] - 150.0
+    r = scenes.uniform(4242, n, 20, -0.05, 0.3)
+    s["rsz_x"] = r
+    s["rsz_y"] = np.where(s["kind"] == 0, r, scenes.uniform(4242, n, 21, -0.05, 0.3))
+    g = (scenes.splitmix64(4242, n, 22) % np.uint64(4)).astype(np.uint32)
+    s["group"] = np.where(g == 3, np.uint32(cb.GROUP_NONE), g)
+    s["interact_mask"] = np.array([0b011, 0b101, 0b110, 0b111], dtype=np.uint32)[g]
+    orc, eng = seeded(oracle, s)
+    T = 0.0
+    for step in range(3):
+        orc.bulk_update(end_time=T + 0.2, record_candidates=True)
+        res = eng.bulk_update(T, end_time=T + 0.2)
+        assert_step_parity(orc, eng, res)
+        T += 0.2
+        drain_until(orc, T)
+        eng.set_overlaps(*orc.dump_overlaps())
+
+
+def test_clustered_fast_small_shapes(oracle):
+    """Config 5 at a size the oracle finishes quickly: dense cells and multi-cell sweeps."""
+    s = scenes.c5(20000)
+    orc, eng = seeded(oracle, s)
+    orc.bulk_update(end_time=0.1, record_candidates=True)
+    res = eng.bulk_update(0.0, end_time=0.1)
+    assert_step_parity(orc, eng, res)
+
+
+def test_aliased_grid_is_still_exact(oracle):
+    """Force a tiny grid period so that many cells share a slot: results must not change."""
+    scene = scenes.uniform_density(5000)
+    orc, eng = seeded(oracle, scene)
+    eng.set_grid(6, 6)
+    orc.bulk_update(end_time=0.1, record_candidates=True)
+    res = eng.bulk_update(0.0, end_time=0.1)
+    assert_step_parity(orc, eng, res)
+
+
+def test_contract_errors(oracle):
+    eng = cb.Engine(CW, PAD)
+    s = scenes.uniform_density(100)
+    eng.upload_state(**s)
+    with pytest.raises(cb.ColliderError) as e:
+        eng.bulk_update(1.0, end_time=0.5)  # end time must exceed present time (core/mod.rs:147-150)
+    assert e.value.code == cb.E_CONTRACT and "end time must exceed present time" in e.value.msg
+    with pytest.raises(cb.ColliderError):
+        cb.Engine(1.0, 2.0)  # requires cell_width > padding (collider.rs:60)
+    with pytest.raises(cb.ColliderError):
+        eng.upload_state(**{**s, "id": s["id"][::-1].copy()})
+
+
+def test_narrowphase_batch_parity(oracle):
+    """collide_time / separate_time kernels against the oracle on random and lattice (exactly-touching) pairs."""
+    n = 200000
+    rng = np.random.default_rng(12345)
+
+    def hitboxes(lattice):
+        kind = rng.integers(0, 2, n).astype(np.uint8)
+        if lattice:
+            px, py = rng.integers(-6, 7, n).astype(float), rng.integers(-6, 7, n).astype(float)
+            w = rng.integers(1, 5, n).astype(float)
+            h = np.where(kind == 0, w, rng.integers(1, 5, n).astype(float))
+            vx, vy = rng.integers(-4, 5, n) * 0.5, rng.integers(-4, 5, n) * 0.5
+        else:
+            px, py = rng.uniform(-6, 6, n), rng.uniform(-6, 6, n)
+            w = rng.uniform(0.05, 4, n)
+            h = np.where(kind == 0, w, rng.uniform(0.05, 4, n))
+            vx, vy = rng.uniform(-3, 3, n), rng.uniform(-3, 3, n)
+        rw = np.where(rng.integers(0, 4, n) == 0, rng.uniform(-0.2, 0.5, n), 0.0)
+        rh = np.where(kind == 0, rw, np.where(rw != 0, rng.uniform(-0.2, 0.5, n), 0.0))
+        still = rng.integers(0, 7, n) == 0
+        vx, vy, rw, rh = [np.where(still, 0.0, v) for v in (vx, vy, rw, rh)]
+        dur = np.where(rng.integers(0, 4, n) == 0, np.inf, rng.uniform(0.01, 8, n))
+        dur = np.where(~still & (dur == np.inf), 5.0, dur)
+        return np.stack([px, py, w, h, vx, vy, rw, rh, dur], axis=1), kind
+
+    eng = cb.Engine(CW, PAD)
+    for lattice in (False, True):
+        a, ka = hitboxes(lattice)
+        b, kb = hitboxes(lattice)
+        want = oracle.collide_time_batch(a, ka, b, kb)
+        got = eng.collide_time_batch(a, ka, b, kb)
+        np.testing.assert_array_equal(bits(got), bits(want))
+        assert np.isfinite(want).sum() > n // 50
+        want = oracle.separate_time_batch(a, ka, b, kb, PAD)
+        got = eng.separate_time_batch(a, ka, b, kb, PAD)
+        np.testing.assert_array_equal(bits(got), bits(want))
