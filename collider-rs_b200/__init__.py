@@ -22,8 +22,8 @@ KIND_CIRCLE, KIND_RECT = 0, 1
 GROUP_NONE = 0xFFFFFFFF
 EV_REITERATE, EV_COLLIDE, EV_SEPARATE = 0, 1, 2
 E_ARG, E_CUDA, E_CONTRACT, E_STATE = -1, -2, -3, -4
-N_STAGES = 6
-STAGE_NAMES = ("pre", "stage_a", "scan", "scatter", "pairs", "tail")
+N_STAGES = 7
+STAGE_NAMES = ("pre", "stage_a", "scan", "scatter", "candidates", "solve", "tail")
 INF = math.inf
 
 

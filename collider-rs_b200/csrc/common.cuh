@@ -156,7 +156,7 @@ struct Counters {
     unsigned int err_flags;
     unsigned int scan_ticket;
     unsigned int overflow_entries;
-    unsigned int n_captured;           // debug capture cursor
+    unsigned int done_blocks;          // solve stage: blocks finished (last-block finalize)
     unsigned long long diff_hi, diff_lo;  // sort: OR of key differences
     unsigned long long n_sort_keys;
 };
@@ -164,6 +164,36 @@ struct Counters {
 __device__ __forceinline__ void report_error(Counters* ctr, uint32_t flags, uint64_t slot) {
     atomicOr(&ctr->err_flags, flags);
     atomicMin(&ctr->err_slot, (unsigned long long)slot);
+}
+
+// Block-wide exclusive scan of one uint32 per thread (blockDim.x == 256 or any multiple of 32 <= 1024);
+// returns the exclusive prefix, *total receives the block sum in every thread.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t s_scan[33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();  // protects s_scan against the previous call's readers
+    if (lane == 31) s_scan[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        uint32_t ws = lane < nw ? s_scan[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= o) ws += t;
+        }
+        if (lane < nw) s_scan[lane] = ws;  // inclusive over warps
+        if (lane == nw - 1) s_scan[32] = ws;
+    }
+    __syncthreads();
+    *total = s_scan[32];
+    return inc - v + (warp ? s_scan[warp - 1] : 0u);
 }
 
 // Grid fold: cell (x, y) -> slot.

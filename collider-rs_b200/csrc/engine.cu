@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -45,7 +46,7 @@ struct DevBuf {
     }
 };
 
-enum { ST_PRE = 0, ST_STAGE_A, ST_SCAN, ST_SCATTER, ST_PAIRS, ST_TAIL, ST_COUNT };
+enum { ST_PRE = 0, ST_STAGE_A, ST_SCAN, ST_SCATTER, ST_CAND, ST_SOLVE, ST_TAIL, ST_COUNT };
 }  // namespace
 
 struct cb200_ctx {
@@ -68,7 +69,8 @@ struct cb200_ctx {
     bool geom_forced = false;
     DevBuf<uint32_t> slots;
     DevBuf<unsigned long long> tile_state;
-    DevBuf<uint2> entries;
+    DevBuf<CellEntry> entries;
+    DevBuf<uint2> cand;
 
     DevBuf<uint2> ov_pairs;
     DevBuf<unsigned long long> ov_table;
@@ -77,10 +79,10 @@ struct cb200_ctx {
 
     DevBuf<PairEvent> events;
     DevBuf<MinKey> partial;
-    uint32_t grid_a = 0, grid_p = 0, grid_s = 0;
+    uint32_t grid_a = 0, grid_p = 0;
     Counters* d_ctr = nullptr;
-    StepResultDev* d_res = nullptr;
-    StepResultDev* h_res = nullptr;  // pinned
+    StepResultDev* d_res = nullptr;  // device alias of h_res (mapped)
+    StepResultDev* h_res = nullptr;  // pinned, mapped
 
     // last step
     bool have_step = false;
@@ -92,7 +94,6 @@ struct cb200_ctx {
     DevBuf<EventOut> ev_out;
     bool ev_sorted = false;
     uint64_t n_ev_sorted = 0;
-    DevBuf<uint2> capture;
 
     uint64_t launches = 0;
     cudaEvent_t ev_t[ST_COUNT + 1] = {};
@@ -143,6 +144,32 @@ std::string flags_message(uint32_t f) {
     if (f & kFHighTime) add("requires time < 1e50");
     if (f & kFIdNotFound) add("hitbox id not found");
     return m;
+}
+
+// Experiment kept for A/B runs (CB200_L2_PERSIST=1): mark the HbRec table persisting in L2.  Measured on B200
+// (1M hitboxes, config 3): the 79 MB persisting carve-out starves the streaming kernels (stage A 60 -> 98 us,
+// scatter 52 -> 156 us) and does not speed up the solve-stage gathers, so it is OFF by default.
+void set_l2_window(cb200_ctx* c) {
+    const char* env = getenv("CB200_L2_PERSIST");
+    if (!(env && env[0] == '1')) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) return;
+    if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
+    const size_t rec_bytes = (size_t)c->n * sizeof(HbRec);
+    if (rec_bytes == 0) return;
+    const size_t carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, rec_bytes);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = c->rec.p;
+    attr.accessPolicyWindow.num_bytes = std::min<size_t>(rec_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)attr.accessPolicyWindow.num_bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+    if (getenv("CB200_VERBOSE"))
+        fprintf(stderr, "[cb200] L2 persist: max %d B, window max %d B, carve %zu B, rec %zu B, hitRatio %.2f\n", prop.persistingL2CacheMaxSize,
+                prop.accessPolicyMaxWindowSize, carve, rec_bytes, attr.accessPolicyWindow.hitRatio);
 }
 
 int ilog2_ceil(uint64_t v) {
@@ -205,8 +232,8 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
     if ((e = cudaMalloc(&c->d_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMalloc", e);
-    if ((e = cudaMalloc(&c->d_res, sizeof(StepResultDev))) != cudaSuccess) return bail("cudaMalloc", e);
-    if ((e = cudaMallocHost(&c->h_res, sizeof(StepResultDev))) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaHostAlloc(&c->h_res, sizeof(StepResultDev), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostGetDevicePointer((void**)&c->d_res, c->h_res, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     for (auto& ev : c->ev_t)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     *out = c;
@@ -224,9 +251,8 @@ void cb200_destroy(cb200_ctx* c) {
     c->slots.release(); c->tile_state.release(); c->entries.release();
     c->ov_pairs.release(); c->ov_table.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
-    c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); c->ev_out.release(); c->capture.release();
+    c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); c->ev_out.release(); c->cand.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
-    if (c->d_res) cudaFree(c->d_res);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->pinned_stage) cudaFreeHost(c->pinned_stage);
     for (auto& ev : c->ev_t)
@@ -295,6 +321,7 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
     choose_geom(ctx, v);
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->n = (uint32_t)n;
+    set_l2_window(ctx);
     ctx->have_state = true;
     ctx->have_step = false;
     ctx->ev_sorted = false;
@@ -419,12 +446,12 @@ static int run_step(cb200_ctx* ctx, double time, bool rebase, const double* cons
     CU(ctx->slots.reserve(n_slots));
     CU(ctx->tile_state.reserve(n_tiles));
     if (ctx->entries.cap == 0) CU(ctx->entries.reserve((size_t)n * 4 + 1024));
+    if (ctx->cand.cap == 0) CU(ctx->cand.reserve((size_t)n * 2 + 1024));
     if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
     const uint32_t per_sm = 8;
     ctx->grid_a = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, ctx->sm_count * per_sm));
     ctx->grid_p = ctx->sm_count * per_sm;
-    ctx->grid_s = std::max<uint32_t>(1, std::min<uint32_t>((ctx->n_ov + kThreads - 1) / kThreads, ctx->sm_count * per_sm));
-    const uint32_t n_partial = ctx->grid_a + ctx->grid_p + ctx->grid_s;
+    const uint32_t n_partial = ctx->grid_a + ctx->grid_p;
     CU(ctx->partial.reserve(n_partial));
 
     for (int attempt = 0; attempt < 4; ++attempt) {
@@ -457,30 +484,34 @@ static int run_step(cb200_ctx* ctx, double time, bool rebase, const double* cons
         k_scan_slots<<<n_tiles, kThreads, 0, ctx->stream>>>(ctx->slots.p, n_slots, ctx->tile_state.p, ctx->d_ctr);
         CU(cudaEventRecord(ctx->ev_t[ST_SCATTER], ctx->stream));
         if (n) k_scatter<<<ctx->grid_a, kThreads, 0, ctx->stream>>>(n, ctx->rec.p, ctx->slots.p, ctx->entries.p, (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu), g, ctx->d_ctr);
-        CU(cudaEventRecord(ctx->ev_t[ST_PAIRS], ctx->stream));
-        PairArgs p;
-        p.entries = ctx->entries.p;
-        p.offsets = ctx->slots.p;
-        p.rec = ctx->rec.p;
-        p.geom = g;
-        p.T = time;
-        p.ov = OverlapSet{ctx->ov_table.p, ctx->n_ov ? ctx->ov_cap_mask : 0u};
-        p.events = ctx->events.p;
-        p.cap_events = (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu);
-        p.ctr = ctx->d_ctr;
-        p.partial = ctx->partial.p + ctx->grid_a;
-        p.capture = nullptr;
-        p.cap_capture = 0;
-        k_pairs<false><<<ctx->grid_p, kThreads, 0, ctx->stream>>>(p);
+        CU(cudaEventRecord(ctx->ev_t[ST_CAND], ctx->stream));
+        CandArgs cd;
+        cd.entries = ctx->entries.p;
+        cd.geom = g;
+        cd.ov = OverlapSet{ctx->ov_table.p, ctx->n_ov ? ctx->ov_cap_mask : 0u};
+        cd.cand = ctx->cand.p;
+        cd.cap_cand = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
+        cd.ctr = ctx->d_ctr;
+        k_candidates<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(cd);
+        CU(cudaEventRecord(ctx->ev_t[ST_SOLVE], ctx->stream));
+        SolveArgs sv;
+        sv.cand = ctx->cand.p;
+        sv.cap_cand = cd.cap_cand;
+        sv.ov_pairs = ctx->ov_pairs.p;
+        sv.n_ov = ctx->n_ov;
+        sv.rec = ctx->rec.p;
+        sv.T = time;
+        sv.padding = ctx->padding;
+        sv.events = ctx->events.p;
+        sv.cap_events = (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu);
+        sv.ctr = ctx->d_ctr;
+        sv.partial = ctx->partial.p;
+        sv.n_partial_a = ctx->grid_a;
+        sv.result = ctx->d_res;
+        k_solve<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(sv);
         CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
-        if (ctx->n_ov)
-            k_separate<<<ctx->grid_s, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, ctx->n_ov, ctx->rec.p, time, ctx->padding, ctx->events.p,
-                                                                  p.cap_events, ctx->d_ctr, ctx->partial.p + ctx->grid_a + ctx->grid_p);
-        else CU(cudaMemsetAsync(ctx->partial.p + ctx->grid_a + ctx->grid_p, 0xff, sizeof(MinKey) * ctx->grid_s, ctx->stream));
-        k_finalize<<<1, kThreads, 0, ctx->stream>>>(ctx->partial.p, n_partial, ctx->d_ctr, ctx->d_res);
-        CU(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(StepResultDev), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
-        ctx->launches += (n ? 2 : 0) + 3 + (ctx->n_ov ? 1 : 0);
+        ctx->launches += (n ? 2 : 0) + 3;
         CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaGetLastError());
         ctx->last = *ctx->h_res;
@@ -491,6 +522,10 @@ static int run_step(cb200_ctx* ctx, double time, bool rebase, const double* cons
         bool again = false;
         if (c.overflow_entries || c.n_entries > ctx->entries.cap) {
             CU(ctx->entries.reserve((size_t)c.n_entries + c.n_entries / 4 + 1024));
+            again = true;
+        }
+        if (c.n_collide > ctx->cand.cap) {
+            CU(ctx->cand.reserve((size_t)c.n_collide + c.n_collide / 4 + 1024));
             again = true;
         }
         if (c.n_pair_events > ctx->events.cap) {
@@ -577,30 +612,11 @@ int cb200_fetch_candidate_pairs(cb200_ctx* ctx, uint64_t* id_hi, uint64_t* id_lo
     const uint64_t total = ctx->last.ctr.n_collide;
     if (n_out) *n_out = total;
     if (cap == 0 || total == 0) return CB200_OK;
-    if (total >= 0xffffffffull) return fail(ctx, CB200_E_STATE, "too many pairs to capture");
-    CU(ctx->capture.reserve(total));
-    CU(cudaMemsetAsync(&ctx->d_ctr->n_captured, 0, 4, ctx->stream));
-    PairArgs p;
-    p.entries = ctx->entries.p;
-    p.offsets = ctx->slots.p;
-    p.rec = ctx->rec.p;
-    p.geom = ctx->geom;
-    p.T = ctx->last_T;
-    p.ov = OverlapSet{ctx->ov_table.p, ctx->n_ov ? ctx->ov_cap_mask : 0u};
-    p.events = nullptr;
-    p.cap_events = 0;
-    p.ctr = ctx->d_ctr;
-    p.partial = ctx->partial.p + ctx->grid_a;
-    p.capture = ctx->capture.p;
-    p.cap_capture = (uint32_t)total;
-    k_pairs<true><<<ctx->grid_p, kThreads, 0, ctx->stream>>>(p);
-    ctx->launches += 1;
     std::vector<uint2> h(total);
     std::vector<uint64_t> ids(ctx->n);
-    CU(cudaMemcpyAsync(h.data(), ctx->capture.p, total * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h.data(), ctx->cand.p, total * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(ids.data(), ctx->ids.p, (size_t)ctx->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaGetLastError());
     for (uint64_t i = 0; i < total && i < cap; ++i) {
         if (id_hi) id_hi[i] = ids[h[i].x];
         if (id_lo) id_lo[i] = ids[h[i].y];
@@ -615,21 +631,19 @@ int cb200_fetch_cell_entries(cb200_ctx* ctx, int32_t* cell_x, int32_t* cell_y, u
     const uint64_t total = ctx->last.ctr.n_entries;
     if (n_out) *n_out = total;
     if (cap == 0 || total == 0) return CB200_OK;
-    std::vector<uint2> h(total);
-    std::vector<HbRec> recs(ctx->n);
+    std::vector<CellEntry> h(total);
     std::vector<uint64_t> ids(ctx->n);
-    CU(cudaMemcpy(h.data(), ctx->entries.p, total * sizeof(uint2), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(recs.data(), ctx->rec.p, (size_t)ctx->n * sizeof(HbRec), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h.data(), ctx->entries.p, total * sizeof(CellEntry), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(ids.data(), ctx->ids.p, (size_t)ctx->n * 8, cudaMemcpyDeviceToHost));
     const uint32_t mw = (1u << ctx->geom.lw) - 1u, mh = (1u << ctx->geom.lh) - 1u;
     for (uint64_t i = 0; i < total && i < cap; ++i) {
-        const HbRec& r = recs[h[i].x];
-        const uint32_t sxs = h[i].y & mw, sys = h[i].y >> ctx->geom.lw;
+        const CellEntry& r = h[i];
+        const uint32_t sxs = r.slot & mw, sys = r.slot >> ctx->geom.lw;
         // the unique cell of the rect that folds onto this slot
         const int32_t x = r.sx + (int32_t)((sxs - (uint32_t)r.sx) & mw), y = r.sy + (int32_t)((sys - (uint32_t)r.sy) & mh);
         if (cell_x) cell_x[i] = x;
         if (cell_y) cell_y[i] = y;
-        if (id) id[i] = ids[h[i].x];
+        if (id) id[i] = ids[r.idx];
     }
     return CB200_OK;
 }

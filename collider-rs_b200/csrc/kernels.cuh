@@ -50,7 +50,7 @@ __device__ __forceinline__ int32_t f64_as_i32(double v) { return __double2int_rz
 //   IndexRect     Grid::index_bounds (grid.rs:101-113)
 //   cell count    first half of the counting sort that replaces Grid::update_area (grid.rs:137-175)
 // Reads the SoA columns coalesced, writes the rebased columns back and the 96-B HbRec for the pair stage.
-__global__ void __launch_bounds__(kThreads) k_stage_a(const StepArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a) {
     MinKey best{kKeyMax, kKeyMax};
     unsigned long long n_sol = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -233,26 +233,37 @@ __global__ void __launch_bounds__(kThreads) k_scan_slots(uint32_t* __restrict__ 
     const uint32_t block_total = s_warp[kThreads / 32 - 1];
     const uint32_t thread_excl = inc - sum + (warp ? s_warp[warp - 1] : 0);
 
-    if (threadIdx.x == 0) {
+    // decoupled look-back by warp 0: 32 predecessor tiles per round
+    if (warp == 0) {
         uint32_t prefix = 0;
         if (tile == 0) {
-            atomicExch(&tile_state[0], (2ull << 62) | block_total);
+            if (lane == 0) atomicExch(&tile_state[0], (2ull << 62) | block_total);
         } else {
-            atomicExch(&tile_state[tile], (1ull << 62) | block_total);
-            int64_t j = (int64_t)tile - 1;
+            if (lane == 0) atomicExch(&tile_state[tile], (1ull << 62) | block_total);
+            int64_t j = (int64_t)tile - 1 - lane;  // lane 0 looks at the nearest predecessor
             for (;;) {
-                unsigned long long st;
-                do {
-                    st = *reinterpret_cast<volatile unsigned long long*>(&tile_state[j]);
-                } while ((st >> 62) == 0);
-                prefix += (uint32_t)st;
-                if ((st >> 62) == 2) break;
-                --j;
+                unsigned long long st = 2ull << 62;  // tiles before tile 0: inclusive prefix 0
+                if (j >= 0) {
+                    do {
+                        st = *reinterpret_cast<volatile unsigned long long*>(&tile_state[j]);
+                    } while ((st >> 62) == 0);
+                }
+                const unsigned incl = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                // lanes up to and including the nearest inclusive tile contribute
+                const int stop = incl ? __ffs(incl) - 1 : 31;
+                uint32_t v = lane <= stop ? (uint32_t)st : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                prefix += v;
+                if (incl) break;
+                j -= 32;
             }
-            atomicExch(&tile_state[tile], (2ull << 62) | (uint32_t)(prefix + block_total));
+            if (lane == 0) atomicExch(&tile_state[tile], (2ull << 62) | (uint32_t)(prefix + block_total));
         }
-        s_prefix = prefix;
-        if ((size_t)(tile + 1) * kScanTile >= n) ctr->n_entries = (unsigned long long)prefix + block_total;
+        if (lane == 0) {
+            s_prefix = prefix;
+            if ((size_t)(tile + 1) * kScanTile >= n) ctr->n_entries = (unsigned long long)prefix + block_total;
+        }
     }
     const unsigned long long nz = block_sum(nonzero);  // contains the __syncthreads that publishes s_prefix
     if (threadIdx.x == 0 && nz) atomicAdd(&ctr->n_cells, nz);
@@ -269,20 +280,36 @@ __global__ void __launch_bounds__(kThreads) k_scan_slots(uint32_t* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Scatter: second half of the counting sort.  offsets[s] enters as the start of slot s and leaves as its end
-// (so afterwards start(s) = s ? offsets[s-1] : 0).  entries[pos] = (hitbox slot index, grid slot).
-__global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const HbRec* __restrict__ rec, uint32_t* offsets, uint2* entries,
+// Scatter: second half of the counting sort.  offsets[s] enters as the start of slot s and is used as the
+// slot's cursor.  A cell entry carries everything the candidate stage tests (IndexRect, profile bits), so
+// that stage streams the entry array and never gathers hitbox records: 32 B = one sector per entry.
+struct alignas(32) CellEntry {
+    int32_t sx, sy, ex, ey;  // IndexRect of the hitbox
+    uint32_t idx;            // hitbox slot index (== HbId rank)
+    uint32_t slot;           // grid slot of this entry
+    uint32_t mask;           // interact_groups bit mask
+    uint32_t group;          // group 0..31
+};
+static_assert(sizeof(CellEntry) == 32, "CellEntry must be one sector");
+
+__global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const HbRec* __restrict__ rec, uint32_t* offsets, CellEntry* entries,
                                                       uint32_t cap_entries, GridGeom geom, Counters* ctr) {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const RecHead h = load_head(rec, i);
         if (!(h.kgb & 2u)) continue;
+        const int4 lo4 = make_int4(h.sx, h.sy, h.ex, h.ey);
         for (int32_t x = h.sx; x != h.ex; ++x)
             for (int32_t y = h.sy; y != h.ey; ++y) {
                 const uint32_t s = geom.slot(x, y);
                 const uint32_t pos = atomicAdd(&offsets[s], 1u);
-                if (pos < cap_entries) entries[pos] = make_uint2(i, s);
-                else ctr->overflow_entries = 1u;
+                if (pos < cap_entries) {
+                    int4* out = reinterpret_cast<int4*>(entries + pos);
+                    out[0] = lo4;
+                    out[1] = make_int4((int)i, (int)s, (int)h.mask, (int)((h.kgb >> 8) & 0xffu));
+                } else {
+                    ctr->overflow_entries = 1u;
+                }
             }
     }
 }
@@ -346,139 +373,196 @@ __global__ void k_overlap_map_ids(const uint64_t* __restrict__ ids, uint32_t n, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Pair stage: one thread per cell entry, paired with the entries that precede it in the same slot.
+// Candidate stage: one thread per cell entry, walking back over the entries that precede it in the same slot
+// (the entry array is sorted by slot, so a slot's entries are contiguous and the walk stays in cache).
 //   candidates   Grid::overlapping_ids (grid.rs:115-135) restricted to the surviving (hi, lo) pairs; the
-//                hash-set de-duplication is replaced by pair ownership: a pair is handled only in the slot of
+//                hash-set de-duplication is replaced by pair ownership: a pair is taken only in the slot of
 //                cell (max(sx_i, sx_j), max(sy_i, sy_j)) — the min corner of the rect intersection — so every
 //                pair sharing >= 1 cell is produced exactly once, and aliased slot-mates are rejected.
 //   filters      lo.group in hi.interact_groups (grid.rs:122, key group); not already overlapping (collider.rs:351)
-//   solve        hi.collide_time(lo rebased to T) (collider.rs:354 -> solvers.rs:25-34)
-//   queue        add_pair_event(T + delay, Collide(hi, lo)), dropped when >= 1e50 (collider.rs:367-372, events.rs:156-159)
-//   min          EventManager::peek_time under the canonical order (events.rs:171-173)
-struct PairArgs {
-    const uint2* entries;
-    const uint32_t* offsets;  // end of each slot
-    const HbRec* rec;
+// Output: the compact candidate list (hi, lo), appended with warp-aggregated atomics.
+struct CandArgs {
+    const CellEntry* entries;
     GridGeom geom;
-    double T;
     OverlapSet ov;
-    PairEvent* events;
-    uint32_t cap_events;
+    uint2* cand;
+    uint32_t cap_cand;
     Counters* ctr;
-    MinKey* partial;   // [gridDim.x]
-    uint2* capture;    // CAPTURE mode: candidate pairs (hi, lo)
-    uint32_t cap_capture;
 };
 
-template <bool CAPTURE>
-__global__ void __launch_bounds__(kThreads) k_pairs(const PairArgs a) {
-    MinKey best{kKeyMax, kKeyMax};
-    unsigned long long n_solved = 0;
+// One (entry, predecessor) test of the candidate stage; on success *hi/*lo receive the pair.
+__device__ __forceinline__ bool candidate_test(const CandArgs& a, const int4& r, const int4& m, const int4& rf, const int4& mf, uint32_t* hi,
+                                               uint32_t* lo) {
+    // ownership: min corner of the rect intersection must be this slot's cell
+    const int32_t ox = max(r.x, rf.x), oy = max(r.y, rf.y);
+    if (ox >= min(r.z, rf.z) || oy >= min(r.w, rf.w)) return false;
+    if (a.geom.slot(ox, oy) != (uint32_t)m.y) return false;
+    const uint32_t i = (uint32_t)m.x, j = (uint32_t)mf.x;
+    const bool i_is_hi = i > j;
+    *hi = i_is_hi ? i : j;
+    *lo = i_is_hi ? j : i;
+    const uint32_t mask_hi = (uint32_t)(i_is_hi ? m.z : mf.z), group_lo = (uint32_t)(i_is_hi ? mf.w : m.w);
+    if (!((mask_hi >> group_lo) & 1u)) return false;
+    if (a.ov.cap_mask && overlap_contains(a.ov, *hi, *lo)) return false;
+    return true;
+}
+
+// Block-aggregated output: pass 1 tests every predecessor and remembers the accepted ones (bit k of `acc` =
+// predecessor e-1-k, for the first 64); one block scan + ONE global atomic per block-iteration reserves the
+// output range; pass 2 writes the pairs.  (A per-warp claim on the single global counter serialises in L2.)
+__global__ void __launch_bounds__(kThreads) k_candidates(const CandArgs a) {
+    __shared__ unsigned long long s_base;
     const uint32_t n_entries = (uint32_t)a.ctr->n_entries;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += stride) {
-        const uint2 en = a.entries[e];
-        const uint32_t i = en.x, slot = en.y;
-        const uint32_t first = slot ? __ldg(a.offsets + slot - 1) : 0u;
-        if (e == first) continue;
-        const RecHead hi_ = load_head(a.rec, i);
-        DurHb body_i;
-        bool have_i = false;
-        for (uint32_t f = first; f < e; ++f) {
-            const uint32_t j = a.entries[f].x;
-            const RecHead hj = load_head(a.rec, j);
-            // ownership: min corner of the rect intersection must be this slot's cell
-            const int32_t ox = max(hi_.sx, hj.sx), oy = max(hi_.sy, hj.sy);
-            if (ox >= min(hi_.ex, hj.ex) || oy >= min(hi_.ey, hj.ey)) continue;
-            if (a.geom.slot(ox, oy) != slot) continue;
-            const bool i_is_hi = i > j;
-            const uint32_t hi = i_is_hi ? i : j, lo = i_is_hi ? j : i;
-            const uint32_t mask_hi = i_is_hi ? hi_.mask : hj.mask;
-            const uint32_t group_lo = ((i_is_hi ? hj.kgb : hi_.kgb) >> 8) & 0xffu;
-            if (!((mask_hi >> group_lo) & 1u)) continue;
-            if (a.ov.cap_mask && overlap_contains(a.ov, hi, lo)) continue;
-            ++n_solved;
-            if (CAPTURE) {
-                const uint32_t pos = warp_agg_claim32(&a.ctr->n_captured);
-                if (pos < a.cap_capture) a.capture[pos] = make_uint2(hi, lo);
-                continue;
-            }
-            if (!have_i) {
-                body_i = load_body(a.rec, i, hi_);
-                have_i = true;
-            }
-            const DurHb body_j = load_body(a.rec, j, hj);
-            // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486): advanced by T - start = 0
-            const DurHb A = i_is_hi ? body_i : body_j;
-            const DurHb B = advanced(i_is_hi ? body_j : body_i, 0.0);
-            const double delay = collide_time(A, B);
-            if (delay != delay) report_error(a.ctr, kFNan, hi);
-            const double t = a.T + delay;
-            if (t < kHighTime) {
-                const unsigned long long pos = warp_agg_claim(&a.ctr->n_pair_events);
-                if (pos < a.cap_events) a.events[pos] = PairEvent{t, hi, lo | kCollideBit};
-                const MinKey k{time_key(t), kPairClass | ((uint64_t)hi << 32) | kCollideBit | lo};
-                if (key_less(k, best)) best = k;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_entries; base += stride) {
+        const uint32_t e = base + threadIdx.x;
+        int4 r = make_int4(0, 0, 0, 0), m = r;
+        unsigned long long acc = 0;
+        uint32_t cnt = 0, run = 0;
+        if (e < n_entries) {
+            const int4* pe = reinterpret_cast<const int4*>(a.entries + e);
+            r = __ldg(pe);
+            m = __ldg(pe + 1);
+            for (uint32_t f = e; f-- > 0; ++run) {
+                const int4* pf = reinterpret_cast<const int4*>(a.entries + f);
+                const int4 mf = __ldg(pf + 1);
+                if (mf.y != m.y) break;
+                const int4 rf = __ldg(pf);
+                uint32_t hi, lo;
+                if (candidate_test(a, r, m, rf, mf, &hi, &lo)) {
+                    ++cnt;
+                    if (run < 64) acc |= 1ull << run;
+                }
             }
         }
-    }
-    best = block_min(best);
-    const unsigned long long tot = block_sum(n_solved);
-    if (threadIdx.x == 0) {
-        a.partial[blockIdx.x] = best;
-        if (tot) atomicAdd(&a.ctr->n_collide, tot);
+        uint32_t total;
+        const uint32_t off = block_excl_scan(cnt, &total);
+        if (total == 0) continue;  // uniform across the block
+        if (threadIdx.x == 0) s_base = atomicAdd(&a.ctr->n_collide, (unsigned long long)total);
+        __syncthreads();
+        unsigned long long pos = s_base + off;
+        const uint32_t i = (uint32_t)m.x;
+        while (acc) {
+            const int k = __ffsll((long long)acc) - 1;
+            acc &= acc - 1;
+            const uint32_t j = (uint32_t)__ldg(reinterpret_cast<const int*>(a.entries + (e - 1 - k)) + 4);
+            if (pos < a.cap_cand) a.cand[pos] = make_uint2(max(i, j), min(i, j));
+            ++pos;
+        }
+        if (run > 64) {  // long slot runs (dense / clustered cells): redo the tests beyond the 64-bit window
+            for (uint32_t k = 64; k < run; ++k) {
+                const int4* pf = reinterpret_cast<const int4*>(a.entries + (e - 1 - k));
+                const int4 rf = __ldg(pf), mf = __ldg(pf + 1);
+                uint32_t hi, lo;
+                if (candidate_test(a, r, m, rf, mf, &hi, &lo)) {
+                    if (pos < a.cap_cand) a.cand[pos] = make_uint2(hi, lo);
+                    ++pos;
+                }
+            }
+        }
+        __syncthreads();  // s_base is rewritten by the next iteration
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Separate stage: one thread per currently-overlapping pair (collider.rs:329-339):
-//   hi.separate_time(lo rebased to T, padding) -> add_pair_event(T + delay, Separate(hi, lo)).
-__global__ void __launch_bounds__(kThreads) k_separate(const uint2* __restrict__ pairs, uint32_t n_pairs, const HbRec* __restrict__ rec,
-                                                       double T, double padding, PairEvent* events, uint32_t cap_events, Counters* ctr,
-                                                       MinKey* partial) {
-    MinKey best{kKeyMax, kKeyMax};
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += stride) {
-        const uint2 pr = pairs[p];
-        const RecHead hh = load_head(rec, pr.x), hl = load_head(rec, pr.y);
-        const DurHb A = load_body(rec, pr.x, hh);
-        const DurHb B = advanced(load_body(rec, pr.y, hl), 0.0);
-        const double delay = separate_time(A, B, padding);
-        if (delay != delay) report_error(ctr, kFNan, pr.x);
-        const double t = T + delay;
-        if (t < kHighTime) {
-            const unsigned long long pos = warp_agg_claim(&ctr->n_pair_events);
-            if (pos < cap_events) events[pos] = PairEvent{t, pr.x, pr.y};
-            const MinKey k{time_key(t), kPairClass | ((uint64_t)pr.x << 32) | pr.y};
-            if (key_less(k, best)) best = k;
-        }
-    }
-    best = block_min(best);
-    if (threadIdx.x == 0) {
-        partial[blockIdx.x] = best;
-        if (blockIdx.x == 0) atomicAdd(&ctr->n_separate, (unsigned long long)n_pairs);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Finalize: reduce the per-block minima of the three stages into the step result (device copy).
+// Solve stage: one thread per pair.  Pairs [0, n_collide) are the candidates, pairs [n_collide, n_collide + n_ov)
+// the currently-overlapping pairs (HitboxInfo.overlaps).
+//   collide      hi.collide_time(lo rebased to T) (collider.rs:354 -> solvers.rs:25-34)
+//                -> add_pair_event(T + delay, Collide(hi, lo)), dropped when >= 1e50 (collider.rs:367-372, events.rs:156-159)
+//   separate     hi.separate_time(lo rebased to T, padding) (collider.rs:329-339 -> solvers.rs:36-44)
+//                -> add_pair_event(T + delay, Separate(hi, lo))
+//   min          EventManager::peek_time under the canonical order (events.rs:171-173): warp shuffle + block reduce
+// The step result, written by the last block of the solve stage straight into mapped pinned host memory.
 struct StepResultDev {
     double next_time;
     uint64_t next_tie;  // MinKey.tie of the minimum (kKeyMax if none)
     Counters ctr;
 };
-__global__ void __launch_bounds__(kThreads) k_finalize(const MinKey* __restrict__ partial, uint32_t n_partial, const Counters* ctr,
-                                                       StepResultDev* out) {
+
+struct SolveArgs {
+    const uint2* cand;
+    uint32_t cap_cand;
+    const uint2* ov_pairs;
+    uint32_t n_ov;
+    const HbRec* rec;
+    double T, padding;
+    PairEvent* events;
+    uint32_t cap_events;
+    Counters* ctr;
+    MinKey* partial;         // [n_partial_a + gridDim.x]: stage A's minima, then this kernel's
+    uint32_t n_partial_a;
+    StepResultDev* result;   // mapped host memory
+};
+
+__global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
+    __shared__ uint32_t s_last;
+    __shared__ unsigned long long s_base;
     MinKey best{kKeyMax, kKeyMax};
+    const uint32_t n_cand = (uint32_t)min((unsigned long long)a.cap_cand, a.ctr->n_collide);
+    const uint32_t total = n_cand + a.n_ov;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
+        const uint32_t p = base + threadIdx.x;
+        PairEvent ev{0.0, 0u, 0u};
+        uint32_t have = 0;
+        if (p < total) {
+            const bool sep = p >= n_cand;
+            const uint2 pr = sep ? a.ov_pairs[p - n_cand] : a.cand[p];
+            const RecHead hh = load_head(a.rec, pr.x), hl = load_head(a.rec, pr.y);
+            const DurHb A = load_body(a.rec, pr.x, hh);
+            // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486): advanced by T - start = 0
+            const DurHb B = advanced(load_body(a.rec, pr.y, hl), 0.0);
+            const double delay = sep ? separate_time(A, B, a.padding) : collide_time(A, B);
+            if (delay != delay) report_error(a.ctr, kFNan, pr.x);
+            const double t = a.T + delay;
+            if (t < kHighTime) {
+                const uint32_t kind_bit = sep ? 0u : kCollideBit;
+                ev = PairEvent{t, pr.x, pr.y | kind_bit};
+                have = 1;
+                const MinKey k{time_key(t), kPairClass | ((uint64_t)pr.x << 32) | kind_bit | pr.y};
+                if (key_less(k, best)) best = k;
+            }
+        }
+        // block-aggregated append: one global atomic per block-iteration
+        uint32_t n_ev;
+        const uint32_t off = block_excl_scan(have, &n_ev);
+        if (n_ev == 0) continue;  // uniform
+        if (threadIdx.x == 0) s_base = atomicAdd(&a.ctr->n_pair_events, (unsigned long long)n_ev);
+        __syncthreads();
+        const unsigned long long pos = s_base + off;
+        if (have && pos < a.cap_events) a.events[pos] = ev;
+        __syncthreads();
+    }
+    best = block_min(best);
+    if (threadIdx.x == 0) {
+        a.partial[a.n_partial_a + blockIdx.x] = best;
+        if (blockIdx.x == 0 && a.n_ov) atomicAdd(&a.ctr->n_separate, (unsigned long long)a.n_ov);
+        __threadfence();
+        s_last = atomicAdd(&a.ctr->done_blocks, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // last block: reduce every per-block minimum of stage A and of this stage, publish the step result
+    __threadfence();
+    best = MinKey{kKeyMax, kKeyMax};
+    const uint32_t n_partial = a.n_partial_a + gridDim.x;
     for (uint32_t i = threadIdx.x; i < n_partial; i += blockDim.x) {
-        const MinKey k = partial[i];
+        const volatile unsigned long long* q = reinterpret_cast<const volatile unsigned long long*>(&a.partial[i]);
+        const MinKey k{q[0], q[1]};
         if (key_less(k, best)) best = k;
     }
     best = block_min(best);
     if (threadIdx.x == 0) {
-        out->next_time = best.t == kKeyMax && best.tie == kKeyMax ? cb_inf() : key_time(best.t);
-        out->next_tie = best.tie;
-        out->ctr = *ctr;
+        a.result->next_time = (best.t == kKeyMax && best.tie == kKeyMax) ? cb_inf() : key_time(best.t);
+        a.result->next_tie = best.tie;
+        const volatile Counters* c = a.ctr;
+        Counters out;
+        out.n_entries = c->n_entries; out.n_cells = c->n_cells; out.n_collide = c->n_collide; out.n_separate = c->n_separate;
+        out.n_pair_events = c->n_pair_events; out.n_solitaire = c->n_solitaire; out.err_slot = c->err_slot;
+        out.err_flags = c->err_flags; out.scan_ticket = c->scan_ticket; out.overflow_entries = c->overflow_entries;
+        out.done_blocks = c->done_blocks; out.diff_hi = 0; out.diff_lo = 0; out.n_sort_keys = 0;
+        a.result->ctr = out;
+        __threadfence_system();
     }
 }
 

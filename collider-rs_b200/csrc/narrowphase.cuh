@@ -150,6 +150,16 @@ CB_HD double box_disc_separate(const DurHb& box, const DurHb& disc) {
     return fmax(base - corner_stage_time(bx, dc), 0.0);
 }
 
+// Field-wise select (keeps both operands in registers; a reference select would force them to local memory).
+CB_HD DurHb pick(bool first, const DurHb& x, const DurHb& y) {
+    DurHb r;
+    r.px = first ? x.px : y.px; r.py = first ? x.py : y.py; r.w = first ? x.w : y.w; r.h = first ? x.h : y.h;
+    r.vx = first ? x.vx : y.vx; r.vy = first ? x.vy : y.vy; r.rw = first ? x.rw : y.rw; r.rh = first ? x.rh : y.rh;
+    r.dur = first ? x.dur : y.dur;
+    r.kind = first ? x.kind : y.kind;
+    return r;
+}
+
 // solvers::time_unpadded (solvers.rs:46-58)
 CB_HD double sweep_unpadded(const DurHb& a, const DurHb& b, bool for_collide, double duration) {
     double result;
@@ -158,8 +168,9 @@ CB_HD double sweep_unpadded(const DurHb& a, const DurHb& b, bool for_collide, do
     } else if (a.kind == kCircle && b.kind == kCircle) {
         result = disc_sweep_time(a.px, a.py, a.w, a.vx, a.vy, a.rw, b.px, b.py, b.w, b.vx, b.vy, b.rw, for_collide);
     } else {
-        const DurHb& box = (a.kind == kRect) ? a : b;
-        const DurHb& disc = (a.kind == kRect) ? b : a;
+        const bool a_is_box = a.kind == kRect;
+        const DurHb box = pick(a_is_box, a, b);
+        const DurHb disc = pick(a_is_box, b, a);
         result = for_collide ? box_disc_collide(box, disc, duration) : box_disc_separate(box, disc);
     }
     return (result >= duration) ? cb_inf() : result;
@@ -214,8 +225,8 @@ CB_HD double collide_time(const DurHb& a, const DurHb& b) {
 // first shape is inflated by 2*padding — the result is not symmetric in (a, b) bit-for-bit.
 CB_HD double separate_time(const DurHb& a_in, const DurHb& b_in, double padding) {
     const bool swap = (a_in.kind == kRect && b_in.kind == kCircle);
-    DurHb a = swap ? b_in : a_in;
-    const DurHb& b = swap ? a_in : b_in;
+    DurHb a = pick(swap, b_in, a_in);
+    const DurHb b = pick(swap, a_in, b_in);
     a.w = a.w + padding * 2.0;
     a.h = a.h + padding * 2.0;
     if (!(a.w >= 0.0 && a.h >= 0.0)) return cb_nan();  // Shape::new, geom/shape/mod.rs:44-47

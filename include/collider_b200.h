@@ -181,8 +181,8 @@ uint64_t cb200_launch_count(const cb200_ctx* ctx);
 /* Device-side duration of cb200_bulk_update and of each of its stages in milliseconds (CUDA events on the
  * context's stream).  For bench.py's roofline. */
 /* Averages since the last cb200_reset_timing.  Stages: 0 pre (H2D velocities + table zeroing), 1 stage A,
- * 2 slot scan, 3 scatter, 4 pair stage, 5 tail (separate stage + finalize + result D2H). */
-#define CB200_N_STAGES 6
+ * 2 slot scan, 3 scatter, 4 candidate stage, 5 solve stage, 6 tail (finalize + result D2H). */
+#define CB200_N_STAGES 7
 int cb200_last_step_timing(cb200_ctx* ctx, float* total_ms, float* stage_ms, int n_stages);
 int cb200_reset_timing(cb200_ctx* ctx);
 
