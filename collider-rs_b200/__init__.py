@@ -83,7 +83,7 @@ EXPORTS = (
     "cb200_host_alloc", "cb200_host_free", "cb200_upload_state", "cb200_download_state", "cb200_set_overlaps",
     "cb200_bulk_update", "cb200_fetch_events", "cb200_fetch_candidate_pairs", "cb200_fetch_cell_entries",
     "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
-    "cb200_last_step_timing", "cb200_reset_timing",
+    "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_shard_begin", "cb200_shard_finish",
 )
 
 _lib = None
@@ -124,6 +124,9 @@ def load_library() -> C.CDLL:
     L.cb200_launch_count.restype = u64
     L.cb200_last_step_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), i32]
     L.cb200_reset_timing.argtypes = [vp]
+    L.cb200_shard_configure.argtypes = [vp, i32, i32, vp]
+    L.cb200_shard_begin.argtypes = [vp, dbl, C.POINTER(VelView), dbl, vp, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
+    L.cb200_shard_finish.argtypes = [vp, u64, C.POINTER(StepResult)]
     _lib = L
     return L
 
@@ -244,6 +247,35 @@ class Engine:
             keep = [None if a is None else _col(a, np.float64, self.n) for a in arrs]
             v = VelView(*[None if a is None else a.ctypes.data for a in keep])
             rc = self._L.cb200_bulk_update(self._h, time, C.byref(v), end_time, C.byref(res))
+        self.last_result = res
+        self._check(rc)
+        return res
+
+    # ---- sharded step (one context per GPU; the exchange between begin and finish is the caller's, see sharding.py) ----
+    def shard_configure(self, rank: int, world: int, col_bounds):
+        b = np.ascontiguousarray(col_bounds, dtype=np.int32)
+        if b.shape != (world + 1,):
+            raise ValueError("col_bounds must have world + 1 entries")
+        self._check(self._L.cb200_shard_configure(self._h, rank, world, _ptr(b)))
+        self.rank, self.world = rank, world
+
+    def shard_begin(self, time: float, end_time: float = INF, vel_x=None, vel_y=None, rsz_x=None, rsz_y=None, end_time_arr=None) -> dict:
+        arrs = [vel_x, vel_y, rsz_x, rsz_y, end_time_arr]
+        counts = np.zeros(self.world, dtype=np.uint64)
+        n_local, stride, cap = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        send, recv = C.c_void_p(), C.c_void_p()
+        v = None
+        if not all(a is None for a in arrs):
+            keep = [None if a is None else _col(a, np.float64, self.n) for a in arrs]
+            v = C.byref(VelView(*[None if a is None else a.ctypes.data for a in keep]))
+        self._check(self._L.cb200_shard_begin(self._h, time, v, end_time, _ptr(counts), C.byref(n_local), C.byref(send), C.byref(stride),
+                                              C.byref(recv), C.byref(cap)))
+        return dict(send_counts=counts, n_local=n_local.value, send_ptr=send.value, send_stride=stride.value, recv_ptr=recv.value,
+                    recv_cap=cap.value)
+
+    def shard_finish(self, n_recv: int) -> StepResult:
+        res = StepResult()
+        rc = self._L.cb200_shard_finish(self._h, n_recv, C.byref(res))
         self.last_result = res
         self._check(rc)
         return res

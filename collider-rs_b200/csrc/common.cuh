@@ -23,19 +23,23 @@ constexpr uint64_t kPairClass = 0x8000000000000000ull;
 
 // The DurHitbox a hitbox presents to the pair stage at the step time (core/dur_hitbox/mod.rs:27-70)
 // plus its IndexRect (index_rect.rs:17-31) and profile bits: 96 B = three 32-B sectors.  Sector 0 is
-// all the ownership / group test needs; sectors 1-2 are fetched only for pairs that are solved.
+// all the binning needs; sectors 1-2 are fetched only for pairs that are solved.  A record is
+// self-contained (it carries the hitbox's global id rank), so it is also the unit of the multi-GPU halo.
 struct alignas(32) HbRec {
-    int32_t sx, sy, ex, ey;  // IndexRect, half-open
-    double dur;              // internal end_time - T
-    uint32_t kgb;            // bit0 kind (0 circle, 1 rect), bit1 binned (has a group and a valid rect), bits 8..15 group
-    uint32_t mask;           // interact_groups as a bit mask
+    int32_t sx, sy;  // IndexRect start
+    uint32_t span;   // (ex - sx) | (ey - sy) << 16     (spans are limited to 65535 cells)
+    uint32_t gid;    // rank of the HbId in ascending-id order (one device: the table slot; sharded: the id itself)
+    double dur;      // internal end_time - T
+    uint32_t kgb;    // bit0 kind (0 circle, 1 rect), bit1 binned (has a group and a valid rect), bits 8..15 group
+    uint32_t mask;   // interact_groups as a bit mask
     double px, py, w, h;
     double vx, vy, rw, rh;
 };
 static_assert(sizeof(HbRec) == 96, "HbRec must be three sectors");
 
-struct RecHead {  // sector 0 of HbRec
+struct RecHead {  // sector 0 of HbRec, decoded
     int32_t sx, sy, ex, ey;
+    uint32_t gid;
     double dur;
     uint32_t kgb, mask;
 };
@@ -44,7 +48,10 @@ __device__ __forceinline__ RecHead load_head(const HbRec* __restrict__ rec, uint
     const int4* p = reinterpret_cast<const int4*>(rec + i);
     const int4 a = __ldg(p), b = __ldg(p + 1);
     RecHead h;
-    h.sx = a.x; h.sy = a.y; h.ex = a.z; h.ey = a.w;
+    h.sx = a.x; h.sy = a.y;
+    h.ex = a.x + (int32_t)((uint32_t)a.z & 0xffffu);
+    h.ey = a.y + (int32_t)((uint32_t)a.z >> 16);
+    h.gid = (uint32_t)a.w;
     h.dur = __hiloint2double(b.y, b.x);
     h.kgb = (uint32_t)b.z;
     h.mask = (uint32_t)b.w;
@@ -157,6 +164,8 @@ struct Counters {
     unsigned int scan_ticket;
     unsigned int overflow_entries;
     unsigned int done_blocks;          // solve stage: blocks finished (last-block finalize)
+    unsigned int n_local;              // sharded: records this rank keeps for its own strip
+    unsigned int overflow_send;        // sharded: a send buffer overflowed
     unsigned long long diff_hi, diff_lo;  // sort: OR of key differences
     unsigned long long n_sort_keys;
 };

@@ -63,7 +63,19 @@ struct cb200_ctx {
     DevBuf<uint8_t> kind, reit;
     DevBuf<uint32_t> group, mask;
     DevBuf<uint64_t> ids;
-    DevBuf<HbRec> rec;
+    DevBuf<HbRec> rec;       // one device: rec[slot]; sharded: the visitor table (own records, then received ones)
+    DevBuf<uint32_t> gid;    // sharded: id rank per slot (== the id)
+    // sharding
+    bool sharded = false;
+    ShardGeom shard{};
+    DevBuf<HbRec> send;      // [world][cap_send]
+    DevBuf<uint32_t> send_count;
+    uint32_t cap_send = 0;
+    DevBuf<unsigned long long> gid_map;
+    uint32_t gid_map_mask = 0;
+    uint32_t n_local = 0;    // own records in the visitor table (last shard_begin)
+    bool shard_open = false; // between shard_begin and shard_finish
+    double shard_T = 0;
 
     GridGeom geom{0, 0};
     bool geom_forced = false;
@@ -248,6 +260,7 @@ void cb200_destroy(cb200_ctx* c) {
     for (auto& b : c->col) b.release();
     for (auto& b : c->nvel) b.release();
     c->kind.release(); c->reit.release(); c->group.release(); c->mask.release(); c->ids.release(); c->rec.release();
+    c->gid.release(); c->send.release(); c->send_count.release(); c->gid_map.release();
     c->slots.release(); c->tile_state.release(); c->entries.release();
     c->ov_pairs.release(); c->ov_table.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
@@ -318,6 +331,21 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
         CU(cudaMemcpyAsync(ctx->ids.p, v->id, n * 8, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemsetAsync(ctx->reit.p, 0, n, ctx->stream));
     }
+    if (ctx->sharded) {
+        // sharded tables: gid = id (ids must be dense enough to fit 31 bits); visitor table and halo buffers sized here
+        std::vector<uint32_t> g(n);
+        for (size_t i = 0; i < n; ++i) {
+            if (v->id[i] >= 0x7fffffffull) return fail(ctx, CB200_E_ARG, "sharded mode requires ids < 2^31 - 1");
+            g[i] = (uint32_t)v->id[i];
+        }
+        CU(ctx->gid.reserve(cap));
+        if (n) CU(cudaMemcpyAsync(ctx->gid.p, g.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(ctx->rec.reserve(2 * n + 65536));
+        ctx->cap_send = (uint32_t)std::max<size_t>(n / 8, 65536);
+        CU(ctx->send.reserve((size_t)ctx->cap_send * ctx->shard.world));
+        CU(ctx->send_count.reserve(ctx->shard.world));
+    }
     choose_geom(ctx, v);
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->n = (uint32_t)n;
@@ -363,7 +391,7 @@ int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_
     const unsigned long long big = ~0ull;
     CU(cudaMemcpyAsync(&ctx->d_ctr->err_slot, &big, 8, cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t blocks = (np + kThreads - 1) / kThreads;
-    k_overlap_map_ids<<<blocks, kThreads, 0, ctx->stream>>>(ctx->ids.p, ctx->n, ctx->ov_ida.p, ctx->ov_idb.p, np, ctx->ov_pairs.p, ctx->d_ctr);
+    k_overlap_map_ids<<<blocks, kThreads, 0, ctx->stream>>>(ctx->sharded ? nullptr : ctx->ids.p, ctx->n, ctx->ov_ida.p, ctx->ov_idb.p, np, ctx->ov_pairs.p, ctx->d_ctr);
     k_overlap_insert<<<blocks, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, np, ctx->ov_table.p, cap - 1);
     ctx->launches += 2;
     Counters h;
@@ -376,16 +404,9 @@ int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_
     return CB200_OK;
 }
 
-static int run_step(cb200_ctx* ctx, double time, bool rebase, const double* const* nv, double end_time);
-
-int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, cb200_step_result* out) {
-    if (!ctx) return CB200_E_ARG;
-    if (!ctx->have_state) return fail(ctx, CB200_E_STATE, "bulk_update before upload_state");
-    if (!(time < 1e50)) return fail(ctx, CB200_E_ARG, "requires time < 1e50");  // collider.rs:100
-    CU(cudaSetDevice(ctx->device));
+static int stage_vel(cb200_ctx* ctx, const cb200_vel_view* vel, const double** nv) {
     const uint32_t n = ctx->n;
-    CU(cudaEventRecord(ctx->ev_t[ST_PRE], ctx->stream));
-    const double* nv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 5; ++k) nv[k] = nullptr;
     if (vel && n) {
         const double* src[5] = {vel->vel_x, vel->vel_y, vel->rsz_x, vel->rsz_y, vel->end_time};
         for (int k = 0; k < 5; ++k)
@@ -395,25 +416,201 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
                 nv[k] = ctx->nvel[k].p;
             }
     }
-    int rc = run_step(ctx, time, true, nv, end_time);
-    if (rc != CB200_OK) return rc;
+    return CB200_OK;
+}
+
+static ShardGeom whole_world() {
+    ShardGeom g{};
+    g.world = 1;
+    g.rank = 0;
+    g.col_lo = INT32_MIN;
+    g.col_hi = INT32_MAX;
+    g.bounds[0] = INT32_MIN;
+    g.bounds[1] = INT32_MAX;
+    return g;
+}
+
+static int prepare_buffers(cb200_ctx* ctx) {
+    const uint32_t n = ctx->n;
+    const uint32_t n_slots = ctx->geom.n_slots();
+    CU(ctx->slots.reserve(n_slots));
+    CU(ctx->tile_state.reserve(n_slots / kScanTile));
+    if (ctx->entries.cap == 0) CU(ctx->entries.reserve((size_t)n * 4 + 1024));
+    if (ctx->cand.cap == 0) CU(ctx->cand.reserve((size_t)n * 2 + 1024));
+    if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
+    const uint32_t per_sm = 8;
+    ctx->grid_a = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, ctx->sm_count * per_sm));
+    ctx->grid_p = ctx->sm_count * per_sm;
+    CU(ctx->partial.reserve(ctx->grid_a + ctx->grid_p));
+    return CB200_OK;
+}
+
+// Front half: zero the step tables, stage A.  One device: also counts cells.  Sharded: packs records per rank.
+static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const double* const* nv, double end_time) {
+    const uint32_t n = ctx->n;
+    const GridGeom g = ctx->geom;
+    const uint32_t n_slots = g.n_slots();
+    CU(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_slots * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)(n_slots / kScanTile) * 8, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->stream));
+    CU(cudaMemsetAsync(&ctx->d_ctr->err_slot, 0xff, 8, ctx->stream));
+    if (ctx->sharded) CU(cudaMemsetAsync(ctx->send_count.p, 0, sizeof(uint32_t) * ctx->shard.world, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_t[ST_STAGE_A], ctx->stream));
+    StepArgs a{};
+    a.n = n;
+    a.rebase = do_rebase ? 1 : 0;
+    a.T = time;
+    a.cell_width = ctx->cell_width;
+    a.padding = ctx->padding;
+    a.end_scalar = end_time;
+    a.s = cols_of(ctx);
+    a.nvx = do_rebase ? nv[0] : nullptr; a.nvy = do_rebase ? nv[1] : nullptr;
+    a.nrw = do_rebase ? nv[2] : nullptr; a.nrh = do_rebase ? nv[3] : nullptr;
+    a.nend = do_rebase ? nv[4] : ctx->col[10].p;  // re-run: the user end_time is the stored pub_end_time
+    a.gid = ctx->sharded ? ctx->gid.p : nullptr;
+    a.rec = ctx->rec.p;
+    a.slot_count = ctx->slots.p;
+    a.geom = g;
+    a.ctr = ctx->d_ctr;
+    a.partial = ctx->partial.p;
+    a.send = ctx->send.p;
+    a.send_count = ctx->send_count.p;
+    a.cap_send = ctx->cap_send;
+    a.cap_vis = (uint32_t)std::min<size_t>(ctx->rec.cap, 0xffffffffu);
+    if (n) {
+        if (ctx->sharded) k_stage_a<true><<<ctx->grid_a, kThreads, 0, ctx->stream>>>(a, ctx->shard);
+        else k_stage_a<false><<<ctx->grid_a, kThreads, 0, ctx->stream>>>(a, whole_world());
+        ctx->launches += 1;
+    } else {
+        CU(cudaMemsetAsync(ctx->partial.p, 0xff, sizeof(MinKey) * ctx->grid_a, ctx->stream));
+    }
+    CU(cudaEventRecord(ctx->ev_t[ST_SCAN], ctx->stream));
+    return CB200_OK;
+}
+
+// Back half over the visitor table: (count,) scan, scatter, candidates, solve + min-reduce + result.
+static int enqueue_back(cb200_ctx* ctx, uint32_t n_vis, double time) {
+    const GridGeom g = ctx->geom;
+    const uint32_t n_slots = g.n_slots();
+    const ShardGeom sh = ctx->sharded ? ctx->shard : whole_world();
+    const uint32_t grid_v = std::max<uint32_t>(1, std::min<uint32_t>((n_vis + kThreads - 1) / kThreads, ctx->sm_count * 8));
+    const bool use_map = ctx->sharded && ctx->n_ov;
+    if (ctx->sharded) {
+        if (use_map) {
+            uint32_t cap = 1024;
+            while (cap < 2 * std::max<uint32_t>(n_vis, 1)) cap <<= 1;
+            CU(ctx->gid_map.reserve(cap));
+            ctx->gid_map_mask = cap - 1;
+            CU(cudaMemsetAsync(ctx->gid_map.p, 0xff, (size_t)cap * 8, ctx->stream));
+        }
+        if (n_vis) {
+            k_count_visitors<<<grid_v, kThreads, 0, ctx->stream>>>(n_vis, ctx->rec.p, ctx->slots.p, g, sh, ctx->gid_map.p, use_map ? ctx->gid_map_mask : 0u);
+            ctx->launches += 1;
+        }
+    }
+    k_scan_slots<<<n_slots / kScanTile, kThreads, 0, ctx->stream>>>(ctx->slots.p, n_slots, ctx->tile_state.p, ctx->d_ctr);
+    CU(cudaEventRecord(ctx->ev_t[ST_SCATTER], ctx->stream));
+    if (n_vis) {
+        k_scatter<<<grid_v, kThreads, 0, ctx->stream>>>(n_vis, ctx->rec.p, ctx->slots.p, ctx->entries.p, (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu), g,
+                                                        sh.col_lo, sh.col_hi, ctx->d_ctr);
+        ctx->launches += 1;
+    }
+    CU(cudaEventRecord(ctx->ev_t[ST_CAND], ctx->stream));
+    CandArgs cd{};
+    cd.entries = ctx->entries.p;
+    cd.geom = g;
+    cd.col_lo = sh.col_lo;
+    cd.col_hi = sh.col_hi;
+    cd.ov = OverlapSet{ctx->ov_table.p, ctx->n_ov ? ctx->ov_cap_mask : 0u};
+    cd.cand = ctx->cand.p;
+    cd.cap_cand = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
+    cd.ctr = ctx->d_ctr;
+    k_candidates<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(cd);
+    CU(cudaEventRecord(ctx->ev_t[ST_SOLVE], ctx->stream));
+    SolveArgs sv{};
+    sv.cand = ctx->cand.p;
+    sv.cap_cand = cd.cap_cand;
+    sv.ov_pairs = ctx->ov_pairs.p;
+    sv.n_ov = ctx->n_ov;
+    sv.rec = ctx->rec.p;
+    sv.T = time;
+    sv.padding = ctx->padding;
+    sv.events = ctx->events.p;
+    sv.cap_events = (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu);
+    sv.ctr = ctx->d_ctr;
+    sv.partial = ctx->partial.p;
+    sv.n_partial_a = ctx->grid_a;
+    sv.result = ctx->d_res;
+    sv.gid_map = ctx->gid_map.p;
+    sv.gid_map_mask = use_map ? ctx->gid_map_mask : 0u;
+    sv.col_lo = sh.col_lo;
+    sv.col_hi = sh.col_hi;
+    k_solve<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(sv);
+    CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
+    CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
+    ctx->launches += 3;
+    return CB200_OK;
+}
+
+// Wait for the step, grow any buffer that overflowed.  *again = the step must be re-run.
+static int complete_step(cb200_ctx* ctx, double time, bool* again) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    ctx->last = *ctx->h_res;
+    ctx->last_T = time;
+    ctx->have_step = true;
+    ctx->ev_sorted = false;
+    const Counters& c = ctx->last.ctr;
+    *again = false;
+    if (c.overflow_entries || c.n_entries > ctx->entries.cap) {
+        CU(ctx->entries.reserve((size_t)c.n_entries + c.n_entries / 4 + 1024));
+        *again = true;
+    }
+    if (c.n_collide > ctx->cand.cap) {
+        CU(ctx->cand.reserve((size_t)c.n_collide + c.n_collide / 4 + 1024));
+        *again = true;
+    }
+    if (c.n_pair_events > ctx->events.cap) {
+        CU(ctx->events.reserve((size_t)c.n_pair_events + c.n_pair_events / 4 + 1024));
+        *again = true;
+    }
+    return CB200_OK;
+}
+
+static void accumulate_timing(cb200_ctx* ctx, int first_stage, bool with_total) {
+    float ms = 0;
+    for (int s = first_stage; s < ST_COUNT; ++s)
+        if (cudaEventElapsedTime(&ms, ctx->ev_t[s], ctx->ev_t[s + 1]) == cudaSuccess) {
+            ctx->stage_ms_sum[s] += ms;
+            if (!with_total) ctx->total_ms_sum += ms;
+        }
+    if (with_total && cudaEventElapsedTime(&ms, ctx->ev_t[ST_PRE], ctx->ev_t[ST_COUNT]) == cudaSuccess) ctx->total_ms_sum += ms;
+}
+
+static int fill_result(cb200_ctx* ctx, cb200_step_result* out) {
     const StepResultDev& r = ctx->last;
+    const uint32_t n = ctx->n;
     if (out) {
         memset(out, 0, sizeof(*out));
         out->next_time = r.next_time;
         out->next_event.time = r.next_time;
         if (r.next_tie != kKeyMax) {
-            // the two ids need one tiny D2H each; cheap and only when the caller asked for the result struct
+            const uint32_t hi = (uint32_t)((r.next_tie >> 32) & 0x7fffffffu), lo = (uint32_t)(r.next_tie & 0x7fffffffu);
             if (r.next_tie & kPairClass) {
-                const uint32_t hi = (uint32_t)((r.next_tie >> 32) & 0x7fffffffu), lo = (uint32_t)(r.next_tie & 0x7fffffffu);
-                CU(cudaMemcpyAsync(&out->next_event.a, ctx->ids.p + hi, 8, cudaMemcpyDeviceToHost, ctx->stream));
-                CU(cudaMemcpyAsync(&out->next_event.b, ctx->ids.p + lo, 8, cudaMemcpyDeviceToHost, ctx->stream));
                 out->next_event.kind = (r.next_tie & kCollideBit) ? CB200_EV_COLLIDE : CB200_EV_SEPARATE;
+                if (ctx->sharded) {
+                    out->next_event.a = hi;
+                    out->next_event.b = lo;
+                } else {
+                    CU(cudaMemcpyAsync(&out->next_event.a, ctx->ids.p + hi, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(cudaMemcpyAsync(&out->next_event.b, ctx->ids.p + lo, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                }
             } else {
-                CU(cudaMemcpyAsync(&out->next_event.a, ctx->ids.p + (uint32_t)r.next_tie, 8, cudaMemcpyDeviceToHost, ctx->stream));
                 out->next_event.kind = CB200_EV_REITERATE;
+                if (ctx->sharded) out->next_event.a = (uint32_t)r.next_tie;
+                else CU(cudaMemcpyAsync(&out->next_event.a, ctx->ids.p + (uint32_t)r.next_tie, 8, cudaMemcpyDeviceToHost, ctx->stream));
             }
-            CU(cudaStreamSynchronize(ctx->stream));
+            if (!ctx->sharded) CU(cudaStreamSynchronize(ctx->stream));
         }
         out->n_hitboxes = n;
         out->n_entries = r.ctr.n_entries;
@@ -427,124 +624,130 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
     }
     if (r.ctr.err_flags) {
         uint64_t bad_id = 0;
-        if (r.ctr.err_slot < n) {
-            CU(cudaMemcpy(&bad_id, ctx->ids.p + r.ctr.err_slot, 8, cudaMemcpyDeviceToHost));
-        }
+        if (r.ctr.err_slot < n && !ctx->sharded) CU(cudaMemcpy(&bad_id, ctx->ids.p + r.ctr.err_slot, 8, cudaMemcpyDeviceToHost));
+        else bad_id = r.ctr.err_slot;
         if (out) out->error_slot = bad_id;
         return fail(ctx, CB200_E_CONTRACT, flags_message(r.ctr.err_flags) + " (hitbox id " + std::to_string(bad_id) + ")");
     }
     return CB200_OK;
 }
 
-// One pass of the pipeline.  rebase=false re-runs binning + pairs on the already-rebased table (used after a
-// buffer grew); stage A is idempotent at the same T except for the (unchanged) velocity install.
-static int run_step(cb200_ctx* ctx, double time, bool rebase, const double* const* nv, double end_time) {
-    const uint32_t n = ctx->n;
-    const GridGeom g = ctx->geom;
-    const uint32_t n_slots = g.n_slots();
-    const uint32_t n_tiles = n_slots / kScanTile;
-    CU(ctx->slots.reserve(n_slots));
-    CU(ctx->tile_state.reserve(n_tiles));
-    if (ctx->entries.cap == 0) CU(ctx->entries.reserve((size_t)n * 4 + 1024));
-    if (ctx->cand.cap == 0) CU(ctx->cand.reserve((size_t)n * 2 + 1024));
-    if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
-    const uint32_t per_sm = 8;
-    ctx->grid_a = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, ctx->sm_count * per_sm));
-    ctx->grid_p = ctx->sm_count * per_sm;
-    const uint32_t n_partial = ctx->grid_a + ctx->grid_p;
-    CU(ctx->partial.reserve(n_partial));
-
-    for (int attempt = 0; attempt < 4; ++attempt) {
-        const bool do_rebase = rebase && attempt == 0;
-        CU(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_slots * 4, ctx->stream));
-        CU(cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)n_tiles * 8, ctx->stream));
-        CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->stream));
-        CU(cudaMemsetAsync(&ctx->d_ctr->err_slot, 0xff, 8, ctx->stream));
-        CU(cudaEventRecord(ctx->ev_t[ST_STAGE_A], ctx->stream));
-
-        StepArgs a;
-        a.n = n;
-        a.rebase = do_rebase ? 1 : 0;
-        a.T = time;
-        a.cell_width = ctx->cell_width;
-        a.padding = ctx->padding;
-        a.end_scalar = end_time;
-        a.s = cols_of(ctx);
-        a.nvx = do_rebase ? nv[0] : nullptr; a.nvy = do_rebase ? nv[1] : nullptr;
-        a.nrw = do_rebase ? nv[2] : nullptr; a.nrh = do_rebase ? nv[3] : nullptr;
-        a.nend = do_rebase ? nv[4] : ctx->col[10].p;  // re-run: the user end_time is the stored pub_end_time
-        a.rec = ctx->rec.p;
-        a.slot_count = ctx->slots.p;
-        a.geom = g;
-        a.ctr = ctx->d_ctr;
-        a.partial = ctx->partial.p;
-        if (n) k_stage_a<<<ctx->grid_a, kThreads, 0, ctx->stream>>>(a);
-        else CU(cudaMemsetAsync(ctx->partial.p, 0xff, sizeof(MinKey) * ctx->grid_a, ctx->stream));
-        CU(cudaEventRecord(ctx->ev_t[ST_SCAN], ctx->stream));
-        k_scan_slots<<<n_tiles, kThreads, 0, ctx->stream>>>(ctx->slots.p, n_slots, ctx->tile_state.p, ctx->d_ctr);
-        CU(cudaEventRecord(ctx->ev_t[ST_SCATTER], ctx->stream));
-        if (n) k_scatter<<<ctx->grid_a, kThreads, 0, ctx->stream>>>(n, ctx->rec.p, ctx->slots.p, ctx->entries.p, (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu), g, ctx->d_ctr);
-        CU(cudaEventRecord(ctx->ev_t[ST_CAND], ctx->stream));
-        CandArgs cd;
-        cd.entries = ctx->entries.p;
-        cd.geom = g;
-        cd.ov = OverlapSet{ctx->ov_table.p, ctx->n_ov ? ctx->ov_cap_mask : 0u};
-        cd.cand = ctx->cand.p;
-        cd.cap_cand = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
-        cd.ctr = ctx->d_ctr;
-        k_candidates<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(cd);
-        CU(cudaEventRecord(ctx->ev_t[ST_SOLVE], ctx->stream));
-        SolveArgs sv;
-        sv.cand = ctx->cand.p;
-        sv.cap_cand = cd.cap_cand;
-        sv.ov_pairs = ctx->ov_pairs.p;
-        sv.n_ov = ctx->n_ov;
-        sv.rec = ctx->rec.p;
-        sv.T = time;
-        sv.padding = ctx->padding;
-        sv.events = ctx->events.p;
-        sv.cap_events = (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu);
-        sv.ctr = ctx->d_ctr;
-        sv.partial = ctx->partial.p;
-        sv.n_partial_a = ctx->grid_a;
-        sv.result = ctx->d_res;
-        k_solve<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(sv);
-        CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
-        CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
-        ctx->launches += (n ? 2 : 0) + 3;
-        CU(cudaStreamSynchronize(ctx->stream));
-        CU(cudaGetLastError());
-        ctx->last = *ctx->h_res;
-        ctx->last_T = time;
-        ctx->have_step = true;
-        ctx->ev_sorted = false;
-        const Counters& c = ctx->last.ctr;
-        bool again = false;
-        if (c.overflow_entries || c.n_entries > ctx->entries.cap) {
-            CU(ctx->entries.reserve((size_t)c.n_entries + c.n_entries / 4 + 1024));
-            again = true;
-        }
-        if (c.n_collide > ctx->cand.cap) {
-            CU(ctx->cand.reserve((size_t)c.n_collide + c.n_collide / 4 + 1024));
-            again = true;
-        }
-        if (c.n_pair_events > ctx->events.cap) {
-            CU(ctx->events.reserve((size_t)c.n_pair_events + c.n_pair_events / 4 + 1024));
-            again = true;
-        }
-        if (!again) {
-            float ms = 0;
-            for (int s = 0; s < ST_COUNT; ++s) {
-                if (cudaEventElapsedTime(&ms, ctx->ev_t[s], ctx->ev_t[s + 1]) == cudaSuccess) ctx->stage_ms_sum[s] += ms;
-            }
-            if (cudaEventElapsedTime(&ms, ctx->ev_t[ST_PRE], ctx->ev_t[ST_COUNT]) == cudaSuccess) ctx->total_ms_sum += ms;
-            ctx->timed_steps += 1;
-            ctx->timing_valid = true;
-            return CB200_OK;
-        }
-        if (c.err_flags) return CB200_OK;  // reported by the caller
+int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, cb200_step_result* out) {
+    if (!ctx) return CB200_E_ARG;
+    if (!ctx->have_state) return fail(ctx, CB200_E_STATE, "bulk_update before upload_state");
+    if (ctx->sharded) return fail(ctx, CB200_E_STATE, "context is sharded: use cb200_shard_begin / cb200_shard_finish");
+    if (!(time < 1e50)) return fail(ctx, CB200_E_ARG, "requires time < 1e50");  // collider.rs:100
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev_t[ST_PRE], ctx->stream));
+    const double* nv[5];
+    int rc = stage_vel(ctx, vel, nv);
+    if (rc != CB200_OK) return rc;
+    if ((rc = prepare_buffers(ctx)) != CB200_OK) return rc;
+    // A step is re-run (without the rebase) when a buffer had to grow.
+    bool again = true;
+    for (int attempt = 0; attempt < 4 && again; ++attempt) {
+        if ((rc = enqueue_front(ctx, time, attempt == 0, nv, end_time)) != CB200_OK) return rc;
+        if ((rc = enqueue_back(ctx, ctx->n, time)) != CB200_OK) return rc;
+        if ((rc = complete_step(ctx, time, &again)) != CB200_OK) return rc;
+        if (ctx->last.ctr.err_flags) break;
     }
-    return fail(ctx, CB200_E_STATE, "step buffers failed to converge");
+    if (again && !ctx->last.ctr.err_flags) return fail(ctx, CB200_E_STATE, "step buffers failed to converge");
+    accumulate_timing(ctx, ST_PRE, true);
+    ctx->timed_steps += 1;
+    ctx->timing_valid = true;
+    return fill_result(ctx, out);
+}
+
+// ---- sharded step -------------------------------------------------------------------------
+int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* col_bounds) {
+    if (!ctx || !col_bounds) return CB200_E_ARG;
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return fail(ctx, CB200_E_ARG, "bad rank / world");
+    for (int d = 0; d < world; ++d)
+        if (!(col_bounds[d] < col_bounds[d + 1])) return fail(ctx, CB200_E_ARG, "strip bounds must be strictly ascending");
+    ShardGeom g{};
+    g.world = world;
+    g.rank = rank;
+    for (int d = 0; d <= world; ++d) g.bounds[d] = col_bounds[d];
+    g.bounds[0] = INT32_MIN;
+    g.bounds[world] = INT32_MAX;
+    g.col_lo = g.bounds[rank];
+    g.col_hi = g.bounds[rank + 1];
+    ctx->shard = g;
+    ctx->sharded = true;
+    ctx->have_state = false;  // the table must be (re-)uploaded: sharded tables carry gid = id
+    return CB200_OK;
+}
+
+int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, uint64_t* send_counts, uint64_t* n_local,
+                      void** send_base, uint64_t* send_stride_bytes, void** recv_base, uint64_t* recv_cap_records) {
+    if (!ctx || !send_counts) return CB200_E_ARG;
+    if (!ctx->sharded) return fail(ctx, CB200_E_STATE, "cb200_shard_configure first");
+    if (!ctx->have_state) return fail(ctx, CB200_E_STATE, "shard_begin before upload_state");
+    if (!(time < 1e50)) return fail(ctx, CB200_E_ARG, "requires time < 1e50");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev_t[ST_PRE], ctx->stream));
+    const double* nv[5];
+    int rc = stage_vel(ctx, vel, nv);
+    if (rc != CB200_OK) return rc;
+    if ((rc = prepare_buffers(ctx)) != CB200_OK) return rc;
+    if ((rc = enqueue_front(ctx, time, true, nv, end_time)) != CB200_OK) return rc;
+    std::vector<uint32_t> cnt(ctx->shard.world);
+    Counters c;
+    CU(cudaMemcpyAsync(cnt.data(), ctx->send_count.p, sizeof(uint32_t) * ctx->shard.world, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&c, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    if (c.overflow_send) return fail(ctx, CB200_E_STATE, "halo send buffer or visitor table overflow (strips too thin for this scene)");
+    for (int d = 0; d < ctx->shard.world; ++d) send_counts[d] = cnt[d];
+    ctx->n_local = c.n_local;
+    ctx->shard_open = true;
+    ctx->shard_T = time;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev_t[ST_PRE], ctx->ev_t[ST_STAGE_A]) == cudaSuccess) { ctx->stage_ms_sum[ST_PRE] += ms; ctx->total_ms_sum += ms; }
+    if (cudaEventElapsedTime(&ms, ctx->ev_t[ST_STAGE_A], ctx->ev_t[ST_SCAN]) == cudaSuccess) { ctx->stage_ms_sum[ST_STAGE_A] += ms; ctx->total_ms_sum += ms; }
+    if (n_local) *n_local = c.n_local;
+    if (send_base) *send_base = ctx->send.p;
+    if (send_stride_bytes) *send_stride_bytes = (uint64_t)ctx->cap_send * sizeof(HbRec);
+    if (recv_base) *recv_base = ctx->rec.p + c.n_local;
+    if (recv_cap_records) *recv_cap_records = ctx->rec.cap - c.n_local;
+    return CB200_OK;
+}
+
+int cb200_shard_finish(cb200_ctx* ctx, uint64_t n_recv, cb200_step_result* out) {
+    if (!ctx) return CB200_E_ARG;
+    if (!ctx->shard_open) return fail(ctx, CB200_E_STATE, "shard_finish without shard_begin");
+    if ((uint64_t)ctx->n_local + n_recv > ctx->rec.cap) return fail(ctx, CB200_E_ARG, "received more records than the visitor table holds");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n_vis = ctx->n_local + (uint32_t)n_recv;
+    int rc;
+    bool again = true;
+    CU(cudaEventRecord(ctx->ev_t[ST_SCAN], ctx->stream));
+    for (int attempt = 0; attempt < 4 && again; ++attempt) {
+        if (attempt > 0) {
+            // re-run of the back half only: slot table and counters are rebuilt, the visitor table is intact
+            const uint32_t n_slots = ctx->geom.n_slots();
+            Counters keep = ctx->last.ctr;
+            CU(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_slots * 4, ctx->stream));
+            CU(cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)(n_slots / kScanTile) * 8, ctx->stream));
+            Counters z{};
+            z.err_slot = keep.err_slot;
+            z.err_flags = keep.err_flags;
+            z.n_solitaire = keep.n_solitaire;
+            z.n_local = keep.n_local;
+            CU(cudaMemcpyAsync(ctx->d_ctr, &z, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            CU(cudaEventRecord(ctx->ev_t[ST_SCAN], ctx->stream));
+        }
+        if ((rc = enqueue_back(ctx, n_vis, ctx->shard_T)) != CB200_OK) return rc;
+        if ((rc = complete_step(ctx, ctx->shard_T, &again)) != CB200_OK) return rc;
+        if (ctx->last.ctr.err_flags) break;
+    }
+    ctx->shard_open = false;
+    if (again && !ctx->last.ctr.err_flags) return fail(ctx, CB200_E_STATE, "step buffers failed to converge");
+    accumulate_timing(ctx, ST_SCAN, false);
+    ctx->timed_steps += 1;
+    ctx->timing_valid = true;
+    return fill_result(ctx, out);
 }
 
 // ---- event queue materialisation -------------------------------------------------------------------------
@@ -564,7 +767,7 @@ static int sort_events(cb200_ctx* ctx) {
     CU(ctx->rs_hist.reserve((size_t)16 * n_blocks));
     CU(cudaMemsetAsync(&ctx->d_ctr->n_sort_keys, 0, 8, ctx->stream));
     CU(cudaMemsetAsync(&ctx->d_ctr->diff_hi, 0, 16, ctx->stream));
-    if (ctx->n) k_keys_solitaire<<<(ctx->n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(ctx->n, ctx->reit.p, ctx->col[9].p, ctx->keys_a.p, ctx->d_ctr);
+    if (ctx->n) k_keys_solitaire<<<(ctx->n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(ctx->n, ctx->reit.p, ctx->col[9].p, ctx->sharded ? ctx->gid.p : nullptr, ctx->keys_a.p, ctx->d_ctr);
     if (n_pairs) k_keys_pairs<<<((uint32_t)n_pairs + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>((uint32_t)n_pairs, ctx->events.p, ctx->keys_a.p, c.n_solitaire);
     k_key_diff<<<std::min<uint32_t>(n_blocks, 1024), kThreads, 0, ctx->stream>>>(nt, ctx->keys_a.p, ctx->d_ctr);
     ctx->launches += 3;
@@ -582,7 +785,7 @@ static int sort_events(cb200_ctx* ctx) {
         ctx->launches += 3;
         std::swap(in, outp);
     }
-    k_decode_events<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(nt, in, ctx->ids.p, ctx->ev_out.p);
+    k_decode_events<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(nt, in, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p);
     ctx->launches += 1;
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
@@ -605,6 +808,16 @@ int cb200_fetch_events(cb200_ctx* ctx, cb200_event* buf, uint64_t cap, uint64_t 
     return CB200_OK;
 }
 
+// gid -> HbId for the debug views (one device: the id column; sharded: identity).
+static int gid_to_id_table(cb200_ctx* ctx, std::vector<uint64_t>& ids) {
+    ids.clear();
+    if (ctx->sharded) return CB200_OK;
+    ids.resize(ctx->n);
+    if (ctx->n) CU(cudaMemcpy(ids.data(), ctx->ids.p, (size_t)ctx->n * 8, cudaMemcpyDeviceToHost));
+    return CB200_OK;
+}
+static inline uint64_t id_of(const std::vector<uint64_t>& ids, uint32_t gid) { return ids.empty() ? (uint64_t)gid : ids[gid]; }
+
 int cb200_fetch_candidate_pairs(cb200_ctx* ctx, uint64_t* id_hi, uint64_t* id_lo, uint64_t cap, uint64_t* n_out) {
     if (!ctx) return CB200_E_ARG;
     if (!ctx->have_step) return fail(ctx, CB200_E_STATE, "fetch_candidate_pairs before bulk_update");
@@ -613,13 +826,17 @@ int cb200_fetch_candidate_pairs(cb200_ctx* ctx, uint64_t* id_hi, uint64_t* id_lo
     if (n_out) *n_out = total;
     if (cap == 0 || total == 0) return CB200_OK;
     std::vector<uint2> h(total);
-    std::vector<uint64_t> ids(ctx->n);
-    CU(cudaMemcpyAsync(h.data(), ctx->cand.p, total * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(ids.data(), ctx->ids.p, (size_t)ctx->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint64_t> ids;
+    int rc = gid_to_id_table(ctx, ids);
+    if (rc != CB200_OK) return rc;
+    CU(cudaMemcpy(h.data(), ctx->cand.p, total * sizeof(uint2), cudaMemcpyDeviceToHost));
+    // candidates hold record indices; the record carries the gid (offset 12 of every 96-byte record)
+    const uint32_t n_rec = ctx->sharded ? (uint32_t)std::min<size_t>(ctx->rec.cap, 0xffffffffu) : ctx->n;
+    std::vector<uint32_t> gids(n_rec);
+    if (n_rec) CU(cudaMemcpy2D(gids.data(), 4, reinterpret_cast<const char*>(ctx->rec.p) + 12, sizeof(HbRec), 4, n_rec, cudaMemcpyDeviceToHost));
     for (uint64_t i = 0; i < total && i < cap; ++i) {
-        if (id_hi) id_hi[i] = ids[h[i].x];
-        if (id_lo) id_lo[i] = ids[h[i].y];
+        if (id_hi) id_hi[i] = id_of(ids, gids[h[i].x]);
+        if (id_lo) id_lo[i] = id_of(ids, gids[h[i].y]);
     }
     return CB200_OK;
 }
@@ -632,18 +849,20 @@ int cb200_fetch_cell_entries(cb200_ctx* ctx, int32_t* cell_x, int32_t* cell_y, u
     if (n_out) *n_out = total;
     if (cap == 0 || total == 0) return CB200_OK;
     std::vector<CellEntry> h(total);
-    std::vector<uint64_t> ids(ctx->n);
+    std::vector<uint64_t> ids;
+    int rc = gid_to_id_table(ctx, ids);
+    if (rc != CB200_OK) return rc;
     CU(cudaMemcpy(h.data(), ctx->entries.p, total * sizeof(CellEntry), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(ids.data(), ctx->ids.p, (size_t)ctx->n * 8, cudaMemcpyDeviceToHost));
     const uint32_t mw = (1u << ctx->geom.lw) - 1u, mh = (1u << ctx->geom.lh) - 1u;
     for (uint64_t i = 0; i < total && i < cap; ++i) {
         const CellEntry& r = h[i];
-        const uint32_t sxs = r.slot & mw, sys = r.slot >> ctx->geom.lw;
+        const uint32_t slot = r.slot_group & kSlotMask;
+        const uint32_t sxs = slot & mw, sys = slot >> ctx->geom.lw;
         // the unique cell of the rect that folds onto this slot
         const int32_t x = r.sx + (int32_t)((sxs - (uint32_t)r.sx) & mw), y = r.sy + (int32_t)((sys - (uint32_t)r.sy) & mh);
         if (cell_x) cell_x[i] = x;
         if (cell_y) cell_y[i] = y;
-        if (id) id[i] = ids[r.idx];
+        if (id) id[i] = id_of(ids, r.gid);
     }
     return CB200_OK;
 }
@@ -651,10 +870,17 @@ int cb200_fetch_cell_entries(cb200_ctx* ctx, int32_t* cell_x, int32_t* cell_y, u
 int cb200_fetch_index_rects(cb200_ctx* ctx, int32_t* rects, uint64_t cap_hitboxes) {
     if (!ctx || !rects) return CB200_E_ARG;
     if (!ctx->have_step) return fail(ctx, CB200_E_STATE, "fetch_index_rects before bulk_update");
+    if (ctx->sharded) return fail(ctx, CB200_E_STATE, "fetch_index_rects is a one-device debug view");
     if (cap_hitboxes < ctx->n) return fail(ctx, CB200_E_ARG, "rect buffer too small");
     CU(cudaSetDevice(ctx->device));
-    // strided D2H: first 16 bytes of every 96-byte record
+    // strided D2H: first 16 bytes of every 96-byte record = sx, sy, span, gid -> decode the span
     if (ctx->n) CU(cudaMemcpy2D(rects, 16, ctx->rec.p, sizeof(HbRec), 16, ctx->n, cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < ctx->n; ++i) {
+        int32_t* r = rects + 4 * i;
+        const uint32_t span = (uint32_t)r[2];
+        r[2] = r[0] + (int32_t)(span & 0xffffu);
+        r[3] = r[1] + (int32_t)(span >> 16);
+    }
     return CB200_OK;
 }
 

@@ -20,23 +20,46 @@ struct StateCols {  // SoA hitbox table, slot order == ascending HbId
     uint8_t* reit;  // 1 = a Reiterate event is queued at `end` (collider.rs:441-447)
 };
 
+// Spatial sharding: cell columns are split into contiguous strips, one per rank.  bounds[d] <=
+// column < bounds[d+1] belongs to rank d (bounds[0] = INT32_MIN, bounds[world] = INT32_MAX).  A pair is solved by
+// the rank whose strip holds the pair's owner cell column max(sx_i, sx_j), which is never left of either rect's
+// start: records only ever travel to ranks at or right of their start column.
+constexpr int kMaxWorld = 64;
+struct ShardGeom {
+    int world, rank;
+    int32_t col_lo, col_hi;          // own strip [col_lo, col_hi); one device: the whole i32 range
+    int32_t bounds[kMaxWorld + 1];
+};
+
 struct StepArgs {
     uint32_t n;
     int rebase;  // 0 = re-run of binning on an already-rebased table (after a buffer grew): skip the advance
     double T, cell_width, padding, end_scalar;
     StateCols s;
     const double *nvx, *nvy, *nrw, *nrh, *nend;  // optional new velocity columns (device), null = keep
-    HbRec* rec;
-    uint32_t* slot_count;
+    const uint32_t* gid;   // null: gid = table slot
+    HbRec* rec;            // one device: rec[i].  Sharded: the visitor table, own records appended at [0, n_local)
+    uint32_t* slot_count;  // one device only (the count is fused here)
     GridGeom geom;
     Counters* ctr;
     MinKey* partial;  // [gridDim.x] solitaire minima
+    // sharded only
+    HbRec* send;           // [world][cap_send] records for the other ranks
+    uint32_t* send_count;  // [world]
+    uint32_t cap_send, cap_vis;
 };
 
 __device__ __forceinline__ bool is_finite(double x) { return fabs(x) < cb_inf(); }
 
 // Rust `f64 as i32`: saturating, NaN -> 0 — exactly cvt.rzi.s32.f64.
 __device__ __forceinline__ int32_t f64_as_i32(double v) { return __double2int_rz(v); }
+
+__device__ __forceinline__ void store_rec(HbRec* dst, const HbRec& rec) {
+    int4* out = reinterpret_cast<int4*>(dst);
+    const int4* in = reinterpret_cast<const int4*>(&rec);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) out[k] = in[k];
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Stage A: per hitbox, the part of internal_update_hitbox that touches only that hitbox.
@@ -48,132 +71,177 @@ __device__ __forceinline__ int32_t f64_as_i32(double v) { return __double2int_rz
 //   DurHitbox     Hitbox::to_dur_hitbox (core/mod.rs:177-187)
 //   swept bounds  DurHitbox::bounding_box (dur_hitbox/mod.rs:88-99)
 //   IndexRect     Grid::index_bounds (grid.rs:101-113)
-//   cell count    first half of the counting sort that replaces Grid::update_area (grid.rs:137-175)
+//   cell count    first half of the counting sort that replaces Grid::update_area (grid.rs:137-175)   [one device]
+//   halo pack     the record goes to every rank whose strip its rect (+1 column) touches                [sharded]
 // Reads the SoA columns coalesced, writes the rebased columns back and the 96-B HbRec for the pair stage.
-__global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a) {
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+template <bool SHARDED>
+__global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const ShardGeom sh) {
+    __shared__ uint32_t s_base;
     MinKey best{kKeyMax, kKeyMax};
     unsigned long long n_sol = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        double px = a.s.px[i], py = a.s.py[i], w = a.s.w[i], h = a.s.h[i];
-        double vx = a.s.vx[i], vy = a.s.vy[i], rw = a.s.rw[i], rh = a.s.rh[i];
-        const double start = a.s.start[i], pub_end_old = a.s.pub_end[i];
-        const uint32_t kind = a.s.kind[i], group = a.s.group[i], mask = a.s.mask[i];
-        const double T = a.T;
-        uint32_t err = 0;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < a.n; base += stride) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t keep_local = 0;
+        HbRec rec;
+        int32_t ex = 0;
+        if (i < a.n) {
+            double px = a.s.px[i], py = a.s.py[i], w = a.s.w[i], h = a.s.h[i];
+            double vx = a.s.vx[i], vy = a.s.vy[i], rw = a.s.rw[i], rh = a.s.rh[i];
+            const double start = a.s.start[i], pub_end_old = a.s.pub_end[i];
+            const uint32_t kind = a.s.kind[i], group = a.s.group[i], mask = a.s.mask[i];
+            const double T = a.T;
+            uint32_t err = 0;
 
-        // pub_hitbox_at_time(T): assert start <= T <= pub_end, then advance by T - start.
-        if (!(T >= start && T <= pub_end_old)) err |= kFInvalidTime;
-        const double dt = T - start;
-        if (!(dt < kHighTime)) err |= kFHighTime;
-        if (a.rebase) {
-            px = px + vx * dt;
-            py = py + vy * dt;
-            w = w + rw * dt;
-            h = h + rh * dt;
-        }
+            // pub_hitbox_at_time(T): assert start <= T <= pub_end, then advance by T - start.
+            if (!(T >= start && T <= pub_end_old)) err |= kFInvalidTime;
+            const double dt = T - start;
+            if (!(dt < kHighTime)) err |= kFHighTime;
+            if (a.rebase) {
+                px = px + vx * dt;
+                py = py + vy * dt;
+                w = w + rw * dt;
+                h = h + rh * dt;
+            }
 
-        // install the new velocity, validate
-        if (a.nvx) vx = a.nvx[i];
-        if (a.nvy) vy = a.nvy[i];
-        if (a.nrw) rw = a.nrw[i];
-        if (a.nrh) rh = a.nrh[i];
-        const double user_end = a.nend ? a.nend[i] : a.end_scalar;
-        if (!(user_end >= T)) err |= kFEndTime;  // also catches NaN
-        if (kind == (uint32_t)kCircle && !(rw == rh)) err |= kFCircleResize;
-        if (!(w >= a.padding && h >= a.padding)) err |= kFTooSmall;
-        if (!(is_finite(px) && is_finite(py) && is_finite(w) && is_finite(h) && is_finite(vx) && is_finite(vy) && is_finite(rw) &&
-              is_finite(rh)))
-            err |= kFNan;
+            // install the new velocity, validate
+            if (a.nvx) vx = a.nvx[i];
+            if (a.nvy) vy = a.nvy[i];
+            if (a.nrw) rw = a.nrw[i];
+            if (a.nrh) rh = a.nrh[i];
+            const double user_end = a.nend ? a.nend[i] : a.end_scalar;
+            if (!(user_end >= T)) err |= kFEndTime;  // also catches NaN
+            if (kind == (uint32_t)kCircle && !(rw == rh)) err |= kFCircleResize;
+            if (!(w >= a.padding && h >= a.padding)) err |= kFTooSmall;
+            if (!(is_finite(px) && is_finite(py) && is_finite(w) && is_finite(h) && is_finite(vx) && is_finite(vy) && is_finite(rw) &&
+                  is_finite(rh)))
+                err |= kFNan;
 
-        // solitaire_event_check (release build)
-        const bool has_group = group != kGroupNone;
-        double period = cb_inf();
-        if (has_group) {
-            const double speed = fmax(fmax(fabs(vx - rw * 0.5), fabs(vy - rh * 0.5)), fmax(fabs(vx + rw * 0.5), fabs(vy + rh * 0.5)));
-            if (!(speed <= 0.0)) period = a.cell_width / speed;
-        }
-        double r_time = T + period;
-        bool reit = true;
-        if (user_end < r_time) {
-            r_time = user_end;
-            reit = false;
-        }
-        {
-            const double min_size = a.padding * 0.9;
-            if (!(w > min_size && h > min_size)) err |= kFTooSmall;
-            double tus = cb_inf();
-            if (rw < 0.0) tus = fmin(tus, (min_size - w) / rw);
-            if (rh < 0.0) tus = fmin(tus, (min_size - h) / rh);
-            const double small_end = T + tus;
-            if (small_end < r_time) {
-                r_time = small_end;
+            // solitaire_event_check (release build)
+            const bool has_group = group != kGroupNone;
+            double period = cb_inf();
+            if (has_group) {
+                const double speed = fmax(fmax(fabs(vx - rw * 0.5), fabs(vy - rh * 0.5)), fmax(fabs(vx + rw * 0.5), fabs(vy + rh * 0.5)));
+                if (!(speed <= 0.0)) period = a.cell_width / speed;
+            }
+            double r_time = T + period;
+            bool reit = true;
+            if (user_end < r_time) {
+                r_time = user_end;
                 reit = false;
             }
-        }
-        reit = reit && (r_time < kHighTime);  // EventManager::new_event_key drops time >= 1e50 (events.rs:156-159)
-        const double dur = r_time - T;
-
-        // swept bounds + IndexRect (only hitboxes with a group enter the grid, collider.rs:328)
-        HbRec rec;
-        rec.sx = rec.sy = 0;
-        rec.ex = rec.ey = 0;
-        bool binned = false;
-        if (has_group && err == 0) {
-            DurHb d;
-            d.px = px; d.py = py; d.w = w; d.h = h; d.vx = vx; d.vy = vy; d.rw = rw; d.rh = rh; d.dur = dur; d.kind = (int)kind;
-            const Box4 bb = swept_bounds(d, dur);
-            if (!bb.ok) {
-                err |= (dur < kHighTime) ? kFNan : kFHighTime;
-            } else {
-                const double min_x = bb.cx - bb.w * 0.5, max_x = bb.cx + bb.w * 0.5;
-                const double min_y = bb.cy - bb.h * 0.5, max_y = bb.cy + bb.h * 0.5;
-                const int32_t sx = f64_as_i32(floor(min_x / a.cell_width));
-                const int32_t sy = f64_as_i32(floor(min_y / a.cell_width));
-                const int32_t ex = max(f64_as_i32(ceil(max_x / a.cell_width)), (int32_t)((uint32_t)sx + 1u));
-                const int32_t ey = max(f64_as_i32(ceil(max_y / a.cell_width)), (int32_t)((uint32_t)sy + 1u));
-                const int64_t nx = (int64_t)ex - sx, ny = (int64_t)ey - sy;
-                if (nx <= 0 || ny <= 0) {
-                    err |= kFEmptyRect;  // IndexRect::new (index_rect.rs:26-29)
-                } else if (nx > (1ll << a.geom.lw) || ny > (1ll << a.geom.lh)) {
-                    err |= kFRectSpan;
-                } else {
-                    rec.sx = sx; rec.sy = sy; rec.ex = ex; rec.ey = ey;
-                    binned = true;
-                    for (int32_t x = sx; x != ex; ++x)
-                        for (int32_t y = sy; y != ey; ++y) atomicAdd(&a.slot_count[a.geom.slot(x, y)], 1u);
+            {
+                const double min_size = a.padding * 0.9;
+                if (!(w > min_size && h > min_size)) err |= kFTooSmall;
+                double tus = cb_inf();
+                if (rw < 0.0) tus = fmin(tus, (min_size - w) / rw);
+                if (rh < 0.0) tus = fmin(tus, (min_size - h) / rh);
+                const double small_end = T + tus;
+                if (small_end < r_time) {
+                    r_time = small_end;
+                    reit = false;
                 }
             }
+            reit = reit && (r_time < kHighTime);  // EventManager::new_event_key drops time >= 1e50 (events.rs:156-159)
+            const double dur = r_time - T;
+
+            // swept bounds + IndexRect (only hitboxes with a group enter the grid, collider.rs:328)
+            rec.sx = rec.sy = 0;
+            rec.span = 0;
+            bool binned = false;
+            if (has_group && err == 0) {
+                DurHb d;
+                d.px = px; d.py = py; d.w = w; d.h = h; d.vx = vx; d.vy = vy; d.rw = rw; d.rh = rh; d.dur = dur; d.kind = (int)kind;
+                const Box4 bb = swept_bounds(d, dur);
+                if (!bb.ok) {
+                    err |= (dur < kHighTime) ? kFNan : kFHighTime;
+                } else {
+                    const double min_x = bb.cx - bb.w * 0.5, max_x = bb.cx + bb.w * 0.5;
+                    const double min_y = bb.cy - bb.h * 0.5, max_y = bb.cy + bb.h * 0.5;
+                    const int32_t sx = f64_as_i32(floor(min_x / a.cell_width));
+                    const int32_t sy = f64_as_i32(floor(min_y / a.cell_width));
+                    ex = max(f64_as_i32(ceil(max_x / a.cell_width)), (int32_t)((uint32_t)sx + 1u));
+                    const int32_t ey = max(f64_as_i32(ceil(max_y / a.cell_width)), (int32_t)((uint32_t)sy + 1u));
+                    const int64_t nx = (int64_t)ex - sx, ny = (int64_t)ey - sy;
+                    if (nx <= 0 || ny <= 0) {
+                        err |= kFEmptyRect;  // IndexRect::new (index_rect.rs:26-29)
+                    } else if (nx > (1ll << a.geom.lw) || ny > (1ll << a.geom.lh) || nx > 0xffff || ny > 0xffff) {
+                        err |= kFRectSpan;
+                    } else {
+                        rec.sx = sx; rec.sy = sy;
+                        rec.span = (uint32_t)nx | ((uint32_t)ny << 16);
+                        binned = true;
+                        if (!SHARDED) {
+                            for (int32_t x = sx; x != ex; ++x)
+                                for (int32_t y = sy; y != ey; ++y) atomicAdd(&a.slot_count[a.geom.slot(x, y)], 1u);
+                        }
+                    }
+                }
+            }
+            if (err) report_error(a.ctr, err, i);
+
+            // write back: state columns + pair-stage record
+            a.s.px[i] = px; a.s.py[i] = py; a.s.w[i] = w; a.s.h[i] = h;
+            if (a.nvx) a.s.vx[i] = vx;
+            if (a.nvy) a.s.vy[i] = vy;
+            if (a.nrw) a.s.rw[i] = rw;
+            if (a.nrh) a.s.rh[i] = rh;
+            a.s.start[i] = T;
+            a.s.end[i] = r_time;
+            a.s.pub_end[i] = user_end;
+            a.s.reit[i] = reit ? 1 : 0;
+
+            const uint32_t gid = a.gid ? a.gid[i] : i;
+            rec.gid = gid;
+            rec.dur = dur;
+            rec.kgb = (kind & 1u) | (binned ? 2u : 0u) | ((has_group ? (group & 0xffu) : 0xffu) << 8);
+            rec.mask = mask;
+            rec.px = px; rec.py = py; rec.w = w; rec.h = h;
+            rec.vx = vx; rec.vy = vy; rec.rw = rw; rec.rh = rh;
+            if (!SHARDED) {
+                store_rec(a.rec + i, rec);
+            } else if (binned) {
+                // every rank whose strip intersects columns [sx, ex + 1): the extra column keeps a partner that is
+                // within `padding` across a cell line (an overlapping pair whose rects do not intersect) visible.
+                const int64_t hi_col = (int64_t)ex + 1;
+                for (int d = 0; d < sh.world; ++d) {
+                    if ((int64_t)sh.bounds[d + 1] <= (int64_t)rec.sx || (int64_t)sh.bounds[d] >= hi_col) continue;
+                    if (d == sh.rank) {
+                        keep_local = 1;
+                    } else {
+                        const uint32_t pos = warp_agg_claim32(&a.send_count[d]);
+                        if (pos < a.cap_send) store_rec(a.send + (size_t)d * a.cap_send + pos, rec);
+                        else a.ctr->overflow_send = 1u;
+                    }
+                }
+            }
+
+            if (reit) {
+                ++n_sol;
+                const MinKey k{time_key(r_time), (uint64_t)gid};
+                if (key_less(k, best)) best = k;
+            }
         }
-        if (err) report_error(a.ctr, err, i);
-
-        // write back: state columns + pair-stage record
-        a.s.px[i] = px; a.s.py[i] = py; a.s.w[i] = w; a.s.h[i] = h;
-        if (a.nvx) a.s.vx[i] = vx;
-        if (a.nvy) a.s.vy[i] = vy;
-        if (a.nrw) a.s.rw[i] = rw;
-        if (a.nrh) a.s.rh[i] = rh;
-        a.s.start[i] = T;
-        a.s.end[i] = r_time;
-        a.s.pub_end[i] = user_end;
-        a.s.reit[i] = reit ? 1 : 0;
-
-        rec.dur = dur;
-        rec.kgb = (kind & 1u) | (binned ? 2u : 0u) | ((has_group ? (group & 0xffu) : 0xffu) << 8);
-        rec.mask = mask;
-        rec.px = px; rec.py = py; rec.w = w; rec.h = h;
-        rec.vx = vx; rec.vy = vy; rec.rw = rw; rec.rh = rh;
-        {
-            int4* out = reinterpret_cast<int4*>(a.rec + i);
-            const int4* in = reinterpret_cast<const int4*>(&rec);
-#pragma unroll
-            for (int k = 0; k < 6; ++k) out[k] = in[k];
-        }
-
-        if (reit) {
-            ++n_sol;
-            const MinKey k{time_key(r_time), (uint64_t)i};
-            if (key_less(k, best)) best = k;
+        if (SHARDED) {
+            // block-aggregated append of the records this rank keeps (one global atomic per block-iteration)
+            uint32_t total;
+            const uint32_t off = block_excl_scan(keep_local, &total);
+            if (total) {
+                if (threadIdx.x == 0) s_base = atomicAdd(&a.ctr->n_local, total);
+                __syncthreads();
+                const uint32_t pos = s_base + off;
+                if (keep_local) {
+                    if (pos < a.cap_vis) store_rec(a.rec + pos, rec);
+                    else a.ctr->overflow_send = 1u;
+                }
+                __syncthreads();
+            }
         }
     }
     best = block_min(best);
@@ -181,6 +249,28 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a) {
     if (threadIdx.x == 0) {
         a.partial[blockIdx.x] = best;
         if (tot) atomicAdd(&a.ctr->n_solitaire, tot);
+    }
+}
+
+// Sharded: count the cells of every visitor record (own + received) that fall into this rank's strip, and index
+// the records by gid for the overlapping-pair lookups.
+__global__ void __launch_bounds__(kThreads) k_count_visitors(uint32_t n_vis, const HbRec* __restrict__ vis, uint32_t* slot_count, GridGeom geom,
+                                                             ShardGeom sh, unsigned long long* gid_map, uint32_t gid_map_mask) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_vis; v += stride) {
+        const RecHead h = load_head(vis, v);
+        const int32_t x0 = max(h.sx, sh.col_lo), x1 = min(h.ex, sh.col_hi);
+        for (int32_t x = x0; x < x1; ++x)
+            for (int32_t y = h.sy; y != h.ey; ++y) atomicAdd(&slot_count[geom.slot(x, y)], 1u);
+        if (gid_map_mask) {
+            uint32_t p = (uint32_t)mix64(h.gid) & gid_map_mask;
+            const unsigned long long val = ((unsigned long long)h.gid << 32) | v;
+            for (;;) {
+                const unsigned long long prev = atomicCAS(&gid_map[p], kKeyMax, val);
+                if (prev == kKeyMax) break;
+                p = (p + 1) & gid_map_mask;
+            }
+        }
     }
 }
 
@@ -281,32 +371,35 @@ __global__ void __launch_bounds__(kThreads) k_scan_slots(uint32_t* __restrict__ 
 
 // ---------------------------------------------------------------------------------------------------------
 // Scatter: second half of the counting sort.  offsets[s] enters as the start of slot s and is used as the
-// slot's cursor.  A cell entry carries everything the candidate stage tests (IndexRect, profile bits), so
+// slot's cursor.  A cell entry carries everything the candidate stage tests (IndexRect, profile bits, id rank), so
 // that stage streams the entry array and never gathers hitbox records: 32 B = one sector per entry.
 struct alignas(32) CellEntry {
     int32_t sx, sy, ex, ey;  // IndexRect of the hitbox
-    uint32_t idx;            // hitbox slot index (== HbId rank)
-    uint32_t slot;           // grid slot of this entry
+    uint32_t vidx;           // index of its record in the visitor table (one device: the table slot)
+    uint32_t slot_group;     // grid slot (26 bits) | group << 26
     uint32_t mask;           // interact_groups bit mask
-    uint32_t group;          // group 0..31
+    uint32_t gid;            // id rank: decides hi/lo and breaks ties
 };
 static_assert(sizeof(CellEntry) == 32, "CellEntry must be one sector");
+constexpr uint32_t kSlotMask = (1u << 26) - 1u;
 
-__global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const HbRec* __restrict__ rec, uint32_t* offsets, CellEntry* entries,
-                                                      uint32_t cap_entries, GridGeom geom, Counters* ctr) {
+__global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n_vis, const HbRec* __restrict__ rec, uint32_t* offsets, CellEntry* entries,
+                                                      uint32_t cap_entries, GridGeom geom, int32_t col_lo, int32_t col_hi, Counters* ctr) {
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vis; i += stride) {
         const RecHead h = load_head(rec, i);
         if (!(h.kgb & 2u)) continue;
         const int4 lo4 = make_int4(h.sx, h.sy, h.ex, h.ey);
-        for (int32_t x = h.sx; x != h.ex; ++x)
+        const uint32_t group = (h.kgb >> 8) & 0x1fu;
+        const int32_t x0 = max(h.sx, col_lo), x1 = min(h.ex, col_hi);
+        for (int32_t x = x0; x < x1; ++x)
             for (int32_t y = h.sy; y != h.ey; ++y) {
                 const uint32_t s = geom.slot(x, y);
                 const uint32_t pos = atomicAdd(&offsets[s], 1u);
                 if (pos < cap_entries) {
                     int4* out = reinterpret_cast<int4*>(entries + pos);
                     out[0] = lo4;
-                    out[1] = make_int4((int)i, (int)s, (int)h.mask, (int)((h.kgb >> 8) & 0xffu));
+                    out[1] = make_int4((int)i, (int)(s | (group << 26)), (int)h.mask, (int)h.gid);
                 } else {
                     ctr->overflow_entries = 1u;
                 }
@@ -320,11 +413,6 @@ struct OverlapSet {
     const unsigned long long* table;  // kKeyMax = empty
     uint32_t cap_mask;                // capacity - 1 (power of two); 0 = no overlaps at all
 };
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    return z ^ (z >> 31);
-}
 __device__ __forceinline__ bool overlap_contains(const OverlapSet& ov, uint32_t hi, uint32_t lo) {
     const unsigned long long key = ((unsigned long long)hi << 32) | lo;
     uint32_t p = (uint32_t)mix64(key) & ov.cap_mask;
@@ -354,6 +442,11 @@ __global__ void k_overlap_map_ids(const uint64_t* __restrict__ ids, uint32_t n, 
     if (i >= n_pairs) return;
     uint32_t s[2];
     const uint64_t want[2] = {id_a[i], id_b[i]};
+    if (ids == nullptr) {  // sharded: the id is its own rank
+        if (want[0] >= 0x7fffffffull || want[1] >= 0x7fffffffull || want[0] == want[1]) report_error(ctr, kFIdNotFound, i);
+        pairs[i] = make_uint2((uint32_t)max(want[0], want[1]), (uint32_t)min(want[0], want[1]));
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         uint32_t lo = 0, hi = n;
@@ -378,32 +471,35 @@ __global__ void k_overlap_map_ids(const uint64_t* __restrict__ ids, uint32_t n, 
 //   candidates   Grid::overlapping_ids (grid.rs:115-135) restricted to the surviving (hi, lo) pairs; the
 //                hash-set de-duplication is replaced by pair ownership: a pair is taken only in the slot of
 //                cell (max(sx_i, sx_j), max(sy_i, sy_j)) — the min corner of the rect intersection — so every
-//                pair sharing >= 1 cell is produced exactly once, and aliased slot-mates are rejected.
+//                pair sharing >= 1 cell is produced exactly once, and aliased slot-mates are rejected.  Sharded:
+//                only the rank whose strip holds the owner cell's column takes the pair.
 //   filters      lo.group in hi.interact_groups (grid.rs:122, key group); not already overlapping (collider.rs:351)
-// Output: the compact candidate list (hi, lo), appended with warp-aggregated atomics.
+// Output: the compact candidate list (record index of hi, record index of lo).
 struct CandArgs {
     const CellEntry* entries;
     GridGeom geom;
+    int32_t col_lo, col_hi;
     OverlapSet ov;
     uint2* cand;
     uint32_t cap_cand;
     Counters* ctr;
 };
 
-// One (entry, predecessor) test of the candidate stage; on success *hi/*lo receive the pair.
+// One (entry, predecessor) test; on success *hi/*lo receive the record indices of the higher / lower id.
 __device__ __forceinline__ bool candidate_test(const CandArgs& a, const int4& r, const int4& m, const int4& rf, const int4& mf, uint32_t* hi,
                                                uint32_t* lo) {
-    // ownership: min corner of the rect intersection must be this slot's cell
+    // ownership: min corner of the rect intersection must be this slot's cell (and, sharded, inside the own strip)
     const int32_t ox = max(r.x, rf.x), oy = max(r.y, rf.y);
     if (ox >= min(r.z, rf.z) || oy >= min(r.w, rf.w)) return false;
-    if (a.geom.slot(ox, oy) != (uint32_t)m.y) return false;
-    const uint32_t i = (uint32_t)m.x, j = (uint32_t)mf.x;
-    const bool i_is_hi = i > j;
-    *hi = i_is_hi ? i : j;
-    *lo = i_is_hi ? j : i;
-    const uint32_t mask_hi = (uint32_t)(i_is_hi ? m.z : mf.z), group_lo = (uint32_t)(i_is_hi ? mf.w : m.w);
+    if (a.geom.slot(ox, oy) != ((uint32_t)m.y & kSlotMask)) return false;
+    if (ox < a.col_lo || ox >= a.col_hi) return false;
+    const uint32_t gi = (uint32_t)m.w, gj = (uint32_t)mf.w;
+    const bool i_is_hi = gi > gj;
+    *hi = (uint32_t)(i_is_hi ? m.x : mf.x);
+    *lo = (uint32_t)(i_is_hi ? mf.x : m.x);
+    const uint32_t mask_hi = (uint32_t)(i_is_hi ? m.z : mf.z), group_lo = (uint32_t)(i_is_hi ? mf.y : m.y) >> 26;
     if (!((mask_hi >> group_lo) & 1u)) return false;
-    if (a.ov.cap_mask && overlap_contains(a.ov, *hi, *lo)) return false;
+    if (a.ov.cap_mask && overlap_contains(a.ov, i_is_hi ? gi : gj, i_is_hi ? gj : gi)) return false;
     return true;
 }
 
@@ -423,10 +519,11 @@ __global__ void __launch_bounds__(kThreads) k_candidates(const CandArgs a) {
             const int4* pe = reinterpret_cast<const int4*>(a.entries + e);
             r = __ldg(pe);
             m = __ldg(pe + 1);
+            const uint32_t slot = (uint32_t)m.y & kSlotMask;
             for (uint32_t f = e; f-- > 0; ++run) {
                 const int4* pf = reinterpret_cast<const int4*>(a.entries + f);
                 const int4 mf = __ldg(pf + 1);
-                if (mf.y != m.y) break;
+                if (((uint32_t)mf.y & kSlotMask) != slot) break;
                 const int4 rf = __ldg(pf);
                 uint32_t hi, lo;
                 if (candidate_test(a, r, m, rf, mf, &hi, &lo)) {
@@ -441,12 +538,12 @@ __global__ void __launch_bounds__(kThreads) k_candidates(const CandArgs a) {
         if (threadIdx.x == 0) s_base = atomicAdd(&a.ctr->n_collide, (unsigned long long)total);
         __syncthreads();
         unsigned long long pos = s_base + off;
-        const uint32_t i = (uint32_t)m.x;
         while (acc) {
             const int k = __ffsll((long long)acc) - 1;
             acc &= acc - 1;
-            const uint32_t j = (uint32_t)__ldg(reinterpret_cast<const int*>(a.entries + (e - 1 - k)) + 4);
-            if (pos < a.cap_cand) a.cand[pos] = make_uint2(max(i, j), min(i, j));
+            const int4 mf = __ldg(reinterpret_cast<const int4*>(a.entries + (e - 1 - k)) + 1);
+            const bool i_is_hi = (uint32_t)m.w > (uint32_t)mf.w;
+            if (pos < a.cap_cand) a.cand[pos] = make_uint2((uint32_t)(i_is_hi ? m.x : mf.x), (uint32_t)(i_is_hi ? mf.x : m.x));
             ++pos;
         }
         if (run > 64) {  // long slot runs (dense / clustered cells): redo the tests beyond the 64-bit window
@@ -465,14 +562,15 @@ __global__ void __launch_bounds__(kThreads) k_candidates(const CandArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Solve stage: one thread per pair.  Pairs [0, n_collide) are the candidates, pairs [n_collide, n_collide + n_ov)
-// the currently-overlapping pairs (HitboxInfo.overlaps).
+// Solve stage: one thread per pair.  Pairs [0, n_collide) are the candidates (record indices), pairs
+// [n_collide, n_collide + n_ov) the currently-overlapping pairs (HitboxInfo.overlaps) as (gid hi, gid lo).
 //   collide      hi.collide_time(lo rebased to T) (collider.rs:354 -> solvers.rs:25-34)
 //                -> add_pair_event(T + delay, Collide(hi, lo)), dropped when >= 1e50 (collider.rs:367-372, events.rs:156-159)
 //   separate     hi.separate_time(lo rebased to T, padding) (collider.rs:329-339 -> solvers.rs:36-44)
 //                -> add_pair_event(T + delay, Separate(hi, lo))
-//   min          EventManager::peek_time under the canonical order (events.rs:171-173): warp shuffle + block reduce
-// The step result, written by the last block of the solve stage straight into mapped pinned host memory.
+//   min          EventManager::peek_time under the canonical order (events.rs:171-173): warp shuffle + block reduce,
+//                the last block to finish reduces all per-block minima and publishes the step result
+// The step result, written by the last block straight into mapped pinned host memory.
 struct StepResultDev {
     double next_time;
     uint64_t next_tie;  // MinKey.tie of the minimum (kKeyMax if none)
@@ -492,12 +590,30 @@ struct SolveArgs {
     MinKey* partial;         // [n_partial_a + gridDim.x]: stage A's minima, then this kernel's
     uint32_t n_partial_a;
     StepResultDev* result;   // mapped host memory
+    // sharded: overlapping pairs are looked up by gid; only the owner-column rank solves them
+    const unsigned long long* gid_map;
+    uint32_t gid_map_mask;   // 0 = one device (gid == record index)
+    int32_t col_lo, col_hi;
 };
 
+__device__ __forceinline__ bool gid_lookup(const SolveArgs& a, uint32_t gid, uint32_t* vidx) {
+    uint32_t p = (uint32_t)mix64(gid) & a.gid_map_mask;
+    for (;;) {
+        const unsigned long long k = __ldg(a.gid_map + p);
+        if (k == kKeyMax) return false;
+        if ((uint32_t)(k >> 32) == gid) {
+            *vidx = (uint32_t)k;
+            return true;
+        }
+        p = (p + 1) & a.gid_map_mask;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
-    __shared__ uint32_t s_last;
     __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_last;
     MinKey best{kKeyMax, kKeyMax};
+    unsigned long long n_sep = 0;
     const uint32_t n_cand = (uint32_t)min((unsigned long long)a.cap_cand, a.ctr->n_collide);
     const uint32_t total = n_cand + a.n_ov;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -507,20 +623,28 @@ __global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
         uint32_t have = 0;
         if (p < total) {
             const bool sep = p >= n_cand;
-            const uint2 pr = sep ? a.ov_pairs[p - n_cand] : a.cand[p];
-            const RecHead hh = load_head(a.rec, pr.x), hl = load_head(a.rec, pr.y);
-            const DurHb A = load_body(a.rec, pr.x, hh);
-            // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486): advanced by T - start = 0
-            const DurHb B = advanced(load_body(a.rec, pr.y, hl), 0.0);
-            const double delay = sep ? separate_time(A, B, a.padding) : collide_time(A, B);
-            if (delay != delay) report_error(a.ctr, kFNan, pr.x);
-            const double t = a.T + delay;
-            if (t < kHighTime) {
-                const uint32_t kind_bit = sep ? 0u : kCollideBit;
-                ev = PairEvent{t, pr.x, pr.y | kind_bit};
-                have = 1;
-                const MinKey k{time_key(t), kPairClass | ((uint64_t)pr.x << 32) | kind_bit | pr.y};
-                if (key_less(k, best)) best = k;
+            uint2 pr = sep ? a.ov_pairs[p - n_cand] : a.cand[p];
+            bool present = true;
+            if (sep && a.gid_map_mask) present = gid_lookup(a, pr.x, &pr.x) && gid_lookup(a, pr.y, &pr.y);
+            if (present) {
+                const RecHead hh = load_head(a.rec, pr.x), hl = load_head(a.rec, pr.y);
+                const int32_t owner_col = max(hh.sx, hl.sx);
+                if (!sep || (owner_col >= a.col_lo && owner_col < a.col_hi)) {
+                    const DurHb A = load_body(a.rec, pr.x, hh);
+                    // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486): advanced by T - start = 0
+                    const DurHb B = advanced(load_body(a.rec, pr.y, hl), 0.0);
+                    const double delay = sep ? separate_time(A, B, a.padding) : collide_time(A, B);
+                    if (delay != delay) report_error(a.ctr, kFNan, hh.gid);
+                    n_sep += sep;
+                    const double t = a.T + delay;
+                    if (t < kHighTime) {
+                        const uint32_t kind_bit = sep ? 0u : kCollideBit;
+                        ev = PairEvent{t, hh.gid, hl.gid | kind_bit};
+                        have = 1;
+                        const MinKey k{time_key(t), kPairClass | ((uint64_t)hh.gid << 32) | kind_bit | hl.gid};
+                        if (key_less(k, best)) best = k;
+                    }
+                }
             }
         }
         // block-aggregated append: one global atomic per block-iteration
@@ -534,9 +658,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
         __syncthreads();
     }
     best = block_min(best);
+    const unsigned long long sep_tot = block_sum(n_sep);
     if (threadIdx.x == 0) {
         a.partial[a.n_partial_a + blockIdx.x] = best;
-        if (blockIdx.x == 0 && a.n_ov) atomicAdd(&a.ctr->n_separate, (unsigned long long)a.n_ov);
+        if (sep_tot) atomicAdd(&a.ctr->n_separate, sep_tot);
         __threadfence();
         s_last = atomicAdd(&a.ctr->done_blocks, 1u) == gridDim.x - 1 ? 1u : 0u;
     }
@@ -560,7 +685,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
         out.n_entries = c->n_entries; out.n_cells = c->n_cells; out.n_collide = c->n_collide; out.n_separate = c->n_separate;
         out.n_pair_events = c->n_pair_events; out.n_solitaire = c->n_solitaire; out.err_slot = c->err_slot;
         out.err_flags = c->err_flags; out.scan_ticket = c->scan_ticket; out.overflow_entries = c->overflow_entries;
-        out.done_blocks = c->done_blocks; out.diff_hi = 0; out.diff_lo = 0; out.n_sort_keys = 0;
+        out.done_blocks = c->done_blocks; out.n_local = c->n_local; out.overflow_send = c->overflow_send;
+        out.diff_hi = 0; out.diff_lo = 0; out.n_sort_keys = 0;
         a.result->ctr = out;
         __threadfence_system();
     }

@@ -13,11 +13,12 @@ struct alignas(16) Key128 {
 };
 
 // Reiterate events live in the state columns (reit flag + internal end_time); append their keys.
-__global__ void k_keys_solitaire(uint32_t n, const uint8_t* __restrict__ reit, const double* __restrict__ end, Key128* keys, Counters* ctr) {
+__global__ void k_keys_solitaire(uint32_t n, const uint8_t* __restrict__ reit, const double* __restrict__ end, const uint32_t* __restrict__ gid,
+                                 Key128* keys, Counters* ctr) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !reit[i]) return;
     const unsigned long long pos = warp_agg_claim(&ctr->n_sort_keys);
-    keys[pos] = Key128{(unsigned long long)i, time_key(end[i])};
+    keys[pos] = Key128{(unsigned long long)(gid ? gid[i] : i), time_key(end[i])};
 }
 __global__ void k_keys_pairs(uint32_t n_ev, const PairEvent* __restrict__ ev, Key128* keys, unsigned long long base) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,11 +192,11 @@ __global__ void k_decode_events(uint32_t n, const Key128* __restrict__ keys, con
     e.pad = 0;
     if (k.lo & kPairClass) {
         const uint32_t hi = (uint32_t)((k.lo >> 32) & 0x7fffffffu), lo = (uint32_t)(k.lo & 0x7fffffffu);
-        e.a = ids[hi];
-        e.b = ids[lo];
+        e.a = ids ? ids[hi] : hi;
+        e.b = ids ? ids[lo] : lo;
         e.kind = (k.lo & kCollideBit) ? 1u : 2u;  // CB200_EV_COLLIDE / CB200_EV_SEPARATE
     } else {
-        e.a = ids[(uint32_t)k.lo];
+        e.a = ids ? ids[(uint32_t)k.lo] : (uint32_t)k.lo;
         e.b = 0;
         e.kind = 0;  // CB200_EV_REITERATE
     }

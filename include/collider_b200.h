@@ -156,6 +156,25 @@ int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_
  * `vel` may be NULL (keep velocities); `end_time` is the HbVel.end_time installed when vel->end_time is NULL. */
 int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, cb200_step_result* out);
 
+/* ---- Spatial sharding across the GPUs of one box — one context per GPU / process ----------------
+ * Cell columns are split into `world` contiguous strips: rank d owns columns [col_bounds[d], col_bounds[d+1])
+ * (the first and last strips are open-ended).  Each rank keeps a fixed set of resident hitboxes (upload_state;
+ * ids must be < 2^31 - 1 and globally unique) and, every step, hands the 96-byte record of each resident to every
+ * rank whose strip its index rect touches.  A pair is solved by exactly one rank: the one whose strip holds the
+ * pair's owner cell (max of the two rect starts), so records only ever need to reach ranks at or right of their
+ * start column.  The exchange itself is done by the caller between the two calls below (NCCL over NVLink:
+ * torch.distributed in this repo, ncclSend/ncclRecv from a Rust host), then the global next event is the minimum of
+ * the per-rank results (allreduce-min on next_time, ties by the event key).
+ *   cb200_shard_begin : stage A on the residents + halo pack.  send_counts[d] = records for rank d, stored at
+ *                       send_base + d * send_stride_bytes; the caller delivers them into the peer's recv_base
+ *                       (contiguously, any order) and then calls
+ *   cb200_shard_finish: bins own + received records restricted to the own strip, candidate pairs, solves, min. */
+#define CB200_RECORD_BYTES 96
+int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* col_bounds /* world + 1 */);
+int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, uint64_t* send_counts /* [world] */,
+                      uint64_t* n_local, void** send_base, uint64_t* send_stride_bytes, void** recv_base, uint64_t* recv_cap_records);
+int cb200_shard_finish(cb200_ctx* ctx, uint64_t n_recv, cb200_step_result* out);
+
 /* Events queued by the last bulk step, sorted by the canonical order (time, class, hi id, kind, lo id)
  * (events.rs:60-68 with SURVEY.md §8c tie-break).  Copies events [offset, offset+cap) into buf. */
 int cb200_fetch_events(cb200_ctx* ctx, cb200_event* buf, uint64_t cap, uint64_t offset, uint64_t* n_out);
