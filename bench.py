@@ -115,7 +115,7 @@ def oracle_timing(scene_fn, n_sample: int, steps: int, warmup: int):
     return n_sample * done / el, (st["collide_solves"] + st["separate_solves"]) / el, el / done * 1e3, st
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -133,10 +133,22 @@ def run_reference(args):
         "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cores_available": os.cpu_count(),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: route everything else that native libraries print to fd 1 (e.g. NCCL's
+    # version banner) to stderr, and keep the real stdout for the result line
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        _main(real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -150,7 +162,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch
     import torch.distributed as dist
@@ -175,22 +187,43 @@ def main():
 
     n = args.n
     scene = make_workload(scenes, args.workload, n, rank, world)
-    eng = cb.Engine(scenes.CELL_WIDTH, scenes.PADDING, device=local_rank)
-    if args.grid:
-        eng.set_grid(*[int(v) for v in args.grid.split(",")])
-    eng.upload_state(**scene)
+    halo = {"sent": 0, "received": 0, "steps": 0}
+    if world == 1:
+        eng = cb.Engine(scenes.CELL_WIDTH, scenes.PADDING, device=local_rank)
+        if args.grid:
+            eng.set_grid(*[int(v) for v in args.grid.split(",")])
+        eng.upload_state(**scene)
+        step_fn = eng.bulk_update
+    else:
+        # spatial sharding: one column strip of the world per rank, NCCL halo exchange between the two
+        # phases of the step, global next event by an all-gather + min of the per-rank keys
+        sharding = importlib.import_module("collider-rs_b200.sharding")
+        side = math.sqrt(n / (1.0 if args.workload == "c3_dense" else 0.025))
+        bounds = sharding.strip_bounds(world, 0.0, side * world, scenes.CELL_WIDTH)
+        sh = sharding.ShardedEngine(cb, scenes.CELL_WIDTH, scenes.PADDING, local_rank, bounds, n * world, sharding.Exchange())
+        eng = sh.eng
+        if args.grid:
+            eng.set_grid(*[int(v) for v in args.grid.split(",")])
+        sh.upload_state(**scene)
+
+        def step_fn(T, end_time, **vel):
+            return sh.bulk_update(T, end_time, **vel)
+
     # first step: pairs already in contact at T = 0 come back as Collide events at T; they become the overlap set
     # (what add_hitbox's immediate-overlap list does in the reference, collider.rs:355-365)
-    res = eng.bulk_update(0.0, end_time=DT)
+    res = step_fn(0.0, end_time=DT)
     ev = eng.fetch_events()
     touching = ev[(ev["kind"] == cb.EV_COLLIDE) & (ev["time"] == 0.0)]
-    eng.set_overlaps(touching["a"], touching["b"])
+    ta, tb = touching["a"].copy(), touching["b"].copy()
+    # sharded: every rank keeps the overlapping pairs it owns (pairs whose owner cell drifts into another strip would
+    # have to be handed over by the host; over this run's 0.1-unit steps that is a vanishing fraction)
+    eng.set_overlaps(ta, tb)
     clock = [DT]  # the next step time is exactly the end_time installed by the previous step
 
     def device_step():
         T = clock[0]
         clock[0] = T + DT
-        return eng.bulk_update(T, end_time=clock[0])
+        return step_fn(T, end_time=clock[0])
 
     for _ in range(args.warmup):
         res = device_step()
@@ -221,7 +254,7 @@ def main():
     def e2e_step():
         T = clock[0]
         clock[0] = T + DT
-        r = eng.bulk_update(T, end_time=clock[0], vel_x=pvx.array, vel_y=pvy.array)
+        r = step_fn(T, end_time=clock[0], vel_x=pvx.array, vel_y=pvy.array)
         evs = eng.fetch_events()
         return r, evs
 
@@ -252,6 +285,7 @@ def main():
         lw, lh = eng.get_grid()
         n_slots = 1 << (lw + lh)
         # algorithmic bytes per launch of each kernel (DESIGN.md "bytes per unit")
+        stage_ms.setdefault("exchange", 0.0)
         alg = {
             "stage_a": 242.0 * n + 8.0 * E,
             "scan": 8.0 * n_slots,
@@ -284,13 +318,17 @@ def main():
                                         "frac": step_bytes / (dev_ms_max * 1e-3) / 1e9 / hbm_peak}},
             "clocks": sampler.summary(),
         }
+        if world > 1:
+            line["config"]["parallelism"] = f"spatial sharding: {world} column strips, NCCL halo exchange of 96-B records + all-gather min"
+            hs, hr = sh.halo_counts()
+            line["halo_records_last_step_rank0"] = {"sent": hs, "received": hr}
         if not args.no_cpu_baseline:
             n_sample = min(n, args.ref_sample)
             ups, sps, ms, st = oracle_timing(lambda m: make_workload(scenes, args.workload, m, 0, 1), n_sample, 3, 1)
             line["cpu_baseline"] = {"value": ups, "unit": UNIT, "cores": 1, "kind": "port", "pair_solves_per_s": sps,
                                     "sample": f"{n_sample} hitboxes of the same scene density, 3 bulk-equivalent steps (ascending set_hitbox_vel loop), single thread",
                                     "host_cores_available": os.cpu_count()}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

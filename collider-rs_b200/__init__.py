@@ -22,8 +22,8 @@ KIND_CIRCLE, KIND_RECT = 0, 1
 GROUP_NONE = 0xFFFFFFFF
 EV_REITERATE, EV_COLLIDE, EV_SEPARATE = 0, 1, 2
 E_ARG, E_CUDA, E_CONTRACT, E_STATE = -1, -2, -3, -4
-N_STAGES = 7
-STAGE_NAMES = ("pre", "stage_a", "scan", "scatter", "candidates", "solve", "tail")
+N_STAGES = 8
+STAGE_NAMES = ("pre", "stage_a", "exchange", "scan", "scatter", "candidates", "solve", "tail")
 INF = math.inf
 
 
@@ -83,7 +83,8 @@ EXPORTS = (
     "cb200_host_alloc", "cb200_host_free", "cb200_upload_state", "cb200_download_state", "cb200_set_overlaps",
     "cb200_bulk_update", "cb200_fetch_events", "cb200_fetch_candidate_pairs", "cb200_fetch_cell_entries",
     "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
-    "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_shard_begin", "cb200_shard_finish",
+    "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_set_stream", "cb200_shard_begin", "cb200_shard_finish",
+    "cb200_shard_result",
 )
 
 _lib = None
@@ -124,9 +125,11 @@ def load_library() -> C.CDLL:
     L.cb200_launch_count.restype = u64
     L.cb200_last_step_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), i32]
     L.cb200_reset_timing.argtypes = [vp]
-    L.cb200_shard_configure.argtypes = [vp, i32, i32, vp]
-    L.cb200_shard_begin.argtypes = [vp, dbl, C.POINTER(VelView), dbl, vp, C.POINTER(u64), C.POINTER(vp), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)]
-    L.cb200_shard_finish.argtypes = [vp, u64, C.POINTER(StepResult)]
+    L.cb200_shard_configure.argtypes = [vp, i32, i32, vp, u64]
+    L.cb200_set_stream.argtypes = [vp, vp]
+    L.cb200_shard_begin.argtypes = [vp, dbl, C.POINTER(VelView), dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
+    L.cb200_shard_finish.argtypes = [vp, C.POINTER(vp)]
+    L.cb200_shard_result.argtypes = [vp, C.POINTER(StepResult)]
     _lib = L
     return L
 
@@ -252,30 +255,37 @@ class Engine:
         return res
 
     # ---- sharded step (one context per GPU; the exchange between begin and finish is the caller's, see sharding.py) ----
-    def shard_configure(self, rank: int, world: int, col_bounds):
+    def shard_configure(self, rank: int, world: int, col_bounds, id_space: int):
         b = np.ascontiguousarray(col_bounds, dtype=np.int32)
         if b.shape != (world + 1,):
             raise ValueError("col_bounds must have world + 1 entries")
-        self._check(self._L.cb200_shard_configure(self._h, rank, world, _ptr(b)))
+        self._check(self._L.cb200_shard_configure(self._h, rank, world, _ptr(b), id_space))
         self.rank, self.world = rank, world
 
+    def set_stream(self, cuda_stream: int):
+        self._check(self._L.cb200_set_stream(self._h, C.c_void_p(cuda_stream)))
+
     def shard_begin(self, time: float, end_time: float = INF, vel_x=None, vel_y=None, rsz_x=None, rsz_y=None, end_time_arr=None) -> dict:
+        """Asynchronous front half.  Returns the exchange buffers: slab d of send_ptr goes to slab `rank` of rank d's recv_ptr."""
         arrs = [vel_x, vel_y, rsz_x, rsz_y, end_time_arr]
-        counts = np.zeros(self.world, dtype=np.uint64)
-        n_local, stride, cap = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        per_peer = C.c_uint64()
         send, recv = C.c_void_p(), C.c_void_p()
         v = None
         if not all(a is None for a in arrs):
-            keep = [None if a is None else _col(a, np.float64, self.n) for a in arrs]
-            v = C.byref(VelView(*[None if a is None else a.ctypes.data for a in keep]))
-        self._check(self._L.cb200_shard_begin(self._h, time, v, end_time, _ptr(counts), C.byref(n_local), C.byref(send), C.byref(stride),
-                                              C.byref(recv), C.byref(cap)))
-        return dict(send_counts=counts, n_local=n_local.value, send_ptr=send.value, send_stride=stride.value, recv_ptr=recv.value,
-                    recv_cap=cap.value)
+            self._keep = [None if a is None else _col(a, np.float64, self.n) for a in arrs]  # alive until the step completes
+            v = C.byref(VelView(*[None if a is None else a.ctypes.data for a in self._keep]))
+        self._check(self._L.cb200_shard_begin(self._h, time, v, end_time, C.byref(send), C.byref(recv), C.byref(per_peer)))
+        return dict(send_ptr=send.value, recv_ptr=recv.value, bytes_per_peer=per_peer.value)
 
-    def shard_finish(self, n_recv: int) -> StepResult:
+    def shard_finish(self) -> int:
+        """Asynchronous back half; returns the device address of this rank's (time key, tie) minimum (2 x u64)."""
+        key = C.c_void_p()
+        self._check(self._L.cb200_shard_finish(self._h, C.byref(key)))
+        return key.value
+
+    def shard_result(self) -> StepResult:
         res = StepResult()
-        rc = self._L.cb200_shard_finish(self._h, n_recv, C.byref(res))
+        rc = self._L.cb200_shard_result(self._h, C.byref(res))
         self.last_result = res
         self._check(rc)
         return res

@@ -46,7 +46,7 @@ struct DevBuf {
     }
 };
 
-enum { ST_PRE = 0, ST_STAGE_A, ST_SCAN, ST_SCATTER, ST_CAND, ST_SOLVE, ST_TAIL, ST_COUNT };
+enum { ST_PRE = 0, ST_STAGE_A, ST_EXCH, ST_SCAN, ST_SCATTER, ST_CAND, ST_SOLVE, ST_TAIL, ST_COUNT };
 }  // namespace
 
 struct cb200_ctx {
@@ -68,13 +68,14 @@ struct cb200_ctx {
     // sharding
     bool sharded = false;
     ShardGeom shard{};
-    DevBuf<HbRec> send;      // [world][cap_send]
+    DevBuf<HbRec> send;      // [world][slab]: record 0 of each slab is its header
     DevBuf<uint32_t> send_count;
-    uint32_t cap_send = 0;
-    DevBuf<unsigned long long> gid_map;
-    uint32_t gid_map_mask = 0;
-    uint32_t n_local = 0;    // own records in the visitor table (last shard_begin)
-    bool shard_open = false; // between shard_begin and shard_finish
+    uint32_t slab = 0;       // records per slab, header included
+    MinKey* d_key = nullptr; // local minimum of the last step (device), input of the all-gather min
+    bool own_stream = true;
+    DevBuf<uint32_t> vmap;   // gid -> record index (direct-addressed over the id space)
+    uint64_t id_space = 0;
+    int shard_phase = 0;     // 0 idle, 1 after shard_begin, 2 after shard_finish (result pending)
     double shard_T = 0;
 
     GridGeom geom{0, 0};
@@ -244,6 +245,7 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
     if ((e = cudaMalloc(&c->d_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&c->d_key, sizeof(MinKey))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaHostAlloc(&c->h_res, sizeof(StepResultDev), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer((void**)&c->d_res, c->h_res, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     for (auto& ev : c->ev_t)
@@ -260,17 +262,18 @@ void cb200_destroy(cb200_ctx* c) {
     for (auto& b : c->col) b.release();
     for (auto& b : c->nvel) b.release();
     c->kind.release(); c->reit.release(); c->group.release(); c->mask.release(); c->ids.release(); c->rec.release();
-    c->gid.release(); c->send.release(); c->send_count.release(); c->gid_map.release();
+    c->gid.release(); c->send.release(); c->send_count.release(); c->vmap.release();
     c->slots.release(); c->tile_state.release(); c->entries.release();
     c->ov_pairs.release(); c->ov_table.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
     c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); c->ev_out.release(); c->cand.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
+    if (c->d_key) cudaFree(c->d_key);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->pinned_stage) cudaFreeHost(c->pinned_stage);
     for (auto& ev : c->ev_t)
         if (ev) cudaEventDestroy(ev);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream && c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -335,16 +338,20 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
         // sharded tables: gid = id (ids must be dense enough to fit 31 bits); visitor table and halo buffers sized here
         std::vector<uint32_t> g(n);
         for (size_t i = 0; i < n; ++i) {
-            if (v->id[i] >= 0x7fffffffull) return fail(ctx, CB200_E_ARG, "sharded mode requires ids < 2^31 - 1");
+            if (v->id[i] >= ctx->id_space) return fail(ctx, CB200_E_ARG, "sharded mode requires ids < id_space");
             g[i] = (uint32_t)v->id[i];
         }
         CU(ctx->gid.reserve(cap));
         if (n) CU(cudaMemcpyAsync(ctx->gid.p, g.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        CU(ctx->rec.reserve(2 * n + 65536));
-        ctx->cap_send = (uint32_t)std::max<size_t>(n / 8, 65536);
-        CU(ctx->send.reserve((size_t)ctx->cap_send * ctx->shard.world));
+        // per-peer slab: header + room for n/64 (>= 4095) halo records; own region of the visitor table = n records
+        if (ctx->slab == 0) ctx->slab = (uint32_t)std::max<size_t>(n / 64, 4095) + 1;
+        CU(ctx->rec.reserve(n + (size_t)ctx->slab * ctx->shard.world));
+        CU(ctx->send.reserve((size_t)ctx->slab * ctx->shard.world));
         CU(ctx->send_count.reserve(ctx->shard.world));
+        CU(ctx->vmap.reserve(ctx->id_space));
+        CU(cudaMemsetAsync(ctx->vmap.p, 0xff, ctx->id_space * 4, ctx->stream));
+        CU(cudaMemsetAsync(ctx->rec.p + n, 0, (size_t)ctx->slab * ctx->shard.world * sizeof(HbRec), ctx->stream));
     }
     choose_geom(ctx, v);
     CU(cudaStreamSynchronize(ctx->stream));
@@ -475,8 +482,8 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     a.partial = ctx->partial.p;
     a.send = ctx->send.p;
     a.send_count = ctx->send_count.p;
-    a.cap_send = ctx->cap_send;
-    a.cap_vis = (uint32_t)std::min<size_t>(ctx->rec.cap, 0xffffffffu);
+    a.slab = ctx->slab;
+    a.vmap = (ctx->sharded && ctx->n_ov) ? ctx->vmap.p : nullptr;
     if (n) {
         if (ctx->sharded) k_stage_a<true><<<ctx->grid_a, kThreads, 0, ctx->stream>>>(a, ctx->shard);
         else k_stage_a<false><<<ctx->grid_a, kThreads, 0, ctx->stream>>>(a, whole_world());
@@ -484,35 +491,39 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     } else {
         CU(cudaMemsetAsync(ctx->partial.p, 0xff, sizeof(MinKey) * ctx->grid_a, ctx->stream));
     }
-    CU(cudaEventRecord(ctx->ev_t[ST_SCAN], ctx->stream));
+    if (ctx->sharded) {
+        k_slab_headers<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->send.p, ctx->send_count.p, ctx->slab, ctx->shard.world, ctx->shard.rank);
+        ctx->launches += 1;
+    }
+    CU(cudaEventRecord(ctx->ev_t[ST_EXCH], ctx->stream));
     return CB200_OK;
 }
 
-// Back half over the visitor table: (count,) scan, scatter, candidates, solve + min-reduce + result.
-static int enqueue_back(cb200_ctx* ctx, uint32_t n_vis, double time) {
+// Back half over the visitor table: (index received records,) scan, scatter, candidates, solve + min-reduce + result.
+// recount = the own records' cells must be counted again (re-run after a buffer grew).
+static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     const GridGeom g = ctx->geom;
     const uint32_t n_slots = g.n_slots();
     const ShardGeom sh = ctx->sharded ? ctx->shard : whole_world();
-    const uint32_t grid_v = std::max<uint32_t>(1, std::min<uint32_t>((n_vis + kThreads - 1) / kThreads, ctx->sm_count * 8));
+    const VisSpace vs{ctx->n, ctx->slab, sh.world};
+    const uint32_t n_vis_max = ctx->sharded ? ctx->n + ctx->slab * (uint32_t)sh.world : ctx->n;
+    const uint32_t grid_v = std::max<uint32_t>(1, std::min<uint32_t>((n_vis_max + kThreads - 1) / kThreads, ctx->sm_count * 8));
     const bool use_map = ctx->sharded && ctx->n_ov;
+    CU(cudaEventRecord(ctx->ev_t[ST_SCAN], ctx->stream));
     if (ctx->sharded) {
-        if (use_map) {
-            uint32_t cap = 1024;
-            while (cap < 2 * std::max<uint32_t>(n_vis, 1)) cap <<= 1;
-            CU(ctx->gid_map.reserve(cap));
-            ctx->gid_map_mask = cap - 1;
-            CU(cudaMemsetAsync(ctx->gid_map.p, 0xff, (size_t)cap * 8, ctx->stream));
-        }
-        if (n_vis) {
-            k_count_visitors<<<grid_v, kThreads, 0, ctx->stream>>>(n_vis, ctx->rec.p, ctx->slots.p, g, sh, ctx->gid_map.p, use_map ? ctx->gid_map_mask : 0u);
-            ctx->launches += 1;
-        }
+        const uint32_t work = recount ? n_vis_max : ctx->slab * (uint32_t)sh.world;
+        const uint32_t grid_i = std::max<uint32_t>(1, std::min<uint32_t>((work + kThreads - 1) / kThreads, ctx->sm_count * 8));
+        uint32_t* vmap = use_map ? ctx->vmap.p : nullptr;
+        if (recount) k_index_visitors<true><<<grid_i, kThreads, 0, ctx->stream>>>(ctx->rec.p, vs, ctx->d_ctr, ctx->slots.p, g, sh.col_lo, sh.col_hi, vmap);
+        else k_index_visitors<false><<<grid_i, kThreads, 0, ctx->stream>>>(ctx->rec.p, vs, ctx->d_ctr, ctx->slots.p, g, sh.col_lo, sh.col_hi, vmap);
+        ctx->launches += 1;
     }
     k_scan_slots<<<n_slots / kScanTile, kThreads, 0, ctx->stream>>>(ctx->slots.p, n_slots, ctx->tile_state.p, ctx->d_ctr);
     CU(cudaEventRecord(ctx->ev_t[ST_SCATTER], ctx->stream));
-    if (n_vis) {
-        k_scatter<<<grid_v, kThreads, 0, ctx->stream>>>(n_vis, ctx->rec.p, ctx->slots.p, ctx->entries.p, (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu), g,
-                                                        sh.col_lo, sh.col_hi, ctx->d_ctr);
+    if (n_vis_max) {
+        const uint32_t cap_e = (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu);
+        if (ctx->sharded) k_scatter<true><<<grid_v, kThreads, 0, ctx->stream>>>(ctx->n, ctx->rec.p, vs, ctx->slots.p, ctx->entries.p, cap_e, g, sh.col_lo, sh.col_hi, ctx->d_ctr);
+        else k_scatter<false><<<grid_v, kThreads, 0, ctx->stream>>>(ctx->n, ctx->rec.p, vs, ctx->slots.p, ctx->entries.p, cap_e, g, sh.col_lo, sh.col_hi, ctx->d_ctr);
         ctx->launches += 1;
     }
     CU(cudaEventRecord(ctx->ev_t[ST_CAND], ctx->stream));
@@ -541,8 +552,10 @@ static int enqueue_back(cb200_ctx* ctx, uint32_t n_vis, double time) {
     sv.partial = ctx->partial.p;
     sv.n_partial_a = ctx->grid_a;
     sv.result = ctx->d_res;
-    sv.gid_map = ctx->gid_map.p;
-    sv.gid_map_mask = use_map ? ctx->gid_map_mask : 0u;
+    sv.local_key = ctx->d_key;
+    sv.vmap = use_map ? ctx->vmap.p : nullptr;
+    sv.id_space = (uint32_t)ctx->id_space;
+    sv.vs = vs;
     sv.col_lo = sh.col_lo;
     sv.col_hi = sh.col_hi;
     k_solve<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(sv);
@@ -647,7 +660,7 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
     bool again = true;
     for (int attempt = 0; attempt < 4 && again; ++attempt) {
         if ((rc = enqueue_front(ctx, time, attempt == 0, nv, end_time)) != CB200_OK) return rc;
-        if ((rc = enqueue_back(ctx, ctx->n, time)) != CB200_OK) return rc;
+        if ((rc = enqueue_back(ctx, time, false)) != CB200_OK) return rc;
         if ((rc = complete_step(ctx, time, &again)) != CB200_OK) return rc;
         if (ctx->last.ctr.err_flags) break;
     }
@@ -659,8 +672,9 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
 }
 
 // ---- sharded step -------------------------------------------------------------------------
-int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* col_bounds) {
+int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* col_bounds, uint64_t id_space) {
     if (!ctx || !col_bounds) return CB200_E_ARG;
+    if (id_space == 0 || id_space >= 0x7fffffffull) return fail(ctx, CB200_E_ARG, "id_space must be in 1 .. 2^31 - 2 (ids of all ranks are < id_space)");
     if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world) return fail(ctx, CB200_E_ARG, "bad rank / world");
     for (int d = 0; d < world; ++d)
         if (!(col_bounds[d] < col_bounds[d + 1])) return fail(ctx, CB200_E_ARG, "strip bounds must be strictly ascending");
@@ -673,14 +687,26 @@ int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* co
     g.col_lo = g.bounds[rank];
     g.col_hi = g.bounds[rank + 1];
     ctx->shard = g;
+    ctx->id_space = id_space;
     ctx->sharded = true;
     ctx->have_state = false;  // the table must be (re-)uploaded: sharded tables carry gid = id
     return CB200_OK;
 }
 
-int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, uint64_t* send_counts, uint64_t* n_local,
-                      void** send_base, uint64_t* send_stride_bytes, void** recv_base, uint64_t* recv_cap_records) {
-    if (!ctx || !send_counts) return CB200_E_ARG;
+int cb200_set_stream(cb200_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return CB200_E_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return CB200_OK;
+}
+
+// Asynchronous: enqueues stage A + halo pack on the context's stream and returns the buffers of the exchange.
+int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, void** send_base, void** recv_base,
+                      uint64_t* bytes_per_peer) {
+    if (!ctx) return CB200_E_ARG;
     if (!ctx->sharded) return fail(ctx, CB200_E_STATE, "cb200_shard_configure first");
     if (!ctx->have_state) return fail(ctx, CB200_E_STATE, "shard_begin before upload_state");
     if (!(time < 1e50)) return fail(ctx, CB200_E_ARG, "requires time < 1e50");
@@ -691,60 +717,54 @@ int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
     if (rc != CB200_OK) return rc;
     if ((rc = prepare_buffers(ctx)) != CB200_OK) return rc;
     if ((rc = enqueue_front(ctx, time, true, nv, end_time)) != CB200_OK) return rc;
-    std::vector<uint32_t> cnt(ctx->shard.world);
-    Counters c;
-    CU(cudaMemcpyAsync(cnt.data(), ctx->send_count.p, sizeof(uint32_t) * ctx->shard.world, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&c, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaGetLastError());
-    if (c.overflow_send) return fail(ctx, CB200_E_STATE, "halo send buffer or visitor table overflow (strips too thin for this scene)");
-    for (int d = 0; d < ctx->shard.world; ++d) send_counts[d] = cnt[d];
-    ctx->n_local = c.n_local;
-    ctx->shard_open = true;
+    ctx->shard_phase = 1;
     ctx->shard_T = time;
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, ctx->ev_t[ST_PRE], ctx->ev_t[ST_STAGE_A]) == cudaSuccess) { ctx->stage_ms_sum[ST_PRE] += ms; ctx->total_ms_sum += ms; }
-    if (cudaEventElapsedTime(&ms, ctx->ev_t[ST_STAGE_A], ctx->ev_t[ST_SCAN]) == cudaSuccess) { ctx->stage_ms_sum[ST_STAGE_A] += ms; ctx->total_ms_sum += ms; }
-    if (n_local) *n_local = c.n_local;
     if (send_base) *send_base = ctx->send.p;
-    if (send_stride_bytes) *send_stride_bytes = (uint64_t)ctx->cap_send * sizeof(HbRec);
-    if (recv_base) *recv_base = ctx->rec.p + c.n_local;
-    if (recv_cap_records) *recv_cap_records = ctx->rec.cap - c.n_local;
+    if (recv_base) *recv_base = ctx->rec.p + ctx->n;
+    if (bytes_per_peer) *bytes_per_peer = (uint64_t)ctx->slab * sizeof(HbRec);
     return CB200_OK;
 }
 
-int cb200_shard_finish(cb200_ctx* ctx, uint64_t n_recv, cb200_step_result* out) {
+// Asynchronous: enqueues the back half (the exchange must already be ordered before it on the same stream).
+// *local_key receives the device address of this rank's (time key, tie) minimum — 16 bytes, the all-gather input.
+int cb200_shard_finish(cb200_ctx* ctx, void** local_key) {
     if (!ctx) return CB200_E_ARG;
-    if (!ctx->shard_open) return fail(ctx, CB200_E_STATE, "shard_finish without shard_begin");
-    if ((uint64_t)ctx->n_local + n_recv > ctx->rec.cap) return fail(ctx, CB200_E_ARG, "received more records than the visitor table holds");
+    if (ctx->shard_phase != 1) return fail(ctx, CB200_E_STATE, "shard_finish without shard_begin");
     CU(cudaSetDevice(ctx->device));
-    const uint32_t n_vis = ctx->n_local + (uint32_t)n_recv;
+    int rc = enqueue_back(ctx, ctx->shard_T, false);
+    if (rc != CB200_OK) return rc;
+    ctx->shard_phase = 2;
+    if (local_key) *local_key = ctx->d_key;
+    return CB200_OK;
+}
+
+// Synchronous: waits for the step; re-runs the back half if a buffer had to grow; fills the (local) result.
+int cb200_shard_result(cb200_ctx* ctx, cb200_step_result* out) {
+    if (!ctx) return CB200_E_ARG;
+    if (ctx->shard_phase != 2) return fail(ctx, CB200_E_STATE, "shard_result without shard_finish");
+    CU(cudaSetDevice(ctx->device));
+    ctx->shard_phase = 0;
     int rc;
-    bool again = true;
-    CU(cudaEventRecord(ctx->ev_t[ST_SCAN], ctx->stream));
-    for (int attempt = 0; attempt < 4 && again; ++attempt) {
-        if (attempt > 0) {
-            // re-run of the back half only: slot table and counters are rebuilt, the visitor table is intact
-            const uint32_t n_slots = ctx->geom.n_slots();
-            Counters keep = ctx->last.ctr;
-            CU(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_slots * 4, ctx->stream));
-            CU(cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)(n_slots / kScanTile) * 8, ctx->stream));
-            Counters z{};
-            z.err_slot = keep.err_slot;
-            z.err_flags = keep.err_flags;
-            z.n_solitaire = keep.n_solitaire;
-            z.n_local = keep.n_local;
-            CU(cudaMemcpyAsync(ctx->d_ctr, &z, sizeof(Counters), cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            CU(cudaEventRecord(ctx->ev_t[ST_SCAN], ctx->stream));
-        }
-        if ((rc = enqueue_back(ctx, n_vis, ctx->shard_T)) != CB200_OK) return rc;
+    bool again = false;
+    if ((rc = complete_step(ctx, ctx->shard_T, &again)) != CB200_OK) return rc;
+    if (ctx->last.ctr.overflow_send) return fail(ctx, CB200_E_STATE, "halo slab overflow: more records for one peer than the slab holds (strips too thin for this scene)");
+    accumulate_timing(ctx, ST_PRE, true);
+    for (int attempt = 0; attempt < 3 && again && !ctx->last.ctr.err_flags; ++attempt) {
+        // re-run of the back half only: slot table and counters are rebuilt, the visitor table is intact
+        const uint32_t n_slots = ctx->geom.n_slots();
+        const Counters keep = ctx->last.ctr;
+        Counters z{};
+        z.err_slot = keep.err_slot;
+        z.err_flags = keep.err_flags;
+        z.n_solitaire = keep.n_solitaire;
+        z.n_local = keep.n_local;
+        CU(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_slots * 4, ctx->stream));
+        CU(cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)(n_slots / kScanTile) * 8, ctx->stream));
+        CU(cudaMemcpy(ctx->d_ctr, &z, sizeof(Counters), cudaMemcpyHostToDevice));
+        if ((rc = enqueue_back(ctx, ctx->shard_T, true)) != CB200_OK) return rc;
         if ((rc = complete_step(ctx, ctx->shard_T, &again)) != CB200_OK) return rc;
-        if (ctx->last.ctr.err_flags) break;
     }
-    ctx->shard_open = false;
     if (again && !ctx->last.ctr.err_flags) return fail(ctx, CB200_E_STATE, "step buffers failed to converge");
-    accumulate_timing(ctx, ST_SCAN, false);
     ctx->timed_steps += 1;
     ctx->timing_valid = true;
     return fill_result(ctx, out);

@@ -43,11 +43,34 @@ struct StepArgs {
     GridGeom geom;
     Counters* ctr;
     MinKey* partial;  // [gridDim.x] solitaire minima
-    // sharded only
-    HbRec* send;           // [world][cap_send] records for the other ranks
+    // sharded only: per-peer slabs of `slab` records each; record 0 of a slab is its header (first word = count)
+    HbRec* send;           // [world][slab]
     uint32_t* send_count;  // [world]
-    uint32_t cap_send, cap_vis;
+    uint32_t slab;
+    uint32_t* vmap;        // gid -> record index of this step (direct-addressed; null when there are no overlapping pairs)
 };
+
+// Sharded visitor index space: the own records kept for this strip are compacted at rec[0, n_local); the records
+// received from rank d sit in rec[n_own + d * slab + 1 ...] behind that slab's header.
+struct VisSpace {
+    uint32_t n_own;  // capacity of the own region (= residents)
+    uint32_t slab;   // records per slab including the header
+    int world;
+};
+__device__ __forceinline__ uint32_t slab_count(const HbRec* rec, const VisSpace& vs, int d) {
+    return __ldg(reinterpret_cast<const unsigned int*>(rec + vs.n_own + (size_t)d * vs.slab));
+}
+// i in [0, n_local + world * slab) -> record index, or false for headers / unused slab tail
+__device__ __forceinline__ bool vis_record(const HbRec* rec, const VisSpace& vs, uint32_t n_local, uint32_t i, uint32_t* v) {
+    if (i < n_local) {
+        *v = i;
+        return true;
+    }
+    const uint32_t j = i - n_local, d = j / vs.slab, k = j % vs.slab;
+    if (k == 0 || k - 1 >= slab_count(rec, vs, (int)d)) return false;
+    *v = vs.n_own + j;
+    return true;
+}
 
 __device__ __forceinline__ bool is_finite(double x) { return fabs(x) < cb_inf(); }
 
@@ -177,10 +200,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
                         rec.sx = sx; rec.sy = sy;
                         rec.span = (uint32_t)nx | ((uint32_t)ny << 16);
                         binned = true;
-                        if (!SHARDED) {
-                            for (int32_t x = sx; x != ex; ++x)
-                                for (int32_t y = sy; y != ey; ++y) atomicAdd(&a.slot_count[a.geom.slot(x, y)], 1u);
-                        }
+                        // cell count (sharded: only the cells inside the own strip)
+                        const int32_t x0 = SHARDED ? max(sx, sh.col_lo) : sx, x1 = SHARDED ? min(ex, sh.col_hi) : ex;
+                        for (int32_t x = x0; x < x1; ++x)
+                            for (int32_t y = sy; y != ey; ++y) atomicAdd(&a.slot_count[a.geom.slot(x, y)], 1u);
                     }
                 }
             }
@@ -216,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
                         keep_local = 1;
                     } else {
                         const uint32_t pos = warp_agg_claim32(&a.send_count[d]);
-                        if (pos < a.cap_send) store_rec(a.send + (size_t)d * a.cap_send + pos, rec);
+                        if (pos + 1 < a.slab) store_rec(a.send + (size_t)d * a.slab + 1 + pos, rec);
                         else a.ctr->overflow_send = 1u;
                     }
                 }
@@ -237,8 +260,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
                 __syncthreads();
                 const uint32_t pos = s_base + off;
                 if (keep_local) {
-                    if (pos < a.cap_vis) store_rec(a.rec + pos, rec);
-                    else a.ctr->overflow_send = 1u;
+                    store_rec(a.rec + pos, rec);  // pos < n always
+                    if (a.vmap) a.vmap[rec.gid] = pos;
                 }
                 __syncthreads();
             }
@@ -252,25 +275,33 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
     }
 }
 
-// Sharded: count the cells of every visitor record (own + received) that fall into this rank's strip, and index
-// the records by gid for the overlapping-pair lookups.
-__global__ void __launch_bounds__(kThreads) k_count_visitors(uint32_t n_vis, const HbRec* __restrict__ vis, uint32_t* slot_count, GridGeom geom,
-                                                             ShardGeom sh, unsigned long long* gid_map, uint32_t gid_map_mask) {
+// Sharded: publish the per-peer record counts in the slab headers (one thread per rank) before the exchange.
+__global__ void k_slab_headers(HbRec* send, const uint32_t* __restrict__ send_count, uint32_t slab, int world, int rank) {
+    const int d = threadIdx.x;
+    if (d >= world) return;
+    const uint32_t c = d == rank ? 0u : min(send_count[d], slab - 1u);
+    *reinterpret_cast<unsigned int*>(send + (size_t)d * slab) = c;
+}
+
+// Sharded, after the exchange: count the strip cells of the RECEIVED records (the own ones were counted in stage A;
+// COUNT_OWN re-counts them too — used when a step is re-run after a buffer grew), and index them by gid for the
+// overlapping-pair lookups.
+template <bool COUNT_OWN>
+__global__ void __launch_bounds__(kThreads) k_index_visitors(const HbRec* __restrict__ rec, VisSpace vs, const Counters* ctr, uint32_t* slot_count,
+                                                             GridGeom geom, int32_t col_lo, int32_t col_hi, uint32_t* vmap) {
+    const uint32_t n_local = ctr->n_local;
+    const uint32_t total = n_local + (uint32_t)vs.world * vs.slab;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n_vis; v += stride) {
-        const RecHead h = load_head(vis, v);
-        const int32_t x0 = max(h.sx, sh.col_lo), x1 = min(h.ex, sh.col_hi);
+    const uint32_t first = COUNT_OWN ? 0u : n_local;
+    for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        uint32_t v;
+        if (!vis_record(rec, vs, n_local, i, &v)) continue;
+        const RecHead h = load_head(rec, v);
+        if (!(h.kgb & 2u)) continue;
+        const int32_t x0 = max(h.sx, col_lo), x1 = min(h.ex, col_hi);
         for (int32_t x = x0; x < x1; ++x)
             for (int32_t y = h.sy; y != h.ey; ++y) atomicAdd(&slot_count[geom.slot(x, y)], 1u);
-        if (gid_map_mask) {
-            uint32_t p = (uint32_t)mix64(h.gid) & gid_map_mask;
-            const unsigned long long val = ((unsigned long long)h.gid << 32) | v;
-            for (;;) {
-                const unsigned long long prev = atomicCAS(&gid_map[p], kKeyMax, val);
-                if (prev == kKeyMax) break;
-                p = (p + 1) & gid_map_mask;
-            }
-        }
+        if (vmap && i >= n_local) vmap[h.gid] = v;  // own records were indexed by stage A
     }
 }
 
@@ -383,10 +414,15 @@ struct alignas(32) CellEntry {
 static_assert(sizeof(CellEntry) == 32, "CellEntry must be one sector");
 constexpr uint32_t kSlotMask = (1u << 26) - 1u;
 
-__global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n_vis, const HbRec* __restrict__ rec, uint32_t* offsets, CellEntry* entries,
+template <bool SHARDED>
+__global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const HbRec* __restrict__ rec, VisSpace vs, uint32_t* offsets, CellEntry* entries,
                                                       uint32_t cap_entries, GridGeom geom, int32_t col_lo, int32_t col_hi, Counters* ctr) {
+    const uint32_t n_local = SHARDED ? ctr->n_local : n;
+    const uint32_t total = SHARDED ? n_local + (uint32_t)vs.world * vs.slab : n;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vis; i += stride) {
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
+        uint32_t i = j;
+        if (SHARDED && !vis_record(rec, vs, n_local, j, &i)) continue;
         const RecHead h = load_head(rec, i);
         if (!(h.kgb & 2u)) continue;
         const int4 lo4 = make_int4(h.sx, h.sy, h.ex, h.ey);
@@ -590,23 +626,28 @@ struct SolveArgs {
     MinKey* partial;         // [n_partial_a + gridDim.x]: stage A's minima, then this kernel's
     uint32_t n_partial_a;
     StepResultDev* result;   // mapped host memory
+    MinKey* local_key;       // device copy of the local minimum (sharded: input of the all-gather min)
     // sharded: overlapping pairs are looked up by gid; only the owner-column rank solves them
-    const unsigned long long* gid_map;
-    uint32_t gid_map_mask;   // 0 = one device (gid == record index)
+    const uint32_t* vmap;    // gid -> record index (entries may be stale: validated); null = one device (gid == record index)
+    uint32_t id_space;
+    VisSpace vs;
     int32_t col_lo, col_hi;
 };
 
-__device__ __forceinline__ bool gid_lookup(const SolveArgs& a, uint32_t gid, uint32_t* vidx) {
-    uint32_t p = (uint32_t)mix64(gid) & a.gid_map_mask;
-    for (;;) {
-        const unsigned long long k = __ldg(a.gid_map + p);
-        if (k == kKeyMax) return false;
-        if ((uint32_t)(k >> 32) == gid) {
-            *vidx = (uint32_t)k;
-            return true;
-        }
-        p = (p + 1) & a.gid_map_mask;
+// A vmap entry is trusted only if it names a record slot that is live in THIS step and that record carries the gid.
+__device__ __forceinline__ bool gid_lookup(const SolveArgs& a, uint32_t n_local, uint32_t gid, uint32_t* vidx) {
+    if (gid >= a.id_space) return false;
+    const uint32_t v = __ldg(a.vmap + gid);
+    if (v >= n_local) {
+        if (v < a.vs.n_own) return false;
+        const uint32_t j = v - a.vs.n_own;
+        if (j >= (uint32_t)a.vs.world * a.vs.slab) return false;
+        const uint32_t d = j / a.vs.slab, k = j % a.vs.slab;
+        if (k == 0 || k - 1 >= slab_count(a.rec, a.vs, (int)d)) return false;
     }
+    if (__ldg(reinterpret_cast<const unsigned int*>(a.rec + v) + 3) != gid) return false;
+    *vidx = v;
+    return true;
 }
 
 __global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
@@ -616,6 +657,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
     unsigned long long n_sep = 0;
     const uint32_t n_cand = (uint32_t)min((unsigned long long)a.cap_cand, a.ctr->n_collide);
     const uint32_t total = n_cand + a.n_ov;
+    const uint32_t n_local = a.ctr->n_local;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
         const uint32_t p = base + threadIdx.x;
@@ -625,7 +667,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
             const bool sep = p >= n_cand;
             uint2 pr = sep ? a.ov_pairs[p - n_cand] : a.cand[p];
             bool present = true;
-            if (sep && a.gid_map_mask) present = gid_lookup(a, pr.x, &pr.x) && gid_lookup(a, pr.y, &pr.y);
+            if (sep && a.vmap) present = gid_lookup(a, n_local, pr.x, &pr.x) && gid_lookup(a, n_local, pr.y, &pr.y);
             if (present) {
                 const RecHead hh = load_head(a.rec, pr.x), hl = load_head(a.rec, pr.y);
                 const int32_t owner_col = max(hh.sx, hl.sx);
@@ -680,6 +722,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
     if (threadIdx.x == 0) {
         a.result->next_time = (best.t == kKeyMax && best.tie == kKeyMax) ? cb_inf() : key_time(best.t);
         a.result->next_tie = best.tie;
+        if (a.local_key) *a.local_key = best;
         const volatile Counters* c = a.ctr;
         Counters out;
         out.n_entries = c->n_entries; out.n_cells = c->n_cells; out.n_collide = c->n_collide; out.n_separate = c->n_separate;

@@ -41,6 +41,32 @@ def event_key(next_time: float, kind: int, a: int, b: int):
     return (next_time, 1, a, 1 if kind == 1 else 0, b)
 
 
+KEY_MAX = (1 << 64) - 1
+PAIR_CLASS = 1 << 63
+COLLIDE_BIT = 1 << 31
+
+
+def key_to_time(tkey: int) -> float:
+    """Inverse of the device's order-preserving u64 image of an f64 (common.cuh time_key)."""
+    bits = (tkey & 0x7FFFFFFFFFFFFFFF) if (tkey >> 63) else (~tkey & KEY_MAX)
+    return struct.unpack("<d", struct.pack("<Q", bits))[0]
+
+
+def decode_key(tkey: int, tie: int):
+    """(time, kind, a, b) of a device MinKey; kind None when the queue is empty."""
+    if tkey == KEY_MAX and tie == KEY_MAX:
+        return (math.inf, None, 0, 0)
+    t = key_to_time(tkey)
+    if tie & PAIR_CLASS:
+        return (t, 1 if tie & COLLIDE_BIT else 2, (tie >> 32) & 0x7FFFFFFF, tie & 0x7FFFFFFF)
+    return (t, 0, tie & 0xFFFFFFFF, 0)
+
+
+def min_key(rows):
+    """Lexicographic minimum of (time key, tie) rows given as signed int64 pairs (the all-gather output)."""
+    return min(((int(a) & KEY_MAX), (int(b) & KEY_MAX)) for a, b in rows)
+
+
 class DevMem:
     """A raw device allocation exposed through __cuda_array_interface__ so torch can wrap it without copying."""
 
@@ -55,7 +81,8 @@ def wrap(ptr: int, nbytes: int, device):
 
 
 class Exchange:
-    """Record exchange + global min over a torch.distributed process group."""
+    """The two collectives of a sharded step over a torch.distributed process group (NCCL on GPUs, gloo in CPU tests):
+    an equal-split all-to-all of the per-peer record slabs and an all-gather of the 16-byte per-rank minimum keys."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -65,73 +92,54 @@ class Exchange:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
-    def exchange_counts(self, send_counts, device):
-        import torch
-
-        s = torch.tensor([int(c) for c in send_counts], dtype=torch.int64, device=device)
-        r = torch.empty_like(s)
-        self.dist.all_to_all_single(r, s, group=self.group) if device.type == "cuda" else self._a2a_cpu(r, s)
-        return [int(x) for x in r.tolist()]
-
-    def _a2a_cpu(self, r, s):
-        # gloo has no all_to_all_single on every build: all_gather the count rows and pick our column
-        import torch
-
-        rows = [torch.empty_like(s) for _ in range(self.world)]
-        self.dist.all_gather(rows, s, group=self.group)
+    def all_to_all_slabs(self, recv_buf, send_buf):
+        """send_buf / recv_buf: uint8 tensors of world * bytes_per_peer; slab d of send_buf lands in slab `rank` of rank d."""
+        if send_buf.device.type == "cuda":
+            self.dist.all_to_all_single(recv_buf, send_buf, group=self.group)
+            return
+        # gloo: no all_to_all_single on CPU tensors in every build -> pairwise isend/irecv
+        per = send_buf.numel() // self.world
+        recv_buf[self.rank * per:(self.rank + 1) * per] = send_buf[self.rank * per:(self.rank + 1) * per]
+        ops = []
         for d in range(self.world):
-            r[d] = rows[d][self.rank]
+            if d != self.rank:
+                ops.append(self.dist.P2POp(self.dist.irecv, recv_buf[d * per:(d + 1) * per], d, self.group))
+                ops.append(self.dist.P2POp(self.dist.isend, send_buf[d * per:(d + 1) * per], d, self.group))
+        for w in self.dist.batch_isend_irecv(ops) if ops else []:
+            w.wait()
 
-    def exchange_records(self, send_buf, send_stride: int, send_counts, recv_buf, recv_counts) -> int:
-        """send_buf: uint8 tensor [world * send_stride]; the first send_counts[d] records of slab d go to rank d.
-        Received records are packed contiguously into recv_buf in rank order.  Returns the number received."""
-        ops, off = [], 0
-        for d in range(self.world):
-            if d == self.rank:
-                continue
-            n_out = int(send_counts[d]) * RECORD_BYTES
-            n_in = int(recv_counts[d]) * RECORD_BYTES
-            if n_in:
-                ops.append(self.dist.P2POp(self.dist.irecv, recv_buf[off:off + n_in], d, self.group))
-                off += n_in
-            if n_out:
-                ops.append(self.dist.P2POp(self.dist.isend, send_buf[d * send_stride:d * send_stride + n_out], d, self.group))
-        if ops:
-            for w in self.dist.batch_isend_irecv(ops):
-                w.wait()
-        return off // RECORD_BYTES
-
-    def global_min(self, key, device):
-        """key: tuple (time f64, class, hi, kind bit, lo).  Returns the minimum over all ranks (same on every rank)."""
+    def all_gather_keys(self, key_local):
+        """key_local: int64 tensor [2] (time key, tie).  Returns an int64 tensor [world, 2]."""
         import torch
 
-        bits = struct.unpack("<q", struct.pack("<d", float(key[0])))[0]
-        mine = torch.tensor([bits, int(key[1]), int(key[2]), int(key[3]), int(key[4])], dtype=torch.int64, device=device)
-        rows = [torch.empty_like(mine) for _ in range(self.world)]
-        self.dist.all_gather(rows, mine, group=self.group)
-        best = None
-        for r in rows:
-            v = r.tolist()
-            k = (struct.unpack("<d", struct.pack("<q", v[0]))[0], v[1], v[2], v[3], v[4])
-            if best is None or k < best:
-                best = k
-        return best
+        out = torch.empty(self.world * 2, dtype=torch.int64, device=key_local.device)
+        if key_local.device.type == "cuda":
+            self.dist.all_gather_into_tensor(out, key_local, group=self.group)
+        else:
+            rows = [torch.empty_like(key_local) for _ in range(self.world)]
+            self.dist.all_gather(rows, key_local, group=self.group)
+            out = torch.cat(rows)
+        return out.view(self.world, 2)
 
 
 class ShardedEngine:
-    """One rank of a sharded `Collider`: a device context + the exchange around its two-phase step."""
+    """One rank of a sharded `Collider`: a device context on torch's current stream + the two collectives of its step.
+    Per step the host enqueues: stage A + halo pack -> all-to-all of the slabs -> binning / candidates / solve / local min
+    -> all-gather of the keys, and synchronises once at the end."""
 
-    def __init__(self, cb, cell_width: float, padding: float, device_index: int, bounds, exchange: Exchange):
+    def __init__(self, cb, cell_width: float, padding: float, device_index: int, bounds, id_space: int, exchange: Exchange):
         import torch
 
         self.cb, self.ex = cb, exchange
         self.device = torch.device("cuda", device_index)
         self.eng = cb.Engine(cell_width, padding, device=device_index)
-        self.eng.shard_configure(exchange.rank, exchange.world, bounds)
-        self.h2d = self.d2h = 0
+        self.eng.shard_configure(exchange.rank, exchange.world, bounds, id_space)
+        self.eng.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._bufs = None
 
     def upload_state(self, **cols):
         self.eng.upload_state(**cols)
+        self._bufs = None
 
     def set_overlaps(self, a, b):
         self.eng.set_overlaps(a, b)
@@ -140,22 +148,30 @@ class ShardedEngine:
         import torch
 
         st = self.eng.shard_begin(time, end_time=end_time, **vel)
-        recv_counts = self.ex.exchange_counts(st["send_counts"], self.device)
-        n_in = sum(recv_counts)
-        if n_in > st["recv_cap"]:
-            raise RuntimeError(f"rank {self.ex.rank}: {n_in} halo records exceed the visitor table ({st['recv_cap']})")
-        send = wrap(st["send_ptr"], st["send_stride"] * self.ex.world, self.device)
-        recv = wrap(st["recv_ptr"], max(n_in, 1) * RECORD_BYTES, self.device)
-        got = self.ex.exchange_records(send, st["send_stride"], st["send_counts"], recv, recv_counts)
-        torch.cuda.current_stream(self.device).synchronize()  # the engine runs on its own stream
-        res = self.eng.shard_finish(got)
-        ev = res.next_event
+        key = (st["send_ptr"], st["recv_ptr"], st["bytes_per_peer"])
+        if self._bufs is None or self._bufs[0] != key:
+            nbytes = st["bytes_per_peer"] * self.ex.world
+            self._bufs = (key, wrap(st["send_ptr"], nbytes, self.device), wrap(st["recv_ptr"], nbytes, self.device))
+        _, send, recv = self._bufs
+        self.ex.all_to_all_slabs(recv, send)
+        key_ptr = self.eng.shard_finish()
+        keys = self.ex.all_gather_keys(wrap(key_ptr, 16, self.device).view(torch.int64))
+        res = self.eng.shard_result()  # the one host synchronisation of the step
         self.local_result = res
-        self.halo_sent = int(sum(int(c) for c in st["send_counts"]))
-        self.halo_received = got
-        self.next_key = self.ex.global_min(event_key(res.next_time, ev.kind, ev.a, ev.b), self.device)
+        self.next_key = min_key(keys.tolist())
+        self.next_event = decode_key(*self.next_key)
         return res
+
+    def halo_counts(self):
+        """(records sent, records received) of the last step — reads the slab headers (D2H; diagnostics only)."""
+        import torch
+
+        _, send, recv = self._bufs
+        per = send.numel() // self.ex.world
+        s = sum(int(send[d * per:d * per + 4].view(torch.int32).item()) for d in range(self.ex.world))
+        r = sum(int(recv[d * per:d * per + 4].view(torch.int32).item()) for d in range(self.ex.world))
+        return s, r
 
     @property
     def next_time(self) -> float:
-        return self.next_key[0]
+        return self.next_event[0]

@@ -162,18 +162,28 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
  * ids must be < 2^31 - 1 and globally unique) and, every step, hands the 96-byte record of each resident to every
  * rank whose strip its index rect touches.  A pair is solved by exactly one rank: the one whose strip holds the
  * pair's owner cell (max of the two rect starts), so records only ever need to reach ranks at or right of their
- * start column.  The exchange itself is done by the caller between the two calls below (NCCL over NVLink:
- * torch.distributed in this repo, ncclSend/ncclRecv from a Rust host), then the global next event is the minimum of
- * the per-rank results (allreduce-min on next_time, ties by the event key).
- *   cb200_shard_begin : stage A on the residents + halo pack.  send_counts[d] = records for rank d, stored at
- *                       send_base + d * send_stride_bytes; the caller delivers them into the peer's recv_base
- *                       (contiguously, any order) and then calls
- *   cb200_shard_finish: bins own + received records restricted to the own strip, candidate pairs, solves, min. */
+ * start column.  The exchange itself is done by the caller between the two halves (NCCL over NVLink:
+ * torch.distributed in this repo, ncclSend/ncclRecv from a Rust host); the global next event is the minimum of the
+ * per-rank keys.
+ * All three calls below are asynchronous on the context's stream except cb200_shard_result:
+ *   cb200_set_stream  : run the context on the caller's CUDA stream (e.g. torch's current stream) so that the
+ *                       exchange collectives are stream-ordered between the two halves — no host sync mid-step.
+ *   cb200_shard_begin : stage A on the residents + halo pack.  The records for rank d sit in slab d of *send_base
+ *                       (bytes_per_peer bytes each: a 96-byte header whose first word is the record count, then the
+ *                       records); the caller delivers slab d into slab `rank` of rank d's *recv_base — exactly one
+ *                       equal-split all-to-all (ncclSend/ncclRecv group; torch.distributed.all_to_all_single).
+ *   cb200_shard_finish: bins own + received records restricted to the own strip, candidate pairs, solves, min.
+ *                       *local_key = device address of this rank's (time key, tie) minimum, 2 x u64: all-gather it and
+ *                       take the lexicographic minimum for the global next event.
+ *   cb200_shard_result: waits for the step and returns this rank's result. */
 #define CB200_RECORD_BYTES 96
-int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* col_bounds /* world + 1 */);
-int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, uint64_t* send_counts /* [world] */,
-                      uint64_t* n_local, void** send_base, uint64_t* send_stride_bytes, void** recv_base, uint64_t* recv_cap_records);
-int cb200_shard_finish(cb200_ctx* ctx, uint64_t n_recv, cb200_step_result* out);
+int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* col_bounds /* world + 1 */,
+                          uint64_t id_space /* every HbId of every rank is < id_space < 2^31 - 1 */);
+int cb200_set_stream(cb200_ctx* ctx, void* cuda_stream);
+int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, void** send_base, void** recv_base,
+                      uint64_t* bytes_per_peer);
+int cb200_shard_finish(cb200_ctx* ctx, void** local_key);
+int cb200_shard_result(cb200_ctx* ctx, cb200_step_result* out);
 
 /* Events queued by the last bulk step, sorted by the canonical order (time, class, hi id, kind, lo id)
  * (events.rs:60-68 with SURVEY.md §8c tie-break).  Copies events [offset, offset+cap) into buf. */
@@ -199,9 +209,10 @@ int cb200_separate_time_batch(cb200_ctx* ctx, uint64_t n, const double* a, const
 uint64_t cb200_launch_count(const cb200_ctx* ctx);
 /* Device-side duration of cb200_bulk_update and of each of its stages in milliseconds (CUDA events on the
  * context's stream).  For bench.py's roofline. */
-/* Averages since the last cb200_reset_timing.  Stages: 0 pre (H2D velocities + table zeroing), 1 stage A,
- * 2 slot scan, 3 scatter, 4 candidate stage, 5 solve stage, 6 tail (finalize + result D2H). */
-#define CB200_N_STAGES 7
+/* Averages since the last cb200_reset_timing.  Stages: 0 pre (H2D velocities + table zeroing), 1 stage A (+ halo
+ * pack), 2 halo exchange (sharded; the caller's collective on the context's stream), 3 slot scan (+ indexing of
+ * received records), 4 scatter, 5 candidate stage, 6 solve stage + min-reduce + result, 7 tail. */
+#define CB200_N_STAGES 8
 int cb200_last_step_timing(cb200_ctx* ctx, float* total_ms, float* stage_ms, int n_stages);
 int cb200_reset_timing(cb200_ctx* ctx);
 

@@ -21,25 +21,19 @@ def bits(a):
 
 
 def exchange_on_one_gpu(engs, states):
+    """The all-to-all of the slabs, done with device-to-device copies between the contexts of one GPU."""
     import torch
 
     dev = torch.device("cuda", 0)
     R = len(engs)
-    n_recv = []
+    torch.cuda.synchronize()  # every context runs on its own stream
     for r in range(R):
-        off = 0
+        per = states[r]["bytes_per_peer"]
         for d in range(R):
-            if d == r:
-                continue
-            nbytes = int(states[d]["send_counts"][r]) * sharding.RECORD_BYTES
-            if nbytes:
-                src = sharding.wrap(states[d]["send_ptr"] + r * states[d]["send_stride"], nbytes, dev)
-                dst = sharding.wrap(states[r]["recv_ptr"] + off, nbytes, dev)
-                dst.copy_(src)
-                off += nbytes
-        n_recv.append(off // sharding.RECORD_BYTES)
+            src = sharding.wrap(states[d]["send_ptr"] + r * per, per, dev)
+            dst = sharding.wrap(states[r]["recv_ptr"] + d * per, per, dev)
+            dst.copy_(src)
     torch.cuda.synchronize()
-    return n_recv
 
 
 def key_of(ev):
@@ -62,7 +56,7 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
     engs = []
     for r in range(world):
         e = cb.Engine(CW, PAD)
-        e.shard_configure(r, world, bounds)
+        e.shard_configure(r, world, bounds, n)
         m = owner == r
         e.upload_state(**{k: v[m] for k, v in st.items()})
         engs.append(e)
@@ -75,9 +69,18 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
         end = np.inf if end_dt is None else T + end_dt
         orc.bulk_update(end_time=end, record_candidates=True)
         states = [e.shard_begin(T, end_time=end) for e in engs]
-        total_halo += sum(int(s["send_counts"].sum()) for s in states)
-        n_recv = exchange_on_one_gpu(engs, states)
-        results = [e.shard_finish(k) for e, k in zip(engs, n_recv)]
+        exchange_on_one_gpu(engs, states)
+        key_ptrs = [e.shard_finish() for e in engs]
+        results = [e.shard_result() for e in engs]
+        import torch
+
+        dev = torch.device("cuda", 0)
+        for st in states:  # records that actually travelled: the slab headers
+            per = st["bytes_per_peer"]
+            total_halo += sum(int(sharding.wrap(st["send_ptr"] + d * per, 4, dev).view(torch.int32).item()) for d in range(world))
+        # the device-side local keys, all-gathered and min-reduced like sharding.ShardedEngine does
+        rows = [sharding.wrap(p, 16, dev).view(torch.int64).tolist() for p in key_ptrs]
+        global_event = sharding.decode_key(*sharding.min_key(rows))
         # events: union over ranks, merged in the canonical order
         ev = np.concatenate([e.fetch_events() for e in engs])
         ev = ev[key_of(ev)]
@@ -89,9 +92,10 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
         np.testing.assert_array_equal(bits(ev["time"]), bits(t))
         # global next event = min over ranks
         keys = [sharding.event_key(r.next_time, r.next_event.kind, r.next_event.a, r.next_event.b) for r in results]
-        assert min(keys)[0] == orc.next_time()
+        assert min(keys)[0] == orc.next_time() == global_event[0]
         if len(t):
             assert min(keys) == sharding.event_key(t[0], int(kind[0]), int(a[0]), int(b[0]))
+            assert global_event == (t[0], int(kind[0]), int(a[0]), 0 if kind[0] == 0 else int(b[0]))
         # candidate pairs: disjoint union == oracle set
         ohi, olo = orc.bulk_candidates()
         pairs = [e.fetch_candidate_pairs() for e in engs]

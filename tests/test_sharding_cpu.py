@@ -3,6 +3,7 @@ strip partition, count/record exchange, global event minimum (the N>1 plumbing o
 import importlib
 import os
 import socket
+import struct
 
 import numpy as np
 import pytest
@@ -25,6 +26,8 @@ def test_strip_bounds_and_destinations():
 def test_event_key_order():
     k = sharding.event_key
     assert k(1.0, 0, 7, 0) < k(1.0, 2, 3, 1) < k(1.0, 1, 3, 1) < k(1.0, 2, 4, 0) < k(1.5, 0, 0, 0) < k(float("inf"), 0, 0, 0)
+    assert sharding.decode_key(sharding.KEY_MAX, sharding.KEY_MAX)[0] == float("inf")
+    assert sharding.key_to_time((0x3FF0000000000000) | (1 << 63)) == 1.0
 
 
 def _free_port():
@@ -44,33 +47,35 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         ex = sharding.Exchange()
-        dev = torch.device("cpu")
-        RB = sharding.RECORD_BYTES
-        stride = 8 * RB
-        # rank r sends (r + 1) * (d + 1) records to rank d, each filled with a byte tag
-        counts = [0 if d == rank else (rank + 1) * (d + 1) for d in range(world)]
-        send = torch.zeros(world * stride, dtype=torch.uint8)
+        per = 3 * sharding.RECORD_BYTES
+        # slab d of rank r is filled with the tag 16 * r + d; after the all-to-all slab d of rank r must hold 16 * d + r
+        send = torch.zeros(world * per, dtype=torch.uint8)
         for d in range(world):
-            send[d * stride:d * stride + counts[d] * RB] = 16 * rank + d
-        recv_counts = ex.exchange_counts(counts, dev)
-        assert recv_counts == [0 if d == rank else (d + 1) * (rank + 1) for d in range(world)]
-        recv = torch.zeros(sum(recv_counts) * RB, dtype=torch.uint8)
-        got = ex.exchange_records(send, stride, counts, recv, recv_counts)
-        assert got == sum(recv_counts)
-        off = 0
+            send[d * per:(d + 1) * per] = 16 * rank + d
+        recv = torch.zeros_like(send)
+        ex.all_to_all_slabs(recv, send)
         for d in range(world):
-            nb = recv_counts[d] * RB
-            assert bool((recv[off:off + nb] == 16 * d + rank).all())
-            off += nb
-        # global minimum of the per-rank next events; same answer on every rank, ties broken by the key
-        mine = sharding.event_key(2.5, 1, 10 + rank, 3) if rank else sharding.event_key(2.5, 2, 11, 4)
-        best = ex.global_min(mine, dev)
-        assert best == (2.5, 1, 11, 0, 4)
-        best = ex.global_min(sharding.event_key(float("inf"), 0, 0, 0) if rank else sharding.event_key(7.25, 0, 5, 0), dev)
-        assert best == (7.25, 0, 5, 0, 0)
+            assert bool((recv[d * per:(d + 1) * per] == 16 * d + rank).all())
+        # all-gather of the per-rank (time key, tie) minima + lexicographic min, in the device's u64 encoding
+        def enc(t, tie):
+            bits = struct.unpack("<Q", struct.pack("<d", t))[0]
+            k = (~bits & sharding.KEY_MAX) if bits >> 63 else (bits | (1 << 63))
+            to_i64 = lambda v: v - (1 << 64) if v >= (1 << 63) else v
+            return torch.tensor([to_i64(k), to_i64(tie)], dtype=torch.int64)
+
+        pair = lambda hi, collide, lo: sharding.PAIR_CLASS | (hi << 32) | (sharding.COLLIDE_BIT if collide else 0) | lo
+        mine = enc(2.5, pair(10 + rank, True, 3)) if rank else enc(2.5, pair(11, False, 4))
+        rows = ex.all_gather_keys(mine).tolist()
+        assert sharding.decode_key(*sharding.min_key(rows)) == (2.5, 2, 11, 4)   # Separate(11, 4) < Collide(11, 3) at equal time
+        mine = torch.tensor([-1, -1], dtype=torch.int64) if rank else enc(7.25, 5)  # rank 1: empty queue (all ones)
+        assert sharding.decode_key(*sharding.min_key(ex.all_gather_keys(mine).tolist())) == (7.25, 0, 5, 0)
+        mine = enc(-1.5, 9) if rank else enc(0.25, 1)                               # negative times order correctly
+        assert sharding.decode_key(*sharding.min_key(ex.all_gather_keys(mine).tolist())) == (-1.5, 0, 9, 0)
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
-        out.put((rank, repr(e)))
+        import traceback
+
+        out.put((rank, traceback.format_exc()))
     finally:
         dist.destroy_process_group()
 
