@@ -83,7 +83,7 @@ EXPORTS = (
     "cb200_host_alloc", "cb200_host_free", "cb200_upload_state", "cb200_download_state", "cb200_set_overlaps",
     "cb200_bulk_update", "cb200_fetch_events", "cb200_fetch_candidate_pairs", "cb200_fetch_cell_entries",
     "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
-    "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_set_stream", "cb200_shard_begin", "cb200_shard_finish",
+    "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_shard_set_slab", "cb200_set_stream", "cb200_shard_begin", "cb200_shard_finish",
     "cb200_shard_result",
 )
 
@@ -127,6 +127,7 @@ def load_library() -> C.CDLL:
     L.cb200_reset_timing.argtypes = [vp]
     L.cb200_shard_configure.argtypes = [vp, i32, i32, vp, u64]
     L.cb200_set_stream.argtypes = [vp, vp]
+    L.cb200_shard_set_slab.argtypes = [vp, u64]
     L.cb200_shard_begin.argtypes = [vp, dbl, C.POINTER(VelView), dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     L.cb200_shard_finish.argtypes = [vp, C.POINTER(vp)]
     L.cb200_shard_result.argtypes = [vp, C.POINTER(StepResult)]
@@ -262,11 +263,14 @@ class Engine:
         self._check(self._L.cb200_shard_configure(self._h, rank, world, _ptr(b), id_space))
         self.rank, self.world = rank, world
 
+    def shard_set_slab(self, records: int):
+        self._check(self._L.cb200_shard_set_slab(self._h, records))
+
     def set_stream(self, cuda_stream: int):
         self._check(self._L.cb200_set_stream(self._h, C.c_void_p(cuda_stream)))
 
     def shard_begin(self, time: float, end_time: float = INF, vel_x=None, vel_y=None, rsz_x=None, rsz_y=None, end_time_arr=None) -> dict:
-        """Asynchronous front half.  Returns the exchange buffers: slab d of send_ptr goes to slab `rank` of rank d's recv_ptr."""
+        """Asynchronous front half.  Returns the exchange buffers: the slab at send_ptr is all-gathered into slot `rank` of every rank's recv_ptr."""
         arrs = [vel_x, vel_y, rsz_x, rsz_y, end_time_arr]
         per_peer = C.c_uint64()
         send, recv = C.c_void_p(), C.c_void_p()
@@ -275,7 +279,7 @@ class Engine:
             self._keep = [None if a is None else _col(a, np.float64, self.n) for a in arrs]  # alive until the step completes
             v = C.byref(VelView(*[None if a is None else a.ctypes.data for a in self._keep]))
         self._check(self._L.cb200_shard_begin(self._h, time, v, end_time, C.byref(send), C.byref(recv), C.byref(per_peer)))
-        return dict(send_ptr=send.value, recv_ptr=recv.value, bytes_per_peer=per_peer.value)
+        return dict(send_ptr=send.value, recv_ptr=recv.value, slab_bytes=per_peer.value)
 
     def shard_finish(self) -> int:
         """Asynchronous back half; returns the device address of this rank's (time key, tie) minimum (2 x u64)."""

@@ -68,7 +68,7 @@ struct cb200_ctx {
     // sharding
     bool sharded = false;
     ShardGeom shard{};
-    DevBuf<HbRec> send;      // [world][slab]: record 0 of each slab is its header
+    DevBuf<HbRec> send;      // [slab]: the outgoing halo slab, record 0 is its header
     DevBuf<uint32_t> send_count;
     uint32_t slab = 0;       // records per slab, header included
     MinKey* d_key = nullptr; // local minimum of the last step (device), input of the all-gather min
@@ -344,11 +344,12 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
         CU(ctx->gid.reserve(cap));
         if (n) CU(cudaMemcpyAsync(ctx->gid.p, g.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        // per-peer slab: header + room for n/64 (>= 4095) halo records; own region of the visitor table = n records
-        if (ctx->slab == 0) ctx->slab = (uint32_t)std::max<size_t>(n / 64, 4095) + 1;
+        // halo slab: header + room for n/256 (>= 2047) records leaving the strip (cb200_shard_set_slab overrides); the
+        // visitor table holds the n own records followed by one received slab per rank
+        if (ctx->slab == 0) ctx->slab = (uint32_t)std::max<size_t>(n / 256, 2047) + 1;
         CU(ctx->rec.reserve(n + (size_t)ctx->slab * ctx->shard.world));
-        CU(ctx->send.reserve((size_t)ctx->slab * ctx->shard.world));
-        CU(ctx->send_count.reserve(ctx->shard.world));
+        CU(ctx->send.reserve(ctx->slab));
+        CU(ctx->send_count.reserve(1));
         CU(ctx->vmap.reserve(ctx->id_space));
         CU(cudaMemsetAsync(ctx->vmap.p, 0xff, ctx->id_space * 4, ctx->stream));
         CU(cudaMemsetAsync(ctx->rec.p + n, 0, (size_t)ctx->slab * ctx->shard.world * sizeof(HbRec), ctx->stream));
@@ -461,7 +462,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     CU(cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)(n_slots / kScanTile) * 8, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->stream));
     CU(cudaMemsetAsync(&ctx->d_ctr->err_slot, 0xff, 8, ctx->stream));
-    if (ctx->sharded) CU(cudaMemsetAsync(ctx->send_count.p, 0, sizeof(uint32_t) * ctx->shard.world, ctx->stream));
+    if (ctx->sharded) CU(cudaMemsetAsync(ctx->send_count.p, 0, sizeof(uint32_t), ctx->stream));
     CU(cudaEventRecord(ctx->ev_t[ST_STAGE_A], ctx->stream));
     StepArgs a{};
     a.n = n;
@@ -492,7 +493,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
         CU(cudaMemsetAsync(ctx->partial.p, 0xff, sizeof(MinKey) * ctx->grid_a, ctx->stream));
     }
     if (ctx->sharded) {
-        k_slab_headers<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->send.p, ctx->send_count.p, ctx->slab, ctx->shard.world, ctx->shard.rank);
+        k_slab_header<<<1, 1, 0, ctx->stream>>>(ctx->send.p, ctx->send_count.p, ctx->slab);
         ctx->launches += 1;
     }
     CU(cudaEventRecord(ctx->ev_t[ST_EXCH], ctx->stream));
@@ -505,7 +506,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     const GridGeom g = ctx->geom;
     const uint32_t n_slots = g.n_slots();
     const ShardGeom sh = ctx->sharded ? ctx->shard : whole_world();
-    const VisSpace vs{ctx->n, ctx->slab, sh.world};
+    const VisSpace vs{ctx->n, ctx->slab, sh.world, sh.rank};
     const uint32_t n_vis_max = ctx->sharded ? ctx->n + ctx->slab * (uint32_t)sh.world : ctx->n;
     const uint32_t grid_v = std::max<uint32_t>(1, std::min<uint32_t>((n_vis_max + kThreads - 1) / kThreads, ctx->sm_count * 8));
     const bool use_map = ctx->sharded && ctx->n_ov;
@@ -693,6 +694,14 @@ int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* co
     return CB200_OK;
 }
 
+int cb200_shard_set_slab(cb200_ctx* ctx, uint64_t records) {
+    if (!ctx) return CB200_E_ARG;
+    if (records < 1 || records >= 0x7ffffff0ull) return fail(ctx, CB200_E_ARG, "bad slab size");
+    ctx->slab = (uint32_t)records + 1;
+    ctx->have_state = false;  // buffers are sized at upload_state
+    return CB200_OK;
+}
+
 int cb200_set_stream(cb200_ctx* ctx, void* cuda_stream) {
     if (!ctx) return CB200_E_ARG;
     CU(cudaSetDevice(ctx->device));
@@ -705,7 +714,7 @@ int cb200_set_stream(cb200_ctx* ctx, void* cuda_stream) {
 
 // Asynchronous: enqueues stage A + halo pack on the context's stream and returns the buffers of the exchange.
 int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, void** send_base, void** recv_base,
-                      uint64_t* bytes_per_peer) {
+                      uint64_t* slab_bytes) {
     if (!ctx) return CB200_E_ARG;
     if (!ctx->sharded) return fail(ctx, CB200_E_STATE, "cb200_shard_configure first");
     if (!ctx->have_state) return fail(ctx, CB200_E_STATE, "shard_begin before upload_state");
@@ -721,7 +730,7 @@ int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
     ctx->shard_T = time;
     if (send_base) *send_base = ctx->send.p;
     if (recv_base) *recv_base = ctx->rec.p + ctx->n;
-    if (bytes_per_peer) *bytes_per_peer = (uint64_t)ctx->slab * sizeof(HbRec);
+    if (slab_bytes) *slab_bytes = (uint64_t)ctx->slab * sizeof(HbRec);
     return CB200_OK;
 }
 
@@ -747,7 +756,7 @@ int cb200_shard_result(cb200_ctx* ctx, cb200_step_result* out) {
     int rc;
     bool again = false;
     if ((rc = complete_step(ctx, ctx->shard_T, &again)) != CB200_OK) return rc;
-    if (ctx->last.ctr.overflow_send) return fail(ctx, CB200_E_STATE, "halo slab overflow: more records for one peer than the slab holds (strips too thin for this scene)");
+    if (ctx->last.ctr.overflow_send) return fail(ctx, CB200_E_STATE, "halo slab overflow: more records leave this rank's strip than the slab holds (cb200_shard_set_slab)");
     accumulate_timing(ctx, ST_PRE, true);
     for (int attempt = 0; attempt < 3 && again && !ctx->last.ctr.err_flags; ++attempt) {
         // re-run of the back half only: slot table and counters are rebuilt, the visitor table is intact

@@ -43,9 +43,10 @@ struct StepArgs {
     GridGeom geom;
     Counters* ctr;
     MinKey* partial;  // [gridDim.x] solitaire minima
-    // sharded only: per-peer slabs of `slab` records each; record 0 of a slab is its header (first word = count)
-    HbRec* send;           // [world][slab]
-    uint32_t* send_count;  // [world]
+    // sharded only: ONE outgoing slab of `slab` records; record 0 is its header (first word = count).  It is
+    // all-gathered: every rank receives every slab and simply bins what falls into its own strip.
+    HbRec* send;           // [slab]
+    uint32_t* send_count;  // [1]
     uint32_t slab;
     uint32_t* vmap;        // gid -> record index of this step (direct-addressed; null when there are no overlapping pairs)
 };
@@ -55,7 +56,7 @@ struct StepArgs {
 struct VisSpace {
     uint32_t n_own;  // capacity of the own region (= residents)
     uint32_t slab;   // records per slab including the header
-    int world;
+    int world, rank; // slab `rank` is this rank's own halo slab coming back from the all-gather: ignored
 };
 __device__ __forceinline__ uint32_t slab_count(const HbRec* rec, const VisSpace& vs, int d) {
     return __ldg(reinterpret_cast<const unsigned int*>(rec + vs.n_own + (size_t)d * vs.slab));
@@ -67,7 +68,7 @@ __device__ __forceinline__ bool vis_record(const HbRec* rec, const VisSpace& vs,
         return true;
     }
     const uint32_t j = i - n_local, d = j / vs.slab, k = j % vs.slab;
-    if (k == 0 || k - 1 >= slab_count(rec, vs, (int)d)) return false;
+    if ((int)d == vs.rank || k == 0 || k - 1 >= slab_count(rec, vs, (int)d)) return false;
     *v = vs.n_own + j;
     return true;
 }
@@ -230,18 +231,16 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
             if (!SHARDED) {
                 store_rec(a.rec + i, rec);
             } else if (binned) {
-                // every rank whose strip intersects columns [sx, ex + 1): the extra column keeps a partner that is
-                // within `padding` across a cell line (an overlapping pair whose rects do not intersect) visible.
+                // The record is needed by every rank whose strip intersects columns [sx, ex + 1): the extra column keeps
+                // a partner that is within `padding` across a cell line (an overlapping pair whose rects do not
+                // intersect) visible.  Own strip -> compacted into the visitor table; any other strip -> the halo slab.
                 const int64_t hi_col = (int64_t)ex + 1;
-                for (int d = 0; d < sh.world; ++d) {
-                    if ((int64_t)sh.bounds[d + 1] <= (int64_t)rec.sx || (int64_t)sh.bounds[d] >= hi_col) continue;
-                    if (d == sh.rank) {
-                        keep_local = 1;
-                    } else {
-                        const uint32_t pos = warp_agg_claim32(&a.send_count[d]);
-                        if (pos + 1 < a.slab) store_rec(a.send + (size_t)d * a.slab + 1 + pos, rec);
-                        else a.ctr->overflow_send = 1u;
-                    }
+                keep_local = ((int64_t)sh.col_hi > (int64_t)rec.sx && (int64_t)sh.col_lo < hi_col) ? 1u : 0u;
+                const bool leaves = (int64_t)rec.sx < (int64_t)sh.col_lo || hi_col > (int64_t)sh.col_hi;
+                if (leaves) {
+                    const uint32_t pos = warp_agg_claim32(a.send_count);
+                    if (pos + 1 < a.slab) store_rec(a.send + 1 + pos, rec);
+                    else a.ctr->overflow_send = 1u;
                 }
             }
 
@@ -275,12 +274,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
     }
 }
 
-// Sharded: publish the per-peer record counts in the slab headers (one thread per rank) before the exchange.
-__global__ void k_slab_headers(HbRec* send, const uint32_t* __restrict__ send_count, uint32_t slab, int world, int rank) {
-    const int d = threadIdx.x;
-    if (d >= world) return;
-    const uint32_t c = d == rank ? 0u : min(send_count[d], slab - 1u);
-    *reinterpret_cast<unsigned int*>(send + (size_t)d * slab) = c;
+// Sharded: publish the record count in the halo slab's header before the all-gather.
+__global__ void k_slab_header(HbRec* send, const uint32_t* __restrict__ send_count, uint32_t slab) {
+    *reinterpret_cast<unsigned int*>(send) = min(send_count[0], slab - 1u);
 }
 
 // Sharded, after the exchange: count the strip cells of the RECEIVED records (the own ones were counted in stage A;
@@ -643,7 +639,7 @@ __device__ __forceinline__ bool gid_lookup(const SolveArgs& a, uint32_t n_local,
         const uint32_t j = v - a.vs.n_own;
         if (j >= (uint32_t)a.vs.world * a.vs.slab) return false;
         const uint32_t d = j / a.vs.slab, k = j % a.vs.slab;
-        if (k == 0 || k - 1 >= slab_count(a.rec, a.vs, (int)d)) return false;
+        if ((int)d == a.vs.rank || k == 0 || k - 1 >= slab_count(a.rec, a.vs, (int)d)) return false;
     }
     if (__ldg(reinterpret_cast<const unsigned int*>(a.rec + v) + 3) != gid) return false;
     *vidx = v;

@@ -82,7 +82,7 @@ def wrap(ptr: int, nbytes: int, device):
 
 class Exchange:
     """The two collectives of a sharded step over a torch.distributed process group (NCCL on GPUs, gloo in CPU tests):
-    an equal-split all-to-all of the per-peer record slabs and an all-gather of the 16-byte per-rank minimum keys."""
+    an all-gather of the per-rank halo slabs and an all-gather of the 16-byte per-rank minimum keys."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -92,21 +92,16 @@ class Exchange:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
-    def all_to_all_slabs(self, recv_buf, send_buf):
-        """send_buf / recv_buf: uint8 tensors of world * bytes_per_peer; slab d of send_buf lands in slab `rank` of rank d."""
+    def all_gather_slabs(self, recv_buf, send_buf):
+        """send_buf: uint8 tensor of one slab; recv_buf: world slabs.  Slot d of recv_buf receives rank d's slab."""
         if send_buf.device.type == "cuda":
-            self.dist.all_to_all_single(recv_buf, send_buf, group=self.group)
+            self.dist.all_gather_into_tensor(recv_buf, send_buf, group=self.group)
             return
-        # gloo: no all_to_all_single on CPU tensors in every build -> pairwise isend/irecv
-        per = send_buf.numel() // self.world
-        recv_buf[self.rank * per:(self.rank + 1) * per] = send_buf[self.rank * per:(self.rank + 1) * per]
-        ops = []
-        for d in range(self.world):
-            if d != self.rank:
-                ops.append(self.dist.P2POp(self.dist.irecv, recv_buf[d * per:(d + 1) * per], d, self.group))
-                ops.append(self.dist.P2POp(self.dist.isend, send_buf[d * per:(d + 1) * per], d, self.group))
-        for w in self.dist.batch_isend_irecv(ops) if ops else []:
-            w.wait()
+        import torch
+
+        rows = [torch.empty_like(send_buf) for _ in range(self.world)]
+        self.dist.all_gather(rows, send_buf, group=self.group)
+        recv_buf.copy_(torch.cat(rows))
 
     def all_gather_keys(self, key_local):
         """key_local: int64 tensor [2] (time key, tie).  Returns an int64 tensor [world, 2]."""
@@ -124,8 +119,9 @@ class Exchange:
 
 class ShardedEngine:
     """One rank of a sharded `Collider`: a device context on torch's current stream + the two collectives of its step.
-    Per step the host enqueues: stage A + halo pack -> all-to-all of the slabs -> binning / candidates / solve / local min
+    Per step the host enqueues: stage A + halo pack -> all-gather of the halo slabs -> binning / candidates / solve / local min
     -> all-gather of the keys, and synchronises once at the end."""
+
 
     def __init__(self, cb, cell_width: float, padding: float, device_index: int, bounds, id_space: int, exchange: Exchange):
         import torch
@@ -148,12 +144,11 @@ class ShardedEngine:
         import torch
 
         st = self.eng.shard_begin(time, end_time=end_time, **vel)
-        key = (st["send_ptr"], st["recv_ptr"], st["bytes_per_peer"])
+        key = (st["send_ptr"], st["recv_ptr"], st["slab_bytes"])
         if self._bufs is None or self._bufs[0] != key:
-            nbytes = st["bytes_per_peer"] * self.ex.world
-            self._bufs = (key, wrap(st["send_ptr"], nbytes, self.device), wrap(st["recv_ptr"], nbytes, self.device))
+            self._bufs = (key, wrap(st["send_ptr"], st["slab_bytes"], self.device), wrap(st["recv_ptr"], st["slab_bytes"] * self.ex.world, self.device))
         _, send, recv = self._bufs
-        self.ex.all_to_all_slabs(recv, send)
+        self.ex.all_gather_slabs(recv, send)
         key_ptr = self.eng.shard_finish()
         keys = self.ex.all_gather_keys(wrap(key_ptr, 16, self.device).view(torch.int64))
         res = self.eng.shard_result()  # the one host synchronisation of the step
@@ -167,9 +162,9 @@ class ShardedEngine:
         import torch
 
         _, send, recv = self._bufs
-        per = send.numel() // self.ex.world
-        s = sum(int(send[d * per:d * per + 4].view(torch.int32).item()) for d in range(self.ex.world))
-        r = sum(int(recv[d * per:d * per + 4].view(torch.int32).item()) for d in range(self.ex.world))
+        per = send.numel()
+        s = int(send[:4].view(torch.int32).item())
+        r = sum(int(recv[d * per:d * per + 4].view(torch.int32).item()) for d in range(self.ex.world) if d != self.ex.rank)
         return s, r
 
     @property

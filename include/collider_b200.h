@@ -160,7 +160,7 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
  * Cell columns are split into `world` contiguous strips: rank d owns columns [col_bounds[d], col_bounds[d+1])
  * (the first and last strips are open-ended).  Each rank keeps a fixed set of resident hitboxes (upload_state;
  * ids must be < 2^31 - 1 and globally unique) and, every step, hands the 96-byte record of each resident to every
- * rank whose strip its index rect touches.  A pair is solved by exactly one rank: the one whose strip holds the
+ * rank whose strip its index rect touches (one all-gather of small per-rank halo slabs).  A pair is solved by exactly one rank: the one whose strip holds the
  * pair's owner cell (max of the two rect starts), so records only ever need to reach ranks at or right of their
  * start column.  The exchange itself is done by the caller between the two halves (NCCL over NVLink:
  * torch.distributed in this repo, ncclSend/ncclRecv from a Rust host); the global next event is the minimum of the
@@ -168,10 +168,12 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
  * All three calls below are asynchronous on the context's stream except cb200_shard_result:
  *   cb200_set_stream  : run the context on the caller's CUDA stream (e.g. torch's current stream) so that the
  *                       exchange collectives are stream-ordered between the two halves — no host sync mid-step.
- *   cb200_shard_begin : stage A on the residents + halo pack.  The records for rank d sit in slab d of *send_base
- *                       (bytes_per_peer bytes each: a 96-byte header whose first word is the record count, then the
- *                       records); the caller delivers slab d into slab `rank` of rank d's *recv_base — exactly one
- *                       equal-split all-to-all (ncclSend/ncclRecv group; torch.distributed.all_to_all_single).
+ *   cb200_shard_begin : stage A on the residents + halo pack.  Every record whose rect (+1 column) leaves the own
+ *                       strip is appended once to the rank's halo slab at *send_base (slab_bytes bytes: a 96-byte
+ *                       header whose first word is the record count, then the records).  The caller all-gathers the
+ *                       slabs: slab of rank d -> slot d of every rank's *recv_base (ncclAllGather;
+ *                       torch.distributed.all_gather_into_tensor) — ONE collective, NVLS-capable on NVSwitch.
+ *                       Receivers bin whatever falls into their strip; the rest produces no cell entries.
  *   cb200_shard_finish: bins own + received records restricted to the own strip, candidate pairs, solves, min.
  *                       *local_key = device address of this rank's (time key, tie) minimum, 2 x u64: all-gather it and
  *                       take the lexicographic minimum for the global next event.
@@ -180,8 +182,9 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
 int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* col_bounds /* world + 1 */,
                           uint64_t id_space /* every HbId of every rank is < id_space < 2^31 - 1 */);
 int cb200_set_stream(cb200_ctx* ctx, void* cuda_stream);
+int cb200_shard_set_slab(cb200_ctx* ctx, uint64_t records); /* capacity of the halo slab; default max(2047, n/256); before upload_state */
 int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, void** send_base, void** recv_base,
-                      uint64_t* bytes_per_peer);
+                      uint64_t* slab_bytes);
 int cb200_shard_finish(cb200_ctx* ctx, void** local_key);
 int cb200_shard_result(cb200_ctx* ctx, cb200_step_result* out);
 

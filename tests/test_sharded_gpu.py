@@ -21,16 +21,16 @@ def bits(a):
 
 
 def exchange_on_one_gpu(engs, states):
-    """The all-to-all of the slabs, done with device-to-device copies between the contexts of one GPU."""
+    """The all-gather of the halo slabs, done with device-to-device copies between the contexts of one GPU."""
     import torch
 
     dev = torch.device("cuda", 0)
     R = len(engs)
     torch.cuda.synchronize()  # every context runs on its own stream
     for r in range(R):
-        per = states[r]["bytes_per_peer"]
+        per = states[r]["slab_bytes"]
         for d in range(R):
-            src = sharding.wrap(states[d]["send_ptr"] + r * per, per, dev)
+            src = sharding.wrap(states[d]["send_ptr"], per, dev)
             dst = sharding.wrap(states[r]["recv_ptr"] + d * per, per, dev)
             dst.copy_(src)
     torch.cuda.synchronize()
@@ -76,8 +76,7 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
 
         dev = torch.device("cuda", 0)
         for st in states:  # records that actually travelled: the slab headers
-            per = st["bytes_per_peer"]
-            total_halo += sum(int(sharding.wrap(st["send_ptr"] + d * per, 4, dev).view(torch.int32).item()) for d in range(world))
+            total_halo += int(sharding.wrap(st["send_ptr"], 4, dev).view(torch.int32).item())
         # the device-side local keys, all-gathered and min-reduced like sharding.ShardedEngine does
         rows = [sharding.wrap(p, 16, dev).view(torch.int64).tolist() for p in key_ptrs]
         global_event = sharding.decode_key(*sharding.min_key(rows))

@@ -48,14 +48,12 @@ def _worker(rank, world, port, out):
     try:
         ex = sharding.Exchange()
         per = 3 * sharding.RECORD_BYTES
-        # slab d of rank r is filled with the tag 16 * r + d; after the all-to-all slab d of rank r must hold 16 * d + r
-        send = torch.zeros(world * per, dtype=torch.uint8)
+        # rank r's halo slab is filled with the tag 16 + r; after the all-gather slot d of every rank must hold 16 + d
+        send = torch.full((per,), 16 + rank, dtype=torch.uint8)
+        recv = torch.zeros(world * per, dtype=torch.uint8)
+        ex.all_gather_slabs(recv, send)
         for d in range(world):
-            send[d * per:(d + 1) * per] = 16 * rank + d
-        recv = torch.zeros_like(send)
-        ex.all_to_all_slabs(recv, send)
-        for d in range(world):
-            assert bool((recv[d * per:(d + 1) * per] == 16 * d + rank).all())
+            assert bool((recv[d * per:(d + 1) * per] == 16 + d).all())
         # all-gather of the per-rank (time key, tie) minima + lexicographic min, in the device's u64 encoding
         def enc(t, tie):
             bits = struct.unpack("<Q", struct.pack("<d", t))[0]
