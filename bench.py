@@ -255,7 +255,7 @@ def _main(out):
         T = clock[0]
         clock[0] = T + DT
         r = step_fn(T, end_time=clock[0], vel_x=pvx.array, vel_y=pvy.array)
-        evs = eng.fetch_events()
+        evs = eng.fetch_events(pinned=True)  # sorted queue of the step, D2H into page-locked memory
         return r, evs
 
     for _ in range(3):

@@ -84,7 +84,7 @@ EXPORTS = (
     "cb200_bulk_update", "cb200_fetch_events", "cb200_fetch_candidate_pairs", "cb200_fetch_cell_entries",
     "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
     "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_shard_set_slab", "cb200_set_stream", "cb200_shard_begin", "cb200_shard_finish",
-    "cb200_shard_result",
+    "cb200_shard_result", "cb200_set_resort_period", "cb200_resort_count",
 )
 
 _lib = None
@@ -131,6 +131,9 @@ def load_library() -> C.CDLL:
     L.cb200_shard_begin.argtypes = [vp, dbl, C.POINTER(VelView), dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     L.cb200_shard_finish.argtypes = [vp, C.POINTER(vp)]
     L.cb200_shard_result.argtypes = [vp, C.POINTER(StepResult)]
+    L.cb200_set_resort_period.argtypes = [vp, i32]
+    L.cb200_resort_count.argtypes = [vp]
+    L.cb200_resort_count.restype = u64
     _lib = L
     return L
 
@@ -179,6 +182,7 @@ class Engine:
         self.cell_width, self.padding, self.device = cell_width, padding, device
         self.n = 0
         self._keep = None
+        self._ev_pin = None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -294,13 +298,26 @@ class Engine:
         self._check(rc)
         return res
 
-    def fetch_events(self, offset: int = 0, cap: int | None = None) -> np.ndarray:
+    def fetch_events(self, offset: int = 0, cap: int | None = None, pinned: bool = False) -> np.ndarray:
+        """Sorted events of the last step.  pinned=True copies into a reusable page-locked buffer (full PCIe speed)
+        and returns a view that stays valid until the next pinned fetch."""
         if cap is None:
             cap = max(0, int(self.last_result.n_events) - offset)
-        buf = np.zeros(cap, dtype=EVENT_DTYPE)
+        if pinned:
+            if self._ev_pin is None or self._ev_pin.array.shape[0] < cap:
+                self._ev_pin = PinnedArray(max(cap + cap // 4, 1024), EVENT_DTYPE)
+            buf = self._ev_pin.array
+        else:
+            buf = np.zeros(cap, dtype=EVENT_DTYPE)
         got = C.c_uint64()
         self._check(self._L.cb200_fetch_events(self._h, _ptr(buf), cap, offset, C.byref(got)))
         return buf[: got.value]
+
+    def set_resort_period(self, steps: int):
+        self._check(self._L.cb200_set_resort_period(self._h, steps))
+
+    def resort_count(self) -> int:
+        return int(self._L.cb200_resort_count(self._h))
 
     def fetch_candidate_pairs(self):
         n = C.c_uint64()

@@ -205,11 +205,26 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total)
     return inc - v + (warp ? s_scan[warp - 1] : 0u);
 }
 
-// Grid fold: cell (x, y) -> slot.
+// Grid fold: cell (x, y) -> slot.  Cells are folded modulo the grid period and laid out in 8 x 8-cell tiles
+// (slot bits: y_hi | x_hi | y_lo3 | x_lo3), so that the hitboxes of one neighbourhood touch a few consecutive cache
+// lines of the slot table and of the slot-sorted entry array (the hitbox table itself is kept in the same order,
+// see k_resort_*).
 struct GridGeom {
     int lw, lh;
+    __host__ __device__ __forceinline__ int tx() const { return lw < 3 ? lw : 3; }
+    __host__ __device__ __forceinline__ int ty() const { return lh < 3 ? lh : 3; }
     __host__ __device__ __forceinline__ uint32_t slot(int32_t x, int32_t y) const {
-        return ((uint32_t)x & ((1u << lw) - 1u)) | (((uint32_t)y & ((1u << lh) - 1u)) << lw);
+        const uint32_t ux = (uint32_t)x & ((1u << lw) - 1u), uy = (uint32_t)y & ((1u << lh) - 1u);
+        const int a = tx(), b = ty();
+        return (ux & ((1u << a) - 1u)) | ((uy & ((1u << b) - 1u)) << a) | ((ux >> a) << (a + b)) | ((uy >> b) << (lw + b));
+    }
+    // inverse: the folded (x, y) of a slot
+    __host__ __device__ __forceinline__ void unslot(uint32_t s, uint32_t* ux, uint32_t* uy) const {
+        const int a = tx(), b = ty();
+        const uint32_t xl = s & ((1u << a) - 1u), yl = (s >> a) & ((1u << b) - 1u);
+        const uint32_t xh = (s >> (a + b)) & ((1u << (lw - a)) - 1u), yh = s >> (lw + b);
+        *ux = xl | (xh << a);
+        *uy = yl | (yh << b);
     }
     __host__ __device__ __forceinline__ uint32_t n_slots() const { return 1u << (lw + lh); }
 };

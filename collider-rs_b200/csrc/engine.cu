@@ -63,8 +63,21 @@ struct cb200_ctx {
     DevBuf<uint8_t> kind, reit;
     DevBuf<uint32_t> group, mask;
     DevBuf<uint64_t> ids;
-    DevBuf<HbRec> rec;       // one device: rec[slot]; sharded: the visitor table (own records, then received ones)
-    DevBuf<uint32_t> gid;    // sharded: id rank per slot (== the id)
+    DevBuf<HbRec> rec;       // one device: rec[row]; sharded: the visitor table (own records, then received ones)
+    // table order (kernels.cuh "Table order"): label[row] = HbId rank (sharded: the id), ord[row] = index in the caller's
+    // arrays (one device: the same buffer as label), row_of[label] = row (one device only)
+    DevBuf<uint32_t> label, ord, row_of;
+    DevBuf<double> col_alt[11];
+    DevBuf<uint8_t> kind_alt, reit_alt;
+    DevBuf<uint32_t> group_alt, mask_alt, label_alt, ord_alt;
+    DevBuf<uint32_t> sort_key, src_row;
+    DevBuf<double> tmp_col;  // download_state staging
+    bool need_resort = false;
+    int resort_period = 16;  // bulk steps between re-sorts (0 = only after upload); CB200_RESORT_PERIOD overrides
+    uint32_t steps_since_resort = 0;
+    uint64_t resorts = 0;
+    uint32_t* d_ticket = nullptr;  // scan ticket, monotonically increasing
+    uint32_t ticket_base = 0, scan_epoch = 0;
     // sharding
     bool sharded = false;
     ShardGeom shard{};
@@ -246,6 +259,9 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
     if ((e = cudaMalloc(&c->d_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&c->d_key, sizeof(MinKey))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&c->d_ticket, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMemset(c->d_ticket, 0, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+    if (const char* rp = getenv("CB200_RESORT_PERIOD")) c->resort_period = std::max(0, atoi(rp));
     if ((e = cudaHostAlloc(&c->h_res, sizeof(StepResultDev), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer((void**)&c->d_res, c->h_res, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     for (auto& ev : c->ev_t)
@@ -262,7 +278,11 @@ void cb200_destroy(cb200_ctx* c) {
     for (auto& b : c->col) b.release();
     for (auto& b : c->nvel) b.release();
     c->kind.release(); c->reit.release(); c->group.release(); c->mask.release(); c->ids.release(); c->rec.release();
-    c->gid.release(); c->send.release(); c->send_count.release(); c->vmap.release();
+    c->label.release(); c->ord.release(); c->row_of.release(); c->send.release(); c->send_count.release(); c->vmap.release();
+    for (auto& b : c->col_alt) b.release();
+    c->kind_alt.release(); c->reit_alt.release(); c->group_alt.release(); c->mask_alt.release(); c->label_alt.release(); c->ord_alt.release();
+    c->sort_key.release(); c->src_row.release(); c->tmp_col.release();
+    if (c->d_ticket) cudaFree(c->d_ticket);
     c->slots.release(); c->tile_state.release(); c->entries.release();
     c->ov_pairs.release(); c->ov_table.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
@@ -283,8 +303,8 @@ int cb200_set_grid(cb200_ctx* ctx, int log2_w, int log2_h) {
         ctx->geom_forced = false;
         return CB200_OK;
     }
-    if (log2_w < 1 || log2_h < 1 || log2_w > 20 || log2_h > 20 || log2_w + log2_h < 12 || log2_w + log2_h > 28)
-        return fail(ctx, CB200_E_ARG, "grid period out of range (need 12 <= log2_w + log2_h <= 28)");
+    if (log2_w < 1 || log2_h < 1 || log2_w > 20 || log2_h > 20 || log2_w + log2_h < 12 || log2_w + log2_h > 26)
+        return fail(ctx, CB200_E_ARG, "grid period out of range (need 12 <= log2_w + log2_h <= 26)");
     ctx->geom = GridGeom{log2_w, log2_h};
     ctx->geom_forced = true;
     return CB200_OK;
@@ -296,6 +316,13 @@ int cb200_get_grid(cb200_ctx* ctx, int* log2_w, int* log2_h) {
     if (log2_h) *log2_h = ctx->geom.lh;
     return CB200_OK;
 }
+
+int cb200_set_resort_period(cb200_ctx* ctx, int steps) {
+    if (!ctx || steps < 0) return CB200_E_ARG;
+    ctx->resort_period = steps;
+    return CB200_OK;
+}
+uint64_t cb200_resort_count(const cb200_ctx* ctx) { return ctx ? ctx->resorts : 0; }
 
 void* cb200_host_alloc(uint64_t bytes) {
     void* p = nullptr;
@@ -334,15 +361,17 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
         CU(cudaMemcpyAsync(ctx->ids.p, v->id, n * 8, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemsetAsync(ctx->reit.p, 0, n, ctx->stream));
     }
+    CU(ctx->label.reserve(cap));
     if (ctx->sharded) {
-        // sharded tables: gid = id (ids must be dense enough to fit 31 bits); visitor table and halo buffers sized here
+        // sharded tables: label = id (ids must fit 31 bits); visitor table and halo buffers sized here
         std::vector<uint32_t> g(n);
         for (size_t i = 0; i < n; ++i) {
             if (v->id[i] >= ctx->id_space) return fail(ctx, CB200_E_ARG, "sharded mode requires ids < id_space");
             g[i] = (uint32_t)v->id[i];
         }
-        CU(ctx->gid.reserve(cap));
-        if (n) CU(cudaMemcpyAsync(ctx->gid.p, g.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx->ord.reserve(cap));
+        if (n) CU(cudaMemcpyAsync(ctx->label.p, g.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (n) k_iota_rows<<<((uint32_t)n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>((uint32_t)n, ctx->ord.p, nullptr);
         CU(cudaStreamSynchronize(ctx->stream));
         // halo slab: header + room for n/256 (>= 2047) records leaving the strip (cb200_shard_set_slab overrides); the
         // visitor table holds the n own records followed by one received slab per rank
@@ -353,7 +382,12 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
         CU(ctx->vmap.reserve(ctx->id_space));
         CU(cudaMemsetAsync(ctx->vmap.p, 0xff, ctx->id_space * 4, ctx->stream));
         CU(cudaMemsetAsync(ctx->rec.p + n, 0, (size_t)ctx->slab * ctx->shard.world * sizeof(HbRec), ctx->stream));
+    } else {
+        CU(ctx->row_of.reserve(cap));
+        if (n) k_iota_rows<<<((uint32_t)n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>((uint32_t)n, ctx->label.p, ctx->row_of.p);
     }
+    ctx->need_resort = true;
+    ctx->steps_since_resort = 0;
     choose_geom(ctx, v);
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->n = (uint32_t)n;
@@ -372,8 +406,16 @@ int cb200_download_state(cb200_ctx* ctx, const cb200_state_out* o) {
     if (o->n < ctx->n) return fail(ctx, CB200_E_ARG, "state_out capacity too small");
     CU(cudaSetDevice(ctx->device));
     double* dst[11] = {o->pos_x, o->pos_y, o->dim_x, o->dim_y, o->vel_x, o->vel_y, o->rsz_x, o->rsz_y, o->start_time, o->end_time, o->pub_end_time};
+    // rows are in grid-slot order: put every column back into the caller's order on the device, then copy
+    const uint32_t n = ctx->n;
+    if (n) CU(ctx->tmp_col.reserve(n));
+    const uint32_t* ord = ctx->sharded ? ctx->ord.p : ctx->label.p;
     for (int k = 0; k < 11; ++k)
-        if (dst[k] && ctx->n) CU(cudaMemcpyAsync(dst[k], ctx->col[k].p, (size_t)ctx->n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (dst[k] && n) {
+            k_unpermute<<<(n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(n, ord, ctx->col[k].p, ctx->tmp_col.p);
+            ctx->launches += 1;
+            CU(cudaMemcpyAsync(dst[k], ctx->tmp_col.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
     CU(cudaStreamSynchronize(ctx->stream));
     return CB200_OK;
 }
@@ -438,11 +480,71 @@ static ShardGeom whole_world() {
     return g;
 }
 
+static int launch_scan(cb200_ctx* ctx, bool record_totals) {
+    const uint32_t n_slots = ctx->geom.n_slots();
+    ScanArgs sa{};
+    sa.data = ctx->slots.p;
+    sa.n = n_slots;
+    sa.chunks = std::min<uint32_t>(n_slots / kScanTile, kScanMaxChunks);
+    sa.state = ctx->tile_state.p;
+    sa.epoch = ++ctx->scan_epoch;
+    sa.ticket = ctx->d_ticket;
+    sa.ticket_base = ctx->ticket_base;
+    sa.ctr = record_totals ? ctx->d_ctr : nullptr;
+    ctx->ticket_base += sa.chunks;
+    k_scan_slots<<<sa.chunks, kThreads, 0, ctx->stream>>>(sa);
+    ctx->launches += 1;
+    return CB200_OK;
+}
+
+// Put the table rows into grid-slot order of their centre cells (kernels.cuh "Table order").
+static int resort_rows(cb200_ctx* ctx) {
+    const uint32_t n = ctx->n;
+    ctx->need_resort = false;
+    ctx->steps_since_resort = 0;
+    if (n < 2) return CB200_OK;
+    const uint32_t n_slots = ctx->geom.n_slots();
+    const uint32_t blocks = (n + kThreads - 1) / kThreads;
+    for (int k = 0; k < 11; ++k) CU(ctx->col_alt[k].reserve(ctx->col[k].cap));
+    CU(ctx->kind_alt.reserve(ctx->kind.cap)); CU(ctx->reit_alt.reserve(ctx->reit.cap)); CU(ctx->group_alt.reserve(ctx->group.cap));
+    CU(ctx->mask_alt.reserve(ctx->mask.cap)); CU(ctx->label_alt.reserve(ctx->label.cap));
+    if (ctx->sharded) CU(ctx->ord_alt.reserve(ctx->ord.cap));
+    CU(ctx->sort_key.reserve(n)); CU(ctx->src_row.reserve(n));
+    CU(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_slots * 4, ctx->stream));
+    k_resort_count<<<blocks, kThreads, 0, ctx->stream>>>(n, ctx->col[0].p, ctx->col[1].p, ctx->cell_width, ctx->geom, ctx->slots.p, ctx->sort_key.p);
+    int rc = launch_scan(ctx, false);
+    if (rc != CB200_OK) return rc;
+    k_resort_rank<<<blocks, kThreads, 0, ctx->stream>>>(n, ctx->sort_key.p, ctx->slots.p, ctx->src_row.p);
+    ResortCols rc_{};
+    for (int k = 0; k < 11; ++k) {
+        rc_.in[k] = ctx->col[k].p;
+        rc_.out[k] = ctx->col_alt[k].p;
+    }
+    rc_.kind_in = ctx->kind.p; rc_.kind_out = ctx->kind_alt.p;
+    rc_.reit_in = ctx->reit.p; rc_.reit_out = ctx->reit_alt.p;
+    rc_.group_in = ctx->group.p; rc_.group_out = ctx->group_alt.p;
+    rc_.mask_in = ctx->mask.p; rc_.mask_out = ctx->mask_alt.p;
+    rc_.label_in = ctx->label.p; rc_.label_out = ctx->label_alt.p;
+    rc_.ord_in = ctx->sharded ? ctx->ord.p : nullptr; rc_.ord_out = ctx->sharded ? ctx->ord_alt.p : nullptr;
+    rc_.row_of = ctx->sharded ? nullptr : ctx->row_of.p;
+    k_resort_gather<<<blocks, kThreads, 0, ctx->stream>>>(n, ctx->src_row.p, rc_);
+    ctx->launches += 3;
+    for (int k = 0; k < 11; ++k) std::swap(ctx->col[k], ctx->col_alt[k]);
+    std::swap(ctx->kind, ctx->kind_alt); std::swap(ctx->reit, ctx->reit_alt); std::swap(ctx->group, ctx->group_alt);
+    std::swap(ctx->mask, ctx->mask_alt); std::swap(ctx->label, ctx->label_alt);
+    if (ctx->sharded) std::swap(ctx->ord, ctx->ord_alt);
+    ctx->resorts += 1;
+    return CB200_OK;
+}
+
 static int prepare_buffers(cb200_ctx* ctx) {
     const uint32_t n = ctx->n;
     const uint32_t n_slots = ctx->geom.n_slots();
     CU(ctx->slots.reserve(n_slots));
-    CU(ctx->tile_state.reserve(n_slots / kScanTile));
+    if (ctx->tile_state.cap == 0) {
+        CU(ctx->tile_state.reserve(kScanMaxChunks));
+        CU(cudaMemsetAsync(ctx->tile_state.p, 0, kScanMaxChunks * 8, ctx->stream));
+    }
     if (ctx->entries.cap == 0) CU(ctx->entries.reserve((size_t)n * 4 + 1024));
     if (ctx->cand.cap == 0) CU(ctx->cand.reserve((size_t)n * 2 + 1024));
     if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
@@ -450,6 +552,12 @@ static int prepare_buffers(cb200_ctx* ctx) {
     ctx->grid_a = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, ctx->sm_count * per_sm));
     ctx->grid_p = ctx->sm_count * per_sm;
     CU(ctx->partial.reserve(ctx->grid_a + ctx->grid_p));
+    // the rows of the previous step's records move with a re-sort: only between steps, never on a re-run
+    if (ctx->need_resort || (ctx->resort_period > 0 && ctx->steps_since_resort >= (uint32_t)ctx->resort_period)) {
+        int rc = resort_rows(ctx);
+        if (rc != CB200_OK) return rc;
+    }
+    ctx->steps_since_resort += 1;
     return CB200_OK;
 }
 
@@ -458,11 +566,9 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     const uint32_t n = ctx->n;
     const GridGeom g = ctx->geom;
     const uint32_t n_slots = g.n_slots();
-    CU(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_slots * 4, ctx->stream));
-    CU(cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)(n_slots / kScanTile) * 8, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->stream));
-    CU(cudaMemsetAsync(&ctx->d_ctr->err_slot, 0xff, 8, ctx->stream));
-    if (ctx->sharded) CU(cudaMemsetAsync(ctx->send_count.p, 0, sizeof(uint32_t), ctx->stream));
+    k_step_zero<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(ctx->slots.p), n_slots / 4, ctx->d_ctr,
+                                                                  ctx->sharded ? ctx->send_count.p : nullptr);
+    ctx->launches += 1;
     CU(cudaEventRecord(ctx->ev_t[ST_STAGE_A], ctx->stream));
     StepArgs a{};
     a.n = n;
@@ -475,7 +581,8 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     a.nvx = do_rebase ? nv[0] : nullptr; a.nvy = do_rebase ? nv[1] : nullptr;
     a.nrw = do_rebase ? nv[2] : nullptr; a.nrh = do_rebase ? nv[3] : nullptr;
     a.nend = do_rebase ? nv[4] : ctx->col[10].p;  // re-run: the user end_time is the stored pub_end_time
-    a.gid = ctx->sharded ? ctx->gid.p : nullptr;
+    a.label = ctx->label.p;
+    a.ord = ctx->sharded ? ctx->ord.p : ctx->label.p;
     a.rec = ctx->rec.p;
     a.slot_count = ctx->slots.p;
     a.geom = g;
@@ -519,7 +626,10 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
         else k_index_visitors<false><<<grid_i, kThreads, 0, ctx->stream>>>(ctx->rec.p, vs, ctx->d_ctr, ctx->slots.p, g, sh.col_lo, sh.col_hi, vmap);
         ctx->launches += 1;
     }
-    k_scan_slots<<<n_slots / kScanTile, kThreads, 0, ctx->stream>>>(ctx->slots.p, n_slots, ctx->tile_state.p, ctx->d_ctr);
+    {
+        int rc = launch_scan(ctx, true);
+        if (rc != CB200_OK) return rc;
+    }
     CU(cudaEventRecord(ctx->ev_t[ST_SCATTER], ctx->stream));
     if (n_vis_max) {
         const uint32_t cap_e = (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu);
@@ -554,15 +664,16 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     sv.n_partial_a = ctx->grid_a;
     sv.result = ctx->d_res;
     sv.local_key = ctx->d_key;
-    sv.vmap = use_map ? ctx->vmap.p : nullptr;
-    sv.id_space = (uint32_t)ctx->id_space;
+    sv.vmap = ctx->sharded ? (use_map ? ctx->vmap.p : nullptr) : ctx->row_of.p;
+    sv.id_space = ctx->sharded ? (uint32_t)ctx->id_space : ctx->n;
+    sv.sharded = ctx->sharded ? 1 : 0;
     sv.vs = vs;
     sv.col_lo = sh.col_lo;
     sv.col_hi = sh.col_hi;
     k_solve<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(sv);
     CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
     CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
-    ctx->launches += 3;
+    ctx->launches += 2;
     return CB200_OK;
 }
 
@@ -690,7 +801,7 @@ int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* co
     ctx->shard = g;
     ctx->id_space = id_space;
     ctx->sharded = true;
-    ctx->have_state = false;  // the table must be (re-)uploaded: sharded tables carry gid = id
+    ctx->have_state = false;  // the table must be (re-)uploaded: sharded tables carry label = id
     return CB200_OK;
 }
 
@@ -768,7 +879,6 @@ int cb200_shard_result(cb200_ctx* ctx, cb200_step_result* out) {
         z.n_solitaire = keep.n_solitaire;
         z.n_local = keep.n_local;
         CU(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_slots * 4, ctx->stream));
-        CU(cudaMemsetAsync(ctx->tile_state.p, 0, (size_t)(n_slots / kScanTile) * 8, ctx->stream));
         CU(cudaMemcpy(ctx->d_ctr, &z, sizeof(Counters), cudaMemcpyHostToDevice));
         if ((rc = enqueue_back(ctx, ctx->shard_T, true)) != CB200_OK) return rc;
         if ((rc = complete_step(ctx, ctx->shard_T, &again)) != CB200_OK) return rc;
@@ -796,7 +906,7 @@ static int sort_events(cb200_ctx* ctx) {
     CU(ctx->rs_hist.reserve((size_t)16 * n_blocks));
     CU(cudaMemsetAsync(&ctx->d_ctr->n_sort_keys, 0, 8, ctx->stream));
     CU(cudaMemsetAsync(&ctx->d_ctr->diff_hi, 0, 16, ctx->stream));
-    if (ctx->n) k_keys_solitaire<<<(ctx->n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(ctx->n, ctx->reit.p, ctx->col[9].p, ctx->sharded ? ctx->gid.p : nullptr, ctx->keys_a.p, ctx->d_ctr);
+    if (ctx->n) k_keys_solitaire<<<(ctx->n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(ctx->n, ctx->reit.p, ctx->col[9].p, ctx->label.p, ctx->keys_a.p, ctx->d_ctr);
     if (n_pairs) k_keys_pairs<<<((uint32_t)n_pairs + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>((uint32_t)n_pairs, ctx->events.p, ctx->keys_a.p, c.n_solitaire);
     k_key_diff<<<std::min<uint32_t>(n_blocks, 1024), kThreads, 0, ctx->stream>>>(nt, ctx->keys_a.p, ctx->d_ctr);
     ctx->launches += 3;
@@ -885,8 +995,8 @@ int cb200_fetch_cell_entries(cb200_ctx* ctx, int32_t* cell_x, int32_t* cell_y, u
     const uint32_t mw = (1u << ctx->geom.lw) - 1u, mh = (1u << ctx->geom.lh) - 1u;
     for (uint64_t i = 0; i < total && i < cap; ++i) {
         const CellEntry& r = h[i];
-        const uint32_t slot = r.slot_group & kSlotMask;
-        const uint32_t sxs = slot & mw, sys = slot >> ctx->geom.lw;
+        uint32_t sxs, sys;
+        ctx->geom.unslot(r.slot_group & kSlotMask, &sxs, &sys);
         // the unique cell of the rect that folds onto this slot
         const int32_t x = r.sx + (int32_t)((sxs - (uint32_t)r.sx) & mw), y = r.sy + (int32_t)((sys - (uint32_t)r.sy) & mh);
         if (cell_x) cell_x[i] = x;
@@ -902,13 +1012,17 @@ int cb200_fetch_index_rects(cb200_ctx* ctx, int32_t* rects, uint64_t cap_hitboxe
     if (ctx->sharded) return fail(ctx, CB200_E_STATE, "fetch_index_rects is a one-device debug view");
     if (cap_hitboxes < ctx->n) return fail(ctx, CB200_E_ARG, "rect buffer too small");
     CU(cudaSetDevice(ctx->device));
-    // strided D2H: first 16 bytes of every 96-byte record = sx, sy, span, gid -> decode the span
-    if (ctx->n) CU(cudaMemcpy2D(rects, 16, ctx->rec.p, sizeof(HbRec), 16, ctx->n, cudaMemcpyDeviceToHost));
+    // strided D2H: first 16 bytes of every 96-byte record = sx, sy, span, label -> decode the span, place by label
+    std::vector<int32_t> raw((size_t)ctx->n * 4);
+    if (ctx->n) CU(cudaMemcpy2D(raw.data(), 16, ctx->rec.p, sizeof(HbRec), 16, ctx->n, cudaMemcpyDeviceToHost));
     for (uint64_t i = 0; i < ctx->n; ++i) {
-        int32_t* r = rects + 4 * i;
-        const uint32_t span = (uint32_t)r[2];
-        r[2] = r[0] + (int32_t)(span & 0xffffu);
-        r[3] = r[1] + (int32_t)(span >> 16);
+        const int32_t* q = raw.data() + 4 * i;
+        const uint32_t span = (uint32_t)q[2], label = (uint32_t)q[3];
+        int32_t* r = rects + 4 * (size_t)label;
+        r[0] = q[0];
+        r[1] = q[1];
+        r[2] = q[0] + (int32_t)(span & 0xffffu);
+        r[3] = q[1] + (int32_t)(span >> 16);
     }
     return CB200_OK;
 }

@@ -13,7 +13,7 @@ namespace cb200 {
 
 constexpr int kThreads = 256;
 
-struct StateCols {  // SoA hitbox table, slot order == ascending HbId
+struct StateCols {  // SoA hitbox table; rows are kept in grid-slot order (k_resort_*), label[row] carries the HbId rank
     double *px, *py, *w, *h, *vx, *vy, *rw, *rh, *start, *end, *pub_end;
     uint8_t* kind;
     uint32_t *group, *mask;
@@ -37,7 +37,8 @@ struct StepArgs {
     double T, cell_width, padding, end_scalar;
     StateCols s;
     const double *nvx, *nvy, *nrw, *nrh, *nend;  // optional new velocity columns (device), null = keep
-    const uint32_t* gid;   // null: gid = table slot
+    const uint32_t* label; // label[row]: rank of the row's HbId in ascending-id order (sharded: the id itself)
+    const uint32_t* ord;   // ord[row]: index of the row's hitbox in the caller's (upload-order) arrays; one device: == label
     HbRec* rec;            // one device: rec[i].  Sharded: the visitor table, own records appended at [0, n_local)
     uint32_t* slot_count;  // one device only (the count is fused here)
     GridGeom geom;
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
             double vx = a.s.vx[i], vy = a.s.vy[i], rw = a.s.rw[i], rh = a.s.rh[i];
             const double start = a.s.start[i], pub_end_old = a.s.pub_end[i];
             const uint32_t kind = a.s.kind[i], group = a.s.group[i], mask = a.s.mask[i];
+            const uint32_t gid = a.label[i];
             const double T = a.T;
             uint32_t err = 0;
 
@@ -135,11 +137,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
             }
 
             // install the new velocity, validate
-            if (a.nvx) vx = a.nvx[i];
-            if (a.nvy) vy = a.nvy[i];
-            if (a.nrw) rw = a.nrw[i];
-            if (a.nrh) rh = a.nrh[i];
-            const double user_end = a.nend ? a.nend[i] : a.end_scalar;
+            // (the caller's arrays are in ascending-id order: gathered by label; a re-run reads the stored pub_end_time by row)
+            const uint32_t o = a.ord[i];
+            if (a.nvx) vx = __ldg(a.nvx + o);
+            if (a.nvy) vy = __ldg(a.nvy + o);
+            if (a.nrw) rw = __ldg(a.nrw + o);
+            if (a.nrh) rh = __ldg(a.nrh + o);
+            const double user_end = a.nend ? __ldg(a.nend + (a.rebase ? o : i)) : a.end_scalar;
             if (!(user_end >= T)) err |= kFEndTime;  // also catches NaN
             if (kind == (uint32_t)kCircle && !(rw == rh)) err |= kFCircleResize;
             if (!(w >= a.padding && h >= a.padding)) err |= kFTooSmall;
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
                     }
                 }
             }
-            if (err) report_error(a.ctr, err, i);
+            if (err) report_error(a.ctr, err, gid);
 
             // write back: state columns + pair-stage record
             a.s.px[i] = px; a.s.py[i] = py; a.s.w[i] = w; a.s.h[i] = h;
@@ -221,7 +225,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
             a.s.pub_end[i] = user_end;
             a.s.reit[i] = reit ? 1 : 0;
 
-            const uint32_t gid = a.gid ? a.gid[i] : i;
             rec.gid = gid;
             rec.dur = dur;
             rec.kgb = (kind & 1u) | (binned ? 2u : 0u) | ((has_group ? (group & 0xffu) : 0xffu) << 8);
@@ -302,98 +305,186 @@ __global__ void __launch_bounds__(kThreads) k_index_visitors(const HbRec* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Exclusive scan of the slot counts (single pass, decoupled look-back).  n is a multiple of the tile size.
-// tile_state[t]: bits 63..62 = flag (0 invalid, 1 tile aggregate, 2 inclusive prefix), low 32 bits value.
-constexpr int kScanItems = 16;
-constexpr int kScanTile = kThreads * kScanItems;
-
-__global__ void __launch_bounds__(kThreads) k_scan_slots(uint32_t* __restrict__ data, uint32_t n, unsigned long long* tile_state,
-                                                         Counters* ctr) {
-    __shared__ uint32_t s_tile, s_prefix;
-    __shared__ uint32_t s_warp[kThreads / 32];
-    if (threadIdx.x == 0) s_tile = atomicAdd(&ctr->scan_ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    uint4* p = reinterpret_cast<uint4*>(data + (size_t)tile * kScanTile + (size_t)threadIdx.x * kScanItems);
-    uint32_t v[kScanItems];
-#pragma unroll
-    for (int k = 0; k < kScanItems / 4; ++k) {
-        const uint4 q = p[k];
-        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-    }
-    uint32_t sum = 0, nonzero = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        sum += v[k];
-        nonzero += v[k] != 0;
-    }
-    // block exclusive scan of the per-thread sums
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t ws = lane < kThreads / 32 ? s_warp[lane] : 0;
-#pragma unroll
-        for (int o = 1; o < kThreads / 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
-            if (lane >= o) ws += t;
+// Step prologue: one kernel zeroes everything a step accumulates into (slot table, counters, halo count).
+__global__ void __launch_bounds__(kThreads) k_step_zero(uint4* slots4, uint32_t n4, Counters* ctr, uint32_t* send_count) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) slots4[i] = z;
+    if (blockIdx.x == 0) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(ctr);
+        if (threadIdx.x < sizeof(Counters) / 4) w[threadIdx.x] = 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ctr->err_slot = ~0ull;
+            if (send_count) *send_count = 0u;
         }
-        if (lane < kThreads / 32) s_warp[lane] = ws;  // inclusive over warps
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Exclusive scan of the slot counts: `chunks` co-resident blocks, one contiguous chunk of the table each.
+//   pass 1  chunk sum (+ non-empty slots) -> published as (epoch << 32 | sum)
+//   wait    every predecessor's sum of THIS epoch (a ticket orders the blocks, so predecessors are running)
+//   pass 2  re-read the chunk (L1/L2-hot) and write the exclusive prefixes
+// n is a power of two >= 4096; chunks = min(n / kScanTile, 512) <= the number of resident blocks, so the waits
+// cannot deadlock.  The epoch makes the state array self-cleaning: no memset between steps.
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kThreads * kScanItems;  // 4096
+constexpr uint32_t kScanMaxChunks = 512;
+
+struct ScanArgs {
+    uint32_t* data;
+    uint32_t n, chunks;
+    unsigned long long* state;  // [chunks]
+    uint32_t epoch;             // != any epoch left in `state` by earlier launches
+    uint32_t* ticket;           // monotonically increasing across launches
+    uint32_t ticket_base;       // value of *ticket before this launch
+    Counters* ctr;              // n_entries / n_cells receive the totals (null: not recorded)
+};
+
+__global__ void __launch_bounds__(kThreads) k_scan_slots(const ScanArgs a) {
+    __shared__ uint32_t s_chunk, s_prefix;
+    __shared__ uint32_t s_warp[kThreads / 32];
+    if (threadIdx.x == 0) s_chunk = atomicAdd(a.ticket, 1u) - a.ticket_base;
+    __syncthreads();
+    const uint32_t chunk = s_chunk;
+    const uint32_t per_chunk = a.n / a.chunks, tiles = per_chunk / kScanTile;
+    uint32_t* base = a.data + (size_t)chunk * per_chunk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // pass 1
+    uint32_t sum = 0, nonzero = 0;
+    for (uint32_t t = 0; t < tiles; ++t) {
+        const uint4* p = reinterpret_cast<const uint4*>(base + (size_t)t * kScanTile + (size_t)threadIdx.x * kScanItems);
+#pragma unroll
+        for (int k = 0; k < kScanItems / 4; ++k) {
+            const uint4 q = p[k];
+            sum += q.x + q.y + q.z + q.w;
+            nonzero += (q.x != 0) + (q.y != 0) + (q.z != 0) + (q.w != 0);
+        }
+    }
+    const unsigned long long packed = block_sum(((unsigned long long)nonzero << 32) | sum);  // valid in thread 0
+    if (threadIdx.x == 0) {
+        const uint32_t chunk_sum = (uint32_t)packed;
+        atomicExch(&a.state[chunk], ((unsigned long long)a.epoch << 32) | chunk_sum);
+        if (a.ctr && (packed >> 32)) atomicAdd(&a.ctr->n_cells, packed >> 32);
+        s_warp[0] = chunk_sum;
     }
     __syncthreads();
-    const uint32_t block_total = s_warp[kThreads / 32 - 1];
-    const uint32_t thread_excl = inc - sum + (warp ? s_warp[warp - 1] : 0);
-
-    // decoupled look-back by warp 0: 32 predecessor tiles per round
+    const uint32_t chunk_sum = s_warp[0];
+    __syncthreads();
+    // wait for the predecessors
     if (warp == 0) {
         uint32_t prefix = 0;
-        if (tile == 0) {
-            if (lane == 0) atomicExch(&tile_state[0], (2ull << 62) | block_total);
-        } else {
-            if (lane == 0) atomicExch(&tile_state[tile], (1ull << 62) | block_total);
-            int64_t j = (int64_t)tile - 1 - lane;  // lane 0 looks at the nearest predecessor
-            for (;;) {
-                unsigned long long st = 2ull << 62;  // tiles before tile 0: inclusive prefix 0
-                if (j >= 0) {
-                    do {
-                        st = *reinterpret_cast<volatile unsigned long long*>(&tile_state[j]);
-                    } while ((st >> 62) == 0);
-                }
-                const unsigned incl = __ballot_sync(0xffffffffu, (st >> 62) == 2);
-                // lanes up to and including the nearest inclusive tile contribute
-                const int stop = incl ? __ffs(incl) - 1 : 31;
-                uint32_t v = lane <= stop ? (uint32_t)st : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                prefix += v;
-                if (incl) break;
-                j -= 32;
-            }
-            if (lane == 0) atomicExch(&tile_state[tile], (2ull << 62) | (uint32_t)(prefix + block_total));
+        for (uint32_t j = lane; j < chunk; j += 32) {
+            unsigned long long st;
+            do {
+                st = *reinterpret_cast<volatile unsigned long long*>(&a.state[j]);
+            } while ((uint32_t)(st >> 32) != a.epoch);
+            prefix += (uint32_t)st;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) prefix += __shfl_xor_sync(0xffffffffu, prefix, o);
         if (lane == 0) {
             s_prefix = prefix;
-            if ((size_t)(tile + 1) * kScanTile >= n) ctr->n_entries = (unsigned long long)prefix + block_total;
+            if (a.ctr && chunk == a.chunks - 1) a.ctr->n_entries = (unsigned long long)prefix + chunk_sum;
         }
     }
-    const unsigned long long nz = block_sum(nonzero);  // contains the __syncthreads that publishes s_prefix
-    if (threadIdx.x == 0 && nz) atomicAdd(&ctr->n_cells, nz);
-    uint32_t run = s_prefix + thread_excl;
+    __syncthreads();
+    // pass 2
+    uint32_t carry = s_prefix;
+    for (uint32_t t = 0; t < tiles; ++t) {
+        uint4* p = reinterpret_cast<uint4*>(base + (size_t)t * kScanTile + (size_t)threadIdx.x * kScanItems);
+        uint32_t v[kScanItems];
+        uint32_t tsum = 0;
 #pragma unroll
-    for (int k = 0; k < kScanItems / 4; ++k) {
-        uint4 q;
-        q.x = run; run += v[4 * k];
-        q.y = run; run += v[4 * k + 1];
-        q.z = run; run += v[4 * k + 2];
-        q.w = run; run += v[4 * k + 3];
-        p[k] = q;
+        for (int k = 0; k < kScanItems / 4; ++k) {
+            const uint4 q = p[k];
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            tsum += q.x + q.y + q.z + q.w;
+        }
+        uint32_t inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        __syncthreads();  // s_warp readers of the previous tile are done
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) {
+            const uint32_t x = s_warp[w];
+            before += w < warp ? x : 0u;
+            total += x;
+        }
+        uint32_t run = carry + before + inc - tsum;
+#pragma unroll
+        for (int k = 0; k < kScanItems / 4; ++k) {
+            uint4 q;
+            q.x = run; run += v[4 * k];
+            q.y = run; run += v[4 * k + 1];
+            q.z = run; run += v[4 * k + 2];
+            q.w = run; run += v[4 * k + 3];
+            p[k] = q;
+        }
+        carry += total;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Table order.  Rows of the hitbox table are kept sorted by the grid slot of their centre cell, so that the
+// atomics of the binning, the entry writes of the scatter and the record gathers of the solve stage all land
+// in nearby cache lines.  The order only affects speed: ids travel in label[row], every result is keyed by label.
+// A re-sort is a counting sort over the slot table (count -> k_scan_slots -> rank) followed by one gather of all
+// columns into the alternate buffers; the engine runs it after upload and every few steps (drift is slow).
+__global__ void __launch_bounds__(kThreads) k_resort_count(uint32_t n, const double* __restrict__ px, const double* __restrict__ py, double cell_width,
+                                                           GridGeom geom, uint32_t* slot_count, uint32_t* key) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = geom.slot(f64_as_i32(floor(px[i] / cell_width)), f64_as_i32(floor(py[i] / cell_width)));
+    key[i] = s;
+    atomicAdd(&slot_count[s], 1u);
+}
+__global__ void __launch_bounds__(kThreads) k_resort_rank(uint32_t n, const uint32_t* __restrict__ key, uint32_t* cursor, uint32_t* src_row) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    src_row[atomicAdd(&cursor[key[i]], 1u)] = i;
+}
+struct ResortCols {
+    const double* in[11];
+    double* out[11];
+    const uint8_t *kind_in, *reit_in;
+    uint8_t *kind_out, *reit_out;
+    const uint32_t *group_in, *mask_in, *label_in, *ord_in;  // ord_in null: ord == label (one device)
+    uint32_t *group_out, *mask_out, *label_out, *ord_out;
+    uint32_t* row_of;  // label -> new row (null: not maintained)
+};
+__global__ void __launch_bounds__(kThreads) k_resort_gather(uint32_t n, const uint32_t* __restrict__ src_row, const ResortCols c) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = src_row[i];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) c.out[k][i] = c.in[k][s];
+    c.kind_out[i] = c.kind_in[s];
+    c.reit_out[i] = c.reit_in[s];
+    c.group_out[i] = c.group_in[s];
+    c.mask_out[i] = c.mask_in[s];
+    const uint32_t l = c.label_in[s];
+    c.label_out[i] = l;
+    if (c.ord_in) c.ord_out[i] = c.ord_in[s];
+    if (c.row_of) c.row_of[l] = i;
+}
+// Column in the caller's order for the host (download_state): out[ord[row]] = col[row].
+__global__ void __launch_bounds__(kThreads) k_unpermute(uint32_t n, const uint32_t* __restrict__ ord, const double* __restrict__ col, double* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[ord[i]] = col[i];
+}
+__global__ void __launch_bounds__(kThreads) k_iota_rows(uint32_t n, uint32_t* label, uint32_t* row_of) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (label) label[i] = i;
+    if (row_of) row_of[i] = i;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -624,17 +715,21 @@ struct SolveArgs {
     StepResultDev* result;   // mapped host memory
     MinKey* local_key;       // device copy of the local minimum (sharded: input of the all-gather min)
     // sharded: overlapping pairs are looked up by gid; only the owner-column rank solves them
-    const uint32_t* vmap;    // gid -> record index (entries may be stale: validated); null = one device (gid == record index)
+    const uint32_t* vmap;    // gid -> record index (entries may be stale: validated)
     uint32_t id_space;
+    int sharded;
     VisSpace vs;
     int32_t col_lo, col_hi;
 };
 
-// A vmap entry is trusted only if it names a record slot that is live in THIS step and that record carries the gid.
+// A map entry is trusted only if it names a record slot that is live in THIS step and that record carries the gid.
+// One device: vmap = row_of (label -> row; record index == row).  Sharded: vmap = gid -> visitor index.
 __device__ __forceinline__ bool gid_lookup(const SolveArgs& a, uint32_t n_local, uint32_t gid, uint32_t* vidx) {
     if (gid >= a.id_space) return false;
     const uint32_t v = __ldg(a.vmap + gid);
-    if (v >= n_local) {
+    if (!a.sharded) {
+        if (v >= a.vs.n_own) return false;
+    } else if (v >= n_local) {
         if (v < a.vs.n_own) return false;
         const uint32_t j = v - a.vs.n_own;
         if (j >= (uint32_t)a.vs.world * a.vs.slab) return false;
@@ -663,7 +758,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
             const bool sep = p >= n_cand;
             uint2 pr = sep ? a.ov_pairs[p - n_cand] : a.cand[p];
             bool present = true;
-            if (sep && a.vmap) present = gid_lookup(a, n_local, pr.x, &pr.x) && gid_lookup(a, n_local, pr.y, &pr.y);
+            if (sep) present = gid_lookup(a, n_local, pr.x, &pr.x) && gid_lookup(a, n_local, pr.y, &pr.y);
             if (present) {
                 const RecHead hh = load_head(a.rec, pr.x), hl = load_head(a.rec, pr.y);
                 const int32_t owner_col = max(hh.sx, hl.sx);

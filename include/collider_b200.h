@@ -61,8 +61,8 @@ enum {
 typedef struct cb200_ctx cb200_ctx;
 
 /* Host SoA view of the hitbox table: HitboxInfo fields (collider.rs:457-464) column by column.
- * `id` must be strictly ascending (slot order == HbId order; the canonical tie-break of SURVEY.md §8c
- * relies on it).  group: HbProfile::group() value in 0..31 or CB200_GROUP_NONE; interact_mask: bit g set
+ * `id` must be strictly ascending (array order == HbId order; the canonical tie-break of SURVEY.md §8c
+ * relies on the rank of an id).  group: HbProfile::group() value in 0..31 or CB200_GROUP_NONE; interact_mask: bit g set
  * iff g is in HbProfile::interact_groups() (core/mod.rs:218-231). */
 typedef struct cb200_state_view {
     uint64_t n;
@@ -135,6 +135,13 @@ int cb200_abi_version(void);
  * never correctness).  0,0 = choose from the uploaded extent (default). */
 int cb200_set_grid(cb200_ctx* ctx, int log2_w, int log2_h);
 int cb200_get_grid(cb200_ctx* ctx, int* log2_w, int* log2_h);
+
+/* Table order.  The device keeps the rows of the hitbox table sorted by the grid slot of their centre cell (so that
+ * binning atomics, entry writes and record gathers stay in nearby cache lines) and re-sorts them after an upload and
+ * then every `steps` bulk steps; 0 = only after an upload.  Default 16 (environment: CB200_RESORT_PERIOD).  The order
+ * affects speed only: every input and output of this API stays in the caller's (ascending-id) order. */
+int cb200_set_resort_period(cb200_ctx* ctx, int steps);
+uint64_t cb200_resort_count(const cb200_ctx* ctx);
 
 /* Pinned (page-locked) host memory for the arrays handed to upload_state / bulk_update / fetch_events, so that
  * the H2D / D2H copies inside those calls run at full PCIe speed.  Plain malloc'd memory is accepted too. */

@@ -176,6 +176,32 @@ def test_clustered_fast_small_shapes(oracle):
     assert_step_parity(orc, eng, res)
 
 
+@pytest.mark.parametrize("period", [0, 1, 3])
+def test_table_order_never_changes_results(oracle, period):
+    """The device keeps its rows in grid-slot order and re-sorts them every `period` steps (0: only after upload);
+    with new velocities arriving in id order and the state read back in id order, nothing may depend on it."""
+    n = 6000
+    scene = scenes.uniform_density(n, seed=991)
+    orc, eng = seeded(oracle, scene)
+    eng.set_resort_period(period)
+    T = 0.0
+    for step in range(5):
+        vx = scenes.uniform(500 + step, n, 1, -12.0, 12.0)  # fast enough to shuffle the cell order between steps
+        vy = scenes.uniform(500 + step, n, 2, -12.0, 12.0)
+        orc.bulk_update(end_time=T + 0.3, vx=vx, vy=vy, record_candidates=True)
+        res = eng.bulk_update(T, end_time=T + 0.3, vel_x=vx, vel_y=vy)
+        assert_step_parity(orc, eng, res, check_grid=(step == 4))
+        T += 0.3
+        drain_until(orc, T)
+        eng.set_overlaps(*orc.dump_overlaps())
+    assert eng.resort_count() == (1 if period == 0 else 1 + 4 // period)
+    rects = eng.fetch_index_rects()
+    gx, gy, gg, gi = orc.dump_grid()
+    for i in (0, 17, n - 1):  # fetch_index_rects is in id order
+        sel = gi == i
+        assert (rects[i][0], rects[i][1], rects[i][2], rects[i][3]) == (gx[sel].min(), gy[sel].min(), gx[sel].max() + 1, gy[sel].max() + 1)
+
+
 def test_aliased_grid_is_still_exact(oracle):
     """Force a tiny grid period so that many cells share a slot: results must not change."""
     scene = scenes.uniform_density(5000)
