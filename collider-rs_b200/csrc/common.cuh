@@ -69,6 +69,31 @@ __device__ __forceinline__ DurHb load_body(const HbRec* __restrict__ rec, uint32
     return r;
 }
 
+// Coherent (plain ld.global) variants for kernels that read records written earlier in the same launch.
+__device__ __forceinline__ RecHead load_head_nc(const HbRec* rec, uint32_t i) {
+    const int4* p = reinterpret_cast<const int4*>(rec + i);
+    const int4 a = p[0], b = p[1];
+    RecHead h;
+    h.sx = a.x; h.sy = a.y;
+    h.ex = a.x + (int32_t)((uint32_t)a.z & 0xffffu);
+    h.ey = a.y + (int32_t)((uint32_t)a.z >> 16);
+    h.gid = (uint32_t)a.w;
+    h.dur = __hiloint2double(b.y, b.x);
+    h.kgb = (uint32_t)b.z;
+    h.mask = (uint32_t)b.w;
+    return h;
+}
+__device__ __forceinline__ DurHb load_body_nc(const HbRec* rec, uint32_t i, const RecHead& h) {
+    const double2* p = reinterpret_cast<const double2*>(rec + i);
+    const double2 a = p[2], b = p[3], c = p[4], d = p[5];
+    DurHb r;
+    r.px = a.x; r.py = a.y; r.w = b.x; r.h = b.y;
+    r.vx = c.x; r.vy = c.y; r.rw = d.x; r.rh = d.y;
+    r.dur = h.dur;
+    r.kind = (int)(h.kgb & 1u);
+    return r;
+}
+
 // One pair event queued by a step: time, creator (higher slot), partner (lower slot) | kind bit.
 struct alignas(16) PairEvent {
     double time;

@@ -8,11 +8,14 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/collider_b200.h"
 #include "kernels.cuh"
+#include "single.cuh"
 #include "sort.cuh"
 
 using namespace cb200;
@@ -76,6 +79,8 @@ struct cb200_ctx {
     int resort_period = 16;  // bulk steps between re-sorts (0 = only after upload); CB200_RESORT_PERIOD overrides
     uint32_t steps_since_resort = 0;
     uint64_t resorts = 0;
+    uint8_t* collider_dirty = nullptr;        // incremental API (collider.inl): dirty-row flags, emptied by a bulk step
+    uint32_t* collider_dirty_count = nullptr;
     uint32_t* d_ticket = nullptr;  // scan ticket, monotonically increasing
     uint32_t ticket_base = 0, scan_epoch = 0;
     // sharding
@@ -569,6 +574,10 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     k_step_zero<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(ctx->slots.p), n_slots / 4, ctx->d_ctr,
                                                                   ctx->sharded ? ctx->send_count.p : nullptr);
     ctx->launches += 1;
+    if (ctx->collider_dirty && n) {
+        CU(cudaMemsetAsync(ctx->collider_dirty, 0, n, ctx->stream));
+        CU(cudaMemsetAsync(ctx->collider_dirty_count, 0, 4, ctx->stream));
+    }
     CU(cudaEventRecord(ctx->ev_t[ST_STAGE_A], ctx->stream));
     StepArgs a{};
     a.n = n;
@@ -1094,3 +1103,5 @@ int cb200_reset_timing(cb200_ctx* ctx) {
 }
 
 }  // extern "C"
+
+#include "collider.inl"

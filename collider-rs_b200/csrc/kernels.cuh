@@ -105,6 +105,123 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 
+// The per-hitbox part of Collider::internal_update_hitbox (collider.rs:231-250), shared by the bulk stage A and by the
+// single-hitbox update (single.cuh).  `h` enters as the stored hitbox (shape at its start_time) and leaves rebased to T
+// with the new velocity installed; returns the error flags (h is then not to be stored).
+struct HbCore {
+    double px, py, w, h, vx, vy, rw, rh;  // Hitbox.value / Hitbox.vel
+    double start, pub_end;                 // HitboxInfo.start_time / pub_end_time (in: stored; out: T / user end_time)
+    double end;                            // out: internal end_time = min(cell period, user end, too-small)  (collider.rs:420-448)
+    double dur;                            // out: end - T
+    uint32_t kind, group, mask;
+    int32_t sx, sy, ex, ey;                // out: IndexRect (valid when binned)
+    bool reit, binned;                     // out: Reiterate queued at `end`; entered the grid
+};
+struct NewVel {
+    bool has_vx, has_vy, has_rw, has_rh;
+    double vx, vy, rw, rh, end_time;
+};
+__device__ __forceinline__ uint32_t hb_update_core(HbCore& h, double T, bool rebase, const NewVel& nv, double cell_width, double padding,
+                                                   const GridGeom& geom) {
+    uint32_t err = 0;
+    // pub_hitbox_at_time(T): assert start <= T <= pub_end, then advance by T - start.
+    if (!(T >= h.start && T <= h.pub_end)) err |= kFInvalidTime;
+    const double dt = T - h.start;
+    if (!(dt < kHighTime)) err |= kFHighTime;
+    if (rebase) {
+        h.px = h.px + h.vx * dt;
+        h.py = h.py + h.vy * dt;
+        h.w = h.w + h.rw * dt;
+        h.h = h.h + h.rh * dt;
+    }
+    // install the new velocity, validate (core/mod.rs:146-162)
+    if (nv.has_vx) h.vx = nv.vx;
+    if (nv.has_vy) h.vy = nv.vy;
+    if (nv.has_rw) h.rw = nv.rw;
+    if (nv.has_rh) h.rh = nv.rh;
+    const double user_end = nv.end_time;
+    if (!(user_end >= T)) err |= kFEndTime;  // also catches NaN
+    if (h.kind == (uint32_t)kCircle && !(h.rw == h.rh)) err |= kFCircleResize;
+    if (!(h.w >= padding && h.h >= padding)) err |= kFTooSmall;
+    if (!(is_finite(h.px) && is_finite(h.py) && is_finite(h.w) && is_finite(h.h) && is_finite(h.vx) && is_finite(h.vy) && is_finite(h.rw) &&
+          is_finite(h.rh)))
+        err |= kFNan;
+
+    // solitaire_event_check (release build)
+    const bool has_group = h.group != kGroupNone;
+    double period = cb_inf();
+    if (has_group) {
+        const double speed = fmax(fmax(fabs(h.vx - h.rw * 0.5), fabs(h.vy - h.rh * 0.5)), fmax(fabs(h.vx + h.rw * 0.5), fabs(h.vy + h.rh * 0.5)));
+        if (!(speed <= 0.0)) period = cell_width / speed;
+    }
+    double r_time = T + period;
+    bool reit = true;
+    if (user_end < r_time) {
+        r_time = user_end;
+        reit = false;
+    }
+    {
+        const double min_size = padding * 0.9;
+        if (!(h.w > min_size && h.h > min_size)) err |= kFTooSmall;
+        double tus = cb_inf();
+        if (h.rw < 0.0) tus = fmin(tus, (min_size - h.w) / h.rw);
+        if (h.rh < 0.0) tus = fmin(tus, (min_size - h.h) / h.rh);
+        const double small_end = T + tus;
+        if (small_end < r_time) {
+            r_time = small_end;
+            reit = false;
+        }
+    }
+    reit = reit && (r_time < kHighTime);  // EventManager::new_event_key drops time >= 1e50 (events.rs:156-159)
+    const double dur = r_time - T;
+
+    // swept bounds + IndexRect (only hitboxes with a group enter the grid, collider.rs:328)
+    h.sx = h.sy = h.ex = h.ey = 0;
+    h.binned = false;
+    if (has_group && err == 0) {
+        DurHb d;
+        d.px = h.px; d.py = h.py; d.w = h.w; d.h = h.h; d.vx = h.vx; d.vy = h.vy; d.rw = h.rw; d.rh = h.rh; d.dur = dur; d.kind = (int)h.kind;
+        const Box4 bb = swept_bounds(d, dur);
+        if (!bb.ok) {
+            err |= (dur < kHighTime) ? kFNan : kFHighTime;
+        } else {
+            const double min_x = bb.cx - bb.w * 0.5, max_x = bb.cx + bb.w * 0.5;
+            const double min_y = bb.cy - bb.h * 0.5, max_y = bb.cy + bb.h * 0.5;
+            const int32_t sx = f64_as_i32(floor(min_x / cell_width));
+            const int32_t sy = f64_as_i32(floor(min_y / cell_width));
+            const int32_t ex = max(f64_as_i32(ceil(max_x / cell_width)), (int32_t)((uint32_t)sx + 1u));
+            const int32_t ey = max(f64_as_i32(ceil(max_y / cell_width)), (int32_t)((uint32_t)sy + 1u));
+            const int64_t nx = (int64_t)ex - sx, ny = (int64_t)ey - sy;
+            if (nx <= 0 || ny <= 0) {
+                err |= kFEmptyRect;  // IndexRect::new (index_rect.rs:26-29)
+            } else if (nx > (1ll << geom.lw) || ny > (1ll << geom.lh) || nx > 0xffff || ny > 0xffff) {
+                err |= kFRectSpan;
+            } else {
+                h.sx = sx; h.sy = sy; h.ex = ex; h.ey = ey;
+                h.binned = true;
+            }
+        }
+    }
+    h.start = T;
+    h.pub_end = user_end;
+    h.end = r_time;
+    h.dur = dur;
+    h.reit = reit;
+    return err;
+}
+__device__ __forceinline__ HbRec make_rec(const HbCore& h, uint32_t gid) {
+    HbRec rec;
+    rec.sx = h.sx; rec.sy = h.sy;
+    rec.span = h.binned ? ((uint32_t)(h.ex - h.sx) | ((uint32_t)(h.ey - h.sy) << 16)) : 0u;
+    rec.gid = gid;
+    rec.dur = h.dur;
+    rec.kgb = (h.kind & 1u) | (h.binned ? 2u : 0u) | ((h.group != kGroupNone ? (h.group & 0xffu) : 0xffu) << 8);
+    rec.mask = h.mask;
+    rec.px = h.px; rec.py = h.py; rec.w = h.w; rec.h = h.h;
+    rec.vx = h.vx; rec.vy = h.vy; rec.rw = h.rw; rec.rh = h.rh;
+    return rec;
+}
+
 template <bool SHARDED>
 __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const ShardGeom sh) {
     __shared__ uint32_t s_base;
@@ -117,120 +234,46 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
         HbRec rec;
         int32_t ex = 0;
         if (i < a.n) {
-            double px = a.s.px[i], py = a.s.py[i], w = a.s.w[i], h = a.s.h[i];
-            double vx = a.s.vx[i], vy = a.s.vy[i], rw = a.s.rw[i], rh = a.s.rh[i];
-            const double start = a.s.start[i], pub_end_old = a.s.pub_end[i];
-            const uint32_t kind = a.s.kind[i], group = a.s.group[i], mask = a.s.mask[i];
+            HbCore h;
+            h.px = a.s.px[i]; h.py = a.s.py[i]; h.w = a.s.w[i]; h.h = a.s.h[i];
+            h.vx = a.s.vx[i]; h.vy = a.s.vy[i]; h.rw = a.s.rw[i]; h.rh = a.s.rh[i];
+            h.start = a.s.start[i]; h.pub_end = a.s.pub_end[i];
+            h.kind = a.s.kind[i]; h.group = a.s.group[i]; h.mask = a.s.mask[i];
             const uint32_t gid = a.label[i];
-            const double T = a.T;
-            uint32_t err = 0;
-
-            // pub_hitbox_at_time(T): assert start <= T <= pub_end, then advance by T - start.
-            if (!(T >= start && T <= pub_end_old)) err |= kFInvalidTime;
-            const double dt = T - start;
-            if (!(dt < kHighTime)) err |= kFHighTime;
-            if (a.rebase) {
-                px = px + vx * dt;
-                py = py + vy * dt;
-                w = w + rw * dt;
-                h = h + rh * dt;
-            }
-
-            // install the new velocity, validate
-            // (the caller's arrays are in ascending-id order: gathered by label; a re-run reads the stored pub_end_time by row)
+            // (the caller's arrays are in upload order: gathered through ord; a re-run reads the stored pub_end_time by row)
             const uint32_t o = a.ord[i];
-            if (a.nvx) vx = __ldg(a.nvx + o);
-            if (a.nvy) vy = __ldg(a.nvy + o);
-            if (a.nrw) rw = __ldg(a.nrw + o);
-            if (a.nrh) rh = __ldg(a.nrh + o);
-            const double user_end = a.nend ? __ldg(a.nend + (a.rebase ? o : i)) : a.end_scalar;
-            if (!(user_end >= T)) err |= kFEndTime;  // also catches NaN
-            if (kind == (uint32_t)kCircle && !(rw == rh)) err |= kFCircleResize;
-            if (!(w >= a.padding && h >= a.padding)) err |= kFTooSmall;
-            if (!(is_finite(px) && is_finite(py) && is_finite(w) && is_finite(h) && is_finite(vx) && is_finite(vy) && is_finite(rw) &&
-                  is_finite(rh)))
-                err |= kFNan;
-
-            // solitaire_event_check (release build)
-            const bool has_group = group != kGroupNone;
-            double period = cb_inf();
-            if (has_group) {
-                const double speed = fmax(fmax(fabs(vx - rw * 0.5), fabs(vy - rh * 0.5)), fmax(fabs(vx + rw * 0.5), fabs(vy + rh * 0.5)));
-                if (!(speed <= 0.0)) period = a.cell_width / speed;
-            }
-            double r_time = T + period;
-            bool reit = true;
-            if (user_end < r_time) {
-                r_time = user_end;
-                reit = false;
-            }
-            {
-                const double min_size = a.padding * 0.9;
-                if (!(w > min_size && h > min_size)) err |= kFTooSmall;
-                double tus = cb_inf();
-                if (rw < 0.0) tus = fmin(tus, (min_size - w) / rw);
-                if (rh < 0.0) tus = fmin(tus, (min_size - h) / rh);
-                const double small_end = T + tus;
-                if (small_end < r_time) {
-                    r_time = small_end;
-                    reit = false;
-                }
-            }
-            reit = reit && (r_time < kHighTime);  // EventManager::new_event_key drops time >= 1e50 (events.rs:156-159)
-            const double dur = r_time - T;
-
-            // swept bounds + IndexRect (only hitboxes with a group enter the grid, collider.rs:328)
-            rec.sx = rec.sy = 0;
-            rec.span = 0;
-            bool binned = false;
-            if (has_group && err == 0) {
-                DurHb d;
-                d.px = px; d.py = py; d.w = w; d.h = h; d.vx = vx; d.vy = vy; d.rw = rw; d.rh = rh; d.dur = dur; d.kind = (int)kind;
-                const Box4 bb = swept_bounds(d, dur);
-                if (!bb.ok) {
-                    err |= (dur < kHighTime) ? kFNan : kFHighTime;
-                } else {
-                    const double min_x = bb.cx - bb.w * 0.5, max_x = bb.cx + bb.w * 0.5;
-                    const double min_y = bb.cy - bb.h * 0.5, max_y = bb.cy + bb.h * 0.5;
-                    const int32_t sx = f64_as_i32(floor(min_x / a.cell_width));
-                    const int32_t sy = f64_as_i32(floor(min_y / a.cell_width));
-                    ex = max(f64_as_i32(ceil(max_x / a.cell_width)), (int32_t)((uint32_t)sx + 1u));
-                    const int32_t ey = max(f64_as_i32(ceil(max_y / a.cell_width)), (int32_t)((uint32_t)sy + 1u));
-                    const int64_t nx = (int64_t)ex - sx, ny = (int64_t)ey - sy;
-                    if (nx <= 0 || ny <= 0) {
-                        err |= kFEmptyRect;  // IndexRect::new (index_rect.rs:26-29)
-                    } else if (nx > (1ll << a.geom.lw) || ny > (1ll << a.geom.lh) || nx > 0xffff || ny > 0xffff) {
-                        err |= kFRectSpan;
-                    } else {
-                        rec.sx = sx; rec.sy = sy;
-                        rec.span = (uint32_t)nx | ((uint32_t)ny << 16);
-                        binned = true;
-                        // cell count (sharded: only the cells inside the own strip)
-                        const int32_t x0 = SHARDED ? max(sx, sh.col_lo) : sx, x1 = SHARDED ? min(ex, sh.col_hi) : ex;
-                        for (int32_t x = x0; x < x1; ++x)
-                            for (int32_t y = sy; y != ey; ++y) atomicAdd(&a.slot_count[a.geom.slot(x, y)], 1u);
-                    }
-                }
+            NewVel nv;
+            nv.has_vx = a.nvx != nullptr; nv.has_vy = a.nvy != nullptr; nv.has_rw = a.nrw != nullptr; nv.has_rh = a.nrh != nullptr;
+            nv.vx = nv.has_vx ? __ldg(a.nvx + o) : 0.0;
+            nv.vy = nv.has_vy ? __ldg(a.nvy + o) : 0.0;
+            nv.rw = nv.has_rw ? __ldg(a.nrw + o) : 0.0;
+            nv.rh = nv.has_rh ? __ldg(a.nrh + o) : 0.0;
+            nv.end_time = a.nend ? __ldg(a.nend + (a.rebase ? o : i)) : a.end_scalar;
+            const uint32_t err = hb_update_core(h, a.T, a.rebase != 0, nv, a.cell_width, a.padding, a.geom);
+            ex = h.ex;
+            if (h.binned) {
+                // cell count (sharded: only the cells inside the own strip)
+                const int32_t x0 = SHARDED ? max(h.sx, sh.col_lo) : h.sx, x1 = SHARDED ? min(h.ex, sh.col_hi) : h.ex;
+                for (int32_t x = x0; x < x1; ++x)
+                    for (int32_t y = h.sy; y != h.ey; ++y) atomicAdd(&a.slot_count[a.geom.slot(x, y)], 1u);
             }
             if (err) report_error(a.ctr, err, gid);
 
             // write back: state columns + pair-stage record
-            a.s.px[i] = px; a.s.py[i] = py; a.s.w[i] = w; a.s.h[i] = h;
-            if (a.nvx) a.s.vx[i] = vx;
-            if (a.nvy) a.s.vy[i] = vy;
-            if (a.nrw) a.s.rw[i] = rw;
-            if (a.nrh) a.s.rh[i] = rh;
-            a.s.start[i] = T;
-            a.s.end[i] = r_time;
-            a.s.pub_end[i] = user_end;
-            a.s.reit[i] = reit ? 1 : 0;
+            a.s.px[i] = h.px; a.s.py[i] = h.py; a.s.w[i] = h.w; a.s.h[i] = h.h;
+            if (a.nvx) a.s.vx[i] = h.vx;
+            if (a.nvy) a.s.vy[i] = h.vy;
+            if (a.nrw) a.s.rw[i] = h.rw;
+            if (a.nrh) a.s.rh[i] = h.rh;
+            a.s.start[i] = h.start;
+            a.s.end[i] = h.end;
+            a.s.pub_end[i] = h.pub_end;
+            a.s.reit[i] = h.reit ? 1 : 0;
 
-            rec.gid = gid;
-            rec.dur = dur;
-            rec.kgb = (kind & 1u) | (binned ? 2u : 0u) | ((has_group ? (group & 0xffu) : 0xffu) << 8);
-            rec.mask = mask;
-            rec.px = px; rec.py = py; rec.w = w; rec.h = h;
-            rec.vx = vx; rec.vy = vy; rec.rw = rw; rec.rh = rh;
+            rec = make_rec(h, gid);
+            const bool binned = h.binned;
+            const bool reit = h.reit;
+            const double r_time = h.end;
             if (!SHARDED) {
                 store_rec(a.rec + i, rec);
             } else if (binned) {

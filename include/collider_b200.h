@@ -215,6 +215,65 @@ int cb200_collide_time_batch(cb200_ctx* ctx, uint64_t n, const double* a, const 
 int cb200_separate_time_batch(cb200_ctx* ctx, uint64_t n, const double* a, const uint8_t* kind_a, const double* b, const uint8_t* kind_b,
                               double padding, double* out);
 
+/* ---- The reference's `Collider<P: HbProfile>` API on the device (src/core/collider.rs:59-318) ---------------------------
+ * A cb200_collider owns one device context and mirrors the reference's public methods one to one; a Rust
+ * `Collider<P>` wrapper keeps a `HashMap<HbId, P>` and forwards every call.  All geometry — rebase,
+ * solitaire check, swept bounds, IndexRect, cell-mate enumeration, collide_time / separate_time, get_hitbox's advance,
+ * query_overlaps' shape test — runs in CUDA kernels; the host keeps only bookkeeping without arithmetic (id maps,
+ * HitboxInfo.overlaps, the order of the event queue, the clock).  Hitboxes may be added, re-aimed and removed one at a
+ * time (k_update_one against the device grid + a dirty list) or all at once (cb200_collider_bulk_update = the bulk step).
+ * Contract panics of the reference come back as CB200_E_CONTRACT with the reference's message.
+ * Simultaneous events are delivered in the canonical order of SURVEY.md 8c. */
+typedef struct cb200_collider cb200_collider;
+
+typedef struct cb200_hitbox { /* Hitbox (core/mod.rs:119-130): PlacedShape + HbVel */
+    double pos_x, pos_y, dim_x, dim_y; /* circle: dim_x == dim_y == diameter */
+    double vel_x, vel_y, rsz_x, rsz_y;
+    double end_time;                   /* HbVel.end_time (core/mod.rs:34-59) */
+    uint32_t kind;                     /* CB200_KIND_* */
+    uint32_t _pad;
+} cb200_hitbox;
+
+typedef struct cb200_profile { /* HbProfile (core/mod.rs:210-238) */
+    uint64_t id;            /* id() */
+    uint32_t group;         /* group(): 0..31 or CB200_GROUP_NONE */
+    uint32_t interact_mask; /* interact_groups() as a bit mask */
+} cb200_profile;
+
+/* HbProfile::can_interact (core/mod.rs:233-237), evaluated on the host for every candidate pair; NULL = always true. */
+typedef int (*cb200_can_interact_fn)(void* user, uint64_t id_a, uint64_t id_b);
+
+int cb200_collider_new(double cell_width, double padding, int device, cb200_collider** out); /* Collider::new      :59-69  */
+void cb200_collider_free(cb200_collider* c);
+const char* cb200_collider_last_error(const cb200_collider* c);
+int cb200_collider_set_can_interact(cb200_collider* c, cb200_can_interact_fn fn, void* user);
+double cb200_collider_time(const cb200_collider* c);                                          /* time               :72-74  */
+int cb200_collider_next_time(cb200_collider* c, double* out);                                 /* next_time          :85-87  */
+int cb200_collider_set_time(cb200_collider* c, double time);                                  /* set_time           :97-102 */
+/* next :113-124 — *has_event = 0 when no event is due at the current time; kind is CB200_EV_COLLIDE / CB200_EV_SEPARATE,
+ * id_1 < id_2.  Reiterate events are processed internally (collider.rs:164-174). */
+int cb200_collider_next(cb200_collider* c, int* has_event, uint32_t* kind, uint64_t* id_1, uint64_t* id_2);
+int cb200_collider_get_hitbox(cb200_collider* c, uint64_t id, cb200_hitbox* out);             /* get_hitbox         :200-202 */
+/* add_hitbox :214-222 — ids of the hitboxes the new one overlaps immediately (ascending), at most `cap` written, *n_out = count */
+int cb200_collider_add_hitbox(cb200_collider* c, const cb200_profile* profile, const cb200_hitbox* hitbox, uint64_t* overlaps, uint64_t cap,
+                              uint64_t* n_out);
+int cb200_collider_set_hitbox_vel(cb200_collider* c, uint64_t id, double vel_x, double vel_y, double rsz_x, double rsz_y,
+                                  double end_time);                                           /* set_hitbox_vel     :225-229 */
+int cb200_collider_remove_hitbox(cb200_collider* c, uint64_t id, uint64_t* overlaps, uint64_t cap, uint64_t* n_out); /* :256-275 */
+int cb200_collider_get_overlaps(cb200_collider* c, uint64_t id, uint64_t* out, uint64_t cap, uint64_t* n_out);       /* :279-288 */
+int cb200_collider_is_overlapping(cb200_collider* c, uint64_t id_1, uint64_t id_2, int* out);                        /* :300-305 */
+int cb200_collider_query_overlaps(cb200_collider* c, uint32_t kind, double pos_x, double pos_y, double dim_x, double dim_y,
+                                  const cb200_profile* profile, uint64_t* out, uint64_t cap, uint64_t* n_out);       /* :309-318 */
+/* The bulk advance/rebuild entry point on a Collider: at the current time, for id ascending,
+ * internal_update_hitbox(id, Some(vel_id)) — one device pass (cb200_bulk_update).  `vel` arrays are in ascending-id order. */
+int cb200_collider_bulk_update(cb200_collider* c, const cb200_vel_view* vel, double end_time, cb200_step_result* out);
+uint64_t cb200_collider_len(const cb200_collider* c);
+/* Rows changed since the grid was last rebuilt are kept on a dirty list that every single-hitbox operation scans; the
+ * grid is rebuilt on the device (count / scan / scatter, no solve) when the list exceeds this many rows.  Default 4096. */
+int cb200_collider_set_rebin_threshold(cb200_collider* c, uint32_t dirty_rows);
+uint64_t cb200_collider_rebin_count(const cb200_collider* c);
+cb200_ctx* cb200_collider_engine(cb200_collider* c); /* the underlying device context (timing, launch counts, grid period) */
+
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 uint64_t cb200_launch_count(const cb200_ctx* ctx);
 /* Device-side duration of cb200_bulk_update and of each of its stages in milliseconds (CUDA events on the
