@@ -84,7 +84,7 @@ EXPORTS = (
     "cb200_bulk_update", "cb200_fetch_events", "cb200_fetch_candidate_pairs", "cb200_fetch_cell_entries",
     "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
     "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_shard_set_slab", "cb200_set_stream", "cb200_shard_begin", "cb200_shard_finish",
-    "cb200_shard_result", "cb200_set_resort_period", "cb200_resort_count",
+    "cb200_shard_result", "cb200_set_resort_period", "cb200_resort_count", "cb200_set_stage_timing",
     "cb200_collider_new", "cb200_collider_free", "cb200_collider_last_error", "cb200_collider_set_can_interact", "cb200_collider_time",
     "cb200_collider_next_time", "cb200_collider_set_time", "cb200_collider_next", "cb200_collider_get_hitbox", "cb200_collider_add_hitbox",
     "cb200_collider_set_hitbox_vel", "cb200_collider_remove_hitbox", "cb200_collider_get_overlaps", "cb200_collider_is_overlapping",
@@ -136,6 +136,7 @@ def load_library() -> C.CDLL:
     L.cb200_shard_begin.argtypes = [vp, dbl, C.POINTER(VelView), dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]
     L.cb200_shard_finish.argtypes = [vp, C.POINTER(vp)]
     L.cb200_shard_result.argtypes = [vp, C.POINTER(StepResult)]
+    L.cb200_set_stage_timing.argtypes = [vp, i32]
     L.cb200_set_resort_period.argtypes = [vp, i32]
     L.cb200_resort_count.argtypes = [vp]
     L.cb200_resort_count.restype = u64
@@ -365,6 +366,9 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self._L.cb200_launch_count(self._h))
+
+    def set_stage_timing(self, on: bool):
+        self._check(self._L.cb200_set_stage_timing(self._h, 1 if on else 0))
 
     def reset_timing(self):
         self._check(self._L.cb200_reset_timing(self._h))

@@ -119,7 +119,7 @@ TableView table_of(cb200_collider* c) {
 }
 GridView grid_of(cb200_collider* c) {
     cb200_ctx* x = c->ctx;
-    return GridView{x->entries.p, x->slots.p, x->geom, c->have_grid ? 1 : 0};
+    return GridView{x->entries.p, x->slots.p, x->chunk_base.p, x->geom, c->have_grid ? 1 : 0};
 }
 
 // Room for `rows` table rows and `labels` labels; existing contents are kept.
@@ -160,10 +160,7 @@ int rebin(cb200_collider* c) {
     collider_geom(c);
     const uint32_t n_slots = x->geom.n_slots();
     CCU(x->slots.reserve(n_slots));
-    if (x->tile_state.cap == 0) {
-        CCU(x->tile_state.reserve(kScanMaxChunks));
-        CCU(cudaMemsetAsync(x->tile_state.p, 0, kScanMaxChunks * 8, x->stream));
-    }
+    CCU(x->chunk_base.reserve(n_slots / kScanChunk));
     if (x->entries.cap == 0) CCU(x->entries.reserve((size_t)n * 4 + 1024));
     for (int attempt = 0; attempt < 3; ++attempt) {
         k_step_zero<<<x->sm_count * 4, kThreads, 0, x->stream>>>(reinterpret_cast<uint4*>(x->slots.p), n_slots / 4, x->d_ctr, nullptr);

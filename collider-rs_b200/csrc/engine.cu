@@ -81,8 +81,8 @@ struct cb200_ctx {
     uint64_t resorts = 0;
     uint8_t* collider_dirty = nullptr;        // incremental API (collider.inl): dirty-row flags, emptied by a bulk step
     uint32_t* collider_dirty_count = nullptr;
-    uint32_t* d_ticket = nullptr;  // scan ticket, monotonically increasing
-    uint32_t ticket_base = 0, scan_epoch = 0;
+    unsigned long long* d_sort_cursor = nullptr;  // entry cursor of the re-sort's counting sort
+    bool stage_timing = true;  // CUDA events between the stages (diagnostic); off: only around the whole step
     // sharding
     bool sharded = false;
     ShardGeom shard{};
@@ -99,7 +99,7 @@ struct cb200_ctx {
     GridGeom geom{0, 0};
     bool geom_forced = false;
     DevBuf<uint32_t> slots;
-    DevBuf<unsigned long long> tile_state;
+    DevBuf<uint32_t> chunk_base;  // start of each scan chunk's runs in the entry array
     DevBuf<CellEntry> entries;
     DevBuf<uint2> cand;
 
@@ -264,8 +264,7 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
     if ((e = cudaMalloc(&c->d_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&c->d_key, sizeof(MinKey))) != cudaSuccess) return bail("cudaMalloc", e);
-    if ((e = cudaMalloc(&c->d_ticket, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
-    if ((e = cudaMemset(c->d_ticket, 0, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset", e);
+    if ((e = cudaMalloc(&c->d_sort_cursor, 8)) != cudaSuccess) return bail("cudaMalloc", e);
     if (const char* rp = getenv("CB200_RESORT_PERIOD")) c->resort_period = std::max(0, atoi(rp));
     if ((e = cudaHostAlloc(&c->h_res, sizeof(StepResultDev), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer((void**)&c->d_res, c->h_res, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
@@ -287,8 +286,8 @@ void cb200_destroy(cb200_ctx* c) {
     for (auto& b : c->col_alt) b.release();
     c->kind_alt.release(); c->reit_alt.release(); c->group_alt.release(); c->mask_alt.release(); c->label_alt.release(); c->ord_alt.release();
     c->sort_key.release(); c->src_row.release(); c->tmp_col.release();
-    if (c->d_ticket) cudaFree(c->d_ticket);
-    c->slots.release(); c->tile_state.release(); c->entries.release();
+    if (c->d_sort_cursor) cudaFree(c->d_sort_cursor);
+    c->slots.release(); c->chunk_base.release(); c->entries.release();
     c->ov_pairs.release(); c->ov_table.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
     c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); c->ev_out.release(); c->cand.release();
@@ -485,19 +484,13 @@ static ShardGeom whole_world() {
     return g;
 }
 
-static int launch_scan(cb200_ctx* ctx, bool record_totals) {
+// Slot counts -> run starts (k_scan_slots).  step = the bulk step's / re-bin's scan (totals go to the step counters);
+// otherwise the re-sort's.
+static int launch_scan(cb200_ctx* ctx, bool step) {
     const uint32_t n_slots = ctx->geom.n_slots();
-    ScanArgs sa{};
-    sa.data = ctx->slots.p;
-    sa.n = n_slots;
-    sa.chunks = std::min<uint32_t>(n_slots / kScanTile, kScanMaxChunks);
-    sa.state = ctx->tile_state.p;
-    sa.epoch = ++ctx->scan_epoch;
-    sa.ticket = ctx->d_ticket;
-    sa.ticket_base = ctx->ticket_base;
-    sa.ctr = record_totals ? ctx->d_ctr : nullptr;
-    ctx->ticket_base += sa.chunks;
-    k_scan_slots<<<sa.chunks, kThreads, 0, ctx->stream>>>(sa);
+    if (!step) CU(cudaMemsetAsync(ctx->d_sort_cursor, 0, 8, ctx->stream));
+    k_scan_slots<<<n_slots / kScanChunk, kThreads, 0, ctx->stream>>>(ctx->slots.p, step ? &ctx->d_ctr->n_entries : ctx->d_sort_cursor, ctx->chunk_base.p,
+                                                                       step ? &ctx->d_ctr->n_cells : nullptr);
     ctx->launches += 1;
     return CB200_OK;
 }
@@ -546,10 +539,7 @@ static int prepare_buffers(cb200_ctx* ctx) {
     const uint32_t n = ctx->n;
     const uint32_t n_slots = ctx->geom.n_slots();
     CU(ctx->slots.reserve(n_slots));
-    if (ctx->tile_state.cap == 0) {
-        CU(ctx->tile_state.reserve(kScanMaxChunks));
-        CU(cudaMemsetAsync(ctx->tile_state.p, 0, kScanMaxChunks * 8, ctx->stream));
-    }
+    CU(ctx->chunk_base.reserve(n_slots / kScanChunk));
     if (ctx->entries.cap == 0) CU(ctx->entries.reserve((size_t)n * 4 + 1024));
     if (ctx->cand.cap == 0) CU(ctx->cand.reserve((size_t)n * 2 + 1024));
     if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
@@ -578,7 +568,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
         CU(cudaMemsetAsync(ctx->collider_dirty, 0, n, ctx->stream));
         CU(cudaMemsetAsync(ctx->collider_dirty_count, 0, 4, ctx->stream));
     }
-    CU(cudaEventRecord(ctx->ev_t[ST_STAGE_A], ctx->stream));
+    if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_STAGE_A], ctx->stream));
     StepArgs a{};
     a.n = n;
     a.rebase = do_rebase ? 1 : 0;
@@ -612,7 +602,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
         k_slab_header<<<1, 1, 0, ctx->stream>>>(ctx->send.p, ctx->send_count.p, ctx->slab);
         ctx->launches += 1;
     }
-    CU(cudaEventRecord(ctx->ev_t[ST_EXCH], ctx->stream));
+    if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_EXCH], ctx->stream));
     return CB200_OK;
 }
 
@@ -626,7 +616,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     const uint32_t n_vis_max = ctx->sharded ? ctx->n + ctx->slab * (uint32_t)sh.world : ctx->n;
     const uint32_t grid_v = std::max<uint32_t>(1, std::min<uint32_t>((n_vis_max + kThreads - 1) / kThreads, ctx->sm_count * 8));
     const bool use_map = ctx->sharded && ctx->n_ov;
-    CU(cudaEventRecord(ctx->ev_t[ST_SCAN], ctx->stream));
+    if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_SCAN], ctx->stream));
     if (ctx->sharded) {
         const uint32_t work = recount ? n_vis_max : ctx->slab * (uint32_t)sh.world;
         const uint32_t grid_i = std::max<uint32_t>(1, std::min<uint32_t>((work + kThreads - 1) / kThreads, ctx->sm_count * 8));
@@ -639,14 +629,14 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
         int rc = launch_scan(ctx, true);
         if (rc != CB200_OK) return rc;
     }
-    CU(cudaEventRecord(ctx->ev_t[ST_SCATTER], ctx->stream));
+    if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_SCATTER], ctx->stream));
     if (n_vis_max) {
         const uint32_t cap_e = (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu);
         if (ctx->sharded) k_scatter<true><<<grid_v, kThreads, 0, ctx->stream>>>(ctx->n, ctx->rec.p, vs, ctx->slots.p, ctx->entries.p, cap_e, g, sh.col_lo, sh.col_hi, ctx->d_ctr);
         else k_scatter<false><<<grid_v, kThreads, 0, ctx->stream>>>(ctx->n, ctx->rec.p, vs, ctx->slots.p, ctx->entries.p, cap_e, g, sh.col_lo, sh.col_hi, ctx->d_ctr);
         ctx->launches += 1;
     }
-    CU(cudaEventRecord(ctx->ev_t[ST_CAND], ctx->stream));
+    if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_CAND], ctx->stream));
     CandArgs cd{};
     cd.entries = ctx->entries.p;
     cd.geom = g;
@@ -657,7 +647,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     cd.cap_cand = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
     cd.ctr = ctx->d_ctr;
     k_candidates<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(cd);
-    CU(cudaEventRecord(ctx->ev_t[ST_SOLVE], ctx->stream));
+    if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_SOLVE], ctx->stream));
     SolveArgs sv{};
     sv.cand = ctx->cand.p;
     sv.cap_cand = cd.cap_cand;
@@ -680,7 +670,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     sv.col_lo = sh.col_lo;
     sv.col_hi = sh.col_hi;
     k_solve<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(sv);
-    CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
+    if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
     CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
     ctx->launches += 2;
     return CB200_OK;
@@ -713,7 +703,7 @@ static int complete_step(cb200_ctx* ctx, double time, bool* again) {
 
 static void accumulate_timing(cb200_ctx* ctx, int first_stage, bool with_total) {
     float ms = 0;
-    for (int s = first_stage; s < ST_COUNT; ++s)
+    for (int s = first_stage; s < ST_COUNT && ctx->stage_timing; ++s)
         if (cudaEventElapsedTime(&ms, ctx->ev_t[s], ctx->ev_t[s + 1]) == cudaSuccess) {
             ctx->stage_ms_sum[s] += ms;
             if (!with_total) ctx->total_ms_sum += ms;
@@ -1092,6 +1082,11 @@ int cb200_last_step_timing(cb200_ctx* ctx, float* total_ms, float* stage_ms, int
     for (int s = 0; s < n_stages && s < ST_COUNT; ++s)
         if (stage_ms) stage_ms[s] = (float)(ctx->stage_ms_sum[s] * k);
     return CB200_OK;
+}
+int cb200_set_stage_timing(cb200_ctx* ctx, int on) {
+    if (!ctx) return CB200_E_ARG;
+    ctx->stage_timing = on != 0;
+    return cb200_reset_timing(ctx);
 }
 int cb200_reset_timing(cb200_ctx* ctx) {
     if (!ctx) return CB200_E_ARG;

@@ -364,115 +364,73 @@ __global__ void __launch_bounds__(kThreads) k_step_zero(uint4* slots4, uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Exclusive scan of the slot counts: `chunks` co-resident blocks, one contiguous chunk of the table each.
-//   pass 1  chunk sum (+ non-empty slots) -> published as (epoch << 32 | sum)
-//   wait    every predecessor's sum of THIS epoch (a ticket orders the blocks, so predecessors are running)
-//   pass 2  re-read the chunk (L1/L2-hot) and write the exclusive prefixes
-// n is a power of two >= 4096; chunks = min(n / kScanTile, 512) <= the number of resident blocks, so the waits
-// cannot deadlock.  The epoch makes the state array self-cleaning: no memset between steps.
-constexpr int kScanItems = 16;
-constexpr int kScanTile = kThreads * kScanItems;  // 4096
-constexpr uint32_t kScanMaxChunks = 512;
+// Slot offsets: the counting sort needs, for every slot, the start of its run in the entry array — but not a
+// particular ORDER of the runs.  So instead of a global prefix sum (whose look-back / wait chain measured 2x the
+// cost of the data movement, profiles/r1c_scan_variants.txt) every block scans its own chunk of kScanChunk slots in
+// registers and takes the chunk's base from one atomicAdd on a global cursor.  One read and one write of the table,
+// no inter-block waiting.  Runs of one chunk are contiguous and in slot order; chunks land in arrival order, and
+// chunk_base[] remembers where each one starts (the run of slot s starts at chunk_base[s / kScanChunk] when s is the
+// first slot of its chunk, else where the run of slot s - 1 ends).
+constexpr int kScanItems = 8;
+constexpr int kScanChunk = kThreads * kScanItems;  // 2048 slots
+static_assert(kScanChunk == 2048, "chunk size is part of the grid view (slot_run_start)");
 
-struct ScanArgs {
-    uint32_t* data;
-    uint32_t n, chunks;
-    unsigned long long* state;  // [chunks]
-    uint32_t epoch;             // != any epoch left in `state` by earlier launches
-    uint32_t* ticket;           // monotonically increasing across launches
-    uint32_t ticket_base;       // value of *ticket before this launch
-    Counters* ctr;              // n_entries / n_cells receive the totals (null: not recorded)
-};
-
-__global__ void __launch_bounds__(kThreads) k_scan_slots(const ScanArgs a) {
-    __shared__ uint32_t s_chunk, s_prefix;
+__global__ void __launch_bounds__(kThreads) k_scan_slots(uint32_t* __restrict__ data, unsigned long long* cursor, uint32_t* __restrict__ chunk_base,
+                                                         unsigned long long* n_cells) {
+    __shared__ uint32_t s_prefix;
     __shared__ uint32_t s_warp[kThreads / 32];
-    if (threadIdx.x == 0) s_chunk = atomicAdd(a.ticket, 1u) - a.ticket_base;
-    __syncthreads();
-    const uint32_t chunk = s_chunk;
-    const uint32_t per_chunk = a.n / a.chunks, tiles = per_chunk / kScanTile;
-    uint32_t* base = a.data + (size_t)chunk * per_chunk;
+    const uint32_t chunk = blockIdx.x;
+    uint4* p = reinterpret_cast<uint4*>(data + (size_t)chunk * kScanChunk + (size_t)threadIdx.x * kScanItems);
+    uint32_t v[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems / 4; ++k) {
+        const uint4 q = p[k];
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+    uint32_t sum = 0, nz = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        sum += v[k];
+        nz += v[k] != 0;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    // pass 1
-    uint32_t sum = 0, nonzero = 0;
-    for (uint32_t t = 0; t < tiles; ++t) {
-        const uint4* p = reinterpret_cast<const uint4*>(base + (size_t)t * kScanTile + (size_t)threadIdx.x * kScanItems);
+    uint32_t inc = sum;
 #pragma unroll
-        for (int k = 0; k < kScanItems / 4; ++k) {
-            const uint4 q = p[k];
-            sum += q.x + q.y + q.z + q.w;
-            nonzero += (q.x != 0) + (q.y != 0) + (q.z != 0) + (q.w != 0);
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
     }
-    const unsigned long long packed = block_sum(((unsigned long long)nonzero << 32) | sum);  // valid in thread 0
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+        const uint32_t x = s_warp[w];
+        before += w < warp ? x : 0u;
+        total += x;
+    }
     if (threadIdx.x == 0) {
-        const uint32_t chunk_sum = (uint32_t)packed;
-        atomicExch(&a.state[chunk], ((unsigned long long)a.epoch << 32) | chunk_sum);
-        if (a.ctr && (packed >> 32)) atomicAdd(&a.ctr->n_cells, packed >> 32);
-        s_warp[0] = chunk_sum;
+        const uint32_t base = (uint32_t)atomicAdd(cursor, (unsigned long long)total);
+        s_prefix = base;
+        chunk_base[chunk] = base;
     }
-    __syncthreads();
-    const uint32_t chunk_sum = s_warp[0];
-    __syncthreads();
-    // wait for the predecessors
-    if (warp == 0) {
-        uint32_t prefix = 0;
-        for (uint32_t j = lane; j < chunk; j += 32) {
-            unsigned long long st;
-            do {
-                st = *reinterpret_cast<volatile unsigned long long*>(&a.state[j]);
-            } while ((uint32_t)(st >> 32) != a.epoch);
-            prefix += (uint32_t)st;
-        }
+    const unsigned long long nz_block = block_sum(nz);  // (its barriers also publish s_prefix)
+    if (threadIdx.x == 0 && nz_block && n_cells) atomicAdd(n_cells, nz_block);
+    uint32_t run = s_prefix + before + inc - sum;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) prefix += __shfl_xor_sync(0xffffffffu, prefix, o);
-        if (lane == 0) {
-            s_prefix = prefix;
-            if (a.ctr && chunk == a.chunks - 1) a.ctr->n_entries = (unsigned long long)prefix + chunk_sum;
-        }
+    for (int k = 0; k < kScanItems / 4; ++k) {
+        uint4 q;
+        q.x = run; run += v[4 * k];
+        q.y = run; run += v[4 * k + 1];
+        q.z = run; run += v[4 * k + 2];
+        q.w = run; run += v[4 * k + 3];
+        p[k] = q;
     }
-    __syncthreads();
-    // pass 2
-    uint32_t carry = s_prefix;
-    for (uint32_t t = 0; t < tiles; ++t) {
-        uint4* p = reinterpret_cast<uint4*>(base + (size_t)t * kScanTile + (size_t)threadIdx.x * kScanItems);
-        uint32_t v[kScanItems];
-        uint32_t tsum = 0;
-#pragma unroll
-        for (int k = 0; k < kScanItems / 4; ++k) {
-            const uint4 q = p[k];
-            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-            tsum += q.x + q.y + q.z + q.w;
-        }
-        uint32_t inc = tsum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
-        }
-        __syncthreads();  // s_warp readers of the previous tile are done
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        uint32_t before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) {
-            const uint32_t x = s_warp[w];
-            before += w < warp ? x : 0u;
-            total += x;
-        }
-        uint32_t run = carry + before + inc - tsum;
-#pragma unroll
-        for (int k = 0; k < kScanItems / 4; ++k) {
-            uint4 q;
-            q.x = run; run += v[4 * k];
-            q.y = run; run += v[4 * k + 1];
-            q.z = run; run += v[4 * k + 2];
-            q.w = run; run += v[4 * k + 3];
-            p[k] = q;
-        }
-        carry += total;
-    }
+}
+
+// After the scatter, slot_end[s] = end of slot s's run.  Start of the run (see k_scan_slots).
+__device__ __forceinline__ uint32_t slot_run_start(const uint32_t* __restrict__ slot_end, const uint32_t* __restrict__ chunk_base, uint32_t s) {
+    return (s % kScanChunk) ? slot_end[s - 1] : chunk_base[s / kScanChunk];
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -42,7 +42,8 @@ struct OneHeader {
 
 struct GridView {
     const CellEntry* entries;
-    const uint32_t* slot_end;  // after the scatter: end of each slot's run (start = end of the previous slot)
+    const uint32_t* slot_end;    // after the scatter: end of each slot's run
+    const uint32_t* chunk_base;  // start of each scan chunk's runs (slot_run_start)
     GridGeom geom;
     int have_grid;
 };
@@ -117,7 +118,7 @@ __device__ __forceinline__ void for_each_cellmate(const TableView& t, const Grid
         for (uint32_t c = threadIdx.x; c < ncells; c += blockDim.x) {
             const int32_t x = sx + (int32_t)(c / ny), y = sy + (int32_t)(c % ny);
             const uint32_t s = g.geom.slot(x, y);
-            const uint32_t e0 = s ? g.slot_end[s - 1] : 0u, e1 = g.slot_end[s];
+            const uint32_t e0 = slot_run_start(g.slot_end, g.chunk_base, s), e1 = g.slot_end[s];
             for (uint32_t e = e0; e < e1; ++e) {
                 const int4* pe = reinterpret_cast<const int4*>(g.entries + e);
                 const int4 r = pe[0], m = pe[1];

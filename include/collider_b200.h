@@ -284,6 +284,9 @@ uint64_t cb200_launch_count(const cb200_ctx* ctx);
 #define CB200_N_STAGES 8
 int cb200_last_step_timing(cb200_ctx* ctx, float* total_ms, float* stage_ms, int n_stages);
 int cb200_reset_timing(cb200_ctx* ctx);
+/* on (default): CUDA events between the stages of a step (each costs ~2 us of stream time); off: only around the whole
+ * step, stage_ms reads 0.  Resets the averages. */
+int cb200_set_stage_timing(cb200_ctx* ctx, int on);
 
 #ifdef __cplusplus
 }
