@@ -180,7 +180,9 @@ __device__ __forceinline__ unsigned long long block_sum(unsigned long long v) {
 struct Counters {
     unsigned long long n_entries;      // E, written by the scan
     unsigned long long n_cells;        // non-empty slots
-    unsigned long long n_collide;      // collide_time evaluations
+    unsigned long long n_collide;      // collide_time evaluations = work items that passed the candidate test
+    unsigned int work_overflow;        // step result: item count of the fullest work sub-list (vs the segment capacity)
+    unsigned int pad0;
     unsigned long long n_separate;     // separate_time evaluations
     unsigned long long n_pair_events;  // pair events with time < 1e50 (may exceed the buffer capacity -> overflow)
     unsigned long long n_solitaire;    // Reiterate events

@@ -101,11 +101,13 @@ struct cb200_ctx {
     DevBuf<uint32_t> slots;
     DevBuf<uint32_t> chunk_base;  // start of each scan chunk's runs in the entry array
     DevBuf<CellEntry> entries;
-    DevBuf<uint2> cand;
+    DevBuf<WorkItem> work;         // (record, record, slot) work items: kWorkLists equal segments (kernels.cuh WorkLists)
+    DevBuf<uint32_t> work_count;   // [kWorkLists]
 
     DevBuf<uint2> ov_pairs;
-    DevBuf<unsigned long long> ov_table;
-    uint32_t n_ov = 0, ov_cap_mask = 0;
+    DevBuf<unsigned long long> ov_table;  // buckets of four keys (kernels.cuh OverlapSet)
+    DevBuf<uint32_t> ov_bits;             // one bit per gid: has at least one overlap
+    uint32_t n_ov = 0, ov_bucket_mask = 0;
     DevBuf<uint64_t> ov_ida, ov_idb;
 
     DevBuf<PairEvent> events;
@@ -287,10 +289,10 @@ void cb200_destroy(cb200_ctx* c) {
     c->kind_alt.release(); c->reit_alt.release(); c->group_alt.release(); c->mask_alt.release(); c->label_alt.release(); c->ord_alt.release();
     c->sort_key.release(); c->src_row.release(); c->tmp_col.release();
     if (c->d_sort_cursor) cudaFree(c->d_sort_cursor);
-    c->slots.release(); c->chunk_base.release(); c->entries.release();
-    c->ov_pairs.release(); c->ov_table.release(); c->ov_ida.release(); c->ov_idb.release();
+    c->slots.release(); c->chunk_base.release(); c->entries.release(); c->work.release(); c->work_count.release();
+    c->ov_pairs.release(); c->ov_table.release(); c->ov_bits.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
-    c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); c->ev_out.release(); c->cand.release();
+    c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); c->ev_out.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->d_key) cudaFree(c->d_key);
     if (c->h_res) cudaFreeHost(c->h_res);
@@ -400,7 +402,7 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
     ctx->have_step = false;
     ctx->ev_sorted = false;
     ctx->n_ov = 0;
-    ctx->ov_cap_mask = 0;
+    ctx->ov_bucket_mask = 0;
     return CB200_OK;
 }
 
@@ -431,13 +433,17 @@ int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_
     if (n_pairs >= 0x40000000ull) return fail(ctx, CB200_E_ARG, "too many overlapping pairs");
     CU(cudaSetDevice(ctx->device));
     ctx->n_ov = 0;
-    ctx->ov_cap_mask = 0;
+    ctx->ov_bucket_mask = 0;
     if (n_pairs == 0) return CB200_OK;
     const uint32_t np = (uint32_t)n_pairs;
     CU(ctx->ov_ida.reserve(np)); CU(ctx->ov_idb.reserve(np)); CU(ctx->ov_pairs.reserve(np));
     uint32_t cap = 1024;
     while (cap < 2 * np) cap <<= 1;
     CU(ctx->ov_table.reserve(cap));
+    const size_t gid_space = ctx->sharded ? (size_t)ctx->id_space : std::max<size_t>(ctx->row_of.cap, ctx->n);
+    const size_t n_words = (gid_space + 31) / 32 + 1;
+    CU(ctx->ov_bits.reserve(n_words));
+    CU(cudaMemsetAsync(ctx->ov_bits.p, 0, n_words * 4, ctx->stream));
     CU(cudaMemcpyAsync(ctx->ov_ida.p, id_a, (size_t)np * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->ov_idb.p, id_b, (size_t)np * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->ov_table.p, 0xff, (size_t)cap * 8, ctx->stream));
@@ -446,7 +452,7 @@ int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_
     CU(cudaMemcpyAsync(&ctx->d_ctr->err_slot, &big, 8, cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t blocks = (np + kThreads - 1) / kThreads;
     k_overlap_map_ids<<<blocks, kThreads, 0, ctx->stream>>>(ctx->sharded ? nullptr : ctx->ids.p, ctx->n, ctx->ov_ida.p, ctx->ov_idb.p, np, ctx->ov_pairs.p, ctx->d_ctr);
-    k_overlap_insert<<<blocks, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, np, ctx->ov_table.p, cap - 1);
+    k_overlap_insert<<<blocks, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, np, ctx->ov_table.p, cap / 4 - 1, ctx->ov_bits.p);
     ctx->launches += 2;
     Counters h;
     CU(cudaMemcpyAsync(&h, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
@@ -454,7 +460,7 @@ int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_
     CU(cudaGetLastError());
     if (h.err_flags) return fail(ctx, CB200_E_ARG, "set_overlaps: hitbox id not found (pair " + std::to_string(h.err_slot) + ")");
     ctx->n_ov = np;
-    ctx->ov_cap_mask = cap - 1;
+    ctx->ov_bucket_mask = cap / 4 - 1;
     return CB200_OK;
 }
 
@@ -486,6 +492,10 @@ static ShardGeom whole_world() {
 
 // Slot counts -> run starts (k_scan_slots).  step = the bulk step's / re-bin's scan (totals go to the step counters);
 // otherwise the re-sort's.
+static WorkLists work_lists_of(cb200_ctx* ctx) {
+    return WorkLists{ctx->work.p, (uint32_t)std::min<size_t>(ctx->work.cap / kWorkLists, 0x7fffffffu), ctx->work_count.p};
+}
+
 static int launch_scan(cb200_ctx* ctx, bool step) {
     const uint32_t n_slots = ctx->geom.n_slots();
     if (!step) CU(cudaMemsetAsync(ctx->d_sort_cursor, 0, 8, ctx->stream));
@@ -541,7 +551,8 @@ static int prepare_buffers(cb200_ctx* ctx) {
     CU(ctx->slots.reserve(n_slots));
     CU(ctx->chunk_base.reserve(n_slots / kScanChunk));
     if (ctx->entries.cap == 0) CU(ctx->entries.reserve((size_t)n * 4 + 1024));
-    if (ctx->cand.cap == 0) CU(ctx->cand.reserve((size_t)n * 2 + 1024));
+    if (ctx->work.cap == 0) CU(ctx->work.reserve(std::max<size_t>((size_t)n * 2 + 1024, (size_t)kWorkLists * 256)));
+    CU(ctx->work_count.reserve(kWorkLists));
     if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
     const uint32_t per_sm = 8;
     ctx->grid_a = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, ctx->sm_count * per_sm));
@@ -562,7 +573,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     const GridGeom g = ctx->geom;
     const uint32_t n_slots = g.n_slots();
     k_step_zero<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(ctx->slots.p), n_slots / 4, ctx->d_ctr,
-                                                                  ctx->sharded ? ctx->send_count.p : nullptr);
+                                                                  ctx->sharded ? ctx->send_count.p : nullptr, ctx->work_count.p, kWorkLists);
     ctx->launches += 1;
     if (ctx->collider_dirty && n) {
         CU(cudaMemsetAsync(ctx->collider_dirty, 0, n, ctx->stream));
@@ -638,19 +649,19 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     }
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_CAND], ctx->stream));
     CandArgs cd{};
-    cd.entries = ctx->entries.p;
     cd.geom = g;
     cd.col_lo = sh.col_lo;
     cd.col_hi = sh.col_hi;
-    cd.ov = OverlapSet{ctx->ov_table.p, ctx->n_ov ? ctx->ov_cap_mask : 0u};
-    cd.cand = ctx->cand.p;
-    cd.cap_cand = (uint32_t)std::min<size_t>(ctx->cand.cap, 0xffffffffu);
-    cd.ctr = ctx->d_ctr;
-    k_candidates<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(cd);
+    cd.ov = OverlapSet{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, ctx->n_ov};
+    EnumArgs en{};
+    en.entries = ctx->entries.p;
+    en.work = work_lists_of(ctx);
+    en.ctr = ctx->d_ctr;
+    k_enum_pairs<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(en);
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_SOLVE], ctx->stream));
     SolveArgs sv{};
-    sv.cand = ctx->cand.p;
-    sv.cap_cand = cd.cap_cand;
+    sv.cd = cd;
+    sv.work = en.work;
     sv.ov_pairs = ctx->ov_pairs.p;
     sv.n_ov = ctx->n_ov;
     sv.rec = ctx->rec.p;
@@ -690,8 +701,8 @@ static int complete_step(cb200_ctx* ctx, double time, bool* again) {
         CU(ctx->entries.reserve((size_t)c.n_entries + c.n_entries / 4 + 1024));
         *again = true;
     }
-    if (c.n_collide > ctx->cand.cap) {
-        CU(ctx->cand.reserve((size_t)c.n_collide + c.n_collide / 4 + 1024));
+    if (c.work_overflow > ctx->work.cap / kWorkLists) {  // the fullest work sub-list did not fit its segment
+        CU(ctx->work.reserve((size_t)kWorkLists * ((size_t)c.work_overflow + c.work_overflow / 4 + 64)));
         *again = true;
     }
     if (c.n_pair_events > ctx->events.cap) {
@@ -878,6 +889,7 @@ int cb200_shard_result(cb200_ctx* ctx, cb200_step_result* out) {
         z.n_solitaire = keep.n_solitaire;
         z.n_local = keep.n_local;
         CU(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_slots * 4, ctx->stream));
+        CU(cudaMemsetAsync(ctx->work_count.p, 0, kWorkLists * 4, ctx->stream));
         CU(cudaMemcpy(ctx->d_ctr, &z, sizeof(Counters), cudaMemcpyHostToDevice));
         if ((rc = enqueue_back(ctx, ctx->shard_T, true)) != CB200_OK) return rc;
         if ((rc = complete_step(ctx, ctx->shard_T, &again)) != CB200_OK) return rc;
@@ -963,18 +975,34 @@ int cb200_fetch_candidate_pairs(cb200_ctx* ctx, uint64_t* id_hi, uint64_t* id_lo
     const uint64_t total = ctx->last.ctr.n_collide;
     if (n_out) *n_out = total;
     if (cap == 0 || total == 0) return CB200_OK;
-    std::vector<uint2> h(total);
     std::vector<uint64_t> ids;
     int rc = gid_to_id_table(ctx, ids);
     if (rc != CB200_OK) return rc;
-    CU(cudaMemcpy(h.data(), ctx->cand.p, total * sizeof(uint2), cudaMemcpyDeviceToHost));
-    // candidates hold record indices; the record carries the gid (offset 12 of every 96-byte record)
-    const uint32_t n_rec = ctx->sharded ? (uint32_t)std::min<size_t>(ctx->rec.cap, 0xffffffffu) : ctx->n;
-    std::vector<uint32_t> gids(n_rec);
-    if (n_rec) CU(cudaMemcpy2D(gids.data(), 4, reinterpret_cast<const char*>(ctx->rec.p) + 12, sizeof(HbRec), 4, n_rec, cudaMemcpyDeviceToHost));
+    // the step keeps (entry, predecessor) work items; re-run the candidate test over them and list what passes
+    const ShardGeom sh = ctx->sharded ? ctx->shard : whole_world();
+    CandArgs cd{};
+    cd.geom = ctx->geom;
+    cd.col_lo = sh.col_lo;
+    cd.col_hi = sh.col_hi;
+    cd.ov = OverlapSet{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, ctx->n_ov};
+    DevBuf<uint2> out;
+    DevBuf<unsigned long long> cnt;
+    CU(out.reserve(total));
+    CU(cnt.reserve(1));
+    CU(cudaMemsetAsync(cnt.p, 0, 8, ctx->stream));
+    k_list_candidates<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(cd, work_lists_of(ctx), ctx->rec.p, out.p, cnt.p, total);
+    ctx->launches += 1;
+    std::vector<uint2> h(total);
+    unsigned long long got = 0;
+    CU(cudaMemcpyAsync(h.data(), out.p, total * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&got, cnt.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    out.release();
+    cnt.release();
+    if (got != total) return fail(ctx, CB200_E_STATE, "candidate listing disagrees with the step's count");
     for (uint64_t i = 0; i < total && i < cap; ++i) {
-        if (id_hi) id_hi[i] = id_of(ids, gids[h[i].x]);
-        if (id_lo) id_lo[i] = id_of(ids, gids[h[i].y]);
+        if (id_hi) id_hi[i] = id_of(ids, h[i].x);
+        if (id_lo) id_lo[i] = id_of(ids, h[i].y);
     }
     return CB200_OK;
 }
@@ -991,16 +1019,20 @@ int cb200_fetch_cell_entries(cb200_ctx* ctx, int32_t* cell_x, int32_t* cell_y, u
     int rc = gid_to_id_table(ctx, ids);
     if (rc != CB200_OK) return rc;
     CU(cudaMemcpy(h.data(), ctx->entries.p, total * sizeof(CellEntry), cudaMemcpyDeviceToHost));
+    // an entry names its record; the record's first 16 bytes hold sx, sy, span, gid
+    const uint32_t n_rec = ctx->sharded ? (uint32_t)std::min<size_t>(ctx->rec.cap, 0xffffffffu) : ctx->n;
+    std::vector<int32_t> heads((size_t)n_rec * 4);
+    if (n_rec) CU(cudaMemcpy2D(heads.data(), 16, ctx->rec.p, sizeof(HbRec), 16, n_rec, cudaMemcpyDeviceToHost));
     const uint32_t mw = (1u << ctx->geom.lw) - 1u, mh = (1u << ctx->geom.lh) - 1u;
     for (uint64_t i = 0; i < total && i < cap; ++i) {
-        const CellEntry& r = h[i];
+        const int32_t* q = heads.data() + 4 * (size_t)h[i].vidx;
         uint32_t sxs, sys;
-        ctx->geom.unslot(r.slot_group & kSlotMask, &sxs, &sys);
+        ctx->geom.unslot(h[i].key & kSlotMask, &sxs, &sys);
         // the unique cell of the rect that folds onto this slot
-        const int32_t x = r.sx + (int32_t)((sxs - (uint32_t)r.sx) & mw), y = r.sy + (int32_t)((sys - (uint32_t)r.sy) & mh);
+        const int32_t x = q[0] + (int32_t)((sxs - (uint32_t)q[0]) & mw), y = q[1] + (int32_t)((sys - (uint32_t)q[1]) & mh);
         if (cell_x) cell_x[i] = x;
         if (cell_y) cell_y[i] = y;
-        if (id) id[i] = id_of(ids, r.gid);
+        if (id) id[i] = id_of(ids, (uint32_t)q[3]);
     }
     return CB200_OK;
 }

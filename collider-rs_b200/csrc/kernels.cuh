@@ -349,12 +349,16 @@ __global__ void __launch_bounds__(kThreads) k_index_visitors(const HbRec* __rest
 
 // ---------------------------------------------------------------------------------------------------------
 // Step prologue: one kernel zeroes everything a step accumulates into (slot table, counters, halo count).
-__global__ void __launch_bounds__(kThreads) k_step_zero(uint4* slots4, uint32_t n4, Counters* ctr, uint32_t* send_count) {
+__global__ void __launch_bounds__(kThreads) k_step_zero(uint4* slots4, uint32_t n4, Counters* ctr, uint32_t* send_count, uint32_t* work_count,
+                                                        uint32_t n_work_lists) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) slots4[i] = z;
     if (blockIdx.x == 0) {
         uint32_t* w = reinterpret_cast<uint32_t*>(ctr);
+        static_assert(sizeof(Counters) / 4 <= kThreads, "one thread per counter word");
         if (threadIdx.x < sizeof(Counters) / 4) w[threadIdx.x] = 0u;
+        if (work_count)
+            for (uint32_t l = threadIdx.x; l < n_work_lists; l += blockDim.x) work_count[l] = 0u;
         __syncthreads();
         if (threadIdx.x == 0) {
             ctr->err_slot = ~0ull;
@@ -490,17 +494,15 @@ __global__ void __launch_bounds__(kThreads) k_iota_rows(uint32_t n, uint32_t* la
 
 // ---------------------------------------------------------------------------------------------------------
 // Scatter: second half of the counting sort.  offsets[s] enters as the start of slot s and is used as the
-// slot's cursor.  A cell entry carries everything the candidate stage tests (IndexRect, profile bits, id rank), so
-// that stage streams the entry array and never gathers hitbox records: 32 B = one sector per entry.
-struct alignas(32) CellEntry {
-    int32_t sx, sy, ex, ey;  // IndexRect of the hitbox
-    uint32_t vidx;           // index of its record in the visitor table (one device: the table slot)
-    uint32_t slot_group;     // grid slot (26 bits) | group << 26
-    uint32_t mask;           // interact_groups bit mask
-    uint32_t gid;            // id rank: decides hi/lo and breaks ties
+// slot's cursor.  A cell entry is 8 bytes — the key (slot, group, kind) the enumeration stage streams, and the index
+// of the hitbox's record, where everything else about it lives.
+struct alignas(8) CellEntry {
+    uint32_t key;   // grid slot (26 bits) | group << 26 (5 bits) | rect << 31
+    uint32_t vidx;  // index of the hitbox's record in the visitor table (one device: the table row)
 };
-static_assert(sizeof(CellEntry) == 32, "CellEntry must be one sector");
+static_assert(sizeof(CellEntry) == 8, "CellEntry is one 8-byte word");
 constexpr uint32_t kSlotMask = (1u << 26) - 1u;
+constexpr uint32_t kEntryKindBit = 0x80000000u;  // key bit 31: the hitbox is a rect
 
 template <bool SHARDED>
 __global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const HbRec* __restrict__ rec, VisSpace vs, uint32_t* offsets, CellEntry* entries,
@@ -513,50 +515,57 @@ __global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const HbRec* _
         if (SHARDED && !vis_record(rec, vs, n_local, j, &i)) continue;
         const RecHead h = load_head(rec, i);
         if (!(h.kgb & 2u)) continue;
-        const int4 lo4 = make_int4(h.sx, h.sy, h.ex, h.ey);
-        const uint32_t group = (h.kgb >> 8) & 0x1fu;
+        const uint32_t group = ((h.kgb >> 8) & 0x1fu) | ((h.kgb & 1u) << 5);  // bit 5 -> key bit 31: the hitbox is a rect
         const int32_t x0 = max(h.sx, col_lo), x1 = min(h.ex, col_hi);
         for (int32_t x = x0; x < x1; ++x)
             for (int32_t y = h.sy; y != h.ey; ++y) {
                 const uint32_t s = geom.slot(x, y);
                 const uint32_t pos = atomicAdd(&offsets[s], 1u);
-                if (pos < cap_entries) {
-                    int4* out = reinterpret_cast<int4*>(entries + pos);
-                    out[0] = lo4;
-                    out[1] = make_int4((int)i, (int)(s | (group << 26)), (int)h.mask, (int)h.gid);
-                } else {
-                    ctr->overflow_entries = 1u;
-                }
+                if (pos < cap_entries) *reinterpret_cast<uint2*>(entries + pos) = make_uint2(s | (group << 26), i);
+                else ctr->overflow_entries = 1u;
             }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Overlap set (HitboxInfo.overlaps, collider.rs:463) as an open-addressing hash set of (hi << 32 | lo).
+// Overlap set (HitboxInfo.overlaps, collider.rs:463): "is (hi, lo) overlapping already?" is asked for every candidate
+// pair, so the common answer — no — must not cost a dependent trip to L2 (it was 22 % of the candidate stage's stall
+// samples, profiles/r1f_candidates.txt).  Two levels:
+//   bits    one bit per gid: the hitbox has at least one overlap.  ~n/8 bytes, cache-resident; a pair is looked up only
+//           if both bits are set
+//   table   open addressing over 32-byte buckets of four (hi << 32 | lo) keys: one sector per probe step
 struct OverlapSet {
-    const unsigned long long* table;  // kKeyMax = empty
-    uint32_t cap_mask;                // capacity - 1 (power of two); 0 = no overlaps at all
+    const ulonglong2* table;  // [2 * n_buckets]; kKeyMax = empty
+    const uint32_t* bits;
+    uint32_t bucket_mask;     // n_buckets - 1 (power of two); unused when n_pairs == 0
+    uint32_t n_pairs;
 };
 __device__ __forceinline__ bool overlap_contains(const OverlapSet& ov, uint32_t hi, uint32_t lo) {
+    if (!((__ldg(ov.bits + (hi >> 5)) >> (hi & 31u)) & 1u) || !((__ldg(ov.bits + (lo >> 5)) >> (lo & 31u)) & 1u)) return false;
     const unsigned long long key = ((unsigned long long)hi << 32) | lo;
-    uint32_t p = (uint32_t)mix64(key) & ov.cap_mask;
+    uint32_t b = (uint32_t)mix64(key) & ov.bucket_mask;
     for (;;) {
-        const unsigned long long k = __ldg(ov.table + p);
-        if (k == key) return true;
-        if (k == kKeyMax) return false;
-        p = (p + 1) & ov.cap_mask;
+        const ulonglong2 q0 = __ldg(ov.table + 2 * (size_t)b), q1 = __ldg(ov.table + 2 * (size_t)b + 1);
+        if (q0.x == key || q0.y == key || q1.x == key || q1.y == key) return true;
+        if (q1.y == kKeyMax) return false;  // buckets fill front to back: a free last slot ends the probe sequence
+        b = (b + 1) & ov.bucket_mask;
     }
 }
-__global__ void k_overlap_insert(const uint2* __restrict__ pairs, uint32_t n_pairs, unsigned long long* table, uint32_t cap_mask) {
+__global__ void k_overlap_insert(const uint2* __restrict__ pairs, uint32_t n_pairs, unsigned long long* table, uint32_t bucket_mask, uint32_t* bits) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     const uint2 pr = pairs[i];
+    atomicOr(bits + (pr.x >> 5), 1u << (pr.x & 31u));
+    atomicOr(bits + (pr.y >> 5), 1u << (pr.y & 31u));
     const unsigned long long key = ((unsigned long long)pr.x << 32) | pr.y;
-    uint32_t p = (uint32_t)mix64(key) & cap_mask;
+    uint32_t b = (uint32_t)mix64(key) & bucket_mask;
     for (;;) {
-        const unsigned long long prev = atomicCAS(&table[p], kKeyMax, key);
-        if (prev == kKeyMax || prev == key) return;
-        p = (p + 1) & cap_mask;
+        // slots of a bucket are claimed front to back, so a bucket never has a hole before a key
+        for (int k = 0; k < 4; ++k) {
+            const unsigned long long prev = atomicCAS(&table[4 * (size_t)b + k], kKeyMax, key);
+            if (prev == kKeyMax || prev == key) return;
+        }
+        b = (b + 1) & bucket_mask;
     }
 }
 // ids -> slots (binary search in the ascending id column); pairs out as (hi slot, lo slot).
@@ -590,98 +599,233 @@ __global__ void k_overlap_map_ids(const uint64_t* __restrict__ ids, uint32_t n, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Candidate stage: one thread per cell entry, walking back over the entries that precede it in the same slot
-// (the entry array is sorted by slot, so a slot's entries are contiguous and the walk stays in cache).
+// Candidate stage, part 1: enumeration.  The entry array is sorted by slot, so the possible partners of an entry are the
+// entries that precede it in its slot run.  This kernel only ENUMERATES those (entry, predecessor) pairs from the 8-byte
+// entries and writes them as dense work lists of (record, record, slot) items — grouped by kind pair (rect/rect,
+// circle/circle, mixed) — for the solve stage, which tests and solves them from the records it has to load anyway.
+// (Testing inside a per-entry walk, a block-wide flattening and a warp-shuffle walk over 32-byte entries were all measured
+// first: each spent 22-33 M warp instructions per step with most lanes idle or waiting — profiles/r1c…r1g.)
+// A block takes kEnumTile consecutive entries per round, one chunk of kEnumChunk per warp, 32 entries per step:
+//   rank in run   one ballot of the run heads; a run that began before the step continues through `last_rank`
+//   k-th predecessor   k lanes down (shuffle), in the previous step's registers, or (long runs) in global memory
+//   output        two passes over the registers: count the items per kind pair, reserve the block's ranges with ONE atomic
+//                 per kind pair and round (on one of kSubLists sub-lists: same-address atomics serialise at ~2 ns each in
+//                 L2, and a warp that appended through its own atomics spent 45 % of its time waiting for them,
+//                 profiles/r1g_enum_solve.txt), then write the items in place — no staging, no per-warp atomics
+constexpr int kEnumChunk = 128;                  // entries per warp and round
+constexpr int kEnumSteps = kEnumChunk / 32;
+constexpr int kEnumTile = kEnumChunk * (kThreads / 32);  // entries per block and round
+constexpr int kSubLists = 8;                     // per kind pair
+constexpr int kWorkLists = 3 * kSubLists;
+
+struct WorkItem {
+    uint32_t a, b;  // record indices of the entry and of its predecessor
+    uint32_t slot;  // the slot of the run they were found in (pair ownership)
+    uint32_t pad;
+};
+struct WorkLists {  // work buffer = kWorkLists equal segments; list l holds kind pair l / kSubLists
+    WorkItem* items;
+    uint32_t seg_cap;
+    uint32_t* count;  // [kWorkLists]
+};
+
+struct EnumArgs {
+    const CellEntry* entries;
+    WorkLists work;
+    Counters* ctr;
+};
+
+// One round of one warp: ranks of its kEnumChunk entries, then either the number of work items per kind pair (COUNT) or
+// the items themselves, written at out[l] + (items of kind pair l before this lane's).
+struct EnumRound {
+    uint2 ent[kEnumSteps];      // (key, vidx) of this lane's entries
+    uint32_t rank[kEnumSteps];
+    unsigned rects[kEnumSteps + 1];  // [0]: the halo's kind ballot
+    uint32_t halo_vidx;
+};
+template <bool COUNT>
+__device__ __forceinline__ void enum_emit(const EnumRound& r, const uint2* __restrict__ ent, uint32_t c0, int lane, uint32_t* cnt, WorkItem* const* out) {
+#pragma unroll
+    for (int s = 0; s < kEnumSteps; ++s) {
+        const uint32_t max_rank = __reduce_max_sync(0xffffffffu, r.rank[s]);
+        const uint32_t my_rect = r.ent[s].x >> 31, slot = r.ent[s].x & kSlotMask;
+        const uint32_t prev_vidx = s ? r.ent[s ? s - 1 : 0].y : r.halo_vidx;
+        const uint32_t e = c0 + (uint32_t)s * 32 + lane;
+        for (uint32_t k = 1; k <= max_rank; ++k) {
+            const bool active = r.rank[s] >= k;
+            const int src = lane - (int)k;
+            uint32_t pred_rect = 0, pred_vidx = 0;
+            if (!COUNT) {
+                if (k <= 31) pred_vidx = __shfl_sync(0xffffffffu, r.ent[s].y, src & 31);
+                if (k <= 63) {  // (src & 31 == 32 + src for src in [-32, -1])
+                    const uint32_t pv = __shfl_sync(0xffffffffu, prev_vidx, src & 31);
+                    if (src < 0) pred_vidx = pv;
+                }
+            }
+            if (src >= 0) pred_rect = (r.rects[s + 1] >> src) & 1u;
+            else if (src >= -32) pred_rect = (r.rects[s] >> (32 + src)) & 1u;
+            else if (active) {  // a run longer than the previous step: global memory
+                const uint2 far = __ldg(ent + (e - k));
+                pred_rect = far.x >> 31;
+                pred_vidx = far.y;
+            }
+            const uint32_t n_rect = my_rect + pred_rect;
+            const uint32_t pair = n_rect == 2 ? 0u : (n_rect == 0 ? 1u : 2u);
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                const unsigned mask = __ballot_sync(0xffffffffu, active && pair == (uint32_t)l);
+                if (!COUNT && active && pair == (uint32_t)l && out[l])
+                    *reinterpret_cast<uint4*>(out[l] + cnt[l] + __popc(mask & ((1u << lane) - 1u))) = make_uint4(r.ent[s].y, pred_vidx, slot, 0u);
+                cnt[l] += __popc(mask);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_enum_pairs(const EnumArgs a) {
+    __shared__ uint32_t s_cnt[kThreads / 32][3], s_off[kThreads / 32][3], s_base[3];
+    const uint32_t n_entries = (uint32_t)a.ctr->n_entries;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t kNoSlot = 0xffffffffu;  // (slots have 26 bits)
+    const uint2* ent = reinterpret_cast<const uint2*>(a.entries);
+    const uint32_t sub = blockIdx.x & (kSubLists - 1);
+    for (uint32_t t0 = blockIdx.x * kEnumTile; t0 < n_entries; t0 += gridDim.x * kEnumTile) {
+        const uint32_t c0 = t0 + (uint32_t)warp * kEnumChunk;
+        const uint32_t c1 = min(c0 + (uint32_t)kEnumChunk, n_entries);  // (c1 <= c0: this warp has nothing)
+        EnumRound r;
+        // all loads of the round first: the chunk and the 32 entries before it
+#pragma unroll
+        for (int s = 0; s < kEnumSteps; ++s) r.ent[s] = c0 + s * 32 + lane < c1 ? __ldg(ent + c0 + s * 32 + lane) : make_uint2(0u, 0u);
+        const bool halo_live = c0 < c1 && c0 + lane >= 32;
+        const uint2 halo = halo_live ? __ldg(ent + (c0 - 32 + lane)) : make_uint2(0u, 0u);
+        r.halo_vidx = halo.y;
+        const uint32_t halo_slot = halo_live ? (halo.x & kSlotMask) : kNoSlot;
+        r.rects[0] = __ballot_sync(0xffffffffu, halo_live && (halo.x & kEntryKindBit));
+        // rank of the last halo entry in its run
+        uint32_t last_slot = __shfl_sync(0xffffffffu, halo_slot, 31), last_rank = 0;
+        if (last_slot != kNoSlot) {
+            const unsigned same = __ballot_sync(0xffffffffu, halo_slot == last_slot);
+            const uint32_t trail = __clz(~same);  // consecutive halo lanes 31, 30, ... in last's run (32: maybe more before the halo)
+            last_rank = trail - 1;
+            if (trail == 32) {
+                uint32_t f = c0 - 32;
+                while (f > 0 && (__ldg(ent + (f - 1)).x & kSlotMask) == last_slot) {
+                    --f;
+                    ++last_rank;
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < kEnumSteps; ++s) {
+            const bool live = c0 + s * 32 + lane < c1;
+            const uint32_t slot = live ? (r.ent[s].x & kSlotMask) : kNoSlot;
+            uint32_t slot_up = __shfl_up_sync(0xffffffffu, slot, 1);
+            if (lane == 0) slot_up = last_slot;
+            const unsigned heads = __ballot_sync(0xffffffffu, live && slot != slot_up);
+            r.rects[s + 1] = __ballot_sync(0xffffffffu, live && (r.ent[s].x & kEntryKindBit));
+            const unsigned below = heads & (0xffffffffu >> (31 - lane));  // heads at or below this lane
+            r.rank[s] = !live ? 0u : (below ? (uint32_t)(lane - (31 - __clz(below))) : (uint32_t)lane + last_rank + 1u);
+            last_slot = __shfl_sync(0xffffffffu, slot, 31);
+            last_rank = __shfl_sync(0xffffffffu, r.rank[s], 31);
+        }
+        // phase 1: how many items per kind pair; the block reserves its ranges with one atomic per kind pair
+        uint32_t cnt[3] = {0u, 0u, 0u};
+        enum_emit<true>(r, ent, c0, lane, cnt, nullptr);
+        if (lane < 3) s_cnt[warp][lane] = cnt[lane];
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            uint32_t run = 0;
+            for (int w = 0; w < kThreads / 32; ++w) {
+                s_off[w][threadIdx.x] = run;
+                run += s_cnt[w][threadIdx.x];
+            }
+            s_base[threadIdx.x] = run ? atomicAdd(&a.work.count[threadIdx.x * kSubLists + sub], run) : 0u;
+        }
+        __syncthreads();
+        // phase 2: write the items
+        WorkItem* out[3];
+        uint32_t room[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const uint32_t at = s_base[l] + s_off[warp][l];
+            room[l] = at + cnt[l] <= a.work.seg_cap ? 1u : 0u;  // a range that does not fit is dropped: the step is re-run with a larger buffer
+            out[l] = room[l] ? a.work.items + (size_t)(l * kSubLists + sub) * a.work.seg_cap + at : nullptr;
+        }
+        uint32_t done[3] = {0u, 0u, 0u};
+        enum_emit<false>(r, ent, c0, lane, done, out);
+        __syncthreads();  // s_cnt / s_off / s_base are rewritten by the next round
+    }
+}
+
+// Candidate stage, part 2: the test of one work item, from the two record heads — run by the solve stage (and by the
+// debug listing kernel).
 //   candidates   Grid::overlapping_ids (grid.rs:115-135) restricted to the surviving (hi, lo) pairs; the
 //                hash-set de-duplication is replaced by pair ownership: a pair is taken only in the slot of
 //                cell (max(sx_i, sx_j), max(sy_i, sy_j)) — the min corner of the rect intersection — so every
 //                pair sharing >= 1 cell is produced exactly once, and aliased slot-mates are rejected.  Sharded:
 //                only the rank whose strip holds the owner cell's column takes the pair.
 //   filters      lo.group in hi.interact_groups (grid.rs:122, key group); not already overlapping (collider.rs:351)
-// Output: the compact candidate list (record index of hi, record index of lo).
 struct CandArgs {
-    const CellEntry* entries;
     GridGeom geom;
     int32_t col_lo, col_hi;
     OverlapSet ov;
-    uint2* cand;
-    uint32_t cap_cand;
-    Counters* ctr;
 };
-
-// One (entry, predecessor) test; on success *hi/*lo receive the record indices of the higher / lower id.
-__device__ __forceinline__ bool candidate_test(const CandArgs& a, const int4& r, const int4& m, const int4& rf, const int4& mf, uint32_t* hi,
-                                               uint32_t* lo) {
-    // ownership: min corner of the rect intersection must be this slot's cell (and, sharded, inside the own strip)
-    const int32_t ox = max(r.x, rf.x), oy = max(r.y, rf.y);
-    if (ox >= min(r.z, rf.z) || oy >= min(r.w, rf.w)) return false;
-    if (a.geom.slot(ox, oy) != ((uint32_t)m.y & kSlotMask)) return false;
+// *a_is_hi: the item's first record carries the higher id.
+__device__ __forceinline__ bool candidate_test(const CandArgs& a, const RecHead& ha, const RecHead& hb, uint32_t slot, bool* a_is_hi) {
+    const int32_t ox = max(ha.sx, hb.sx), oy = max(ha.sy, hb.sy);
+    if (ox >= min(ha.ex, hb.ex) || oy >= min(ha.ey, hb.ey)) return false;
+    if (a.geom.slot(ox, oy) != slot) return false;
     if (ox < a.col_lo || ox >= a.col_hi) return false;
-    const uint32_t gi = (uint32_t)m.w, gj = (uint32_t)mf.w;
-    const bool i_is_hi = gi > gj;
-    *hi = (uint32_t)(i_is_hi ? m.x : mf.x);
-    *lo = (uint32_t)(i_is_hi ? mf.x : m.x);
-    const uint32_t mask_hi = (uint32_t)(i_is_hi ? m.z : mf.z), group_lo = (uint32_t)(i_is_hi ? mf.y : m.y) >> 26;
+    const bool first_hi = ha.gid > hb.gid;
+    *a_is_hi = first_hi;
+    const uint32_t mask_hi = first_hi ? ha.mask : hb.mask, group_lo = ((first_hi ? hb.kgb : ha.kgb) >> 8) & 31u;
     if (!((mask_hi >> group_lo) & 1u)) return false;
-    if (a.ov.cap_mask && overlap_contains(a.ov, i_is_hi ? gi : gj, i_is_hi ? gj : gi)) return false;
+    if (a.ov.n_pairs && overlap_contains(a.ov, first_hi ? ha.gid : hb.gid, first_hi ? hb.gid : ha.gid)) return false;
     return true;
 }
 
-// Block-aggregated output: pass 1 tests every predecessor and remembers the accepted ones (bit k of `acc` =
-// predecessor e-1-k, for the first 64); one block scan + ONE global atomic per block-iteration reserves the
-// output range; pass 2 writes the pairs.  (A per-warp claim on the single global counter serialises in L2.)
-__global__ void __launch_bounds__(kThreads) k_candidates(const CandArgs a) {
-    __shared__ unsigned long long s_base;
-    const uint32_t n_entries = (uint32_t)a.ctr->n_entries;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n_entries; base += stride) {
-        const uint32_t e = base + threadIdx.x;
-        int4 r = make_int4(0, 0, 0, 0), m = r;
-        unsigned long long acc = 0;
-        uint32_t cnt = 0, run = 0;
-        if (e < n_entries) {
-            const int4* pe = reinterpret_cast<const int4*>(a.entries + e);
-            r = __ldg(pe);
-            m = __ldg(pe + 1);
-            const uint32_t slot = (uint32_t)m.y & kSlotMask;
-            for (uint32_t f = e; f-- > 0; ++run) {
-                const int4* pf = reinterpret_cast<const int4*>(a.entries + f);
-                const int4 mf = __ldg(pf + 1);
-                if (((uint32_t)mf.y & kSlotMask) != slot) break;
-                const int4 rf = __ldg(pf);
-                uint32_t hi, lo;
-                if (candidate_test(a, r, m, rf, mf, &hi, &lo)) {
-                    ++cnt;
-                    if (run < 64) acc |= 1ull << run;
-                }
-            }
+// Index space of the work lists of one step: list l holds min(count[l], seg_cap) items; first[l] = items before it.
+struct WorkIndex {
+    uint32_t first[kWorkLists + 1];
+};
+__device__ __forceinline__ void work_index_build(const WorkLists& w, WorkIndex* s_idx) {  // all threads of the block; barrier inside
+    __shared__ uint32_t s_tmp[kWorkLists];
+    for (int l = threadIdx.x; l < kWorkLists; l += blockDim.x) s_tmp[l] = min(w.count[l], w.seg_cap);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int l = 0; l < kWorkLists; ++l) {
+            s_idx->first[l] = run;
+            run += s_tmp[l];
         }
-        uint32_t total;
-        const uint32_t off = block_excl_scan(cnt, &total);
-        if (total == 0) continue;  // uniform across the block
-        if (threadIdx.x == 0) s_base = atomicAdd(&a.ctr->n_collide, (unsigned long long)total);
-        __syncthreads();
-        unsigned long long pos = s_base + off;
-        while (acc) {
-            const int k = __ffsll((long long)acc) - 1;
-            acc &= acc - 1;
-            const int4 mf = __ldg(reinterpret_cast<const int4*>(a.entries + (e - 1 - k)) + 1);
-            const bool i_is_hi = (uint32_t)m.w > (uint32_t)mf.w;
-            if (pos < a.cap_cand) a.cand[pos] = make_uint2((uint32_t)(i_is_hi ? m.x : mf.x), (uint32_t)(i_is_hi ? mf.x : m.x));
-            ++pos;
-        }
-        if (run > 64) {  // long slot runs (dense / clustered cells): redo the tests beyond the 64-bit window
-            for (uint32_t k = 64; k < run; ++k) {
-                const int4* pf = reinterpret_cast<const int4*>(a.entries + (e - 1 - k));
-                const int4 rf = __ldg(pf), mf = __ldg(pf + 1);
-                uint32_t hi, lo;
-                if (candidate_test(a, r, m, rf, mf, &hi, &lo)) {
-                    if (pos < a.cap_cand) a.cand[pos] = make_uint2(hi, lo);
-                    ++pos;
-                }
-            }
-        }
-        __syncthreads();  // s_base is rewritten by the next iteration
+        s_idx->first[kWorkLists] = run;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ WorkItem work_item_at(const WorkLists& w, const WorkIndex* s_idx, uint32_t p) {
+    int lo = 0, hi = kWorkLists;  // the list l with first[l] <= p < first[l + 1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_idx->first[mid] <= p) lo = mid;
+        else hi = mid;
+    }
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(w.items + (size_t)lo * w.seg_cap + (p - s_idx->first[lo])));
+    return WorkItem{q.x, q.y, q.z, q.w};
+}
+
+// Debug / parity view: the accepted candidate pairs as (gid hi, gid lo), unordered (cb200_fetch_candidate_pairs).
+__global__ void __launch_bounds__(kThreads) k_list_candidates(const CandArgs a, const WorkLists w, const HbRec* __restrict__ rec, uint2* out,
+                                                              unsigned long long* n_out, uint64_t cap) {
+    __shared__ WorkIndex s_idx;
+    work_index_build(w, &s_idx);
+    const uint32_t total = s_idx.first[kWorkLists];
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        const WorkItem it = work_item_at(w, &s_idx, p);
+        const RecHead ha = load_head(rec, it.a), hb = load_head(rec, it.b);
+        bool a_is_hi;
+        if (!candidate_test(a, ha, hb, it.slot, &a_is_hi)) continue;
+        const unsigned long long pos = warp_agg_claim(n_out);
+        if (pos < cap) out[pos] = a_is_hi ? make_uint2(ha.gid, hb.gid) : make_uint2(hb.gid, ha.gid);
     }
 }
 
@@ -702,8 +846,8 @@ struct StepResultDev {
 };
 
 struct SolveArgs {
-    const uint2* cand;
-    uint32_t cap_cand;
+    CandArgs cd;             // the candidate test of a work item
+    WorkLists work;          // k_enum_pairs' lists
     const uint2* ov_pairs;
     uint32_t n_ov;
     const HbRec* rec;
@@ -715,7 +859,7 @@ struct SolveArgs {
     uint32_t n_partial_a;
     StepResultDev* result;   // mapped host memory
     MinKey* local_key;       // device copy of the local minimum (sharded: input of the all-gather min)
-    // sharded: overlapping pairs are looked up by gid; only the owner-column rank solves them
+    // overlapping pairs are looked up by gid; sharded: only the owner-column rank solves them
     const uint32_t* vmap;    // gid -> record index (entries may be stale: validated)
     uint32_t id_space;
     int sharded;
@@ -742,60 +886,94 @@ __device__ __forceinline__ bool gid_lookup(const SolveArgs& a, uint32_t n_local,
     return true;
 }
 
+// Pair events are collected in shared memory and flushed with one global atomic per kSolveBuf events (instead of a
+// block scan + atomic + two barriers per iteration).
+constexpr uint32_t kSolveBuf = 4 * kThreads;
+
 __global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
+    __shared__ PairEvent s_ev[kSolveBuf];
+    __shared__ WorkIndex s_idx;
+    __shared__ uint32_t s_n, s_last;
     __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_last;
     MinKey best{kKeyMax, kKeyMax};
-    unsigned long long n_sep = 0;
-    const uint32_t n_cand = (uint32_t)min((unsigned long long)a.cap_cand, a.ctr->n_collide);
+    unsigned long long n_sep = 0, n_col = 0;
+    if (threadIdx.x == 0) s_n = 0;
+    work_index_build(a.work, &s_idx);
+    const uint32_t n_cand = s_idx.first[kWorkLists];
     const uint32_t total = n_cand + a.n_ov;
     const uint32_t n_local = a.ctr->n_local;
     const uint32_t stride = gridDim.x * blockDim.x;
+    auto flush = [&]() {  // all threads
+        __syncthreads();
+        const uint32_t n_ev = s_n;
+        if (n_ev) {
+            if (threadIdx.x == 0) s_base = atomicAdd(&a.ctr->n_pair_events, (unsigned long long)n_ev);
+            __syncthreads();
+            const unsigned long long pos = s_base;
+            for (uint32_t k = threadIdx.x; k < n_ev; k += blockDim.x)
+                if (pos + k < a.cap_events) a.events[pos + k] = s_ev[k];
+            __syncthreads();
+            if (threadIdx.x == 0) s_n = 0;
+            __syncthreads();
+        }
+    };
+    uint32_t pending_rounds = 0;
     for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
         const uint32_t p = base + threadIdx.x;
-        PairEvent ev{0.0, 0u, 0u};
-        uint32_t have = 0;
         if (p < total) {
             const bool sep = p >= n_cand;
-            uint2 pr = sep ? a.ov_pairs[p - n_cand] : a.cand[p];
+            uint32_t ia, ib, slot = 0;  // record indices
             bool present = true;
-            if (sep) present = gid_lookup(a, n_local, pr.x, &pr.x) && gid_lookup(a, n_local, pr.y, &pr.y);
+            if (sep) {
+                const uint2 pr = a.ov_pairs[p - n_cand];
+                present = gid_lookup(a, n_local, pr.x, &ia) && gid_lookup(a, n_local, pr.y, &ib);
+            } else {
+                const WorkItem it = work_item_at(a.work, &s_idx, p);
+                ia = it.a; ib = it.b; slot = it.slot;
+            }
             if (present) {
-                const RecHead hh = load_head(a.rec, pr.x), hl = load_head(a.rec, pr.y);
-                const int32_t owner_col = max(hh.sx, hl.sx);
-                if (!sep || (owner_col >= a.col_lo && owner_col < a.col_hi)) {
-                    const DurHb A = load_body(a.rec, pr.x, hh);
+                // all twelve 16-byte loads of the two records are issued before anything depends on them
+                const RecHead ha = load_head(a.rec, ia), hb = load_head(a.rec, ib);
+                const DurHb da = load_body(a.rec, ia, ha), db = load_body(a.rec, ib, hb);
+                bool a_is_hi = true;  // overlap pairs arrive as (hi, lo)
+                if (!sep) {
+                    present = candidate_test(a.cd, ha, hb, slot, &a_is_hi);
+                    n_col += present;
+                } else {
+                    const int32_t owner_col = max(ha.sx, hb.sx);
+                    present = owner_col >= a.col_lo && owner_col < a.col_hi;
+                }
+                if (present) {
+                    const DurHb A = pick(a_is_hi, da, db);
                     // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486): advanced by T - start = 0
-                    const DurHb B = advanced(load_body(a.rec, pr.y, hl), 0.0);
+                    const DurHb B = advanced(pick(a_is_hi, db, da), 0.0);
+                    const uint32_t gid_hi = a_is_hi ? ha.gid : hb.gid, gid_lo = a_is_hi ? hb.gid : ha.gid;
                     const double delay = sep ? separate_time(A, B, a.padding) : collide_time(A, B);
-                    if (delay != delay) report_error(a.ctr, kFNan, hh.gid);
+                    if (delay != delay) report_error(a.ctr, kFNan, gid_hi);
                     n_sep += sep;
                     const double t = a.T + delay;
                     if (t < kHighTime) {
                         const uint32_t kind_bit = sep ? 0u : kCollideBit;
-                        ev = PairEvent{t, hh.gid, hl.gid | kind_bit};
-                        have = 1;
-                        const MinKey k{time_key(t), kPairClass | ((uint64_t)hh.gid << 32) | kind_bit | hl.gid};
+                        s_ev[atomicAdd(&s_n, 1u)] = PairEvent{t, gid_hi, gid_lo | kind_bit};
+                        const MinKey k{time_key(t), kPairClass | ((uint64_t)gid_hi << 32) | kind_bit | gid_lo};
                         if (key_less(k, best)) best = k;
                     }
                 }
             }
         }
-        // block-aggregated append: one global atomic per block-iteration
-        uint32_t n_ev;
-        const uint32_t off = block_excl_scan(have, &n_ev);
-        if (n_ev == 0) continue;  // uniform
-        if (threadIdx.x == 0) s_base = atomicAdd(&a.ctr->n_pair_events, (unsigned long long)n_ev);
-        __syncthreads();
-        const unsigned long long pos = s_base + off;
-        if (have && pos < a.cap_events) a.events[pos] = ev;
-        __syncthreads();
+        // the buffer holds kSolveBuf events and an iteration adds at most blockDim.x
+        if (++pending_rounds == kSolveBuf / kThreads) {
+            flush();
+            pending_rounds = 0;
+        }
     }
+    flush();
     best = block_min(best);
-    const unsigned long long sep_tot = block_sum(n_sep);
+    const unsigned long long sep_tot = block_sum(n_sep), col_tot = block_sum(n_col);
     if (threadIdx.x == 0) {
         a.partial[a.n_partial_a + blockIdx.x] = best;
         if (sep_tot) atomicAdd(&a.ctr->n_separate, sep_tot);
+        if (col_tot) atomicAdd(&a.ctr->n_collide, col_tot);
         __threadfence();
         s_last = atomicAdd(&a.ctr->done_blocks, 1u) == gridDim.x - 1 ? 1u : 0u;
     }
@@ -817,7 +995,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
         if (a.local_key) *a.local_key = best;
         const volatile Counters* c = a.ctr;
         Counters out;
-        out.n_entries = c->n_entries; out.n_cells = c->n_cells; out.n_collide = c->n_collide; out.n_separate = c->n_separate;
+        out.n_entries = c->n_entries; out.n_cells = c->n_cells; out.n_separate = c->n_separate;
+        out.work_overflow = 0;
+        for (int l = 0; l < kWorkLists; ++l) out.work_overflow = max(out.work_overflow, a.work.count[l]);  // fullest sub-list
+        out.pad0 = 0;
+        out.n_collide = c->n_collide;
         out.n_pair_events = c->n_pair_events; out.n_solitaire = c->n_solitaire; out.err_slot = c->err_slot;
         out.err_flags = c->err_flags; out.scan_ticket = c->scan_ticket; out.overflow_entries = c->overflow_entries;
         out.done_blocks = c->done_blocks; out.n_local = c->n_local; out.overflow_send = c->overflow_send;

@@ -120,15 +120,15 @@ __device__ __forceinline__ void for_each_cellmate(const TableView& t, const Grid
             const uint32_t s = g.geom.slot(x, y);
             const uint32_t e0 = slot_run_start(g.slot_end, g.chunk_base, s), e1 = g.slot_end[s];
             for (uint32_t e = e0; e < e1; ++e) {
-                const int4* pe = reinterpret_cast<const int4*>(g.entries + e);
-                const int4 r = pe[0], m = pe[1];
-                const uint32_t v = (uint32_t)m.x;
+                const uint32_t v = g.entries[e].vidx;
+                // rows that moved, appeared or changed since the entry array was built are dirty; every other row's record
+                // still holds the IndexRect it was binned with
                 if (v >= t.n || v == self_row || t.dirty[v]) continue;
                 const RecHead hj = load_head_nc(t.rec, v);
-                if (hj.gid != (uint32_t)m.w || !(hj.kgb & 2u)) continue;
+                if (!(hj.kgb & 2u)) continue;
                 // ownership: (x, y) must be the min corner of the rect intersection (also rejects aliased slot-mates)
-                if (max(sx, r.x) != x || max(sy, r.y) != y) continue;
-                if (x >= min(ex, r.z) || y >= min(ey, r.w)) continue;
+                if (max(sx, hj.sx) != x || max(sy, hj.sy) != y) continue;
+                if (x >= min(ex, hj.ex) || y >= min(ey, hj.ey)) continue;
                 f(v, hj);
             }
         }
