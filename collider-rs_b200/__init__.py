@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libcollider_b200.so")
+LIB_PATH = os.environ.get("CB200_LIB") or os.path.join(_HERE, "lib", "libcollider_b200.so")
 
 KIND_CIRCLE, KIND_RECT = 0, 1
 GROUP_NONE = 0xFFFFFFFF
@@ -78,6 +78,11 @@ class StepResult(C.Structure):
     ]
 
 
+class P2PInfo(C.Structure):
+    _fields_ = [("rec_handle", C.c_uint8 * 64), ("mail_handle", C.c_uint8 * 64), ("rec_ptr", C.c_uint64), ("mail_ptr", C.c_uint64),
+                ("recv_offset_bytes", C.c_uint64), ("pid", C.c_uint64), ("device", C.c_int32), ("slab_records", C.c_uint32)]
+
+
 EXPORTS = (
     "cb200_abi_version", "cb200_create", "cb200_destroy", "cb200_last_error", "cb200_set_grid", "cb200_get_grid",
     "cb200_host_alloc", "cb200_host_free", "cb200_upload_state", "cb200_download_state", "cb200_set_overlaps",
@@ -85,6 +90,7 @@ EXPORTS = (
     "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
     "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_shard_set_slab", "cb200_set_stream", "cb200_shard_begin", "cb200_shard_finish",
     "cb200_shard_result", "cb200_set_resort_period", "cb200_resort_count", "cb200_set_stage_timing",
+    "cb200_shard_p2p_export", "cb200_shard_p2p_import", "cb200_shard_step", "cb200_shard_global_next", "cb200_shard_local_key",
     "cb200_collider_new", "cb200_collider_free", "cb200_collider_last_error", "cb200_collider_set_can_interact", "cb200_collider_time",
     "cb200_collider_next_time", "cb200_collider_set_time", "cb200_collider_next", "cb200_collider_get_hitbox", "cb200_collider_add_hitbox",
     "cb200_collider_set_hitbox_vel", "cb200_collider_remove_hitbox", "cb200_collider_get_overlaps", "cb200_collider_is_overlapping",
@@ -137,6 +143,12 @@ def load_library() -> C.CDLL:
     L.cb200_shard_finish.argtypes = [vp, C.POINTER(vp)]
     L.cb200_shard_result.argtypes = [vp, C.POINTER(StepResult)]
     L.cb200_set_stage_timing.argtypes = [vp, i32]
+    L.cb200_shard_p2p_export.argtypes = [vp, C.POINTER(P2PInfo)]
+    L.cb200_shard_p2p_import.argtypes = [vp, C.POINTER(P2PInfo)]
+    L.cb200_shard_step.argtypes = [vp, dbl, C.POINTER(VelView), dbl]
+    L.cb200_shard_global_next.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]
+    L.cb200_shard_local_key.argtypes = [vp]
+    L.cb200_shard_local_key.restype = vp
     L.cb200_set_resort_period.argtypes = [vp, i32]
     L.cb200_resort_count.argtypes = [vp]
     L.cb200_resort_count.restype = u64
@@ -290,6 +302,35 @@ class Engine:
             v = C.byref(VelView(*[None if a is None else a.ctypes.data for a in self._keep]))
         self._check(self._L.cb200_shard_begin(self._h, time, v, end_time, C.byref(send), C.byref(recv), C.byref(per_peer)))
         return dict(send_ptr=send.value, recv_ptr=recv.value, slab_bytes=per_peer.value)
+
+    # ---- direct exchange over peer memory (cb200_shard_p2p_*) ----
+    def p2p_export(self) -> bytes:
+        info = P2PInfo()
+        self._check(self._L.cb200_shard_p2p_export(self._h, C.byref(info)))
+        return bytes(info)
+
+    def p2p_import(self, infos):
+        """infos: one exported blob per rank, indexed by rank."""
+        arr = (P2PInfo * len(infos))(*[P2PInfo.from_buffer_copy(b) for b in infos])
+        self._check(self._L.cb200_shard_p2p_import(self._h, arr))
+
+    def shard_step(self, time: float, end_time: float = INF, vel_x=None, vel_y=None, rsz_x=None, rsz_y=None, end_time_arr=None):
+        """The whole sharded step with the direct exchange, asynchronous; shard_result() waits for it."""
+        arrs = [vel_x, vel_y, rsz_x, rsz_y, end_time_arr]
+        v = None
+        if not all(a is None for a in arrs):
+            self._keep = [None if a is None else _col(a, np.float64, self.n) for a in arrs]
+            v = C.byref(VelView(*[None if a is None else a.ctypes.data for a in self._keep]))
+        self._check(self._L.cb200_shard_step(self._h, time, v, end_time))
+
+    def shard_global_next(self):
+        """(time key, tie, complete) of the minimum over all ranks after a direct-exchange step."""
+        t, tie, ok = C.c_uint64(), C.c_uint64(), C.c_int()
+        self._check(self._L.cb200_shard_global_next(self._h, C.byref(t), C.byref(tie), C.byref(ok)))
+        return t.value, tie.value, bool(ok.value)
+
+    def shard_local_key_ptr(self) -> int:
+        return int(self._L.cb200_shard_local_key(self._h))
 
     def shard_finish(self) -> int:
         """Asynchronous back half; returns the device address of this rank's (time key, tie) minimum (2 x u64)."""

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <map>
@@ -93,6 +94,16 @@ struct cb200_ctx {
     bool own_stream = true;
     DevBuf<uint32_t> vmap;   // gid -> record index (direct-addressed over the id space)
     uint64_t id_space = 0;
+    // direct exchange over peer memory (kernels.cuh "Direct halo exchange")
+    bool p2p = false;
+    PeerTable peers{};
+    Mailbox* d_mail = nullptr;
+    void* ipc_opened[2 * kMaxWorld] = {};
+    int n_ipc_opened = 0;
+    uint64_t p2p_step = 0;
+    int p2p_parity = 0;
+    GlobalKey* h_gkey = nullptr;  // pinned, mapped
+    GlobalKey* d_gkey = nullptr;
     int shard_phase = 0;     // 0 idle, 1 after shard_begin, 2 after shard_finish (result pending)
     double shard_T = 0;
 
@@ -295,6 +306,9 @@ void cb200_destroy(cb200_ctx* c) {
     c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); c->ev_out.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->d_key) cudaFree(c->d_key);
+    for (int i = 0; i < c->n_ipc_opened; ++i) cudaIpcCloseMemHandle(c->ipc_opened[i]);
+    if (c->d_mail) cudaFree(c->d_mail);
+    if (c->h_gkey) cudaFreeHost(c->h_gkey);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->pinned_stage) cudaFreeHost(c->pinned_stage);
     for (auto& ev : c->ev_t)
@@ -382,12 +396,14 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
         // halo slab: header + room for n/256 (>= 2047) records leaving the strip (cb200_shard_set_slab overrides); the
         // visitor table holds the n own records followed by one received slab per rank
         if (ctx->slab == 0) ctx->slab = (uint32_t)std::max<size_t>(n / 256, 2047) + 1;
-        CU(ctx->rec.reserve(n + (size_t)ctx->slab * ctx->shard.world));
+        // (two receive areas: the direct exchange double-buffers them by step parity)
+        CU(ctx->rec.reserve(n + 2 * (size_t)ctx->slab * ctx->shard.world));
+        ctx->p2p = false;  // peers must be re-imported: the receive area moved
         CU(ctx->send.reserve(ctx->slab));
         CU(ctx->send_count.reserve(1));
         CU(ctx->vmap.reserve(ctx->id_space));
         CU(cudaMemsetAsync(ctx->vmap.p, 0xff, ctx->id_space * 4, ctx->stream));
-        CU(cudaMemsetAsync(ctx->rec.p + n, 0, (size_t)ctx->slab * ctx->shard.world * sizeof(HbRec), ctx->stream));
+        CU(cudaMemsetAsync(ctx->rec.p + n, 0, 2 * (size_t)ctx->slab * ctx->shard.world * sizeof(HbRec), ctx->stream));
     } else {
         CU(ctx->row_of.reserve(cap));
         if (n) k_iota_rows<<<((uint32_t)n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>((uint32_t)n, ctx->label.p, ctx->row_of.p);
@@ -545,6 +561,28 @@ static int resort_rows(cb200_ctx* ctx) {
     return CB200_OK;
 }
 
+// Every device allocation a step (and a re-sort) needs.  cudaMalloc synchronises the device, so contexts that wait for each
+// other inside their kernels (direct exchange) must have done this before the first step.
+static int reserve_step_buffers(cb200_ctx* ctx) {
+    const uint32_t n = ctx->n;
+    const uint32_t n_slots = ctx->geom.n_slots();
+    CU(ctx->slots.reserve(n_slots));
+    CU(ctx->chunk_base.reserve(n_slots / kScanChunk));
+    if (ctx->entries.cap == 0) CU(ctx->entries.reserve((size_t)n * 4 + 1024));
+    if (ctx->work.cap == 0) CU(ctx->work.reserve(std::max<size_t>((size_t)n * 2 + 1024, (size_t)kWorkLists * 256)));
+    CU(ctx->work_count.reserve(kWorkLists));
+    if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
+    CU(ctx->partial.reserve((size_t)ctx->sm_count * 16));
+    if (n >= 2) {
+        for (int k = 0; k < 11; ++k) CU(ctx->col_alt[k].reserve(ctx->col[k].cap));
+        CU(ctx->kind_alt.reserve(ctx->kind.cap)); CU(ctx->reit_alt.reserve(ctx->reit.cap)); CU(ctx->group_alt.reserve(ctx->group.cap));
+        CU(ctx->mask_alt.reserve(ctx->mask.cap)); CU(ctx->label_alt.reserve(ctx->label.cap));
+        if (ctx->sharded) CU(ctx->ord_alt.reserve(ctx->ord.cap));
+        CU(ctx->sort_key.reserve(n)); CU(ctx->src_row.reserve(n));
+    }
+    return CB200_OK;
+}
+
 static int prepare_buffers(cb200_ctx* ctx) {
     const uint32_t n = ctx->n;
     const uint32_t n_slots = ctx->geom.n_slots();
@@ -623,7 +661,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     const GridGeom g = ctx->geom;
     const uint32_t n_slots = g.n_slots();
     const ShardGeom sh = ctx->sharded ? ctx->shard : whole_world();
-    const VisSpace vs{ctx->n, ctx->slab, sh.world, sh.rank};
+    const VisSpace vs{ctx->n, ctx->n + (ctx->p2p ? (uint32_t)ctx->p2p_parity * (uint32_t)sh.world * ctx->slab : 0u), ctx->slab, sh.world, sh.rank};
     const uint32_t n_vis_max = ctx->sharded ? ctx->n + ctx->slab * (uint32_t)sh.world : ctx->n;
     const uint32_t grid_v = std::max<uint32_t>(1, std::min<uint32_t>((n_vis_max + kThreads - 1) / kThreads, ctx->sm_count * 8));
     const bool use_map = ctx->sharded && ctx->n_ov;
@@ -899,6 +937,140 @@ int cb200_shard_result(cb200_ctx* ctx, cb200_step_result* out) {
     ctx->timing_valid = true;
     return fill_result(ctx, out);
 }
+
+// ---- direct exchange over peer memory --------------------------------------------------------------------
+int cb200_shard_p2p_export(cb200_ctx* ctx, cb200_p2p_info* out) {
+    if (!ctx || !out) return CB200_E_ARG;
+    if (!ctx->sharded || !ctx->have_state) return fail(ctx, CB200_E_STATE, "p2p_export needs a configured, uploaded sharded context");
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->d_mail) {
+        CU(cudaMalloc(&ctx->d_mail, sizeof(Mailbox)));
+        CU(cudaHostAlloc(&ctx->h_gkey, sizeof(GlobalKey), cudaHostAllocMapped));
+        CU(cudaHostGetDevicePointer((void**)&ctx->d_gkey, ctx->h_gkey, 0));
+    }
+    CU(cudaMemset(ctx->d_mail, 0, sizeof(Mailbox)));
+    memset(out, 0, sizeof(*out));
+    static_assert(sizeof(cudaIpcMemHandle_t) == CB200_IPC_HANDLE_BYTES, "ipc handle size");
+    cudaIpcMemHandle_t h;
+    // (a failing cudaIpcGetMemHandle is not fatal: peers in the same process use the raw pointers)
+    if (cudaIpcGetMemHandle(&h, ctx->rec.p) == cudaSuccess) memcpy(out->rec_handle, &h, sizeof(h));
+    else cudaGetLastError();
+    if (cudaIpcGetMemHandle(&h, ctx->d_mail) == cudaSuccess) memcpy(out->mail_handle, &h, sizeof(h));
+    else cudaGetLastError();
+    out->rec_ptr = (uint64_t)(uintptr_t)ctx->rec.p;
+    out->mail_ptr = (uint64_t)(uintptr_t)ctx->d_mail;
+    out->recv_offset_bytes = (uint64_t)ctx->n * sizeof(HbRec);
+    out->pid = (uint64_t)getpid();
+    out->device = ctx->device;
+    out->slab_records = ctx->slab;
+    return CB200_OK;
+}
+
+int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world entries, indexed by rank */) {
+    if (!ctx || !infos) return CB200_E_ARG;
+    if (!ctx->sharded || !ctx->d_mail) return fail(ctx, CB200_E_STATE, "p2p_import after p2p_export");
+    CU(cudaSetDevice(ctx->device));
+    for (int i = 0; i < ctx->n_ipc_opened; ++i) cudaIpcCloseMemHandle(ctx->ipc_opened[i]);
+    ctx->n_ipc_opened = 0;
+    const int world = ctx->shard.world, rank = ctx->shard.rank;
+    PeerTable pt{};
+    for (int d = 0; d < world; ++d) {
+        if (infos[d].slab_records != ctx->slab) return fail(ctx, CB200_E_ARG, "peers must use the same halo slab size (cb200_shard_set_slab)");
+        if (d == rank) {
+            pt.recv[d] = ctx->rec.p + ctx->n;
+            pt.mail[d] = ctx->d_mail;
+            continue;
+        }
+        char* rec_base = nullptr;
+        Mailbox* mail = nullptr;
+        if (infos[d].pid == (uint64_t)getpid()) {
+            // same process (several contexts of one host, e.g. the tests): the peer's pointers are valid here
+            rec_base = (char*)(uintptr_t)infos[d].rec_ptr;
+            mail = (Mailbox*)(uintptr_t)infos[d].mail_ptr;
+            if (infos[d].device != ctx->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(infos[d].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, CB200_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+        } else {
+            cudaIpcMemHandle_t h;
+            void* p = nullptr;
+            memcpy(&h, infos[d].rec_handle, sizeof(h));
+            CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            ctx->ipc_opened[ctx->n_ipc_opened++] = p;
+            rec_base = (char*)p;
+            memcpy(&h, infos[d].mail_handle, sizeof(h));
+            CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            ctx->ipc_opened[ctx->n_ipc_opened++] = p;
+            mail = (Mailbox*)p;
+        }
+        pt.recv[d] = reinterpret_cast<HbRec*>(rec_base + infos[d].recv_offset_bytes);
+        pt.mail[d] = mail;
+    }
+    ctx->peers = pt;
+    ctx->p2p = true;
+    ctx->p2p_step = 0;
+    // CUDA loads a kernel's code at its first launch, and that load waits for the device to go idle: it must not happen
+    // behind a kernel that is waiting for a peer.  Touch every kernel of the step now.
+    {
+        cudaFuncAttributes fa;
+        const void* fns[] = {(const void*)k_step_zero, (const void*)k_stage_a<true>, (const void*)k_slab_header, (const void*)k_push_halo,
+                             (const void*)k_wait_flags, (const void*)k_index_visitors<true>, (const void*)k_index_visitors<false>,
+                             (const void*)k_scan_slots, (const void*)k_scatter<true>, (const void*)k_enum_pairs, (const void*)k_solve,
+                             (const void*)k_push_key, (const void*)k_reduce_keys, (const void*)k_resort_count, (const void*)k_resort_rank,
+                             (const void*)k_resort_gather};
+        for (const void* f : fns) CU(cudaFuncGetAttributes(&fa, f));
+    }
+    return reserve_step_buffers(ctx);
+}
+
+// One whole sharded step, asynchronous on the context's stream: stage A + halo pack, push the slab to every peer, wait for
+// theirs, bin / enumerate / solve, exchange the next-event keys.  cb200_shard_result waits for it.
+int cb200_shard_step(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time) {
+    if (!ctx) return CB200_E_ARG;
+    if (!ctx->p2p) return fail(ctx, CB200_E_STATE, "cb200_shard_p2p_import first");
+    if (!ctx->have_state) return fail(ctx, CB200_E_STATE, "shard_step before upload_state");
+    if (!(time < 1e50)) return fail(ctx, CB200_E_ARG, "requires time < 1e50");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev_t[ST_PRE], ctx->stream));
+    const double* nv[5];
+    int rc = stage_vel(ctx, vel, nv);
+    if (rc != CB200_OK) return rc;
+    if ((rc = prepare_buffers(ctx)) != CB200_OK) return rc;
+    ctx->p2p_step += 1;
+    ctx->p2p_parity = (int)(ctx->p2p_step & 1);
+    const int world = ctx->shard.world, rank = ctx->shard.rank;
+    if ((rc = enqueue_front(ctx, time, true, nv, end_time)) != CB200_OK) return rc;
+    if (world > 1) {
+        k_push_halo<<<world - 1, 1024, 0, ctx->stream>>>(ctx->send.p, ctx->peers, world, rank, ctx->slab, ctx->p2p_parity, ctx->p2p_step);
+        k_wait_flags<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_mail->flag_halo, world, rank, ctx->p2p_step);
+        ctx->launches += 2;
+    }
+    ctx->shard_T = time;
+    if ((rc = enqueue_back(ctx, time, false)) != CB200_OK) return rc;
+    k_push_key<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_key, ctx->d_ctr, ctx->work_count.p, (uint32_t)std::min<size_t>(ctx->work.cap / kWorkLists, 0x7fffffffu),
+                                                 (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu), (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu),
+                                                 ctx->peers, ctx->d_mail, world, rank, ctx->p2p_parity, ctx->p2p_step);
+    k_reduce_keys<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_mail, world, rank, ctx->p2p_parity, ctx->p2p_step, ctx->d_gkey);
+    ctx->launches += 2;
+    CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
+    ctx->shard_phase = 2;
+    return CB200_OK;
+}
+
+// After cb200_shard_result of a direct-exchange step: the global next event (minimum over all ranks).  *complete == 0:
+// some rank had to re-run the step with larger buffers after the keys were exchanged — all-gather the local keys again
+// (cb200_shard_finish's local_key) to get the final minimum.
+int cb200_shard_global_next(cb200_ctx* ctx, uint64_t* time_key_out, uint64_t* tie_out, int* complete) {
+    if (!ctx) return CB200_E_ARG;
+    if (!ctx->p2p || !ctx->h_gkey || ctx->h_gkey->tag != ctx->p2p_step) return fail(ctx, CB200_E_STATE, "no direct-exchange step has completed");
+    if (time_key_out) *time_key_out = ctx->h_gkey->t;
+    if (tie_out) *tie_out = ctx->h_gkey->tie;
+    if (complete) *complete = (int)ctx->h_gkey->complete;
+    return CB200_OK;
+}
+
+void* cb200_shard_local_key(cb200_ctx* ctx) { return ctx ? ctx->d_key : nullptr; }
 
 // ---- event queue materialisation -------------------------------------------------------------------------
 static int sort_events(cb200_ctx* ctx) {

@@ -25,6 +25,8 @@ struct StateCols {  // SoA hitbox table; rows are kept in grid-slot order (k_res
 // the rank whose strip holds the pair's owner cell column max(sx_i, sx_j), which is never left of either rect's
 // start: records only ever travel to ranks at or right of their start column.
 constexpr int kMaxWorld = 64;
+constexpr int kSubLists = 8;               // work sub-lists per kind pair (k_enum_pairs)
+constexpr int kWorkLists = 3 * kSubLists;
 struct ShardGeom {
     int world, rank;
     int32_t col_lo, col_hi;          // own strip [col_lo, col_hi); one device: the whole i32 range
@@ -53,14 +55,15 @@ struct StepArgs {
 };
 
 // Sharded visitor index space: the own records kept for this strip are compacted at rec[0, n_local); the records
-// received from rank d sit in rec[n_own + d * slab + 1 ...] behind that slab's header.
+// received from rank d sit in rec[recv0 + d * slab + 1 ...] behind that slab's header.
 struct VisSpace {
     uint32_t n_own;  // capacity of the own region (= residents)
+    uint32_t recv0;  // first record of this step's received slabs (n_own; direct exchange: + parity * world * slab)
     uint32_t slab;   // records per slab including the header
     int world, rank; // slab `rank` is this rank's own halo slab coming back from the all-gather: ignored
 };
 __device__ __forceinline__ uint32_t slab_count(const HbRec* rec, const VisSpace& vs, int d) {
-    return __ldg(reinterpret_cast<const unsigned int*>(rec + vs.n_own + (size_t)d * vs.slab));
+    return __ldg(reinterpret_cast<const unsigned int*>(rec + vs.recv0 + (size_t)d * vs.slab));
 }
 // i in [0, n_local + world * slab) -> record index, or false for headers / unused slab tail
 __device__ __forceinline__ bool vis_record(const HbRec* rec, const VisSpace& vs, uint32_t n_local, uint32_t i, uint32_t* v) {
@@ -70,7 +73,7 @@ __device__ __forceinline__ bool vis_record(const HbRec* rec, const VisSpace& vs,
     }
     const uint32_t j = i - n_local, d = j / vs.slab, k = j % vs.slab;
     if ((int)d == vs.rank || k == 0 || k - 1 >= slab_count(rec, vs, (int)d)) return false;
-    *v = vs.n_own + j;
+    *v = vs.recv0 + j;
     return true;
 }
 
@@ -348,6 +351,100 @@ __global__ void __launch_bounds__(kThreads) k_index_visitors(const HbRec* __rest
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Direct halo exchange over peer memory (NVLink / NVSwitch): every rank's visitor table and mailbox are mapped into its
+// peers (cudaIpc or same-process pointers), so the exchange is two tiny kernels instead of two NCCL collectives —
+//   k_push_halo   copies the rank's halo slab (header + the records that are actually there) straight into slot `rank` of
+//                 every peer's receive area for this step's parity, then raises flag_halo[rank] = tag on that peer
+//   k_wait_halo   spins (on local memory) until every peer has raised its flag for this step
+// and the same pattern for the 24-byte next-event keys after the solve stage (k_push_key / k_reduce_keys).  Slab areas and
+// key rows are double-buffered by step parity; a rank can run at most one step ahead of a peer, because its next back half
+// needs that peer's next flag.  tag = the step number.  A rank whose buffers overflowed in the step marks its key incomplete;
+// every rank then sees complete == 0 in the reduced key and the host repeats the key exchange after the re-run.
+struct Mailbox {
+    unsigned long long flag_halo[kMaxWorld];
+    unsigned long long flag_key[kMaxWorld];
+    unsigned long long keys[2][kMaxWorld][4];  // [parity][rank] = {time key, tie, complete, -}
+};
+struct PeerTable {
+    HbRec* recv[kMaxWorld];     // peer d's receive area for parity 0, slot 0 (parity 1 follows world * slab records later)
+    Mailbox* mail[kMaxWorld];
+};
+
+__global__ void __launch_bounds__(1024) k_push_halo(const HbRec* __restrict__ send, PeerTable peers, int world, int rank, uint32_t slab, int parity,
+                                                    unsigned long long tag) {
+    const int d = blockIdx.x + (blockIdx.x >= (unsigned)rank ? 1 : 0);  // blocks enumerate the peers
+    if (d >= world) return;
+    const uint32_t count = min(*reinterpret_cast<const unsigned int*>(send), slab - 1u);
+    const int4* src = reinterpret_cast<const int4*>(send);
+    int4* dst = reinterpret_cast<int4*>(peers.recv[d] + ((size_t)parity * world + rank) * slab);
+    const uint32_t n16 = (count + 1u) * 6u;  // header + records, 96 B = 6 x 16 B each
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(&peers.mail[d]->flag_halo[rank]) = tag;
+        __threadfence_system();
+    }
+}
+__global__ void k_wait_flags(const unsigned long long* flags, int world, int rank, unsigned long long tag) {
+    const int d = threadIdx.x;
+    if (d >= world || d == rank) return;
+    while (*reinterpret_cast<const volatile unsigned long long*>(flags + d) < tag) __nanosleep(100);
+    __threadfence_system();
+}
+__global__ void k_push_key(const MinKey* __restrict__ local_key, const Counters* ctr, const uint32_t* work_count, uint32_t seg_cap, uint32_t cap_entries,
+                           uint32_t cap_events, PeerTable peers, Mailbox* own, int world, int rank, int parity, unsigned long long tag) {
+    const int d = threadIdx.x;
+    if (d >= world) return;
+    // complete = no buffer of this rank overflowed in this step (else the step is re-run and the keys exchanged again)
+    unsigned long long complete = 1;
+    if (ctr->overflow_entries || ctr->overflow_send || ctr->n_entries > cap_entries || ctr->n_pair_events > cap_events) complete = 0;
+    for (int l = 0; l < kWorkLists; ++l)
+        if (work_count[l] > seg_cap) complete = 0;
+    Mailbox* m = d == rank ? own : peers.mail[d];
+    volatile unsigned long long* row = m->keys[parity][rank];
+    row[0] = local_key->t;
+    row[1] = local_key->tie;
+    row[2] = complete;
+    __threadfence_system();
+    if (d != rank) {
+        *reinterpret_cast<volatile unsigned long long*>(&m->flag_key[rank]) = tag;
+        __threadfence_system();
+    }
+}
+struct GlobalKey {
+    unsigned long long t, tie, complete, tag;
+};
+__global__ void k_reduce_keys(const Mailbox* own, int world, int rank, int parity, unsigned long long tag, GlobalKey* out /* mapped host */) {
+    __shared__ unsigned long long s_t[kMaxWorld], s_tie[kMaxWorld], s_ok[kMaxWorld];
+    const int d = threadIdx.x;
+    if (d < world) {
+        if (d != rank)
+            while (*reinterpret_cast<const volatile unsigned long long*>(&own->flag_key[d]) < tag) __nanosleep(100);
+        __threadfence_system();
+        const volatile unsigned long long* row = own->keys[parity][d];
+        s_t[d] = row[0];
+        s_tie[d] = row[1];
+        s_ok[d] = row[2];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MinKey best{kKeyMax, kKeyMax};
+        unsigned long long ok = 1;
+        for (int k = 0; k < world; ++k) {
+            const MinKey c{s_t[k], s_tie[k]};
+            if (key_less(c, best)) best = c;
+            ok &= s_ok[k];
+        }
+        out->t = best.t;
+        out->tie = best.tie;
+        out->complete = ok;
+        out->tag = tag;
+        __threadfence_system();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Step prologue: one kernel zeroes everything a step accumulates into (slot table, counters, halo count).
 __global__ void __launch_bounds__(kThreads) k_step_zero(uint4* slots4, uint32_t n4, Counters* ctr, uint32_t* send_count, uint32_t* work_count,
                                                         uint32_t n_work_lists) {
@@ -615,8 +712,6 @@ __global__ void k_overlap_map_ids(const uint64_t* __restrict__ ids, uint32_t n, 
 constexpr int kEnumChunk = 128;                  // entries per warp and round
 constexpr int kEnumSteps = kEnumChunk / 32;
 constexpr int kEnumTile = kEnumChunk * (kThreads / 32);  // entries per block and round
-constexpr int kSubLists = 8;                     // per kind pair
-constexpr int kWorkLists = 3 * kSubLists;
 
 struct WorkItem {
     uint32_t a, b;  // record indices of the entry and of its predecessor
@@ -875,8 +970,8 @@ __device__ __forceinline__ bool gid_lookup(const SolveArgs& a, uint32_t n_local,
     if (!a.sharded) {
         if (v >= a.vs.n_own) return false;
     } else if (v >= n_local) {
-        if (v < a.vs.n_own) return false;
-        const uint32_t j = v - a.vs.n_own;
+        if (v < a.vs.recv0) return false;
+        const uint32_t j = v - a.vs.recv0;
         if (j >= (uint32_t)a.vs.world * a.vs.slab) return false;
         const uint32_t d = j / a.vs.slab, k = j % a.vs.slab;
         if ((int)d == a.vs.rank || k == 0 || k - 1 >= slab_count(a.rec, a.vs, (int)d)) return false;
@@ -890,7 +985,10 @@ __device__ __forceinline__ bool gid_lookup(const SolveArgs& a, uint32_t n_local,
 // block scan + atomic + two barriers per iteration).
 constexpr uint32_t kSolveBuf = 4 * kThreads;
 
-__global__ void __launch_bounds__(kThreads, 4) k_solve(const SolveArgs a) {
+#ifndef CB200_LB_SOLVE
+#define CB200_LB_SOLVE 4
+#endif
+__global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveArgs a) {
     __shared__ PairEvent s_ev[kSolveBuf];
     __shared__ WorkIndex s_idx;
     __shared__ uint32_t s_n, s_last;

@@ -123,7 +123,7 @@ class ShardedEngine:
     -> all-gather of the keys, and synchronises once at the end."""
 
 
-    def __init__(self, cb, cell_width: float, padding: float, device_index: int, bounds, id_space: int, exchange: Exchange):
+    def __init__(self, cb, cell_width: float, padding: float, device_index: int, bounds, id_space: int, exchange: Exchange, direct: bool = True):
         import torch
 
         self.cb, self.ex = cb, exchange
@@ -132,10 +132,27 @@ class ShardedEngine:
         self.eng.shard_configure(exchange.rank, exchange.world, bounds, id_space)
         self.eng.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._bufs = None
+        self.want_direct, self.direct = direct, False
 
     def upload_state(self, **cols):
         self.eng.upload_state(**cols)
         self._bufs = None
+        self.direct = False
+        if self.want_direct:
+            # Direct exchange over peer memory: the ranks swap their cudaIpc handles once (host side, through the process
+            # group) and from then on the step kernels write halo records and keys straight into the peers' memory.
+            # If a peer cannot be opened (no peer access between two devices), every rank falls back to the collectives.
+            infos = [None] * self.ex.world
+            self.ex.dist.all_gather_object(infos, self.eng.p2p_export(), group=self.ex.group)
+            ok = 1
+            try:
+                self.eng.p2p_import(infos)
+            except self.cb.ColliderError as e:
+                self.direct_error = str(e)
+                ok = 0
+            oks = [None] * self.ex.world
+            self.ex.dist.all_gather_object(oks, ok, group=self.ex.group)
+            self.direct = all(oks)
 
     def set_overlaps(self, a, b):
         self.eng.set_overlaps(a, b)
@@ -143,6 +160,17 @@ class ShardedEngine:
     def bulk_update(self, time: float, end_time: float, **vel):
         import torch
 
+        if self.direct:
+            self.eng.shard_step(time, end_time=end_time, **vel)
+            res = self.eng.shard_result()  # the one host synchronisation of the step
+            tkey, tie, complete = self.eng.shard_global_next()
+            if not complete:  # some rank re-ran the step with larger buffers: every rank sees this and repeats the key exchange
+                keys = self.ex.all_gather_keys(wrap(self.eng.shard_local_key_ptr(), 16, self.device).view(torch.int64))
+                tkey, tie = min_key(keys.tolist())
+            self.local_result = res
+            self.next_key = (tkey, tie)
+            self.next_event = decode_key(tkey, tie)
+            return res
         st = self.eng.shard_begin(time, end_time=end_time, **vel)
         key = (st["send_ptr"], st["recv_ptr"], st["slab_bytes"])
         if self._bufs is None or self._bufs[0] != key:
@@ -161,6 +189,8 @@ class ShardedEngine:
         """(records sent, records received) of the last step — reads the slab headers (D2H; diagnostics only)."""
         import torch
 
+        if self._bufs is None:
+            return 0, 0  # direct exchange: the slabs live in the engine
         _, send, recv = self._bufs
         per = send.numel()
         s = int(send[:4].view(torch.int32).item())

@@ -195,6 +195,34 @@ int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
 int cb200_shard_finish(cb200_ctx* ctx, void** local_key);
 int cb200_shard_result(cb200_ctx* ctx, cb200_step_result* out);
 
+/* Direct halo exchange over peer memory (NVLink 5 / NVSwitch) — replaces the two collectives of a sharded step by device
+ * kernels that write straight into the peers' memory: after stage A each rank copies its halo slab (only the records that
+ * are there) into slot `rank` of every peer's visitor table and raises a flag in the peer's mailbox; the binning kernels
+ * start once all flags of the step are up; the 24-byte next-event keys travel the same way after the solve stage.  One
+ * host synchronisation per step, no NCCL call on the data path.
+ *   cb200_shard_p2p_export : after cb200_upload_state; fills `info` (cudaIpc handles of the visitor table and the mailbox,
+ *                            the receive offset).  The host exchanges the infos of all ranks (any transport: they are
+ *                            sent once) and hands the table, indexed by rank, to
+ *   cb200_shard_p2p_import : opens the peers (cudaIpcOpenMemHandle; contexts of the same process are addressed directly).
+ *   cb200_shard_step       : the whole step, asynchronous on the context's stream.  Then cb200_shard_result (waits; local
+ *                            result) and cb200_shard_global_next (the minimum over all ranks as (time key, tie):
+ *                            cb200_step_result.next_event of the winning rank in the order of the device keys). */
+#define CB200_IPC_HANDLE_BYTES 64
+typedef struct cb200_p2p_info {
+    uint8_t rec_handle[CB200_IPC_HANDLE_BYTES];
+    uint8_t mail_handle[CB200_IPC_HANDLE_BYTES];
+    uint64_t rec_ptr, mail_ptr;   /* valid in the exporting process only */
+    uint64_t recv_offset_bytes;   /* of the receive area inside the visitor table allocation */
+    uint64_t pid;
+    int32_t device;
+    uint32_t slab_records;
+} cb200_p2p_info;
+int cb200_shard_p2p_export(cb200_ctx* ctx, cb200_p2p_info* info);
+int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world entries, indexed by rank */);
+int cb200_shard_step(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time);
+int cb200_shard_global_next(cb200_ctx* ctx, uint64_t* time_key, uint64_t* tie, int* complete);
+void* cb200_shard_local_key(cb200_ctx* ctx); /* device address of this rank's (time key, tie): input of a repeated key all-gather */
+
 /* Events queued by the last bulk step, sorted by the canonical order (time, class, hi id, kind, lo id)
  * (events.rs:60-68 with SURVEY.md §8c tie-break).  Copies events [offset, offset+cap) into buf. */
 int cb200_fetch_events(cb200_ctx* ctx, cb200_event* buf, uint64_t cap, uint64_t offset, uint64_t* n_out);

@@ -42,7 +42,7 @@ def key_of(ev):
     return np.lexsort((ev["b"], kbit, ev["a"], cls, ev["time"]))
 
 
-def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space"):
+def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space", direct=False):
     n = len(scene["id"])
     orc = oracle.Collider(CW, PAD)
     orc.add_hitboxes(scene)
@@ -60,6 +60,11 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
         m = owner == r
         e.upload_state(**{k: v[m] for k, v in st.items()})
         engs.append(e)
+    if direct:
+        # direct exchange over peer memory: here the "peers" are contexts of this process, addressed by raw pointers
+        infos = [e.p2p_export() for e in engs]
+        for e in engs:
+            e.p2p_import(infos)
     T = 0.0
     total_halo = 0
     for step in range(steps):
@@ -68,18 +73,31 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
             e.set_overlaps(ov_a, ov_b)
         end = np.inf if end_dt is None else T + end_dt
         orc.bulk_update(end_time=end, record_candidates=True)
-        states = [e.shard_begin(T, end_time=end) for e in engs]
-        exchange_on_one_gpu(engs, states)
-        key_ptrs = [e.shard_finish() for e in engs]
-        results = [e.shard_result() for e in engs]
         import torch
 
         dev = torch.device("cuda", 0)
-        for st in states:  # records that actually travelled: the slab headers
-            total_halo += int(sharding.wrap(st["send_ptr"], 4, dev).view(torch.int32).item())
-        # the device-side local keys, all-gathered and min-reduced like sharding.ShardedEngine does
-        rows = [sharding.wrap(p, 16, dev).view(torch.int64).tolist() for p in key_ptrs]
-        global_event = sharding.decode_key(*sharding.min_key(rows))
+        if direct:
+            for e in engs:  # every rank's step is enqueued before any is waited for: the kernels wait for each other's flags
+                e.shard_step(T, end_time=end)
+            results = [e.shard_result() for e in engs]
+            gk = [e.shard_global_next() for e in engs]
+            rows = [sharding.wrap(e.shard_local_key_ptr(), 16, dev).view(torch.int64).tolist() for e in engs]
+            want = sharding.min_key(rows)
+            for tkey, tie, complete in gk:
+                assert not complete or (tkey, tie) == want  # every rank reduced the same global minimum on the device
+            assert step == 0 or all(c for _, _, c in gk), "only the first step may have to grow buffers"
+            global_event = sharding.decode_key(*want)
+            total_halo += 1
+        else:
+            states = [e.shard_begin(T, end_time=end) for e in engs]
+            exchange_on_one_gpu(engs, states)
+            key_ptrs = [e.shard_finish() for e in engs]
+            results = [e.shard_result() for e in engs]
+            for st in states:  # records that actually travelled: the slab headers
+                total_halo += int(sharding.wrap(st["send_ptr"], 4, dev).view(torch.int32).item())
+            # the device-side local keys, all-gathered and min-reduced like sharding.ShardedEngine does
+            rows = [sharding.wrap(p, 16, dev).view(torch.int64).tolist() for p in key_ptrs]
+            global_event = sharding.decode_key(*sharding.min_key(rows))
         # events: union over ranks, merged in the canonical order
         ev = np.concatenate([e.fetch_events() for e in engs])
         ev = ev[key_of(ev)]
@@ -117,6 +135,17 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
 def test_sharded_equals_single_collider(oracle, world):
     halo = run_sharded_case(oracle, scenes.uniform_density(6000), world, steps=3, dt=0.1, end_dt=0.1)
     assert halo > 0, "the scene must actually exercise the halo exchange"
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_direct_exchange(oracle, world):
+    """The same parity bar with the halo records and keys pushed straight into the peers' memory by the step kernels
+    (cb200_shard_step), no collective and no host copy in between."""
+    run_sharded_case(oracle, scenes.uniform_density(6000), world, steps=4, dt=0.1, end_dt=0.1, direct=True)
+
+
+def test_sharded_direct_exchange_clustered(oracle):
+    run_sharded_case(oracle, scenes.c5(8000), 4, steps=1, dt=0.1, end_dt=0.1, direct=True)  # (one step: the harness does not replay Reiterates)
 
 
 def test_sharded_full_cell_sweeps_and_reiterates(oracle):
