@@ -200,7 +200,8 @@ def _main(out):
         sharding = importlib.import_module("collider-rs_b200.sharding")
         side = math.sqrt(n / (1.0 if args.workload == "c3_dense" else 0.025))
         bounds = sharding.strip_bounds(world, 0.0, side * world, scenes.CELL_WIDTH)
-        sh = sharding.ShardedEngine(cb, scenes.CELL_WIDTH, scenes.PADDING, local_rank, bounds, n * world, sharding.Exchange())
+        sh = sharding.ShardedEngine(cb, scenes.CELL_WIDTH, scenes.PADDING, local_rank, bounds, n * world, sharding.Exchange(),
+                                    direct=os.environ.get("CB200_EXCHANGE", "direct") != "nccl")
         eng = sh.eng
         if args.grid:
             eng.set_grid(*[int(v) for v in args.grid.split(",")])
@@ -327,9 +328,14 @@ def _main(out):
             "clocks": sampler.summary(),
         }
         if world > 1:
-            line["config"]["parallelism"] = f"spatial sharding: {world} column strips, NCCL halo exchange of 96-B records + all-gather min"
-            hs, hr = sh.halo_counts()
-            line["halo_records_last_step_rank0"] = {"sent": hs, "received": hr}
+            if sh.direct:
+                line["config"]["parallelism"] = (f"spatial sharding: {world} column strips; halo records (96 B) and next-event keys pushed into the peers' "
+                                                 f"memory over NVLink by the step kernels (cudaIpc), one host sync per step, no collective on the data path")
+            else:
+                line["config"]["parallelism"] = f"spatial sharding: {world} column strips, NCCL all-gather of halo slabs (96-B records) + all-gather min"
+                hs, hr = sh.halo_counts()
+                line["halo_records_last_step_rank0"] = {"sent": hs, "received": hr}
+            line["config"]["exchange"] = "direct" if sh.direct else "nccl"
         if not args.no_cpu_baseline:
             n_sample = min(n, args.ref_sample)
             ups, sps, ms, st = oracle_timing(lambda m: make_workload(scenes, args.workload, m, 0, 1), n_sample, 3, 1)

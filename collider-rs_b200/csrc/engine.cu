@@ -611,7 +611,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     const GridGeom g = ctx->geom;
     const uint32_t n_slots = g.n_slots();
     k_step_zero<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(ctx->slots.p), n_slots / 4, ctx->d_ctr,
-                                                                  ctx->sharded ? ctx->send_count.p : nullptr, ctx->work_count.p, kWorkLists);
+                                                                  ctx->sharded ? ctx->send_count.p : nullptr, ctx->work_count.p, kWorkLists, ctx->sharded ? n : 0u);
     ctx->launches += 1;
     if (ctx->collider_dirty && n) {
         CU(cudaMemsetAsync(ctx->collider_dirty, 0, n, ctx->stream));

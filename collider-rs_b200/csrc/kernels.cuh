@@ -54,7 +54,7 @@ struct StepArgs {
     uint32_t* vmap;        // gid -> record index of this step (direct-addressed; null when there are no overlapping pairs)
 };
 
-// Sharded visitor index space: the own records kept for this strip are compacted at rec[0, n_local); the records
+// Sharded visitor index space: the own records sit at their rows rec[0, n_local = n); the records
 // received from rank d sit in rec[recv0 + d * slab + 1 ...] behind that slab's header.
 struct VisSpace {
     uint32_t n_own;  // capacity of the own region (= residents)
@@ -227,13 +227,11 @@ __device__ __forceinline__ HbRec make_rec(const HbCore& h, uint32_t gid) {
 
 template <bool SHARDED>
 __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const ShardGeom sh) {
-    __shared__ uint32_t s_base;
     MinKey best{kKeyMax, kKeyMax};
     unsigned long long n_sol = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x; base < a.n; base += stride) {
         const uint32_t i = base + threadIdx.x;
-        uint32_t keep_local = 0;
         HbRec rec;
         int32_t ex = 0;
         if (i < a.n) {
@@ -277,14 +275,14 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
             const bool binned = h.binned;
             const bool reit = h.reit;
             const double r_time = h.end;
-            if (!SHARDED) {
-                store_rec(a.rec + i, rec);
-            } else if (binned) {
+            // the record stays at its row; a sharded rank bins only the cells inside its own strip (above and in k_scatter)
+            store_rec(a.rec + i, rec);
+            if (SHARDED && a.vmap) a.vmap[gid] = i;
+            if (SHARDED && binned) {
                 // The record is needed by every rank whose strip intersects columns [sx, ex + 1): the extra column keeps
                 // a partner that is within `padding` across a cell line (an overlapping pair whose rects do not
-                // intersect) visible.  Own strip -> compacted into the visitor table; any other strip -> the halo slab.
+                // intersect) visible.  Any strip other than the own one -> the halo slab.
                 const int64_t hi_col = (int64_t)ex + 1;
-                keep_local = ((int64_t)sh.col_hi > (int64_t)rec.sx && (int64_t)sh.col_lo < hi_col) ? 1u : 0u;
                 const bool leaves = (int64_t)rec.sx < (int64_t)sh.col_lo || hi_col > (int64_t)sh.col_hi;
                 if (leaves) {
                     const uint32_t pos = warp_agg_claim32(a.send_count);
@@ -297,21 +295,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const
                 ++n_sol;
                 const MinKey k{time_key(r_time), (uint64_t)gid};
                 if (key_less(k, best)) best = k;
-            }
-        }
-        if (SHARDED) {
-            // block-aggregated append of the records this rank keeps (one global atomic per block-iteration)
-            uint32_t total;
-            const uint32_t off = block_excl_scan(keep_local, &total);
-            if (total) {
-                if (threadIdx.x == 0) s_base = atomicAdd(&a.ctr->n_local, total);
-                __syncthreads();
-                const uint32_t pos = s_base + off;
-                if (keep_local) {
-                    store_rec(a.rec + pos, rec);  // pos < n always
-                    if (a.vmap) a.vmap[rec.gid] = pos;
-                }
-                __syncthreads();
             }
         }
     }
@@ -447,7 +430,7 @@ __global__ void k_reduce_keys(const Mailbox* own, int world, int rank, int parit
 // ---------------------------------------------------------------------------------------------------------
 // Step prologue: one kernel zeroes everything a step accumulates into (slot table, counters, halo count).
 __global__ void __launch_bounds__(kThreads) k_step_zero(uint4* slots4, uint32_t n4, Counters* ctr, uint32_t* send_count, uint32_t* work_count,
-                                                        uint32_t n_work_lists) {
+                                                        uint32_t n_work_lists, uint32_t n_local) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) slots4[i] = z;
     if (blockIdx.x == 0) {
@@ -459,6 +442,7 @@ __global__ void __launch_bounds__(kThreads) k_step_zero(uint4* slots4, uint32_t 
         __syncthreads();
         if (threadIdx.x == 0) {
             ctr->err_slot = ~0ull;
+            ctr->n_local = n_local;  // sharded: the own records occupy rows [0, n) of the visitor table
             if (send_count) *send_count = 0u;
         }
     }
