@@ -233,7 +233,7 @@ def _main(out):
     sampler = ClockSampler(local_rank)
     sampler.start()
     solves = 0
-    entries = cells = events = 0
+    entries = cells = events = work = seps = 0
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -242,6 +242,8 @@ def _main(out):
         entries += res.n_entries
         cells += res.n_cells
         events += res.n_events
+        work += res.n_work_items
+        seps += res.n_separate_solves
     barrier()
     wall = time.perf_counter() - t0
     launches = eng.launch_count() - launches0
@@ -289,20 +291,29 @@ def _main(out):
 
     if rank == 0:
         K = args.steps
-        E, Cc, V, P = entries / K, cells / K, events / K, solves / K
+        E, Cc, V, P, W, Q = entries / K, cells / K, events / K, solves / K, work / K, seps / K
         lw, lh = eng.get_grid()
         n_slots = 1 << (lw + lh)
         # algorithmic bytes per launch of each kernel (DESIGN.md "bytes per unit")
         stage_ms.setdefault("exchange", 0.0)
         alg = {
-            "stage_a": 242.0 * n + 8.0 * E,
+            "pre": 4.0 * n_slots,                              # k_step_zero
+            "stage_a": 246.0 * n + 8.0 * E,
             "scan": 8.0 * n_slots,
-            "scatter": 32.0 * n + 40.0 * E,
-            "candidates": 32.0 * E + 8.0 * P,
-            "solve": 200.0 * P + 16.0 * V,
+            "scatter": 32.0 * n + 16.0 * E,
+            "candidates": 8.0 * E + 16.0 * W,                  # k_enum_pairs
+            "solve": 208.0 * W + 200.0 * Q + 16.0 * V,         # test + solve + events
         }
-        dom = max(alg, key=lambda k: stage_ms[k])
+        kernel_of = {"pre": "k_step_zero", "stage_a": "k_stage_a", "scan": "k_scan_slots", "scatter": "k_scatter", "candidates": "k_enum_pairs",
+                     "solve": "k_solve"}
+        dom = max((k for k in alg if k != "pre"), key=lambda k: stage_ms[k])
         achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
+        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this same command (profiles/)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and args.workload == "c3" and n == 1_000_000:
+            with open(tpath) as f:
+                traffic = json.load(f).get(kernel_of[dom])
         step_bytes = sum(alg.values())
         line = {
             "metric": METRIC, "value": n * world * K / wall_max, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
@@ -317,12 +328,14 @@ def _main(out):
             "pair_solves_per_s": solves_all / wall_max,
             "device_ms_per_step": dev_ms_max,
             "stage_ms": stage_ms,
-            "per_step": {"cell_entries": E, "cells": Cc, "pair_solves": P, "events": V},
+            "per_step": {"cell_entries": E, "cells": Cc, "work_items": W, "pair_solves": P, "events": V},
             "gpu_launches": int(launches),
             "e2e": {"value": n * world * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(16 * n), "d2h_bytes_per_step": int(d2h / K),
                     "ms_per_step": e2e_max / K * 1e3},
-            "roofline": {"bound": "hbm", "kernel": f"k_{dom}", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_kind": peak_kind,
+            "roofline": {"bound": "hbm", "kernel": kernel_of[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": traffic, "peak_kind": peak_kind,
+                         "per_kernel": {kernel_of[k]: {"ms": stage_ms[k], "bytes": alg[k], "frac": alg[k] / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak}
+                                        for k in alg if stage_ms.get(k)},
                          "whole_step": {"bytes": step_bytes, "achieved": step_bytes / (dev_ms_max * 1e-3) / 1e9,
                                         "frac": step_bytes / (dev_ms_max * 1e-3) / 1e9 / hbm_peak}},
             "clocks": sampler.summary(),

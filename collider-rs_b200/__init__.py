@@ -75,6 +75,7 @@ class StepResult(C.Structure):
         ("error_flags", C.c_uint32),
         ("_pad", C.c_uint32),
         ("error_slot", C.c_uint64),
+        ("n_work_items", C.c_uint64),
     ]
 
 

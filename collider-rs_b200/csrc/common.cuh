@@ -183,6 +183,7 @@ struct Counters {
     unsigned long long n_collide;      // collide_time evaluations = work items that passed the candidate test
     unsigned int work_overflow;        // step result: item count of the fullest work sub-list (vs the segment capacity)
     unsigned int pad0;
+    unsigned long long n_work;         // step result: (record, record, slot) work items enumerated
     unsigned long long n_separate;     // separate_time evaluations
     unsigned long long n_pair_events;  // pair events with time < 1e50 (may exceed the buffer capacity -> overflow)
     unsigned long long n_solitaire;    // Reiterate events

@@ -791,6 +791,7 @@ static int fill_result(cb200_ctx* ctx, cb200_step_result* out) {
         out->n_collide_solves = r.ctr.n_collide;
         out->n_separate_solves = r.ctr.n_separate;
         out->n_solitaire = r.ctr.n_solitaire;
+        out->n_work_items = r.ctr.n_work;
         out->n_events = r.ctr.n_pair_events + r.ctr.n_solitaire;
         out->error_flags = r.ctr.err_flags;
         out->error_slot = 0;

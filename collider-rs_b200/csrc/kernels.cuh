@@ -1079,7 +1079,11 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
         Counters out;
         out.n_entries = c->n_entries; out.n_cells = c->n_cells; out.n_separate = c->n_separate;
         out.work_overflow = 0;
-        for (int l = 0; l < kWorkLists; ++l) out.work_overflow = max(out.work_overflow, a.work.count[l]);  // fullest sub-list
+        out.n_work = 0;
+        for (int l = 0; l < kWorkLists; ++l) {
+            out.work_overflow = max(out.work_overflow, a.work.count[l]);  // fullest sub-list
+            out.n_work += a.work.count[l];
+        }
         out.pad0 = 0;
         out.n_collide = c->n_collide;
         out.n_pair_events = c->n_pair_events; out.n_solitaire = c->n_solitaire; out.err_slot = c->err_slot;

@@ -121,6 +121,7 @@ typedef struct cb200_step_result {
     uint32_t error_flags;   /* CB200_F_* */
     uint32_t _pad;
     uint64_t error_slot;    /* lowest-numbered reporting slot's id, when error_flags != 0 */
+    uint64_t n_work_items;  /* W: (hitbox, hitbox) pairs of one slot run enumerated for the candidate test (>= n_collide_solves) */
 } cb200_step_result;
 
 /* Collider::new (collider.rs:59-69): requires cell_width > padding > 0 (else CB200_E_ARG with the

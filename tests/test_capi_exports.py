@@ -39,7 +39,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_layouts_match_header(lib):
     cb, _ = lib
     assert ctypes.sizeof(cb.Event) == 32
-    assert ctypes.sizeof(cb.StepResult) == 8 + 32 + 7 * 8 + 8 + 8
+    assert ctypes.sizeof(cb.StepResult) == 8 + 32 + 7 * 8 + 8 + 8 + 8
     assert ctypes.sizeof(cb.StateView) == 16 * 8
     assert ctypes.sizeof(cb.VelView) == 5 * 8
 
