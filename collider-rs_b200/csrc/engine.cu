@@ -715,6 +715,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     sv.vmap = ctx->sharded ? (use_map ? ctx->vmap.p : nullptr) : ctx->row_of.p;
     sv.id_space = ctx->sharded ? (uint32_t)ctx->id_space : ctx->n;
     sv.sharded = ctx->sharded ? 1 : 0;
+    sv.ids = ctx->sharded ? nullptr : ctx->ids.p;
     sv.vs = vs;
     sv.col_lo = sh.col_lo;
     sv.col_hi = sh.col_hi;
@@ -768,22 +769,9 @@ static int fill_result(cb200_ctx* ctx, cb200_step_result* out) {
         out->next_time = r.next_time;
         out->next_event.time = r.next_time;
         if (r.next_tie != kKeyMax) {
-            const uint32_t hi = (uint32_t)((r.next_tie >> 32) & 0x7fffffffu), lo = (uint32_t)(r.next_tie & 0x7fffffffu);
-            if (r.next_tie & kPairClass) {
-                out->next_event.kind = (r.next_tie & kCollideBit) ? CB200_EV_COLLIDE : CB200_EV_SEPARATE;
-                if (ctx->sharded) {
-                    out->next_event.a = hi;
-                    out->next_event.b = lo;
-                } else {
-                    CU(cudaMemcpyAsync(&out->next_event.a, ctx->ids.p + hi, 8, cudaMemcpyDeviceToHost, ctx->stream));
-                    CU(cudaMemcpyAsync(&out->next_event.b, ctx->ids.p + lo, 8, cudaMemcpyDeviceToHost, ctx->stream));
-                }
-            } else {
-                out->next_event.kind = CB200_EV_REITERATE;
-                if (ctx->sharded) out->next_event.a = (uint32_t)r.next_tie;
-                else CU(cudaMemcpyAsync(&out->next_event.a, ctx->ids.p + (uint32_t)r.next_tie, 8, cudaMemcpyDeviceToHost, ctx->stream));
-            }
-            if (!ctx->sharded) CU(cudaStreamSynchronize(ctx->stream));
+            out->next_event.kind = !(r.next_tie & kPairClass) ? CB200_EV_REITERATE : ((r.next_tie & kCollideBit) ? CB200_EV_COLLIDE : CB200_EV_SEPARATE);
+            out->next_event.a = r.next_id_a;  // (resolved label -> id by the last block of k_solve)
+            out->next_event.b = r.next_id_b;
         }
         out->n_hitboxes = n;
         out->n_entries = r.ctr.n_entries;

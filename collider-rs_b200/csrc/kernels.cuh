@@ -225,8 +225,11 @@ __device__ __forceinline__ HbRec make_rec(const HbCore& h, uint32_t gid) {
     return rec;
 }
 
+#ifndef CB200_LB_A
+#define CB200_LB_A 4
+#endif
 template <bool SHARDED>
-__global__ void __launch_bounds__(kThreads, 4) k_stage_a(const StepArgs a, const ShardGeom sh) {
+__global__ void __launch_bounds__(kThreads, CB200_LB_A) k_stage_a(const StepArgs a, const ShardGeom sh) {
     MinKey best{kKeyMax, kKeyMax};
     unsigned long long n_sol = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -688,11 +691,12 @@ __global__ void k_overlap_map_ids(const uint64_t* __restrict__ ids, uint32_t n, 
 // first: each spent 22-33 M warp instructions per step with most lanes idle or waiting — profiles/r1c…r1g.)
 // A block takes kEnumTile consecutive entries per round, one chunk of kEnumChunk per warp, 32 entries per step:
 //   rank in run   one ballot of the run heads; a run that began before the step continues through `last_rank`
-//   k-th predecessor   k lanes down (shuffle), in the previous step's registers, or (long runs) in global memory
-//   output        two passes over the registers: count the items per kind pair, reserve the block's ranges with ONE atomic
-//                 per kind pair and round (on one of kSubLists sub-lists: same-address atomics serialise at ~2 ns each in
-//                 L2, and a warp that appended through its own atomics spent 45 % of its time waiting for them,
-//                 profiles/r1g_enum_solve.txt), then write the items in place — no staging, no per-warp atomics
+//   item counts   the kind of the k-th predecessor is a bit of the kind ballots, so a lane's items per kind pair are two
+//                 popcounts per entry; one warp scan per kind pair gives every lane its own output range
+//   output        the block reserves its ranges with ONE atomic per kind pair and round (on one of kSubLists sub-lists:
+//                 same-address atomics serialise at ~2 ns each in L2, and a warp that appended through its own atomics
+//                 spent 45 % of its time waiting for them, profiles/r1g_enum_solve.txt); each lane then writes its items
+//                 in place, reading the predecessors' 8-byte entries back from L1 — no staging, no per-warp atomics
 constexpr int kEnumChunk = 128;                  // entries per warp and round
 constexpr int kEnumSteps = kEnumChunk / 32;
 constexpr int kEnumTile = kEnumChunk * (kThreads / 32);  // entries per block and round
@@ -714,51 +718,16 @@ struct EnumArgs {
     Counters* ctr;
 };
 
-// One round of one warp: ranks of its kEnumChunk entries, then either the number of work items per kind pair (COUNT) or
-// the items themselves, written at out[l] + (items of kind pair l before this lane's).
-struct EnumRound {
-    uint2 ent[kEnumSteps];      // (key, vidx) of this lane's entries
-    uint32_t rank[kEnumSteps];
-    unsigned rects[kEnumSteps + 1];  // [0]: the halo's kind ballot
-    uint32_t halo_vidx;
-};
-template <bool COUNT>
-__device__ __forceinline__ void enum_emit(const EnumRound& r, const uint2* __restrict__ ent, uint32_t c0, int lane, uint32_t* cnt, WorkItem* const* out) {
-#pragma unroll
-    for (int s = 0; s < kEnumSteps; ++s) {
-        const uint32_t max_rank = __reduce_max_sync(0xffffffffu, r.rank[s]);
-        const uint32_t my_rect = r.ent[s].x >> 31, slot = r.ent[s].x & kSlotMask;
-        const uint32_t prev_vidx = s ? r.ent[s ? s - 1 : 0].y : r.halo_vidx;
-        const uint32_t e = c0 + (uint32_t)s * 32 + lane;
-        for (uint32_t k = 1; k <= max_rank; ++k) {
-            const bool active = r.rank[s] >= k;
-            const int src = lane - (int)k;
-            uint32_t pred_rect = 0, pred_vidx = 0;
-            if (!COUNT) {
-                if (k <= 31) pred_vidx = __shfl_sync(0xffffffffu, r.ent[s].y, src & 31);
-                if (k <= 63) {  // (src & 31 == 32 + src for src in [-32, -1])
-                    const uint32_t pv = __shfl_sync(0xffffffffu, prev_vidx, src & 31);
-                    if (src < 0) pred_vidx = pv;
-                }
-            }
-            if (src >= 0) pred_rect = (r.rects[s + 1] >> src) & 1u;
-            else if (src >= -32) pred_rect = (r.rects[s] >> (32 + src)) & 1u;
-            else if (active) {  // a run longer than the previous step: global memory
-                const uint2 far = __ldg(ent + (e - k));
-                pred_rect = far.x >> 31;
-                pred_vidx = far.y;
-            }
-            const uint32_t n_rect = my_rect + pred_rect;
-            const uint32_t pair = n_rect == 2 ? 0u : (n_rect == 0 ? 1u : 2u);
-#pragma unroll
-            for (int l = 0; l < 3; ++l) {
-                const unsigned mask = __ballot_sync(0xffffffffu, active && pair == (uint32_t)l);
-                if (!COUNT && active && pair == (uint32_t)l && out[l])
-                    *reinterpret_cast<uint4*>(out[l] + cnt[l] + __popc(mask & ((1u << lane) - 1u))) = make_uint4(r.ent[s].y, pred_vidx, slot, 0u);
-                cnt[l] += __popc(mask);
-            }
-        }
-    }
+// Work items of one lane: for each of its entries, the `rank` entries before it.  The kind of a predecessor is a bit of the
+// window (previous step's kind ballot, this step's), so the per-list COUNTS are two popcounts per entry; the items
+// themselves are written by a lane-private loop that reads the predecessor's 8-byte entry back from L1.
+__device__ __forceinline__ uint32_t rect_preds(unsigned prev_rects, unsigned rects, int lane, uint32_t rank) {
+    // predecessors k = 1..min(rank, 32 + lane) sit at window bits [32 + lane - k]; window = prev_rects | rects << 32
+    const unsigned long long window = (unsigned long long)prev_rects | ((unsigned long long)rects << 32);
+    const uint32_t in_window = min(rank, 32u + (uint32_t)lane);
+    const unsigned long long below_me = (1ull << (32 + lane)) - 1ull;                         // bits under this lane's
+    const unsigned long long from = in_window >= 64u ? 0ull : ~((1ull << (32 + lane - in_window)) - 1ull);
+    return (uint32_t)__popcll(window & below_me & from);
 }
 
 __global__ void __launch_bounds__(kThreads) k_enum_pairs(const EnumArgs a) {
@@ -771,15 +740,14 @@ __global__ void __launch_bounds__(kThreads) k_enum_pairs(const EnumArgs a) {
     for (uint32_t t0 = blockIdx.x * kEnumTile; t0 < n_entries; t0 += gridDim.x * kEnumTile) {
         const uint32_t c0 = t0 + (uint32_t)warp * kEnumChunk;
         const uint32_t c1 = min(c0 + (uint32_t)kEnumChunk, n_entries);  // (c1 <= c0: this warp has nothing)
-        EnumRound r;
         // all loads of the round first: the chunk and the 32 entries before it
+        uint2 ent_s[kEnumSteps];
 #pragma unroll
-        for (int s = 0; s < kEnumSteps; ++s) r.ent[s] = c0 + s * 32 + lane < c1 ? __ldg(ent + c0 + s * 32 + lane) : make_uint2(0u, 0u);
+        for (int s = 0; s < kEnumSteps; ++s) ent_s[s] = c0 + s * 32 + lane < c1 ? __ldg(ent + c0 + s * 32 + lane) : make_uint2(0u, 0u);
         const bool halo_live = c0 < c1 && c0 + lane >= 32;
         const uint2 halo = halo_live ? __ldg(ent + (c0 - 32 + lane)) : make_uint2(0u, 0u);
-        r.halo_vidx = halo.y;
         const uint32_t halo_slot = halo_live ? (halo.x & kSlotMask) : kNoSlot;
-        r.rects[0] = __ballot_sync(0xffffffffu, halo_live && (halo.x & kEntryKindBit));
+        unsigned prev_rects = __ballot_sync(0xffffffffu, halo_live && (halo.x & kEntryKindBit));
         // rank of the last halo entry in its run
         uint32_t last_slot = __shfl_sync(0xffffffffu, halo_slot, 31), last_rank = 0;
         if (last_slot != kNoSlot) {
@@ -794,23 +762,46 @@ __global__ void __launch_bounds__(kThreads) k_enum_pairs(const EnumArgs a) {
                 }
             }
         }
+        // ranks, and per-lane item counts per kind pair: [0] rect/rect, [1] circle/circle, [2] mixed
+        uint32_t rank[kEnumSteps], cnt[3] = {0u, 0u, 0u};
 #pragma unroll
         for (int s = 0; s < kEnumSteps; ++s) {
             const bool live = c0 + s * 32 + lane < c1;
-            const uint32_t slot = live ? (r.ent[s].x & kSlotMask) : kNoSlot;
+            const uint32_t slot = live ? (ent_s[s].x & kSlotMask) : kNoSlot;
             uint32_t slot_up = __shfl_up_sync(0xffffffffu, slot, 1);
             if (lane == 0) slot_up = last_slot;
             const unsigned heads = __ballot_sync(0xffffffffu, live && slot != slot_up);
-            r.rects[s + 1] = __ballot_sync(0xffffffffu, live && (r.ent[s].x & kEntryKindBit));
+            const unsigned rects = __ballot_sync(0xffffffffu, live && (ent_s[s].x & kEntryKindBit));
             const unsigned below = heads & (0xffffffffu >> (31 - lane));  // heads at or below this lane
-            r.rank[s] = !live ? 0u : (below ? (uint32_t)(lane - (31 - __clz(below))) : (uint32_t)lane + last_rank + 1u);
+            rank[s] = !live ? 0u : (below ? (uint32_t)(lane - (31 - __clz(below))) : (uint32_t)lane + last_rank + 1u);
+            uint32_t n_rect = rect_preds(prev_rects, rects, lane, rank[s]);
+            for (uint32_t k = 33u + (uint32_t)lane; k <= rank[s]; ++k)  // a run longer than the window: global memory
+                n_rect += __ldg(ent + (c0 + s * 32 + lane - k)).x >> 31;
+            if (ent_s[s].x >> 31) {
+                cnt[0] += n_rect;
+                cnt[2] += rank[s] - n_rect;
+            } else {
+                cnt[2] += n_rect;
+                cnt[1] += rank[s] - n_rect;
+            }
+            prev_rects = rects;
             last_slot = __shfl_sync(0xffffffffu, slot, 31);
-            last_rank = __shfl_sync(0xffffffffu, r.rank[s], 31);
+            last_rank = __shfl_sync(0xffffffffu, rank[s], 31);
         }
-        // phase 1: how many items per kind pair; the block reserves its ranges with one atomic per kind pair
-        uint32_t cnt[3] = {0u, 0u, 0u};
-        enum_emit<true>(r, ent, c0, lane, cnt, nullptr);
-        if (lane < 3) s_cnt[warp][lane] = cnt[lane];
+        // the block reserves its ranges with one atomic per kind pair; lanes get disjoint sub-ranges by a warp scan
+        uint32_t lane_off[3], warp_tot[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            uint32_t inc = cnt[l];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            lane_off[l] = inc - cnt[l];
+            warp_tot[l] = __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane < 3) s_cnt[warp][lane] = lane == 0 ? warp_tot[0] : (lane == 1 ? warp_tot[1] : warp_tot[2]);
         __syncthreads();
         if (threadIdx.x < 3) {
             uint32_t run = 0;
@@ -821,17 +812,31 @@ __global__ void __launch_bounds__(kThreads) k_enum_pairs(const EnumArgs a) {
             s_base[threadIdx.x] = run ? atomicAdd(&a.work.count[threadIdx.x * kSubLists + sub], run) : 0u;
         }
         __syncthreads();
-        // phase 2: write the items
-        WorkItem* out[3];
-        uint32_t room[3];
+        uint32_t pos[3];
+        bool room = true;  // a range that does not fit its segment is dropped: the step is re-run with a larger buffer
 #pragma unroll
         for (int l = 0; l < 3; ++l) {
             const uint32_t at = s_base[l] + s_off[warp][l];
-            room[l] = at + cnt[l] <= a.work.seg_cap ? 1u : 0u;  // a range that does not fit is dropped: the step is re-run with a larger buffer
-            out[l] = room[l] ? a.work.items + (size_t)(l * kSubLists + sub) * a.work.seg_cap + at : nullptr;
+            room = room && at + warp_tot[l] <= a.work.seg_cap;
+            pos[l] = at + lane_off[l];
         }
-        uint32_t done[3] = {0u, 0u, 0u};
-        enum_emit<false>(r, ent, c0, lane, done, out);
+        if (room) {
+            uint4* const out0 = reinterpret_cast<uint4*>(a.work.items + (size_t)(0 * kSubLists + sub) * a.work.seg_cap);
+            uint4* const out1 = reinterpret_cast<uint4*>(a.work.items + (size_t)(1 * kSubLists + sub) * a.work.seg_cap);
+            uint4* const out2 = reinterpret_cast<uint4*>(a.work.items + (size_t)(2 * kSubLists + sub) * a.work.seg_cap);
+#pragma unroll
+            for (int s = 0; s < kEnumSteps; ++s) {
+                const uint32_t e = c0 + s * 32 + lane, my_rect = ent_s[s].x >> 31, slot = ent_s[s].x & kSlotMask;
+                for (uint32_t k = 1; k <= rank[s]; ++k) {
+                    const uint2 pred = __ldg(ent + (e - k));
+                    const uint4 item = make_uint4(ent_s[s].y, pred.y, slot, 0u);
+                    const uint32_t n_rect = my_rect + (pred.x >> 31);
+                    if (n_rect == 2) out0[pos[0]++] = item;
+                    else if (n_rect == 0) out1[pos[1]++] = item;
+                    else out2[pos[2]++] = item;
+                }
+            }
+        }
         __syncthreads();  // s_cnt / s_off / s_base are rewritten by the next round
     }
 }
@@ -921,6 +926,7 @@ __global__ void __launch_bounds__(kThreads) k_list_candidates(const CandArgs a, 
 struct StepResultDev {
     double next_time;
     uint64_t next_tie;  // MinKey.tie of the minimum (kKeyMax if none)
+    uint64_t next_id_a, next_id_b;  // its HbIds (label -> id), so the host needs no further copy
     Counters ctr;
 };
 
@@ -944,6 +950,7 @@ struct SolveArgs {
     int sharded;
     VisSpace vs;
     int32_t col_lo, col_hi;
+    const uint64_t* ids;     // label -> HbId (null: the label is the id)
 };
 
 // A map entry is trusted only if it names a record slot that is live in THIS step and that record carries the gid.
@@ -1074,6 +1081,13 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
     if (threadIdx.x == 0) {
         a.result->next_time = (best.t == kKeyMax && best.tie == kKeyMax) ? cb_inf() : key_time(best.t);
         a.result->next_tie = best.tie;
+        {
+            const bool pair = (best.tie & kPairClass) != 0;
+            const uint32_t la = pair ? (uint32_t)((best.tie >> 32) & 0x7fffffffu) : (uint32_t)best.tie, lb = (uint32_t)(best.tie & 0x7fffffffu);
+            const bool any = !(best.t == kKeyMax && best.tie == kKeyMax);
+            a.result->next_id_a = !any ? 0ull : (a.ids ? a.ids[la] : (uint64_t)la);
+            a.result->next_id_b = !any || !pair ? 0ull : (a.ids ? a.ids[lb] : (uint64_t)lb);
+        }
         if (a.local_key) *a.local_key = best;
         const volatile Counters* c = a.ctr;
         Counters out;
