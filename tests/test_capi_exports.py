@@ -77,3 +77,13 @@ def test_create_fails_loudly_without_a_gpu(lib):
     with pytest.raises(cb.ColliderError) as e:
         cb.Engine(1.0, 2.0)
     assert "cell_width > padding" in e.value.msg
+
+
+def test_cpp_wrapper_compiles_and_links(lib, tmp_path):
+    """The header-only C++ `Collider<P>` (include/collider_b200.hpp) and its test program build against the library."""
+    cb, _ = lib
+    libdir = os.path.dirname(cb.LIB_PATH)
+    exe = str(tmp_path / "host_collider_check")
+    res = subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "host_collider_check.cpp"), "-L" + libdir,
+                          "-lcollider_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr

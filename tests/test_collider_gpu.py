@@ -6,6 +6,8 @@ Collider.  Part 2 drives the device Collider and the CPU oracle in lockstep with
 and requires every return value to be equal: event tuples in order, times and get_hitbox results bit-for-bit.
 """
 import importlib
+import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -421,3 +423,29 @@ def test_bulk_steps_with_events_between_lockstep(oracle):
         readme_loop(c, T_next, react)
         T = T_next
     assert c.events > 50
+
+
+def test_config1_full_size_lockstep(oracle):
+    """BASELINE config 1 as stated: 1,000 mixed circles/squares in a 200x200 box, cell 4, padding 0.01, random velocities,
+    the README loop with velocity halving on Collide — oracle and device in lockstep, every event and time compared."""
+    s = scenes.c1(1000)
+    c = Lockstep(oracle, scenes.CELL_WIDTH, scenes.PADDING)
+    for id, hb in scene_hitboxes(oracle, s):
+        c.add_hitbox(id, hb)
+    readme_loop(c, 100.0, halve(c))
+    assert c.events > 300
+    for i in range(0, 1000, 97):
+        c.get_hitbox(i)
+        c.get_overlaps(i)
+
+
+def test_cpp_wrapper_runs_the_reference_tests(tmp_path):
+    """include/collider_b200.hpp (the C++ twin of the Rust `Collider<P>` wrapper) + tests/host_collider_check.cpp:
+    test_smoke, test_separate_initial_overlap and the lib.rs doctest of the reference, compiled with g++ against the .so."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(cb.LIB_PATH)
+    exe = str(tmp_path / "host_collider_check")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(root, "tests", "host_collider_check.cpp"), "-L" + libdir, "-lcollider_b200",
+                    "-Wl,-rpath," + libdir], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "host_collider_check ok" in out.stdout, out.stdout + out.stderr
