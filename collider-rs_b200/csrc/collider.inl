@@ -111,6 +111,7 @@ TableView table_of(cb200_collider* c) {
     t.label = x->label.p;
     t.row_of = x->row_of.p;
     t.rec = x->rec.p;
+    t.bink = x->bink.p;
     t.dirty = c->dirty.p;
     t.dirty_list = c->dirty_list.p;
     t.dirty_count = c->d_dirty_count;
@@ -129,7 +130,7 @@ int ensure_capacity(cb200_collider* c, size_t rows, size_t labels) {
     const size_t old_rows = c->dirty.cap, old_labels = x->row_of.cap;
     for (auto& b : x->col) CCU(b.reserve(rows, true, st));
     CCU(x->kind.reserve(rows, true, st)); CCU(x->reit.reserve(rows, true, st)); CCU(x->group.reserve(rows, true, st));
-    CCU(x->mask.reserve(rows, true, st)); CCU(x->label.reserve(rows, true, st)); CCU(x->rec.reserve(rows, true, st));
+    CCU(x->mask.reserve(rows, true, st)); CCU(x->label.reserve(rows, true, st)); CCU(x->rec.reserve(rows, true, st)); CCU(x->bink.reserve(rows, true, st));
     CCU(c->dirty.reserve(rows, true, st)); CCU(c->dirty_list.reserve(rows, true, st));
     if (c->dirty.cap > old_rows) CCU(cudaMemsetAsync(c->dirty.p + old_rows, 0, c->dirty.cap - old_rows, st));
     CCU(x->row_of.reserve(labels, true, st));
@@ -170,7 +171,7 @@ int rebin(cb200_collider* c) {
         const VisSpace vs{n, 0, 1, 0};
         const uint32_t cap_e = (uint32_t)std::min<size_t>(x->entries.cap, 0xffffffffu);
         const uint32_t grid_v = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, x->sm_count * 8));
-        if (n) k_scatter<false><<<grid_v, kThreads, 0, x->stream>>>(n, x->rec.p, vs, x->slots.p, x->entries.p, cap_e, x->geom, INT32_MIN, INT32_MAX, x->d_ctr);
+        if (n) k_scatter<false><<<grid_v, kThreads, 0, x->stream>>>(n, x->rec.p, x->bink.p, vs, x->slots.p, x->entries.p, cap_e, x->geom, INT32_MIN, INT32_MAX, x->d_ctr);
         x->launches += 3;
         Counters h;
         CCU(cudaMemcpyAsync(&h, x->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, x->stream));

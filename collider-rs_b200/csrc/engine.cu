@@ -68,6 +68,7 @@ struct cb200_ctx {
     DevBuf<uint32_t> group, mask;
     DevBuf<uint64_t> ids;
     DevBuf<HbRec> rec;       // one device: rec[row]; sharded: the visitor table (own records, then received ones)
+    DevBuf<int4> bink;       // (sx, sy, span, kgb) per record
     // table order (kernels.cuh "Table order"): label[row] = HbId rank (sharded: the id), ord[row] = index in the caller's
     // arrays (one device: the same buffer as label), row_of[label] = row (one device only)
     DevBuf<uint32_t> label, ord, row_of;
@@ -294,7 +295,7 @@ void cb200_destroy(cb200_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& b : c->col) b.release();
     for (auto& b : c->nvel) b.release();
-    c->kind.release(); c->reit.release(); c->group.release(); c->mask.release(); c->ids.release(); c->rec.release();
+    c->kind.release(); c->reit.release(); c->group.release(); c->mask.release(); c->ids.release(); c->rec.release(); c->bink.release();
     c->label.release(); c->ord.release(); c->row_of.release(); c->send.release(); c->send_count.release(); c->vmap.release();
     for (auto& b : c->col_alt) b.release();
     c->kind_alt.release(); c->reit_alt.release(); c->group_alt.release(); c->mask_alt.release(); c->label_alt.release(); c->ord_alt.release();
@@ -373,7 +374,7 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
         if (n) CU(cudaMemcpyAsync(ctx->col[k].p, src[k], n * 8, cudaMemcpyHostToDevice, ctx->stream));
     }
     CU(ctx->kind.reserve(cap)); CU(ctx->reit.reserve(cap)); CU(ctx->group.reserve(cap)); CU(ctx->mask.reserve(cap));
-    CU(ctx->ids.reserve(cap)); CU(ctx->rec.reserve(cap));
+    CU(ctx->ids.reserve(cap)); CU(ctx->rec.reserve(cap)); CU(ctx->bink.reserve(cap));
     if (n) {
         CU(cudaMemcpyAsync(ctx->kind.p, v->kind, n, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->group.p, v->group, n * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -398,6 +399,7 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
         if (ctx->slab == 0) ctx->slab = (uint32_t)std::max<size_t>(n / 256, 2047) + 1;
         // (two receive areas: the direct exchange double-buffers them by step parity)
         CU(ctx->rec.reserve(n + 2 * (size_t)ctx->slab * ctx->shard.world));
+        CU(ctx->bink.reserve(n + 2 * (size_t)ctx->slab * ctx->shard.world));
         ctx->p2p = false;  // peers must be re-imported: the receive area moved
         CU(ctx->send.reserve(ctx->slab));
         CU(ctx->send_count.reserve(1));
@@ -632,6 +634,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     a.label = ctx->label.p;
     a.ord = ctx->sharded ? ctx->ord.p : ctx->label.p;
     a.rec = ctx->rec.p;
+    a.bink = ctx->bink.p;
     a.slot_count = ctx->slots.p;
     a.geom = g;
     a.ctr = ctx->d_ctr;
@@ -670,8 +673,8 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
         const uint32_t work = recount ? n_vis_max : ctx->slab * (uint32_t)sh.world;
         const uint32_t grid_i = std::max<uint32_t>(1, std::min<uint32_t>((work + kThreads - 1) / kThreads, ctx->sm_count * 8));
         uint32_t* vmap = use_map ? ctx->vmap.p : nullptr;
-        if (recount) k_index_visitors<true><<<grid_i, kThreads, 0, ctx->stream>>>(ctx->rec.p, vs, ctx->d_ctr, ctx->slots.p, g, sh.col_lo, sh.col_hi, vmap);
-        else k_index_visitors<false><<<grid_i, kThreads, 0, ctx->stream>>>(ctx->rec.p, vs, ctx->d_ctr, ctx->slots.p, g, sh.col_lo, sh.col_hi, vmap);
+        if (recount) k_index_visitors<true><<<grid_i, kThreads, 0, ctx->stream>>>(ctx->rec.p, ctx->bink.p, vs, ctx->d_ctr, ctx->slots.p, g, sh.col_lo, sh.col_hi, vmap);
+        else k_index_visitors<false><<<grid_i, kThreads, 0, ctx->stream>>>(ctx->rec.p, ctx->bink.p, vs, ctx->d_ctr, ctx->slots.p, g, sh.col_lo, sh.col_hi, vmap);
         ctx->launches += 1;
     }
     {
@@ -681,8 +684,8 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_SCATTER], ctx->stream));
     if (n_vis_max) {
         const uint32_t cap_e = (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu);
-        if (ctx->sharded) k_scatter<true><<<grid_v, kThreads, 0, ctx->stream>>>(ctx->n, ctx->rec.p, vs, ctx->slots.p, ctx->entries.p, cap_e, g, sh.col_lo, sh.col_hi, ctx->d_ctr);
-        else k_scatter<false><<<grid_v, kThreads, 0, ctx->stream>>>(ctx->n, ctx->rec.p, vs, ctx->slots.p, ctx->entries.p, cap_e, g, sh.col_lo, sh.col_hi, ctx->d_ctr);
+        if (ctx->sharded) k_scatter<true><<<grid_v, kThreads, 0, ctx->stream>>>(ctx->n, ctx->rec.p, ctx->bink.p, vs, ctx->slots.p, ctx->entries.p, cap_e, g, sh.col_lo, sh.col_hi, ctx->d_ctr);
+        else k_scatter<false><<<grid_v, kThreads, 0, ctx->stream>>>(ctx->n, ctx->rec.p, ctx->bink.p, vs, ctx->slots.p, ctx->entries.p, cap_e, g, sh.col_lo, sh.col_hi, ctx->d_ctr);
         ctx->launches += 1;
     }
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_CAND], ctx->stream));

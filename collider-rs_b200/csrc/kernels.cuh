@@ -41,7 +41,8 @@ struct StepArgs {
     const double *nvx, *nvy, *nrw, *nrh, *nend;  // optional new velocity columns (device), null = keep
     const uint32_t* label; // label[row]: rank of the row's HbId in ascending-id order (sharded: the id itself)
     const uint32_t* ord;   // ord[row]: index of the row's hitbox in the caller's (upload-order) arrays; one device: == label
-    HbRec* rec;            // one device: rec[i].  Sharded: the visitor table, own records appended at [0, n_local)
+    HbRec* rec;            // one device: rec[i].  Sharded: the visitor table, own records at [0, n), received ones behind
+    int4* bink;            // bink[i] = (sx, sy, span, kgb) of rec[i]: all the scatter needs, 16 B instead of a 96-B record
     uint32_t* slot_count;  // one device only (the count is fused here)
     GridGeom geom;
     Counters* ctr;
@@ -280,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_A) k_stage_a(const StepArgs
             const double r_time = h.end;
             // the record stays at its row; a sharded rank bins only the cells inside its own strip (above and in k_scatter)
             store_rec(a.rec + i, rec);
+            a.bink[i] = make_int4(rec.sx, rec.sy, (int)rec.span, (int)rec.kgb);
             if (SHARDED && a.vmap) a.vmap[gid] = i;
             if (SHARDED && binned) {
                 // The record is needed by every rank whose strip intersects columns [sx, ex + 1): the extra column keeps
@@ -318,7 +320,7 @@ __global__ void k_slab_header(HbRec* send, const uint32_t* __restrict__ send_cou
 // COUNT_OWN re-counts them too — used when a step is re-run after a buffer grew), and index them by gid for the
 // overlapping-pair lookups.
 template <bool COUNT_OWN>
-__global__ void __launch_bounds__(kThreads) k_index_visitors(const HbRec* __restrict__ rec, VisSpace vs, const Counters* ctr, uint32_t* slot_count,
+__global__ void __launch_bounds__(kThreads) k_index_visitors(const HbRec* __restrict__ rec, int4* bink, VisSpace vs, const Counters* ctr, uint32_t* slot_count,
                                                              GridGeom geom, int32_t col_lo, int32_t col_hi, uint32_t* vmap) {
     const uint32_t n_local = ctr->n_local;
     const uint32_t total = n_local + (uint32_t)vs.world * vs.slab;
@@ -328,6 +330,7 @@ __global__ void __launch_bounds__(kThreads) k_index_visitors(const HbRec* __rest
         uint32_t v;
         if (!vis_record(rec, vs, n_local, i, &v)) continue;
         const RecHead h = load_head(rec, v);
+        if (i >= n_local) bink[v] = make_int4(h.sx, h.sy, (int)((uint32_t)(h.ex - h.sx) | ((uint32_t)(h.ey - h.sy) << 16)), (int)h.kgb);
         if (!(h.kgb & 2u)) continue;
         const int32_t x0 = max(h.sx, col_lo), x1 = min(h.ex, col_hi);
         for (int32_t x = x0; x < x1; ++x)
@@ -589,20 +592,22 @@ constexpr uint32_t kSlotMask = (1u << 26) - 1u;
 constexpr uint32_t kEntryKindBit = 0x80000000u;  // key bit 31: the hitbox is a rect
 
 template <bool SHARDED>
-__global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const HbRec* __restrict__ rec, VisSpace vs, uint32_t* offsets, CellEntry* entries,
-                                                      uint32_t cap_entries, GridGeom geom, int32_t col_lo, int32_t col_hi, Counters* ctr) {
+__global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const HbRec* __restrict__ rec, const int4* __restrict__ bink, VisSpace vs, uint32_t* offsets,
+                                                      CellEntry* entries, uint32_t cap_entries, GridGeom geom, int32_t col_lo, int32_t col_hi, Counters* ctr) {
     const uint32_t n_local = SHARDED ? ctr->n_local : n;
     const uint32_t total = SHARDED ? n_local + (uint32_t)vs.world * vs.slab : n;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += stride) {
         uint32_t i = j;
         if (SHARDED && !vis_record(rec, vs, n_local, j, &i)) continue;
-        const RecHead h = load_head(rec, i);
-        if (!(h.kgb & 2u)) continue;
-        const uint32_t group = ((h.kgb >> 8) & 0x1fu) | ((h.kgb & 1u) << 5);  // bit 5 -> key bit 31: the hitbox is a rect
-        const int32_t x0 = max(h.sx, col_lo), x1 = min(h.ex, col_hi);
+        const int4 b = __ldg(bink + i);  // (sx, sy, span, kgb)
+        const uint32_t kgb = (uint32_t)b.w;
+        if (!(kgb & 2u)) continue;
+        const uint32_t group = ((kgb >> 8) & 0x1fu) | ((kgb & 1u) << 5);  // bit 5 -> key bit 31: the hitbox is a rect
+        const int32_t sy = b.y, ex = b.x + (int32_t)((uint32_t)b.z & 0xffffu), ey = b.y + (int32_t)((uint32_t)b.z >> 16);
+        const int32_t x0 = max(b.x, col_lo), x1 = min(ex, col_hi);
         for (int32_t x = x0; x < x1; ++x)
-            for (int32_t y = h.sy; y != h.ey; ++y) {
+            for (int32_t y = sy; y != ey; ++y) {
                 const uint32_t s = geom.slot(x, y);
                 const uint32_t pos = atomicAdd(&offsets[s], 1u);
                 if (pos < cap_entries) *reinterpret_cast<uint2*>(entries + pos) = make_uint2(s | (group << 26), i);

@@ -53,6 +53,7 @@ struct TableView {
     uint32_t* label;
     uint32_t* row_of;  // label -> row
     HbRec* rec;
+    int4* bink;             // (sx, sy, span, kgb) of every record (the scatter's input)
     uint8_t* dirty;         // row is in dirty_list
     uint32_t* dirty_list;
     uint32_t* dirty_count;
@@ -195,7 +196,9 @@ __global__ void __launch_bounds__(kThreads) k_update_one(const OneArgs a) {
                         t.label[row] = a.label;
                         t.row_of[a.label] = row;
                     }
-                    store_rec(t.rec + row, make_rec(h, a.label));
+                    const HbRec nr = make_rec(h, a.label);
+                    store_rec(t.rec + row, nr);
+                    t.bink[row] = make_int4(nr.sx, nr.sy, (int)nr.span, (int)nr.kgb);
                     mark_dirty(t, row);
                 }
             }
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) k_update_one(const OneArgs a) {
         }
         return;
     }
-    const TableView tv{t.s, t.label, t.row_of, t.rec, t.dirty, t.dirty_list, t.dirty_count, t.n + (a.op == kOpAdd ? 1u : 0u)};
+    const TableView tv{t.s, t.label, t.row_of, t.rec, t.bink, t.dirty, t.dirty_list, t.dirty_count, t.n + (a.op == kOpAdd ? 1u : 0u)};
     if (self.binned) {  // collider.rs:328: only hitboxes with a group are tracked
         const DurHb me = self.d;
         // Separate events for the current overlaps (collider.rs:329-339)
@@ -403,6 +406,7 @@ __global__ void k_remove_row(TableView t, uint32_t label, OneHeader* head) {
         const int4* src = reinterpret_cast<const int4*>(t.rec + last);
         int4* dst = reinterpret_cast<int4*>(t.rec + row);
         for (int k = 0; k < 6; ++k) dst[k] = src[k];
+        t.bink[row] = t.bink[last];
         mark_dirty(t, row);
     }
     head->n_dirty = *t.dirty_count;
