@@ -85,6 +85,7 @@ struct cb200_ctx {
     uint32_t* collider_dirty_count = nullptr;
     unsigned long long* d_sort_cursor = nullptr;  // entry cursor of the re-sort's counting sort
     bool stage_timing = true;  // CUDA events between the stages (diagnostic); off: only around the whole step
+    bool stage_a_tma = false;  // CB200_STAGE_A=tma: input columns staged through shared memory by bulk async copies (measured slower, kept for A/B)
     // sharding
     bool sharded = false;
     ShardGeom shard{};
@@ -280,6 +281,10 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaMalloc(&c->d_key, sizeof(MinKey))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&c->d_sort_cursor, 8)) != cudaSuccess) return bail("cudaMalloc", e);
     if (const char* rp = getenv("CB200_RESORT_PERIOD")) c->resort_period = std::max(0, atoi(rp));
+    if (const char* sa = getenv("CB200_STAGE_A")) c->stage_a_tma = strcmp(sa, "tma") == 0;
+    if ((e = cudaFuncSetAttribute(k_stage_a_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(StageATile)))) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_stage_a_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(StageATile)))) != cudaSuccess)
+        return bail("cudaFuncSetAttribute", e);
     if ((e = cudaHostAlloc(&c->h_res, sizeof(StepResultDev), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer((void**)&c->d_res, c->h_res, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     for (auto& ev : c->ev_t)
@@ -635,6 +640,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     a.ord = ctx->sharded ? ctx->ord.p : ctx->label.p;
     a.rec = ctx->rec.p;
     a.bink = ctx->bink.p;
+    a.dbg = getenv("CB200_DBG_A") ? (uint32_t)atoi(getenv("CB200_DBG_A")) : 0u;
     a.slot_count = ctx->slots.p;
     a.geom = g;
     a.ctr = ctx->d_ctr;
@@ -644,10 +650,31 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     a.slab = ctx->slab;
     a.vmap = (ctx->sharded && ctx->n_ov) ? ctx->vmap.p : nullptr;
     if (n) {
-        if (ctx->sharded) k_stage_a<true><<<ctx->grid_a, kThreads, 0, ctx->stream>>>(a, ctx->shard);
-        else k_stage_a<false><<<ctx->grid_a, kThreads, 0, ctx->stream>>>(a, whole_world());
-        ctx->launches += 1;
+        // CB200_STAGE_A=tma: full 256-row tiles through the TMA-staged kernel, the tail through the plain one (default: everything)
+        const uint32_t n_tiles = ctx->stage_a_tma ? n / kThreads : 0u;
+        const ShardGeom shg = ctx->sharded ? ctx->shard : whole_world();
+        uint32_t used = 0;
+        if (n_tiles) {
+            const uint32_t grid_t = std::min<uint32_t>(n_tiles, (uint32_t)ctx->sm_count * 4u);
+            const size_t smem = 2 * sizeof(StageATile);
+            a.partial_base = 0;
+            if (ctx->sharded) k_stage_a_tma<true><<<grid_t, kThreads, smem, ctx->stream>>>(a, shg, n_tiles);
+            else k_stage_a_tma<false><<<grid_t, kThreads, smem, ctx->stream>>>(a, shg, n_tiles);
+            used = grid_t;
+            ctx->launches += 1;
+        }
+        const uint32_t first_row = n_tiles * kThreads;
+        if (first_row < n) {
+            const uint32_t grid_r = std::max<uint32_t>(1, std::min<uint32_t>((n - first_row + kThreads - 1) / kThreads, ctx->sm_count * 8));
+            a.partial_base = used;
+            if (ctx->sharded) k_stage_a<true><<<grid_r, kThreads, 0, ctx->stream>>>(a, shg, first_row);
+            else k_stage_a<false><<<grid_r, kThreads, 0, ctx->stream>>>(a, shg, first_row);
+            used += grid_r;
+            ctx->launches += 1;
+        }
+        ctx->grid_a = used;
     } else {
+        ctx->grid_a = 1;
         CU(cudaMemsetAsync(ctx->partial.p, 0xff, sizeof(MinKey) * ctx->grid_a, ctx->stream));
     }
     if (ctx->sharded) {
@@ -719,6 +746,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     sv.id_space = ctx->sharded ? (uint32_t)ctx->id_space : ctx->n;
     sv.sharded = ctx->sharded ? 1 : 0;
     sv.ids = ctx->sharded ? nullptr : ctx->ids.p;
+    sv.dbg = getenv("CB200_DBG_S") ? (uint32_t)atoi(getenv("CB200_DBG_S")) : 0u;
     sv.vs = vs;
     sv.col_lo = sh.col_lo;
     sv.col_hi = sh.col_hi;
@@ -1006,7 +1034,7 @@ int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world 
     // behind a kernel that is waiting for a peer.  Touch every kernel of the step now.
     {
         cudaFuncAttributes fa;
-        const void* fns[] = {(const void*)k_step_zero, (const void*)k_stage_a<true>, (const void*)k_slab_header, (const void*)k_push_halo,
+        const void* fns[] = {(const void*)k_step_zero, (const void*)k_stage_a<true>, (const void*)k_stage_a_tma<true>, (const void*)k_slab_header, (const void*)k_push_halo,
                              (const void*)k_wait_flags, (const void*)k_index_visitors<true>, (const void*)k_index_visitors<false>,
                              (const void*)k_scan_slots, (const void*)k_scatter<true>, (const void*)k_enum_pairs, (const void*)k_solve,
                              (const void*)k_push_key, (const void*)k_reduce_keys, (const void*)k_resort_count, (const void*)k_resort_rank,

@@ -7,6 +7,8 @@
 // which leaves, for every pair whose NEW index rects share a cell, one event created by the higher id
 // against the lower id already rebased to T.  Each kernel cites the reference lines whose results it reproduces.
 #pragma once
+#include <cuda/barrier>
+
 #include "common.cuh"
 
 namespace cb200 {
@@ -46,7 +48,9 @@ struct StepArgs {
     uint32_t* slot_count;  // one device only (the count is fused here)
     GridGeom geom;
     Counters* ctr;
-    MinKey* partial;  // [gridDim.x] solitaire minima
+    MinKey* partial;  // solitaire minima, one per block of the stage-A launches
+    uint32_t partial_base;  // first slot of this launch
+    uint32_t dbg;           // timing experiments only (CB200_DBG_A): 1 skip the cell count, 2 skip the record store, 4 skip the state write-back
     // sharded only: ONE outgoing slab of `slab` records; record 0 is its header (first word = count).  It is
     // all-gathered: every rank receives every slab and simply bins what falls into its own strip.
     HbRec* send;           // [slab]
@@ -226,87 +230,187 @@ __device__ __forceinline__ HbRec make_rec(const HbCore& h, uint32_t gid) {
     return rec;
 }
 
+// Everything of stage A after the row's stored state has been read into `h`.
+template <bool SHARDED>
+__device__ __forceinline__ HbRec stage_a_row(const StepArgs& a, const ShardGeom& sh, uint32_t i, HbCore& h, uint32_t gid, uint32_t o, MinKey& best,
+                                             unsigned long long& n_sol) {
+    // (the caller's arrays are in upload order: gathered through ord; a re-run reads the stored pub_end_time by row)
+    NewVel nv;
+    nv.has_vx = a.nvx != nullptr; nv.has_vy = a.nvy != nullptr; nv.has_rw = a.nrw != nullptr; nv.has_rh = a.nrh != nullptr;
+    nv.vx = nv.has_vx ? __ldg(a.nvx + o) : 0.0;
+    nv.vy = nv.has_vy ? __ldg(a.nvy + o) : 0.0;
+    nv.rw = nv.has_rw ? __ldg(a.nrw + o) : 0.0;
+    nv.rh = nv.has_rh ? __ldg(a.nrh + o) : 0.0;
+    nv.end_time = a.nend ? __ldg(a.nend + (a.rebase ? o : i)) : a.end_scalar;
+    const uint32_t err = hb_update_core(h, a.T, a.rebase != 0, nv, a.cell_width, a.padding, a.geom);
+    if (h.binned && !(a.dbg & 1u)) {
+        // cell count (sharded: only the cells inside the own strip)
+        const int32_t x0 = SHARDED ? max(h.sx, sh.col_lo) : h.sx, x1 = SHARDED ? min(h.ex, sh.col_hi) : h.ex;
+        for (int32_t x = x0; x < x1; ++x)
+            for (int32_t y = h.sy; y != h.ey; ++y) atomicAdd(&a.slot_count[a.geom.slot(x, y)], 1u);
+    }
+    if (err) report_error(a.ctr, err, gid);
+
+    // write back: state columns + pair-stage record
+    if (!(a.dbg & 4u)) {
+    a.s.px[i] = h.px; a.s.py[i] = h.py; a.s.w[i] = h.w; a.s.h[i] = h.h;
+    if (a.nvx) a.s.vx[i] = h.vx;
+    if (a.nvy) a.s.vy[i] = h.vy;
+    if (a.nrw) a.s.rw[i] = h.rw;
+    if (a.nrh) a.s.rh[i] = h.rh;
+    a.s.start[i] = h.start;
+    a.s.end[i] = h.end;
+    a.s.pub_end[i] = h.pub_end;
+    a.s.reit[i] = h.reit ? 1 : 0;
+    }
+
+    // the record stays at its row; a sharded rank bins only the cells inside its own strip (above and in k_scatter)
+    const HbRec rec = make_rec(h, gid);
+    if (!(a.dbg & 2u)) a.bink[i] = make_int4(rec.sx, rec.sy, (int)rec.span, (int)rec.kgb);
+    if (SHARDED && a.vmap) a.vmap[gid] = i;
+    if (SHARDED && h.binned) {
+        // The record is needed by every rank whose strip intersects columns [sx, ex + 1): the extra column keeps
+        // a partner that is within `padding` across a cell line (an overlapping pair whose rects do not
+        // intersect) visible.  Any strip other than the own one -> the halo slab.
+        const int64_t hi_col = (int64_t)h.ex + 1;
+        const bool leaves = (int64_t)rec.sx < (int64_t)sh.col_lo || hi_col > (int64_t)sh.col_hi;
+        if (leaves) {
+            const uint32_t pos = warp_agg_claim32(a.send_count);
+            if (pos + 1 < a.slab) store_rec(a.send + 1 + pos, rec);
+            else a.ctr->overflow_send = 1u;
+        }
+    }
+    if (h.reit) {
+        ++n_sol;
+        const MinKey k{time_key(h.end), (uint64_t)gid};
+        if (key_less(k, best)) best = k;
+    }
+    return rec;
+}
+
+// The 96-byte records of a warp's 32 consecutive rows, written as 3 KB of contiguous 16-byte chunks: each lane parks its
+// record in shared memory (stride 112 B: conflict-free 128-bit accesses) and then stores chunks lane, lane + 32, ... of the
+// warp's block — full sectors, half the store transactions of 32 lanes writing 16 bytes each at a 96-byte stride (the
+// record store was 25 of stage A's 62 us: profiles/stage_a_ablation.py).
+constexpr int kRecStageStride = 7;  // int4 slots per record in shared memory (6 used)
+__device__ __forceinline__ void store_recs_warp(HbRec* rec_base /* rec + first row of the warp */, uint32_t n_valid, const HbRec& mine, int4* s_warp /* [32 * 7] */) {
+    const int lane = threadIdx.x & 31;
+    const int4* in = reinterpret_cast<const int4*>(&mine);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s_warp[lane * kRecStageStride + k] = in[k];
+    __syncwarp();
+    int4* out = reinterpret_cast<int4*>(rec_base);
+    const uint32_t n_chunks = n_valid * 6u;
+    const uint64_t keep = l2_policy_evict_last();
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        const uint32_t c = (uint32_t)lane + 32u * j;
+        if (c < n_chunks) st_int4_keep(out + c, s_warp[(c / 6u) * kRecStageStride + (c % 6u)], keep);
+    }
+    __syncwarp();
+}
+
 #ifndef CB200_LB_A
 #define CB200_LB_A 4
 #endif
+// Plain variant: every thread loads its row's columns itself (also the tail of the staged variant).
 template <bool SHARDED>
-__global__ void __launch_bounds__(kThreads, CB200_LB_A) k_stage_a(const StepArgs a, const ShardGeom sh) {
+__global__ void __launch_bounds__(kThreads, CB200_LB_A) k_stage_a(const StepArgs a, const ShardGeom sh, uint32_t first_row) {
+    __shared__ int4 s_rec[kThreads / 32][32 * kRecStageStride];
     MinKey best{kKeyMax, kKeyMax};
     unsigned long long n_sol = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x; base < a.n; base += stride) {
+    for (uint32_t base = first_row + blockIdx.x * blockDim.x; base < a.n; base += stride) {
         const uint32_t i = base + threadIdx.x;
         HbRec rec;
-        int32_t ex = 0;
         if (i < a.n) {
             HbCore h;
             h.px = a.s.px[i]; h.py = a.s.py[i]; h.w = a.s.w[i]; h.h = a.s.h[i];
             h.vx = a.s.vx[i]; h.vy = a.s.vy[i]; h.rw = a.s.rw[i]; h.rh = a.s.rh[i];
             h.start = a.s.start[i]; h.pub_end = a.s.pub_end[i];
             h.kind = a.s.kind[i]; h.group = a.s.group[i]; h.mask = a.s.mask[i];
-            const uint32_t gid = a.label[i];
-            // (the caller's arrays are in upload order: gathered through ord; a re-run reads the stored pub_end_time by row)
-            const uint32_t o = a.ord[i];
-            NewVel nv;
-            nv.has_vx = a.nvx != nullptr; nv.has_vy = a.nvy != nullptr; nv.has_rw = a.nrw != nullptr; nv.has_rh = a.nrh != nullptr;
-            nv.vx = nv.has_vx ? __ldg(a.nvx + o) : 0.0;
-            nv.vy = nv.has_vy ? __ldg(a.nvy + o) : 0.0;
-            nv.rw = nv.has_rw ? __ldg(a.nrw + o) : 0.0;
-            nv.rh = nv.has_rh ? __ldg(a.nrh + o) : 0.0;
-            nv.end_time = a.nend ? __ldg(a.nend + (a.rebase ? o : i)) : a.end_scalar;
-            const uint32_t err = hb_update_core(h, a.T, a.rebase != 0, nv, a.cell_width, a.padding, a.geom);
-            ex = h.ex;
-            if (h.binned) {
-                // cell count (sharded: only the cells inside the own strip)
-                const int32_t x0 = SHARDED ? max(h.sx, sh.col_lo) : h.sx, x1 = SHARDED ? min(h.ex, sh.col_hi) : h.ex;
-                for (int32_t x = x0; x < x1; ++x)
-                    for (int32_t y = h.sy; y != h.ey; ++y) atomicAdd(&a.slot_count[a.geom.slot(x, y)], 1u);
-            }
-            if (err) report_error(a.ctr, err, gid);
-
-            // write back: state columns + pair-stage record
-            a.s.px[i] = h.px; a.s.py[i] = h.py; a.s.w[i] = h.w; a.s.h[i] = h.h;
-            if (a.nvx) a.s.vx[i] = h.vx;
-            if (a.nvy) a.s.vy[i] = h.vy;
-            if (a.nrw) a.s.rw[i] = h.rw;
-            if (a.nrh) a.s.rh[i] = h.rh;
-            a.s.start[i] = h.start;
-            a.s.end[i] = h.end;
-            a.s.pub_end[i] = h.pub_end;
-            a.s.reit[i] = h.reit ? 1 : 0;
-
-            rec = make_rec(h, gid);
-            const bool binned = h.binned;
-            const bool reit = h.reit;
-            const double r_time = h.end;
-            // the record stays at its row; a sharded rank bins only the cells inside its own strip (above and in k_scatter)
-            store_rec(a.rec + i, rec);
-            a.bink[i] = make_int4(rec.sx, rec.sy, (int)rec.span, (int)rec.kgb);
-            if (SHARDED && a.vmap) a.vmap[gid] = i;
-            if (SHARDED && binned) {
-                // The record is needed by every rank whose strip intersects columns [sx, ex + 1): the extra column keeps
-                // a partner that is within `padding` across a cell line (an overlapping pair whose rects do not
-                // intersect) visible.  Any strip other than the own one -> the halo slab.
-                const int64_t hi_col = (int64_t)ex + 1;
-                const bool leaves = (int64_t)rec.sx < (int64_t)sh.col_lo || hi_col > (int64_t)sh.col_hi;
-                if (leaves) {
-                    const uint32_t pos = warp_agg_claim32(a.send_count);
-                    if (pos + 1 < a.slab) store_rec(a.send + 1 + pos, rec);
-                    else a.ctr->overflow_send = 1u;
-                }
-            }
-
-            if (reit) {
-                ++n_sol;
-                const MinKey k{time_key(r_time), (uint64_t)gid};
-                if (key_less(k, best)) best = k;
-            }
+            rec = stage_a_row<SHARDED>(a, sh, i, h, a.label[i], a.ord[i], best, n_sol);
         }
+        const uint32_t warp_row = base + (threadIdx.x & ~31u);
+        if (warp_row < a.n && !(a.dbg & 2u)) store_recs_warp(a.rec + warp_row, min(32u, a.n - warp_row), rec, s_rec[threadIdx.x >> 5]);
     }
     best = block_min(best);
     const unsigned long long tot = block_sum(n_sol);
     if (threadIdx.x == 0) {
-        a.partial[blockIdx.x] = best;
+        a.partial[a.partial_base + blockIdx.x] = best;
+        if (tot) atomicAdd(&a.ctr->n_solitaire, tot);
+    }
+}
+
+// Staged variant: the 14 input columns of a 256-row tile are brought into shared memory by bulk async copies (TMA,
+// cp.async.bulk, one elected thread, completion on an mbarrier), two tiles deep, so the bytes in flight per SM do not
+// depend on how many threads happen to be in their load phase (the plain variant sat at 55 % of the HBM peak with every
+// warp stalled on its first use of a loaded value, profiles/r1c_step_kernels.txt).  Persistent blocks; full tiles only.
+struct StageATile {
+    double col[10][kThreads];  // px py w h vx vy rw rh start pub_end
+    uint32_t group[kThreads], mask[kThreads], label[kThreads], ord[kThreads];
+    uint8_t kind[kThreads];
+};
+constexpr uint32_t kStageATileBytes = 10 * kThreads * 8 + 4 * kThreads * 4 + kThreads;
+
+template <bool SHARDED>
+__global__ void __launch_bounds__(kThreads, CB200_LB_A) k_stage_a_tma(const StepArgs a, const ShardGeom sh, uint32_t n_tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StageATile* tile = reinterpret_cast<StageATile*>(smem_raw);  // [2]
+    __shared__ int4 s_rec[kThreads / 32][32 * kRecStageStride];
+    __shared__ cuda::barrier<cuda::thread_scope_block> bar[2];
+    if (threadIdx.x == 0) {
+        init(&bar[0], blockDim.x);
+        init(&bar[1], blockDim.x);
+        cuda::device::experimental::fence_proxy_async_shared_cta();
+    }
+    __syncthreads();
+    const double* src[10] = {a.s.px, a.s.py, a.s.w, a.s.h, a.s.vx, a.s.vy, a.s.rw, a.s.rh, a.s.start, a.s.pub_end};
+    auto issue = [&](uint32_t t, int stage) {  // thread 0 only
+        const size_t row0 = (size_t)t * kThreads;
+        StageATile& dst = tile[stage];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) cuda::device::memcpy_async_tx(dst.col[k], src[k] + row0, cuda::aligned_size_t<16>(kThreads * 8), bar[stage]);
+        cuda::device::memcpy_async_tx(dst.group, a.s.group + row0, cuda::aligned_size_t<16>(kThreads * 4), bar[stage]);
+        cuda::device::memcpy_async_tx(dst.mask, a.s.mask + row0, cuda::aligned_size_t<16>(kThreads * 4), bar[stage]);
+        cuda::device::memcpy_async_tx(dst.label, a.label + row0, cuda::aligned_size_t<16>(kThreads * 4), bar[stage]);
+        cuda::device::memcpy_async_tx(dst.ord, a.ord + row0, cuda::aligned_size_t<16>(kThreads * 4), bar[stage]);
+        cuda::device::memcpy_async_tx(dst.kind, a.s.kind + row0, cuda::aligned_size_t<16>(kThreads), bar[stage]);
+    };
+    MinKey best{kKeyMax, kKeyMax};
+    unsigned long long n_sol = 0;
+    cuda::barrier<cuda::thread_scope_block>::arrival_token token[2];
+    auto arm = [&](uint32_t t, int stage) {  // all threads: arrive on the stage's barrier; thread 0 also posts the copies
+        if (threadIdx.x == 0) {
+            issue(t, stage);
+            token[stage] = cuda::device::barrier_arrive_tx(bar[stage], 1, kStageATileBytes);
+        } else {
+            token[stage] = bar[stage].arrive();
+        }
+    };
+    uint32_t t = blockIdx.x;
+    int stage = 0;
+    if (t < n_tiles) arm(t, 0);
+    for (; t < n_tiles; t += gridDim.x, stage ^= 1) {
+        const uint32_t t_next = t + gridDim.x;
+        if (t_next < n_tiles) arm(t_next, stage ^ 1);  // (that stage was released by the barrier at the end of the previous iteration)
+        bar[stage].wait(std::move(token[stage]));
+        const StageATile& src_tile = tile[stage];
+        const uint32_t i = t * kThreads + threadIdx.x;
+        HbCore h;
+        h.px = src_tile.col[0][threadIdx.x]; h.py = src_tile.col[1][threadIdx.x]; h.w = src_tile.col[2][threadIdx.x]; h.h = src_tile.col[3][threadIdx.x];
+        h.vx = src_tile.col[4][threadIdx.x]; h.vy = src_tile.col[5][threadIdx.x]; h.rw = src_tile.col[6][threadIdx.x]; h.rh = src_tile.col[7][threadIdx.x];
+        h.start = src_tile.col[8][threadIdx.x]; h.pub_end = src_tile.col[9][threadIdx.x];
+        h.kind = src_tile.kind[threadIdx.x]; h.group = src_tile.group[threadIdx.x]; h.mask = src_tile.mask[threadIdx.x];
+        const uint32_t gid = src_tile.label[threadIdx.x], o = src_tile.ord[threadIdx.x];
+        __syncthreads();  // every thread has its row in registers: the stage may be refilled
+        const HbRec rec = stage_a_row<SHARDED>(a, sh, i, h, gid, o, best, n_sol);
+        if (!(a.dbg & 2u)) store_recs_warp(a.rec + (i & ~31u), 32u, rec, s_rec[threadIdx.x >> 5]);
+    }
+    best = block_min(best);
+    const unsigned long long tot = block_sum(n_sol);
+    if (threadIdx.x == 0) {
+        a.partial[a.partial_base + blockIdx.x] = best;
         if (tot) atomicAdd(&a.ctr->n_solitaire, tot);
     }
 }
@@ -956,6 +1060,7 @@ struct SolveArgs {
     VisSpace vs;
     int32_t col_lo, col_hi;
     const uint64_t* ids;     // label -> HbId (null: the label is the id)
+    uint32_t dbg;            // timing experiments only (CB200_DBG_S): 1 skip the narrowphase, 2 skip the event append, 4 skip the candidate test
 };
 
 // A map entry is trusted only if it names a record slot that is live in THIS step and that record carries the gid.
@@ -1012,6 +1117,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
         }
     };
     uint32_t pending_rounds = 0;
+    const uint64_t keep = l2_policy_evict_last();
     for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
         const uint32_t p = base + threadIdx.x;
         if (p < total) {
@@ -1027,11 +1133,13 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
             }
             if (present) {
                 // all twelve 16-byte loads of the two records are issued before anything depends on them
-                const RecHead ha = load_head(a.rec, ia), hb = load_head(a.rec, ib);
-                const DurHb da = load_body(a.rec, ia, ha), db = load_body(a.rec, ib, hb);
+                RecHead ha, hb;
+                DurHb da, db;
+                load_rec_keep(a.rec, ia, keep, &ha, &da);
+                load_rec_keep(a.rec, ib, keep, &hb, &db);
                 bool a_is_hi = true;  // overlap pairs arrive as (hi, lo)
                 if (!sep) {
-                    present = candidate_test(a.cd, ha, hb, slot, &a_is_hi);
+                    present = (a.dbg & 4u) ? true : candidate_test(a.cd, ha, hb, slot, &a_is_hi);
                     n_col += present;
                 } else {
                     const int32_t owner_col = max(ha.sx, hb.sx);
@@ -1042,11 +1150,11 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
                     // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486): advanced by T - start = 0
                     const DurHb B = advanced(pick(a_is_hi, db, da), 0.0);
                     const uint32_t gid_hi = a_is_hi ? ha.gid : hb.gid, gid_lo = a_is_hi ? hb.gid : ha.gid;
-                    const double delay = sep ? separate_time(A, B, a.padding) : collide_time(A, B);
+                    const double delay = (a.dbg & 1u) ? (A.px + B.px) : (sep ? separate_time(A, B, a.padding) : collide_time(A, B));
                     if (delay != delay) report_error(a.ctr, kFNan, gid_hi);
                     n_sep += sep;
                     const double t = a.T + delay;
-                    if (t < kHighTime) {
+                    if (t < kHighTime && !(a.dbg & 2u)) {
                         const uint32_t kind_bit = sep ? 0u : kCollideBit;
                         s_ev[atomicAdd(&s_n, 1u)] = PairEvent{t, gid_hi, gid_lo | kind_bit};
                         const MinKey k{time_key(t), kPairClass | ((uint64_t)gid_hi << 32) | kind_bit | gid_lo};
