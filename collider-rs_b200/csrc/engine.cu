@@ -137,6 +137,7 @@ struct cb200_ctx {
     // sorted event cache
     DevBuf<Key128> keys_a, keys_b;
     DevBuf<uint32_t> rs_hist;
+    DevBuf<uint32_t> bs_tab[5];  // bucket sort, one per recursion depth: counts / offsets, cursors, oversized buckets, range
     DevBuf<EventOut> ev_out;
     bool ev_sorted = false;
     uint64_t n_ev_sorted = 0;
@@ -309,7 +310,7 @@ void cb200_destroy(cb200_ctx* c) {
     c->slots.release(); c->chunk_base.release(); c->entries.release(); c->work.release(); c->work_count.release();
     c->ov_pairs.release(); c->ov_table.release(); c->ov_bits.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
-    c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); c->ev_out.release();
+    c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); for (auto& b : c->bs_tab) b.release(); c->ev_out.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->d_key) cudaFree(c->d_key);
     for (int i = 0; i < c->n_ipc_opened; ++i) cudaIpcCloseMemHandle(c->ipc_opened[i]);
@@ -1093,6 +1094,77 @@ int cb200_shard_global_next(cb200_ctx* ctx, uint64_t* time_key_out, uint64_t* ti
 void* cb200_shard_local_key(cb200_ctx* ctx) { return ctx ? ctx->d_key : nullptr; }
 
 // ---- event queue materialisation -------------------------------------------------------------------------
+// Sorts keys[0, n) in place (scratch: the same range of `tmp`) by the bucket sort of sort.cuh.  field: 1 = cut the buckets on
+// the time key, 0 = on the tie word (all keys of the range share one time).  *ok = false: give up (the caller falls back
+// to the radix sort).  One small D2H + sync per level.
+static int sort_range(cb200_ctx* ctx, Key128* keys, Key128* tmp, uint32_t n, int field, int depth, bool* ok) {
+    *ok = false;
+    if (n < 2) {
+        *ok = true;
+        return CB200_OK;
+    }
+    if (depth > 3) return CB200_OK;
+    int log2_buckets = 6;
+    while ((1u << log2_buckets) * 12u < n && log2_buckets < 22) ++log2_buckets;
+    const uint32_t n_buckets = 1u << log2_buckets;
+    const size_t words = 2 * (size_t)n_buckets + 2 + 2 * kBsMaxBig + 8;
+    DevBuf<uint32_t>& tab = ctx->bs_tab[depth];  // (deeper levels run while the parent's table is still needed: one per depth)
+    CU(tab.reserve(words));
+    uint32_t* count = tab.p;                      // then: offsets [n_buckets + 1]
+    uint32_t* cursor = tab.p + n_buckets + 1;     // [n_buckets]
+    uint32_t* big = cursor + n_buckets;           // [1 + 2 * kBsMaxBig]
+    BsRange* range = reinterpret_cast<BsRange*>(tab.p + ((2 * (size_t)n_buckets + 2 + 2 * kBsMaxBig + 1) & ~(size_t)1));
+    const BsRange init{~0ull, 0ull};
+    CU(cudaMemsetAsync(count, 0, ((size_t)n_buckets + 1) * 4, ctx->stream));
+    CU(cudaMemcpyAsync(range, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t blocks = (n + kThreads - 1) / kThreads;
+    k_bs_minmax<<<std::min<uint32_t>(blocks, 1024), kThreads, 0, ctx->stream>>>(n, keys, field, range);
+    ctx->launches += 1;
+    if (depth > 0 && field == 1) {
+        // an oversized bucket of the time key: if all its times are equal, the tie word decides
+        BsRange r;
+        CU(cudaMemcpyAsync(&r, range, sizeof(r), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (r.lo == r.hi) return sort_range(ctx, keys, tmp, n, 0, depth, ok);
+    }
+    k_bs_count<<<blocks, kThreads, 0, ctx->stream>>>(n, keys, field, range, log2_buckets, count);
+    k_bs_scan<<<1, 1024, 0, ctx->stream>>>(count, n_buckets, count, cursor, big);
+    k_bs_scatter<<<blocks, kThreads, 0, ctx->stream>>>(n, keys, field, range, log2_buckets, cursor, tmp);
+    k_bs_local<<<std::min<uint32_t>((n_buckets + 7) / 8, (uint32_t)ctx->sm_count * 8u), 256, 0, ctx->stream>>>(tmp, count, n_buckets, keys);
+    ctx->launches += 4;
+    uint32_t h_big[1 + 2 * kBsMaxBig];
+    CU(cudaMemcpyAsync(h_big, big, sizeof(h_big), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (getenv("CB200_VERBOSE")) fprintf(stderr, "[cb200] event sort level %d field %d: %u keys, %u buckets, %u oversized\n", depth, field, n, n_buckets, h_big[0]);
+    if (h_big[0] > (uint32_t)kBsMaxBig) {
+        // too fragmented: fall back.  The oversized buckets exist only in tmp: hand the complete multiset back first.
+        CU(cudaMemcpyAsync(keys, tmp, (size_t)n * sizeof(Key128), cudaMemcpyDeviceToDevice, ctx->stream));
+        return CB200_OK;
+    }
+    for (uint32_t k = 0; k < h_big[0]; ++k) {
+        const uint32_t off = h_big[1 + 2 * k], m = h_big[2 + 2 * k];
+        if (m == n) {
+            // no progress: every key has the same value in this field (the keys are in tmp, unsorted)
+            CU(cudaMemcpyAsync(keys, tmp, (size_t)n * sizeof(Key128), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (field == 1) return sort_range(ctx, keys, tmp, n, 0, depth + 1, ok);
+            return CB200_OK;
+        }
+        // the bucket's keys sit in tmp (k_bs_local skipped it): sort them there, then bring them over
+        bool sub_ok = false;
+        int rc = sort_range(ctx, tmp + off, keys + off, m, field, depth + 1, &sub_ok);
+        if (rc != CB200_OK) return rc;
+        CU(cudaMemcpyAsync(keys + off, tmp + off, (size_t)m * sizeof(Key128), cudaMemcpyDeviceToDevice, ctx->stream));
+        if (!sub_ok) {
+            // give up: the remaining oversized buckets are still only in tmp
+            for (uint32_t k2 = k + 1; k2 < h_big[0]; ++k2)
+                CU(cudaMemcpyAsync(keys + h_big[1 + 2 * k2], tmp + h_big[1 + 2 * k2], (size_t)h_big[2 + 2 * k2] * sizeof(Key128), cudaMemcpyDeviceToDevice, ctx->stream));
+            return CB200_OK;
+        }
+    }
+    *ok = true;
+    return CB200_OK;
+}
+
 static int sort_events(cb200_ctx* ctx) {
     if (ctx->ev_sorted) return CB200_OK;
     const Counters& c = ctx->last.ctr;
@@ -1108,24 +1180,34 @@ static int sort_events(cb200_ctx* ctx) {
     const uint32_t n_blocks = (nt + kRsTile - 1) / kRsTile;
     CU(ctx->rs_hist.reserve((size_t)16 * n_blocks));
     CU(cudaMemsetAsync(&ctx->d_ctr->n_sort_keys, 0, 8, ctx->stream));
-    CU(cudaMemsetAsync(&ctx->d_ctr->diff_hi, 0, 16, ctx->stream));
     if (ctx->n) k_keys_solitaire<<<(ctx->n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(ctx->n, ctx->reit.p, ctx->col[9].p, ctx->label.p, ctx->keys_a.p, ctx->d_ctr);
     if (n_pairs) k_keys_pairs<<<((uint32_t)n_pairs + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>((uint32_t)n_pairs, ctx->events.p, ctx->keys_a.p, c.n_solitaire);
-    k_key_diff<<<std::min<uint32_t>(n_blocks, 1024), kThreads, 0, ctx->stream>>>(nt, ctx->keys_a.p, ctx->d_ctr);
-    ctx->launches += 3;
-    unsigned long long diff[2];
-    CU(cudaMemcpyAsync(diff, &ctx->d_ctr->diff_hi, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    const unsigned long long diff_hi = diff[0], diff_lo = diff[1];
+    ctx->launches += 2;
     Key128 *in = ctx->keys_a.p, *outp = ctx->keys_b.p;
-    for (int shift = 0; shift < 128; shift += 4) {
-        const unsigned long long d = shift < 64 ? (diff_lo >> shift) & 15ull : (diff_hi >> (shift - 64)) & 15ull;
-        if (!d) continue;
-        k_rs_hist<<<n_blocks, kRsThreads, 0, ctx->stream>>>(in, nt, shift, ctx->rs_hist.p, n_blocks);
-        k_rs_scan<<<1, 1024, 0, ctx->stream>>>(ctx->rs_hist.p, 16 * n_blocks);
-        k_rs_scatter<<<n_blocks, kRsThreads, 0, ctx->stream>>>(in, outp, nt, shift, ctx->rs_hist.p, n_blocks);
-        ctx->launches += 3;
-        std::swap(in, outp);
+    // fast path: bucket sort by time range + per-bucket rank sort, recursing into oversized buckets (sort.cuh)
+    bool sorted = false;
+    {
+        int rc = sort_range(ctx, in, outp, nt, 1, 0, &sorted);
+        if (rc != CB200_OK) return rc;
+    }
+    if (!sorted) {
+        // fallback: LSD radix sort on the digits that differ
+        CU(cudaMemsetAsync(&ctx->d_ctr->diff_hi, 0, 16, ctx->stream));
+        k_key_diff<<<std::min<uint32_t>(n_blocks, 1024), kThreads, 0, ctx->stream>>>(nt, ctx->keys_a.p, ctx->d_ctr);
+        ctx->launches += 1;
+        unsigned long long diff[2];
+        CU(cudaMemcpyAsync(diff, &ctx->d_ctr->diff_hi, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        const unsigned long long diff_hi = diff[0], diff_lo = diff[1];
+        for (int shift = 0; shift < 128; shift += 4) {
+            const unsigned long long d = shift < 64 ? (diff_lo >> shift) & 15ull : (diff_hi >> (shift - 64)) & 15ull;
+            if (!d) continue;
+            k_rs_hist<<<n_blocks, kRsThreads, 0, ctx->stream>>>(in, nt, shift, ctx->rs_hist.p, n_blocks);
+            k_rs_scan<<<1, 1024, 0, ctx->stream>>>(ctx->rs_hist.p, 16 * n_blocks);
+            k_rs_scatter<<<n_blocks, kRsThreads, 0, ctx->stream>>>(in, outp, nt, shift, ctx->rs_hist.p, n_blocks);
+            ctx->launches += 3;
+            std::swap(in, outp);
+        }
     }
     k_decode_events<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(nt, in, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p);
     ctx->launches += 1;

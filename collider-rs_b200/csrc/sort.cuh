@@ -177,6 +177,144 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const Key128* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fast path: bucket sort.  Event times of a step are spread over [T, end_time], so the order-preserving time key is cut
+// into 2^b equal ranges (~12 events each), the keys are counting-sorted into those buckets, and every bucket is finished by
+// one warp with a rank sort on the full 128-bit key in shared memory.  Six launches instead of ~70 for the LSD radix sort
+// above, which remains the fallback when some bucket is too large (many events at exactly the same time).
+constexpr int kBsMaxBucket = 128;  // keys a warp sorts in shared memory
+
+// The buckets are cut on ONE 64-bit field of the key: the time key (field 1), or — for a set of keys that all carry the
+// same time, e.g. everything that happens exactly at T — the tie word (field 0).  Buckets that come out too large for a warp
+// are sorted again on their own range (the host recurses, sort_range in engine.cu).
+struct BsRange {
+    unsigned long long lo, hi;  // min / max of the field
+};
+__device__ __forceinline__ unsigned long long bs_field(const Key128& k, int field) { return field ? k.hi : k.lo; }
+__global__ void k_bs_minmax(uint32_t n, const Key128* __restrict__ keys, int field, BsRange* r) {
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long t = bs_field(keys[i], field);
+        lo = min(lo, t);
+        hi = max(hi, t);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&r->lo, lo);
+        atomicMax(&r->hi, hi);
+    }
+}
+// Bucket of a field value: monotone non-decreasing in the value (that is all the sort needs).  Times are cut linearly in
+// the time itself — the bit pattern of a double is linear only inside one binade, and a step starting at T = 0 spans all of
+// them; the tie word is an integer and is cut on its leading bits.
+__device__ __forceinline__ uint32_t bs_bucket(unsigned long long t, const BsRange& r, int log2_buckets, int field) {
+    if (field == 1) {
+        const double lo = key_time(r.lo), hi = key_time(r.hi), x = key_time(t);
+        const double scaled = (x - lo) * ((double)(1u << log2_buckets) / (hi - lo));  // hi > lo here; finite (times < 1e50)
+        const uint32_t last = (1u << log2_buckets) - 1u;
+        return scaled >= (double)last ? last : (uint32_t)scaled;
+    }
+    const unsigned long long span = r.hi - r.lo;
+    const int bits = span ? 64 - __clzll((long long)span) : 0;  // span < 2^bits
+    const int shift = bits > log2_buckets ? bits - log2_buckets : 0;
+    return (uint32_t)((t - r.lo) >> shift);
+}
+__global__ void k_bs_count(uint32_t n, const Key128* __restrict__ keys, int field, const BsRange* r, int log2_buckets, uint32_t* count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&count[r->lo == r->hi ? 0u : bs_bucket(bs_field(keys[i], field), *r, log2_buckets, field)], 1u);
+}
+// one block: offsets[b] = exclusive prefix of count (offsets[n_buckets] = total), cursor = a copy; big[0] = number of buckets
+// with more than kBsMaxBucket keys, big[1 + 2k], big[2 + 2k] = offset and size of the k-th of them (k < kBsMaxBig)
+constexpr int kBsMaxBig = 15;
+__global__ void __launch_bounds__(1024) k_bs_scan(const uint32_t* count, uint32_t n_buckets, uint32_t* offsets, uint32_t* cursor, uint32_t* big) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry, s_big;
+    if (threadIdx.x == 0) {
+        s_carry = 0;
+        s_big = 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_buckets; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_buckets ? count[i] : 0;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t ws = s_w[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += t;
+            }
+            s_w[lane] = ws;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + inc - v + (warp ? s_w[warp - 1] : 0);
+        if (i < n_buckets) {
+            offsets[i] = excl;
+            cursor[i] = excl;
+            if (v > (uint32_t)kBsMaxBucket) {
+                const uint32_t k = atomicAdd(&s_big, 1u);
+                if (k < (uint32_t)kBsMaxBig) {
+                    big[1 + 2 * k] = excl;
+                    big[2 + 2 * k] = v;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        offsets[n_buckets] = s_carry;
+        big[0] = s_big;
+    }
+}
+__global__ void k_bs_scatter(uint32_t n, const Key128* __restrict__ keys, int field, const BsRange* r, int log2_buckets, uint32_t* cursor, Key128* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Key128 k = keys[i];
+    out[atomicAdd(&cursor[r->lo == r->hi ? 0u : bs_bucket(bs_field(k, field), *r, log2_buckets, field)], 1u)] = k;
+}
+__device__ __forceinline__ bool key128_less(const Key128& a, const Key128& b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+// one warp per bucket: rank sort in shared memory; larger buckets are left in `in` (the host sorts them there next)
+__global__ void __launch_bounds__(256) k_bs_local(const Key128* __restrict__ in, const uint32_t* __restrict__ offsets, uint32_t n_buckets, Key128* out) {
+    __shared__ Key128 s_keys[8][kBsMaxBucket];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t b = blockIdx.x * 8 + warp; b < n_buckets; b += gridDim.x * 8) {
+        const uint32_t o0 = offsets[b], m = offsets[b + 1] - o0;
+        if (m == 0) continue;
+        if (m > (uint32_t)kBsMaxBucket) continue;
+        if (m == 1) {
+            if (lane == 0) out[o0] = in[o0];
+            continue;
+        }
+        for (uint32_t i = lane; i < m; i += 32) s_keys[warp][i] = in[o0 + i];
+        __syncwarp();
+        for (uint32_t i = lane; i < m; i += 32) {
+            const Key128 k = s_keys[warp][i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < m; ++j) {
+                const Key128 q = s_keys[warp][j];
+                rank += (key128_less(q, k) || (q.hi == k.hi && q.lo == k.lo && j < i)) ? 1u : 0u;
+            }
+            out[o0 + rank] = k;
+        }
+        __syncwarp();
+    }
+}
+
 // Decode sorted keys to the C-ABI event records (layout of cb200_event: f64 time, u64 a, u64 b, u32 kind, u32 pad).
 struct EventOut {
     double time;

@@ -202,6 +202,37 @@ def test_table_order_never_changes_results(oracle, period):
         assert (rects[i][0], rects[i][1], rects[i][2], rects[i][3]) == (gx[sel].min(), gy[sel].min(), gx[sel].max() + 1, gy[sel].max() + 1)
 
 
+def canonical_order(ev):
+    cls = np.where(ev["kind"] == 0, 0, 1)
+    kbit = np.where(ev["kind"] == 1, 1, 0)
+    return np.lexsort((ev["b"], kbit, ev["a"], cls, ev["time"]))
+
+
+def test_event_queue_order_at_scale(oracle):
+    """The queue materialisation (bucket sort on the time key, recursing into heavy ties, radix fallback) on 120k hitboxes:
+    step 1 starts at T = 0 (event times span every binade) and is compared with the oracle event by event; step 2 runs
+    without processing the Collide events of step 1, so every pair already in contact reports time == T exactly (tens of
+    thousands of ties ordered by the tie word) — checked for canonical order, uniqueness and count."""
+    n = 120_000
+    scene = scenes.uniform_density(n, density=0.05, seed=4711)
+    orc, eng = seeded(oracle, scene)
+    orc.bulk_update(end_time=0.1)
+    res = eng.bulk_update(0.0, end_time=0.1)
+    t, kind, a, b = oracle_events(orc)
+    ev = eng.fetch_events()
+    assert len(ev) == len(t) == res.n_events > 2_000
+    np.testing.assert_array_equal(ev["kind"], kind)
+    np.testing.assert_array_equal(ev["a"], a)
+    np.testing.assert_array_equal(bits(ev["time"]), bits(t))
+    res = eng.bulk_update(0.1, end_time=0.2)
+    ev = eng.fetch_events(pinned=True).copy()
+    assert len(ev) == res.n_events
+    assert (ev["time"] == 0.1).sum() > 200, "the case must contain a heavy tie"
+    np.testing.assert_array_equal(canonical_order(ev), np.arange(len(ev)))
+    key = (ev["a"].astype(np.uint64) << np.uint64(32) | ev["b"]) * np.uint64(4) + ev["kind"].astype(np.uint64)
+    assert len(np.unique(key)) == len(ev)
+
+
 def test_aliased_grid_is_still_exact(oracle):
     """Force a tiny grid period so that many cells share a slot: results must not change."""
     scene = scenes.uniform_density(5000)
