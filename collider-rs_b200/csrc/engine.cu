@@ -85,6 +85,19 @@ struct cb200_ctx {
     uint32_t* collider_dirty_count = nullptr;
     unsigned long long* d_sort_cursor = nullptr;  // entry cursor of the re-sort's counting sort
     bool stage_timing = true;  // CUDA events between the stages (diagnostic); off: only around the whole step
+    // CUDA graph replay of the step (one launch instead of 6-7); CB200_GRAPH=0 disables
+    StepDyn* d_dyn = nullptr;
+    StepDyn* h_dyn = nullptr;  // pinned
+    bool use_graph = true;
+    struct GraphSlot {
+        uint64_t sig = 0;
+        cudaGraphExec_t exec = nullptr;
+    };
+    GraphSlot graphs[4];
+    int graph_next = 0;
+    bool capturing = false;
+    uint32_t graph_kernels[4] = {};  // kernels inside each captured graph (for the launch counter)
+    uint64_t graph_launches = 0, graph_captures = 0;
     bool stage_a_tma = false;  // CB200_STAGE_A=tma: input columns staged through shared memory by bulk async copies (measured slower, kept for A/B)
     // sharding
     bool sharded = false;
@@ -281,6 +294,9 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaMalloc(&c->d_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&c->d_key, sizeof(MinKey))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&c->d_sort_cursor, 8)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&c->d_dyn, sizeof(StepDyn))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaHostAlloc(&c->h_dyn, sizeof(StepDyn), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if (const char* g = getenv("CB200_GRAPH")) c->use_graph = g[0] != '0';
     if (const char* rp = getenv("CB200_RESORT_PERIOD")) c->resort_period = std::max(0, atoi(rp));
     if (const char* sa = getenv("CB200_STAGE_A")) c->stage_a_tma = strcmp(sa, "tma") == 0;
     if ((e = cudaFuncSetAttribute(k_stage_a_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(StageATile)))) != cudaSuccess ||
@@ -307,6 +323,10 @@ void cb200_destroy(cb200_ctx* c) {
     c->kind_alt.release(); c->reit_alt.release(); c->group_alt.release(); c->mask_alt.release(); c->label_alt.release(); c->ord_alt.release();
     c->sort_key.release(); c->src_row.release(); c->tmp_col.release();
     if (c->d_sort_cursor) cudaFree(c->d_sort_cursor);
+    if (c->d_dyn) cudaFree(c->d_dyn);
+    if (c->h_dyn) cudaFreeHost(c->h_dyn);
+    for (auto& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     c->slots.release(); c->chunk_base.release(); c->entries.release(); c->work.release(); c->work_count.release();
     c->ov_pairs.release(); c->ov_table.release(); c->ov_bits.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
@@ -614,6 +634,14 @@ static int prepare_buffers(cb200_ctx* ctx) {
 }
 
 // Front half: zero the step tables, stage A.  One device: also counts cells.  Sharded: packs records per rank.
+// The step's time and scalar end_time reach the kernels through ctx->d_dyn (set_step_dyn), not through their arguments.
+static int set_step_dyn(cb200_ctx* ctx, double time, double end_time) {
+    ctx->h_dyn->T = time;
+    ctx->h_dyn->end_scalar = end_time;
+    CU(cudaMemcpyAsync(ctx->d_dyn, ctx->h_dyn, sizeof(StepDyn), cudaMemcpyHostToDevice, ctx->stream));
+    return CB200_OK;
+}
+
 static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const double* const* nv, double end_time) {
     const uint32_t n = ctx->n;
     const GridGeom g = ctx->geom;
@@ -629,10 +657,9 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     StepArgs a{};
     a.n = n;
     a.rebase = do_rebase ? 1 : 0;
-    a.T = time;
+    a.dyn = ctx->d_dyn;
     a.cell_width = ctx->cell_width;
     a.padding = ctx->padding;
-    a.end_scalar = end_time;
     a.s = cols_of(ctx);
     a.nvx = do_rebase ? nv[0] : nullptr; a.nvy = do_rebase ? nv[1] : nullptr;
     a.nrw = do_rebase ? nv[2] : nullptr; a.nrh = do_rebase ? nv[3] : nullptr;
@@ -650,6 +677,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     a.send_count = ctx->send_count.p;
     a.slab = ctx->slab;
     a.vmap = (ctx->sharded && ctx->n_ov) ? ctx->vmap.p : nullptr;
+    a.ov_bits = ctx->ov_bits.p;
     if (n) {
         // CB200_STAGE_A=tma: full 256-row tiles through the TMA-staged kernel, the tail through the plain one (default: everything)
         const uint32_t n_tiles = ctx->stage_a_tma ? n / kThreads : 0u;
@@ -701,8 +729,8 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
         const uint32_t work = recount ? n_vis_max : ctx->slab * (uint32_t)sh.world;
         const uint32_t grid_i = std::max<uint32_t>(1, std::min<uint32_t>((work + kThreads - 1) / kThreads, ctx->sm_count * 8));
         uint32_t* vmap = use_map ? ctx->vmap.p : nullptr;
-        if (recount) k_index_visitors<true><<<grid_i, kThreads, 0, ctx->stream>>>(ctx->rec.p, ctx->bink.p, vs, ctx->d_ctr, ctx->slots.p, g, sh.col_lo, sh.col_hi, vmap);
-        else k_index_visitors<false><<<grid_i, kThreads, 0, ctx->stream>>>(ctx->rec.p, ctx->bink.p, vs, ctx->d_ctr, ctx->slots.p, g, sh.col_lo, sh.col_hi, vmap);
+        if (recount) k_index_visitors<true><<<grid_i, kThreads, 0, ctx->stream>>>(ctx->rec.p, ctx->bink.p, vs, ctx->d_ctr, ctx->slots.p, g, sh.col_lo, sh.col_hi, vmap, ctx->ov_bits.p);
+        else k_index_visitors<false><<<grid_i, kThreads, 0, ctx->stream>>>(ctx->rec.p, ctx->bink.p, vs, ctx->d_ctr, ctx->slots.p, g, sh.col_lo, sh.col_hi, vmap, ctx->ov_bits.p);
         ctx->launches += 1;
     }
     {
@@ -734,7 +762,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     sv.ov_pairs = ctx->ov_pairs.p;
     sv.n_ov = ctx->n_ov;
     sv.rec = ctx->rec.p;
-    sv.T = time;
+    sv.dyn = ctx->d_dyn;
     sv.padding = ctx->padding;
     sv.events = ctx->events.p;
     sv.cap_events = (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu);
@@ -826,6 +854,81 @@ static int fill_result(cb200_ctx* ctx, cb200_step_result* out) {
     return CB200_OK;
 }
 
+// Everything that is baked into the kernel arguments of a step: if none of it changed since a graph was captured, the graph
+// can be replayed (the step's time and scalar end_time travel through d_dyn).
+static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    auto mix = [&h](uint64_t v) {
+        for (int i = 0; i < 8; ++i) {
+            h ^= (v >> (8 * i)) & 0xff;
+            h *= 0x100000001b3ull;
+        }
+    };
+    mix(ctx->n); mix((uint64_t)ctx->geom.lw << 8 | (uint64_t)ctx->geom.lh); mix(ctx->n_ov); mix(ctx->ov_bucket_mask);
+    for (auto& b : ctx->col) mix((uint64_t)(uintptr_t)b.p);
+    const void* ptrs[] = {ctx->kind.p, ctx->reit.p, ctx->group.p, ctx->mask.p, ctx->label.p, ctx->row_of.p, ctx->rec.p, ctx->bink.p, ctx->slots.p,
+                          ctx->chunk_base.p, ctx->entries.p, ctx->work.p, ctx->work_count.p, ctx->events.p, ctx->partial.p, ctx->ov_pairs.p,
+                          ctx->ov_table.p, ctx->ov_bits.p, ctx->ids.p, ctx->collider_dirty, ctx->collider_dirty_count, nv[0], nv[1], nv[2], nv[3], nv[4]};
+    for (const void* p : ptrs) mix((uint64_t)(uintptr_t)p);
+    mix(ctx->entries.cap); mix(ctx->work.cap); mix(ctx->events.cap); mix(ctx->stage_a_tma ? 1 : 0);
+    if (const char* d = getenv("CB200_DBG_A")) mix((uint64_t)atoi(d) + 17);
+    if (const char* d = getenv("CB200_DBG_S")) mix((uint64_t)atoi(d) + 31);
+    return h ? h : 1;
+}
+
+// Replays (capturing first, if needed) the whole step — zero, stage A, scan, scatter, enumerate, solve — as ONE graph launch.
+static int launch_step_graph(cb200_ctx* ctx, double time, const double* const* nv, double end_time, bool* replayed) {
+    *replayed = false;
+    const uint64_t sig = step_signature(ctx, nv);
+    cb200_ctx::GraphSlot* slot = nullptr;
+    for (auto& g : ctx->graphs)
+        if (g.exec && g.sig == sig) slot = &g;
+    if (!slot) {
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->use_graph = false;  // (e.g. a stream that cannot be captured): plain launches from now on
+            return CB200_OK;
+        }
+        const uint64_t launches_before = ctx->launches;
+        ctx->capturing = true;
+        int rc = enqueue_front(ctx, time, true, nv, end_time);
+        if (rc == CB200_OK) rc = enqueue_back(ctx, time, false);
+        ctx->capturing = false;
+        const uint32_t n_kernels = (uint32_t)(ctx->launches - launches_before);
+        ctx->launches = launches_before;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc != CB200_OK || e != cudaSuccess || !graph) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            ctx->use_graph = false;
+            return rc;
+        }
+        slot = &ctx->graphs[ctx->graph_next];
+        ctx->graph_next = (ctx->graph_next + 1) % 4;
+        if (slot->exec) cudaGraphExecDestroy(slot->exec);
+        slot->exec = nullptr;
+        const cudaError_t ei = cudaGraphInstantiate(&slot->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) {
+            cudaGetLastError();
+            slot->exec = nullptr;
+            ctx->use_graph = false;
+            return CB200_OK;
+        }
+        slot->sig = sig;
+        ctx->graph_kernels[slot - ctx->graphs] = n_kernels;
+        ctx->graph_captures += 1;
+        if (getenv("CB200_VERBOSE")) fprintf(stderr, "[cb200] captured step graph #%llu (%u kernels), signature %016llx\n", (unsigned long long)ctx->graph_captures, n_kernels, (unsigned long long)sig);
+    }
+    CU(cudaGraphLaunch(slot->exec, ctx->stream));
+    ctx->launches += ctx->graph_kernels[slot - ctx->graphs];
+    CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
+    ctx->graph_launches += 1;
+    *replayed = true;
+    return CB200_OK;
+}
+
 int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, cb200_step_result* out) {
     if (!ctx) return CB200_E_ARG;
     if (!ctx->have_state) return fail(ctx, CB200_E_STATE, "bulk_update before upload_state");
@@ -837,11 +940,18 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
     int rc = stage_vel(ctx, vel, nv);
     if (rc != CB200_OK) return rc;
     if ((rc = prepare_buffers(ctx)) != CB200_OK) return rc;
+    if ((rc = set_step_dyn(ctx, time, end_time)) != CB200_OK) return rc;
     // A step is re-run (without the rebase) when a buffer had to grow.
     bool again = true;
     for (int attempt = 0; attempt < 4 && again; ++attempt) {
-        if ((rc = enqueue_front(ctx, time, attempt == 0, nv, end_time)) != CB200_OK) return rc;
-        if ((rc = enqueue_back(ctx, time, false)) != CB200_OK) return rc;
+        bool replayed = false;
+        if (attempt == 0 && ctx->use_graph && !ctx->stage_timing) {
+            if ((rc = launch_step_graph(ctx, time, nv, end_time, &replayed)) != CB200_OK) return rc;
+        }
+        if (!replayed) {
+            if ((rc = enqueue_front(ctx, time, attempt == 0, nv, end_time)) != CB200_OK) return rc;
+            if ((rc = enqueue_back(ctx, time, false)) != CB200_OK) return rc;
+        }
         if ((rc = complete_step(ctx, time, &again)) != CB200_OK) return rc;
         if (ctx->last.ctr.err_flags) break;
     }
@@ -905,6 +1015,7 @@ int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
     int rc = stage_vel(ctx, vel, nv);
     if (rc != CB200_OK) return rc;
     if ((rc = prepare_buffers(ctx)) != CB200_OK) return rc;
+    if ((rc = set_step_dyn(ctx, time, end_time)) != CB200_OK) return rc;
     if ((rc = enqueue_front(ctx, time, true, nv, end_time)) != CB200_OK) return rc;
     ctx->shard_phase = 1;
     ctx->shard_T = time;
@@ -1061,6 +1172,7 @@ int cb200_shard_step(cb200_ctx* ctx, double time, const cb200_vel_view* vel, dou
     ctx->p2p_step += 1;
     ctx->p2p_parity = (int)(ctx->p2p_step & 1);
     const int world = ctx->shard.world, rank = ctx->shard.rank;
+    if ((rc = set_step_dyn(ctx, time, end_time)) != CB200_OK) return rc;
     if ((rc = enqueue_front(ctx, time, true, nv, end_time)) != CB200_OK) return rc;
     if (world > 1) {
         k_push_halo<<<world - 1, 1024, 0, ctx->stream>>>(ctx->send.p, ctx->peers, world, rank, ctx->slab, ctx->p2p_parity, ctx->p2p_step);

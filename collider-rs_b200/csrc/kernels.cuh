@@ -35,10 +35,17 @@ struct ShardGeom {
     int32_t bounds[kMaxWorld + 1];
 };
 
+// The two scalars that change from step to step live in device memory, so that the kernel arguments of a step stay the same
+// and the whole step can be replayed as one CUDA graph (engine.cu).
+struct StepDyn {
+    double T, end_scalar;
+};
+
 struct StepArgs {
     uint32_t n;
     int rebase;  // 0 = re-run of binning on an already-rebased table (after a buffer grew): skip the advance
-    double T, cell_width, padding, end_scalar;
+    const StepDyn* dyn;
+    double cell_width, padding;
     StateCols s;
     const double *nvx, *nvy, *nrw, *nrh, *nend;  // optional new velocity columns (device), null = keep
     const uint32_t* label; // label[row]: rank of the row's HbId in ascending-id order (sharded: the id itself)
@@ -57,6 +64,7 @@ struct StepArgs {
     uint32_t* send_count;  // [1]
     uint32_t slab;
     uint32_t* vmap;        // gid -> record index of this step (direct-addressed; null when there are no overlapping pairs)
+    const uint32_t* ov_bits;  // one bit per gid: the hitbox has an overlap — only those are looked up through vmap
 };
 
 // Sharded visitor index space: the own records sit at their rows rec[0, n_local = n); the records
@@ -241,8 +249,9 @@ __device__ __forceinline__ HbRec stage_a_row(const StepArgs& a, const ShardGeom&
     nv.vy = nv.has_vy ? __ldg(a.nvy + o) : 0.0;
     nv.rw = nv.has_rw ? __ldg(a.nrw + o) : 0.0;
     nv.rh = nv.has_rh ? __ldg(a.nrh + o) : 0.0;
-    nv.end_time = a.nend ? __ldg(a.nend + (a.rebase ? o : i)) : a.end_scalar;
-    const uint32_t err = hb_update_core(h, a.T, a.rebase != 0, nv, a.cell_width, a.padding, a.geom);
+    const StepDyn dyn = *a.dyn;
+    nv.end_time = a.nend ? __ldg(a.nend + (a.rebase ? o : i)) : dyn.end_scalar;
+    const uint32_t err = hb_update_core(h, dyn.T, a.rebase != 0, nv, a.cell_width, a.padding, a.geom);
     if (h.binned && !(a.dbg & 1u)) {
         // cell count (sharded: only the cells inside the own strip)
         const int32_t x0 = SHARDED ? max(h.sx, sh.col_lo) : h.sx, x1 = SHARDED ? min(h.ex, sh.col_hi) : h.ex;
@@ -267,7 +276,7 @@ __device__ __forceinline__ HbRec stage_a_row(const StepArgs& a, const ShardGeom&
     // the record stays at its row; a sharded rank bins only the cells inside its own strip (above and in k_scatter)
     const HbRec rec = make_rec(h, gid);
     if (!(a.dbg & 2u)) a.bink[i] = make_int4(rec.sx, rec.sy, (int)rec.span, (int)rec.kgb);
-    if (SHARDED && a.vmap) a.vmap[gid] = i;
+    if (SHARDED && a.vmap && ((__ldg(a.ov_bits + (gid >> 5)) >> (gid & 31u)) & 1u)) a.vmap[gid] = i;
     if (SHARDED && h.binned) {
         // The record is needed by every rank whose strip intersects columns [sx, ex + 1): the extra column keeps
         // a partner that is within `padding` across a cell line (an overlapping pair whose rects do not
@@ -425,7 +434,7 @@ __global__ void k_slab_header(HbRec* send, const uint32_t* __restrict__ send_cou
 // overlapping-pair lookups.
 template <bool COUNT_OWN>
 __global__ void __launch_bounds__(kThreads) k_index_visitors(const HbRec* __restrict__ rec, int4* bink, VisSpace vs, const Counters* ctr, uint32_t* slot_count,
-                                                             GridGeom geom, int32_t col_lo, int32_t col_hi, uint32_t* vmap) {
+                                                             GridGeom geom, int32_t col_lo, int32_t col_hi, uint32_t* vmap, const uint32_t* __restrict__ ov_bits) {
     const uint32_t n_local = ctr->n_local;
     const uint32_t total = n_local + (uint32_t)vs.world * vs.slab;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -439,7 +448,7 @@ __global__ void __launch_bounds__(kThreads) k_index_visitors(const HbRec* __rest
         const int32_t x0 = max(h.sx, col_lo), x1 = min(h.ex, col_hi);
         for (int32_t x = x0; x < x1; ++x)
             for (int32_t y = h.sy; y != h.ey; ++y) atomicAdd(&slot_count[geom.slot(x, y)], 1u);
-        if (vmap && i >= n_local) vmap[h.gid] = v;  // own records were indexed by stage A
+        if (vmap && i >= n_local && ((__ldg(ov_bits + (h.gid >> 5)) >> (h.gid & 31u)) & 1u)) vmap[h.gid] = v;  // (own records: stage A)
     }
 }
 
@@ -1045,7 +1054,8 @@ struct SolveArgs {
     const uint2* ov_pairs;
     uint32_t n_ov;
     const HbRec* rec;
-    double T, padding;
+    const StepDyn* dyn;
+    double padding;
     PairEvent* events;
     uint32_t cap_events;
     Counters* ctr;
@@ -1117,6 +1127,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
         }
     };
     uint32_t pending_rounds = 0;
+    const double T = a.dyn->T;
     const uint64_t keep = l2_policy_evict_last();
     for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
         const uint32_t p = base + threadIdx.x;
@@ -1153,7 +1164,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
                     const double delay = (a.dbg & 1u) ? (A.px + B.px) : (sep ? separate_time(A, B, a.padding) : collide_time(A, B));
                     if (delay != delay) report_error(a.ctr, kFNan, gid_hi);
                     n_sep += sep;
-                    const double t = a.T + delay;
+                    const double t = T + delay;
                     if (t < kHighTime && !(a.dbg & 2u)) {
                         const uint32_t kind_bit = sep ? 0u : kCollideBit;
                         s_ev[atomicAdd(&s_n, 1u)] = PairEvent{t, gid_hi, gid_lo | kind_bit};
