@@ -111,6 +111,7 @@ struct cb200_ctx {
     uint64_t id_space = 0;
     // direct exchange over peer memory (kernels.cuh "Direct halo exchange")
     bool p2p = false;
+    bool p2p_same_process = false;  // a peer context lives in this process (tests): no graph capture between steps that wait for each other
     PeerTable peers{};
     Mailbox* d_mail = nullptr;
     void* ipc_opened[2 * kMaxWorld] = {};
@@ -638,6 +639,7 @@ static int prepare_buffers(cb200_ctx* ctx) {
 static int set_step_dyn(cb200_ctx* ctx, double time, double end_time) {
     ctx->h_dyn->T = time;
     ctx->h_dyn->end_scalar = end_time;
+    ctx->h_dyn->tag = ctx->p2p_step;
     CU(cudaMemcpyAsync(ctx->d_dyn, ctx->h_dyn, sizeof(StepDyn), cudaMemcpyHostToDevice, ctx->stream));
     return CB200_OK;
 }
@@ -854,6 +856,25 @@ static int fill_result(cb200_ctx* ctx, cb200_step_result* out) {
     return CB200_OK;
 }
 
+// The kernels of one step of a direct-exchange rank: front half, halo push / wait, back half, key push / reduce.
+static int enqueue_direct_step(cb200_ctx* ctx, double time, const double* const* nv, double end_time) {
+    const int world = ctx->shard.world, rank = ctx->shard.rank;
+    int rc = enqueue_front(ctx, time, true, nv, end_time);
+    if (rc != CB200_OK) return rc;
+    if (world > 1) {
+        k_push_halo<<<world - 1, 1024, 0, ctx->stream>>>(ctx->send.p, ctx->peers, world, rank, ctx->slab, ctx->p2p_parity, ctx->d_dyn);
+        k_wait_flags<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_mail->flag_halo, world, rank, ctx->d_dyn);
+        ctx->launches += 2;
+    }
+    if ((rc = enqueue_back(ctx, time, false)) != CB200_OK) return rc;
+    k_push_key<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_key, ctx->d_ctr, ctx->work_count.p, (uint32_t)std::min<size_t>(ctx->work.cap / kWorkLists, 0x7fffffffu),
+                                                 (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu), (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu),
+                                                 ctx->peers, ctx->d_mail, world, rank, ctx->p2p_parity, ctx->d_dyn);
+    k_reduce_keys<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_mail, world, rank, ctx->p2p_parity, ctx->d_dyn, ctx->d_gkey);
+    ctx->launches += 2;
+    return CB200_OK;
+}
+
 // Everything that is baked into the kernel arguments of a step: if none of it changed since a graph was captured, the graph
 // can be replayed (the step's time and scalar end_time travel through d_dyn).
 static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
@@ -871,6 +892,16 @@ static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
                           ctx->ov_table.p, ctx->ov_bits.p, ctx->ids.p, ctx->collider_dirty, ctx->collider_dirty_count, nv[0], nv[1], nv[2], nv[3], nv[4]};
     for (const void* p : ptrs) mix((uint64_t)(uintptr_t)p);
     mix(ctx->entries.cap); mix(ctx->work.cap); mix(ctx->events.cap); mix(ctx->stage_a_tma ? 1 : 0);
+    if (ctx->sharded) {
+        mix(0x5aa5); mix((uint64_t)ctx->p2p_parity); mix(ctx->slab); mix((uint64_t)ctx->shard.world << 8 | (uint64_t)ctx->shard.rank);
+        const void* sp[] = {ctx->ord.p, ctx->send.p, ctx->send_count.p, ctx->vmap.p, ctx->d_mail, ctx->d_key, ctx->d_gkey};
+        for (const void* q : sp) mix((uint64_t)(uintptr_t)q);
+        for (int d = 0; d < ctx->shard.world; ++d) {
+            mix((uint64_t)(uintptr_t)ctx->peers.recv[d]);
+            mix((uint64_t)(uintptr_t)ctx->peers.mail[d]);
+            mix((uint64_t)(uint32_t)ctx->shard.bounds[d]);
+        }
+    }
     if (const char* d = getenv("CB200_DBG_A")) mix((uint64_t)atoi(d) + 17);
     if (const char* d = getenv("CB200_DBG_S")) mix((uint64_t)atoi(d) + 31);
     return h ? h : 1;
@@ -892,8 +923,13 @@ static int launch_step_graph(cb200_ctx* ctx, double time, const double* const* n
         }
         const uint64_t launches_before = ctx->launches;
         ctx->capturing = true;
-        int rc = enqueue_front(ctx, time, true, nv, end_time);
-        if (rc == CB200_OK) rc = enqueue_back(ctx, time, false);
+        int rc;
+        if (ctx->sharded) {
+            rc = enqueue_direct_step(ctx, time, nv, end_time);
+        } else {
+            rc = enqueue_front(ctx, time, true, nv, end_time);
+            if (rc == CB200_OK) rc = enqueue_back(ctx, time, false);
+        }
         ctx->capturing = false;
         const uint32_t n_kernels = (uint32_t)(ctx->launches - launches_before);
         ctx->launches = launches_before;
@@ -1105,6 +1141,7 @@ int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world 
     for (int i = 0; i < ctx->n_ipc_opened; ++i) cudaIpcCloseMemHandle(ctx->ipc_opened[i]);
     ctx->n_ipc_opened = 0;
     const int world = ctx->shard.world, rank = ctx->shard.rank;
+    ctx->p2p_same_process = false;
     PeerTable pt{};
     for (int d = 0; d < world; ++d) {
         if (infos[d].slab_records != ctx->slab) return fail(ctx, CB200_E_ARG, "peers must use the same halo slab size (cb200_shard_set_slab)");
@@ -1116,6 +1153,7 @@ int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world 
         char* rec_base = nullptr;
         Mailbox* mail = nullptr;
         if (infos[d].pid == (uint64_t)getpid()) {
+            ctx->p2p_same_process = true;
             // same process (several contexts of one host, e.g. the tests): the peer's pointers are valid here
             rec_base = (char*)(uintptr_t)infos[d].rec_ptr;
             mail = (Mailbox*)(uintptr_t)infos[d].mail_ptr;
@@ -1171,21 +1209,14 @@ int cb200_shard_step(cb200_ctx* ctx, double time, const cb200_vel_view* vel, dou
     if ((rc = prepare_buffers(ctx)) != CB200_OK) return rc;
     ctx->p2p_step += 1;
     ctx->p2p_parity = (int)(ctx->p2p_step & 1);
-    const int world = ctx->shard.world, rank = ctx->shard.rank;
     if ((rc = set_step_dyn(ctx, time, end_time)) != CB200_OK) return rc;
-    if ((rc = enqueue_front(ctx, time, true, nv, end_time)) != CB200_OK) return rc;
-    if (world > 1) {
-        k_push_halo<<<world - 1, 1024, 0, ctx->stream>>>(ctx->send.p, ctx->peers, world, rank, ctx->slab, ctx->p2p_parity, ctx->p2p_step);
-        k_wait_flags<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_mail->flag_halo, world, rank, ctx->p2p_step);
-        ctx->launches += 2;
-    }
     ctx->shard_T = time;
-    if ((rc = enqueue_back(ctx, time, false)) != CB200_OK) return rc;
-    k_push_key<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_key, ctx->d_ctr, ctx->work_count.p, (uint32_t)std::min<size_t>(ctx->work.cap / kWorkLists, 0x7fffffffu),
-                                                 (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu), (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu),
-                                                 ctx->peers, ctx->d_mail, world, rank, ctx->p2p_parity, ctx->p2p_step);
-    k_reduce_keys<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_mail, world, rank, ctx->p2p_parity, ctx->p2p_step, ctx->d_gkey);
-    ctx->launches += 2;
+    bool replayed = false;
+    // (graph instantiation may synchronise the device: not while a peer context of this very process is waiting in a kernel)
+    if (ctx->use_graph && !ctx->stage_timing && !ctx->p2p_same_process) {
+        if ((rc = launch_step_graph(ctx, time, nv, end_time, &replayed)) != CB200_OK) return rc;
+    }
+    if (!replayed && (rc = enqueue_direct_step(ctx, time, nv, end_time)) != CB200_OK) return rc;
     CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
     ctx->shard_phase = 2;
     return CB200_OK;

@@ -39,6 +39,7 @@ struct ShardGeom {
 // and the whole step can be replayed as one CUDA graph (engine.cu).
 struct StepDyn {
     double T, end_scalar;
+    unsigned long long tag;  // direct exchange: the step number the flags of this step carry
 };
 
 struct StepArgs {
@@ -473,7 +474,8 @@ struct PeerTable {
 };
 
 __global__ void __launch_bounds__(1024) k_push_halo(const HbRec* __restrict__ send, PeerTable peers, int world, int rank, uint32_t slab, int parity,
-                                                    unsigned long long tag) {
+                                                    const StepDyn* dyn) {
+    const unsigned long long tag = dyn->tag;
     const int d = blockIdx.x + (blockIdx.x >= (unsigned)rank ? 1 : 0);  // blocks enumerate the peers
     if (d >= world) return;
     const uint32_t count = min(*reinterpret_cast<const unsigned int*>(send), slab - 1u);
@@ -488,14 +490,16 @@ __global__ void __launch_bounds__(1024) k_push_halo(const HbRec* __restrict__ se
         __threadfence_system();
     }
 }
-__global__ void k_wait_flags(const unsigned long long* flags, int world, int rank, unsigned long long tag) {
+__global__ void k_wait_flags(const unsigned long long* flags, int world, int rank, const StepDyn* dyn) {
+    const unsigned long long tag = dyn->tag;
     const int d = threadIdx.x;
     if (d >= world || d == rank) return;
     while (*reinterpret_cast<const volatile unsigned long long*>(flags + d) < tag) __nanosleep(100);
     __threadfence_system();
 }
 __global__ void k_push_key(const MinKey* __restrict__ local_key, const Counters* ctr, const uint32_t* work_count, uint32_t seg_cap, uint32_t cap_entries,
-                           uint32_t cap_events, PeerTable peers, Mailbox* own, int world, int rank, int parity, unsigned long long tag) {
+                           uint32_t cap_events, PeerTable peers, Mailbox* own, int world, int rank, int parity, const StepDyn* dyn) {
+    const unsigned long long tag = dyn->tag;
     const int d = threadIdx.x;
     if (d >= world) return;
     // complete = no buffer of this rank overflowed in this step (else the step is re-run and the keys exchanged again)
@@ -517,8 +521,9 @@ __global__ void k_push_key(const MinKey* __restrict__ local_key, const Counters*
 struct GlobalKey {
     unsigned long long t, tie, complete, tag;
 };
-__global__ void k_reduce_keys(const Mailbox* own, int world, int rank, int parity, unsigned long long tag, GlobalKey* out /* mapped host */) {
+__global__ void k_reduce_keys(const Mailbox* own, int world, int rank, int parity, const StepDyn* dyn, GlobalKey* out /* mapped host */) {
     __shared__ unsigned long long s_t[kMaxWorld], s_tie[kMaxWorld], s_ok[kMaxWorld];
+    const unsigned long long tag = dyn->tag;
     const int d = threadIdx.x;
     if (d < world) {
         if (d != rank)

@@ -130,9 +130,12 @@ class ShardedEngine:
         self.device = torch.device("cuda", device_index)
         self.eng = cb.Engine(cell_width, padding, device=device_index)
         self.eng.shard_configure(exchange.rank, exchange.world, bounds, id_space)
-        self.eng.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._bufs = None
         self.want_direct, self.direct = direct, False
+        # The collective exchange is stream-ordered with the step on torch's current stream.  The direct exchange has no
+        # collective in the step, so the engine keeps its own stream (which it can capture into a CUDA graph).
+        if not direct:
+            self.eng.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     def upload_state(self, **cols):
         self.eng.upload_state(**cols)
@@ -153,6 +156,10 @@ class ShardedEngine:
             oks = [None] * self.ex.world
             self.ex.dist.all_gather_object(oks, ok, group=self.ex.group)
             self.direct = all(oks)
+            if not self.direct:
+                import torch
+
+                self.eng.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     def set_overlaps(self, a, b):
         self.eng.set_overlaps(a, b)
