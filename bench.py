@@ -301,9 +301,9 @@ def _main(out):
         stage_ms.setdefault("exchange", 0.0)
         alg = {
             "pre": 4.0 * n_slots,                              # k_step_zero
-            "stage_a": 246.0 * n + 8.0 * E,
+            "stage_a": 262.0 * n + 8.0 * E,
             "scan": 8.0 * n_slots,
-            "scatter": 32.0 * n + 16.0 * E,
+            "scatter": 16.0 * n + 16.0 * E,
             "candidates": 8.0 * E + 16.0 * W,                  # k_enum_pairs
             "solve": 208.0 * W + 200.0 * Q + 16.0 * V,         # test + solve + events
         }
