@@ -123,6 +123,7 @@ def _bind(L):
     L.cb200_collider_next.argtypes = [vp, C.POINTER(i32), C.POINTER(u32), C.POINTER(u64), C.POINTER(u64)]
     L.cb200_collider_get_hitbox.argtypes = [vp, u64, C.POINTER(HitboxC)]
     L.cb200_collider_add_hitbox.argtypes = [vp, C.POINTER(ProfileC), C.POINTER(HitboxC), vp, u64, C.POINTER(u64)]
+    L.cb200_collider_add_hitboxes.argtypes = [vp, u64, C.POINTER(ProfileC), C.POINTER(HitboxC), vp, vp, u64, C.POINTER(u64)]
     L.cb200_collider_set_hitbox_vel.argtypes = [vp, u64, dbl, dbl, dbl, dbl, dbl]
     L.cb200_collider_remove_hitbox.argtypes = [vp, u64, vp, u64, C.POINTER(u64)]
     L.cb200_collider_get_overlaps.argtypes = [vp, u64, vp, u64, C.POINTER(u64)]
@@ -212,6 +213,33 @@ class Collider:
         if n.value <= out.size:
             return [int(x) for x in out[: n.value]]
         return self.get_overlaps(id)
+
+    def add_hitboxes(self, scene: dict, end_time=INF):
+        """Batched add_hitbox over a scene dict (id, pos_x, pos_y, dim_x, dim_y, vel_x, vel_y, kind[, rsz_x, rsz_y, group,
+        interact_mask]); returns the immediately overlapping pairs as two id arrays (later-added id, earlier id)."""
+        n = len(scene["id"])
+        z = np.zeros(n)
+        profs = (ProfileC * n)()
+        hbs = (HitboxC * n)()
+        group = scene.get("group", np.zeros(n, np.uint32))
+        mask = scene.get("interact_mask", np.ones(n, np.uint32))
+        rx, ry = scene.get("rsz_x", z), scene.get("rsz_y", z)
+        et = np.broadcast_to(np.asarray(end_time, dtype=np.float64), (n,))
+        for i in range(n):
+            profs[i] = ProfileC(int(scene["id"][i]), int(group[i]), int(mask[i]))
+            hbs[i] = HitboxC(scene["pos_x"][i], scene["pos_y"][i], scene["dim_x"][i], scene["dim_y"][i], scene["vel_x"][i], scene["vel_y"][i],
+                             rx[i], ry[i], et[i], int(scene["kind"][i]), 0)
+        cap = 1024
+        while True:
+            a = np.zeros(cap, dtype=np.uint64)
+            b = np.zeros(cap, dtype=np.uint64)
+            m = C.c_uint64()
+            self._check(self._L.cb200_collider_add_hitboxes(self._h, n, profs, hbs, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), cap, C.byref(m)))
+            if m.value <= cap:
+                return a[: m.value], b[: m.value]
+            # the hitboxes are in; only the pair list was cut short: read it back from the overlap sets
+            pairs = [(i, j) for i in scene["id"] for j in self.get_overlaps(int(i)) if j < i]
+            return np.array([p[0] for p in pairs], dtype=np.uint64), np.array([p[1] for p in pairs], dtype=np.uint64)
 
     def set_hitbox_vel(self, id, vel):
         self._check(self._L.cb200_collider_set_hitbox_vel(self._h, id, vel.vx, vel.vy, vel.rw, vel.rh, vel.end_time))

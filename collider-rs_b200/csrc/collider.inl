@@ -698,6 +698,167 @@ int cb200_collider_add_hitbox(cb200_collider* c, const cb200_profile* profile, c
     return CB200_OK;
 }
 
+// Batched add_hitbox: exactly `for k in ascending id: add_hitbox(profiles[k], hitboxes[k])` at the current time
+// (collider.rs:214-222), as ONE device pass when the collider is empty — the table is uploaded and an add-mode step
+// (SolveArgs.add_mode) bins it, finds the candidate pairs, reports the pairs that overlap immediately and queues Separate /
+// Collide / Reiterate events.  A non-empty collider takes the hitboxes one by one.  pair_a[k] was added after pair_b[k].
+int cb200_collider_add_hitboxes(cb200_collider* c, uint64_t n, const cb200_profile* profiles, const cb200_hitbox* hitboxes, uint64_t* pair_a,
+                                uint64_t* pair_b, uint64_t cap_pairs, uint64_t* n_pairs) {
+    if (!c || (n && (!profiles || !hitboxes))) return CB200_E_ARG;
+    if (n_pairs) *n_pairs = 0;
+    if (n == 0) return CB200_OK;
+    cb200_ctx* x = c->ctx;
+    cudaSetDevice(x->device);
+    std::vector<uint32_t> order(n);
+    for (uint64_t k = 0; k < n; ++k) order[k] = (uint32_t)k;
+    std::sort(order.begin(), order.end(), [&](uint32_t p, uint32_t q) { return profiles[p].id < profiles[q].id; });
+    for (uint64_t k = 1; k < n; ++k)
+        if (profiles[order[k - 1]].id == profiles[order[k]].id) return cfail(c, CB200_E_CONTRACT, "assertion failed: self.hitboxes.insert(id, info).is_none()");
+    uint64_t n_out = 0;
+    if (!c->infos.empty() || c->can_interact || x->sharded || n >= 0x7ffffff0ull) {
+        // one by one (also when a can_interact callback must see every candidate before an event exists)
+        std::vector<uint64_t> ov(64);
+        for (uint64_t k = 0; k < n; ++k) {
+            uint64_t m = 0;
+            int rc = cb200_collider_add_hitbox(c, &profiles[order[k]], &hitboxes[order[k]], ov.data(), ov.size(), &m);
+            if (rc != CB200_OK) return rc;
+            if (m > ov.size()) {
+                ov.resize(m);
+                if ((rc = cb200_collider_get_overlaps(c, profiles[order[k]].id, ov.data(), ov.size(), &m)) != CB200_OK) return rc;
+            }
+            for (uint64_t j = 0; j < m; ++j, ++n_out)
+                if (n_out < cap_pairs) {
+                    if (pair_a) pair_a[n_out] = profiles[order[k]].id;
+                    if (pair_b) pair_b[n_out] = ov[j];
+                }
+        }
+        if (n_pairs) *n_pairs = n_out;
+        return CB200_OK;
+    }
+    // ---- empty collider: upload + one add-mode step ----
+    for (uint64_t k = 0; k < n; ++k) {
+        const cb200_profile& p = profiles[k];
+        const cb200_hitbox& h = hitboxes[k];
+        if (p.group != CB200_GROUP_NONE && p.group > 31) return cfail(c, CB200_E_ARG, "group must be 0..31 or CB200_GROUP_NONE");
+        if (h.kind > 1) return cfail(c, CB200_E_ARG, "bad shape kind");
+        if (!(h.dim_x >= 0.0 && h.dim_y >= 0.0)) return cfail(c, CB200_E_CONTRACT, "dims must be non-negative");
+        if (h.kind == CB200_KIND_CIRCLE && !(h.dim_x == h.dim_y)) return cfail(c, CB200_E_CONTRACT, "circle width must equal height");
+    }
+    int rc = ensure_capacity(c, n, n);
+    if (rc != CB200_OK) return rc;
+    {
+        std::vector<double> col(n);
+        auto put = [&](int k, auto get) -> int {
+            for (uint64_t i = 0; i < n; ++i) col[i] = get(hitboxes[order[i]]);
+            CCU(cudaMemcpy(x->col[k].p, col.data(), n * 8, cudaMemcpyHostToDevice));
+            return CB200_OK;
+        };
+        const double T = c->time;
+        if ((rc = put(0, [](const cb200_hitbox& h) { return h.pos_x; })) != CB200_OK || (rc = put(1, [](const cb200_hitbox& h) { return h.pos_y; })) != CB200_OK ||
+            (rc = put(2, [](const cb200_hitbox& h) { return h.dim_x; })) != CB200_OK || (rc = put(3, [](const cb200_hitbox& h) { return h.dim_y; })) != CB200_OK ||
+            (rc = put(4, [](const cb200_hitbox& h) { return h.vel_x; })) != CB200_OK || (rc = put(5, [](const cb200_hitbox& h) { return h.vel_y; })) != CB200_OK ||
+            (rc = put(6, [](const cb200_hitbox& h) { return h.rsz_x; })) != CB200_OK || (rc = put(7, [](const cb200_hitbox& h) { return h.rsz_y; })) != CB200_OK ||
+            (rc = put(8, [T](const cb200_hitbox&) { return T; })) != CB200_OK || (rc = put(9, [](const cb200_hitbox& h) { return h.end_time; })) != CB200_OK ||
+            (rc = put(10, [](const cb200_hitbox& h) { return h.end_time; })) != CB200_OK)
+            return rc;
+        std::vector<uint8_t> kind(n);
+        std::vector<uint32_t> group(n), mask(n);
+        for (uint64_t i = 0; i < n; ++i) {
+            kind[i] = (uint8_t)hitboxes[order[i]].kind;
+            group[i] = profiles[order[i]].group;
+            mask[i] = profiles[order[i]].interact_mask;
+        }
+        CCU(cudaMemcpy(x->kind.p, kind.data(), n, cudaMemcpyHostToDevice));
+        CCU(cudaMemcpy(x->group.p, group.data(), n * 4, cudaMemcpyHostToDevice));
+        CCU(cudaMemcpy(x->mask.p, mask.data(), n * 4, cudaMemcpyHostToDevice));
+        CCU(cudaMemset(x->reit.p, 0, n));
+        k_iota_rows<<<((uint32_t)n + kThreads - 1) / kThreads, kThreads, 0, x->stream>>>((uint32_t)n, x->label.p, x->row_of.p);
+    }
+    x->n = (uint32_t)n;
+    x->have_state = true;
+    x->need_resort = true;
+    x->steps_since_resort = 0;
+    x->n_ov = 0;
+    x->ov_bucket_mask = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const cb200_profile& p = profiles[order[i]];
+        c->infos[p.id] = cb200_collider::Info{(uint32_t)i, p.group, p.interact_mask, {}, {}};
+        c->by_id[p.id] = (uint32_t)i;
+        c->id_of_label[i] = p.id;
+    }
+    CCU(x->ids.reserve(n));
+    CCU(cudaMemcpy(x->ids.p, c->id_of_label.data(), n * 8, cudaMemcpyHostToDevice));
+    c->ids_dirty = false;
+    collider_geom(c);
+    x->collider_dirty = c->dirty.p;
+    x->collider_dirty_count = c->d_dirty_count;
+    // the add-mode step: like a re-run of a bulk step (no rebase; the user end_time is read from the stored column)
+    if (!x->d_n_imm) CCU(cudaMalloc(&x->d_n_imm, 8));
+    if (x->imm_pairs.cap == 0) CCU(x->imm_pairs.reserve(n / 4 + 1024));
+    if ((rc = prepare_buffers(x)) != CB200_OK) return cfail(c, rc, x->err);
+    if ((rc = set_step_dyn(x, c->time, INFINITY)) != CB200_OK) return cfail(c, rc, x->err);
+    const double* nv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    x->add_mode = true;
+    bool again = true;
+    unsigned long long n_imm = 0;
+    for (int attempt = 0; attempt < 5 && again; ++attempt) {
+        CCU(cudaMemsetAsync(x->d_n_imm, 0, 8, x->stream));
+        CCU(cudaEventRecord(x->ev_t[ST_PRE], x->stream));
+        if ((rc = enqueue_front(x, c->time, false, nv, INFINITY)) != CB200_OK || (rc = enqueue_back(x, c->time, false)) != CB200_OK ||
+            (rc = complete_step(x, c->time, &again)) != CB200_OK) {
+            x->add_mode = false;
+            return cfail(c, rc, x->err);
+        }
+        CCU(cudaMemcpy(&n_imm, x->d_n_imm, 8, cudaMemcpyDeviceToHost));
+        if (n_imm > x->imm_pairs.cap) {
+            CCU(x->imm_pairs.reserve(n_imm + n_imm / 4));
+            again = true;
+        }
+        if (x->last.ctr.err_flags) break;
+    }
+    x->add_mode = false;
+    cb200_step_result res;
+    if ((rc = fill_result(x, &res)) != CB200_OK) {
+        // a contract failure (e.g. a shape smaller than the padding): nothing was added
+        const std::string msg = x->err;
+        c->infos.clear();
+        c->by_id.clear();
+        std::fill(c->id_of_label.begin(), c->id_of_label.end(), UINT64_MAX);
+        x->n = 0;
+        x->have_step = false;
+        return cfail(c, rc, msg);
+    }
+    if (again) return cfail(c, CB200_E_STATE, "step buffers failed to converge");
+    if ((rc = sort_events(x)) != CB200_OK) return cfail(c, rc, x->err);
+    // immediate overlaps (collider.rs:355-365)
+    std::vector<uint2> imm(n_imm);
+    if (n_imm) CCU(cudaMemcpy(imm.data(), x->imm_pairs.p, n_imm * sizeof(uint2), cudaMemcpyDeviceToHost));
+    std::sort(imm.begin(), imm.end(), [](const uint2& p, const uint2& q) { return p.x < q.x || (p.x == q.x && p.y < q.y); });
+    for (const uint2& pr : imm) {
+        const uint64_t a_id = c->id_of_label[pr.x], b_id = c->id_of_label[pr.y];
+        overlap_insert(c->infos[a_id].overlaps, b_id);
+        overlap_insert(c->infos[b_id].overlaps, a_id);
+        if (n_out < cap_pairs) {
+            if (pair_a) pair_a[n_out] = a_id;
+            if (pair_b) pair_b[n_out] = b_id;
+        }
+        ++n_out;
+    }
+    if (n_pairs) *n_pairs = n_out;
+    c->overlaps_dirty = true;
+    // the queue is the device-sorted run
+    c->overlay.clear();
+    std::fill(c->cleared.begin(), c->cleared.end(), 0);
+    c->base.clear();
+    c->base_off = c->base_cur = 0;
+    c->base_total = res.n_events;
+    c->base_on_host = false;
+    c->next_index += res.n_events;
+    c->have_grid = true;
+    c->n_dirty = 0;
+    return CB200_OK;
+}
+
 int cb200_collider_set_hitbox_vel(cb200_collider* c, uint64_t id, double vel_x, double vel_y, double rsz_x, double rsz_y, double end_time) {
     if (!c) return CB200_E_ARG;  // collider.rs:225-229
     cudaSetDevice(c->ctx->device);

@@ -96,6 +96,10 @@ struct cb200_ctx {
     GraphSlot graphs[4];
     int graph_next = 0;
     bool capturing = false;
+    // add mode of the step (collider.inl add_hitboxes): see SolveArgs
+    bool add_mode = false, last_add_mode = false;
+    DevBuf<uint2> imm_pairs;
+    unsigned long long* d_n_imm = nullptr;
     uint32_t graph_kernels[4] = {};  // kernels inside each captured graph (for the launch counter)
     uint64_t graph_launches = 0, graph_captures = 0;
     bool stage_a_tma = false;  // CB200_STAGE_A=tma: input columns staged through shared memory by bulk async copies (measured slower, kept for A/B)
@@ -331,7 +335,7 @@ void cb200_destroy(cb200_ctx* c) {
     c->slots.release(); c->chunk_base.release(); c->entries.release(); c->work.release(); c->work_count.release();
     c->ov_pairs.release(); c->ov_table.release(); c->ov_bits.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
-    c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); for (auto& b : c->bs_tab) b.release(); c->ev_out.release();
+    c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); for (auto& b : c->bs_tab) b.release(); c->imm_pairs.release(); if (c->d_n_imm) cudaFree(c->d_n_imm); c->ev_out.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->d_key) cudaFree(c->d_key);
     for (int i = 0; i < c->n_ipc_opened; ++i) cudaIpcCloseMemHandle(c->ipc_opened[i]);
@@ -778,6 +782,10 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     sv.sharded = ctx->sharded ? 1 : 0;
     sv.ids = ctx->sharded ? nullptr : ctx->ids.p;
     sv.dbg = getenv("CB200_DBG_S") ? (uint32_t)atoi(getenv("CB200_DBG_S")) : 0u;
+    sv.add_mode = ctx->add_mode ? 1 : 0;
+    sv.imm_pairs = ctx->imm_pairs.p;
+    sv.n_imm = ctx->d_n_imm;
+    sv.cap_imm = (uint32_t)std::min<size_t>(ctx->imm_pairs.cap, 0xffffffffu);
     sv.vs = vs;
     sv.col_lo = sh.col_lo;
     sv.col_hi = sh.col_hi;
@@ -793,6 +801,7 @@ static int complete_step(cb200_ctx* ctx, double time, bool* again) {
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     ctx->last = *ctx->h_res;
+    ctx->last_add_mode = ctx->add_mode;
     ctx->last_T = time;
     ctx->have_step = true;
     ctx->ev_sorted = false;
@@ -831,7 +840,8 @@ static int fill_result(cb200_ctx* ctx, cb200_step_result* out) {
         out->next_time = r.next_time;
         out->next_event.time = r.next_time;
         if (r.next_tie != kKeyMax) {
-            out->next_event.kind = !(r.next_tie & kPairClass) ? CB200_EV_REITERATE : ((r.next_tie & kCollideBit) ? CB200_EV_COLLIDE : CB200_EV_SEPARATE);
+            const bool collide = ctx->last_add_mode ? (r.next_tie & 1ull) != 0 : (r.next_tie & kCollideBit) != 0;
+            out->next_event.kind = !(r.next_tie & kPairClass) ? CB200_EV_REITERATE : (collide ? CB200_EV_COLLIDE : CB200_EV_SEPARATE);
             out->next_event.a = r.next_id_a;  // (resolved label -> id by the last block of k_solve)
             out->next_event.b = r.next_id_b;
         }
@@ -1352,7 +1362,7 @@ static int sort_events(cb200_ctx* ctx) {
             std::swap(in, outp);
         }
     }
-    k_decode_events<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(nt, in, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p);
+    k_decode_events<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(nt, in, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p, ctx->last_add_mode ? 1 : 0);
     ctx->launches += 1;
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());

@@ -1076,6 +1076,13 @@ struct SolveArgs {
     int32_t col_lo, col_hi;
     const uint64_t* ids;     // label -> HbId (null: the label is the id)
     uint32_t dbg;            // timing experiments only (CB200_DBG_S): 1 skip the narrowphase, 2 skip the event append, 4 skip the candidate test
+    // add mode (batched Collider::add_hitbox, collider.rs:214-222 + 355-365): a candidate whose collide delay is exactly 0.0
+    // overlaps NOW — its pair is reported in imm_pairs and its event is the Separate; simultaneous events of one hitbox are
+    // ordered by partner id alone (they were created in one ascending loop), so the kind bit sits below the partner label
+    int add_mode;
+    uint2* imm_pairs;        // (gid hi, gid lo)
+    unsigned long long* n_imm;
+    uint32_t cap_imm;
 };
 
 // A map entry is trusted only if it names a record slot that is live in THIS step and that record carries the gid.
@@ -1166,14 +1173,22 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
                     // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486): advanced by T - start = 0
                     const DurHb B = advanced(pick(a_is_hi, db, da), 0.0);
                     const uint32_t gid_hi = a_is_hi ? ha.gid : hb.gid, gid_lo = a_is_hi ? hb.gid : ha.gid;
-                    const double delay = (a.dbg & 1u) ? (A.px + B.px) : (sep ? separate_time(A, B, a.padding) : collide_time(A, B));
+                    double delay = (a.dbg & 1u) ? (A.px + B.px) : (sep ? separate_time(A, B, a.padding) : collide_time(A, B));
+                    bool is_sep = sep;
+                    if (a.add_mode && !sep && delay == 0.0) {
+                        // immediate overlap: process_collision (collider.rs:177-197) queues the Separate
+                        const unsigned long long at = atomicAdd(a.n_imm, 1ull);
+                        if (at < a.cap_imm) a.imm_pairs[at] = make_uint2(gid_hi, gid_lo);
+                        delay = separate_time(A, B, a.padding);
+                        is_sep = true;
+                    }
                     if (delay != delay) report_error(a.ctr, kFNan, gid_hi);
                     n_sep += sep;
                     const double t = T + delay;
                     if (t < kHighTime && !(a.dbg & 2u)) {
-                        const uint32_t kind_bit = sep ? 0u : kCollideBit;
-                        s_ev[atomicAdd(&s_n, 1u)] = PairEvent{t, gid_hi, gid_lo | kind_bit};
-                        const MinKey k{time_key(t), kPairClass | ((uint64_t)gid_hi << 32) | kind_bit | gid_lo};
+                        const uint32_t low = a.add_mode ? ((gid_lo << 1) | (is_sep ? 0u : 1u)) : (gid_lo | (is_sep ? 0u : kCollideBit));
+                        s_ev[atomicAdd(&s_n, 1u)] = PairEvent{t, gid_hi, low};
+                        const MinKey k{time_key(t), kPairClass | ((uint64_t)gid_hi << 32) | low};
                         if (key_less(k, best)) best = k;
                     }
                 }
@@ -1212,7 +1227,8 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
         a.result->next_tie = best.tie;
         {
             const bool pair = (best.tie & kPairClass) != 0;
-            const uint32_t la = pair ? (uint32_t)((best.tie >> 32) & 0x7fffffffu) : (uint32_t)best.tie, lb = (uint32_t)(best.tie & 0x7fffffffu);
+            const uint32_t la = pair ? (uint32_t)((best.tie >> 32) & 0x7fffffffu) : (uint32_t)best.tie;
+            const uint32_t lb = a.add_mode ? (uint32_t)((best.tie & 0xffffffffu) >> 1) : (uint32_t)(best.tie & 0x7fffffffu);
             const bool any = !(best.t == kKeyMax && best.tie == kKeyMax);
             a.result->next_id_a = !any ? 0ull : (a.ids ? a.ids[la] : (uint64_t)la);
             a.result->next_id_b = !any || !pair ? 0ull : (a.ids ? a.ids[lb] : (uint64_t)lb);

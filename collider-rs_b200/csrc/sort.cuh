@@ -321,7 +321,7 @@ struct EventOut {
     uint64_t a, b;
     uint32_t kind, pad;
 };
-__global__ void k_decode_events(uint32_t n, const Key128* __restrict__ keys, const uint64_t* __restrict__ ids, EventOut* out) {
+__global__ void k_decode_events(uint32_t n, const Key128* __restrict__ keys, const uint64_t* __restrict__ ids, EventOut* out, int add_mode) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Key128 k = keys[i];
@@ -329,10 +329,11 @@ __global__ void k_decode_events(uint32_t n, const Key128* __restrict__ keys, con
     e.time = key_time(k.hi);
     e.pad = 0;
     if (k.lo & kPairClass) {
-        const uint32_t hi = (uint32_t)((k.lo >> 32) & 0x7fffffffu), lo = (uint32_t)(k.lo & 0x7fffffffu);
+        const uint32_t hi = (uint32_t)((k.lo >> 32) & 0x7fffffffu);
+        const uint32_t lo = add_mode ? (uint32_t)((k.lo & 0xffffffffu) >> 1) : (uint32_t)(k.lo & 0x7fffffffu);
         e.a = ids ? ids[hi] : hi;
         e.b = ids ? ids[lo] : lo;
-        e.kind = (k.lo & kCollideBit) ? 1u : 2u;  // CB200_EV_COLLIDE / CB200_EV_SEPARATE
+        e.kind = (add_mode ? (k.lo & 1ull) : (k.lo & kCollideBit)) ? 1u : 2u;  // CB200_EV_COLLIDE / CB200_EV_SEPARATE
     } else {
         e.a = ids ? ids[(uint32_t)k.lo] : (uint32_t)k.lo;
         e.b = 0;

@@ -286,6 +286,11 @@ int cb200_collider_get_hitbox(cb200_collider* c, uint64_t id, cb200_hitbox* out)
 /* add_hitbox :214-222 — ids of the hitboxes the new one overlaps immediately (ascending), at most `cap` written, *n_out = count */
 int cb200_collider_add_hitbox(cb200_collider* c, const cb200_profile* profile, const cb200_hitbox* hitbox, uint64_t* overlaps, uint64_t cap,
                               uint64_t* n_out);
+/* Batched add_hitbox: the same as calling add_hitbox for every entry in ascending id order at the current time; on an
+ * empty collider it is one device pass (upload + an add-mode step).  (pair_a[k], pair_b[k]): pair_a[k] overlapped
+ * pair_b[k] the moment it was added (pair_a[k] > pair_b[k]); at most cap_pairs written, *n_pairs = count. */
+int cb200_collider_add_hitboxes(cb200_collider* c, uint64_t n, const cb200_profile* profiles, const cb200_hitbox* hitboxes, uint64_t* pair_a,
+                                uint64_t* pair_b, uint64_t cap_pairs, uint64_t* n_pairs);
 int cb200_collider_set_hitbox_vel(cb200_collider* c, uint64_t id, double vel_x, double vel_y, double rsz_x, double rsz_y,
                                   double end_time);                                           /* set_hitbox_vel     :225-229 */
 int cb200_collider_remove_hitbox(cb200_collider* c, uint64_t id, uint64_t* overlaps, uint64_t cap, uint64_t* n_out); /* :256-275 */

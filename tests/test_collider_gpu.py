@@ -449,3 +449,34 @@ def test_cpp_wrapper_runs_the_reference_tests(tmp_path):
                     "-Wl,-rpath," + libdir], check=True, capture_output=True)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "host_collider_check ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_batched_add_equals_sequential_adds(oracle):
+    """cb200_collider_add_hitboxes on an empty collider (one device pass) against the oracle's add_hitbox loop: the same
+    immediate overlaps, then the same event stream through the README loop.  Dense enough that many shapes overlap at t = 0."""
+    n = 4000
+    s = scenes.make_scene(n, 220.0, seed=scenes.SEED_BASE + 77, squares=True)
+    c = Lockstep(oracle, scenes.CELL_WIDTH, scenes.PADDING)
+    want = []
+    for id, hb in scene_hitboxes(oracle, s):
+        for other in c.o.add_hitbox(id, hb):
+            want.append((id, other))
+    a, b = c.d.add_hitboxes(s)
+    assert sorted(zip(a.tolist(), b.tolist())) == sorted(want) and len(want) > 50
+    assert c.d.len() == n and c.d.launch_count() < 200  # one pass (+ buffer growth re-runs, the queue sort), not 4000 calls
+    for i in (0, 1234, n - 1):
+        c.get_overlaps(i)
+        c.get_hitbox(i)
+    readme_loop(c, 3.0, halve(c))
+    assert c.events > 200
+    # and on a non-empty collider it falls back to single adds with the same semantics
+    extra = scenes.make_scene(50, 220.0, seed=scenes.SEED_BASE + 78, squares=True)
+    extra["id"] = extra["id"] + np.uint64(n)
+    want = []
+    t_now = c.time()
+    for id, hb in scene_hitboxes(oracle, extra):
+        for other in c.o.add_hitbox(id, hb):
+            want.append((id, other))
+    a, b = c.d.add_hitboxes(extra)
+    assert sorted(zip(a.tolist(), b.tolist())) == sorted(want)
+    readme_loop(c, t_now + 1.0, halve(c))
