@@ -135,6 +135,8 @@ def _bind(L):
     L.cb200_collider_set_rebin_threshold.argtypes = [vp, u32]
     L.cb200_collider_rebin_count.argtypes = [vp]
     L.cb200_collider_rebin_count.restype = u64
+    L.cb200_collider_prefetch_count.argtypes = [vp]
+    L.cb200_collider_prefetch_count.restype = u64
     L.cb200_collider_engine.argtypes = [vp]
     L.cb200_collider_engine.restype = vp
     L._collider_bound = True
@@ -291,6 +293,9 @@ class Collider:
 
     def rebin_count(self) -> int:
         return int(self._L.cb200_collider_rebin_count(self._h))
+
+    def prefetch_count(self) -> int:
+        return int(self._L.cb200_collider_prefetch_count(self._h))
 
     def launch_count(self) -> int:
         return int(self._L.cb200_launch_count(self._L.cb200_collider_engine(self._h)))

@@ -59,7 +59,19 @@ struct cb200_collider {
         uint32_t label, group, mask;
         std::vector<uint64_t> overlaps;  // ascending ids
         std::vector<EvKey> keys;         // overlay events this hitbox is part of
+        uint64_t version = 0;            // changes whenever the hitbox's device state changes (solve cache validity)
     };
+    // Prefetched narrowphase results for queued Collide / Separate events (uid -> result): see prefetch_solves.
+    struct CachedSolve {
+        double time;
+        uint32_t err;
+        uint64_t ver_a, ver_b;
+    };
+    std::unordered_map<uint64_t, CachedSolve> solve_cache;
+    uint64_t version_counter = 0;
+    Mapped<PairJob> jobs;
+    Mapped<PairOut> job_out;
+    uint64_t prefetches = 0, prefetched = 0;
     std::unordered_map<uint64_t, Info> infos;
     std::map<uint64_t, uint32_t> by_id;  // ordered id -> label: labels are order-isomorphic to the ids
     std::vector<uint64_t> id_of_label;   // UINT64_MAX = free
@@ -437,6 +449,7 @@ int internal_update(cb200_collider* c, uint64_t id, const double* vel5, bool che
     if (h.err_flags) return contract_error(c, h.err_flags, id);
     if (h.noop) return CB200_OK;
     c->n_dirty = h.n_dirty;
+    inf.version = ++c->version_counter;
     clear_related(c, id, inf);
     // solitaire_event_check (collider.rs:441-447), then Separate events in ascending partner id, then Collide events
     if (h.reit && (rc = add_event(c, h.end_time, QEvent{CB200_EV_REITERATE, id, 0})) != CB200_OK) return rc;
@@ -457,26 +470,91 @@ int internal_update(cb200_collider* c, uint64_t id, const double* vel5, bool che
     return CB200_OK;
 }
 
-int pair_solve(cb200_collider* c, uint64_t a, uint64_t b, bool separate, double* time_out) {
+// uid of a queued event for the solve cache: overlay events by their insertion index (pair events carry bit 63), events of
+// the device-sorted run by their position (bit 62).
+inline uint64_t uid_of(bool from_base, uint64_t base_pos, const EvKey& key) { return from_base ? (0x4000000000000000ull | base_pos) : key.index; }
+
+// One launch for the solves of the next queued events (the one being processed first): what process_event would compute
+// for each of them at its own event time — separate_time after a Collide (collider.rs:177-197), collide_time after a
+// Separate (collider.rs:148-158).  Speculative: a result is used only if both hitboxes still carry the versions seen here.
+constexpr size_t kPrefetchMax = 2048;
+int prefetch_solves(cb200_collider* c, uint64_t need_uid, const QEvent& need_ev, double need_time) {
     cb200_ctx* x = c->ctx;
-    k_pair_solve<<<1, 1, 0, x->stream>>>(table_of(c), c->infos[a].label, c->infos[b].label, separate ? 1 : 0, c->time, x->padding, c->head.d);
+    CCU(c->jobs.reserve(kPrefetchMax));
+    CCU(c->job_out.reserve(kPrefetchMax));
+    std::vector<uint64_t> uids;
+    std::vector<std::pair<uint64_t, uint64_t>> ab;
+    uids.reserve(kPrefetchMax);
+    auto push = [&](uint64_t uid, const QEvent& ev, double t) {
+        auto ia = c->infos.find(ev.a), ib = c->infos.find(ev.b);
+        if (ia == c->infos.end() || ib == c->infos.end()) return;
+        c->jobs.h[uids.size()] = PairJob{ia->second.label, ib->second.label, ev.kind == CB200_EV_COLLIDE ? 1u : 0u, 0u, t};
+        uids.push_back(uid);
+        ab.emplace_back(ia->second.version, ib->second.version);
+    };
+    auto cached_valid = [&](uint64_t uid, const QEvent& ev) {
+        auto it = c->solve_cache.find(uid);
+        if (it == c->solve_cache.end()) return false;
+        auto ia = c->infos.find(ev.a), ib = c->infos.find(ev.b);
+        return ia != c->infos.end() && ib != c->infos.end() && it->second.ver_a == ia->second.version && it->second.ver_b == ib->second.version;
+    };
+    push(need_uid, need_ev, need_time);
+    // upcoming events of the run (the fetched window) and of the overlay, half the budget each
+    for (uint64_t p = c->base_cur; p < c->base_off + c->base.size() && p < c->base_total && uids.size() < kPrefetchMax / 2; ++p) {
+        if (p < c->base_off) continue;
+        const cb200_event& e = c->base[p - c->base_off];
+        if (e.kind == CB200_EV_REITERATE || base_dead(c, e)) continue;
+        const uint64_t uid = uid_of(true, p, EvKey{});
+        const QEvent ev{e.kind, e.a, e.b};
+        if (uid == need_uid || cached_valid(uid, ev)) continue;
+        push(uid, ev, e.time);
+    }
+    for (auto it = c->overlay.begin(); it != c->overlay.end() && uids.size() < kPrefetchMax; ++it) {
+        if (it->second.kind == CB200_EV_REITERATE) continue;
+        const uint64_t uid = uid_of(false, 0, it->first);
+        if (uid == need_uid || cached_valid(uid, it->second)) continue;
+        push(uid, it->second, it->first.time);
+    }
+    const uint32_t n = (uint32_t)uids.size();
+    k_pair_solve_batch<<<(n + 127) / 128, 128, 0, x->stream>>>(table_of(c), c->jobs.d, n, x->padding, c->job_out.d);
     x->launches += 1;
     int rc = wait_head(c);
     if (rc != CB200_OK) return rc;
-    if (c->head.h->err_flags) return contract_error(c, c->head.h->err_flags, a);
-    *time_out = c->head.h->end_time;
+    if (c->solve_cache.size() > 8 * kPrefetchMax) c->solve_cache.clear();  // (stale entries of events that were cancelled)
+    for (uint32_t k = 0; k < n; ++k) c->solve_cache[uids[k]] = cb200_collider::CachedSolve{c->job_out.h[k].time, c->job_out.h[k].err, ab[k].first, ab[k].second};
+    c->prefetches += 1;
+    c->prefetched += n;
     return CB200_OK;
 }
 
+// The narrowphase result process_event needs for the event `uid` = (ev, at the current time).
+int pair_solve(cb200_collider* c, uint64_t uid, const QEvent& ev, double* time_out) {
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        auto it = c->solve_cache.find(uid);
+        if (it != c->solve_cache.end()) {
+            const cb200_collider::CachedSolve cs = it->second;
+            c->solve_cache.erase(it);
+            if (cs.ver_a == c->infos[ev.a].version && cs.ver_b == c->infos[ev.b].version) {
+                if (cs.err) return contract_error(c, cs.err, ev.a);
+                *time_out = cs.time;
+                return CB200_OK;
+            }
+        }
+        int rc = prefetch_solves(c, uid, ev, c->time);
+        if (rc != CB200_OK) return rc;
+    }
+    return cfail(c, CB200_E_STATE, "solve prefetch failed to produce the requested event");
+}
+
 // Collider::process_collision (collider.rs:177-197)
-int process_collision(cb200_collider* c, uint64_t a, uint64_t b, const double* sep_time) {
+int process_collision(cb200_collider* c, uint64_t a, uint64_t b, const double* sep_time, uint64_t uid) {
     overlap_insert(c->infos[a].overlaps, b);
     overlap_insert(c->infos[b].overlaps, a);
     c->overlaps_dirty = true;
     double t;
     if (sep_time) t = *sep_time;
     else {
-        int rc = pair_solve(c, a, b, true, &t);
+        int rc = pair_solve(c, uid, QEvent{CB200_EV_COLLIDE, a, b}, &t);
         if (rc != CB200_OK) return rc;
     }
     return add_event(c, t, QEvent{CB200_EV_SEPARATE, a, b});
@@ -517,7 +595,7 @@ void cb200_collider_free(cb200_collider* c) {
         cudaSetDevice(c->ctx->device);
         cudaStreamSynchronize(c->ctx->stream);
     }
-    c->head.release(); c->items.release(); c->ov.release(); c->qout.release();
+    c->head.release(); c->items.release(); c->ov.release(); c->qout.release(); c->jobs.release(); c->job_out.release();
     c->dirty.release(); c->dirty_list.release();
     if (c->d_dirty_count) cudaFree(c->d_dirty_count);
     cb200_destroy(c->ctx);
@@ -528,6 +606,7 @@ const char* cb200_collider_last_error(const cb200_collider* c) { return c ? c->e
 cb200_ctx* cb200_collider_engine(cb200_collider* c) { return c ? c->ctx : nullptr; }
 uint64_t cb200_collider_len(const cb200_collider* c) { return c ? c->infos.size() : 0; }
 uint64_t cb200_collider_rebin_count(const cb200_collider* c) { return c ? c->rebins : 0; }
+uint64_t cb200_collider_prefetch_count(const cb200_collider* c) { return c ? c->prefetches : 0; }
 
 int cb200_collider_set_can_interact(cb200_collider* c, cb200_can_interact_fn fn, void* user) {
     if (!c) return CB200_E_ARG;
@@ -574,6 +653,7 @@ int cb200_collider_next(cb200_collider* c, int* has_event, uint32_t* kind, uint6
         int rc = queue_head(c, &h);
         if (rc != CB200_OK) return rc;
         if (!h.any || !(h.time == c->time)) return CB200_OK;  // EventManager::next (events.rs:175-189)
+        const uint64_t uid = uid_of(h.from_base, c->base_cur, h.key);
         if (h.from_base) {
             c->base_cur += 1;
         } else {
@@ -587,13 +667,13 @@ int cb200_collider_next(cb200_collider* c, int* has_event, uint32_t* kind, uint6
             continue;
         }
         if (ev.kind == CB200_EV_COLLIDE) {
-            if ((rc = process_collision(c, ev.a, ev.b, nullptr)) != CB200_OK) return rc;
+            if ((rc = process_collision(c, ev.a, ev.b, nullptr, uid)) != CB200_OK) return rc;
         } else {
             if (!overlap_remove(c->infos[ev.a].overlaps, ev.b) || !overlap_remove(c->infos[ev.b].overlaps, ev.a))
                 return cfail(c, CB200_E_STATE, "Separate event for a pair that is not overlapping");
             c->overlaps_dirty = true;
             double t;
-            if ((rc = pair_solve(c, ev.a, ev.b, false, &t)) != CB200_OK) return rc;
+            if ((rc = pair_solve(c, uid, ev, &t)) != CB200_OK) return rc;
             if ((rc = add_event(c, t, QEvent{CB200_EV_COLLIDE, ev.a, ev.b})) != CB200_OK) return rc;
         }
         *has_event = 1;
@@ -641,7 +721,7 @@ int cb200_collider_add_hitbox(cb200_collider* c, const cb200_profile* profile, c
     if (rc != CB200_OK) return rc;
     if (x->n == 0 && !c->have_grid) collider_geom(c);
     uint32_t label = 0;
-    c->infos[id] = cb200_collider::Info{0, profile->group, profile->interact_mask, {}, {}};
+    c->infos[id] = cb200_collider::Info{0, profile->group, profile->interact_mask, {}, {}, ++c->version_counter};
     if ((rc = ensure_capacity(c, (size_t)x->n + 1, c->by_id.size() + 2)) != CB200_OK || (rc = assign_label(c, id, &label)) != CB200_OK) {
         c->infos.erase(id);
         c->by_id.erase(id);
@@ -689,7 +769,7 @@ int cb200_collider_add_hitbox(cb200_collider* c, const cb200_profile* profile, c
         if (p.second.kind == kItemImmediate) {
             if (overlaps && n_res < cap) overlaps[n_res] = p.first;
             ++n_res;
-            if ((rc = process_collision(c, id, p.first, &p.second.time)) != CB200_OK) return rc;
+            if ((rc = process_collision(c, id, p.first, &p.second.time, 0)) != CB200_OK) return rc;
         } else if ((rc = add_event(c, p.second.time, QEvent{CB200_EV_COLLIDE, id, p.first})) != CB200_OK) {
             return rc;
         }
@@ -782,7 +862,7 @@ int cb200_collider_add_hitboxes(cb200_collider* c, uint64_t n, const cb200_profi
     x->ov_bucket_mask = 0;
     for (uint64_t i = 0; i < n; ++i) {
         const cb200_profile& p = profiles[order[i]];
-        c->infos[p.id] = cb200_collider::Info{(uint32_t)i, p.group, p.interact_mask, {}, {}};
+        c->infos[p.id] = cb200_collider::Info{(uint32_t)i, p.group, p.interact_mask, {}, {}, ++c->version_counter};
         c->by_id[p.id] = (uint32_t)i;
         c->id_of_label[i] = p.id;
     }
@@ -847,6 +927,7 @@ int cb200_collider_add_hitboxes(cb200_collider* c, uint64_t n, const cb200_profi
     if (n_pairs) *n_pairs = n_out;
     c->overlaps_dirty = true;
     // the queue is the device-sorted run
+    c->solve_cache.clear();
     c->overlay.clear();
     std::fill(c->cleared.begin(), c->cleared.end(), 0);
     c->base.clear();
@@ -1000,6 +1081,8 @@ int cb200_collider_bulk_update(cb200_collider* c, const cb200_vel_view* vel, dou
     // updates overwrite
     if ((rc = sort_events(x)) != CB200_OK) return cfail(c, rc, x->err);
     // every hitbox was updated: every older event is gone (clear_related_events per hitbox); the run is the queue
+    c->solve_cache.clear();
+    for (auto& kv : c->infos) kv.second.version = ++c->version_counter;
     c->overlay.clear();
     for (auto& kv : c->infos) kv.second.keys.clear();
     std::fill(c->cleared.begin(), c->cleared.end(), 0);

@@ -283,6 +283,34 @@ __global__ void k_pair_solve(TableView t, uint32_t label_a, uint32_t label_b, in
     __threadfence_system();
 }
 
+// The same for a batch of queued events, each at its own event time: the host prefetches the solves of the next events in
+// one launch instead of one launch per event (collider.inl prefetch_solves); a result is used only if neither hitbox
+// changed in between.
+struct PairJob {
+    uint32_t label_a, label_b;
+    uint32_t separate, pad;
+    double t;
+};
+struct PairOut {
+    double time;  // t + delay
+    uint32_t err, pad;
+};
+__global__ void __launch_bounds__(128) k_pair_solve_batch(TableView t, const PairJob* __restrict__ jobs, uint32_t n, double padding, PairOut* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const PairJob j = jobs[i];
+    uint32_t err = 0;
+    const uint32_t ra = t.row_of[j.label_a], rb = t.row_of[j.label_b];
+    if (ra >= t.n || rb >= t.n) {
+        out[i] = PairOut{0.0, kFIdNotFound, 0u};
+        return;
+    }
+    const DurHb A = row_at_time(t.s, ra, j.t, &err), B = row_at_time(t.s, rb, j.t, &err);
+    const double delay = j.separate ? separate_time(A, B, padding) : collide_time(A, B);
+    if (delay != delay) err |= kFNan;
+    out[i] = PairOut{j.t + delay, err, 0u};
+}
+
 // Collider::get_hitbox = HitboxInfo::pub_hitbox_at_time(T) (collider.rs:200-202, 488-497).
 __global__ void k_get_hitbox(TableView t, uint32_t label, double T, OneHeader* head) {
     const uint32_t j = t.row_of[label];

@@ -306,6 +306,9 @@ uint64_t cb200_collider_len(const cb200_collider* c);
  * grid is rebuilt on the device (count / scan / scatter, no solve) when the list exceeds this many rows.  Default 4096. */
 int cb200_collider_set_rebin_threshold(cb200_collider* c, uint32_t dirty_rows);
 uint64_t cb200_collider_rebin_count(const cb200_collider* c);
+/* next() needs one narrowphase solve per Collide / Separate event; the library computes them for up to 2048 queued events
+ * per launch ahead of time and uses a prefetched result only if neither hitbox changed since.  Number of such launches. */
+uint64_t cb200_collider_prefetch_count(const cb200_collider* c);
 cb200_ctx* cb200_collider_engine(cb200_collider* c); /* the underlying device context (timing, launch counts, grid period) */
 
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */

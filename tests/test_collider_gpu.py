@@ -434,6 +434,7 @@ def test_config1_full_size_lockstep(oracle):
         c.add_hitbox(id, hb)
     readme_loop(c, 100.0, halve(c))
     assert c.events > 300
+    assert 0 < c.d.prefetch_count() < c.events  # the narrowphase solves behind next() are computed many events per launch
     for i in range(0, 1000, 97):
         c.get_hitbox(i)
         c.get_overlaps(i)
