@@ -221,16 +221,21 @@ class Collider:
         interact_mask]); returns the immediately overlapping pairs as two id arrays (later-added id, earlier id)."""
         n = len(scene["id"])
         z = np.zeros(n)
-        profs = (ProfileC * n)()
-        hbs = (HitboxC * n)()
-        group = scene.get("group", np.zeros(n, np.uint32))
-        mask = scene.get("interact_mask", np.ones(n, np.uint32))
-        rx, ry = scene.get("rsz_x", z), scene.get("rsz_y", z)
-        et = np.broadcast_to(np.asarray(end_time, dtype=np.float64), (n,))
-        for i in range(n):
-            profs[i] = ProfileC(int(scene["id"][i]), int(group[i]), int(mask[i]))
-            hbs[i] = HitboxC(scene["pos_x"][i], scene["pos_y"][i], scene["dim_x"][i], scene["dim_y"][i], scene["vel_x"][i], scene["vel_y"][i],
-                             rx[i], ry[i], et[i], int(scene["kind"][i]), 0)
+        # the two C arrays, filled column-wise through numpy views of the same layout
+        pd = np.zeros(n, dtype=np.dtype([("id", "<u8"), ("group", "<u4"), ("interact_mask", "<u4")]))
+        hd = np.zeros(n, dtype=np.dtype([(k, "<f8") for k in ("pos_x", "pos_y", "dim_x", "dim_y", "vel_x", "vel_y", "rsz_x", "rsz_y", "end_time")]
+                                        + [("kind", "<u4"), ("_pad", "<u4")]))
+        assert pd.dtype.itemsize == C.sizeof(ProfileC) and hd.dtype.itemsize == C.sizeof(HitboxC)
+        pd["id"] = scene["id"]
+        pd["group"] = scene.get("group", np.zeros(n, np.uint32))
+        pd["interact_mask"] = scene.get("interact_mask", np.ones(n, np.uint32))
+        for k in ("pos_x", "pos_y", "dim_x", "dim_y", "vel_x", "vel_y"):
+            hd[k] = scene[k]
+        hd["rsz_x"], hd["rsz_y"] = scene.get("rsz_x", z), scene.get("rsz_y", z)
+        hd["end_time"] = np.broadcast_to(np.asarray(end_time, dtype=np.float64), (n,))
+        hd["kind"] = scene["kind"]
+        profs = C.cast(pd.ctypes.data, C.POINTER(ProfileC))
+        hbs = C.cast(hd.ctypes.data, C.POINTER(HitboxC))
         cap = 1024
         while True:
             a = np.zeros(cap, dtype=np.uint64)

@@ -77,6 +77,8 @@ struct cb200_collider {
     std::vector<uint64_t> id_of_label;   // UINT64_MAX = free
     bool ids_dirty = true;               // the device label -> id table is stale
     bool overlaps_dirty = true;          // the device overlap set is stale
+    std::set<std::pair<uint64_t, uint64_t>> overlap_pairs;  // every overlapping pair once, (lower id, higher id)
+    std::vector<uint64_t> with_keys;     // ids whose Info.keys may be non-empty (cleared wholesale by a bulk step)
 
     std::map<EvKey, QEvent, EvKeyLess> overlay;
     uint64_t next_index = 0;
@@ -297,7 +299,15 @@ int add_event(cb200_collider* c, double time, const QEvent& ev) {
     const EvKey key{time, index};
     c->overlay.emplace(key, ev);
     c->infos[ev.a].keys.push_back(key);
-    if (ev.kind != CB200_EV_REITERATE) c->infos[ev.b].keys.push_back(key);
+    if (c->with_keys.size() > (1u << 22)) {  // (no bulk step for a long time: keep the list a set)
+        std::sort(c->with_keys.begin(), c->with_keys.end());
+        c->with_keys.erase(std::unique(c->with_keys.begin(), c->with_keys.end()), c->with_keys.end());
+    }
+    c->with_keys.push_back(ev.a);
+    if (ev.kind != CB200_EV_REITERATE) {
+        c->infos[ev.b].keys.push_back(key);
+        c->with_keys.push_back(ev.b);
+    }
     return CB200_OK;
 }
 
@@ -319,6 +329,12 @@ void clear_related(cb200_collider* c, uint64_t id, cb200_collider::Info& inf) {
 }
 
 void overlap_insert(std::vector<uint64_t>& v, uint64_t id) { v.insert(std::lower_bound(v.begin(), v.end(), id), id); }
+void pair_insert(cb200_collider* c, uint64_t a, uint64_t b) {
+    overlap_insert(c->infos[a].overlaps, b);
+    overlap_insert(c->infos[b].overlaps, a);
+    c->overlap_pairs.emplace(std::min(a, b), std::max(a, b));
+    c->overlaps_dirty = true;
+}
 bool overlap_remove(std::vector<uint64_t>& v, uint64_t id) {
     auto it = std::lower_bound(v.begin(), v.end(), id);
     if (it == v.end() || *it != id) return false;
@@ -548,9 +564,7 @@ int pair_solve(cb200_collider* c, uint64_t uid, const QEvent& ev, double* time_o
 
 // Collider::process_collision (collider.rs:177-197)
 int process_collision(cb200_collider* c, uint64_t a, uint64_t b, const double* sep_time, uint64_t uid) {
-    overlap_insert(c->infos[a].overlaps, b);
-    overlap_insert(c->infos[b].overlaps, a);
-    c->overlaps_dirty = true;
+    pair_insert(c, a, b);
     double t;
     if (sep_time) t = *sep_time;
     else {
@@ -671,6 +685,7 @@ int cb200_collider_next(cb200_collider* c, int* has_event, uint32_t* kind, uint6
         } else {
             if (!overlap_remove(c->infos[ev.a].overlaps, ev.b) || !overlap_remove(c->infos[ev.b].overlaps, ev.a))
                 return cfail(c, CB200_E_STATE, "Separate event for a pair that is not overlapping");
+            c->overlap_pairs.erase({std::min(ev.a, ev.b), std::max(ev.a, ev.b)});
             c->overlaps_dirty = true;
             double t;
             if ((rc = pair_solve(c, uid, ev, &t)) != CB200_OK) return rc;
@@ -916,8 +931,7 @@ int cb200_collider_add_hitboxes(cb200_collider* c, uint64_t n, const cb200_profi
     std::sort(imm.begin(), imm.end(), [](const uint2& p, const uint2& q) { return p.x < q.x || (p.x == q.x && p.y < q.y); });
     for (const uint2& pr : imm) {
         const uint64_t a_id = c->id_of_label[pr.x], b_id = c->id_of_label[pr.y];
-        overlap_insert(c->infos[a_id].overlaps, b_id);
-        overlap_insert(c->infos[b_id].overlaps, a_id);
+        pair_insert(c, a_id, b_id);
         if (n_out < cap_pairs) {
             if (pair_a) pair_a[n_out] = a_id;
             if (pair_b) pair_b[n_out] = b_id;
@@ -965,6 +979,7 @@ int cb200_collider_remove_hitbox(cb200_collider* c, uint64_t id, uint64_t* overl
     uint64_t n_res = 0;
     for (uint64_t other : it->second.overlaps) {
         overlap_remove(c->infos[other].overlaps, id);
+        c->overlap_pairs.erase({std::min(other, id), std::max(other, id)});
         if (overlaps && n_res < cap) overlaps[n_res] = other;
         ++n_res;
     }
@@ -1060,12 +1075,12 @@ int cb200_collider_bulk_update(cb200_collider* c, const cb200_vel_view* vel, dou
     }
     if (c->overlaps_dirty) {
         std::vector<uint64_t> pa, pb;
-        for (auto& kv : c->infos)
-            for (uint64_t other : kv.second.overlaps)
-                if (kv.first < other) {
-                    pa.push_back(kv.first);
-                    pb.push_back(other);
-                }
+        pa.reserve(c->overlap_pairs.size());
+        pb.reserve(c->overlap_pairs.size());
+        for (const auto& pr : c->overlap_pairs) {
+            pa.push_back(pr.first);
+            pb.push_back(pr.second);
+        }
         rc = cb200_set_overlaps(x, pa.data(), pb.data(), pa.size());
         if (rc != CB200_OK) return cfail(c, rc, x->err);
         c->overlaps_dirty = false;
@@ -1081,10 +1096,13 @@ int cb200_collider_bulk_update(cb200_collider* c, const cb200_vel_view* vel, dou
     // updates overwrite
     if ((rc = sort_events(x)) != CB200_OK) return cfail(c, rc, x->err);
     // every hitbox was updated: every older event is gone (clear_related_events per hitbox); the run is the queue
-    c->solve_cache.clear();
-    for (auto& kv : c->infos) kv.second.version = ++c->version_counter;
+    c->solve_cache.clear();  // (so the hitbox versions need no bump)
     c->overlay.clear();
-    for (auto& kv : c->infos) kv.second.keys.clear();
+    for (uint64_t id : c->with_keys) {
+        auto it = c->infos.find(id);
+        if (it != c->infos.end()) it->second.keys.clear();
+    }
+    c->with_keys.clear();
     std::fill(c->cleared.begin(), c->cleared.end(), 0);
     c->base.clear();
     c->base_off = c->base_cur = 0;
