@@ -154,7 +154,7 @@ def _main(out):
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000, help="hitboxes per GPU")
+    ap.add_argument("--n", "--hitboxes", dest="n", type=int, default=1_000_000, help="hitboxes per GPU")
     ap.add_argument("--workload", default="c3", choices=["c3", "c3_dense", "c5"])
     ap.add_argument("--ref-sample", type=int, default=200_000, help="hitboxes in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

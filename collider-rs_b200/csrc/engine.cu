@@ -426,9 +426,9 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
         if (n) CU(cudaMemcpyAsync(ctx->label.p, g.data(), n * 4, cudaMemcpyHostToDevice, ctx->stream));
         if (n) k_iota_rows<<<((uint32_t)n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>((uint32_t)n, ctx->ord.p, nullptr);
         CU(cudaStreamSynchronize(ctx->stream));
-        // halo slab: header + room for n/256 (>= 2047) records leaving the strip (cb200_shard_set_slab overrides); the
+        // halo slab: header + room for n/64 (>= 4095) records leaving the strip (cb200_shard_set_slab overrides); the
         // visitor table holds the n own records followed by one received slab per rank
-        if (ctx->slab == 0) ctx->slab = (uint32_t)std::max<size_t>(n / 256, 2047) + 1;
+        if (ctx->slab == 0) ctx->slab = (uint32_t)std::max<size_t>(n / 64, 4095) + 1;
         // (two receive areas: the direct exchange double-buffers them by step parity)
         CU(ctx->rec.reserve(n + 2 * (size_t)ctx->slab * ctx->shard.world));
         CU(ctx->bink.reserve(n + 2 * (size_t)ctx->slab * ctx->shard.world));

@@ -190,7 +190,7 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
 int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* col_bounds /* world + 1 */,
                           uint64_t id_space /* every HbId of every rank is < id_space < 2^31 - 1 */);
 int cb200_set_stream(cb200_ctx* ctx, void* cuda_stream);
-int cb200_shard_set_slab(cb200_ctx* ctx, uint64_t records); /* capacity of the halo slab; default max(2047, n/256); before upload_state */
+int cb200_shard_set_slab(cb200_ctx* ctx, uint64_t records); /* capacity of the halo slab; default max(4095, n/64): the direct exchange only moves the records that are there; before upload_state */
 int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, void** send_base, void** recv_base,
                       uint64_t* slab_bytes);
 int cb200_shard_finish(cb200_ctx* ctx, void** local_key);
