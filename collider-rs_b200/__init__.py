@@ -90,7 +90,7 @@ EXPORTS = (
     "cb200_bulk_update", "cb200_fetch_events", "cb200_fetch_candidate_pairs", "cb200_fetch_cell_entries",
     "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
     "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_shard_set_slab", "cb200_set_stream", "cb200_shard_begin", "cb200_shard_finish",
-    "cb200_shard_result", "cb200_set_resort_period", "cb200_resort_count", "cb200_set_stage_timing",
+    "cb200_shard_result", "cb200_set_resort_period", "cb200_resort_count", "cb200_event_sort_fallbacks", "cb200_set_stage_timing",
     "cb200_shard_p2p_export", "cb200_shard_p2p_import", "cb200_shard_step", "cb200_shard_global_next", "cb200_shard_local_key",
     "cb200_collider_new", "cb200_collider_free", "cb200_collider_last_error", "cb200_collider_set_can_interact", "cb200_collider_time",
     "cb200_collider_next_time", "cb200_collider_set_time", "cb200_collider_next", "cb200_collider_get_hitbox", "cb200_collider_add_hitbox",
@@ -153,6 +153,8 @@ def load_library() -> C.CDLL:
     L.cb200_set_resort_period.argtypes = [vp, i32]
     L.cb200_resort_count.argtypes = [vp]
     L.cb200_resort_count.restype = u64
+    L.cb200_event_sort_fallbacks.argtypes = [vp]
+    L.cb200_event_sort_fallbacks.restype = u64
     _lib = L
     return L
 
@@ -366,6 +368,9 @@ class Engine:
 
     def resort_count(self) -> int:
         return int(self._L.cb200_resort_count(self._h))
+
+    def event_sort_fallbacks(self) -> int:
+        return int(self._L.cb200_event_sort_fallbacks(self._h))
 
     def fetch_candidate_pairs(self):
         n = C.c_uint64()

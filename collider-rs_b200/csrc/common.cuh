@@ -116,6 +116,32 @@ __device__ __forceinline__ void load_rec_keep(const HbRec* __restrict__ rec, uin
     d->kind = (int)(h->kgb & 1u);
 }
 
+// The same record through three 256-bit loads (LDG.E.256 on sm_100a): one request per 32-B sector instead of two.
+__device__ __forceinline__ void ld256_nc(const void* p, unsigned long long (&v)[4]) {
+    asm("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void load_rec_wide(const HbRec* __restrict__ rec, uint32_t i, RecHead* h, DurHb* d) {
+    const char* p = reinterpret_cast<const char*>(rec + i);
+    unsigned long long s0[4], s1[4], s2[4];
+    ld256_nc(p, s0);
+    ld256_nc(p + 32, s1);
+    ld256_nc(p + 64, s2);
+    h->sx = (int32_t)(uint32_t)s0[0]; h->sy = (int32_t)(uint32_t)(s0[0] >> 32);
+    const uint32_t span = (uint32_t)s0[1];
+    h->ex = h->sx + (int32_t)(span & 0xffffu);
+    h->ey = h->sy + (int32_t)(span >> 16);
+    h->gid = (uint32_t)(s0[1] >> 32);
+    h->dur = __longlong_as_double((long long)s0[2]);
+    h->kgb = (uint32_t)s0[3];
+    h->mask = (uint32_t)(s0[3] >> 32);
+    d->px = __longlong_as_double((long long)s1[0]); d->py = __longlong_as_double((long long)s1[1]);
+    d->w = __longlong_as_double((long long)s1[2]); d->h = __longlong_as_double((long long)s1[3]);
+    d->vx = __longlong_as_double((long long)s2[0]); d->vy = __longlong_as_double((long long)s2[1]);
+    d->rw = __longlong_as_double((long long)s2[2]); d->rh = __longlong_as_double((long long)s2[3]);
+    d->dur = h->dur;
+    d->kind = (int)(h->kgb & 1u);
+}
+
 // Coherent (plain ld.global) variants for kernels that read records written earlier in the same launch.
 __device__ __forceinline__ RecHead load_head_nc(const HbRec* rec, uint32_t i) {
     const int4* p = reinterpret_cast<const int4*>(rec + i);

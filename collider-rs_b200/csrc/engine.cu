@@ -103,6 +103,7 @@ struct cb200_ctx {
     unsigned long long* d_n_imm = nullptr;
     uint32_t graph_kernels[4] = {};  // kernels inside each captured graph (for the launch counter)
     uint64_t graph_launches = 0, graph_captures = 0;
+    bool ld256 = false;        // CB200_LD256=1: k_solve gathers records with 256-bit loads (measured: 86 vs 84 us, kept for A/B)
     bool stage_a_tma = false;  // CB200_STAGE_A=tma: input columns staged through shared memory by bulk async copies (measured slower, kept for A/B)
     // sharding
     bool sharded = false;
@@ -159,6 +160,10 @@ struct cb200_ctx {
     DevBuf<uint32_t> bs_tab[5];  // bucket sort, one per recursion depth: counts / offsets, cursors, oversized buckets, range
     DevBuf<EventOut> ev_out;
     bool ev_sorted = false;
+    bool sort_oneshot = true;        // CB200_SORT=slow: recursive bucket sort / radix sort only (A/B and tests)
+    uint32_t* h_sort_big = nullptr;  // pinned, mapped: k_bs_scan8's oversized-bucket report [1 + 2 * kBsMaxBig]
+    uint32_t* d_sort_big = nullptr;  // its device alias
+    uint64_t sort_fallbacks = 0;
     uint64_t n_ev_sorted = 0;
 
     uint64_t launches = 0;
@@ -305,11 +310,15 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if (const char* g = getenv("CB200_GRAPH")) c->use_graph = g[0] != '0';
     if (const char* rp = getenv("CB200_RESORT_PERIOD")) c->resort_period = std::max(0, atoi(rp));
     if (const char* sa = getenv("CB200_STAGE_A")) c->stage_a_tma = strcmp(sa, "tma") == 0;
+    if (const char* w = getenv("CB200_LD256")) c->ld256 = w[0] != '0';
     if ((e = cudaFuncSetAttribute(k_stage_a_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(StageATile)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_stage_a_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(StageATile)))) != cudaSuccess)
         return bail("cudaFuncSetAttribute", e);
     if ((e = cudaHostAlloc(&c->h_res, sizeof(StepResultDev), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer((void**)&c->d_res, c->h_res, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
+    if ((e = cudaHostAlloc(&c->h_sort_big, (1 + 2 * kBsMaxBig) * sizeof(uint32_t), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostGetDevicePointer((void**)&c->d_sort_big, c->h_sort_big, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
+    if (const char* so = getenv("CB200_SORT")) c->sort_oneshot = strcmp(so, "slow") != 0;
     for (auto& ev : c->ev_t)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     *out = c;
@@ -343,6 +352,7 @@ void cb200_destroy(cb200_ctx* c) {
     if (c->d_mail) cudaFree(c->d_mail);
     if (c->h_gkey) cudaFreeHost(c->h_gkey);
     if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->h_sort_big) cudaFreeHost(c->h_sort_big);
     if (c->pinned_stage) cudaFreeHost(c->pinned_stage);
     for (auto& ev : c->ev_t)
         if (ev) cudaEventDestroy(ev);
@@ -376,6 +386,7 @@ int cb200_set_resort_period(cb200_ctx* ctx, int steps) {
     return CB200_OK;
 }
 uint64_t cb200_resort_count(const cb200_ctx* ctx) { return ctx ? ctx->resorts : 0; }
+uint64_t cb200_event_sort_fallbacks(const cb200_ctx* ctx) { return ctx ? ctx->sort_fallbacks : 0; }
 
 void* cb200_host_alloc(uint64_t bytes) {
     void* p = nullptr;
@@ -513,6 +524,17 @@ int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_
     ctx->ov_bucket_mask = cap / 4 - 1;
     return CB200_OK;
 }
+
+// CB200_SYNC_DEBUG=1 (with CB200_GRAPH=0): wait after every stage and name the one that failed.
+static int dbg_sync(cb200_ctx* ctx, const char* stage) {
+    static const bool on = getenv("CB200_SYNC_DEBUG") != nullptr;
+    if (!on) return CB200_OK;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, CB200_E_CUDA, std::string("stage ") + stage + ": " + cudaGetErrorString(e));
+    return CB200_OK;
+}
+#define DBG_SYNC(stage) do { int rc_ = dbg_sync(ctx, stage); if (rc_ != CB200_OK) return rc_; } while (0)
 
 static int stage_vel(cb200_ctx* ctx, const cb200_vel_view* vel, const double** nv) {
     const uint32_t n = ctx->n;
@@ -656,6 +678,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     k_step_zero<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(ctx->slots.p), n_slots / 4, ctx->d_ctr,
                                                                   ctx->sharded ? ctx->send_count.p : nullptr, ctx->work_count.p, kWorkLists, ctx->sharded ? n : 0u);
     ctx->launches += 1;
+    DBG_SYNC("k_step_zero");
     if (ctx->collider_dirty && n) {
         CU(cudaMemsetAsync(ctx->collider_dirty, 0, n, ctx->stream));
         CU(cudaMemsetAsync(ctx->collider_dirty_count, 0, 4, ctx->stream));
@@ -713,6 +736,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
         ctx->grid_a = 1;
         CU(cudaMemsetAsync(ctx->partial.p, 0xff, sizeof(MinKey) * ctx->grid_a, ctx->stream));
     }
+    DBG_SYNC("k_stage_a");
     if (ctx->sharded) {
         k_slab_header<<<1, 1, 0, ctx->stream>>>(ctx->send.p, ctx->send_count.p, ctx->slab);
         ctx->launches += 1;
@@ -744,6 +768,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
         int rc = launch_scan(ctx, true);
         if (rc != CB200_OK) return rc;
     }
+    DBG_SYNC("k_scan_slots");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_SCATTER], ctx->stream));
     if (n_vis_max) {
         const uint32_t cap_e = (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu);
@@ -751,6 +776,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
         else k_scatter<false><<<grid_v, kThreads, 0, ctx->stream>>>(ctx->n, ctx->rec.p, ctx->bink.p, vs, ctx->slots.p, ctx->entries.p, cap_e, g, sh.col_lo, sh.col_hi, ctx->d_ctr);
         ctx->launches += 1;
     }
+    DBG_SYNC("k_scatter");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_CAND], ctx->stream));
     CandArgs cd{};
     cd.geom = g;
@@ -759,9 +785,11 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     cd.ov = OverlapSet{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, ctx->n_ov};
     EnumArgs en{};
     en.entries = ctx->entries.p;
+    en.cap_entries = (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu);
     en.work = work_lists_of(ctx);
     en.ctr = ctx->d_ctr;
     k_enum_pairs<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(en);
+    DBG_SYNC("k_enum_pairs");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_SOLVE], ctx->stream));
     SolveArgs sv{};
     sv.cd = cd;
@@ -790,7 +818,9 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     sv.vs = vs;
     sv.col_lo = sh.col_lo;
     sv.col_hi = sh.col_hi;
-    k_solve<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(sv);
+    if (ctx->ld256) k_solve<true><<<ctx->grid_p, kThreads, 0, ctx->stream>>>(sv);
+    else k_solve<false><<<ctx->grid_p, kThreads, 0, ctx->stream>>>(sv);
+    DBG_SYNC("k_solve");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
     CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
     ctx->launches += 2;
@@ -915,6 +945,7 @@ static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
     }
     if (const char* d = getenv("CB200_DBG_A")) mix((uint64_t)atoi(d) + 17);
     if (const char* d = getenv("CB200_DBG_S")) mix((uint64_t)atoi(d) + 31);
+    mix(ctx->ld256 ? 257u : 129u);
     return h ? h : 1;
 }
 
@@ -1197,7 +1228,7 @@ int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world 
         cudaFuncAttributes fa;
         const void* fns[] = {(const void*)k_step_zero, (const void*)k_stage_a<true>, (const void*)k_stage_a_tma<true>, (const void*)k_slab_header, (const void*)k_push_halo,
                              (const void*)k_wait_flags, (const void*)k_index_visitors<true>, (const void*)k_index_visitors<false>,
-                             (const void*)k_scan_slots, (const void*)k_scatter<true>, (const void*)k_enum_pairs, (const void*)k_solve,
+                             (const void*)k_scan_slots, (const void*)k_scatter<true>, (const void*)k_enum_pairs, (const void*)k_solve<true>, (const void*)k_solve<false>,
                              (const void*)k_push_key, (const void*)k_reduce_keys, (const void*)k_resort_count, (const void*)k_resort_rank,
                              (const void*)k_resort_gather};
         for (const void* f : fns) CU(cudaFuncGetAttributes(&fa, f));
@@ -1319,31 +1350,55 @@ static int sort_range(cb200_ctx* ctx, Key128* keys, Key128* tmp, uint32_t n, int
     return CB200_OK;
 }
 
-static int sort_events(cb200_ctx* ctx) {
-    if (ctx->ev_sorted) return CB200_OK;
-    const Counters& c = ctx->last.ctr;
-    const uint64_t n_pairs = c.n_pair_events, total = n_pairs + c.n_solitaire;
-    ctx->n_ev_sorted = total;
-    if (total == 0) {
-        ctx->ev_sorted = true;
-        return CB200_OK;
-    }
-    if (total >= 0xffffffffull) return fail(ctx, CB200_E_STATE, "too many events to sort");
-    const uint32_t nt = (uint32_t)total;
-    CU(ctx->keys_a.reserve(nt)); CU(ctx->keys_b.reserve(nt)); CU(ctx->ev_out.reserve(nt));
-    const uint32_t n_blocks = (nt + kRsTile - 1) / kRsTile;
-    CU(ctx->rs_hist.reserve((size_t)16 * n_blocks));
+// Order keys of every queued event of the last step, in keys_a (queued on the stream).
+static int build_sort_keys(cb200_ctx* ctx, uint32_t n_pairs, uint64_t n_solitaire) {
     CU(cudaMemsetAsync(&ctx->d_ctr->n_sort_keys, 0, 8, ctx->stream));
     if (ctx->n) k_keys_solitaire<<<(ctx->n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(ctx->n, ctx->reit.p, ctx->col[9].p, ctx->label.p, ctx->keys_a.p, ctx->d_ctr);
-    if (n_pairs) k_keys_pairs<<<((uint32_t)n_pairs + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>((uint32_t)n_pairs, ctx->events.p, ctx->keys_a.p, c.n_solitaire);
+    if (n_pairs) k_keys_pairs<<<(n_pairs + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(n_pairs, ctx->events.p, ctx->keys_a.p, n_solitaire);
     ctx->launches += 2;
+    return CB200_OK;
+}
+
+// One-shot bucket sort (sort.cuh): everything is queued without a host round trip — keys, two-region bucket cut, rank sort,
+// decode into ev_out.  Whether it succeeded (no bucket too large for a warp) is in ctx->h_sort_big[0] once the stream has
+// been synchronised; the caller checks it and falls back to sort_events_slow.
+static int enqueue_sort_oneshot(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, uint64_t n_solitaire) {
+    int rc = build_sort_keys(ctx, n_pairs, n_solitaire);
+    if (rc != CB200_OK) return rc;
+    int log2_buckets = 6;
+    while ((1u << log2_buckets) * 12u < nt && log2_buckets < 22) ++log2_buckets;
+    const uint32_t nb = 1u << log2_buckets, n_buckets = 2 * nb;  // region A (ties at the first time) + region B (by time)
+    DevBuf<uint32_t>& tab = ctx->bs_tab[0];
+    CU(tab.reserve(2 * (size_t)n_buckets + 2 + 8));
+    uint32_t* count = tab.p;                   // then: offsets [n_buckets + 1]
+    uint32_t* cursor = tab.p + n_buckets + 1;  // [n_buckets]
+    BsRange* range = reinterpret_cast<BsRange*>(tab.p + ((2 * (size_t)n_buckets + 2) & ~(size_t)1));
+    const BsRange init{~0ull, 0ull};
+    CU(cudaMemsetAsync(count, 0, ((size_t)n_buckets + 1) * 4, ctx->stream));
+    CU(cudaMemcpyAsync(range, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t blocks = (nt + kThreads - 1) / kThreads;
+    const uint32_t label_bound = std::max<uint32_t>(1u, ctx->sharded ? (uint32_t)std::min<uint64_t>(ctx->id_space, 0x7fffffffull) : ctx->n);
+    Key128 *keys = ctx->keys_a.p, *tmp = ctx->keys_b.p;
+    k_bs_minmax<<<std::min<uint32_t>(blocks, 1024), kThreads, 0, ctx->stream>>>(nt, keys, 1, range);
+    k_bs2_count<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, range, log2_buckets, label_bound, count);
+    k_bs_scan8<<<1, 1024, 0, ctx->stream>>>(count, n_buckets, count, cursor, ctx->d_sort_big);
+    k_bs2_scatter<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, range, log2_buckets, label_bound, cursor, tmp);
+    k_bs_local<<<std::min<uint32_t>((n_buckets + 7) / 8, (uint32_t)ctx->sm_count * 8u), 256, 0, ctx->stream>>>(tmp, count, n_buckets, keys);
+    k_decode_events<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p, ctx->last_add_mode ? 1 : 0);
+    ctx->launches += 6;
+    CU(cudaGetLastError());
+    return CB200_OK;
+}
+
+// Recursive bucket sort, then the LSD radix sort: for steps with many events at one later time.
+static int sort_events_slow(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, uint64_t n_solitaire) {
+    int rc = build_sort_keys(ctx, n_pairs, n_solitaire);
+    if (rc != CB200_OK) return rc;
+    const uint32_t n_blocks = (nt + kRsTile - 1) / kRsTile;
+    CU(ctx->rs_hist.reserve((size_t)16 * n_blocks));
     Key128 *in = ctx->keys_a.p, *outp = ctx->keys_b.p;
-    // fast path: bucket sort by time range + per-bucket rank sort, recursing into oversized buckets (sort.cuh)
     bool sorted = false;
-    {
-        int rc = sort_range(ctx, in, outp, nt, 1, 0, &sorted);
-        if (rc != CB200_OK) return rc;
-    }
+    if ((rc = sort_range(ctx, in, outp, nt, 1, 0, &sorted)) != CB200_OK) return rc;
     if (!sorted) {
         // fallback: LSD radix sort on the digits that differ
         CU(cudaMemsetAsync(&ctx->d_ctr->diff_hi, 0, 16, ctx->stream));
@@ -1367,21 +1422,64 @@ static int sort_events(cb200_ctx* ctx) {
     ctx->launches += 1;
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
-    ctx->ev_sorted = true;
     return CB200_OK;
 }
+
+// Sorted events of the last step in ev_out.  `copy_to` (optional): `take` records from `offset` are copied to the host
+// behind the sort, so a fetch costs one synchronisation.
+static int sort_events_to(cb200_ctx* ctx, EventOut* copy_to, uint64_t offset, uint64_t cap, uint64_t* taken) {
+    if (taken) *taken = 0;
+    const bool was_sorted = ctx->ev_sorted;
+    uint32_t nt = 0, n_pairs = 0;
+    uint64_t n_solitaire = 0;
+    if (!was_sorted) {
+        const Counters& c = ctx->last.ctr;
+        n_solitaire = c.n_solitaire;
+        const uint64_t total = c.n_pair_events + c.n_solitaire;
+        ctx->n_ev_sorted = total;
+        if (total >= 0xffffffffull) return fail(ctx, CB200_E_STATE, "too many events to sort");
+        nt = (uint32_t)total;
+        n_pairs = (uint32_t)c.n_pair_events;
+        if (nt) {
+            CU(ctx->keys_a.reserve(nt)); CU(ctx->keys_b.reserve(nt)); CU(ctx->ev_out.reserve(nt));
+            ctx->h_sort_big[0] = 0;
+            int rc = ctx->sort_oneshot ? enqueue_sort_oneshot(ctx, nt, n_pairs, n_solitaire) : sort_events_slow(ctx, nt, n_pairs, n_solitaire);
+            if (rc != CB200_OK) return rc;
+        }
+    }
+    const uint64_t avail = ctx->n_ev_sorted > offset ? ctx->n_ev_sorted - offset : 0;
+    const uint64_t take = copy_to ? std::min(avail, cap) : 0;
+    if (take) CU(cudaMemcpyAsync(copy_to, ctx->ev_out.p + offset, take * sizeof(EventOut), cudaMemcpyDeviceToHost, ctx->stream));
+    if (take || (!was_sorted && nt)) CU(cudaStreamSynchronize(ctx->stream));
+    if (!was_sorted && nt && ctx->sort_oneshot && ctx->h_sort_big[0] != 0) {
+        ctx->sort_fallbacks += 1;
+        if (getenv("CB200_VERBOSE")) fprintf(stderr, "[cb200] one-shot event sort: %u oversized buckets of %u keys, falling back\n", ctx->h_sort_big[0], nt);
+        int rc = sort_events_slow(ctx, nt, n_pairs, n_solitaire);
+        if (rc != CB200_OK) return rc;
+        if (take) CU(cudaMemcpy(copy_to, ctx->ev_out.p + offset, take * sizeof(EventOut), cudaMemcpyDeviceToHost));
+    }
+    ctx->ev_sorted = true;
+    if (taken) *taken = take;
+    return CB200_OK;
+}
+static int sort_events(cb200_ctx* ctx) { return sort_events_to(ctx, nullptr, 0, 0, nullptr); }
 
 int cb200_fetch_events(cb200_ctx* ctx, cb200_event* buf, uint64_t cap, uint64_t offset, uint64_t* n_out) {
     if (!ctx) return CB200_E_ARG;
     if (!ctx->have_step) return fail(ctx, CB200_E_STATE, "fetch_events before bulk_update");
     CU(cudaSetDevice(ctx->device));
     static_assert(sizeof(cb200_event) == sizeof(EventOut), "event layout");
-    int rc = sort_events(ctx);
+    if (!buf && cap) {
+        // (the count is not known before the sort: a null buffer is an error only if something would be written)
+        int rc = sort_events(ctx);
+        if (rc != CB200_OK) return rc;
+        if (ctx->n_ev_sorted > offset) return fail(ctx, CB200_E_ARG, "null event buffer");
+        if (n_out) *n_out = 0;
+        return CB200_OK;
+    }
+    uint64_t take = 0;
+    int rc = sort_events_to(ctx, reinterpret_cast<EventOut*>(buf), offset, cap, &take);
     if (rc != CB200_OK) return rc;
-    uint64_t avail = ctx->n_ev_sorted > offset ? ctx->n_ev_sorted - offset : 0;
-    uint64_t take = std::min(avail, cap);
-    if (take && !buf) return fail(ctx, CB200_E_ARG, "null event buffer");
-    if (take) CU(cudaMemcpy(buf, ctx->ev_out.p + offset, take * sizeof(EventOut), cudaMemcpyDeviceToHost));
     if (n_out) *n_out = take;
     return CB200_OK;
 }

@@ -837,6 +837,7 @@ struct WorkLists {  // work buffer = kWorkLists equal segments; list l holds kin
 
 struct EnumArgs {
     const CellEntry* entries;
+    uint32_t cap_entries;  // the scatter wrote only the entries below it (an overflowing step is re-run)
     WorkLists work;
     Counters* ctr;
 };
@@ -855,7 +856,7 @@ __device__ __forceinline__ uint32_t rect_preds(unsigned prev_rects, unsigned rec
 
 __global__ void __launch_bounds__(kThreads) k_enum_pairs(const EnumArgs a) {
     __shared__ uint32_t s_cnt[kThreads / 32][3], s_off[kThreads / 32][3], s_base[3];
-    const uint32_t n_entries = (uint32_t)a.ctr->n_entries;
+    const uint32_t n_entries = (uint32_t)min(a.ctr->n_entries, (unsigned long long)a.cap_entries);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr uint32_t kNoSlot = 0xffffffffu;  // (slots have 26 bits)
     const uint2* ent = reinterpret_cast<const uint2*>(a.entries);
@@ -935,15 +936,13 @@ __global__ void __launch_bounds__(kThreads) k_enum_pairs(const EnumArgs a) {
             s_base[threadIdx.x] = run ? atomicAdd(&a.work.count[threadIdx.x * kSubLists + sub], run) : 0u;
         }
         __syncthreads();
+        // Items past the end of a segment are dropped (the step is re-run with a larger buffer) — one by one, so that every
+        // position below seg_cap IS written: the solve stage reads min(count, seg_cap) items of each list.
         uint32_t pos[3];
-        bool room = true;  // a range that does not fit its segment is dropped: the step is re-run with a larger buffer
 #pragma unroll
-        for (int l = 0; l < 3; ++l) {
-            const uint32_t at = s_base[l] + s_off[warp][l];
-            room = room && at + warp_tot[l] <= a.work.seg_cap;
-            pos[l] = at + lane_off[l];
-        }
-        if (room) {
+        for (int l = 0; l < 3; ++l) pos[l] = s_base[l] + s_off[warp][l] + lane_off[l];
+        {
+            const uint32_t cap = a.work.seg_cap;
             uint4* const out0 = reinterpret_cast<uint4*>(a.work.items + (size_t)(0 * kSubLists + sub) * a.work.seg_cap);
             uint4* const out1 = reinterpret_cast<uint4*>(a.work.items + (size_t)(1 * kSubLists + sub) * a.work.seg_cap);
             uint4* const out2 = reinterpret_cast<uint4*>(a.work.items + (size_t)(2 * kSubLists + sub) * a.work.seg_cap);
@@ -954,9 +953,16 @@ __global__ void __launch_bounds__(kThreads) k_enum_pairs(const EnumArgs a) {
                     const uint2 pred = __ldg(ent + (e - k));
                     const uint4 item = make_uint4(ent_s[s].y, pred.y, slot, 0u);
                     const uint32_t n_rect = my_rect + (pred.x >> 31);
-                    if (n_rect == 2) out0[pos[0]++] = item;
-                    else if (n_rect == 0) out1[pos[1]++] = item;
-                    else out2[pos[2]++] = item;
+                    if (n_rect == 2) {
+                        if (pos[0] < cap) out0[pos[0]] = item;
+                        ++pos[0];
+                    } else if (n_rect == 0) {
+                        if (pos[1] < cap) out1[pos[1]] = item;
+                        ++pos[1];
+                    } else {
+                        if (pos[2] < cap) out2[pos[2]] = item;
+                        ++pos[2];
+                    }
                 }
             }
         }
@@ -1111,6 +1117,7 @@ constexpr uint32_t kSolveBuf = 4 * kThreads;
 #ifndef CB200_LB_SOLVE
 #define CB200_LB_SOLVE 4
 #endif
+template <bool WIDE>  // WIDE: records through 256-bit loads
 __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveArgs a) {
     __shared__ PairEvent s_ev[kSolveBuf];
     __shared__ WorkIndex s_idx;
@@ -1158,8 +1165,13 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
                 // all twelve 16-byte loads of the two records are issued before anything depends on them
                 RecHead ha, hb;
                 DurHb da, db;
-                load_rec_keep(a.rec, ia, keep, &ha, &da);
-                load_rec_keep(a.rec, ib, keep, &hb, &db);
+                if (WIDE) {
+                    load_rec_wide(a.rec, ia, &ha, &da);
+                    load_rec_wide(a.rec, ib, &hb, &db);
+                } else {
+                    load_rec_keep(a.rec, ia, keep, &ha, &da);
+                    load_rec_keep(a.rec, ib, keep, &hb, &db);
+                }
                 bool a_is_hi = true;  // overlap pairs arrive as (hi, lo)
                 if (!sep) {
                     present = (a.dbg & 4u) ? true : candidate_test(a.cd, ha, hb, slot, &a_is_hi);

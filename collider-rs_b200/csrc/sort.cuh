@@ -315,6 +315,99 @@ __global__ void __launch_bounds__(256) k_bs_local(const Key128* __restrict__ in,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// One-shot variant (no host round trip between the launches): two bucket regions cut in one pass.
+//   region A  keys whose time equals the smallest time of the set — in a bulk step that is everything that happens exactly
+//             at T (delay 0.0): there the tie word decides, so they are cut linearly on (class, first label)
+//   region B  all later keys, cut linearly in time as above
+// Both cuts are monotone in the (time, tie) order, so bucket order == key order and the warp rank sort finishes the job.
+// The host looks at `big` only after everything (decode and the copy to the host included) has been queued; a bucket that
+// came out too large for a warp sends it to the recursive path above.
+__device__ __forceinline__ uint32_t bs2_bucket(const Key128& k, const BsRange& r, int log2_buckets, uint32_t label_bound) {
+    const uint32_t nb = 1u << log2_buckets;
+    if (k.hi == r.lo) {
+        const uint32_t half = nb >> 1;
+        const bool pair = (k.lo & kPairClass) != 0;
+        uint32_t label = pair ? (uint32_t)((k.lo >> 32) & 0x7fffffffu) : (uint32_t)min(k.lo, 0xffffffffull);
+        label = min(label, label_bound - 1u);
+        return (pair ? half : 0u) + (uint32_t)(((unsigned long long)label * half) / label_bound);
+    }
+    return nb + bs_bucket(k.hi, r, log2_buckets, 1);  // (r.hi > r.lo here)
+}
+__global__ void k_bs2_count(uint32_t n, const Key128* __restrict__ keys, const BsRange* r, int log2_buckets, uint32_t label_bound, uint32_t* count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&count[bs2_bucket(keys[i], *r, log2_buckets, label_bound)], 1u);
+}
+__global__ void k_bs2_scatter(uint32_t n, const Key128* __restrict__ keys, const BsRange* r, int log2_buckets, uint32_t label_bound, uint32_t* cursor,
+                              Key128* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Key128 k = keys[i];
+    out[atomicAdd(&cursor[bs2_bucket(k, *r, log2_buckets, label_bound)], 1u)] = k;
+}
+
+// The scan of k_bs_scan with eight buckets per thread and round (the one-shot path has twice the buckets).
+__global__ void __launch_bounds__(1024) k_bs_scan8(const uint32_t* count, uint32_t n_buckets, uint32_t* offsets, uint32_t* cursor, uint32_t* big) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry, s_big;
+    if (threadIdx.x == 0) {
+        s_carry = 0;
+        s_big = 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_buckets; base += 8192) {
+        const uint32_t i0 = base + threadIdx.x * 8u;
+        uint32_t v[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[j] = i0 + j < n_buckets ? count[i0 + j] : 0u;
+            sum += v[j];
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t ws = s_w[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += t;
+            }
+            s_w[lane] = ws;
+        }
+        __syncthreads();
+        uint32_t excl = s_carry + inc - sum + (warp ? s_w[warp - 1] : 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (i0 + j < n_buckets) {
+                offsets[i0 + j] = excl;
+                cursor[i0 + j] = excl;
+                if (v[j] > (uint32_t)kBsMaxBucket) {
+                    const uint32_t k = atomicAdd(&s_big, 1u);
+                    if (k < (uint32_t)kBsMaxBig) {
+                        big[1 + 2 * k] = excl;
+                        big[2 + 2 * k] = v[j];
+                    }
+                }
+            }
+            excl += v[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        offsets[n_buckets] = s_carry;
+        big[0] = s_big;
+    }
+}
+
 // Decode sorted keys to the C-ABI event records (layout of cb200_event: f64 time, u64 a, u64 b, u32 kind, u32 pad).
 struct EventOut {
     double time;

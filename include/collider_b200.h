@@ -144,6 +144,12 @@ int cb200_get_grid(cb200_ctx* ctx, int* log2_w, int* log2_h);
 int cb200_set_resort_period(cb200_ctx* ctx, int steps);
 uint64_t cb200_resort_count(const cb200_ctx* ctx);
 
+/* Event-queue order (EventKey's Ord, events.rs:28-68, under the canonical tie order): cb200_fetch_events sorts the
+ * step's events on the device with a one-shot bucket sort (ties at the step time cut on the tie word, later events cut
+ * by time) and copies them out behind it — one synchronisation per fetch.  A step with a heavy tie at a LATER time takes
+ * the recursive path instead; this counts how often that happened (environment: CB200_SORT=slow forces it). */
+uint64_t cb200_event_sort_fallbacks(const cb200_ctx* ctx);
+
 /* Pinned (page-locked) host memory for the arrays handed to upload_state / bulk_update / fetch_events, so that
  * the H2D / D2H copies inside those calls run at full PCIe speed.  Plain malloc'd memory is accepted too. */
 void* cb200_host_alloc(uint64_t bytes);

@@ -208,11 +208,14 @@ def canonical_order(ev):
     return np.lexsort((ev["b"], kbit, ev["a"], cls, ev["time"]))
 
 
-def test_event_queue_order_at_scale(oracle):
-    """The queue materialisation (bucket sort on the time key, recursing into heavy ties, radix fallback) on 120k hitboxes:
+@pytest.mark.parametrize("sort_mode", ["oneshot", "slow"])
+def test_event_queue_order_at_scale(oracle, sort_mode, monkeypatch):
+    """The queue materialisation (one-shot two-region bucket sort; CB200_SORT=slow: bucket sort on the time key, recursing
+    into heavy ties, radix fallback) on 120k hitboxes:
     step 1 starts at T = 0 (event times span every binade) and is compared with the oracle event by event; step 2 runs
     without processing the Collide events of step 1, so every pair already in contact reports time == T exactly (tens of
     thousands of ties ordered by the tie word) — checked for canonical order, uniqueness and count."""
+    monkeypatch.setenv("CB200_SORT", sort_mode)
     n = 120_000
     scene = scenes.uniform_density(n, density=0.05, seed=4711)
     orc, eng = seeded(oracle, scene)
@@ -231,6 +234,45 @@ def test_event_queue_order_at_scale(oracle):
     np.testing.assert_array_equal(canonical_order(ev), np.arange(len(ev)))
     key = (ev["a"].astype(np.uint64) << np.uint64(32) | ev["b"]) * np.uint64(4) + ev["kind"].astype(np.uint64)
     assert len(np.unique(key)) == len(ev)
+    assert eng.event_sort_fallbacks() == 0, "ties at the step time must not leave the one-shot path"
+
+
+def test_event_queue_heavy_ties_at_later_times(oracle):
+    """Two velocity classes and end_time = +inf: half of the Reiterate events fall on exactly T + 2, the other half on
+    exactly T + 4 (cell periods, grid.rs:61-72), with the pair events spread around them.  The tie at T + 4 is not at the
+    first event time, so the one-shot sort reports an oversized bucket and the recursive path takes over; then a second
+    step where every event time is equal (no pair events at all)."""
+    n = 20_000
+    scene = scenes.uniform_density(n, seed=99)
+    half = np.arange(n) % 2 == 0
+    vx = np.where(half, 2.0, -1.0)
+    vy = np.where(half, 2.0, 0.5)
+    orc, eng = seeded(oracle, scene)
+    orc.bulk_update(end_time=cb.INF, vx=vx, vy=vy)
+    res = eng.bulk_update(0.0, end_time=cb.INF, vel_x=vx, vel_y=vy)
+    t, kind, a, b = oracle_events(orc)
+    ev = eng.fetch_events()
+    assert len(ev) == len(t) == res.n_events
+    assert (t == 2.0).sum() >= n // 2 and (t == 4.0).sum() >= n // 2 - 1
+    np.testing.assert_array_equal(ev["kind"], kind)
+    np.testing.assert_array_equal(ev["a"], a)
+    np.testing.assert_array_equal(ev["b"], np.where(kind == 0, 0, b))
+    np.testing.assert_array_equal(bits(ev["time"]), bits(t))
+    assert eng.event_sort_fallbacks() == 1
+    # all hitboxes move alike: no pair can collide, every event is a Reiterate at exactly T + 2 -> region A alone
+    scene2 = scenes.uniform_density(n, seed=100)
+    orc2, eng2 = seeded(oracle, scene2)
+    v = np.full(n, 2.0)
+    orc2.bulk_update(end_time=cb.INF, vx=v, vy=v)
+    res2 = eng2.bulk_update(0.0, end_time=cb.INF, vel_x=v, vel_y=v)
+    t2, kind2, a2, b2 = oracle_events(orc2)
+    ev2 = eng2.fetch_events()
+    assert len(ev2) == len(t2) == res2.n_events
+    sol = kind2 == 0
+    assert sol.sum() == n and np.all(t2[sol] == 2.0)
+    np.testing.assert_array_equal(ev2["kind"], kind2)
+    np.testing.assert_array_equal(ev2["a"], a2)
+    np.testing.assert_array_equal(bits(ev2["time"]), bits(t2))
 
 
 def test_aliased_grid_is_still_exact(oracle):
