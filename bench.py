@@ -274,11 +274,14 @@ def _main(out):
     for _ in range(3):
         e2e_step()
     d2h = 0
+    e2e_each = []
     barrier()
     t1 = time.perf_counter()
     for _ in range(args.steps):
+        ts = time.perf_counter()
         r, evs = e2e_step()
         d2h += evs.nbytes + C_sizeof_result(cb)
+        e2e_each.append((time.perf_counter() - ts) * 1e3)
     barrier()
     e2e_wall = time.perf_counter() - t1
     sampler.stop_flag = True
@@ -334,7 +337,8 @@ def _main(out):
             "per_step": {"cell_entries": E, "cells": Cc, "work_items": W, "pair_solves": P, "events": V},
             "gpu_launches": int(launches),
             "e2e": {"value": n * world * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(16 * n), "d2h_bytes_per_step": int(d2h / K),
-                    "ms_per_step": e2e_max / K * 1e3},
+                    "ms_per_step": e2e_max / K * 1e3, "ms_per_step_median_rank0": float(np.median(e2e_each)), "ms_per_step_max_rank0": float(np.max(e2e_each)),
+                    "event_sort_fallbacks": eng.event_sort_fallbacks()},
             "roofline": {"bound": "hbm", "kernel": kernel_of[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_kind": peak_kind,
                          "per_kernel": {kernel_of[k]: {"ms": stage_ms[k], "bytes": alg[k], "frac": alg[k] / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak}

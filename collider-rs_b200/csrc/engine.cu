@@ -145,7 +145,8 @@ struct cb200_ctx {
 
     DevBuf<PairEvent> events;
     DevBuf<MinKey> partial;
-    uint32_t grid_a = 0, grid_p = 0;
+    uint32_t grid_a = 0, grid_p = 0, grid_s = 0;        // blocks of stage A, of the enumeration, of the solve stage
+    uint32_t per_sm_a = 8, per_sm_p = 8, per_sm_s = 4;  // ... per SM (CB200_PER_SM_A / _P / _S); solve: one wave (measured 84 -> 79 us)
     Counters* d_ctr = nullptr;
     StepResultDev* d_res = nullptr;  // device alias of h_res (mapped)
     StepResultDev* h_res = nullptr;  // pinned, mapped
@@ -311,6 +312,9 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if (const char* rp = getenv("CB200_RESORT_PERIOD")) c->resort_period = std::max(0, atoi(rp));
     if (const char* sa = getenv("CB200_STAGE_A")) c->stage_a_tma = strcmp(sa, "tma") == 0;
     if (const char* w = getenv("CB200_LD256")) c->ld256 = w[0] != '0';
+    if (const char* v = getenv("CB200_PER_SM_A")) c->per_sm_a = (uint32_t)std::max(1, std::min(32, atoi(v)));
+    if (const char* v = getenv("CB200_PER_SM_P")) c->per_sm_p = (uint32_t)std::max(1, std::min(32, atoi(v)));
+    if (const char* v = getenv("CB200_PER_SM_S")) c->per_sm_s = (uint32_t)std::max(1, std::min(32, atoi(v)));
     if ((e = cudaFuncSetAttribute(k_stage_a_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(StageATile)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_stage_a_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(StageATile)))) != cudaSuccess)
         return bail("cudaFuncSetAttribute", e);
@@ -625,7 +629,7 @@ static int reserve_step_buffers(cb200_ctx* ctx) {
     CU(ctx->slots.reserve(n_slots));
     CU(ctx->chunk_base.reserve(n_slots / kScanChunk));
     if (ctx->entries.cap == 0) CU(ctx->entries.reserve((size_t)n * 4 + 1024));
-    if (ctx->work.cap == 0) CU(ctx->work.reserve(std::max<size_t>((size_t)n * 2 + 1024, (size_t)kWorkLists * 256)));
+    if (ctx->work.cap == 0) CU(ctx->work.reserve(std::max<size_t>((size_t)n * 2 + 1024, (size_t)kWorkLists * 2048)));
     CU(ctx->work_count.reserve(kWorkLists));
     if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
     CU(ctx->partial.reserve((size_t)ctx->sm_count * 16));
@@ -645,13 +649,13 @@ static int prepare_buffers(cb200_ctx* ctx) {
     CU(ctx->slots.reserve(n_slots));
     CU(ctx->chunk_base.reserve(n_slots / kScanChunk));
     if (ctx->entries.cap == 0) CU(ctx->entries.reserve((size_t)n * 4 + 1024));
-    if (ctx->work.cap == 0) CU(ctx->work.reserve(std::max<size_t>((size_t)n * 2 + 1024, (size_t)kWorkLists * 256)));
+    if (ctx->work.cap == 0) CU(ctx->work.reserve(std::max<size_t>((size_t)n * 2 + 1024, (size_t)kWorkLists * 2048)));
     CU(ctx->work_count.reserve(kWorkLists));
     if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
-    const uint32_t per_sm = 8;
-    ctx->grid_a = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, ctx->sm_count * per_sm));
-    ctx->grid_p = ctx->sm_count * per_sm;
-    CU(ctx->partial.reserve(ctx->grid_a + ctx->grid_p));
+    ctx->grid_a = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, ctx->sm_count * ctx->per_sm_a));
+    ctx->grid_p = ctx->sm_count * ctx->per_sm_p;
+    ctx->grid_s = ctx->sm_count * ctx->per_sm_s;
+    CU(ctx->partial.reserve(ctx->grid_a + ctx->grid_s));
     // the rows of the previous step's records move with a re-sort: only between steps, never on a re-run
     if (ctx->need_resort || (ctx->resort_period > 0 && ctx->steps_since_resort >= (uint32_t)ctx->resort_period)) {
         int rc = resort_rows(ctx);
@@ -818,8 +822,8 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     sv.vs = vs;
     sv.col_lo = sh.col_lo;
     sv.col_hi = sh.col_hi;
-    if (ctx->ld256) k_solve<true><<<ctx->grid_p, kThreads, 0, ctx->stream>>>(sv);
-    else k_solve<false><<<ctx->grid_p, kThreads, 0, ctx->stream>>>(sv);
+    if (ctx->ld256) k_solve<true><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
+    else k_solve<false><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
     DBG_SYNC("k_solve");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
     CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
@@ -1350,12 +1354,17 @@ static int sort_range(cb200_ctx* ctx, Key128* keys, Key128* tmp, uint32_t n, int
     return CB200_OK;
 }
 
-// Order keys of every queued event of the last step, in keys_a (queued on the stream).
-static int build_sort_keys(cb200_ctx* ctx, uint32_t n_pairs, uint64_t n_solitaire) {
+// Order keys of every queued event of the last step, in keys_a (queued on the stream); range (optional, initialised by the
+// caller): min / max of their time keys.
+static int build_sort_keys(cb200_ctx* ctx, uint32_t n_pairs, uint64_t n_solitaire, BsRange* range) {
     CU(cudaMemsetAsync(&ctx->d_ctr->n_sort_keys, 0, 8, ctx->stream));
-    if (ctx->n) k_keys_solitaire<<<(ctx->n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(ctx->n, ctx->reit.p, ctx->col[9].p, ctx->label.p, ctx->keys_a.p, ctx->d_ctr);
-    if (n_pairs) k_keys_pairs<<<(n_pairs + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(n_pairs, ctx->events.p, ctx->keys_a.p, n_solitaire);
-    ctx->launches += 2;
+    const uint32_t max_blocks = (uint32_t)ctx->sm_count * 8u;
+    if (ctx->n && n_solitaire)
+        k_keys_solitaire<<<std::min<uint32_t>((ctx->n + kThreads - 1) / kThreads, max_blocks), kThreads, 0, ctx->stream>>>(ctx->n, ctx->reit.p, ctx->col[9].p, ctx->label.p,
+                                                                                                                     ctx->keys_a.p, ctx->d_ctr, range);
+    if (n_pairs)
+        k_keys_pairs<<<std::min<uint32_t>((n_pairs + kThreads - 1) / kThreads, max_blocks), kThreads, 0, ctx->stream>>>(n_pairs, ctx->events.p, ctx->keys_a.p, n_solitaire, range);
+    ctx->launches += (ctx->n && n_solitaire ? 1 : 0) + (n_pairs ? 1 : 0);
     return CB200_OK;
 }
 
@@ -1363,25 +1372,27 @@ static int build_sort_keys(cb200_ctx* ctx, uint32_t n_pairs, uint64_t n_solitair
 // decode into ev_out.  Whether it succeeded (no bucket too large for a warp) is in ctx->h_sort_big[0] once the stream has
 // been synchronised; the caller checks it and falls back to sort_events_slow.
 static int enqueue_sort_oneshot(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, uint64_t n_solitaire) {
-    int rc = build_sort_keys(ctx, n_pairs, n_solitaire);
-    if (rc != CB200_OK) return rc;
     int log2_buckets = 6;
     while ((1u << log2_buckets) * 12u < nt && log2_buckets < 22) ++log2_buckets;
     const uint32_t nb = 1u << log2_buckets, n_buckets = 2 * nb;  // region A (ties at the first time) + region B (by time)
+    const uint32_t scan_blocks = (n_buckets + kBs2Chunk - 1) / kBs2Chunk;
     DevBuf<uint32_t>& tab = ctx->bs_tab[0];
-    CU(tab.reserve(2 * (size_t)n_buckets + 2 + 8));
-    uint32_t* count = tab.p;                   // then: offsets [n_buckets + 1]
-    uint32_t* cursor = tab.p + n_buckets + 1;  // [n_buckets]
-    BsRange* range = reinterpret_cast<BsRange*>(tab.p + ((2 * (size_t)n_buckets + 2) & ~(size_t)1));
+    CU(tab.reserve(2 * (size_t)n_buckets + 2 + 8 + scan_blocks));
+    uint32_t* count = tab.p;                   // [n_buckets + 1] then: offsets
+    uint32_t* cursor = tab.p + n_buckets + 4;  // [n_buckets] (16-byte aligned like count)
+    BsRange* range = reinterpret_cast<BsRange*>(tab.p + 2 * (size_t)n_buckets + 4);
+    uint32_t* block_total = tab.p + 2 * (size_t)n_buckets + 8;
     const BsRange init{~0ull, 0ull};
     CU(cudaMemsetAsync(count, 0, ((size_t)n_buckets + 1) * 4, ctx->stream));
     CU(cudaMemcpyAsync(range, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = build_sort_keys(ctx, n_pairs, n_solitaire, range);
+    if (rc != CB200_OK) return rc;
     const uint32_t blocks = (nt + kThreads - 1) / kThreads;
     const uint32_t label_bound = std::max<uint32_t>(1u, ctx->sharded ? (uint32_t)std::min<uint64_t>(ctx->id_space, 0x7fffffffull) : ctx->n);
     Key128 *keys = ctx->keys_a.p, *tmp = ctx->keys_b.p;
-    k_bs_minmax<<<std::min<uint32_t>(blocks, 1024), kThreads, 0, ctx->stream>>>(nt, keys, 1, range);
     k_bs2_count<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, range, log2_buckets, label_bound, count);
-    k_bs_scan8<<<1, 1024, 0, ctx->stream>>>(count, n_buckets, count, cursor, ctx->d_sort_big);
+    k_bs2_scan_local<<<scan_blocks, 256, 0, ctx->stream>>>(count, n_buckets, cursor, block_total);
+    k_bs2_scan_add<<<scan_blocks, 256, 0, ctx->stream>>>(count, n_buckets, cursor, block_total, ctx->d_sort_big);
     k_bs2_scatter<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, range, log2_buckets, label_bound, cursor, tmp);
     k_bs_local<<<std::min<uint32_t>((n_buckets + 7) / 8, (uint32_t)ctx->sm_count * 8u), 256, 0, ctx->stream>>>(tmp, count, n_buckets, keys);
     k_decode_events<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p, ctx->last_add_mode ? 1 : 0);
@@ -1392,7 +1403,7 @@ static int enqueue_sort_oneshot(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, u
 
 // Recursive bucket sort, then the LSD radix sort: for steps with many events at one later time.
 static int sort_events_slow(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, uint64_t n_solitaire) {
-    int rc = build_sort_keys(ctx, n_pairs, n_solitaire);
+    int rc = build_sort_keys(ctx, n_pairs, n_solitaire, nullptr);
     if (rc != CB200_OK) return rc;
     const uint32_t n_blocks = (nt + kRsTile - 1) / kRsTile;
     CU(ctx->rs_hist.reserve((size_t)16 * n_blocks));

@@ -13,18 +13,61 @@ struct alignas(16) Key128 {
 };
 
 // Reiterate events live in the state columns (reit flag + internal end_time); append their keys.
-__global__ void k_keys_solitaire(uint32_t n, const uint8_t* __restrict__ reit, const double* __restrict__ end, const uint32_t* __restrict__ gid,
-                                 Key128* keys, Counters* ctr) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !reit[i]) return;
-    const unsigned long long pos = warp_agg_claim(&ctr->n_sort_keys);
-    keys[pos] = Key128{(unsigned long long)(gid ? gid[i] : i), time_key(end[i])};
+// Both key kernels also reduce the range of the time keys they produce into *range (min, max; null: not wanted): one
+// atomic pair per block instead of a separate pass over the keys.
+struct BsRange {
+    unsigned long long lo, hi;  // min / max of a key field
+};
+__device__ __forceinline__ void block_range_reduce(unsigned long long lo, unsigned long long hi, BsRange* range) {
+    __shared__ unsigned long long s_lo[32], s_hi[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) {
+        s_lo[warp] = lo;
+        s_hi[warp] = hi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        lo = lane < nw ? s_lo[lane] : ~0ull;
+        hi = lane < nw ? s_hi[lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0 && lo <= hi) {
+            atomicMin(&range->lo, lo);
+            atomicMax(&range->hi, hi);
+        }
+    }
 }
-__global__ void k_keys_pairs(uint32_t n_ev, const PairEvent* __restrict__ ev, Key128* keys, unsigned long long base) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ev) return;
-    const PairEvent e = ev[i];
-    keys[base + i] = Key128{kPairClass | ((unsigned long long)e.a << 32) | e.b_kind, time_key(e.time)};
+__global__ void k_keys_solitaire(uint32_t n, const uint8_t* __restrict__ reit, const double* __restrict__ end, const uint32_t* __restrict__ gid,
+                                 Key128* keys, Counters* ctr, BsRange* range) {
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (!reit[i]) continue;
+        const unsigned long long pos = warp_agg_claim(&ctr->n_sort_keys);
+        const unsigned long long t = time_key(end[i]);
+        keys[pos] = Key128{(unsigned long long)(gid ? gid[i] : i), t};
+        lo = min(lo, t);
+        hi = max(hi, t);
+    }
+    if (range) block_range_reduce(lo, hi, range);
+}
+__global__ void k_keys_pairs(uint32_t n_ev, const PairEvent* __restrict__ ev, Key128* keys, unsigned long long base, BsRange* range) {
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ev; i += gridDim.x * blockDim.x) {
+        const PairEvent e = ev[i];
+        const unsigned long long t = time_key(e.time);
+        keys[base + i] = Key128{kPairClass | ((unsigned long long)e.a << 32) | e.b_kind, t};
+        lo = min(lo, t);
+        hi = max(hi, t);
+    }
+    if (range) block_range_reduce(lo, hi, range);
 }
 __global__ void k_key_diff(uint32_t n, const Key128* __restrict__ keys, Counters* ctr) {
     const Key128 k0 = keys[0];
@@ -187,9 +230,6 @@ constexpr int kBsMaxBucket = 128;  // keys a warp sorts in shared memory
 // The buckets are cut on ONE 64-bit field of the key: the time key (field 1), or — for a set of keys that all carry the
 // same time, e.g. everything that happens exactly at T — the tie word (field 0).  Buckets that come out too large for a warp
 // are sorted again on their own range (the host recurses, sort_range in engine.cu).
-struct BsRange {
-    unsigned long long lo, hi;  // min / max of the field
-};
 __device__ __forceinline__ unsigned long long bs_field(const Key128& k, int field) { return field ? k.hi : k.lo; }
 __global__ void k_bs_minmax(uint32_t n, const Key128* __restrict__ keys, int field, BsRange* r) {
     unsigned long long lo = ~0ull, hi = 0ull;
@@ -346,65 +386,86 @@ __global__ void k_bs2_scatter(uint32_t n, const Key128* __restrict__ keys, const
     out[atomicAdd(&cursor[bs2_bucket(k, *r, log2_buckets, label_bound)], 1u)] = k;
 }
 
-// The scan of k_bs_scan with eight buckets per thread and round (the one-shot path has twice the buckets).
-__global__ void __launch_bounds__(1024) k_bs_scan8(const uint32_t* count, uint32_t n_buckets, uint32_t* offsets, uint32_t* cursor, uint32_t* big) {
-    __shared__ uint32_t s_w[32];
-    __shared__ uint32_t s_carry, s_big;
-    if (threadIdx.x == 0) {
-        s_carry = 0;
-        s_big = 0;
+// The bucket scan of the one-shot path, over all SMs (one block walking 2 x 32768 buckets took 81 us — its strided 4-byte
+// stores serialise in one SM's L1): k_bs2_scan_local scans kBs2Chunk buckets per block (eight per thread, 32-byte
+// accesses) and leaves the block totals; k_bs2_scan_add gives every block the sum of the totals before it (there are at
+// most a few thousand), writes offsets and cursors, and reports the buckets that are too large for a warp.
+constexpr int kBs2Chunk = 256 * 8;
+__global__ void __launch_bounds__(256) k_bs2_scan_local(const uint32_t* __restrict__ count, uint32_t n_buckets, uint32_t* __restrict__ local,
+                                                        uint32_t* __restrict__ block_total) {
+    __shared__ uint32_t s_w[8];
+    const uint32_t i0 = blockIdx.x * kBs2Chunk + threadIdx.x * 8u;
+    uint32_t v[8], sum = 0;
+    if (i0 + 8 <= n_buckets) {
+        const uint4 q0 = *reinterpret_cast<const uint4*>(count + i0), q1 = *reinterpret_cast<const uint4*>(count + i0 + 4);
+        v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = i0 + j < n_buckets ? count[i0 + j] : 0u;
     }
-    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += v[j];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < n_buckets; base += 8192) {
-        const uint32_t i0 = base + threadIdx.x * 8u;
-        uint32_t v[8], sum = 0;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        before += w < warp ? s_w[w] : 0u;
+        total += s_w[w];
+    }
+    uint32_t excl = before + inc - sum;
+    if (i0 + 8 <= n_buckets) {
+        uint4 q0, q1;
+        q0.x = excl; excl += v[0]; q0.y = excl; excl += v[1]; q0.z = excl; excl += v[2]; q0.w = excl; excl += v[3];
+        q1.x = excl; excl += v[4]; q1.y = excl; excl += v[5]; q1.z = excl; excl += v[6]; q1.w = excl;
+        *reinterpret_cast<uint4*>(local + i0) = q0;
+        *reinterpret_cast<uint4*>(local + i0 + 4) = q1;
+    } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            v[j] = i0 + j < n_buckets ? count[i0 + j] : 0u;
-            sum += v[j];
-        }
-        uint32_t inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t ws = s_w[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
-                if (lane >= o) ws += t;
-            }
-            s_w[lane] = ws;
-        }
-        __syncthreads();
-        uint32_t excl = s_carry + inc - sum + (warp ? s_w[warp - 1] : 0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (i0 + j < n_buckets) {
-                offsets[i0 + j] = excl;
-                cursor[i0 + j] = excl;
-                if (v[j] > (uint32_t)kBsMaxBucket) {
-                    const uint32_t k = atomicAdd(&s_big, 1u);
-                    if (k < (uint32_t)kBsMaxBig) {
-                        big[1 + 2 * k] = excl;
-                        big[2 + 2 * k] = v[j];
-                    }
-                }
-            }
+            if (i0 + j < n_buckets) local[i0 + j] = excl;
             excl += v[j];
         }
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = excl;
-        __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        offsets[n_buckets] = s_carry;
-        big[0] = s_big;
+    if (threadIdx.x == 0) block_total[blockIdx.x] = total;
+}
+// count -> offsets in place (offsets[n_buckets] = total); cursor = the block-local scan on entry, a copy of offsets on exit
+__global__ void __launch_bounds__(256) k_bs2_scan_add(uint32_t* count_offsets, uint32_t n_buckets, uint32_t* cursor, const uint32_t* __restrict__ block_total,
+                                                      uint32_t* big /* mapped host memory; big[0] zeroed by the host */) {
+    __shared__ uint32_t s_w[8];
+    uint32_t part = 0;
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += blockDim.x) part += block_total[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = part;
+    __syncthreads();
+    uint32_t prefix = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) prefix += s_w[w];
+    const uint32_t i0 = blockIdx.x * kBs2Chunk + threadIdx.x * 8u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t i = i0 + j;
+        if (i < n_buckets) {
+            const uint32_t v = count_offsets[i], off = prefix + cursor[i];
+            count_offsets[i] = off;
+            cursor[i] = off;
+            if (v > (uint32_t)kBsMaxBucket) {
+                const uint32_t k = atomicAdd(big, 1u);
+                if (k < (uint32_t)kBsMaxBig) {
+                    big[1 + 2 * k] = off;
+                    big[2 + 2 * k] = v;
+                }
+            }
+            if (i == n_buckets - 1) count_offsets[n_buckets] = off + v;
+        }
     }
 }
 
