@@ -103,6 +103,7 @@ struct cb200_ctx {
     unsigned long long* d_n_imm = nullptr;
     uint32_t graph_kernels[4] = {};  // kernels inside each captured graph (for the launch counter)
     uint64_t graph_launches = 0, graph_captures = 0;
+    bool solve_two_phase = false;  // CB200_SOLVE=2: k_solve2, filter + dense solve (measured slower: 89 vs 79 us at config 3; kept for A/B and as a second parity check)
     bool ld256 = false;        // CB200_LD256=1: k_solve gathers records with 256-bit loads (measured: 86 vs 84 us, kept for A/B)
     bool stage_a_tma = false;  // CB200_STAGE_A=tma: input columns staged through shared memory by bulk async copies (measured slower, kept for A/B)
     // sharding
@@ -312,6 +313,7 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if (const char* rp = getenv("CB200_RESORT_PERIOD")) c->resort_period = std::max(0, atoi(rp));
     if (const char* sa = getenv("CB200_STAGE_A")) c->stage_a_tma = strcmp(sa, "tma") == 0;
     if (const char* w = getenv("CB200_LD256")) c->ld256 = w[0] != '0';
+    if (const char* w = getenv("CB200_SOLVE")) c->solve_two_phase = w[0] == '2';
     if (const char* v = getenv("CB200_PER_SM_A")) c->per_sm_a = (uint32_t)std::max(1, std::min(32, atoi(v)));
     if (const char* v = getenv("CB200_PER_SM_P")) c->per_sm_p = (uint32_t)std::max(1, std::min(32, atoi(v)));
     if (const char* v = getenv("CB200_PER_SM_S")) c->per_sm_s = (uint32_t)std::max(1, std::min(32, atoi(v)));
@@ -822,7 +824,8 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     sv.vs = vs;
     sv.col_lo = sh.col_lo;
     sv.col_hi = sh.col_hi;
-    if (ctx->ld256) k_solve<true><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
+    if (ctx->solve_two_phase && !sv.dbg) k_solve2<<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
+    else if (ctx->ld256) k_solve<true><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
     else k_solve<false><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
     DBG_SYNC("k_solve");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
@@ -950,6 +953,7 @@ static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
     if (const char* d = getenv("CB200_DBG_A")) mix((uint64_t)atoi(d) + 17);
     if (const char* d = getenv("CB200_DBG_S")) mix((uint64_t)atoi(d) + 31);
     mix(ctx->ld256 ? 257u : 129u);
+    mix(ctx->solve_two_phase ? 2u : 1u);
     return h ? h : 1;
 }
 
@@ -1232,7 +1236,7 @@ int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world 
         cudaFuncAttributes fa;
         const void* fns[] = {(const void*)k_step_zero, (const void*)k_stage_a<true>, (const void*)k_stage_a_tma<true>, (const void*)k_slab_header, (const void*)k_push_halo,
                              (const void*)k_wait_flags, (const void*)k_index_visitors<true>, (const void*)k_index_visitors<false>,
-                             (const void*)k_scan_slots, (const void*)k_scatter<true>, (const void*)k_enum_pairs, (const void*)k_solve<true>, (const void*)k_solve<false>,
+                             (const void*)k_scan_slots, (const void*)k_scatter<true>, (const void*)k_enum_pairs, (const void*)k_solve<true>, (const void*)k_solve<false>, (const void*)k_solve2,
                              (const void*)k_push_key, (const void*)k_reduce_keys, (const void*)k_resort_count, (const void*)k_resort_rank,
                              (const void*)k_resort_gather};
         for (const void* f : fns) CU(cudaFuncGetAttributes(&fa, f));

@@ -1110,6 +1110,63 @@ __device__ __forceinline__ bool gid_lookup(const SolveArgs& a, uint32_t n_local,
     return true;
 }
 
+// End of the solve stage (all threads of the block): block minimum and counters out; the last block to finish reduces every
+// per-block minimum of stage A and of this stage and publishes the step result.
+__device__ __forceinline__ void solve_epilogue(const SolveArgs& a, MinKey best, unsigned long long n_sep, unsigned long long n_col) {
+    __shared__ uint32_t s_last;
+    best = block_min(best);
+    const unsigned long long sep_tot = block_sum(n_sep), col_tot = block_sum(n_col);
+    if (threadIdx.x == 0) {
+        a.partial[a.n_partial_a + blockIdx.x] = best;
+        if (sep_tot) atomicAdd(&a.ctr->n_separate, sep_tot);
+        if (col_tot) atomicAdd(&a.ctr->n_collide, col_tot);
+        __threadfence();
+        s_last = atomicAdd(&a.ctr->done_blocks, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // last block: reduce every per-block minimum of stage A and of this stage, publish the step result
+    __threadfence();
+    best = MinKey{kKeyMax, kKeyMax};
+    const uint32_t n_partial = a.n_partial_a + gridDim.x;
+    for (uint32_t i = threadIdx.x; i < n_partial; i += blockDim.x) {
+        const volatile unsigned long long* q = reinterpret_cast<const volatile unsigned long long*>(&a.partial[i]);
+        const MinKey k{q[0], q[1]};
+        if (key_less(k, best)) best = k;
+    }
+    best = block_min(best);
+    if (threadIdx.x == 0) {
+        a.result->next_time = (best.t == kKeyMax && best.tie == kKeyMax) ? cb_inf() : key_time(best.t);
+        a.result->next_tie = best.tie;
+        {
+            const bool pair = (best.tie & kPairClass) != 0;
+            const uint32_t la = pair ? (uint32_t)((best.tie >> 32) & 0x7fffffffu) : (uint32_t)best.tie;
+            const uint32_t lb = a.add_mode ? (uint32_t)((best.tie & 0xffffffffu) >> 1) : (uint32_t)(best.tie & 0x7fffffffu);
+            const bool any = !(best.t == kKeyMax && best.tie == kKeyMax);
+            a.result->next_id_a = !any ? 0ull : (a.ids ? a.ids[la] : (uint64_t)la);
+            a.result->next_id_b = !any || !pair ? 0ull : (a.ids ? a.ids[lb] : (uint64_t)lb);
+        }
+        if (a.local_key) *a.local_key = best;
+        const volatile Counters* c = a.ctr;
+        Counters out;
+        out.n_entries = c->n_entries; out.n_cells = c->n_cells; out.n_separate = c->n_separate;
+        out.work_overflow = 0;
+        out.n_work = 0;
+        for (int l = 0; l < kWorkLists; ++l) {
+            out.work_overflow = max(out.work_overflow, a.work.count[l]);  // fullest sub-list
+            out.n_work += a.work.count[l];
+        }
+        out.pad0 = 0;
+        out.n_collide = c->n_collide;
+        out.n_pair_events = c->n_pair_events; out.n_solitaire = c->n_solitaire; out.err_slot = c->err_slot;
+        out.err_flags = c->err_flags; out.scan_ticket = c->scan_ticket; out.overflow_entries = c->overflow_entries;
+        out.done_blocks = c->done_blocks; out.n_local = c->n_local; out.overflow_send = c->overflow_send;
+        out.diff_hi = 0; out.diff_lo = 0; out.n_sort_keys = 0;
+        a.result->ctr = out;
+        __threadfence_system();
+    }
+}
+
 // Pair events are collected in shared memory and flushed with one global atomic per kSolveBuf events (instead of a
 // block scan + atomic + two barriers per iteration).
 constexpr uint32_t kSolveBuf = 4 * kThreads;
@@ -1121,7 +1178,7 @@ template <bool WIDE>  // WIDE: records through 256-bit loads
 __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveArgs a) {
     __shared__ PairEvent s_ev[kSolveBuf];
     __shared__ WorkIndex s_idx;
-    __shared__ uint32_t s_n, s_last;
+    __shared__ uint32_t s_n;
     __shared__ unsigned long long s_base;
     MinKey best{kKeyMax, kKeyMax};
     unsigned long long n_sep = 0, n_col = 0;
@@ -1213,57 +1270,163 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
         }
     }
     flush();
-    best = block_min(best);
-    const unsigned long long sep_tot = block_sum(n_sep), col_tot = block_sum(n_col);
+    solve_epilogue(a, best, n_sep, n_col);
+}
+
+// Two-phase solve stage (CB200_SOLVE=2; measured SLOWER than k_solve — 89 vs 79 us at config 3, 2.12 vs 1.92 ms at 1 shape
+// per unit^2 — and kept as an A/B variant and as a second implementation the parity tests run).  In k_solve above a thread carries its item through everything, and most items stop
+// early — the candidate test, and above all collide_time's swept-bounds test (solvers.rs:27-30) — so the sweep math ran with
+// 17 of 32 lanes on average (ncu, profiles/r1k_step_kernels.txt).  Here a block alternates between
+//   filter   one thread per work item: records, candidate test, duration, swept bounds of both shapes, touch test.  The
+//            survivors (record of the higher id, record of the lower id) go to a queue in shared memory; the overlapping
+//            pairs of the separate list go there directly
+//   solve    whenever 256 survivors are queued, one thread each: sweep_unpadded / separate_time with full warps, event
+//            append, running minimum.  The records are read again (they are in L1 / L2 from the filter)
+// The arithmetic is the same device functions in the same order as in k_solve (collide_time = bounds + touch + sweep), so
+// the results are bit-identical; tests/test_bulk_gpu.py runs both kernels against the oracle.  Why it loses: the second read
+// of the records and the extra barriers cost more than the idle lanes did — the stage is bound by the record gathers
+// (l1tex data-pipe wavefronts 46 %, the busiest unit), not by issue slots (31 %).
+constexpr uint32_t kQueueCap = 2 * kThreads;
+constexpr uint32_t kSepBit = 0x80000000u;  // in Survivor.y
+
+__global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve2(const SolveArgs a) {
+    __shared__ PairEvent s_ev[kSolveBuf];
+    __shared__ uint2 s_q[kQueueCap];  // (record of the hi id, record of the lo id | kSepBit)
+    __shared__ WorkIndex s_idx;
+    __shared__ uint32_t s_n, s_qn;
+    __shared__ unsigned long long s_base;
+    MinKey best{kKeyMax, kKeyMax};
+    unsigned long long n_sep = 0, n_col = 0;
     if (threadIdx.x == 0) {
-        a.partial[a.n_partial_a + blockIdx.x] = best;
-        if (sep_tot) atomicAdd(&a.ctr->n_separate, sep_tot);
-        if (col_tot) atomicAdd(&a.ctr->n_collide, col_tot);
-        __threadfence();
-        s_last = atomicAdd(&a.ctr->done_blocks, 1u) == gridDim.x - 1 ? 1u : 0u;
+        s_n = 0;
+        s_qn = 0;
+    }
+    work_index_build(a.work, &s_idx);  // (barriers inside)
+    const uint32_t n_cand = s_idx.first[kWorkLists];
+    const uint32_t total = n_cand + a.n_ov;
+    const uint32_t n_local = a.ctr->n_local;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const double T = a.dyn->T;
+    const uint64_t keep = l2_policy_evict_last();
+    auto flush = [&]() {  // all threads
+        __syncthreads();
+        const uint32_t n_ev = s_n;
+        if (n_ev) {
+            if (threadIdx.x == 0) s_base = atomicAdd(&a.ctr->n_pair_events, (unsigned long long)n_ev);
+            __syncthreads();
+            const unsigned long long pos = s_base;
+            for (uint32_t k = threadIdx.x; k < n_ev; k += blockDim.x)
+                if (pos + k < a.cap_events) a.events[pos + k] = s_ev[k];
+            __syncthreads();
+            if (threadIdx.x == 0) s_n = 0;
+            __syncthreads();
+        }
+    };
+    uint32_t pending_rounds = 0;
+    // solve phase: survivors s_q[first .. first + count), count <= blockDim.x (all threads call)
+    auto solve_batch = [&](uint32_t first, uint32_t count) {
+        if (threadIdx.x < count) {
+            const uint2 sv = s_q[first + threadIdx.x];
+            const bool sep = (sv.y & kSepBit) != 0;
+            RecHead hh, hl;
+            DurHb A, Bl;
+            load_rec_keep(a.rec, sv.x, keep, &hh, &A);
+            load_rec_keep(a.rec, sv.y & ~kSepBit, keep, &hl, &Bl);
+            // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486): advanced by T - start = 0
+            const DurHb B = advanced(Bl, 0.0);
+            double delay = sep ? separate_time(A, B, a.padding) : sweep_unpadded(A, B, true, fmin(A.dur, B.dur));
+            bool is_sep = sep;
+            if (a.add_mode && !sep && delay == 0.0) {
+                // immediate overlap: process_collision (collider.rs:177-197) queues the Separate
+                const unsigned long long at = atomicAdd(a.n_imm, 1ull);
+                if (at < a.cap_imm) a.imm_pairs[at] = make_uint2(hh.gid, hl.gid);
+                delay = separate_time(A, B, a.padding);
+                is_sep = true;
+            }
+            if (delay != delay) report_error(a.ctr, kFNan, hh.gid);
+            const double t = T + delay;
+            if (t < kHighTime) {
+                const uint32_t low = a.add_mode ? ((hl.gid << 1) | (is_sep ? 0u : 1u)) : (hl.gid | (is_sep ? 0u : kCollideBit));
+                s_ev[atomicAdd(&s_n, 1u)] = PairEvent{t, hh.gid, low};
+                const MinKey k{time_key(t), kPairClass | ((uint64_t)hh.gid << 32) | low};
+                if (key_less(k, best)) best = k;
+            }
+        }
+        // the event buffer holds kSolveBuf events and a batch adds at most blockDim.x
+        if (++pending_rounds == kSolveBuf / kThreads) {
+            flush();
+            pending_rounds = 0;
+        }
+    };
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
+        // ---- filter ----
+        const uint32_t p = base + threadIdx.x;
+        bool push = false;
+        uint2 sv = make_uint2(0u, 0u);
+        if (p < total) {
+            if (p >= n_cand) {
+                // an overlapping pair (hi, lo): solved by the rank that owns its cell column
+                const uint2 pr = a.ov_pairs[p - n_cand];
+                uint32_t ia, ib;
+                if (gid_lookup(a, n_local, pr.x, &ia) && gid_lookup(a, n_local, pr.y, &ib)) {
+                    const RecHead ha = load_head(a.rec, ia), hb = load_head(a.rec, ib);
+                    const int32_t owner_col = max(ha.sx, hb.sx);
+                    if (owner_col >= a.col_lo && owner_col < a.col_hi) {
+                        push = true;
+                        sv = make_uint2(ia, ib | kSepBit);
+                        n_sep += 1;
+                    }
+                }
+            } else {
+                const WorkItem it = work_item_at(a.work, &s_idx, p);
+                RecHead ha, hb;
+                DurHb da, db;
+                load_rec_keep(a.rec, it.a, keep, &ha, &da);
+                load_rec_keep(a.rec, it.b, keep, &hb, &db);
+                bool a_is_hi = true;
+                if (candidate_test(a.cd, ha, hb, it.slot, &a_is_hi)) {
+                    n_col += 1;
+                    // collide_time (solvers.rs:25-34) up to the touch test, on (hi, lo advanced by zero): only the four
+                    // advanced fields of the lower id's shape differ from its record
+                    const DurHb da0 = advanced(da, 0.0), db0 = advanced(db, 0.0);
+                    da.px = a_is_hi ? da.px : da0.px; da.py = a_is_hi ? da.py : da0.py; da.w = a_is_hi ? da.w : da0.w; da.h = a_is_hi ? da.h : da0.h;
+                    db.px = a_is_hi ? db0.px : db.px; db.py = a_is_hi ? db0.py : db.py; db.w = a_is_hi ? db0.w : db.w; db.h = a_is_hi ? db0.h : db.h;
+                    const double duration = a_is_hi ? fmin(da.dur, db.dur) : fmin(db.dur, da.dur);
+                    const Box4 ba = swept_bounds(da, duration), bb = swept_bounds(db, duration);
+                    if (!(ba.ok && bb.ok)) {
+                        report_error(a.ctr, kFNan, a_is_hi ? ha.gid : hb.gid);
+                    } else if (boxes_touch(ba, bb)) {
+                        push = true;
+                        sv = a_is_hi ? make_uint2(it.a, it.b) : make_uint2(it.b, it.a);
+                    }
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, push);
+        if (m) {
+            uint32_t at = 0;
+            if (lane == 0) at = atomicAdd(&s_qn, (uint32_t)__popc(m));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (push) s_q[at + __popc(m & ((1u << lane) - 1u))] = sv;
+        }
+        __syncthreads();
+        // ---- solve a full batch ----
+        const uint32_t q = s_qn;  // < 2 * blockDim.x
+        if (q >= blockDim.x) {
+            solve_batch(q - blockDim.x, blockDim.x);
+            __syncthreads();
+            if (threadIdx.x == 0) s_qn = q - blockDim.x;
+            __syncthreads();
+        }
     }
     __syncthreads();
-    if (!s_last) return;
-    // last block: reduce every per-block minimum of stage A and of this stage, publish the step result
-    __threadfence();
-    best = MinKey{kKeyMax, kKeyMax};
-    const uint32_t n_partial = a.n_partial_a + gridDim.x;
-    for (uint32_t i = threadIdx.x; i < n_partial; i += blockDim.x) {
-        const volatile unsigned long long* q = reinterpret_cast<const volatile unsigned long long*>(&a.partial[i]);
-        const MinKey k{q[0], q[1]};
-        if (key_less(k, best)) best = k;
+    {
+        const uint32_t q = s_qn;
+        if (q) solve_batch(0, q);
     }
-    best = block_min(best);
-    if (threadIdx.x == 0) {
-        a.result->next_time = (best.t == kKeyMax && best.tie == kKeyMax) ? cb_inf() : key_time(best.t);
-        a.result->next_tie = best.tie;
-        {
-            const bool pair = (best.tie & kPairClass) != 0;
-            const uint32_t la = pair ? (uint32_t)((best.tie >> 32) & 0x7fffffffu) : (uint32_t)best.tie;
-            const uint32_t lb = a.add_mode ? (uint32_t)((best.tie & 0xffffffffu) >> 1) : (uint32_t)(best.tie & 0x7fffffffu);
-            const bool any = !(best.t == kKeyMax && best.tie == kKeyMax);
-            a.result->next_id_a = !any ? 0ull : (a.ids ? a.ids[la] : (uint64_t)la);
-            a.result->next_id_b = !any || !pair ? 0ull : (a.ids ? a.ids[lb] : (uint64_t)lb);
-        }
-        if (a.local_key) *a.local_key = best;
-        const volatile Counters* c = a.ctr;
-        Counters out;
-        out.n_entries = c->n_entries; out.n_cells = c->n_cells; out.n_separate = c->n_separate;
-        out.work_overflow = 0;
-        out.n_work = 0;
-        for (int l = 0; l < kWorkLists; ++l) {
-            out.work_overflow = max(out.work_overflow, a.work.count[l]);  // fullest sub-list
-            out.n_work += a.work.count[l];
-        }
-        out.pad0 = 0;
-        out.n_collide = c->n_collide;
-        out.n_pair_events = c->n_pair_events; out.n_solitaire = c->n_solitaire; out.err_slot = c->err_slot;
-        out.err_flags = c->err_flags; out.scan_ticket = c->scan_ticket; out.overflow_entries = c->overflow_entries;
-        out.done_blocks = c->done_blocks; out.n_local = c->n_local; out.overflow_send = c->overflow_send;
-        out.diff_hi = 0; out.diff_lo = 0; out.n_sort_keys = 0;
-        a.result->ctr = out;
-        __threadfence_system();
-    }
+    flush();
+    solve_epilogue(a, best, n_sep, n_col);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -91,8 +91,10 @@ def drain_until(orc, t_stop):
             return n
 
 
+@pytest.mark.parametrize("solve", ["two_phase", "one_phase"])
 @pytest.mark.parametrize("n", [1, 2, 1000, 20000])
-def test_bulk_step_parity_uniform(oracle, n):
+def test_bulk_step_parity_uniform(oracle, n, solve, monkeypatch):
+    monkeypatch.setenv("CB200_SOLVE", "1" if solve == "one_phase" else "2")  # (read when the engine is created)
     scene = scenes.uniform_density(n)
     orc, eng = seeded(oracle, scene)
     orc.bulk_update(end_time=0.1, record_candidates=True)
@@ -167,8 +169,10 @@ def test_resizing_groups_and_negative_coordinates(oracle):
         eng.set_overlaps(*orc.dump_overlaps())
 
 
-def test_clustered_fast_small_shapes(oracle):
+@pytest.mark.parametrize("solve", ["two_phase", "one_phase"])
+def test_clustered_fast_small_shapes(oracle, solve, monkeypatch):
     """Config 5 at a size the oracle finishes quickly: dense cells and multi-cell sweeps."""
+    monkeypatch.setenv("CB200_SOLVE", "1" if solve == "one_phase" else "2")
     s = scenes.c5(20000)
     orc, eng = seeded(oracle, s)
     orc.bulk_update(end_time=0.1, record_candidates=True)
