@@ -137,6 +137,8 @@ def _bind(L):
     L.cb200_collider_rebin_count.restype = u64
     L.cb200_collider_prefetch_count.argtypes = [vp]
     L.cb200_collider_prefetch_count.restype = u64
+    L.cb200_collider_hitbox_cache_hits.argtypes = [vp]
+    L.cb200_collider_hitbox_cache_hits.restype = u64
     L.cb200_collider_engine.argtypes = [vp]
     L.cb200_collider_engine.restype = vp
     L._collider_bound = True
@@ -298,6 +300,9 @@ class Collider:
 
     def rebin_count(self) -> int:
         return int(self._L.cb200_collider_rebin_count(self._h))
+
+    def hitbox_cache_hits(self) -> int:
+        return int(self._L.cb200_collider_hitbox_cache_hits(self._h))
 
     def prefetch_count(self) -> int:
         return int(self._L.cb200_collider_prefetch_count(self._h))

@@ -68,6 +68,22 @@ struct cb200_collider {
         uint64_t ver_a, ver_b;
     };
     std::unordered_map<uint64_t, CachedSolve> solve_cache;
+    // get_hitbox answers that came back with the prefetched solves: (id, bits of the event time) -> hitbox at that time.
+    // Served only while the collider stands at that time and the hitbox still carries the version seen by the prefetch.
+    struct CachedHitbox {
+        uint64_t version;
+        double hb[9];
+        uint32_t kind, err;
+    };
+    struct HbKey {
+        uint64_t id, tbits;
+        bool operator==(const HbKey& o) const { return id == o.id && tbits == o.tbits; }
+    };
+    struct HbKeyHash {
+        size_t operator()(const HbKey& k) const { return (size_t)((k.id * 0x9E3779B97F4A7C15ull) ^ (k.tbits * 0xC2B2AE3D27D4EB4Full)); }
+    };
+    std::unordered_map<HbKey, CachedHitbox, HbKeyHash> hitbox_cache;
+    uint64_t hitbox_cache_hits = 0;
     uint64_t version_counter = 0;
     Mapped<PairJob> jobs;
     Mapped<PairOut> job_out;
@@ -499,7 +515,7 @@ int prefetch_solves(cb200_collider* c, uint64_t need_uid, const QEvent& need_ev,
     CCU(c->jobs.reserve(kPrefetchMax));
     CCU(c->job_out.reserve(kPrefetchMax));
     std::vector<uint64_t> uids;
-    std::vector<std::pair<uint64_t, uint64_t>> ab;
+    std::vector<std::pair<uint64_t, uint64_t>> ab, ids;
     uids.reserve(kPrefetchMax);
     auto push = [&](uint64_t uid, const QEvent& ev, double t) {
         auto ia = c->infos.find(ev.a), ib = c->infos.find(ev.b);
@@ -507,6 +523,7 @@ int prefetch_solves(cb200_collider* c, uint64_t need_uid, const QEvent& need_ev,
         c->jobs.h[uids.size()] = PairJob{ia->second.label, ib->second.label, ev.kind == CB200_EV_COLLIDE ? 1u : 0u, 0u, t};
         uids.push_back(uid);
         ab.emplace_back(ia->second.version, ib->second.version);
+        ids.emplace_back(ev.a, ev.b);
     };
     auto cached_valid = [&](uint64_t uid, const QEvent& ev) {
         auto it = c->solve_cache.find(uid);
@@ -537,7 +554,20 @@ int prefetch_solves(cb200_collider* c, uint64_t need_uid, const QEvent& need_ev,
     int rc = wait_head(c);
     if (rc != CB200_OK) return rc;
     if (c->solve_cache.size() > 8 * kPrefetchMax) c->solve_cache.clear();  // (stale entries of events that were cancelled)
-    for (uint32_t k = 0; k < n; ++k) c->solve_cache[uids[k]] = cb200_collider::CachedSolve{c->job_out.h[k].time, c->job_out.h[k].err, ab[k].first, ab[k].second};
+    if (c->hitbox_cache.size() > 16 * kPrefetchMax) c->hitbox_cache.clear();
+    for (uint32_t k = 0; k < n; ++k) {
+        const PairOut& o = c->job_out.h[k];
+        c->solve_cache[uids[k]] = cb200_collider::CachedSolve{o.time, o.err, ab[k].first, ab[k].second};
+        if (o.err_a == kFIdNotFound) continue;
+        uint64_t tbits;
+        const double t = c->jobs.h[k].t;
+        memcpy(&tbits, &t, 8);
+        cb200_collider::CachedHitbox ha{ab[k].first, {}, o.kind_a, o.err_a}, hb{ab[k].second, {}, o.kind_b, o.err_b};
+        memcpy(ha.hb, o.hb_a, sizeof(ha.hb));
+        memcpy(hb.hb, o.hb_b, sizeof(hb.hb));
+        c->hitbox_cache[cb200_collider::HbKey{ids[k].first, tbits}] = ha;
+        c->hitbox_cache[cb200_collider::HbKey{ids[k].second, tbits}] = hb;
+    }
     c->prefetches += 1;
     c->prefetched += n;
     return CB200_OK;
@@ -621,6 +651,7 @@ cb200_ctx* cb200_collider_engine(cb200_collider* c) { return c ? c->ctx : nullpt
 uint64_t cb200_collider_len(const cb200_collider* c) { return c ? c->infos.size() : 0; }
 uint64_t cb200_collider_rebin_count(const cb200_collider* c) { return c ? c->rebins : 0; }
 uint64_t cb200_collider_prefetch_count(const cb200_collider* c) { return c ? c->prefetches : 0; }
+uint64_t cb200_collider_hitbox_cache_hits(const cb200_collider* c) { return c ? c->hitbox_cache_hits : 0; }
 
 int cb200_collider_set_can_interact(cb200_collider* c, cb200_can_interact_fn fn, void* user) {
     if (!c) return CB200_E_ARG;
@@ -704,6 +735,23 @@ int cb200_collider_get_hitbox(cb200_collider* c, uint64_t id, cb200_hitbox* out)
     auto it = c->infos.find(id);
     if (it == c->infos.end()) return not_found(c, id);
     cb200_ctx* x = c->ctx;
+    {
+        // the answer may have come back with the prefetched solve of the event the caller is handling (prefetch_solves)
+        uint64_t tbits;
+        memcpy(&tbits, &c->time, 8);
+        auto hc = c->hitbox_cache.find(cb200_collider::HbKey{id, tbits});
+        if (hc != c->hitbox_cache.end() && hc->second.version == it->second.version) {
+            const cb200_collider::CachedHitbox& h = hc->second;
+            if (h.err) return contract_error(c, h.err, id);
+            out->pos_x = h.hb[0]; out->pos_y = h.hb[1]; out->dim_x = h.hb[2]; out->dim_y = h.hb[3];
+            out->vel_x = h.hb[4]; out->vel_y = h.hb[5]; out->rsz_x = h.hb[6]; out->rsz_y = h.hb[7];
+            out->end_time = h.hb[8];
+            out->kind = h.kind;
+            out->_pad = 0;
+            c->hitbox_cache_hits += 1;
+            return CB200_OK;
+        }
+    }
     cudaSetDevice(x->device);
     k_get_hitbox<<<1, 1, 0, x->stream>>>(table_of(c), it->second.label, c->time, c->head.d);
     x->launches += 1;
@@ -941,6 +989,7 @@ int cb200_collider_add_hitboxes(cb200_collider* c, uint64_t n, const cb200_profi
     if (n_pairs) *n_pairs = n_out;
     c->overlaps_dirty = true;
     // the queue is the device-sorted run
+    c->hitbox_cache.clear();
     c->solve_cache.clear();
     c->overlay.clear();
     std::fill(c->cleared.begin(), c->cleared.end(), 0);
@@ -1097,6 +1146,7 @@ int cb200_collider_bulk_update(cb200_collider* c, const cb200_vel_view* vel, dou
     if ((rc = sort_events(x)) != CB200_OK) return cfail(c, rc, x->err);
     // every hitbox was updated: every older event is gone (clear_related_events per hitbox); the run is the queue
     c->solve_cache.clear();  // (so the hitbox versions need no bump)
+    c->hitbox_cache.clear();
     c->overlay.clear();
     for (uint64_t id : c->with_keys) {
         auto it = c->infos.find(id);

@@ -136,11 +136,23 @@ struct cb200_ctx {
     DevBuf<uint32_t> chunk_base;  // start of each scan chunk's runs in the entry array
     DevBuf<CellEntry> entries;
     DevBuf<WorkItem> work;         // (record, record, slot) work items: kWorkLists equal segments (kernels.cuh WorkLists)
-    DevBuf<uint32_t> work_count;   // [kWorkLists]
+    DevBuf<uint32_t> work_count;   // [kWorkLists + 2]: item counts of the work lists, the dense-run descriptor count, k_solve_dense's cursor
+    DevBuf<uint2> dense;           // dense-run descriptors (k_enum_pairs -> k_solve_dense)
+    uint32_t grid_d = 0;           // blocks of k_solve_dense
+    // Dense slot runs: from rank dense_rank on, the entries of a run go to k_solve_dense instead of becoming work items
+    // (kDenseOff: none do).  Both paths are exact; which one a step uses is decided from the PREVIOUS step's counters
+    // (choose_dense): in a sparse scene the dense kernel would be an empty launch in front of k_solve (measured 6 us alone,
+    // more inside the step), in a dense one it is ~2x faster than work items.  CB200_DENSE_RANK pins the choice (0: off).
+    uint32_t dense_rank = kDenseOff;
+    uint32_t dense_rank_cfg = kDenseRank;
+    bool dense_auto = true;
+    double dense_auto_ratio = 2.0;     // dense when the last step solved more than this many candidate pairs per cell entry
 
     DevBuf<uint2> ov_pairs;
     DevBuf<unsigned long long> ov_table;  // buckets of four keys (kernels.cuh OverlapSet)
     DevBuf<uint32_t> ov_bits;             // one bit per gid: has at least one overlap
+    DevBuf<uint32_t> ov_pair_bits;        // one bit per hash(pair), >= 16 bits per pair
+    uint32_t ov_pair_mask = 0;            // its words - 1
     uint32_t n_ov = 0, ov_bucket_mask = 0;
     DevBuf<uint64_t> ov_ida, ov_idb;
 
@@ -148,6 +160,8 @@ struct cb200_ctx {
     DevBuf<MinKey> partial;
     uint32_t grid_a = 0, grid_p = 0, grid_s = 0;        // blocks of stage A, of the enumeration, of the solve stage
     uint32_t per_sm_a = 8, per_sm_p = 8, per_sm_s = 4;  // ... per SM (CB200_PER_SM_A / _P / _S); solve: one wave (measured 84 -> 79 us)
+    uint32_t per_sm_d = CB200_LB_DENSE2;                  // k_solve_dense: one wave at its launch bounds (CB200_PER_SM_D)
+    bool dense_lockstep = false;                          // CB200_DENSE_KERNEL=1: the first dense kernel (A/B)
     Counters* d_ctr = nullptr;
     StepResultDev* d_res = nullptr;  // device alias of h_res (mapped)
     StepResultDev* h_res = nullptr;  // pinned, mapped
@@ -314,9 +328,18 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if (const char* sa = getenv("CB200_STAGE_A")) c->stage_a_tma = strcmp(sa, "tma") == 0;
     if (const char* w = getenv("CB200_LD256")) c->ld256 = w[0] != '0';
     if (const char* w = getenv("CB200_SOLVE")) c->solve_two_phase = w[0] == '2';
+    if (const char* v = getenv("CB200_DENSE_RANK")) {
+        c->dense_auto = false;
+        c->dense_rank = atoi(v) <= 0 ? kDenseOff : (uint32_t)atoi(v);
+    }
+    if (const char* v = getenv("CB200_DENSE_AUTO_RANK")) c->dense_rank_cfg = (uint32_t)std::max(1, atoi(v));
+    if (const char* v = getenv("CB200_DENSE_AUTO_RATIO")) c->dense_auto_ratio = atof(v);
     if (const char* v = getenv("CB200_PER_SM_A")) c->per_sm_a = (uint32_t)std::max(1, std::min(32, atoi(v)));
     if (const char* v = getenv("CB200_PER_SM_P")) c->per_sm_p = (uint32_t)std::max(1, std::min(32, atoi(v)));
     if (const char* v = getenv("CB200_PER_SM_S")) c->per_sm_s = (uint32_t)std::max(1, std::min(32, atoi(v)));
+    if (const char* v = getenv("CB200_DENSE_KERNEL")) c->dense_lockstep = v[0] == '1';
+    if (c->dense_lockstep) c->per_sm_d = CB200_LB_DENSE;
+    if (const char* v = getenv("CB200_PER_SM_D")) c->per_sm_d = (uint32_t)std::max(1, std::min(32, atoi(v)));
     if ((e = cudaFuncSetAttribute(k_stage_a_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(StageATile)))) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_stage_a_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(StageATile)))) != cudaSuccess)
         return bail("cudaFuncSetAttribute", e);
@@ -348,8 +371,8 @@ void cb200_destroy(cb200_ctx* c) {
     if (c->h_dyn) cudaFreeHost(c->h_dyn);
     for (auto& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
-    c->slots.release(); c->chunk_base.release(); c->entries.release(); c->work.release(); c->work_count.release();
-    c->ov_pairs.release(); c->ov_table.release(); c->ov_bits.release(); c->ov_ida.release(); c->ov_idb.release();
+    c->slots.release(); c->chunk_base.release(); c->entries.release(); c->work.release(); c->work_count.release(); c->dense.release();
+    c->ov_pairs.release(); c->ov_table.release(); c->ov_bits.release(); c->ov_pair_bits.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
     c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); for (auto& b : c->bs_tab) b.release(); c->imm_pairs.release(); if (c->d_n_imm) cudaFree(c->d_n_imm); c->ev_out.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
@@ -511,6 +534,10 @@ int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_
     const size_t n_words = (gid_space + 31) / 32 + 1;
     CU(ctx->ov_bits.reserve(n_words));
     CU(cudaMemsetAsync(ctx->ov_bits.p, 0, n_words * 4, ctx->stream));
+    uint32_t pair_words = 1024;
+    while (pair_words < np / 2u + 1u) pair_words <<= 1;  // >= 16 bits per pair
+    CU(ctx->ov_pair_bits.reserve(pair_words));
+    CU(cudaMemsetAsync(ctx->ov_pair_bits.p, 0, (size_t)pair_words * 4, ctx->stream));
     CU(cudaMemcpyAsync(ctx->ov_ida.p, id_a, (size_t)np * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->ov_idb.p, id_b, (size_t)np * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->ov_table.p, 0xff, (size_t)cap * 8, ctx->stream));
@@ -519,7 +546,7 @@ int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_
     CU(cudaMemcpyAsync(&ctx->d_ctr->err_slot, &big, 8, cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t blocks = (np + kThreads - 1) / kThreads;
     k_overlap_map_ids<<<blocks, kThreads, 0, ctx->stream>>>(ctx->sharded ? nullptr : ctx->ids.p, ctx->n, ctx->ov_ida.p, ctx->ov_idb.p, np, ctx->ov_pairs.p, ctx->d_ctr);
-    k_overlap_insert<<<blocks, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, np, ctx->ov_table.p, cap / 4 - 1, ctx->ov_bits.p);
+    k_overlap_insert<<<blocks, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, np, ctx->ov_table.p, cap / 4 - 1, ctx->ov_bits.p, ctx->ov_pair_bits.p, pair_words - 1);
     ctx->launches += 2;
     Counters h;
     CU(cudaMemcpyAsync(&h, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
@@ -528,6 +555,7 @@ int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_
     if (h.err_flags) return fail(ctx, CB200_E_ARG, "set_overlaps: hitbox id not found (pair " + std::to_string(h.err_slot) + ")");
     ctx->n_ov = np;
     ctx->ov_bucket_mask = cap / 4 - 1;
+    ctx->ov_pair_mask = pair_words - 1;
     return CB200_OK;
 }
 
@@ -570,6 +598,24 @@ static ShardGeom whole_world() {
 
 // Slot counts -> run starts (k_scan_slots).  step = the bulk step's / re-bin's scan (totals go to the step counters);
 // otherwise the re-sort's.
+static DenseList dense_list_of(cb200_ctx* ctx) {
+    return DenseList{ctx->dense.p, ctx->work_count.p + kWorkLists, (uint32_t)std::min<size_t>(ctx->dense.cap, 0xffffffffu), ctx->work_count.p + kWorkLists + 1, ctx->dense_rank};
+}
+static void choose_dense(cb200_ctx* ctx) {
+    if (!ctx->dense_auto) return;
+    const Counters& c = ctx->last.ctr;
+    const bool dense = ctx->have_step && c.n_entries > 0 && (double)c.n_collide > ctx->dense_auto_ratio * (double)c.n_entries;
+    ctx->dense_rank = dense ? ctx->dense_rank_cfg : kDenseOff;
+}
+// one descriptor per long run (> rank entries) + one per 32 entries: never more than this.  Sized for the configured rank even
+// while the dense path is switched off (choose_dense): switching it on must not reallocate in the middle of a run — a
+// cudaFree / cudaMalloc waits for the device, and with a direct peer exchange in flight (k_wait_flags spinning on a context
+// whose peer has not been enqueued yet) that wait would never end.
+static cudaError_t reserve_dense(cb200_ctx* ctx) {
+    const uint32_t rank = ctx->dense_auto ? ctx->dense_rank_cfg : ctx->dense_rank;
+    if (rank == kDenseOff) return ctx->dense.reserve(64);
+    return ctx->dense.reserve(ctx->entries.cap / ((size_t)rank + 1) + ctx->entries.cap / 32 + 64);
+}
 static WorkLists work_lists_of(cb200_ctx* ctx) {
     return WorkLists{ctx->work.p, (uint32_t)std::min<size_t>(ctx->work.cap / kWorkLists, 0x7fffffffu), ctx->work_count.p};
 }
@@ -626,15 +672,17 @@ static int resort_rows(cb200_ctx* ctx) {
 // Every device allocation a step (and a re-sort) needs.  cudaMalloc synchronises the device, so contexts that wait for each
 // other inside their kernels (direct exchange) must have done this before the first step.
 static int reserve_step_buffers(cb200_ctx* ctx) {
+    choose_dense(ctx);
     const uint32_t n = ctx->n;
     const uint32_t n_slots = ctx->geom.n_slots();
     CU(ctx->slots.reserve(n_slots));
     CU(ctx->chunk_base.reserve(n_slots / kScanChunk));
     if (ctx->entries.cap == 0) CU(ctx->entries.reserve((size_t)n * 4 + 1024));
     if (ctx->work.cap == 0) CU(ctx->work.reserve(std::max<size_t>((size_t)n * 2 + 1024, (size_t)kWorkLists * 2048)));
-    CU(ctx->work_count.reserve(kWorkLists));
+    CU(ctx->work_count.reserve(kWorkLists + 2));
+    CU(reserve_dense(ctx));
     if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
-    CU(ctx->partial.reserve((size_t)ctx->sm_count * 16));
+    CU(ctx->partial.reserve((size_t)ctx->sm_count * 24));
     if (n >= 2) {
         for (int k = 0; k < 11; ++k) CU(ctx->col_alt[k].reserve(ctx->col[k].cap));
         CU(ctx->kind_alt.reserve(ctx->kind.cap)); CU(ctx->reit_alt.reserve(ctx->reit.cap)); CU(ctx->group_alt.reserve(ctx->group.cap));
@@ -646,18 +694,21 @@ static int reserve_step_buffers(cb200_ctx* ctx) {
 }
 
 static int prepare_buffers(cb200_ctx* ctx) {
+    choose_dense(ctx);
     const uint32_t n = ctx->n;
     const uint32_t n_slots = ctx->geom.n_slots();
     CU(ctx->slots.reserve(n_slots));
     CU(ctx->chunk_base.reserve(n_slots / kScanChunk));
     if (ctx->entries.cap == 0) CU(ctx->entries.reserve((size_t)n * 4 + 1024));
     if (ctx->work.cap == 0) CU(ctx->work.reserve(std::max<size_t>((size_t)n * 2 + 1024, (size_t)kWorkLists * 2048)));
-    CU(ctx->work_count.reserve(kWorkLists));
+    CU(ctx->work_count.reserve(kWorkLists + 2));
+    CU(reserve_dense(ctx));
     if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
     ctx->grid_a = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, ctx->sm_count * ctx->per_sm_a));
     ctx->grid_p = ctx->sm_count * ctx->per_sm_p;
     ctx->grid_s = ctx->sm_count * ctx->per_sm_s;
-    CU(ctx->partial.reserve(ctx->grid_a + ctx->grid_s));
+    ctx->grid_d = ctx->sm_count * ctx->per_sm_d;
+    CU(ctx->partial.reserve(ctx->grid_a + ctx->grid_s + ctx->grid_d));
     // the rows of the previous step's records move with a re-sort: only between steps, never on a re-run
     if (ctx->need_resort || (ctx->resort_period > 0 && ctx->steps_since_resort >= (uint32_t)ctx->resort_period)) {
         int rc = resort_rows(ctx);
@@ -682,7 +733,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     const GridGeom g = ctx->geom;
     const uint32_t n_slots = g.n_slots();
     k_step_zero<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(ctx->slots.p), n_slots / 4, ctx->d_ctr,
-                                                                  ctx->sharded ? ctx->send_count.p : nullptr, ctx->work_count.p, kWorkLists, ctx->sharded ? n : 0u);
+                                                                  ctx->sharded ? ctx->send_count.p : nullptr, ctx->work_count.p, kWorkLists + 2, ctx->sharded ? n : 0u);
     ctx->launches += 1;
     DBG_SYNC("k_step_zero");
     if (ctx->collider_dirty && n) {
@@ -788,11 +839,12 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     cd.geom = g;
     cd.col_lo = sh.col_lo;
     cd.col_hi = sh.col_hi;
-    cd.ov = OverlapSet{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, ctx->n_ov};
+    cd.ov = OverlapSet{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, ctx->n_ov, ctx->ov_pair_bits.p, ctx->ov_pair_mask};
     EnumArgs en{};
     en.entries = ctx->entries.p;
     en.cap_entries = (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu);
     en.work = work_lists_of(ctx);
+    en.dense = dense_list_of(ctx);
     en.ctr = ctx->d_ctr;
     k_enum_pairs<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(en);
     DBG_SYNC("k_enum_pairs");
@@ -810,6 +862,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     sv.ctr = ctx->d_ctr;
     sv.partial = ctx->partial.p;
     sv.n_partial_a = ctx->grid_a;
+    sv.n_partial_dense = ctx->dense_rank == kDenseOff ? 0u : ctx->grid_d;
     sv.result = ctx->d_res;
     sv.local_key = ctx->d_key;
     sv.vmap = ctx->sharded ? (use_map ? ctx->vmap.p : nullptr) : ctx->row_of.p;
@@ -824,6 +877,18 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     sv.vs = vs;
     sv.col_lo = sh.col_lo;
     sv.col_hi = sh.col_hi;
+    if (ctx->dense_rank != kDenseOff) {
+        // long slot runs (dense cells) first: their minima and counts are folded in by the last block of the kernel below
+        DenseArgs da{};
+        da.list = en.dense;
+        da.entries = reinterpret_cast<const uint2*>(ctx->entries.p);
+        da.cap_entries = en.cap_entries;
+        da.partial_at = ctx->grid_a + ctx->grid_s;
+        if (ctx->dense_lockstep) k_solve_dense_lockstep<<<ctx->grid_d, kThreads, 0, ctx->stream>>>(sv, da);
+        else k_solve_dense<<<ctx->grid_d, kDenseThreads, 0, ctx->stream>>>(sv, da);
+        ctx->launches += 1;
+        DBG_SYNC("k_solve_dense");
+    }
     if (ctx->solve_two_phase && !sv.dbg) k_solve2<<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
     else if (ctx->ld256) k_solve<true><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
     else k_solve<false><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
@@ -847,6 +912,7 @@ static int complete_step(cb200_ctx* ctx, double time, bool* again) {
     *again = false;
     if (c.overflow_entries || c.n_entries > ctx->entries.cap) {
         CU(ctx->entries.reserve((size_t)c.n_entries + c.n_entries / 4 + 1024));
+        CU(reserve_dense(ctx));
         *again = true;
     }
     if (c.work_overflow > ctx->work.cap / kWorkLists) {  // the fullest work sub-list did not fit its segment
@@ -933,13 +999,13 @@ static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
             h *= 0x100000001b3ull;
         }
     };
-    mix(ctx->n); mix((uint64_t)ctx->geom.lw << 8 | (uint64_t)ctx->geom.lh); mix(ctx->n_ov); mix(ctx->ov_bucket_mask);
+    mix(ctx->n); mix((uint64_t)ctx->geom.lw << 8 | (uint64_t)ctx->geom.lh); mix(ctx->n_ov); mix(ctx->ov_bucket_mask); mix(ctx->ov_pair_mask);
     for (auto& b : ctx->col) mix((uint64_t)(uintptr_t)b.p);
     const void* ptrs[] = {ctx->kind.p, ctx->reit.p, ctx->group.p, ctx->mask.p, ctx->label.p, ctx->row_of.p, ctx->rec.p, ctx->bink.p, ctx->slots.p,
                           ctx->chunk_base.p, ctx->entries.p, ctx->work.p, ctx->work_count.p, ctx->events.p, ctx->partial.p, ctx->ov_pairs.p,
-                          ctx->ov_table.p, ctx->ov_bits.p, ctx->ids.p, ctx->collider_dirty, ctx->collider_dirty_count, nv[0], nv[1], nv[2], nv[3], nv[4]};
+                          ctx->ov_table.p, ctx->ov_bits.p, ctx->ov_pair_bits.p, ctx->ids.p, ctx->collider_dirty, ctx->collider_dirty_count, nv[0], nv[1], nv[2], nv[3], nv[4]};
     for (const void* p : ptrs) mix((uint64_t)(uintptr_t)p);
-    mix(ctx->entries.cap); mix(ctx->work.cap); mix(ctx->events.cap); mix(ctx->stage_a_tma ? 1 : 0);
+    mix(ctx->entries.cap); mix(ctx->work.cap); mix(ctx->events.cap); mix((uint64_t)(uintptr_t)ctx->dense.p); mix(ctx->dense.cap); mix(ctx->dense_rank); mix(ctx->dense_lockstep ? 3 : 5); mix(ctx->stage_a_tma ? 1 : 0);
     if (ctx->sharded) {
         mix(0x5aa5); mix((uint64_t)ctx->p2p_parity); mix(ctx->slab); mix((uint64_t)ctx->shard.world << 8 | (uint64_t)ctx->shard.rank);
         const void* sp[] = {ctx->ord.p, ctx->send.p, ctx->send_count.p, ctx->vmap.p, ctx->d_mail, ctx->d_key, ctx->d_gkey};
@@ -1145,7 +1211,7 @@ int cb200_shard_result(cb200_ctx* ctx, cb200_step_result* out) {
         z.n_solitaire = keep.n_solitaire;
         z.n_local = keep.n_local;
         CU(cudaMemsetAsync(ctx->slots.p, 0, (size_t)n_slots * 4, ctx->stream));
-        CU(cudaMemsetAsync(ctx->work_count.p, 0, kWorkLists * 4, ctx->stream));
+        CU(cudaMemsetAsync(ctx->work_count.p, 0, (kWorkLists + 2) * 4, ctx->stream));
         CU(cudaMemcpy(ctx->d_ctr, &z, sizeof(Counters), cudaMemcpyHostToDevice));
         if ((rc = enqueue_back(ctx, ctx->shard_T, true)) != CB200_OK) return rc;
         if ((rc = complete_step(ctx, ctx->shard_T, &again)) != CB200_OK) return rc;
@@ -1236,7 +1302,7 @@ int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world 
         cudaFuncAttributes fa;
         const void* fns[] = {(const void*)k_step_zero, (const void*)k_stage_a<true>, (const void*)k_stage_a_tma<true>, (const void*)k_slab_header, (const void*)k_push_halo,
                              (const void*)k_wait_flags, (const void*)k_index_visitors<true>, (const void*)k_index_visitors<false>,
-                             (const void*)k_scan_slots, (const void*)k_scatter<true>, (const void*)k_enum_pairs, (const void*)k_solve<true>, (const void*)k_solve<false>, (const void*)k_solve2,
+                             (const void*)k_scan_slots, (const void*)k_scatter<true>, (const void*)k_enum_pairs, (const void*)k_solve<true>, (const void*)k_solve<false>, (const void*)k_solve2, (const void*)k_solve_dense, (const void*)k_solve_dense_lockstep,
                              (const void*)k_push_key, (const void*)k_reduce_keys, (const void*)k_resort_count, (const void*)k_resort_rank,
                              (const void*)k_resort_gather};
         for (const void* f : fns) CU(cudaFuncGetAttributes(&fa, f));
@@ -1525,14 +1591,21 @@ int cb200_fetch_candidate_pairs(cb200_ctx* ctx, uint64_t* id_hi, uint64_t* id_lo
     cd.geom = ctx->geom;
     cd.col_lo = sh.col_lo;
     cd.col_hi = sh.col_hi;
-    cd.ov = OverlapSet{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, ctx->n_ov};
+    cd.ov = OverlapSet{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, ctx->n_ov, ctx->ov_pair_bits.p, ctx->ov_pair_mask};
     DevBuf<uint2> out;
     DevBuf<unsigned long long> cnt;
     CU(out.reserve(total));
     CU(cnt.reserve(1));
     CU(cudaMemsetAsync(cnt.p, 0, 8, ctx->stream));
     k_list_candidates<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(cd, work_lists_of(ctx), ctx->rec.p, out.p, cnt.p, total);
-    ctx->launches += 1;
+    if (ctx->dense_rank != kDenseOff) {
+        DenseArgs da{};
+        da.list = dense_list_of(ctx);
+        da.entries = reinterpret_cast<const uint2*>(ctx->entries.p);
+        da.cap_entries = (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu);
+        k_list_candidates_dense<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(cd, da, ctx->d_ctr, ctx->rec.p, out.p, cnt.p, total);
+    }
+    ctx->launches += 2;
     std::vector<uint2> h(total);
     unsigned long long got = 0;
     CU(cudaMemcpyAsync(h.data(), out.p, total * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));

@@ -740,17 +740,27 @@ __global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const HbRec* _
 // samples, profiles/r1f_candidates.txt).  Two levels:
 //   bits    one bit per gid: the hitbox has at least one overlap.  ~n/8 bytes, cache-resident; a pair is looked up only
 //           if both bits are set
+//   pair    one bit per hash(hi, lo) in a table of >= 16 bits per pair (a one-hash Bloom filter): where most hitboxes overlap
+//           something (1 shape per unit^2: all of them) the gid bits pass everything and every candidate paid a 32-byte DRAM
+//           sector in the table below (18 % of k_solve_dense's stall samples, profiles/r1n); this 4-byte load hits L2 and
+//           answers "no" for ~15 of 16 pairs that do not overlap
 //   table   open addressing over 32-byte buckets of four (hi << 32 | lo) keys: one sector per probe step
 struct OverlapSet {
     const ulonglong2* table;  // [2 * n_buckets]; kKeyMax = empty
     const uint32_t* bits;
     uint32_t bucket_mask;     // n_buckets - 1 (power of two); unused when n_pairs == 0
     uint32_t n_pairs;
+    const uint32_t* pair_bits;  // [pair_mask + 1] words
+    uint32_t pair_mask;         // words - 1 (power of two)
 };
+__device__ __forceinline__ uint32_t pair_bit_index(unsigned long long h) { return (uint32_t)(h >> 32); }  // (the bucket uses the low half)
 __device__ __forceinline__ bool overlap_contains(const OverlapSet& ov, uint32_t hi, uint32_t lo) {
     if (!((__ldg(ov.bits + (hi >> 5)) >> (hi & 31u)) & 1u) || !((__ldg(ov.bits + (lo >> 5)) >> (lo & 31u)) & 1u)) return false;
     const unsigned long long key = ((unsigned long long)hi << 32) | lo;
-    uint32_t b = (uint32_t)mix64(key) & ov.bucket_mask;
+    const unsigned long long h = mix64(key);
+    const uint32_t pb = pair_bit_index(h);
+    if (!((__ldg(ov.pair_bits + ((pb >> 5) & ov.pair_mask)) >> (pb & 31u)) & 1u)) return false;
+    uint32_t b = (uint32_t)h & ov.bucket_mask;
     for (;;) {
         const ulonglong2 q0 = __ldg(ov.table + 2 * (size_t)b), q1 = __ldg(ov.table + 2 * (size_t)b + 1);
         if (q0.x == key || q0.y == key || q1.x == key || q1.y == key) return true;
@@ -758,14 +768,18 @@ __device__ __forceinline__ bool overlap_contains(const OverlapSet& ov, uint32_t 
         b = (b + 1) & ov.bucket_mask;
     }
 }
-__global__ void k_overlap_insert(const uint2* __restrict__ pairs, uint32_t n_pairs, unsigned long long* table, uint32_t bucket_mask, uint32_t* bits) {
+__global__ void k_overlap_insert(const uint2* __restrict__ pairs, uint32_t n_pairs, unsigned long long* table, uint32_t bucket_mask, uint32_t* bits,
+                                 uint32_t* pair_bits, uint32_t pair_mask) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     const uint2 pr = pairs[i];
     atomicOr(bits + (pr.x >> 5), 1u << (pr.x & 31u));
     atomicOr(bits + (pr.y >> 5), 1u << (pr.y & 31u));
     const unsigned long long key = ((unsigned long long)pr.x << 32) | pr.y;
-    uint32_t b = (uint32_t)mix64(key) & bucket_mask;
+    const unsigned long long h = mix64(key);
+    const uint32_t pb = pair_bit_index(h);
+    atomicOr(pair_bits + ((pb >> 5) & pair_mask), 1u << (pb & 31u));
+    uint32_t b = (uint32_t)h & bucket_mask;
     for (;;) {
         // slots of a bucket are claimed front to back, so a bucket never has a hole before a key
         for (int k = 0; k < 4; ++k) {
@@ -835,10 +849,23 @@ struct WorkLists {  // work buffer = kWorkLists equal segments; list l holds kin
     uint32_t* count;  // [kWorkLists]
 };
 
+// Long slot runs (dense cells) are not expanded into work items: an entry whose rank in its run is >= kDenseRank leaves its
+// pairs to k_solve_dense, which walks the run from shared memory.  The entries of rank kDenseRank, kDenseRank + 32, ... each
+// append one descriptor (first entry of the run, own rank): the 32 entries from that rank on are the lanes of one warp there.
+constexpr uint32_t kDenseRank = 4;  // measured at 1 shape per unit^2: 1.09 ms per step with 2 or 4, 1.16 with 8; clustered config 5: 0.54 with 4, 0.57 with 8, 0.61 with 2
+constexpr uint32_t kDenseOff = 0xffffffffu;  // DenseList.rank0: every pair becomes a work item (A/B: CB200_DENSE_RANK=0)
+struct DenseList {
+    uint2* desc;      // (entry index of the run's first entry, rank j0)
+    uint32_t* count;
+    uint32_t cap;     // >= entries / (rank0 + 1) + entries / 32 (one per long run + one per 32 entries): cannot overflow
+    uint32_t* cursor; // next descriptor to hand out (k_solve_dense); zeroed with the counts
+    uint32_t rank0;   // first dense rank (kDenseRank; 1 ..: tests force everything through the dense kernel)
+};
 struct EnumArgs {
     const CellEntry* entries;
     uint32_t cap_entries;  // the scatter wrote only the entries below it (an overflowing step is re-run)
     WorkLists work;
+    DenseList dense;
     Counters* ctr;
 };
 
@@ -897,9 +924,20 @@ __global__ void __launch_bounds__(kThreads) k_enum_pairs(const EnumArgs a) {
             const unsigned heads = __ballot_sync(0xffffffffu, live && slot != slot_up);
             const unsigned rects = __ballot_sync(0xffffffffu, live && (ent_s[s].x & kEntryKindBit));
             const unsigned below = heads & (0xffffffffu >> (31 - lane));  // heads at or below this lane
-            rank[s] = !live ? 0u : (below ? (uint32_t)(lane - (31 - __clz(below))) : (uint32_t)lane + last_rank + 1u);
+            const uint32_t rk = !live ? 0u : (below ? (uint32_t)(lane - (31 - __clz(below))) : (uint32_t)lane + last_rank + 1u);  // rank in the run
+            // dense part of a run: one descriptor per 32 ranks from kDenseRank on, no work items
+            const uint32_t rank0 = a.dense.rank0;
+            const bool desc = live && rk >= rank0 && ((rk - rank0) & 31u) == 0u;
+            const unsigned dm = __ballot_sync(0xffffffffu, desc);
+            if (dm) {
+                uint32_t at = 0;
+                if (lane == __ffs(dm) - 1) at = atomicAdd(a.dense.count, (uint32_t)__popc(dm));
+                at = __shfl_sync(0xffffffffu, at, __ffs(dm) - 1) + (uint32_t)__popc(dm & ((1u << lane) - 1u));
+                if (desc && at < a.dense.cap) a.dense.desc[at] = make_uint2(c0 + s * 32 + lane - rk, rk);
+            }
+            rank[s] = rk < rank0 ? rk : 0u;  // predecessors that become work items
             uint32_t n_rect = rect_preds(prev_rects, rects, lane, rank[s]);
-            for (uint32_t k = 33u + (uint32_t)lane; k <= rank[s]; ++k)  // a run longer than the window: global memory
+            for (uint32_t k = 33u + (uint32_t)lane; k <= rank[s]; ++k)  // a run longer than the window (dense path off): global memory
                 n_rect += __ldg(ent + (c0 + s * 32 + lane - k)).x >> 31;
             if (ent_s[s].x >> 31) {
                 cnt[0] += n_rect;
@@ -910,7 +948,7 @@ __global__ void __launch_bounds__(kThreads) k_enum_pairs(const EnumArgs a) {
             }
             prev_rects = rects;
             last_slot = __shfl_sync(0xffffffffu, slot, 31);
-            last_rank = __shfl_sync(0xffffffffu, rank[s], 31);
+            last_rank = __shfl_sync(0xffffffffu, rk, 31);
         }
         // the block reserves its ranges with one atomic per kind pair; lanes get disjoint sub-ranges by a warp scan
         uint32_t lane_off[3], warp_tot[3];
@@ -984,7 +1022,11 @@ struct CandArgs {
     OverlapSet ov;
 };
 // *a_is_hi: the item's first record carries the higher id.
-__device__ __forceinline__ bool candidate_test(const CandArgs& a, const RecHead& ha, const RecHead& hb, uint32_t slot, bool* a_is_hi) {
+// candidate_geom: everything but the overlap lookup.  The step's solve count is (pairs passing candidate_geom) - (overlapping
+// pairs passing candidate_geom): every pair that shares a cell is enumerated exactly once, so the solve stage counts the
+// first term over its items and the second over the overlap list it walks anyway — the dense kernel then needs the hash
+// lookup only for the pairs that survive its swept-bounds filter.
+__device__ __forceinline__ bool candidate_geom(const CandArgs& a, const RecHead& ha, const RecHead& hb, uint32_t slot, bool* a_is_hi) {
     const int32_t ox = max(ha.sx, hb.sx), oy = max(ha.sy, hb.sy);
     if (ox >= min(ha.ex, hb.ex) || oy >= min(ha.ey, hb.ey)) return false;
     if (a.geom.slot(ox, oy) != slot) return false;
@@ -992,9 +1034,18 @@ __device__ __forceinline__ bool candidate_test(const CandArgs& a, const RecHead&
     const bool first_hi = ha.gid > hb.gid;
     *a_is_hi = first_hi;
     const uint32_t mask_hi = first_hi ? ha.mask : hb.mask, group_lo = ((first_hi ? hb.kgb : ha.kgb) >> 8) & 31u;
-    if (!((mask_hi >> group_lo) & 1u)) return false;
-    if (a.ov.n_pairs && overlap_contains(a.ov, first_hi ? ha.gid : hb.gid, first_hi ? hb.gid : ha.gid)) return false;
-    return true;
+    return ((mask_hi >> group_lo) & 1u) != 0u;
+}
+__device__ __forceinline__ bool is_overlapping(const CandArgs& a, const RecHead& ha, const RecHead& hb, bool a_is_hi) {
+    return a.ov.n_pairs && overlap_contains(a.ov, a_is_hi ? ha.gid : hb.gid, a_is_hi ? hb.gid : ha.gid);
+}
+__device__ __forceinline__ bool candidate_test(const CandArgs& a, const RecHead& ha, const RecHead& hb, uint32_t slot, bool* a_is_hi) {
+    return candidate_geom(a, ha, hb, slot, a_is_hi) && !is_overlapping(a, ha, hb, *a_is_hi);
+}
+// An overlapping pair (both record heads at hand): would it have been enumerated as a candidate but for the overlap lookup?
+__device__ __forceinline__ bool overlap_pair_is_candidate(const CandArgs& a, const RecHead& ha, const RecHead& hb) {
+    bool hi;
+    return candidate_geom(a, ha, hb, a.geom.slot(max(ha.sx, hb.sx), max(ha.sy, hb.sy)), &hi);
 }
 
 // Index space of the work lists of one step: list l holds min(count[l], seg_cap) items; first[l] = items before it.
@@ -1070,8 +1121,9 @@ struct SolveArgs {
     PairEvent* events;
     uint32_t cap_events;
     Counters* ctr;
-    MinKey* partial;         // [n_partial_a + gridDim.x]: stage A's minima, then this kernel's
+    MinKey* partial;         // [n_partial_a + gridDim.x + n_partial_dense]: stage A's minima, this kernel's, k_solve_dense's
     uint32_t n_partial_a;
+    uint32_t n_partial_dense;
     StepResultDev* result;   // mapped host memory
     MinKey* local_key;       // device copy of the local minimum (sharded: input of the all-gather min)
     // overlapping pairs are looked up by gid; sharded: only the owner-column rank solves them
@@ -1112,14 +1164,15 @@ __device__ __forceinline__ bool gid_lookup(const SolveArgs& a, uint32_t n_local,
 
 // End of the solve stage (all threads of the block): block minimum and counters out; the last block to finish reduces every
 // per-block minimum of stage A and of this stage and publishes the step result.
-__device__ __forceinline__ void solve_epilogue(const SolveArgs& a, MinKey best, unsigned long long n_sep, unsigned long long n_col) {
+// n_col: items that passed candidate_geom MINUS overlapping pairs that pass it (see candidate_geom) — per thread, may be negative.
+__device__ __forceinline__ void solve_epilogue(const SolveArgs& a, MinKey best, uint32_t n_sep, int32_t n_col) {
     __shared__ uint32_t s_last;
     best = block_min(best);
-    const unsigned long long sep_tot = block_sum(n_sep), col_tot = block_sum(n_col);
+    const unsigned long long sep_tot = block_sum((unsigned long long)n_sep), col_tot = block_sum((unsigned long long)(long long)n_col);
     if (threadIdx.x == 0) {
         a.partial[a.n_partial_a + blockIdx.x] = best;
         if (sep_tot) atomicAdd(&a.ctr->n_separate, sep_tot);
-        if (col_tot) atomicAdd(&a.ctr->n_collide, col_tot);
+        if (col_tot) atomicAdd(&a.ctr->n_collide, col_tot);  // (mod 2^64: the sum over all blocks of both solve kernels is >= 0)
         __threadfence();
         s_last = atomicAdd(&a.ctr->done_blocks, 1u) == gridDim.x - 1 ? 1u : 0u;
     }
@@ -1128,7 +1181,7 @@ __device__ __forceinline__ void solve_epilogue(const SolveArgs& a, MinKey best, 
     // last block: reduce every per-block minimum of stage A and of this stage, publish the step result
     __threadfence();
     best = MinKey{kKeyMax, kKeyMax};
-    const uint32_t n_partial = a.n_partial_a + gridDim.x;
+    const uint32_t n_partial = a.n_partial_a + gridDim.x + a.n_partial_dense;
     for (uint32_t i = threadIdx.x; i < n_partial; i += blockDim.x) {
         const volatile unsigned long long* q = reinterpret_cast<const volatile unsigned long long*>(&a.partial[i]);
         const MinKey k{q[0], q[1]};
@@ -1181,7 +1234,8 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
     __shared__ uint32_t s_n;
     __shared__ unsigned long long s_base;
     MinKey best{kKeyMax, kKeyMax};
-    unsigned long long n_sep = 0, n_col = 0;
+    uint32_t n_sep = 0;
+    int32_t n_col = 0;  // net: candidates - overlapping pairs that are candidates (solve_epilogue)
     if (threadIdx.x == 0) s_n = 0;
     work_index_build(a.work, &s_idx);
     const uint32_t n_cand = s_idx.first[kWorkLists];
@@ -1230,6 +1284,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
                     load_rec_keep(a.rec, ib, keep, &hb, &db);
                 }
                 bool a_is_hi = true;  // overlap pairs arrive as (hi, lo)
+#if CB200_SOLVE_COUNT_OLD  /* timing A/B only: counts are exact only while the dense path is off */
                 if (!sep) {
                     present = (a.dbg & 4u) ? true : candidate_test(a.cd, ha, hb, slot, &a_is_hi);
                     n_col += present;
@@ -1237,6 +1292,17 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
                     const int32_t owner_col = max(ha.sx, hb.sx);
                     present = owner_col >= a.col_lo && owner_col < a.col_hi;
                 }
+#else
+                if (!sep) {
+                    present = (a.dbg & 4u) ? true : candidate_geom(a.cd, ha, hb, slot, &a_is_hi);
+                    n_col += present;
+                    present = present && ((a.dbg & 4u) || !is_overlapping(a.cd, ha, hb, a_is_hi));
+                } else {
+                    const int32_t owner_col = max(ha.sx, hb.sx);
+                    present = owner_col >= a.col_lo && owner_col < a.col_hi;
+                    n_col -= present && overlap_pair_is_candidate(a.cd, ha, hb);
+                }
+#endif
                 if (present) {
                     const DurHb A = pick(a_is_hi, da, db);
                     // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486): advanced by T - start = 0
@@ -1296,7 +1362,8 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve2(const Solve
     __shared__ uint32_t s_n, s_qn;
     __shared__ unsigned long long s_base;
     MinKey best{kKeyMax, kKeyMax};
-    unsigned long long n_sep = 0, n_col = 0;
+    uint32_t n_sep = 0;
+    int32_t n_col = 0;  // net: candidates - overlapping pairs that are candidates (solve_epilogue)
     if (threadIdx.x == 0) {
         s_n = 0;
         s_qn = 0;
@@ -1376,6 +1443,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve2(const Solve
                         push = true;
                         sv = make_uint2(ia, ib | kSepBit);
                         n_sep += 1;
+                        n_col -= overlap_pair_is_candidate(a.cd, ha, hb);
                     }
                 }
             } else {
@@ -1385,8 +1453,9 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve2(const Solve
                 load_rec_keep(a.rec, it.a, keep, &ha, &da);
                 load_rec_keep(a.rec, it.b, keep, &hb, &db);
                 bool a_is_hi = true;
-                if (candidate_test(a.cd, ha, hb, it.slot, &a_is_hi)) {
-                    n_col += 1;
+                const bool geom = candidate_geom(a.cd, ha, hb, it.slot, &a_is_hi);
+                n_col += geom;
+                if (geom && !is_overlapping(a.cd, ha, hb, a_is_hi)) {
                     // collide_time (solvers.rs:25-34) up to the touch test, on (hi, lo advanced by zero): only the four
                     // advanced fields of the lower id's shape differ from its record
                     const DurHb da0 = advanced(da, 0.0), db0 = advanced(db, 0.0);
@@ -1427,6 +1496,377 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve2(const Solve
     }
     flush();
     solve_epilogue(a, best, n_sep, n_col);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Dense cells.  A slot run of L entries holds L (L - 1) / 2 (entry, predecessor) pairs; as work items each costs 16 bytes
+// written, 16 read and two 96-byte gathers.  At 1 shape per unit^2 (config 4's density, ~30 entries per run) that was 30 M
+// items per million hitboxes: 0.52 ms to enumerate and 1.9 ms to solve.  Here one warp takes 32 consecutive entries of a run
+// (ranks j0 .. j0 + 31, one per lane, the entry's record in registers) and walks ALL their predecessors in chunks of 32
+// records staged in shared memory: every lane reads the same partner record (a broadcast), so a pair costs six shared-memory
+// loads and no global traffic.  Ranks below kDenseRank stay work items (short runs are the common case at low density).
+// The pair itself goes through the same candidate test and narrowphase as a work item (solve_candidate).
+
+#ifndef CB200_DENSE_MERGED
+#define CB200_DENSE_MERGED 1  /* collide_time_merged in the dense kernels' solve (narrowphase.cuh) */
+#endif
+// The pair has passed the candidate test: narrowphase + event (the body of k_solve for one candidate).
+__device__ __forceinline__ bool solve_pair(const SolveArgs& a, double T, const RecHead& ha, const DurHb& da, const RecHead& hb, const DurHb& db, bool a_is_hi,
+                                           PairEvent* ev, MinKey* best) {
+    const DurHb A = pick(a_is_hi, da, db);
+    // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486): advanced by T - start = 0
+    const DurHb B = advanced(pick(a_is_hi, db, da), 0.0);
+    const uint32_t gid_hi = a_is_hi ? ha.gid : hb.gid, gid_lo = a_is_hi ? hb.gid : ha.gid;
+#if CB200_DENSE_MERGED
+    double delay = collide_time_merged(A, B);
+#else
+    double delay = collide_time(A, B);
+#endif
+    bool is_sep = false;
+    if (a.add_mode && delay == 0.0) {
+        // immediate overlap: process_collision (collider.rs:177-197) queues the Separate
+        const unsigned long long at = atomicAdd(a.n_imm, 1ull);
+        if (at < a.cap_imm) a.imm_pairs[at] = make_uint2(gid_hi, gid_lo);
+        delay = separate_time(A, B, a.padding);
+        is_sep = true;
+    }
+    if (delay != delay) report_error(a.ctr, kFNan, gid_hi);
+    const double t = T + delay;
+    if (!(t < kHighTime)) return false;
+    const uint32_t low = a.add_mode ? ((gid_lo << 1) | (is_sep ? 0u : 1u)) : (gid_lo | (is_sep ? 0u : kCollideBit));
+    *ev = PairEvent{t, gid_hi, low};
+    const MinKey k{time_key(t), kPairClass | ((uint64_t)gid_hi << 32) | low};
+    if (key_less(k, *best)) *best = k;
+    return true;
+}
+
+// One candidate = (record of an entry, record of one of its predecessors in the slot run, the slot): candidate test,
+// collide_time, event.  *n_col counts the candidates that passed candidate_geom.  Returns true if *ev was produced.
+__device__ __forceinline__ bool solve_candidate(const SolveArgs& a, double T, const RecHead& ha, const DurHb& da, const RecHead& hb, const DurHb& db,
+                                                uint32_t slot, unsigned long long* n_col, PairEvent* ev, MinKey* best) {
+    bool a_is_hi = true;
+    if (!candidate_geom(a.cd, ha, hb, slot, &a_is_hi)) return false;
+    *n_col += 1;
+    if (is_overlapping(a.cd, ha, hb, a_is_hi)) return false;
+    return solve_pair(a, T, ha, da, hb, db, a_is_hi, ev, best);
+}
+
+__device__ __forceinline__ void decode_rec(const int4& a, const int4& b, const int4& c, const int4& e, const int4& f, const int4& g, RecHead* h, DurHb* d) {
+    h->sx = a.x; h->sy = a.y;
+    h->ex = a.x + (int32_t)((uint32_t)a.z & 0xffffu);
+    h->ey = a.y + (int32_t)((uint32_t)a.z >> 16);
+    h->gid = (uint32_t)a.w;
+    h->dur = __hiloint2double(b.y, b.x);
+    h->kgb = (uint32_t)b.z;
+    h->mask = (uint32_t)b.w;
+    d->px = __hiloint2double(c.y, c.x); d->py = __hiloint2double(c.w, c.z);
+    d->w = __hiloint2double(e.y, e.x); d->h = __hiloint2double(e.w, e.z);
+    d->vx = __hiloint2double(f.y, f.x); d->vy = __hiloint2double(f.w, f.z);
+    d->rw = __hiloint2double(g.y, g.x); d->rh = __hiloint2double(g.w, g.z);
+    d->dur = h->dur;
+    d->kind = (int)(h->kgb & 1u);
+}
+
+// The walk of one descriptor by one warp.  f(active, ha, da, hb, db, slot) is called with the whole warp converged for every
+// predecessor step; `active` lanes hold a pair (their entry, the predecessor of this step).
+constexpr int kRecInt4 = sizeof(HbRec) / 16;
+template <class F>
+__device__ __forceinline__ void dense_walk(const uint2* __restrict__ entries, uint32_t n_entries, const HbRec* __restrict__ rec, uint2 ds,
+                                           int4* s_chunk /* this warp's [32 * kRecInt4] */, F&& f) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t run0 = ds.x, j0 = ds.y;
+    const uint32_t slot = __ldg(entries + run0).x & kSlotMask;
+    const uint32_t ej = run0 + j0 + (uint32_t)lane;
+    uint2 entj = make_uint2(0u, 0u);
+    if (ej < n_entries) entj = __ldg(entries + ej);
+    const bool valid_j = ej < n_entries && (entj.x & kSlotMask) == slot;  // (the run may end inside the warp's 32 ranks)
+    RecHead ha{};
+    DurHb da{};
+    if (valid_j) {
+        const int4* p = reinterpret_cast<const int4*>(rec + entj.y);
+        decode_rec(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3), __ldg(p + 4), __ldg(p + 5), &ha, &da);
+    }
+    const uint32_t n_valid = (uint32_t)__popc(__ballot_sync(0xffffffffu, valid_j));  // lanes 0 .. n_valid - 1 (a run is contiguous)
+    const uint32_t i_end = j0 + n_valid - 1u;  // predecessors 0 .. i_end - 1 are needed (n_valid >= 1: the descriptor's own entry)
+    for (uint32_t i0 = 0; i0 < i_end; i0 += 32) {
+        // stage predecessors i0 .. i0 + 31 (they lie inside the run: i < j for a valid j)
+        const uint32_t i = i0 + (uint32_t)lane;
+        if (i < i_end) {
+            const uint2 enti = __ldg(entries + run0 + i);
+            const int4* p = reinterpret_cast<const int4*>(rec + enti.y);
+            int4* q = s_chunk + lane * kRecInt4;
+#pragma unroll
+            for (int k = 0; k < kRecInt4; ++k) q[k] = __ldg(p + k);
+        }
+        __syncwarp();
+        const uint32_t n_i = min(32u, i_end - i0);
+        for (uint32_t k = 0; k < n_i; ++k) {
+            const bool active = valid_j && (i0 + k) < (j0 + (uint32_t)lane);
+            const int4* q = s_chunk + k * kRecInt4;
+            RecHead hb;
+            DurHb db;
+            decode_rec(q[0], q[1], q[2], q[3], q[4], q[5], &hb, &db);
+            f(active, ha, da, hb, db, slot);
+        }
+        __syncwarp();
+    }
+}
+
+struct DenseArgs {
+    DenseList list;
+    const uint2* entries;
+    uint32_t cap_entries;
+    uint32_t partial_at;  // this kernel's first slot in SolveArgs.partial
+};
+constexpr int kDenseEvBuf = 64;  // pair events a warp collects before it appends 32 of them with one atomic
+
+#ifndef CB200_LB_DENSE
+#define CB200_LB_DENSE 2
+#endif
+// First version (CB200_DENSE_KERNEL=1; measured SLOWER than work items: 3.77 vs 1.94 + 0.54 ms at 1 shape per unit^2): every
+// (entry, predecessor) step runs the whole candidate test + narrowphase in lockstep.  The records come from shared memory, but
+// the stage is issue-bound there, not gather-bound: ~1000 warp instructions per step with 44 % of the lanes holding a pair
+// (lane j only pairs with predecessors i < j), and the hash lookup of the overlap set on every pair.
+__global__ void __launch_bounds__(kThreads, CB200_LB_DENSE) k_solve_dense_lockstep(const SolveArgs a, const DenseArgs d) {
+    __shared__ int4 s_rec[kThreads / 32][32 * kRecInt4];
+    __shared__ PairEvent s_ev[kThreads / 32][kDenseEvBuf];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_desc = min(*d.list.count, d.list.cap);
+    const uint32_t n_entries = (uint32_t)min(a.ctr->n_entries, (unsigned long long)d.cap_entries);
+    const double T = a.dyn->T;
+    MinKey best{kKeyMax, kKeyMax};
+    unsigned long long n_col = 0;
+    uint32_t n_buf = 0;  // events in this warp's buffer (the same value in every lane)
+    auto append = [&](uint32_t n) {  // the first n buffered events -> the global event list (whole warp)
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&a.ctr->n_pair_events, (unsigned long long)n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t k = lane; k < n; k += 32)
+            if (base + k < a.cap_events) a.events[base + k] = s_ev[warp][k];
+        __syncwarp();
+    };
+    const uint32_t n_warps = gridDim.x * (kThreads / 32);
+    for (uint32_t q = blockIdx.x * (kThreads / 32) + warp; q < n_desc; q += n_warps) {
+        dense_walk(d.entries, n_entries, a.rec, d.list.desc[q], s_rec[warp], [&](bool active, const RecHead& ha, const DurHb& da, const RecHead& hb, const DurHb& db, uint32_t slot) {
+            PairEvent ev;
+            bool made = false;
+            if (active) made = solve_candidate(a, T, ha, da, hb, db, slot, &n_col, &ev, &best);
+            const unsigned m = __ballot_sync(0xffffffffu, made);
+            if (m) {
+                if (made) s_ev[warp][n_buf + (uint32_t)__popc(m & ((1u << lane) - 1u))] = ev;
+                n_buf += (uint32_t)__popc(m);
+                __syncwarp();
+                if (n_buf >= 32u) {
+                    append(32u);
+                    const uint32_t rest = n_buf - 32u;  // < 32
+                    PairEvent keep_ev;
+                    if ((uint32_t)lane < rest) keep_ev = s_ev[warp][32 + lane];
+                    __syncwarp();
+                    if ((uint32_t)lane < rest) s_ev[warp][lane] = keep_ev;
+                    __syncwarp();
+                    n_buf = rest;
+                }
+            }
+        });
+    }
+    if (n_buf) append(n_buf);
+    best = block_min(best);
+    const unsigned long long col_tot = block_sum(n_col);
+    if (threadIdx.x == 0) {
+        a.partial[d.partial_at + blockIdx.x] = best;
+        if (col_tot) atomicAdd(&a.ctr->n_collide, col_tot);
+    }
+}
+
+// The dense kernel in use: filter, then solve.
+//   filter   (lockstep, one predecessor per step, cheap) candidate_geom from the record heads, then the first exit of
+//            collide_time (solvers.rs:27-30: the swept bounds of the two hitboxes over min(duration) do not touch -> no
+//            event) from four edges per record that are computed ONCE per record when it is staged: the swept bounds over the
+//            record's OWN duration.  They are the bounds collide_time would compute whenever the two durations are equal
+//            bit for bit (every hitbox whose cell period exceeds the step has duration = end_time - T): then the test here is
+//            that very test, same operations on the same operands.  If the durations differ, or either record's bounds are
+//            not `ok` (the reference would panic), the pair simply passes.  The partner of the pair is `advanced by 0.0` in
+//            collide_time (x + v * 0.0): for finite velocities that only turns -0.0 into +0.0, which no comparison or later
+//            sum can see; records with a non-finite velocity pass unfiltered.  Survivors go to a queue in shared memory as
+//            (lane of the entry, index of the predecessor in the staged chunk).
+//   solve    whenever 32 survivors are queued (and when a chunk of predecessors ends) each lane takes one: both records from
+//            shared memory, the overlap-set lookup, the full collide_time — all 32 lanes busy, and only for the ~1/3 of the
+//            pairs whose swept bounds touch.
+constexpr uint32_t kDenseThreads = 128;
+constexpr uint32_t kDenseWarps = kDenseThreads / 32;
+#ifndef CB200_LB_DENSE2
+#define CB200_LB_DENSE2 4
+#endif
+__global__ void __launch_bounds__(kDenseThreads, CB200_LB_DENSE2) k_solve_dense(const SolveArgs a, const DenseArgs d) {
+    __shared__ int4 s_own[kDenseWarps][32 * kRecInt4];   // the records of the warp's 32 entries (lane j's at j)
+    __shared__ int4 s_pred[kDenseWarps][32 * kRecInt4];  // the staged chunk of predecessors
+    __shared__ double s_edge[kDenseWarps][32][4];        // their swept edges l, r, b, t
+    __shared__ double s_dur[kDenseWarps][32];            // and dur_key
+    __shared__ uint16_t s_q[kDenseWarps][1024];          // survivors of a chunk: predecessor index << 5 | lane of the entry
+    __shared__ PairEvent s_ev[kDenseWarps][kDenseEvBuf];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_desc = min(*d.list.count, d.list.cap);
+    const uint32_t n_entries = (uint32_t)min(a.ctr->n_entries, (unsigned long long)d.cap_entries);
+    const double T = a.dyn->T;
+    MinKey best{kKeyMax, kKeyMax};
+    unsigned long long n_col = 0;
+    uint32_t n_buf = 0;  // events in this warp's buffer (the same value in every lane)
+    auto append = [&](uint32_t n) {  // the first n buffered events -> the global event list (whole warp)
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&a.ctr->n_pair_events, (unsigned long long)n);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t k = lane; k < n; k += 32)
+            if (base + k < a.cap_events) a.events[base + k] = s_ev[warp][k];
+        __syncwarp();
+    };
+    for (;;) {
+        // descriptors are handed out one by one (their cost grows with the rank they start at)
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(d.list.cursor, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= n_desc) break;
+        const uint2 ds = d.list.desc[q];
+        const uint32_t run0 = ds.x, j0 = ds.y;
+        const uint32_t slot = __ldg(d.entries + run0).x & kSlotMask;
+        uint32_t cell_x, cell_y;  // the folded cell of the run: a pair belongs to it iff its owner cell folds to the same
+        a.cd.geom.unslot(slot, &cell_x, &cell_y);
+        const uint32_t fold_x = (1u << a.cd.geom.lw) - 1u, fold_y = (1u << a.cd.geom.lh) - 1u;
+        // ---- this warp's entries: ranks j0 .. j0 + 31 of the run, one per lane ----
+        const uint32_t ej = run0 + j0 + (uint32_t)lane;
+        uint2 entj = make_uint2(0u, 0u);
+        if (ej < n_entries) entj = __ldg(d.entries + ej);
+        const bool valid_j = ej < n_entries && (entj.x & kSlotMask) == slot;  // (the run may end inside the warp's 32 ranks)
+        RecHead ha{};
+        SweptEdges ea{};
+        if (valid_j) {
+            const int4* p = reinterpret_cast<const int4*>(a.rec + entj.y);
+            int4 r[kRecInt4];
+#pragma unroll
+            for (int k = 0; k < kRecInt4; ++k) r[k] = __ldg(p + k);
+            int4* o = s_own[warp] + lane * kRecInt4;
+#pragma unroll
+            for (int k = 0; k < kRecInt4; ++k) o[k] = r[k];
+            DurHb da;
+            decode_rec(r[0], r[1], r[2], r[3], r[4], r[5], &ha, &da);
+            ea = swept_edges(da);
+        }
+        const uint32_t group_a = (ha.kgb >> 8) & 31u;
+        const uint32_t n_valid = (uint32_t)__popc(__ballot_sync(0xffffffffu, valid_j));  // lanes 0 .. n_valid - 1 (a run is contiguous)
+        const uint32_t i_end = j0 + n_valid - 1u;  // predecessors 0 .. i_end - 1 are needed (n_valid >= 1: the descriptor's own entry)
+        for (uint32_t i0 = 0; i0 < i_end; i0 += 32) {
+            // ---- stage predecessors i0 .. i0 + 31 (they lie inside the run: i < j for a valid j) ----
+            const uint32_t i = i0 + (uint32_t)lane;
+            if (i < i_end) {
+                const uint2 enti = __ldg(d.entries + run0 + i);
+                const int4* p = reinterpret_cast<const int4*>(a.rec + enti.y);
+                int4 r[kRecInt4];
+#pragma unroll
+                for (int k = 0; k < kRecInt4; ++k) r[k] = __ldg(p + k);
+                int4* o = s_pred[warp] + lane * kRecInt4;
+#pragma unroll
+                for (int k = 0; k < kRecInt4; ++k) o[k] = r[k];
+                RecHead hp;
+                DurHb dp;
+                decode_rec(r[0], r[1], r[2], r[3], r[4], r[5], &hp, &dp);
+                const SweptEdges ep = swept_edges(dp);
+                s_edge[warp][lane][0] = ep.l; s_edge[warp][lane][1] = ep.r; s_edge[warp][lane][2] = ep.b; s_edge[warp][lane][3] = ep.t;
+                s_dur[warp][lane] = ep.dur_key;
+            }
+            __syncwarp();
+            const uint32_t n_i = min(32u, i_end - i0);
+            // ---- filter: (lane's entry, predecessor i0 + k) for every k; the survivors of this lane are bits of `keep` ----
+            // candidate_geom with the slot test written as "the owner cell folds to the run's cell" (GridGeom::slot is a
+            // bijection on the folded coordinates), then the swept-edge test
+            uint32_t keep = 0u;
+            const uint32_t rank_j = j0 + (uint32_t)lane;
+            const uint32_t k_end = (!valid_j || rank_j <= i0) ? 0u : min(n_i, rank_j - i0);  // predecessors of this lane in the chunk
+            for (uint32_t k = 0; k < n_i; ++k) {
+                const int4 h0 = s_pred[warp][k * kRecInt4], h1 = s_pred[warp][k * kRecInt4 + 1];
+                const double2 e0 = *reinterpret_cast<const double2*>(&s_edge[warp][k][0]), e1 = *reinterpret_cast<const double2*>(&s_edge[warp][k][2]);
+                const double dk = s_dur[warp][k];
+                const int32_t bsx = h0.x, bsy = h0.y;
+                const int32_t bex = bsx + (int32_t)((uint32_t)h0.z & 0xffffu), bey = bsy + (int32_t)((uint32_t)h0.z >> 16);
+                const uint32_t bgid = (uint32_t)h0.w, bkgb = (uint32_t)h1.z, bmask = (uint32_t)h1.w;
+                const int32_t ox = max(ha.sx, bsx), oy = max(ha.sy, bsy);
+                const bool first_hi = ha.gid > bgid;
+                const uint32_t mask_hi = first_hi ? ha.mask : bmask, group_lo = first_hi ? ((bkgb >> 8) & 31u) : group_a;
+                const bool geom = (k < k_end) & (ox < min(ha.ex, bex)) & (oy < min(ha.ey, bey)) & (((uint32_t)ox & fold_x) == cell_x) &
+                                  (((uint32_t)oy & fold_y) == cell_y) & (ox >= a.cd.col_lo) & (ox < a.cd.col_hi) & (((mask_hi >> group_lo) & 1u) != 0u);
+                const bool touch = (ea.r - e0.x >= 0.0) & (ea.t - e1.x >= 0.0) & (e0.y - ea.l >= 0.0) & (e1.y - ea.b >= 0.0);
+                const bool pass = geom & (touch | !(ea.dur_key == dk));
+                n_col += geom;
+                keep |= (pass ? 1u : 0u) << k;
+            }
+            // ---- queue: every lane writes its survivors behind those of the lanes below it ----
+            uint32_t incl = (uint32_t)__popc(keep);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const uint32_t n_q = __shfl_sync(0xffffffffu, incl, 31);
+            for (uint32_t at = incl - (uint32_t)__popc(keep); keep; keep &= keep - 1u) s_q[warp][at++] = (uint16_t)(((uint32_t)(__ffs(keep) - 1) << 5) | (uint32_t)lane);
+            __syncwarp();
+            // ---- solve: 32 survivors at a time ----
+            for (uint32_t first = 0; first < n_q; first += 32) {
+                PairEvent ev;
+                bool made = false;
+                if (first + (uint32_t)lane < n_q) {
+                    const uint32_t e = s_q[warp][first + lane];
+                    const int4* pa = s_own[warp] + (e & 31u) * kRecInt4;
+                    const int4* pb = s_pred[warp] + (e >> 5) * kRecInt4;
+                    RecHead h1, h2;
+                    DurHb d1, d2;
+                    decode_rec(pa[0], pa[1], pa[2], pa[3], pa[4], pa[5], &h1, &d1);
+                    decode_rec(pb[0], pb[1], pb[2], pb[3], pb[4], pb[5], &h2, &d2);
+                    const bool first_hi = h1.gid > h2.gid;
+                    if (!is_overlapping(a.cd, h1, h2, first_hi)) made = solve_pair(a, T, h1, d1, h2, d2, first_hi, &ev, &best);
+                }
+                const unsigned me = __ballot_sync(0xffffffffu, made);
+                if (made) s_ev[warp][n_buf + (uint32_t)__popc(me & ((1u << lane) - 1u))] = ev;
+                n_buf += (uint32_t)__popc(me);
+                __syncwarp();
+                if (n_buf >= 32u) {
+                    append(32u);
+                    const uint32_t rest = n_buf - 32u;  // < 32
+                    PairEvent keep_ev;
+                    if ((uint32_t)lane < rest) keep_ev = s_ev[warp][32 + lane];
+                    __syncwarp();
+                    if ((uint32_t)lane < rest) s_ev[warp][lane] = keep_ev;
+                    __syncwarp();
+                    n_buf = rest;
+                }
+            }
+            __syncwarp();  // (s_pred and s_q are rewritten by the next chunk)
+        }
+        __syncwarp();  // (s_own is rewritten by the next descriptor)
+    }
+    if (n_buf) append(n_buf);
+    best = block_min(best);
+    const unsigned long long col_tot = block_sum(n_col);
+    if (threadIdx.x == 0) {
+        a.partial[d.partial_at + blockIdx.x] = best;
+        if (col_tot) atomicAdd(&a.ctr->n_collide, col_tot);
+    }
+}
+
+// Debug / parity view of the dense part (see k_list_candidates).
+__global__ void __launch_bounds__(kThreads) k_list_candidates_dense(const CandArgs a, const DenseArgs d, const Counters* ctr, const HbRec* __restrict__ rec, uint2* out,
+                                                                    unsigned long long* n_out, uint64_t cap) {
+    __shared__ int4 s_rec[kThreads / 32][32 * kRecInt4];
+    const int warp = threadIdx.x >> 5;
+    const uint32_t n_desc = min(*d.list.count, d.list.cap);
+    const uint32_t n_entries = (uint32_t)min(ctr->n_entries, (unsigned long long)d.cap_entries);
+    const uint32_t n_warps = gridDim.x * (kThreads / 32);
+    for (uint32_t q = blockIdx.x * (kThreads / 32) + warp; q < n_desc; q += n_warps) {
+        dense_walk(d.entries, n_entries, rec, d.list.desc[q], s_rec[warp], [&](bool active, const RecHead& ha, const DurHb&, const RecHead& hb, const DurHb&, uint32_t slot) {
+            bool a_is_hi = true;
+            if (active && candidate_test(a, ha, hb, slot, &a_is_hi)) {
+                const unsigned long long pos = warp_agg_claim(n_out);
+                if (pos < cap) out[pos] = a_is_hi ? make_uint2(ha.gid, hb.gid) : make_uint2(hb.gid, ha.gid);
+            }
+        });
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------

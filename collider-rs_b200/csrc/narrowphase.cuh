@@ -78,6 +78,7 @@ CB_HD double box_sweep_time(const DurHb& a, const DurHb& b, bool for_collide) {
     const double ov[4] = {av_r - bv_l, av_t - bv_b, bv_r - av_l, bv_t - av_b};
     double start = 0.0, end = cb_inf();
     bool decided = false;
+#if CB200_BOX_SWEEP_TWO_ARMS  /* A/B: the division written once in each arm */
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const bool apart = o[c] < 0.0;
@@ -88,6 +89,22 @@ CB_HD double box_sweep_time(const DurHb& a, const DurHb& b, bool for_collide) {
             end = fmin(end, -o[c] / ov[c]);
         }
     }
+#else
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        // one quotient per card, shared by both arms (an f64 division is ~30 instructions; a diverged warp would otherwise run
+        // the sequence once per arm), and none when neither arm needs it
+        const bool apart = o[c] < 0.0;
+        const bool to_start = apart && for_collide && !(ov[c] <= 0.0);
+        const bool to_end = !apart && ov[c] < 0.0;
+        decided = decided || (apart && !to_start);
+        if (to_start || to_end) {
+            const double q = -o[c] / ov[c];
+            start = to_start ? fmax(start, q) : start;
+            end = to_end ? fmin(end, q) : end;
+        }
+    }
+#endif
     if (decided || start >= end) return for_collide ? cb_inf() : 0.0;
     return for_collide ? start : end;
 }
@@ -219,6 +236,84 @@ CB_HD double collide_time(const DurHb& a, const DurHb& b) {
     if (!(ba.ok && bb.ok)) return cb_nan();
     if (!boxes_touch(ba, bb)) return cb_inf();
     return sweep_unpadded(a, b, true, duration);
+}
+
+// collide_time with the three kind pairs folded into ONE box stage and ONE disc stage, for callers whose warps hold mixed
+// kind pairs (k_solve_dense): sweep_unpadded above runs box_sweep_time in its rect/rect arm and again in its rect/circle arm,
+// and disc_sweep_time in its circle/circle arm and again in the corner stage — a warp with all three pairs pays for all
+// four.  Here every lane runs the same operations on the same operands as collide_time would (results are bit-identical,
+// tests/host_narrowphase_check.cpp), but a diverged warp executes each stage once.
+CB_HD double collide_time_merged(const DurHb& a, const DurHb& b) {
+    const double duration = fmin(a.dur, b.dur);
+    const Box4 ba = swept_bounds(a, duration), bb = swept_bounds(b, duration);
+    if (!(ba.ok && bb.ok)) return cb_nan();
+    if (!boxes_touch(ba, bb)) return cb_inf();
+    const bool a_rect = a.kind == kRect, b_rect = b.kind == kRect;
+    const bool both_disc = !a_rect && !b_rect, mixed = a_rect != b_rect;
+    // box stage: rect/rect on (a, b); rect/circle on (box, disc)
+    const bool keep = a_rect || !mixed;
+    const DurHb x = pick(keep, a, b), y = pick(keep, b, a);
+    double result = cb_inf();
+    bool disc_stage = both_disc;
+    double base = 0.0;
+    // disc stage operands: circle/circle = the two shapes; rect/circle = (moving corner as a zero-diameter disc, disc)
+    double p_px = a.px, p_py = a.py, p_d = a.w, p_vx = a.vx, p_vy = a.vy, p_rd = a.rw;
+    double q_px = b.px, q_py = b.py, q_d = b.w, q_vx = b.vx, q_vy = b.vy, q_rd = b.rw;
+    if (!both_disc) {
+        base = box_sweep_time(x, y, true);
+        result = base;  // rect/rect
+        if (mixed) {
+            // box_disc_collide + corner_stage_time
+            result = cb_inf();
+            if (!(base >= duration)) {
+                const DurHb bx = advanced(x, base), dc = advanced(y, base);
+                const double l = bx.px - bx.w * 0.5, r = bx.px + bx.w * 0.5;
+                const double bo = bx.py - bx.h * 0.5, t = bx.py + bx.h * 0.5;
+                const int sx = dc.px < l ? -1 : (dc.px > r ? 1 : 0);
+                const int sy = dc.py < bo ? -1 : (dc.py > t ? 1 : 0);
+                if (sx == 0 || sy == 0) {
+                    result = base + 0.0;
+                } else {
+                    disc_stage = true;
+                    p_px = sx < 0 ? l : r; p_py = sy < 0 ? bo : t; p_d = 0.0;
+                    p_vx = sx < 0 ? bx.vx - bx.rw * 0.5 : bx.vx + bx.rw * 0.5;
+                    p_vy = sy < 0 ? bx.vy - bx.rh * 0.5 : bx.vy + bx.rh * 0.5;
+                    p_rd = 0.0;
+                    q_px = dc.px; q_py = dc.py; q_d = dc.w; q_vx = dc.vx; q_vy = dc.vy; q_rd = dc.rw;
+                }
+            }
+        }
+    }
+    if (disc_stage) {
+        const double r2 = disc_sweep_time(p_px, p_py, p_d, p_vx, p_vy, p_rd, q_px, q_py, q_d, q_vx, q_vy, q_rd, true);
+        result = both_disc ? r2 : base + r2;
+    }
+    return (result >= duration) ? cb_inf() : result;
+}
+
+// The swept bounds of a hitbox over its OWN duration, as the four edges boxes_touch derives, for filtering pairs before
+// collide_time (k_solve_dense).  When two hitboxes have the same duration bit for bit these are the bounds collide_time
+// computes for the pair (duration = fmin of equals), so `!swept_edges_touch` is exactly its "bounds do not touch -> inf"
+// exit.  dur_key = NaN marks edges that must never filter: bounds not `ok` (the reference would panic) or a non-finite
+// velocity (the partner is advanced by 0.0 inside collide_time: x + v * 0.0 keeps x for finite v up to the sign of zero,
+// which no comparison or later sum observes, but not for an infinite v).
+struct SweptEdges {
+    double l, r, b, t;
+    double dur_key;
+};
+CB_HD bool cb_finite(double x) { return (x - x) == 0.0; }
+CB_HD SweptEdges swept_edges(const DurHb& d) {
+    const Box4 bx = swept_bounds(d, d.dur);
+    SweptEdges e;
+    e.l = bx.cx - bx.w * 0.5; e.r = bx.cx + bx.w * 0.5; e.b = bx.cy - bx.h * 0.5; e.t = bx.cy + bx.h * 0.5;
+    const bool plain = bx.ok && cb_finite(d.vx) && cb_finite(d.vy) && cb_finite(d.rw) && cb_finite(d.rh);
+    e.dur_key = plain ? d.dur : cb_nan();
+    return e;
+}
+// false: collide_time of the pair is +inf (its swept bounds do not touch); true: it has to be evaluated
+CB_HD bool swept_filter_pass(const SweptEdges& a, double b_l, double b_r, double b_b, double b_t, double b_dur_key) {
+    const bool touch = (a.r - b_l >= 0.0) && (a.t - b_b >= 0.0) && (b_r - a.l >= 0.0) && (b_t - a.b >= 0.0);
+    return touch || !(a.dur_key == b_dur_key);
 }
 
 // solvers::separate_time (solvers.rs:36-44): the circle of a (rect, circle) pair goes first, and only the

@@ -294,7 +294,28 @@ struct PairJob {
 struct PairOut {
     double time;  // t + delay
     uint32_t err, pad;
+    // Collider::get_hitbox of both hitboxes at the event time (what the user's handler asks for next): pos, dims, vel, resize,
+    // public end_time; kind; contract flags
+    double hb_a[9], hb_b[9];
+    uint32_t kind_a, kind_b, err_a, err_b;
 };
+// HitboxInfo::pub_hitbox_at_time(T) (collider.rs:488-497) of row j; returns the contract flags.
+__device__ __forceinline__ uint32_t pub_hitbox_at(const StateCols& s, uint32_t j, double T, double* hb, uint32_t* kind) {
+    uint32_t err = 0;
+    const double start = s.start[j], pub_end = s.pub_end[j];
+    if (!(T >= start && T <= pub_end)) err |= kFInvalidTime;
+    const double dt = T - start;
+    if (!(dt < kHighTime)) err |= kFHighTime;
+    const double vx = s.vx[j], vy = s.vy[j], rw = s.rw[j], rh = s.rh[j];
+    hb[0] = s.px[j] + vx * dt;
+    hb[1] = s.py[j] + vy * dt;
+    hb[2] = s.w[j] + rw * dt;
+    hb[3] = s.h[j] + rh * dt;
+    hb[4] = vx; hb[5] = vy; hb[6] = rw; hb[7] = rh;
+    hb[8] = pub_end;
+    *kind = s.kind[j] & 1u;
+    return err;
+}
 __global__ void __launch_bounds__(128) k_pair_solve_batch(TableView t, const PairJob* __restrict__ jobs, uint32_t n, double padding, PairOut* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -302,32 +323,28 @@ __global__ void __launch_bounds__(128) k_pair_solve_batch(TableView t, const Pai
     uint32_t err = 0;
     const uint32_t ra = t.row_of[j.label_a], rb = t.row_of[j.label_b];
     if (ra >= t.n || rb >= t.n) {
-        out[i] = PairOut{0.0, kFIdNotFound, 0u};
+        out[i].time = 0.0;
+        out[i].err = kFIdNotFound;
+        out[i].err_a = out[i].err_b = kFIdNotFound;
         return;
     }
     const DurHb A = row_at_time(t.s, ra, j.t, &err), B = row_at_time(t.s, rb, j.t, &err);
     const double delay = j.separate ? separate_time(A, B, padding) : collide_time(A, B);
     if (delay != delay) err |= kFNan;
-    out[i] = PairOut{j.t + delay, err, 0u};
+    PairOut o;
+    o.time = j.t + delay;
+    o.err = err;
+    o.pad = 0;
+    o.err_a = pub_hitbox_at(t.s, ra, j.t, o.hb_a, &o.kind_a);
+    o.err_b = pub_hitbox_at(t.s, rb, j.t, o.hb_b, &o.kind_b);
+    out[i] = o;
 }
 
 // Collider::get_hitbox = HitboxInfo::pub_hitbox_at_time(T) (collider.rs:200-202, 488-497).
 __global__ void k_get_hitbox(TableView t, uint32_t label, double T, OneHeader* head) {
-    const uint32_t j = t.row_of[label];
-    uint32_t err = 0;
-    const double start = t.s.start[j], pub_end = t.s.pub_end[j];
-    if (!(T >= start && T <= pub_end)) err |= kFInvalidTime;
-    const double dt = T - start;
-    if (!(dt < kHighTime)) err |= kFHighTime;
-    const double vx = t.s.vx[j], vy = t.s.vy[j], rw = t.s.rw[j], rh = t.s.rh[j];
-    head->hb[0] = t.s.px[j] + vx * dt;
-    head->hb[1] = t.s.py[j] + vy * dt;
-    head->hb[2] = t.s.w[j] + rw * dt;
-    head->hb[3] = t.s.h[j] + rh * dt;
-    head->hb[4] = vx; head->hb[5] = vy; head->hb[6] = rw; head->hb[7] = rh;
-    head->hb[8] = pub_end;
-    head->kind = t.s.kind[j] & 1u;
-    head->err_flags = err;
+    uint32_t kind;
+    head->err_flags = pub_hitbox_at(t.s, t.row_of[label], T, head->hb, &kind);
+    head->kind = kind;
     __threadfence_system();
 }
 

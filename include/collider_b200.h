@@ -315,6 +315,10 @@ uint64_t cb200_collider_rebin_count(const cb200_collider* c);
 /* next() needs one narrowphase solve per Collide / Separate event; the library computes them for up to 2048 queued events
  * per launch ahead of time and uses a prefetched result only if neither hitbox changed since.  Number of such launches. */
 uint64_t cb200_collider_prefetch_count(const cb200_collider* c);
+/* get_hitbox calls answered from the prefetch: the launch that solves the next queued events also evaluates
+ * pub_hitbox_at_time (collider.rs:488-497) of their two hitboxes at the event time, which is what a Collide handler
+ * asks for next; an answer is used only while the collider stands at that time and the hitbox is unchanged. */
+uint64_t cb200_collider_hitbox_cache_hits(const cb200_collider* c);
 cb200_ctx* cb200_collider_engine(cb200_collider* c); /* the underlying device context (timing, launch counts, grid period) */
 
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */

@@ -180,6 +180,32 @@ def test_clustered_fast_small_shapes(oracle, solve, monkeypatch):
     assert_step_parity(orc, eng, res)
 
 
+@pytest.mark.parametrize("dense_rank,kernel", [("1", "filter"), ("8", "filter"), ("0", "filter"), ("8", "lockstep"), ("auto", "filter")])
+@pytest.mark.parametrize("density", [1.0, 6.0])
+def test_dense_cells(oracle, density, dense_rank, kernel, monkeypatch):
+    """Config 4's density (1 shape per unit^2, ~30 entries per slot run) and six times that (runs of ~200 entries: several
+    descriptors per run, a warp's 32 ranks ending inside the run).  CB200_DENSE_RANK = first rank of a run that k_solve_dense
+    takes: 1 = every pair through the dense kernel, 8 = the default split, 0 = none (work items only); CB200_DENSE_KERNEL=1
+    = the first (lockstep) dense kernel, kept for A/B; "auto" = the default: chosen per step from the previous step's counters
+    (work items on the first step, the dense kernel from the second)."""
+    if dense_rank == "auto":
+        monkeypatch.delenv("CB200_DENSE_RANK", raising=False)
+    else:
+        monkeypatch.setenv("CB200_DENSE_RANK", dense_rank)
+    monkeypatch.setenv("CB200_DENSE_KERNEL", "1" if kernel == "lockstep" else "2")
+    scene = scenes.uniform_density(5000, density=density, seed=scenes.SEED_BASE + 40)
+    orc, eng = seeded(oracle, scene)
+    T = 0.0
+    for step in range(3 if dense_rank == "auto" else 2):
+        orc.bulk_update(end_time=T + 0.1, record_candidates=True)
+        res = eng.bulk_update(T, end_time=T + 0.1)
+        assert res.n_collide_solves > 5000 * (10 if density < 2 else 60)
+        assert_step_parity(orc, eng, res, check_grid=(step == 0))
+        T += 0.1
+        drain_until(orc, T)
+        eng.set_overlaps(*orc.dump_overlaps())
+
+
 @pytest.mark.parametrize("period", [0, 1, 3])
 def test_table_order_never_changes_results(oracle, period):
     """The device keeps its rows in grid-slot order and re-sorts them every `period` steps (0: only after upload);

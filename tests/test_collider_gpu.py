@@ -314,6 +314,7 @@ def test_config1_readme_loop_lockstep(oracle):
         c.add_hitbox(id, hb)
     readme_loop(c, 25.0, halve(c))
     assert c.events > 50
+    assert c.d.hitbox_cache_hits() > 50, "the Collide handler's get_hitbox calls must be served from the prefetch"
     for i in (0, 100, 249):
         c.get_hitbox(i)
         c.get_overlaps(i)
@@ -481,3 +482,20 @@ def test_batched_add_equals_sequential_adds(oracle):
     a, b = c.d.add_hitboxes(extra)
     assert sorted(zip(a.tolist(), b.tolist())) == sorted(want)
     readme_loop(c, t_now + 1.0, halve(c))
+
+
+def test_batched_add_dense(oracle):
+    """The batched add at config 4's density: the immediate overlaps found by k_solve_dense (add mode) are the oracle's."""
+    n = 3000
+    s = scenes.uniform_density(n, density=1.0, seed=scenes.SEED_BASE + 79)
+    c = Lockstep(oracle, scenes.CELL_WIDTH, scenes.PADDING)
+    want = []
+    for id, hb in scene_hitboxes(oracle, s):
+        for other in c.o.add_hitbox(id, hb):
+            want.append((id, other))
+    a, b = c.d.add_hitboxes(s)
+    assert sorted(zip(a.tolist(), b.tolist())) == sorted(want) and len(want) > 2000
+    for i in (0, 1234, n - 1):
+        c.get_overlaps(i)
+    readme_loop(c, 0.25, halve(c))
+    assert c.events > 200

@@ -159,3 +159,10 @@ def test_sharded_residents_unrelated_to_position(oracle):
 
 def test_sharded_clustered(oracle):
     run_sharded_case(oracle, scenes.c5(8000), 4, steps=1, dt=0.1, end_dt=0.1)
+
+
+@pytest.mark.parametrize("direct", [False, True])
+def test_sharded_dense_cells(oracle, direct):
+    """Config 4's density across 2 ranks: the long slot runs go through k_solve_dense, pairs straddling the strip edge are
+    still solved by exactly one rank."""
+    run_sharded_case(oracle, scenes.uniform_density(4000, density=1.0, seed=scenes.SEED_BASE + 41), 2, steps=2, dt=0.1, end_dt=0.1, direct=direct)

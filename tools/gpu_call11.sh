@@ -1,0 +1,34 @@
+#!/bin/bash
+# dense kernel v3 (per-lane survivor masks, folded-cell test, one division per card, merged kind pairs, descriptor cursor) + auto policy
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/c11_tests.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/c11_tests.log
+run() { # name, args..., env via ENVV
+  name=$1; shift
+  env $ENVV timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline "$@" > gpurun_out/c11_$name.json 2> gpurun_out/c11_$name.err
+  python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/c11_$name.json"))
+    print("$name", "wall %.1f dev %.1f e2e %.1f" % (d["ms_per_step"]*1e3, d["device_ms_per_step"]*1e3, d["e2e"]["ms_per_step_median_rank0"]*1e3), {k:round(v*1e3,1) for k,v in d["stage_ms"].items()}, d["per_step"])
+except Exception as e:
+    print("$name FAILED", e); print(open("gpurun_out/c11_$name.err").read()[-1500:])
+PY
+}
+L=collider-rs_b200/lib
+ENVV="X=1" run dense_auto --workload c3_dense
+ENVV="CB200_DENSE_RANK=8" run dense_d8 --workload c3_dense
+ENVV="CB200_DENSE_RANK=4" run dense_d4 --workload c3_dense
+ENVV="CB200_DENSE_RANK=2" run dense_d2 --workload c3_dense
+ENVV="CB200_DENSE_RANK=0" run dense_d0 --workload c3_dense
+ENVV="CB200_DENSE_RANK=4 CB200_LIB=$L/libcb_m0.so" run dense_d4_m0 --workload c3_dense
+ENVV="CB200_DENSE_RANK=4 CB200_LIB=$L/libcb_l3.so CB200_PER_SM_D=3" run dense_d4_l3 --workload c3_dense
+ENVV="CB200_DENSE_RANK=4 CB200_LIB=$L/libcb_l5.so CB200_PER_SM_D=5" run dense_d4_l5 --workload c3_dense
+ENVV="X=1" run c5_auto --workload c5
+ENVV="CB200_DENSE_RANK=8" run c5_d8 --workload c5
+ENVV="CB200_DENSE_RANK=4" run c5_d4 --workload c5
+ENVV="CB200_DENSE_RANK=0" run c5_d0 --workload c5
+ENVV="X=1" run c3_auto
+ENVV="CB200_DENSE_RANK=0" run c3_d0
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_solve' --launch-skip 50 -c 2 \
+  -f -o gpurun_out/prof_r1n_dense env CB200_DENSE_RANK=4 python bench.py --steps 5 --warmup 5 --no-cpu-baseline --workload c3_dense > gpurun_out/c11_ncu_dense.log 2>&1
+echo "ncu dense rc=$?"
