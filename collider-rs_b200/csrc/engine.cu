@@ -889,9 +889,12 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
         ctx->launches += 1;
         DBG_SYNC("k_solve_dense");
     }
+    const bool net = ctx->dense_rank != kDenseOff;  // (k_solve's NET)
     if (ctx->solve_two_phase && !sv.dbg) k_solve2<<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
-    else if (ctx->ld256) k_solve<true><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
-    else k_solve<false><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
+    else if (ctx->ld256 && net) k_solve<true, true><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
+    else if (ctx->ld256) k_solve<true, false><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
+    else if (net) k_solve<false, true><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
+    else k_solve<false, false><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
     DBG_SYNC("k_solve");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
     CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
@@ -1302,7 +1305,7 @@ int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world 
         cudaFuncAttributes fa;
         const void* fns[] = {(const void*)k_step_zero, (const void*)k_stage_a<true>, (const void*)k_stage_a_tma<true>, (const void*)k_slab_header, (const void*)k_push_halo,
                              (const void*)k_wait_flags, (const void*)k_index_visitors<true>, (const void*)k_index_visitors<false>,
-                             (const void*)k_scan_slots, (const void*)k_scatter<true>, (const void*)k_enum_pairs, (const void*)k_solve<true>, (const void*)k_solve<false>, (const void*)k_solve2, (const void*)k_solve_dense, (const void*)k_solve_dense_lockstep,
+                             (const void*)k_scan_slots, (const void*)k_scatter<true>, (const void*)k_enum_pairs, (const void*)k_solve<true, true>, (const void*)k_solve<true, false>, (const void*)k_solve<false, true>, (const void*)k_solve<false, false>, (const void*)k_solve2, (const void*)k_solve_dense, (const void*)k_solve_dense_lockstep,
                              (const void*)k_push_key, (const void*)k_reduce_keys, (const void*)k_resort_count, (const void*)k_resort_rank,
                              (const void*)k_resort_gather};
         for (const void* f : fns) CU(cudaFuncGetAttributes(&fa, f));
