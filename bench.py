@@ -11,7 +11,8 @@ padding 0.01, bulk step every 0.1 time units).  N>1: weak scaling, one 1M-hitbox
 Prints ONE JSON line (rank 0).  `value` = device-resident whole-job throughput; `e2e` = the same metric with
 new velocities coming from pinned HOST arrays each step and the sorted event list read back (H2D + D2H inside
 the timed region); `roofline` = dominant kernel vs the measured HBM peak; `cpu_baseline` = the oracle (C++
-restatement of the reference; Rust toolchain absent) on one host core, bounded sample.
+restatement of the reference; Rust toolchain absent) on one host core, bounded sample.  `--impl reference` times that
+oracle on ALL host threads (one independent Collider per thread: the reference itself is single-threaded).
 """
 from __future__ import annotations
 
@@ -115,20 +116,64 @@ def oracle_timing(scene_fn, n_sample: int, steps: int, warmup: int):
     return n_sample * done / el, (st["collide_solves"] + st["separate_solves"]) / el, el / done * 1e3, st
 
 
+def oracle_timing_threads(scene_fn, n_sample: int, steps: int, warmup: int, threads: int):
+    """The same, on every host thread: the reference is single-threaded, so "all the host threads it can use" is one
+    independent Collider per thread, each on its own tile (n_sample hitboxes, same density, different seed offset).  The C
+    calls release the GIL.  Returns whole-host (updates/s, solves/s, ms per step of one collider)."""
+    from concurrent.futures import ThreadPoolExecutor
+    import threading as th
+
+    from oracle import oracle_py as oracle
+
+    oracle.lib()  # build / load once, before the threads start
+    start = th.Barrier(threads)
+    spans = [None] * threads
+
+    def worker(k):
+        s = scene_fn(n_sample, k)
+        orc = oracle.Collider(4.0, 0.01)
+        orc.add_hitboxes(s)
+        T = 0.0
+        for _ in range(warmup):
+            orc.bulk_update(end_time=T + DT)
+            T = min(T + DT, orc.next_time())
+            orc.set_time(T)
+        orc.stats(reset=True)
+        start.wait()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            orc.bulk_update(end_time=T + DT)
+            T = min(T + DT, orc.next_time())
+            orc.set_time(T)
+        t1 = time.perf_counter()
+        st = orc.stats()
+        spans[k] = (t0, t1, st["collide_solves"] + st["separate_solves"])
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(worker, range(threads)))
+    el = max(t1 for _, t1, _ in spans) - min(t0 for t0, _, _ in spans)
+    return threads * n_sample * steps / el, sum(sv for _, _, sv in spans) / el, el / steps * 1e3
+
+
 def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = min(args.n, args.ref_sample)
     scenes = importlib.import_module("collider-rs_b200.scenes")
-    ups, sps, ms, st = oracle_timing(lambda m: make_workload(scenes, args.workload, m, 0, 1), n_sample, args.steps, max(1, min(args.warmup, 1)))
-    sample = f"{n_sample} hitboxes of the {args.workload} scene (same density), {args.steps} bulk-equivalent steps (ascending set_hitbox_vel loop)"
+    threads = max(1, args.ref_threads or (os.cpu_count() or 1))
+    # bounded: every thread steps its own tile of the scene; the tile shrinks with the thread count so that the run (scene
+    # set-up included) stays within a few minutes on any host
+    n_sample = max(10_000, min(args.n, args.ref_sample) // max(1, threads // 4))
+    ups, sps, ms = oracle_timing_threads(lambda m, k: make_workload(scenes, args.workload, m, k, 1), n_sample, args.steps, max(1, min(args.warmup, 1)), threads)
+    sample = (f"{threads} independent colliders side by side, one per host thread (the reference is single-threaded), each a tile of {n_sample} hitboxes of the "
+              f"{args.workload} scene (same density), {args.steps} bulk-equivalent steps (ascending set_hitbox_vel loop)")
     line = {
         "impl": "reference", "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {args.n} mixed circles/rects, cell_width 4, padding 0.01, bulk step every {DT}", "cpu_sample_hitboxes": n_sample},
+        "config": {"workload": f"{args.workload}: {args.n} mixed circles/rects, cell_width 4, padding 0.01, bulk step every {DT}", "cpu_sample_hitboxes": n_sample * threads,
+                   "cpu_threads": threads},
         "pair_solves_per_s": sps,
-        "cpu_baseline": {"value": ups, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": ups, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "note": "C++17 restatement of the reference (oracle/); the Rust crate cannot be built here (no rustc/cargo)"},
         "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cores_available": os.cpu_count(),
@@ -157,6 +202,7 @@ def _main(out):
     ap.add_argument("--n", "--hitboxes", dest="n", type=int, default=1_000_000, help="hitboxes per GPU")
     ap.add_argument("--workload", default="c3", choices=["c3", "c3_dense", "c5"])
     ap.add_argument("--ref-sample", type=int, default=200_000, help="hitboxes in the CPU sample")
+    ap.add_argument("--ref-threads", type=int, default=0, help="--impl reference: host threads (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--grid", default="", help="force the device grid period: log2_w,log2_h")
     args = ap.parse_args()
