@@ -94,14 +94,15 @@ struct cb200_ctx {
         uint64_t sig = 0;
         cudaGraphExec_t exec = nullptr;
     };
-    GraphSlot graphs[4];
+    static constexpr int kGraphSlots = 8;  // column-buffer set x step parity (sharded) x dense path on / off
+    GraphSlot graphs[kGraphSlots];
     int graph_next = 0;
     bool capturing = false;
     // add mode of the step (collider.inl add_hitboxes): see SolveArgs
     bool add_mode = false, last_add_mode = false;
     DevBuf<uint2> imm_pairs;
     unsigned long long* d_n_imm = nullptr;
-    uint32_t graph_kernels[4] = {};  // kernels inside each captured graph (for the launch counter)
+    uint32_t graph_kernels[kGraphSlots] = {};  // kernels inside each captured graph (for the launch counter)
     uint64_t graph_launches = 0, graph_captures = 0;
     bool solve_two_phase = false;  // CB200_SOLVE=2: k_solve2, filter + dense solve (measured slower: 89 vs 79 us at config 3; kept for A/B and as a second parity check)
     bool ld256 = false;        // CB200_LD256=1: k_solve gathers records with 256-bit loads (measured: 86 vs 84 us, kept for A/B)
@@ -604,7 +605,9 @@ static DenseList dense_list_of(cb200_ctx* ctx) {
 static void choose_dense(cb200_ctx* ctx) {
     if (!ctx->dense_auto) return;
     const Counters& c = ctx->last.ctr;
-    const bool dense = ctx->have_step && c.n_entries > 0 && (double)c.n_collide > ctx->dense_auto_ratio * (double)c.n_entries;
+    // hysteresis: a scene hovering at the threshold must not flip every step (each flip is another step graph)
+    const double ratio = ctx->dense_rank == kDenseOff ? ctx->dense_auto_ratio : 0.75 * ctx->dense_auto_ratio;
+    const bool dense = ctx->have_step && c.n_entries > 0 && (double)c.n_collide > ratio * (double)c.n_entries;
     ctx->dense_rank = dense ? ctx->dense_rank_cfg : kDenseOff;
 }
 // one descriptor per long run (> rank entries) + one per 32 entries: never more than this.  Sized for the configured rank even
@@ -1060,7 +1063,7 @@ static int launch_step_graph(cb200_ctx* ctx, double time, const double* const* n
             return rc;
         }
         slot = &ctx->graphs[ctx->graph_next];
-        ctx->graph_next = (ctx->graph_next + 1) % 4;
+        ctx->graph_next = (ctx->graph_next + 1) % cb200_ctx::kGraphSlots;
         if (slot->exec) cudaGraphExecDestroy(slot->exec);
         slot->exec = nullptr;
         const cudaError_t ei = cudaGraphInstantiate(&slot->exec, graph, 0);
