@@ -1500,11 +1500,11 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve2(const Solve
 // ---------------------------------------------------------------------------------------------------------
 // Dense cells.  A slot run of L entries holds L (L - 1) / 2 (entry, predecessor) pairs; as work items each costs 16 bytes
 // written, 16 read and two 96-byte gathers.  At 1 shape per unit^2 (config 4's density, ~30 entries per run) that was 30 M
-// items per million hitboxes: 0.52 ms to enumerate and 1.9 ms to solve.  Here one warp takes 32 consecutive entries of a run
-// (ranks j0 .. j0 + 31, one per lane, the entry's record in registers) and walks ALL their predecessors in chunks of 32
-// records staged in shared memory: every lane reads the same partner record (a broadcast), so a pair costs six shared-memory
-// loads and no global traffic.  Ranks below kDenseRank stay work items (short runs are the common case at low density).
-// The pair itself goes through the same candidate test and narrowphase as a work item (solve_candidate).
+// items per million hitboxes: 0.53 ms to enumerate and 1.94 ms to solve.  The dense kernels instead give 32 consecutive
+// entries of a run (ranks j0 .. j0 + 31, one per lane) to one warp, which walks ALL their predecessors in chunks of 32
+// records staged in shared memory: no work items, no gathers.  Ranks below DenseList.rank0 stay work items (short runs
+// are the common case at low density).  Two kernels: k_solve_dense_lockstep (first version, A/B only) and k_solve_dense
+// (filter + solve; the one in use).  Measurements and the reasoning: DESIGN.md section 4, "Dense cells".
 
 #ifndef CB200_DENSE_MERGED
 #define CB200_DENSE_MERGED 1  /* collide_time_merged in the dense kernels' solve (narrowphase.cuh) */
