@@ -396,7 +396,10 @@ def _main(out):
                          "per_kernel": {kernel_of[k]: {"ms": stage_ms[k], "bytes": alg[k], "frac": alg[k] / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak}
                                         for k in alg if stage_ms.get(k)},
                          "whole_step": {"bytes": step_bytes, "achieved": step_bytes / (dev_ms_max * 1e-3) / 1e9,
-                                        "frac": step_bytes / (dev_ms_max * 1e-3) / 1e9 / hbm_peak}},
+                                        "frac": step_bytes / (dev_ms_max * 1e-3) / 1e9 / hbm_peak,
+                                        # SURVEY 8d's strict I/O lower bound of a step: 152 B of state in + out per hitbox, 24 B per event
+                                        "io_lower_bound_bytes": 152.0 * n + 24.0 * V,
+                                        "io_lower_bound_frac": (152.0 * n + 24.0 * V) / (dev_ms_max * 1e-3) / 1e9 / hbm_peak}},
             "clocks": sampler.summary(),
         }
         if world > 1:
