@@ -145,6 +145,7 @@ struct cb200_ctx {
     // (choose_dense): in a sparse scene the dense kernel would be an empty launch in front of k_solve (measured 6 us alone,
     // more inside the step), in a dense one it is ~2x faster than work items.  CB200_DENSE_RANK pins the choice (0: off).
     uint32_t dense_rank = kDenseOff;
+    uint32_t last_dense_rank = kDenseOff;  // what the last completed step ran with (cb200_fetch_candidate_pairs)
     uint32_t dense_rank_cfg = kDenseRank;
     bool dense_auto = true;
     double dense_auto_ratio = 2.0;     // dense when the last step solved more than this many candidate pairs per cell entry
@@ -911,6 +912,7 @@ static int complete_step(cb200_ctx* ctx, double time, bool* again) {
     CU(cudaGetLastError());
     ctx->last = *ctx->h_res;
     ctx->last_add_mode = ctx->add_mode;
+    ctx->last_dense_rank = ctx->dense_rank;
     ctx->last_T = time;
     ctx->have_step = true;
     ctx->ev_sorted = false;
@@ -1604,7 +1606,7 @@ int cb200_fetch_candidate_pairs(cb200_ctx* ctx, uint64_t* id_hi, uint64_t* id_lo
     CU(cnt.reserve(1));
     CU(cudaMemsetAsync(cnt.p, 0, 8, ctx->stream));
     k_list_candidates<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(cd, work_lists_of(ctx), ctx->rec.p, out.p, cnt.p, total);
-    if (ctx->dense_rank != kDenseOff) {
+    if (ctx->last_dense_rank != kDenseOff) {
         DenseArgs da{};
         da.list = dense_list_of(ctx);
         da.entries = reinterpret_cast<const uint2*>(ctx->entries.p);
