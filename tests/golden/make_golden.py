@@ -27,6 +27,9 @@ CASES = [
     # config-5 fast shapes (speed <= 100) have a cell period of 0.04: keep the window shorter so that no Reiterate
     # (a single-hitbox update) falls between two bulk steps of the chained device state
     dict(name="clustered_2000", scene="c5", n=2000, end=0.03, dt=0.03, steps=3),
+    # config 4's density (1 shape per unit^2, ~30 entries per slot run): from its second step on the device takes the
+    # dense-run path (k_solve_dense), chosen from the first step's counters
+    dict(name="dense_250", scene="uniform", n=250, density=1.0, end=0.1, dt=0.1, steps=3),
 ]
 
 
@@ -35,7 +38,7 @@ def make_scene(case):
         return scenes.c1(case["n"])
     if case["scene"] == "c5":
         return scenes.c5(case["n"])
-    return scenes.uniform_density(case["n"])
+    return scenes.uniform_density(case["n"], density=case.get("density", 0.025))
 
 
 def drain_until(orc, t_stop):

@@ -22,7 +22,7 @@ def make_scene(case):
         return scenes.c1(case["n"])
     if case["scene"] == "c5":
         return scenes.c5(case["n"])
-    return scenes.uniform_density(case["n"])
+    return scenes.uniform_density(case["n"], density=case.get("density", 0.025))
 
 
 def fx(h):
