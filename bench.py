@@ -1,22 +1,31 @@
 #!/usr/bin/env python
-"""bench.py — hitbox updates/s + pair TOI solves/s of the bulk step (BASELINE.json metric).
+"""bench.py — hitbox updates/s + pair TOI solves/s of the bulk step (BASELINE.json metric), SURVEY.md 8(d) contract.
 
-A "step" = one cb200_bulk_update over the whole scene: every hitbox rebased to T, re-binned into the grid,
-every candidate pair's collide_time solved (plus separate_time for the overlapping pairs), next event
-min-reduced.  Workload at N=1: config 3 (1M mixed circles/rects, uniform density 0.025/unit^2, cell 4,
-padding 0.01, bulk step every 0.1 time units).  N>1: weak scaling, one 1M-hitbox column strip per GPU.
+A "step" = one bulk update of the whole scene through the C ABI: every hitbox rebased to T, re-binned into the grid, every
+candidate pair's collide_time solved (plus separate_time for the overlapping pairs), next event min-reduced, and the ordered
+event queue of the step materialised and copied to the host.  Workload at N=1: config 3 (1M mixed circles/rects, uniform
+density 0.025/unit^2, cell 4, padding 0.01, bulk step every 0.1 time units).  N>1: weak scaling, one 1M-hitbox column strip
+per GPU; the same line carries a `config4` block (16,777,216 shapes in 4096^2 split over the N strips — strong scaling; the
+N=1 line carries the one-GPU anchor).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n HITBOXES] [--workload c3|c3_dense|c5]
 
-Prints ONE JSON line (rank 0).  `value` = device-resident whole-job throughput; `e2e` = the same metric with
-new velocities coming from pinned HOST arrays each step and the sorted event list read back (H2D + D2H inside
-the timed region); `roofline` = dominant kernel vs the measured HBM peak; `cpu_baseline` = the oracle (C++
-restatement of the reference; Rust toolchain absent) on one host core, bounded sample.  `--impl reference` times that
-oracle on ALL host threads (one independent Collider per thread: the reference itself is single-threaded).
+ONE JSON line on stdout (rank 0):
+  value / ms_per_step   t_step of SURVEY 8(d): device-resident state, bulk step + queue materialisation + D2H of the sorted
+                        event list into pinned memory; median over `repeats` runs of K steps, max over ranks
+  device_ms_per_step    the kernels of the bulk step alone (CUDA events on the engine stream)
+  e2e                   the same through host buffers: new velocities H2D from pinned memory every step, events D2H
+  roofline              B_step = 184 N + 104 E + 16 C + 24 V / device time of the step, vs the measured HBM peak;
+                        per-kernel figures beside it
+  cpu_baseline          the oracle port (C++ restatement of the reference; no Rust toolchain) on ONE host core, bounded sample
+  config1 / config2     event-driven loops through the Collider API, device vs port (N=1 only)
+  parity                a down-scaled copy of the workload run through the same code path and checked against the oracle
+`--impl reference` times ONE single-threaded oracle collider on the full scene (the reference is single-threaded).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import importlib
 import json
 import math
@@ -33,29 +42,39 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 DT = 0.1  # bulk step period (config 2/3)
-METRIC = "hitbox updates/sec (full re-bin + pair TOI solve + next-event min per bulk step)"
+METRIC = "hitbox updates/sec (full re-bin + pair TOI solve + next-event min + ordered event list per bulk step)"
 UNIT = "hitbox updates/s"
+C4_TOTAL = 16_777_216
+C4_SIDE = 4096.0
+DENSITY = {"c3": 0.025, "c3_dense": 1.0, "c5": 0.025}
 
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config_of(args):
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": f"{args.workload}: {args.n} mixed circles/rects per GPU, uniform density {DENSITY[args.workload]}/unit^2, cell_width 4, padding 0.01, "
+                        f"bulk step every {DT} (full re-bin + pair TOI solve + next-event min + ordered event list)",
+            "hitboxes_per_gpu": args.n, "scaling_unit": "one column strip of the world per GPU"}
 
 
 def make_workload(scenes, name: str, n: int, rank: int, world: int):
     """Per-rank scene.  Weak scaling: rank r owns the column strip [r*W, (r+1)*W) of a world `world` strips wide."""
-    if name == "c3":
-        side = math.sqrt(n / 0.025)
-        s = scenes.make_scene(n, side, side, seed=scenes.SEED_BASE + 3 + 1000 * rank, x0=side * rank)
-    elif name == "c3_dense":
-        side = math.sqrt(n / 1.0)
+    if name in ("c3", "c3_dense"):
+        side = math.sqrt(n / DENSITY[name])
         s = scenes.make_scene(n, side, side, seed=scenes.SEED_BASE + 3 + 1000 * rank, x0=side * rank)
     elif name == "c5":
         s = scenes.c5(n)
         s["pos_x"] = s["pos_x"] + math.sqrt(n / 0.025) * rank
+    elif name == "c4":  # config 4: C4_TOTAL shapes in 4096 x 4096, strip `rank` of `world`
+        per = n
+        s = scenes.make_scene(per, C4_SIDE / world, C4_SIDE, seed=scenes.SEED_BASE + 4 + 1000 * rank, x0=C4_SIDE / world * rank)
     else:
         raise SystemExit(f"unknown workload {name}")
     s["id"] = s["id"] + np.uint64(rank) * np.uint64(n)
@@ -90,97 +109,95 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def oracle_timing(scene_fn, n_sample: int, steps: int, warmup: int):
-    """The reference's CPU implementation of the path (C++ restatement; Rust toolchain absent): the ascending
-    set_hitbox_vel loop per step, single-threaded like the reference.  Returns (updates/s, solves/s, ms/step, stats)."""
+# ------------------------------------------------------------------------------------------------ CPU side (oracle port)
+def oracle_bulk_timing(scene, steps: int, warmup: int):
+    """The reference's CPU implementation of the path (C++ restatement; Rust toolchain absent): ONE collider, the ascending
+    set_hitbox_vel loop per step, single-threaded like the reference.  (updates/s, solves/s, ms/step, set-up seconds)."""
     from oracle import oracle_py as oracle
 
-    s = scene_fn(n_sample)
+    t_setup = time.perf_counter()
     orc = oracle.Collider(4.0, 0.01)
-    orc.add_hitboxes(s)
+    orc.add_hitboxes(scene)
+    t_setup = time.perf_counter() - t_setup
+    n = len(scene["id"])
     T = 0.0
     for _ in range(warmup):
         orc.bulk_update(end_time=T + DT)
-        T = min(T + DT, orc.next_time())
+        T = min(T + DT, orc.next_time())  # stay within the reference's set_time contract without draining events
         orc.set_time(T)
     orc.stats(reset=True)
     t0 = time.perf_counter()
-    done = 0
     for _ in range(steps):
         orc.bulk_update(end_time=T + DT)
-        done += 1
-        T = min(T + DT, orc.next_time())  # stay within the reference's set_time contract without draining events
+        T = min(T + DT, orc.next_time())
         orc.set_time(T)
     el = time.perf_counter() - t0
     st = orc.stats()
-    return n_sample * done / el, (st["collide_solves"] + st["separate_solves"]) / el, el / done * 1e3, st
+    return n * steps / el, (st["collide_solves"] + st["separate_solves"]) / el, el / steps * 1e3, t_setup
 
 
-def oracle_timing_threads(scene_fn, n_sample: int, steps: int, warmup: int, threads: int):
-    """The same, on every host thread: the reference is single-threaded, so "all the host threads it can use" is one
-    independent Collider per thread, each on its own tile (n_sample hitboxes, same density, different seed offset).  The C
-    calls release the GIL.  Returns whole-host (updates/s, solves/s, ms per step of one collider)."""
+def oracle_tiles_all_threads(scenes, workload: str, n_tile: int, steps: int, threads: int):
+    """Separately named row: one independent collider per host thread, each on its own tile of the scene (no cross-tile pairs)."""
     from concurrent.futures import ThreadPoolExecutor
-    import threading as th
 
     from oracle import oracle_py as oracle
 
-    oracle.lib()  # build / load once, before the threads start
-    start = th.Barrier(threads)
+    oracle.lib()
+    start = threading.Barrier(threads)
     spans = [None] * threads
 
     def worker(k):
-        s = scene_fn(n_sample, k)
+        s = make_workload(scenes, workload, n_tile, k, 1)
         orc = oracle.Collider(4.0, 0.01)
         orc.add_hitboxes(s)
-        T = 0.0
-        for _ in range(warmup):
-            orc.bulk_update(end_time=T + DT)
-            T = min(T + DT, orc.next_time())
-            orc.set_time(T)
-        orc.stats(reset=True)
+        orc.bulk_update(end_time=DT)
+        T = min(DT, orc.next_time())
+        orc.set_time(T)
         start.wait()
         t0 = time.perf_counter()
         for _ in range(steps):
             orc.bulk_update(end_time=T + DT)
             T = min(T + DT, orc.next_time())
             orc.set_time(T)
-        t1 = time.perf_counter()
-        st = orc.stats()
-        spans[k] = (t0, t1, st["collide_solves"] + st["separate_solves"])
+        spans[k] = (t0, time.perf_counter())
 
     with ThreadPoolExecutor(threads) as ex:
         list(ex.map(worker, range(threads)))
-    el = max(t1 for _, t1, _ in spans) - min(t0 for t0, _, _ in spans)
-    return threads * n_sample * steps / el, sum(sv for _, _, sv in spans) / el, el / steps * 1e3
+    el = max(t1 for _, t1 in spans) - min(t0 for t0, _ in spans)
+    return threads * n_tile * steps / el
 
 
 def run_reference(args, out):
+    """Reference arm: ONE single-threaded collider on the full scene of this config — same config as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     scenes = importlib.import_module("collider-rs_b200.scenes")
-    threads = max(1, args.ref_threads or (os.cpu_count() or 1))
-    # bounded: every thread steps its own tile of the scene; the tile shrinks with the thread count so that the run (scene
-    # set-up included) stays within a few minutes on any host
-    n_sample = max(10_000, min(args.n, args.ref_sample) // max(1, threads // 4))
-    ups, sps, ms = oracle_timing_threads(lambda m, k: make_workload(scenes, args.workload, m, k, 1), n_sample, args.steps, max(1, min(args.warmup, 1)), threads)
-    sample = (f"{threads} independent colliders side by side, one per host thread (the reference is single-threaded), each a tile of {n_sample} hitboxes of the "
-              f"{args.workload} scene (same density), {args.steps} bulk-equivalent steps (ascending set_hitbox_vel loop)")
+    scene = make_workload(scenes, args.workload, args.n, 0, 1)
+    warm = max(1, min(args.warmup, 2))
+    ups, sps, ms, t_setup = oracle_bulk_timing(scene, args.steps, warm)
+    sample = (f"ONE single-threaded collider (the reference is single-threaded) on the full {args.n}-hitbox {args.workload} scene, {warm} warm-up + "
+              f"{args.steps} bulk-equivalent steps (ascending set_hitbox_vel loop, end_time = T + {DT}); add_hitbox set-up {t_setup:.1f} s outside the timed region")
     line = {
-        "impl": "reference", "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": ups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {args.n} mixed circles/rects, cell_width 4, padding 0.01, bulk step every {DT}", "cpu_sample_hitboxes": n_sample * threads,
-                   "cpu_threads": threads},
+        "config": config_of(args),
         "pair_solves_per_s": sps,
-        "cpu_baseline": {"value": ups, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": ups, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "note": "C++17 restatement of the reference (oracle/); the Rust crate cannot be built here (no rustc/cargo)"},
         "e2e": {"value": ups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cores_available": os.cpu_count(),
     }
+    if not args.no_all_threads:
+        threads = max(1, os.cpu_count() or 1)
+        n_tile = max(10_000, min(args.n, 200_000) // max(1, threads // 4))
+        line["cpu_all_threads_tiled"] = {
+            "value": oracle_tiles_all_threads(scenes, args.workload, n_tile, 3, threads), "unit": UNIT, "cores": threads,
+            "note": f"NOT the config: {threads} independent colliders side by side, one per host thread, each a {n_tile}-hitbox tile of the same density (no cross-tile pairs)"}
     print(json.dumps(line), file=out)
 
 
+# ------------------------------------------------------------------------------------------------ GPU side
 def main():
     # stdout carries exactly ONE JSON line: route everything else that native libraries print to fd 1 (e.g. NCCL's
     # version banner) to stderr, and keep the real stdout for the result line
@@ -193,6 +210,251 @@ def main():
         real_stdout.flush()
 
 
+class Job:
+    """One workload on this rank: engine (single or sharded), step function, overlap hand-over."""
+
+    def __init__(self, cb, scenes, sharding, dist, workload, n, rank, world, local_rank, grid="", slab=0):
+        self.cb, self.rank, self.world, self.n, self.dist = cb, rank, world, n, dist
+        self.scene = make_workload(scenes, workload, n, rank, world)
+        self.sh = None
+        if world == 1:
+            self.eng = cb.Engine(scenes.CELL_WIDTH, scenes.PADDING, device=local_rank)
+            if grid:
+                self.eng.set_grid(*[int(v) for v in grid.split(",")])
+            self.eng.upload_state(**self.scene)
+            self.step = self.eng.bulk_update
+        else:
+            # spatial sharding (SURVEY.md 8e): one column strip of the world per rank; halo records and next-event keys are pushed
+            # into the peers' memory by the step kernels (CB200_EXCHANGE=nccl: two NCCL all-gathers instead)
+            width = C4_SIDE / world if workload == "c4" else math.sqrt(n / DENSITY[workload])
+            bounds = sharding.strip_bounds(world, 0.0, width * world, scenes.CELL_WIDTH)
+            self.sh = sharding.ShardedEngine(cb, scenes.CELL_WIDTH, scenes.PADDING, local_rank, bounds, n * world, sharding.Exchange(),
+                                             direct=os.environ.get("CB200_EXCHANGE", "direct") != "nccl")
+            self.eng = self.sh.eng
+            if slab:
+                self.eng.shard_set_slab(slab)
+            if grid:
+                self.eng.set_grid(*[int(v) for v in grid.split(",")])
+            self.sh.upload_state(**self.scene)
+            self.strip = (width * rank, width * (rank + 1))
+            self.step = lambda T, end_time, **vel: self.sh.bulk_update(T, end_time, **vel)
+        self.clock = DT
+
+    def first_step(self):
+        """Pairs already in contact at T = 0 come back as Collide events at T; they become the overlap set (what add_hitbox's
+        immediate-overlap list does in the reference, collider.rs:355-365).  Sharded: a pair whose owner cell may drift into
+        another strip is handed to every rank (each rank solves only the pairs whose owner column it holds)."""
+        cb = self.cb
+        res = self.step(0.0, end_time=DT)
+        ev = self.eng.fetch_events()
+        touching = ev[(ev["kind"] == cb.EV_COLLIDE) & (ev["time"] == 0.0)]
+        ta, tb = touching["a"].copy(), touching["b"].copy()
+        if self.world > 1:
+            lo, hi = np.uint64(self.rank * self.n), np.uint64((self.rank + 1) * self.n)
+            px = self.scene["pos_x"]
+
+            def near_edge(ids):
+                local = (ids >= lo) & (ids < hi)
+                x = px[np.where(local, ids - lo, 0).astype(np.int64)]
+                return ~local | (x < self.strip[0] + 16.0) | (x > self.strip[1] - 16.0)
+
+            m = near_edge(ta) | near_edge(tb)
+            parts = [None] * self.world
+            self.dist.all_gather_object(parts, (ta[m], tb[m]))
+            ta = np.concatenate([ta[~m]] + [p[0] for p in parts])
+            tb = np.concatenate([tb[~m]] + [p[1] for p in parts])
+        self.eng.set_overlaps(ta, tb)
+        return res
+
+    def device_step(self):
+        T = self.clock
+        self.clock = T + DT  # the next step time is exactly the end_time installed by the previous step
+        return self.step(T, end_time=self.clock)
+
+
+def events_digest(ev):
+    h = hashlib.sha256()
+    for k in ("time", "a", "b", "kind"):
+        h.update(np.ascontiguousarray(ev[k]).tobytes())
+    return h.hexdigest()
+
+
+def parity_check(cb, scenes, sharding, dist, workload, rank, world, local_rank, n_small=20_000):
+    """A down-scaled copy of the workload through the SAME code path (sharded exchange included), two steps, against the oracle:
+    the union of the ranks' sorted event lists must be the oracle's list, bit for bit."""
+    from oracle import oracle_py as oracle
+
+    job = Job(cb, scenes, sharding, dist, workload, n_small, rank, world, local_rank)
+    full = {k: np.concatenate([make_workload(scenes, workload, n_small, r, world)[k] for r in range(world)]) for k in job.scene}
+    ok, n_events = True, 0
+    orc = None
+    if rank == 0:
+        orc = oracle.Collider(scenes.CELL_WIDTH, scenes.PADDING)
+        orc.add_hitboxes(full)
+    T = 0.0
+    for step in range(2):
+        if rank == 0:
+            oa, ob = orc.dump_overlaps()
+        else:
+            oa = ob = None
+        if world > 1:
+            box = [(oa, ob)]
+            dist.broadcast_object_list(box, src=0)
+            oa, ob = box[0]
+        job.eng.set_overlaps(oa, ob)
+        job.step(T, end_time=T + DT)
+        ev = job.eng.fetch_events().copy()
+        parts = [ev]
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, ev)
+        if rank == 0:
+            orc.bulk_update(end_time=T + DT)
+            t, idx, kind, a, b = orc.dump_events()
+            evs = np.concatenate(parts)
+            cls, kbit = np.where(evs["kind"] == 0, 0, 1), np.where(evs["kind"] == 1, 1, 0)
+            evs = evs[np.lexsort((evs["b"], kbit, evs["a"], cls, evs["time"]))]
+            same = (len(evs) == len(t) and np.array_equal(evs["kind"], kind) and np.array_equal(evs["a"], a) and
+                    np.array_equal(evs["b"], np.where(kind == 0, 0, b)) and np.array_equal(evs["time"].view(np.uint64), t.view(np.uint64)))
+            ok = ok and bool(same)
+            n_events += len(t)
+            T += DT
+            while True:
+                tt = min(orc.next_time(), T)
+                orc.set_time(tt)
+                while orc.next() is not None:
+                    pass
+                if tt >= T:
+                    break
+        else:
+            T += DT
+    return {"scene": f"{workload} at {n_small} hitboxes per GPU, {world} GPU(s), 2 chained steps, same code path", "events_compared": int(n_events),
+            "bit_identical_to_oracle": ok}
+
+
+def timed_passes(job, barrier, steps, repeats, body):
+    """`repeats` runs of `steps` calls of body(); returns (per-run wall seconds, accumulated dict of body's counters)."""
+    walls, acc = [], {}
+    for _ in range(repeats):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for k, v in body().items():
+                acc[k] = acc.get(k, 0) + v
+        barrier()
+        walls.append(time.perf_counter() - t0)
+    return walls, acc
+
+
+def collider_rows(cb, scenes, device):
+    """Configs 1 and 2 through the Collider API (event-driven: README.md:66-80 loop, velocity halving on Collide), device
+    Collider vs the oracle port, both driven by a native loop (cb200_collider_run_halving_loop / orc_halving_loop)."""
+    from oracle import oracle_py as oracle
+
+    col = importlib.import_module("collider-rs_b200.collider")
+    rows = {}
+    # config 1: 1,000 shapes to t = 100
+    s = scenes.c1()
+    orc = oracle.Collider(scenes.CELL_WIDTH, scenes.PADDING)
+    orc.add_hitboxes(s)
+    orc.stats(reset=True)
+    t0 = time.perf_counter()
+    ev_o, col_o = orc.halving_loop(100.0)
+    t_o = time.perf_counter() - t0
+    upd_o = orc.stats()["updates"]
+    d = col.Collider(scenes.CELL_WIDTH, scenes.PADDING, device=device)
+    d.add_hitboxes(s)
+    l0 = d.launch_count()
+    t0 = time.perf_counter()
+    ev_d, col_d = d.halving_loop(100.0)
+    t_d = time.perf_counter() - t0
+    rows["config1"] = {"workload": "1,000 mixed circles/squares in 200x200, README loop to t=100, velocity halving on Collide",
+                       "events": ev_d, "events_match_port": bool(ev_d == ev_o and col_d == col_o),
+                       "device_collider": {"events_per_s": ev_d / t_d, "seconds": t_d, "gpu_launches": d.launch_count() - l0},
+                       "cpu_port_single_thread": {"events_per_s": ev_o / t_o, "hitbox_updates_per_s": upd_o / t_o, "seconds": t_o}}
+    # config 2: 100k shapes, bulk step every 0.1 with new velocities, events processed in between
+    s = scenes.c2()
+    n = len(s["id"])
+    steps = 5
+    orc = oracle.Collider(scenes.CELL_WIDTH, scenes.PADDING)
+    orc.add_hitboxes(s, end_time=DT)
+    d = col.Collider(scenes.CELL_WIDTH, scenes.PADDING, device=device)
+    d.add_hitboxes(s, end_time=DT)
+    vel = [(scenes.uniform(300 + k, n, 1, -2.0, 2.0), scenes.uniform(300 + k, n, 2, -2.0, 2.0)) for k in range(steps)]
+    out = {}
+    for name, c in (("cpu_port_single_thread", orc), ("device_collider", d)):
+        T, ev_n, t_bulk, t_loop = 0.0, 0, 0.0, 0.0
+        for k in range(steps):
+            t0 = time.perf_counter()
+            c.bulk_update(end_time=T + DT, vx=vel[k][0], vy=vel[k][1])
+            t1 = time.perf_counter()
+            e, _ = c.halving_loop(T + DT)
+            t2 = time.perf_counter()
+            ev_n += e
+            t_bulk += t1 - t0
+            t_loop += t2 - t1
+            T += DT
+        out[name] = {"hitbox_updates_per_s": n * steps / (t_bulk + t_loop), "bulk_ms_per_step": t_bulk / steps * 1e3, "events": ev_n,
+                     "events_per_s": ev_n / t_loop if t_loop > 0 else None, "event_loop_ms_per_step": t_loop / steps * 1e3}
+    rows["config2"] = {"workload": f"100k mixed circles/rects, bulk update every {DT} with new velocities (host arrays), events between the steps "
+                                   f"processed through next() with velocity halving on Collide, {steps} steps",
+                       "events_match_port": bool(out["device_collider"]["events"] == out["cpu_port_single_thread"]["events"]), **out}
+    return rows
+
+
+def config4_block(cb, scenes, sharding, dist, rank, world, local_rank, barrier, steps=5, warmup=3):
+    """BASELINE config 4: 16,777,216 shapes in 4096 x 4096 (1 per unit^2), split over the N column strips (N=1: the one-GPU anchor)."""
+    import torch
+
+    n = C4_TOTAL // world
+    old = os.environ.get("CB200_DENSE_RANK")
+    os.environ["CB200_DENSE_RANK"] = "4"  # dense slot runs from the first step (the automatic choice needs one step of history)
+    try:
+        job = Job(cb, scenes, sharding, dist, "c4", n, rank, world, local_rank, slab=max(131072, n // 32) if world > 1 else 0)
+    finally:
+        if old is None:
+            os.environ.pop("CB200_DENSE_RANK", None)
+        else:
+            os.environ["CB200_DENSE_RANK"] = old
+    job.first_step()
+    job.eng.set_stage_timing(False)
+    for _ in range(warmup):
+        job.device_step()
+    job.eng.reset_timing()
+    solves = [0]
+
+    def body():
+        r = job.device_step()
+        solves[0] += r.n_collide_solves + r.n_separate_solves
+        return {}
+
+    walls, _ = timed_passes(job, barrier, steps, 1, body)
+    dev_ms, _ = job.eng.step_timing()
+    ev_bytes = [0]
+
+    def body_fetch():
+        job.device_step()
+        evs = job.eng.fetch_events(pinned=True)
+        ev_bytes[0] += evs.nbytes
+        return {}
+
+    body_fetch()
+    walls_t, _ = timed_passes(job, barrier, steps, 1, body_fetch)
+    t = torch.tensor([walls[0], walls_t[0], dev_ms], dtype=torch.float64, device="cuda")
+    s = torch.tensor([float(solves[0])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    wall, wall_t, dev = t.tolist()
+    fallbacks = job.eng.event_sort_fallbacks()
+    del job
+    return {"workload": f"{C4_TOTAL} shapes in 4096 x 4096 (1 per unit^2), {world} column strip(s) of {n} hitboxes, bulk step every {DT}, dense slot runs through k_solve_dense",
+            "n_gpus": world, "hitboxes_total": C4_TOTAL, "steps": steps, "warmup": warmup,
+            "device_ms_per_step": dev, "ms_per_step_device_resident": wall / steps * 1e3, "hitbox_updates_per_s": C4_TOTAL * steps / wall,
+            "pair_solves_per_s": s.item() / wall, "t_step_ms_with_event_list": wall_t / steps * 1e3, "d2h_bytes_per_step_rank0": int(ev_bytes[0] / (steps + 1)),
+            "event_sort_fallbacks": fallbacks, "scaling": "strong (fixed 16,777,216 hitboxes; compare with the n_gpus=1 line's block)"}
+
+
 def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,9 +463,13 @@ def _main(out):
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", "--hitboxes", dest="n", type=int, default=1_000_000, help="hitboxes per GPU")
     ap.add_argument("--workload", default="c3", choices=["c3", "c3_dense", "c5"])
-    ap.add_argument("--ref-sample", type=int, default=200_000, help="hitboxes in the CPU sample")
-    ap.add_argument("--ref-threads", type=int, default=0, help="--impl reference: host threads (0 = all)")
+    ap.add_argument("--repeats", type=int, default=3, help="runs of K steps; the median run is reported")
+    ap.add_argument("--ref-sample", type=int, default=500_000, help="hitboxes in the cpu_baseline sample of the GPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-all-threads", action="store_true", help="--impl reference: skip the separately named all-threads row")
+    ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--no-collider-rows", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--grid", default="", help="force the device grid period: log2_w,log2_h")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -229,194 +495,165 @@ def _main(out):
 
     cb = importlib.import_module("collider-rs_b200")
     scenes = importlib.import_module("collider-rs_b200.scenes")
+    sharding = importlib.import_module("collider-rs_b200.sharding")
     hbm_peak, peak_kind = load_peaks()
+    n, K, R = args.n, args.steps, max(1, args.repeats)
 
-    n = args.n
-    scene = make_workload(scenes, args.workload, n, rank, world)
-    halo = {"sent": 0, "received": 0, "steps": 0}
-    if world == 1:
-        eng = cb.Engine(scenes.CELL_WIDTH, scenes.PADDING, device=local_rank)
-        if args.grid:
-            eng.set_grid(*[int(v) for v in args.grid.split(",")])
-        eng.upload_state(**scene)
-        step_fn = eng.bulk_update
-    else:
-        # spatial sharding: one column strip of the world per rank, NCCL halo exchange between the two
-        # phases of the step, global next event by an all-gather + min of the per-rank keys
-        sharding = importlib.import_module("collider-rs_b200.sharding")
-        side = math.sqrt(n / (1.0 if args.workload == "c3_dense" else 0.025))
-        bounds = sharding.strip_bounds(world, 0.0, side * world, scenes.CELL_WIDTH)
-        sh = sharding.ShardedEngine(cb, scenes.CELL_WIDTH, scenes.PADDING, local_rank, bounds, n * world, sharding.Exchange(),
-                                    direct=os.environ.get("CB200_EXCHANGE", "direct") != "nccl")
-        eng = sh.eng
-        if args.grid:
-            eng.set_grid(*[int(v) for v in args.grid.split(",")])
-        sh.upload_state(**scene)
+    parity = None if args.no_parity else parity_check(cb, scenes, sharding, dist, args.workload, rank, world, local_rank)
 
-        def step_fn(T, end_time, **vel):
-            return sh.bulk_update(T, end_time, **vel)
-
-    # first step: pairs already in contact at T = 0 come back as Collide events at T; they become the overlap set
-    # (what add_hitbox's immediate-overlap list does in the reference, collider.rs:355-365)
-    res = step_fn(0.0, end_time=DT)
-    ev = eng.fetch_events()
-    touching = ev[(ev["kind"] == cb.EV_COLLIDE) & (ev["time"] == 0.0)]
-    ta, tb = touching["a"].copy(), touching["b"].copy()
-    # sharded: every rank keeps the overlapping pairs it owns (pairs whose owner cell drifts into another strip would
-    # have to be handed over by the host; over this run's 0.1-unit steps that is a vanishing fraction)
-    eng.set_overlaps(ta, tb)
-    clock = [DT]  # the next step time is exactly the end_time installed by the previous step
-
-    def device_step():
-        T = clock[0]
-        clock[0] = T + DT
-        return step_fn(T, end_time=clock[0])
-
+    job = Job(cb, scenes, sharding, dist, args.workload, n, rank, world, local_rank, grid=args.grid)
+    eng = job.eng
+    job.first_step()
     eng.set_stage_timing(False)  # the timed region carries two CUDA events per step (start / end), none between the kernels;
     # the engine then replays the step as one CUDA graph — captured during the warm-up (once per column-buffer set: the table
     # re-sort every 16 steps alternates between two)
     for _ in range(max(args.warmup, 17)):
-        res = device_step()
-    launches0 = eng.launch_count()
-    eng.reset_timing()
+        job.device_step()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    solves = 0
-    entries = cells = events = work = seps = 0
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res = device_step()
-        solves += res.n_collide_solves + res.n_separate_solves
-        entries += res.n_entries
-        cells += res.n_cells
-        events += res.n_events
-        work += res.n_work_items
-        seps += res.n_separate_solves
-    barrier()
-    wall = time.perf_counter() - t0
-    launches = eng.launch_count() - launches0
-    dev_ms, _ = eng.step_timing()
-    # per-kernel durations: the same steps again with CUDA events between the stages (each event adds ~2 us of stream time,
-    # so these are upper bounds and their sum exceeds device_ms_per_step)
+
+    # (1) device-resident step alone: kernels of the bulk step, CUDA events per step
+    launches0 = eng.launch_count()
+    eng.reset_timing()
+
+    def body_dev():
+        r = job.device_step()
+        return {"solves": r.n_collide_solves + r.n_separate_solves, "entries": r.n_entries, "cells": r.n_cells, "events": r.n_events,
+                "work": r.n_work_items, "seps": r.n_separate_solves}
+
+    walls_dev, acc = timed_passes(job, barrier, K, R, body_dev)
+    launches = (eng.launch_count() - launches0) // R
+    dev_ms, _ = eng.step_timing()  # average over all R*K steps
+
+    # (2) t_step of SURVEY 8(d): step + ordered queue (device sort) + D2H of the event list into pinned memory
+    digest = [None]
+
+    def body_tstep():
+        job.device_step()
+        evs = eng.fetch_events(pinned=True)
+        if digest[0] is None:
+            digest[0] = events_digest(evs)
+        return {"ev_bytes": evs.nbytes}
+
+    body_tstep()
+    digest[0] = None
+    walls_t, acc_t = timed_passes(job, barrier, K, R, body_tstep)
+
+    # (3) per-kernel durations: K steps with CUDA events between the stages (each event adds ~2 us of stream time, so these are
+    # upper bounds and their sum exceeds device_ms_per_step)
     eng.set_stage_timing(True)
-    for _ in range(args.steps):
-        device_step()
+    for _ in range(K):
+        job.device_step()
     _, stage_ms = eng.step_timing()
     eng.set_stage_timing(False)
 
-    # e2e: new velocities arrive from pinned host arrays every step, sorted events are read back
+    # (4) e2e: new velocities arrive from pinned host arrays every step, sorted events are read back
     pvx, pvy = cb.PinnedArray(n, np.float64), cb.PinnedArray(n, np.float64)
-    pvx.array[:] = scene["vel_x"]
-    pvy.array[:] = scene["vel_y"]
+    pvx.array[:] = job.scene["vel_x"]
+    pvy.array[:] = job.scene["vel_y"]
 
-    def e2e_step():
-        T = clock[0]
-        clock[0] = T + DT
-        r = step_fn(T, end_time=clock[0], vel_x=pvx.array, vel_y=pvy.array)
+    def body_e2e():
+        T = job.clock
+        job.clock = T + DT
+        job.step(T, end_time=job.clock, vel_x=pvx.array, vel_y=pvy.array)
         evs = eng.fetch_events(pinned=True)  # sorted queue of the step, D2H into page-locked memory
-        return r, evs
+        return {"d2h": evs.nbytes + C_sizeof_result(cb)}
 
     for _ in range(3):
-        e2e_step()
-    d2h = 0
-    e2e_each = []
-    barrier()
-    t1 = time.perf_counter()
-    for _ in range(args.steps):
-        ts = time.perf_counter()
-        r, evs = e2e_step()
-        d2h += evs.nbytes + C_sizeof_result(cb)
-        e2e_each.append((time.perf_counter() - ts) * 1e3)
-    barrier()
-    e2e_wall = time.perf_counter() - t1
+        body_e2e()
+    walls_e, acc_e = timed_passes(job, barrier, K, R, body_e2e)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    times = torch.tensor([wall, e2e_wall, dev_ms], dtype=torch.float64, device="cuda")
-    sums = torch.tensor([float(solves), float(entries), float(cells), float(events)], dtype=torch.float64, device="cuda")
+    med = lambda w: float(np.median(w))
+    times = torch.tensor([med(walls_dev), med(walls_t), med(walls_e), dev_ms, min(walls_t), max(walls_t)], dtype=torch.float64, device="cuda")
+    sums = torch.tensor([float(acc["solves"]), float(acc["entries"]), float(acc["cells"]), float(acc["events"])], dtype=torch.float64, device="cuda")
+    digests = [digest[0]]
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    wall_max, e2e_max, dev_ms_max = times.tolist()
-    solves_all, entries_all, cells_all, events_all = sums.tolist()
+        digests = [None] * world
+        dist.all_gather_object(digests, digest[0])
+    wall_dev, wall_t, wall_e, dev_ms_max, wall_t_min, wall_t_max = times.tolist()
+    solves_all = sums.tolist()[0]
+
+    sort_fallbacks = eng.event_sort_fallbacks()
+    c4 = None
+    if not args.no_config4 and args.workload == "c3":
+        del job, eng
+        c4 = config4_block(cb, scenes, sharding, dist, rank, world, local_rank, barrier)
 
     if rank == 0:
-        K = args.steps
-        E, Cc, V, P, W, Q = entries / K, cells / K, events / K, solves / K, work / K, seps / K
-        lw, lh = eng.get_grid()
-        n_slots = 1 << (lw + lh)
-        # algorithmic bytes per launch of each kernel (DESIGN.md "bytes per unit")
+        KR = K * R
+        E, Cc, V, P, W, Q = acc["entries"] / KR, acc["cells"] / KR, acc["events"] / KR, acc["solves"] / KR, acc["work"] / KR, acc["seps"] / KR
+        # B_step = 184 N + 104 E + 16 C + 24 V — state in/out 152 N, rect re-reads of the sort passes 32 N, entry
+        # write + read 8 E, records gathered per entry in the pair stage 96 E, cell count/offset 16 C, events 24 V
+        b_step = 184.0 * n + 104.0 * E + 16.0 * Cc + 24.0 * V
+        t_dev = dev_ms_max * 1e-3
+        achieved = b_step / t_dev / 1e9
         stage_ms.setdefault("exchange", 0.0)
-        alg = {
-            "pre": 4.0 * n_slots,                              # k_step_zero
-            "stage_a": 262.0 * n + 8.0 * E,
-            "scan": 8.0 * n_slots,
-            "scatter": 16.0 * n + 16.0 * E,
-            "candidates": 8.0 * E + 16.0 * W,                  # k_enum_pairs
-            "solve": 208.0 * W + 200.0 * Q + 16.0 * V,         # test + solve + events
+        kernel_terms = {  # the same B_step attributed to the kernels that move it
+            "stage_a": ("k_stage_a", 152.0 * n),
+            "scan": ("k_step_zero + k_scan_slots", 16.0 * Cc),
+            "scatter": ("k_scatter", 32.0 * n + 4.0 * E),
+            "candidates": ("k_enum_pairs", 4.0 * E),
+            "solve": ("k_solve (+ k_solve_dense)", 96.0 * E + 24.0 * V),
         }
-        kernel_of = {"pre": "k_step_zero", "stage_a": "k_stage_a", "scan": "k_scan_slots", "scatter": "k_scatter", "candidates": "k_enum_pairs",
-                     "solve": "k_solve"}  # (dense_path: the solve stage is k_solve_dense + k_solve)
-        # Dense scenes (c3_dense, c5): long slot runs are solved by k_solve_dense from shared memory and never become work items,
-        # so W no longer counts them; that kernel is issue-bound (f64), not HBM-bound — its pairs are reported, its bytes are not
-        # part of this model (DESIGN.md "Dense cells").
-        dense_path = W + Q < 0.9 * P
-        dom = max((k for k in alg if k != "pre"), key=lambda k: stage_ms[k])
-        achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
-        # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this same command (profiles/)
+        stage_ms["scan"] = stage_ms.get("scan", 0.0) + stage_ms.get("pre", 0.0)
+        per_kernel = {name: {"ms": stage_ms[k], "survey_bytes": b, "frac": b / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak}
+                      for k, (name, b) in kernel_terms.items() if stage_ms.get(k)}
+        dom = max(kernel_terms, key=lambda k: stage_ms.get(k, 0.0))
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath) and args.workload == "c3" and n == 1_000_000:
             with open(tpath) as f:
-                traffic = json.load(f).get(kernel_of[dom])
-        step_bytes = sum(alg.values())
+                tj = json.load(f)
+            traffic = tj.get("whole_step_bytes") or sum(v for v in tj.values() if isinstance(v, (int, float)))
         line = {
-            "metric": METRIC, "value": n * world * K / wall_max, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
-            "ms_per_step": wall_max / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": f"{args.workload}: {n} mixed circles/rects per GPU, uniform density, cell_width 4, padding 0.01, bulk step every {DT} "
-                            f"(full re-bin + pair TOI solve + next-event min)",
-                "hitboxes_per_gpu": n, "grid_slots": n_slots, "l2": "working set per step (SoA state + HbRec + slot table + entries) > 126 MB L2; no flush",
-                "timing": "wall clock around K synchronous C-ABI calls bracketed by barrier+cuda sync, max over ranks; device_ms_per_step = CUDA events on the engine "
-                          "stream around each whole step; stage_ms = a second pass of K steps with events between the kernels",
-            },
-            "pair_solves_per_s": solves_all / wall_max,
+            "metric": METRIC, "value": n * world * K / wall_t, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": wall_t / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_of(args),
+            "timing": {"repeats": R, "reported": "median run of `repeats` runs of K steps, max over ranks",
+                       "value": "t_step of SURVEY 8(d): device-resident state; bulk step + ordered event queue (device sort) + D2H of the event list into pinned "
+                                "host memory; wall clock around the synchronous C-ABI calls, bracketed by barrier + cuda sync",
+                       "t_step_ms_min_max_over_runs": [wall_t_min / K * 1e3, wall_t_max / K * 1e3],
+                       "l2": "working set per step (SoA state + records + slot table + entries, > 300 MB) exceeds the 126 MB L2; no flush needed"},
             "device_ms_per_step": dev_ms_max,
+            "device_resident_step_only": {"value": n * world * K / wall_dev, "unit": UNIT, "ms_per_step": wall_dev / K * 1e3,
+                                          "note": "the bulk step without materialising / copying the event list (next event and counters only)"},
+            "pair_solves_per_s": solves_all / R / wall_t,
             "stage_ms": stage_ms,
-            "per_step": {"cell_entries": E, "cells": Cc, "work_items": W, "pair_solves": P, "events": V},
-            "dense_path": {"active": bool(dense_path), "pairs_per_step": max(0.0, P - Q - W) if dense_path else 0.0,
-                           "note": "pairs of long slot runs solved by k_solve_dense (issue-bound; outside the HBM byte model)"},
+            "per_step": {"cell_entries": E, "cells": Cc, "work_items": W, "pair_solves": P, "events": V, "event_list_bytes": acc_t["ev_bytes"] / KR},
             "gpu_launches": int(launches),
-            "e2e": {"value": n * world * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": int(16 * n), "d2h_bytes_per_step": int(d2h / K),
-                    "ms_per_step": e2e_max / K * 1e3, "ms_per_step_median_rank0": float(np.median(e2e_each)), "ms_per_step_max_rank0": float(np.max(e2e_each)),
-                    "event_sort_fallbacks": eng.event_sort_fallbacks()},
-            "roofline": {"bound": "hbm", "kernel": kernel_of[dom], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "peak_kind": peak_kind,
-                         "per_kernel": {kernel_of[k]: {"ms": stage_ms[k], "bytes": alg[k], "frac": alg[k] / (stage_ms[k] * 1e-3) / 1e9 / hbm_peak}
-                                        for k in alg if stage_ms.get(k)},
-                         "whole_step": {"bytes": step_bytes, "achieved": step_bytes / (dev_ms_max * 1e-3) / 1e9,
-                                        "frac": step_bytes / (dev_ms_max * 1e-3) / 1e9 / hbm_peak,
-                                        # SURVEY 8d's strict I/O lower bound of a step: 152 B of state in + out per hitbox, 24 B per event
-                                        "io_lower_bound_bytes": 152.0 * n + 24.0 * V,
-                                        "io_lower_bound_frac": (152.0 * n + 24.0 * V) / (dev_ms_max * 1e-3) / 1e9 / hbm_peak}},
+            "e2e": {"value": n * world * K / wall_e, "unit": UNIT, "h2d_bytes_per_step": int(16 * n), "d2h_bytes_per_step": int(acc_e["d2h"] / KR),
+                    "ms_per_step": wall_e / K * 1e3, "event_sort_fallbacks": sort_fallbacks},
+            "roofline": {"bound": "hbm", "kernel": "bulk step (all kernels of one cb200_bulk_update)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
+                         "bytes_model": "SURVEY 8(d): B_step = 184 N + 104 E + 16 C + 24 V", "b_step_bytes": b_step,
+                         "frac_on_t_step": b_step / (wall_t / K) / 1e9 / hbm_peak,
+                         "io_lower_bound_bytes": 152.0 * n + 24.0 * V, "io_lower_bound_frac": (152.0 * n + 24.0 * V) / t_dev / 1e9 / hbm_peak,
+                         "dominant_kernel": per_kernel.get(kernel_terms[dom][0]) and {"name": kernel_terms[dom][0], **per_kernel[kernel_terms[dom][0]]},
+                         "per_kernel": per_kernel},
+            "events_sha256_first_timed_step": digests,
             "clocks": sampler.summary(),
         }
+        if parity is not None:
+            line["parity"] = parity
         if world > 1:
-            if sh.direct:
-                line["config"]["parallelism"] = (f"spatial sharding: {world} column strips; halo records (96 B) and next-event keys pushed into the peers' "
-                                                 f"memory over NVLink by the step kernels (cudaIpc), one host sync per step, no collective on the data path")
-            else:
-                line["config"]["parallelism"] = f"spatial sharding: {world} column strips, NCCL all-gather of halo slabs (96-B records) + all-gather min"
-                hs, hr = sh.halo_counts()
-                line["halo_records_last_step_rank0"] = {"sent": hs, "received": hr}
-            line["config"]["exchange"] = "direct" if sh.direct else "nccl"
-        if not args.no_cpu_baseline:
+            line["config"]["parallelism"] = (f"spatial sharding: {world} column strips; halo records (96 B) and next-event keys "
+                                             + ("pushed into the peers' memory over NVLink by the step kernels (cudaIpc), one host sync per step, no collective on the data path"
+                                                if os.environ.get("CB200_EXCHANGE", "direct") != "nccl" else "exchanged by two NCCL all-gathers"))
+        if c4 is not None:
+            line["config4"] = c4
+        if not args.no_cpu_baseline and world == 1:
             n_sample = min(n, args.ref_sample)
-            ups, sps, ms, st = oracle_timing(lambda m: make_workload(scenes, args.workload, m, 0, 1), n_sample, 3, 1)
+            ups, sps, ms, _ = oracle_bulk_timing(make_workload(scenes, args.workload, n_sample, 0, 1), 5, 1)
             line["cpu_baseline"] = {"value": ups, "unit": UNIT, "cores": 1, "kind": "port", "pair_solves_per_s": sps,
-                                    "sample": f"{n_sample} hitboxes of the same scene density, 3 bulk-equivalent steps (ascending set_hitbox_vel loop), single thread",
+                                    "sample": f"{n_sample} hitboxes of the same scene density, 5 bulk-equivalent steps (ascending set_hitbox_vel loop), single thread; "
+                                              f"`--impl reference` runs the full {n}-hitbox scene",
                                     "host_cores_available": os.cpu_count()}
+        if not args.no_collider_rows and world == 1:
+            line.update(collider_rows(cb, scenes, local_rank))
         print(json.dumps(line), file=out)
     if world > 1:
         dist.barrier()

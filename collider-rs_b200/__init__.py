@@ -91,13 +91,13 @@ EXPORTS = (
     "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
     "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_shard_set_slab", "cb200_set_stream", "cb200_shard_begin", "cb200_shard_finish",
     "cb200_shard_result", "cb200_set_resort_period", "cb200_resort_count", "cb200_event_sort_fallbacks", "cb200_set_stage_timing",
-    "cb200_shard_p2p_export", "cb200_shard_p2p_import", "cb200_shard_step", "cb200_shard_global_next", "cb200_shard_local_key",
+    "cb200_shard_p2p_export", "cb200_shard_p2p_import", "cb200_shard_step", "cb200_shard_global_next", "cb200_shard_local_key", "cb200_shard_abort",
     "cb200_collider_new", "cb200_collider_free", "cb200_collider_last_error", "cb200_collider_set_can_interact", "cb200_collider_time",
     "cb200_collider_next_time", "cb200_collider_set_time", "cb200_collider_next", "cb200_collider_get_hitbox", "cb200_collider_add_hitbox",
     "cb200_collider_set_hitbox_vel", "cb200_collider_remove_hitbox", "cb200_collider_get_overlaps", "cb200_collider_is_overlapping",
     "cb200_collider_query_overlaps", "cb200_collider_bulk_update", "cb200_collider_len", "cb200_collider_set_rebin_threshold",
     "cb200_collider_rebin_count", "cb200_collider_engine", "cb200_collider_add_hitboxes", "cb200_collider_prefetch_count",
-    "cb200_collider_hitbox_cache_hits",
+    "cb200_collider_hitbox_cache_hits", "cb200_collider_run_halving_loop",
 )
 
 _lib = None
@@ -151,6 +151,7 @@ def load_library() -> C.CDLL:
     L.cb200_shard_global_next.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(i32)]
     L.cb200_shard_local_key.argtypes = [vp]
     L.cb200_shard_local_key.restype = vp
+    L.cb200_shard_abort.argtypes = [vp]
     L.cb200_set_resort_period.argtypes = [vp, i32]
     L.cb200_resort_count.argtypes = [vp]
     L.cb200_resort_count.restype = u64
@@ -332,6 +333,9 @@ class Engine:
         t, tie, ok = C.c_uint64(), C.c_uint64(), C.c_int()
         self._check(self._L.cb200_shard_global_next(self._h, C.byref(t), C.byref(tie), C.byref(ok)))
         return t.value, tie.value, bool(ok.value)
+
+    def shard_abort(self):
+        self._L.cb200_shard_abort(self._h)
 
     def shard_local_key_ptr(self) -> int:
         return int(self._L.cb200_shard_local_key(self._h))

@@ -139,6 +139,7 @@ def _bind(L):
     L.cb200_collider_prefetch_count.restype = u64
     L.cb200_collider_hitbox_cache_hits.argtypes = [vp]
     L.cb200_collider_hitbox_cache_hits.restype = u64
+    L.cb200_collider_run_halving_loop.argtypes = [vp, C.c_double, C.POINTER(u64), C.POINTER(u64)]
     L.cb200_collider_engine.argtypes = [vp]
     L.cb200_collider_engine.restype = vp
     L._collider_bound = True
@@ -294,6 +295,12 @@ class Collider:
             rc = self._L.cb200_collider_bulk_update(self._h, C.byref(v), end_time, C.byref(res))
         self._check(rc)
         return res
+
+    def halving_loop(self, t_end: float):
+        """README.md:66-80 loop up to t_end with velocity halving on Collide, run natively in the library; (events, collides)."""
+        ne, nc = C.c_uint64(), C.c_uint64()
+        self._check(self._L.cb200_collider_run_halving_loop(self._h, t_end, C.byref(ne), C.byref(nc)))
+        return ne.value, nc.value
 
     def set_rebin_threshold(self, rows: int):
         self._check(self._L.cb200_collider_set_rebin_threshold(self._h, rows))

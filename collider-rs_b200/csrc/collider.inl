@@ -1105,6 +1105,38 @@ int cb200_collider_query_overlaps(cb200_collider* c, uint32_t kind, double pos_x
     return cfail(c, CB200_E_STATE, "query buffer failed to converge");
 }
 
+// Benchmark driver: the user loop of the reference's README (README.md:66-80) run natively over this API — advance to the
+// next event, pop it, and on Collide halve the velocity of both hitboxes (get_hitbox + set_hitbox_vel, end_time kept) —
+// so that bench.py times the Collider API itself rather than Python's call overhead.  The oracle has the same loop
+// (orc_halving_loop).  *n_events / *n_collides: user-visible events and the Collide events among them.
+int cb200_collider_run_halving_loop(cb200_collider* c, double t_end, uint64_t* n_events, uint64_t* n_collides) {
+    if (!c) return CB200_E_ARG;
+    uint64_t n_ev = 0, n_col = 0;
+    int rc = CB200_OK;
+    while (c->time < t_end) {
+        double nt;
+        if ((rc = cb200_collider_next_time(c, &nt)) != CB200_OK) break;
+        if ((rc = cb200_collider_set_time(c, nt < t_end ? nt : t_end)) != CB200_OK) break;
+        int has = 0;
+        uint32_t kind = 0;
+        uint64_t ids[2] = {0, 0};
+        if ((rc = cb200_collider_next(c, &has, &kind, &ids[0], &ids[1])) != CB200_OK) break;
+        if (!has) continue;
+        ++n_ev;
+        if (kind != CB200_EV_COLLIDE) continue;
+        ++n_col;
+        for (int k = 0; k < 2 && rc == CB200_OK; ++k) {
+            cb200_hitbox hb;
+            if ((rc = cb200_collider_get_hitbox(c, ids[k], &hb)) != CB200_OK) break;
+            rc = cb200_collider_set_hitbox_vel(c, ids[k], hb.vel_x * 0.5, hb.vel_y * 0.5, hb.rsz_x, hb.rsz_y, hb.end_time);
+        }
+        if (rc != CB200_OK) break;
+    }
+    if (n_events) *n_events = n_ev;
+    if (n_collides) *n_collides = n_col;
+    return rc;
+}
+
 // The bulk entry point on the Collider: for id ascending, internal_update_hitbox(id, Some(vel_id)) at the current time
 // (SURVEY.md 8b).  `vel` arrays are in ascending-id order.
 int cb200_collider_bulk_update(cb200_collider* c, const cb200_vel_view* vel, double end_time, cb200_step_result* out) {

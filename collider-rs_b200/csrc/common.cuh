@@ -15,7 +15,7 @@ namespace cb200 {
 // ---- error flags (mirrors include/collider_b200.h CB200_F_*) ----
 constexpr uint32_t kFInvalidTime = 1u << 0, kFEndTime = 1u << 1, kFCircleResize = 1u << 2, kFTooSmall = 1u << 3,
                    kFEmptyRect = 1u << 4, kFRectSpan = 1u << 5, kFNan = 1u << 6, kFHighTime = 1u << 7,
-                   kFIdNotFound = 1u << 8;
+                   kFIdNotFound = 1u << 8, kFPeerLost = 1u << 9;
 
 constexpr uint32_t kGroupNone = 0xFFFFFFFFu;
 constexpr uint32_t kCollideBit = 0x80000000u;  // in PairEvent.b_kind: 1 = Collide, 0 = Separate
@@ -181,6 +181,7 @@ struct MinKey {
 };
 __device__ __forceinline__ bool key_less(const MinKey& a, const MinKey& b) { return a.t < b.t || (a.t == b.t && a.tie < b.tie); }
 __host__ __device__ __forceinline__ uint64_t time_key(double t) {
+    t = t + 0.0;  // -0.0 -> +0.0 (round-to-nearest; every other value unchanged): the two zeros are one time in the reference's order (N64's Ord is partial_cmp, float.rs:36-42)
 #if defined(__CUDA_ARCH__)
     const uint64_t b = (uint64_t)__double_as_longlong(t);
 #else

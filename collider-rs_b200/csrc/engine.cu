@@ -128,6 +128,7 @@ struct cb200_ctx {
     int p2p_parity = 0;
     GlobalKey* h_gkey = nullptr;  // pinned, mapped
     GlobalKey* d_gkey = nullptr;
+    unsigned long long peer_timeout_ns = 20ull * 1000000000ull;  // bound of every wait for a peer (CB200_PEER_TIMEOUT_MS)
     int shard_phase = 0;     // 0 idle, 1 after shard_begin, 2 after shard_finish (result pending)
     double shard_T = 0;
 
@@ -232,6 +233,7 @@ std::string flags_message(uint32_t f) {
     if (f & kFNan) add("unexpected NaN");
     if (f & kFHighTime) add("requires time < 1e50");
     if (f & kFIdNotFound) add("hitbox id not found");
+    if (f & kFPeerLost) add("a peer rank did not deliver its halo records or key (aborted or timed out)");
     return m;
 }
 
@@ -327,6 +329,7 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaHostAlloc(&c->h_dyn, sizeof(StepDyn), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if (const char* g = getenv("CB200_GRAPH")) c->use_graph = g[0] != '0';
     if (const char* rp = getenv("CB200_RESORT_PERIOD")) c->resort_period = std::max(0, atoi(rp));
+    if (const char* pt = getenv("CB200_PEER_TIMEOUT_MS")) c->peer_timeout_ns = (unsigned long long)std::max(1, atoi(pt)) * 1000000ull;
     if (const char* sa = getenv("CB200_STAGE_A")) c->stage_a_tma = strcmp(sa, "tma") == 0;
     if (const char* w = getenv("CB200_LD256")) c->ld256 = w[0] != '0';
     if (const char* w = getenv("CB200_SOLVE")) c->solve_two_phase = w[0] == '2';
@@ -686,7 +689,8 @@ static int reserve_step_buffers(cb200_ctx* ctx) {
     CU(ctx->work_count.reserve(kWorkLists + 2));
     CU(reserve_dense(ctx));
     if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
-    CU(ctx->partial.reserve((size_t)ctx->sm_count * 24));
+    CU(ctx->partial.reserve((size_t)ctx->sm_count * (32 + 32 + 32 + 8)));  // worst case of the CB200_PER_SM_* overrides
+    for (auto& b : ctx->nvel) CU(b.reserve(std::max<uint32_t>(n, 1)));       // (stage_vel must not allocate while a peer waits in a kernel)
     if (n >= 2) {
         for (int k = 0; k < 11; ++k) CU(ctx->col_alt[k].reserve(ctx->col[k].cap));
         CU(ctx->kind_alt.reserve(ctx->kind.cap)); CU(ctx->reit_alt.reserve(ctx->reit.cap)); CU(ctx->group_alt.reserve(ctx->group.cap));
@@ -985,14 +989,14 @@ static int enqueue_direct_step(cb200_ctx* ctx, double time, const double* const*
     if (rc != CB200_OK) return rc;
     if (world > 1) {
         k_push_halo<<<world - 1, 1024, 0, ctx->stream>>>(ctx->send.p, ctx->peers, world, rank, ctx->slab, ctx->p2p_parity, ctx->d_dyn);
-        k_wait_flags<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_mail->flag_halo, world, rank, ctx->d_dyn);
+        k_wait_flags<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_mail, world, rank, ctx->d_dyn, ctx->d_ctr, ctx->peer_timeout_ns);
         ctx->launches += 2;
     }
     if ((rc = enqueue_back(ctx, time, false)) != CB200_OK) return rc;
     k_push_key<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_key, ctx->d_ctr, ctx->work_count.p, (uint32_t)std::min<size_t>(ctx->work.cap / kWorkLists, 0x7fffffffu),
                                                  (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu), (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu),
                                                  ctx->peers, ctx->d_mail, world, rank, ctx->p2p_parity, ctx->d_dyn);
-    k_reduce_keys<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_mail, world, rank, ctx->p2p_parity, ctx->d_dyn, ctx->d_gkey);
+    k_reduce_keys<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->d_mail, world, rank, ctx->p2p_parity, ctx->d_dyn, ctx->d_gkey, ctx->peer_timeout_ns);
     ctx->launches += 2;
     return CB200_OK;
 }
@@ -1015,7 +1019,7 @@ static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
     for (const void* p : ptrs) mix((uint64_t)(uintptr_t)p);
     mix(ctx->entries.cap); mix(ctx->work.cap); mix(ctx->events.cap); mix((uint64_t)(uintptr_t)ctx->dense.p); mix(ctx->dense.cap); mix(ctx->dense_rank); mix(ctx->dense_lockstep ? 3 : 5); mix(ctx->stage_a_tma ? 1 : 0);
     if (ctx->sharded) {
-        mix(0x5aa5); mix((uint64_t)ctx->p2p_parity); mix(ctx->slab); mix((uint64_t)ctx->shard.world << 8 | (uint64_t)ctx->shard.rank);
+        mix(0x5aa5); mix(ctx->peer_timeout_ns); mix((uint64_t)ctx->p2p_parity); mix(ctx->slab); mix((uint64_t)ctx->shard.world << 8 | (uint64_t)ctx->shard.rank);
         const void* sp[] = {ctx->ord.p, ctx->send.p, ctx->send_count.p, ctx->vmap.p, ctx->d_mail, ctx->d_key, ctx->d_gkey};
         for (const void* q : sp) mix((uint64_t)(uintptr_t)q);
         for (int d = 0; d < ctx->shard.world; ++d) {
@@ -1206,8 +1210,14 @@ int cb200_shard_result(cb200_ctx* ctx, cb200_step_result* out) {
     ctx->shard_phase = 0;
     int rc;
     bool again = false;
-    if ((rc = complete_step(ctx, ctx->shard_T, &again)) != CB200_OK) return rc;
-    if (ctx->last.ctr.overflow_send) return fail(ctx, CB200_E_STATE, "halo slab overflow: more records leave this rank's strip than the slab holds (cb200_shard_set_slab)");
+    if ((rc = complete_step(ctx, ctx->shard_T, &again)) != CB200_OK) {
+        cb200_shard_abort(ctx);
+        return rc;
+    }
+    if (ctx->last.ctr.overflow_send) {
+        cb200_shard_abort(ctx);
+        return fail(ctx, CB200_E_STATE, "halo slab overflow: more records leave this rank's strip than the slab holds (cb200_shard_set_slab)");
+    }
     accumulate_timing(ctx, ST_PRE, true);
     for (int attempt = 0; attempt < 3 && again && !ctx->last.ctr.err_flags; ++attempt) {
         // re-run of the back half only: slot table and counters are rebuilt, the visitor table is intact
@@ -1227,7 +1237,22 @@ int cb200_shard_result(cb200_ctx* ctx, cb200_step_result* out) {
     if (again && !ctx->last.ctr.err_flags) return fail(ctx, CB200_E_STATE, "step buffers failed to converge");
     ctx->timed_steps += 1;
     ctx->timing_valid = true;
-    return fill_result(ctx, out);
+    rc = fill_result(ctx, out);
+    if (rc != CB200_OK) cb200_shard_abort(ctx);  // this rank stops stepping: do not leave the peers waiting for it
+    return rc;
+}
+
+// Tell every peer of a direct-exchange rank that this rank gives up (their pending waits end with CB200_F_PEER_LOST).
+// Called by the library when a sharded step fails; a host that catches an error of its own between steps calls it too.
+int cb200_shard_abort(cb200_ctx* ctx) {
+    if (!ctx) return CB200_E_ARG;
+    if (!ctx->p2p || ctx->shard.world < 2) return CB200_OK;
+    cudaSetDevice(ctx->device);
+    k_raise_abort<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->peers, ctx->shard.world, ctx->shard.rank);
+    ctx->launches += 1;
+    cudaStreamSynchronize(ctx->stream);
+    cudaGetLastError();
+    return CB200_OK;
 }
 
 // ---- direct exchange over peer memory --------------------------------------------------------------------
@@ -1311,7 +1336,7 @@ int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world 
         const void* fns[] = {(const void*)k_step_zero, (const void*)k_stage_a<true>, (const void*)k_stage_a_tma<true>, (const void*)k_slab_header, (const void*)k_push_halo,
                              (const void*)k_wait_flags, (const void*)k_index_visitors<true>, (const void*)k_index_visitors<false>,
                              (const void*)k_scan_slots, (const void*)k_scatter<true>, (const void*)k_enum_pairs, (const void*)k_solve<true, true>, (const void*)k_solve<true, false>, (const void*)k_solve<false, true>, (const void*)k_solve<false, false>, (const void*)k_solve2, (const void*)k_solve_dense, (const void*)k_solve_dense_lockstep,
-                             (const void*)k_push_key, (const void*)k_reduce_keys, (const void*)k_resort_count, (const void*)k_resort_rank,
+                             (const void*)k_push_key, (const void*)k_reduce_keys, (const void*)k_raise_abort, (const void*)k_resort_count, (const void*)k_resort_rank,
                              (const void*)k_resort_gather};
         for (const void* f : fns) CU(cudaFuncGetAttributes(&fa, f));
     }
@@ -1352,6 +1377,7 @@ int cb200_shard_step(cb200_ctx* ctx, double time, const cb200_vel_view* vel, dou
 int cb200_shard_global_next(cb200_ctx* ctx, uint64_t* time_key_out, uint64_t* tie_out, int* complete) {
     if (!ctx) return CB200_E_ARG;
     if (!ctx->p2p || !ctx->h_gkey || ctx->h_gkey->tag != ctx->p2p_step) return fail(ctx, CB200_E_STATE, "no direct-exchange step has completed");
+    if (ctx->h_gkey->lost) return fail(ctx, CB200_E_CONTRACT, flags_message(kFPeerLost));
     if (time_key_out) *time_key_out = ctx->h_gkey->t;
     if (tie_out) *tie_out = ctx->h_gkey->tie;
     if (complete) *complete = (int)ctx->h_gkey->complete;
@@ -1434,14 +1460,14 @@ static int sort_range(cb200_ctx* ctx, Key128* keys, Key128* tmp, uint32_t n, int
 
 // Order keys of every queued event of the last step, in keys_a (queued on the stream); range (optional, initialised by the
 // caller): min / max of their time keys.
-static int build_sort_keys(cb200_ctx* ctx, uint32_t n_pairs, uint64_t n_solitaire, BsRange* range) {
+static int build_sort_keys(cb200_ctx* ctx, uint32_t n_pairs, uint64_t n_solitaire, BsRange* range, BsRange* lab_range = nullptr) {
     CU(cudaMemsetAsync(&ctx->d_ctr->n_sort_keys, 0, 8, ctx->stream));
     const uint32_t max_blocks = (uint32_t)ctx->sm_count * 8u;
     if (ctx->n && n_solitaire)
         k_keys_solitaire<<<std::min<uint32_t>((ctx->n + kThreads - 1) / kThreads, max_blocks), kThreads, 0, ctx->stream>>>(ctx->n, ctx->reit.p, ctx->col[9].p, ctx->label.p,
-                                                                                                                     ctx->keys_a.p, ctx->d_ctr, range);
+                                                                                                                     ctx->keys_a.p, ctx->d_ctr, range, lab_range);
     if (n_pairs)
-        k_keys_pairs<<<std::min<uint32_t>((n_pairs + kThreads - 1) / kThreads, max_blocks), kThreads, 0, ctx->stream>>>(n_pairs, ctx->events.p, ctx->keys_a.p, n_solitaire, range);
+        k_keys_pairs<<<std::min<uint32_t>((n_pairs + kThreads - 1) / kThreads, max_blocks), kThreads, 0, ctx->stream>>>(n_pairs, ctx->events.p, ctx->keys_a.p, n_solitaire, range, lab_range);
     ctx->launches += (ctx->n && n_solitaire ? 1 : 0) + (n_pairs ? 1 : 0);
     return CB200_OK;
 }
@@ -1455,23 +1481,22 @@ static int enqueue_sort_oneshot(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, u
     const uint32_t nb = 1u << log2_buckets, n_buckets = 2 * nb;  // region A (ties at the first time) + region B (by time)
     const uint32_t scan_blocks = (n_buckets + kBs2Chunk - 1) / kBs2Chunk;
     DevBuf<uint32_t>& tab = ctx->bs_tab[0];
-    CU(tab.reserve(2 * (size_t)n_buckets + 2 + 8 + scan_blocks));
+    CU(tab.reserve(2 * (size_t)n_buckets + 2 + 12 + scan_blocks));
     uint32_t* count = tab.p;                   // [n_buckets + 1] then: offsets
     uint32_t* cursor = tab.p + n_buckets + 4;  // [n_buckets] (16-byte aligned like count)
-    BsRange* range = reinterpret_cast<BsRange*>(tab.p + 2 * (size_t)n_buckets + 4);
-    uint32_t* block_total = tab.p + 2 * (size_t)n_buckets + 8;
-    const BsRange init{~0ull, 0ull};
+    BsRange* range = reinterpret_cast<BsRange*>(tab.p + 2 * (size_t)n_buckets + 4);  // [2]: time keys, first labels
+    uint32_t* block_total = tab.p + 2 * (size_t)n_buckets + 12;
+    static const BsRange init[2] = {{~0ull, 0ull}, {~0ull, 0ull}};
     CU(cudaMemsetAsync(count, 0, ((size_t)n_buckets + 1) * 4, ctx->stream));
-    CU(cudaMemcpyAsync(range, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = build_sort_keys(ctx, n_pairs, n_solitaire, range);
+    CU(cudaMemcpyAsync(range, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = build_sort_keys(ctx, n_pairs, n_solitaire, range, range + 1);
     if (rc != CB200_OK) return rc;
     const uint32_t blocks = (nt + kThreads - 1) / kThreads;
-    const uint32_t label_bound = std::max<uint32_t>(1u, ctx->sharded ? (uint32_t)std::min<uint64_t>(ctx->id_space, 0x7fffffffull) : ctx->n);
     Key128 *keys = ctx->keys_a.p, *tmp = ctx->keys_b.p;
-    k_bs2_count<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, range, log2_buckets, label_bound, count);
+    k_bs2_count<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, range, log2_buckets, count);
     k_bs2_scan_local<<<scan_blocks, 256, 0, ctx->stream>>>(count, n_buckets, cursor, block_total);
     k_bs2_scan_add<<<scan_blocks, 256, 0, ctx->stream>>>(count, n_buckets, cursor, block_total, ctx->d_sort_big);
-    k_bs2_scatter<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, range, log2_buckets, label_bound, cursor, tmp);
+    k_bs2_scatter<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, range, log2_buckets, cursor, tmp);
     k_bs_local<<<std::min<uint32_t>((n_buckets + 7) / 8, (uint32_t)ctx->sm_count * 8u), 256, 0, ctx->stream>>>(tmp, count, n_buckets, keys);
     k_decode_events<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p, ctx->last_add_mode ? 1 : 0);
     ctx->launches += 6;

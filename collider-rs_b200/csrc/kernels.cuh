@@ -467,6 +467,7 @@ struct Mailbox {
     unsigned long long flag_halo[kMaxWorld];
     unsigned long long flag_key[kMaxWorld];
     unsigned long long keys[2][kMaxWorld][4];  // [parity][rank] = {time key, tie, complete, -}
+    unsigned long long abort;                  // raised by a peer that gave up on its step (k_raise_abort): waiters stop spinning
 };
 struct PeerTable {
     HbRec* recv[kMaxWorld];     // peer d's receive area for parity 0, slot 0 (parity 1 follows world * slab records later)
@@ -490,11 +491,32 @@ __global__ void __launch_bounds__(1024) k_push_halo(const HbRec* __restrict__ se
         __threadfence_system();
     }
 }
-__global__ void k_wait_flags(const unsigned long long* flags, int world, int rank, const StepDyn* dyn) {
+// Waiting for a peer is bounded: a rank that stopped stepping (an error on its side, a Python exception, a crashed process)
+// must not leave its peers inside a kernel for ever.  The wait ends when the flag arrives, when any peer raised this rank's
+// abort word, or after timeout_ns of %globaltimer — the last two set kFPeerLost in the step's error flags, which the host
+// reports as a failed step.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long tag, const Mailbox* own, unsigned long long timeout_ns) {
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
+    while (*reinterpret_cast<const volatile unsigned long long*>(flag) < tag) {
+        __nanosleep(100);
+        if ((++spins & 63u) == 0u) {
+            if (*reinterpret_cast<const volatile unsigned long long*>(&own->abort) != 0ull) return false;
+            if (global_timer_ns() - t0 > timeout_ns) return false;
+        }
+    }
+    return true;
+}
+__global__ void k_wait_flags(const Mailbox* own, int world, int rank, const StepDyn* dyn, Counters* ctr, unsigned long long timeout_ns) {
     const unsigned long long tag = dyn->tag;
     const int d = threadIdx.x;
     if (d >= world || d == rank) return;
-    while (*reinterpret_cast<const volatile unsigned long long*>(flags + d) < tag) __nanosleep(100);
+    if (!wait_flag(&own->flag_halo[d], tag, own, timeout_ns)) report_error(ctr, kFPeerLost, (uint64_t)d);
     __threadfence_system();
 }
 __global__ void k_push_key(const MinKey* __restrict__ local_key, const Counters* ctr, const uint32_t* work_count, uint32_t seg_cap, uint32_t cap_entries,
@@ -519,20 +541,25 @@ __global__ void k_push_key(const MinKey* __restrict__ local_key, const Counters*
     }
 }
 struct GlobalKey {
-    unsigned long long t, tie, complete, tag;
+    unsigned long long t, tie, complete, tag, lost;  // lost: a peer never delivered its key (timeout / abort)
 };
-__global__ void k_reduce_keys(const Mailbox* own, int world, int rank, int parity, const StepDyn* dyn, GlobalKey* out /* mapped host */) {
+__global__ void k_reduce_keys(const Mailbox* own, int world, int rank, int parity, const StepDyn* dyn, GlobalKey* out /* mapped host */,
+                              unsigned long long timeout_ns) {
     __shared__ unsigned long long s_t[kMaxWorld], s_tie[kMaxWorld], s_ok[kMaxWorld];
+    __shared__ unsigned int s_lost;
     const unsigned long long tag = dyn->tag;
     const int d = threadIdx.x;
+    if (d == 0) s_lost = 0u;
+    __syncthreads();
     if (d < world) {
-        if (d != rank)
-            while (*reinterpret_cast<const volatile unsigned long long*>(&own->flag_key[d]) < tag) __nanosleep(100);
+        bool arrived = true;
+        if (d != rank) arrived = wait_flag(&own->flag_key[d], tag, own, timeout_ns);
         __threadfence_system();
         const volatile unsigned long long* row = own->keys[parity][d];
-        s_t[d] = row[0];
-        s_tie[d] = row[1];
-        s_ok[d] = row[2];
+        s_t[d] = arrived ? row[0] : kKeyMax;
+        s_tie[d] = arrived ? row[1] : kKeyMax;
+        s_ok[d] = arrived ? row[2] : 0ull;
+        if (!arrived) atomicOr(&s_lost, 1u);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -546,9 +573,17 @@ __global__ void k_reduce_keys(const Mailbox* own, int world, int rank, int parit
         out->t = best.t;
         out->tie = best.tie;
         out->complete = ok;
+        out->lost = s_lost;
         out->tag = tag;
         __threadfence_system();
     }
+}
+// A rank that fails its step tells every peer: their waits end with kFPeerLost instead of spinning until the timeout.
+__global__ void k_raise_abort(PeerTable peers, int world, int rank) {
+    const int d = threadIdx.x;
+    if (d >= world || d == rank) return;
+    *reinterpret_cast<volatile unsigned long long*>(&peers.mail[d]->abort) = 1ull;
+    __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@ struct BsRange {
 };
 __device__ __forceinline__ void block_range_reduce(unsigned long long lo, unsigned long long hi, BsRange* range) {
     __shared__ unsigned long long s_lo[32], s_hi[32];
+    __syncthreads();  // (called twice per kernel: time range, label range)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -46,28 +47,35 @@ __device__ __forceinline__ void block_range_reduce(unsigned long long lo, unsign
     }
 }
 __global__ void k_keys_solitaire(uint32_t n, const uint8_t* __restrict__ reit, const double* __restrict__ end, const uint32_t* __restrict__ gid,
-                                 Key128* keys, Counters* ctr, BsRange* range) {
-    unsigned long long lo = ~0ull, hi = 0ull;
+                                 Key128* keys, Counters* ctr, BsRange* range, BsRange* lab_range) {
+    unsigned long long lo = ~0ull, hi = 0ull, llo = ~0ull, lhi = 0ull;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (!reit[i]) continue;
         const unsigned long long pos = warp_agg_claim(&ctr->n_sort_keys);
         const unsigned long long t = time_key(end[i]);
-        keys[pos] = Key128{(unsigned long long)(gid ? gid[i] : i), t};
+        const unsigned long long label = (unsigned long long)(gid ? gid[i] : i);
+        keys[pos] = Key128{label, t};
         lo = min(lo, t);
         hi = max(hi, t);
+        llo = min(llo, label);
+        lhi = max(lhi, label);
     }
     if (range) block_range_reduce(lo, hi, range);
+    if (lab_range) block_range_reduce(llo, lhi, lab_range);
 }
-__global__ void k_keys_pairs(uint32_t n_ev, const PairEvent* __restrict__ ev, Key128* keys, unsigned long long base, BsRange* range) {
-    unsigned long long lo = ~0ull, hi = 0ull;
+__global__ void k_keys_pairs(uint32_t n_ev, const PairEvent* __restrict__ ev, Key128* keys, unsigned long long base, BsRange* range, BsRange* lab_range) {
+    unsigned long long lo = ~0ull, hi = 0ull, llo = ~0ull, lhi = 0ull;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ev; i += gridDim.x * blockDim.x) {
         const PairEvent e = ev[i];
         const unsigned long long t = time_key(e.time);
         keys[base + i] = Key128{kPairClass | ((unsigned long long)e.a << 32) | e.b_kind, t};
         lo = min(lo, t);
         hi = max(hi, t);
+        llo = min(llo, (unsigned long long)e.a);
+        lhi = max(lhi, (unsigned long long)e.a);
     }
     if (range) block_range_reduce(lo, hi, range);
+    if (lab_range) block_range_reduce(llo, lhi, lab_range);
 }
 __global__ void k_key_diff(uint32_t n, const Key128* __restrict__ keys, Counters* ctr) {
     const Key128 k0 = keys[0];
@@ -363,27 +371,30 @@ __global__ void __launch_bounds__(256) k_bs_local(const Key128* __restrict__ in,
 // Both cuts are monotone in the (time, tie) order, so bucket order == key order and the warp rank sort finishes the job.
 // The host looks at `big` only after everything (decode and the copy to the host included) has been queued; a bucket that
 // came out too large for a warp sends it to the recursive path above.
-__device__ __forceinline__ uint32_t bs2_bucket(const Key128& k, const BsRange& r, int log2_buckets, uint32_t label_bound) {
+// The labels are cut over the range [lab.lo, lab.hi] the step's keys actually carry (reduced by the key kernels next to the
+// time range): a sharded rank's labels (= ids) cover about 1 / world of the id space, and cutting over the whole id space
+// left most of region A's buckets empty and the rest oversized (every fetch then fell back to the recursive sort).
+__device__ __forceinline__ uint32_t bs2_bucket(const Key128& k, const BsRange& r, int log2_buckets, const BsRange& lab) {
     const uint32_t nb = 1u << log2_buckets;
     if (k.hi == r.lo) {
         const uint32_t half = nb >> 1;
         const bool pair = (k.lo & kPairClass) != 0;
-        uint32_t label = pair ? (uint32_t)((k.lo >> 32) & 0x7fffffffu) : (uint32_t)min(k.lo, 0xffffffffull);
-        label = min(label, label_bound - 1u);
-        return (pair ? half : 0u) + (uint32_t)(((unsigned long long)label * half) / label_bound);
+        const unsigned long long label = pair ? ((k.lo >> 32) & 0x7fffffffull) : min(k.lo, 0xffffffffull);
+        const unsigned long long bound = lab.hi - lab.lo + 1ull;                      // (lab.lo <= label <= lab.hi)
+        const unsigned long long rel = min(label - min(label, lab.lo), bound - 1ull);
+        return (pair ? half : 0u) + (uint32_t)((rel * half) / bound);
     }
     return nb + bs_bucket(k.hi, r, log2_buckets, 1);  // (r.hi > r.lo here)
 }
-__global__ void k_bs2_count(uint32_t n, const Key128* __restrict__ keys, const BsRange* r, int log2_buckets, uint32_t label_bound, uint32_t* count) {
+__global__ void k_bs2_count(uint32_t n, const Key128* __restrict__ keys, const BsRange* r /* [2]: time range, label range */, int log2_buckets, uint32_t* count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) atomicAdd(&count[bs2_bucket(keys[i], *r, log2_buckets, label_bound)], 1u);
+    if (i < n) atomicAdd(&count[bs2_bucket(keys[i], r[0], log2_buckets, r[1])], 1u);
 }
-__global__ void k_bs2_scatter(uint32_t n, const Key128* __restrict__ keys, const BsRange* r, int log2_buckets, uint32_t label_bound, uint32_t* cursor,
-                              Key128* out) {
+__global__ void k_bs2_scatter(uint32_t n, const Key128* __restrict__ keys, const BsRange* r, int log2_buckets, uint32_t* cursor, Key128* out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Key128 k = keys[i];
-    out[atomicAdd(&cursor[bs2_bucket(k, *r, log2_buckets, label_bound)], 1u)] = k;
+    out[atomicAdd(&cursor[bs2_bucket(k, r[0], log2_buckets, r[1])], 1u)] = k;
 }
 
 // The bucket scan of the one-shot path, over all SMs (one block walking 2 x 32768 buckets took 81 us — its strided 4-byte

@@ -168,8 +168,12 @@ class ShardedEngine:
         import torch
 
         if self.direct:
-            self.eng.shard_step(time, end_time=end_time, **vel)
-            res = self.eng.shard_result()  # the one host synchronisation of the step
+            try:
+                self.eng.shard_step(time, end_time=end_time, **vel)
+                res = self.eng.shard_result()  # the one host synchronisation of the step
+            except BaseException:
+                self.eng.shard_abort()  # this rank stops stepping: its peers' waits end with CB200_F_PEER_LOST, not a hang
+                raise
             tkey, tie, complete = self.eng.shard_global_next()
             if not complete:  # some rank re-ran the step with larger buffers: every rank sees this and repeats the key exchange
                 keys = self.ex.all_gather_keys(wrap(self.eng.shard_local_key_ptr(), 16, self.device).view(torch.int64))
@@ -185,8 +189,10 @@ class ShardedEngine:
         _, send, recv = self._bufs
         self.ex.all_gather_slabs(recv, send)
         key_ptr = self.eng.shard_finish()
+        # shard_result may re-run the back half after growing a buffer that overflowed, and the re-run rewrites the local
+        # key (the first run dropped candidate pairs): the keys are gathered only after it, from the final value
+        res = self.eng.shard_result()
         keys = self.ex.all_gather_keys(wrap(key_ptr, 16, self.device).view(torch.int64))
-        res = self.eng.shard_result()  # the one host synchronisation of the step
         self.local_result = res
         self.next_key = min_key(keys.tolist())
         self.next_event = decode_key(*self.next_key)

@@ -46,7 +46,8 @@ enum {
     CB200_F_RECT_SPAN = 1u << 5,      /* index rect wider than the device grid period (engine limit, not a reference panic) */
     CB200_F_NAN = 1u << 6,            /* "unexpected NaN"                                         float.rs:31 */
     CB200_F_HIGH_TIME = 1u << 7,      /* "requires time < 1e50"                                   core/mod.rs:142 */
-    CB200_F_ID_NOT_FOUND = 1u << 8    /* "hitbox id {} not found"                                 collider.rs:235,260,283,294 */
+    CB200_F_ID_NOT_FOUND = 1u << 8,   /* "hitbox id {} not found"                                 collider.rs:235,260,283,294 */
+    CB200_F_PEER_LOST = 1u << 9       /* sharded, direct exchange: a peer rank aborted or did not arrive within the timeout (engine condition) */
 };
 
 #define CB200_KIND_CIRCLE 0 /* ShapeKind::Circle, geom/shape/mod.rs:27-31 */
@@ -229,6 +230,11 @@ int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world 
 int cb200_shard_step(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time);
 int cb200_shard_global_next(cb200_ctx* ctx, uint64_t* time_key, uint64_t* tie, int* complete);
 void* cb200_shard_local_key(cb200_ctx* ctx); /* device address of this rank's (time key, tie): input of a repeated key all-gather */
+/* Every wait of a step kernel for a peer is bounded (environment CB200_PEER_TIMEOUT_MS, default 20000) and ends early when a
+ * peer raises this rank's abort word; either way the step fails with CB200_F_PEER_LOST instead of hanging.  The library
+ * raises the abort word of all peers when a sharded step of this rank fails; a host that stops stepping for a reason of
+ * its own (an exception between steps) calls cb200_shard_abort so that its peers return at once. */
+int cb200_shard_abort(cb200_ctx* ctx);
 
 /* Events queued by the last bulk step, sorted by the canonical order (time, class, hi id, kind, lo id)
  * (events.rs:60-68 with SURVEY.md §8c tie-break).  Copies events [offset, offset+cap) into buf. */
@@ -307,6 +313,9 @@ int cb200_collider_query_overlaps(cb200_collider* c, uint32_t kind, double pos_x
 /* The bulk advance/rebuild entry point on a Collider: at the current time, for id ascending,
  * internal_update_hitbox(id, Some(vel_id)) — one device pass (cb200_bulk_update).  `vel` arrays are in ascending-id order. */
 int cb200_collider_bulk_update(cb200_collider* c, const cb200_vel_view* vel, double end_time, cb200_step_result* out);
+/* Benchmark driver: the user loop of the reference's README (README.md:66-80) up to t_end, run natively over the calls above
+ * with the Collide handler halving both hitboxes' velocities (get_hitbox + set_hitbox_vel) — BASELINE config 1/2's loop. */
+int cb200_collider_run_halving_loop(cb200_collider* c, double t_end, uint64_t* n_events, uint64_t* n_collides);
 uint64_t cb200_collider_len(const cb200_collider* c);
 /* Rows changed since the grid was last rebuilt are kept on a dirty list that every single-hitbox operation scans; the
  * grid is rebuilt on the device (count / scan / scatter, no solve) when the list exceeds this many rows.  Default 4096. */

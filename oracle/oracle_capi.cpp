@@ -301,6 +301,36 @@ void orc_separate_time_batch(uint64_t n, const double* a, const uint8_t* ka, con
     }
 }
 // returns 1 if Some(root)
+// Benchmark driver (bench.py cpu_baseline rows for configs 1 and 2): the user loop of README.md:66-80 run natively — advance
+// to the next event, pop it, and on Collide halve both hitboxes' velocities (get_hitbox + set_hitbox_vel, end_time kept).
+// out = {user-visible events, Collide events among them}.  Returns -1 on a panic.
+int orc_halving_loop(void* hp, double t_end, uint64_t* out) {
+    auto* h = (Handle*)hp;
+    uint64_t n_ev = 0, n_col = 0;
+    int rc = guard(h, [&] {
+        Collider& c = *h->c;
+        while (c.time() < t_end) {
+            const double nt = c.next_time();
+            c.set_time(nt < t_end ? nt : t_end);
+            if (auto ev = c.next()) {
+                ++n_ev;
+                if ((int)ev->kind == 1) {
+                    ++n_col;
+                    for (HbId id : {ev->id_1, ev->id_2}) {
+                        Hitbox hb = c.get_hitbox(id);
+                        hb.vel.value.x *= 0.5;
+                        hb.vel.value.y *= 0.5;
+                        c.set_hitbox_vel(id, hb.vel);
+                    }
+                }
+            }
+        }
+    });
+    out[0] = n_ev;
+    out[1] = n_col;
+    return rc;
+}
+
 int orc_quad_root_ascending(double a, double b, double c, double* root) { return quad_root_ascending(a, b, c, root) ? 1 : 0; }
 // IndexRect iteration: fills xs/ys (cap entries), returns count or -1 on panic
 int64_t orc_index_rect_iter(int32_t sx, int32_t sy, int32_t ex, int32_t ey, int32_t* xs, int32_t* ys, uint64_t cap) {

@@ -68,6 +68,7 @@ def lib():
         L.orc_len.argtypes = [C.c_void_p]
         L.orc_bulk_update.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_double, C.c_int]
         L.orc_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_halving_loop.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.orc_bulk_candidates.restype = C.c_int64
         L.orc_bulk_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_dump_events.restype = C.c_int64
@@ -321,6 +322,12 @@ class Collider:
         arrs = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (vx, vy, rw, rh, end_time_arr)]
         ptrs = [None if a is None else _p(a) for a in arrs]
         self._check(self._L.orc_bulk_update(self._h, *ptrs, float(end_time), 1 if record_candidates else 0))
+
+    def halving_loop(self, t_end: float):
+        """README.md:66-80 loop up to t_end with velocity halving on Collide, run natively; (events, collides)."""
+        out = np.zeros(2, dtype=np.uint64)
+        self._check(self._L.orc_halving_loop(self._h, float(t_end), _p(out)))
+        return int(out[0]), int(out[1])
 
     def stats(self, reset=False):
         out = np.zeros(4, dtype=np.uint64)

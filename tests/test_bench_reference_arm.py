@@ -1,4 +1,5 @@
-"""bench.py --impl reference runs on the CPU only (the oracle on the host's threads): its JSON line must carry the contract's keys."""
+"""bench.py --impl reference runs on the CPU only (ONE single-threaded oracle collider on the config's scene, like the
+reference): its JSON line must carry the contract's keys and the same `config` the GPU arm prints."""
 import json
 import os
 import subprocess
@@ -8,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--ref-sample", "20000", "--ref-threads", "2"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--n", "20000", "--no-all-threads"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
@@ -16,7 +17,8 @@ def test_reference_arm_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "hitbox updates/s"
     assert d["value"] > 0 and d["steps"] == 2 and d["dtype"] == "f64" and d["data"] == "synthetic"
-    assert d["cpu_baseline"]["cores"] == 2 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert "ONE single-threaded collider" in d["cpu_baseline"]["sample"] and d["config"]["hitboxes_per_gpu"] == 20000
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 
