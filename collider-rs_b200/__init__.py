@@ -91,7 +91,7 @@ EXPORTS = (
     "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
     "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_shard_set_slab", "cb200_set_stream", "cb200_shard_begin", "cb200_shard_finish",
     "cb200_shard_result", "cb200_set_resort_period", "cb200_resort_count", "cb200_event_sort_fallbacks", "cb200_set_stage_timing",
-    "cb200_shard_p2p_export", "cb200_shard_p2p_import", "cb200_shard_step", "cb200_shard_global_next", "cb200_shard_local_key", "cb200_shard_abort",
+    "cb200_shard_p2p_export", "cb200_shard_p2p_import", "cb200_shard_step", "cb200_shard_global_next", "cb200_shard_local_key", "cb200_shard_abort", "cb200_last_step_path", "cb200_tile_fallbacks", "cb200_get_tile",
     "cb200_collider_new", "cb200_collider_free", "cb200_collider_last_error", "cb200_collider_set_can_interact", "cb200_collider_time",
     "cb200_collider_next_time", "cb200_collider_set_time", "cb200_collider_next", "cb200_collider_get_hitbox", "cb200_collider_add_hitbox",
     "cb200_collider_set_hitbox_vel", "cb200_collider_remove_hitbox", "cb200_collider_get_overlaps", "cb200_collider_is_overlapping",
@@ -152,6 +152,10 @@ def load_library() -> C.CDLL:
     L.cb200_shard_local_key.argtypes = [vp]
     L.cb200_shard_local_key.restype = vp
     L.cb200_shard_abort.argtypes = [vp]
+    L.cb200_last_step_path.argtypes = [vp]
+    L.cb200_tile_fallbacks.argtypes = [vp]
+    L.cb200_tile_fallbacks.restype = u64
+    L.cb200_get_tile.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.cb200_set_resort_period.argtypes = [vp, i32]
     L.cb200_resort_count.argtypes = [vp]
     L.cb200_resort_count.restype = u64
@@ -418,6 +422,17 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self._L.cb200_launch_count(self._h))
+
+    def last_step_path(self) -> str:
+        return {1: "tile", 0: "global"}.get(self._L.cb200_last_step_path(self._h), "none")
+
+    def tile_fallbacks(self) -> int:
+        return int(self._L.cb200_tile_fallbacks(self._h))
+
+    def get_tile(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._check(self._L.cb200_get_tile(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def set_stage_timing(self, on: bool):
         self._check(self._L.cb200_set_stage_timing(self._h, 1 if on else 0))

@@ -184,9 +184,23 @@ int wait_head(cb200_collider* c) {
     return CB200_OK;
 }
 
+// A bulk step on the tile path leaves no global grid (slot table, entry array, per-row records) behind; the single-hitbox
+// operations read it, so the first of them after such a step has the engine rebuild it from the rebased table.
+int sync_grid(cb200_collider* c) {
+    cb200_ctx* x = c->ctx;
+    if (!x->have_step || !x->last_step_tile || x->global_grid_valid) return CB200_OK;
+    int rc = rebuild_global_grid(x);
+    if (rc != CB200_OK) return cfail(c, rc, x->err);
+    return CB200_OK;
+}
+
 // Rebuild the slot-sorted entry array from the current records (no rebase, no solve); empties the dirty list.
 int rebin(cb200_collider* c) {
     cb200_ctx* x = c->ctx;
+    {
+        int rc = sync_grid(c);
+        if (rc != CB200_OK) return rc;
+    }
     const uint32_t n = x->n;
     collider_geom(c);
     const uint32_t n_slots = x->geom.n_slots();
@@ -220,6 +234,8 @@ int rebin(cb200_collider* c) {
 }
 
 int maybe_rebin(cb200_collider* c) {
+    int rc = sync_grid(c);
+    if (rc != CB200_OK) return rc;
     if (c->n_dirty > c->rebin_threshold) return rebin(c);
     return CB200_OK;
 }
@@ -363,6 +379,10 @@ bool overlap_remove(std::vector<uint64_t>& v, uint64_t id) {
 // carries the old labels, so the grid is rebuilt.
 int relabel(cb200_collider* c) {
     cb200_ctx* x = c->ctx;
+    {
+        int rc = sync_grid(c);
+        if (rc != CB200_OK) return rc;
+    }
     std::vector<uint32_t> new_of_old(c->id_of_label.size(), kRowNone);
     std::vector<uint64_t> ids;
     ids.reserve(c->by_id.size());
@@ -821,6 +841,8 @@ int cb200_collider_add_hitbox(cb200_collider* c, const cb200_profile* profile, c
     }
     x->n = n_before + 1;
     x->have_state = true;
+    x->tile_ok = false;  // a row was appended: the tile tables are rebuilt by the re-sort the next bulk step starts with
+    x->need_resort = true;
     c->n_dirty = h.n_dirty;
     if (h.reit && (rc = add_event(c, h.end_time, QEvent{CB200_EV_REITERATE, id, 0})) != CB200_OK) return rc;
     std::vector<std::pair<uint64_t, OneItem>> col;
@@ -942,6 +964,7 @@ int cb200_collider_add_hitboxes(cb200_collider* c, uint64_t n, const cb200_profi
     if ((rc = set_step_dyn(x, c->time, INFINITY)) != CB200_OK) return cfail(c, rc, x->err);
     const double* nv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     x->add_mode = true;
+    x->step_is_tile = false;  // (the add-mode step runs on the global path)
     bool again = true;
     unsigned long long n_imm = 0;
     for (int attempt = 0; attempt < 5 && again; ++attempt) {
@@ -1017,6 +1040,12 @@ int cb200_collider_remove_hitbox(cb200_collider* c, uint64_t id, uint64_t* overl
     if (it == c->infos.end()) return not_found(c, id);
     cb200_ctx* x = c->ctx;
     cudaSetDevice(x->device);
+    {
+        int rc = sync_grid(c);
+        if (rc != CB200_OK) return rc;
+    }
+    x->tile_ok = false;  // rows move: the tile tables are rebuilt by the re-sort the next bulk step starts with
+    x->need_resort = true;
     clear_related(c, id, it->second);
     k_remove_row<<<1, 1, 0, x->stream>>>(table_of(c), it->second.label, c->head.d);
     x->launches += 1;

@@ -270,6 +270,9 @@ struct Counters {
     unsigned int overflow_send;        // sharded: a send buffer overflowed
     unsigned long long diff_hi, diff_lo;  // sort: OR of key differences
     unsigned long long n_sort_keys;
+    unsigned long long n_tile_pairs;   // tile path: (entry, predecessor) pairs walked in shared memory (the step result's work items)
+    unsigned int tile_fail;            // tile path: a visitor slab or a single cell exceeded its capacity -> the host repeats the step on the global path
+    unsigned int pad1;
 };
 
 __device__ __forceinline__ void report_error(Counters* ctr, uint32_t flags, uint64_t slot) {

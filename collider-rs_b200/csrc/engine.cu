@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "single.cuh"
 #include "sort.cuh"
+#include "tile.cuh"
 
 using namespace cb200;
 
@@ -134,6 +135,22 @@ struct cb200_ctx {
 
     GridGeom geom{0, 0};
     bool geom_forced = false;
+    double world_cells = 0;  // cells of the uploaded extent (choose_geom): the density the tile size is chosen from
+    // ---- tile path (tile.cuh): binning / enumeration / solve per block of cells in shared memory ----
+    bool tile_enabled = true;     // CB200_TILE=0: the global path only
+    bool tile_ok = false;         // the row-range / home tables match the current row order (written at the re-sort)
+    bool tile_suspended = false;  // a tile step exceeded a capacity: global path until the next re-sort
+    bool step_is_tile = false, last_step_tile = false;
+    bool global_grid_valid = false;  // the slot table / entry array / records describe the last step (always after a global step)
+    TileGeom tgeom{};
+    uint32_t tile_target = 160;   // home rows per tile the tile size is chosen for (CB200_TILE_TARGET)
+    uint32_t tile_cap_rec = 352, tile_cap_ent = 1408, tile_cap_q = 1024, tile_vcap = 0;  // CB200_TILE_CAP
+    uint32_t per_sm_t = 3, grid_t = 0;
+    size_t tile_smem = 0;
+    DevBuf<uint2> tile_rows;
+    DevBuf<uint32_t> home, vis_count;
+    DevBuf<HbRec> vis;
+    uint64_t tile_steps = 0, tile_fallbacks = 0;
     DevBuf<uint32_t> slots;
     DevBuf<uint32_t> chunk_base;  // start of each scan chunk's runs in the entry array
     DevBuf<CellEntry> entries;
@@ -271,6 +288,7 @@ int ilog2_ceil(uint64_t v) {
 
 // Choose the grid period from the extent of the uploaded table (host view) unless forced.
 void choose_geom(cb200_ctx* c, const cb200_state_view* v) {
+    c->world_cells = 0;
     if (c->geom_forced) return;
     double minx = INFINITY, maxx = -INFINITY, miny = INFINITY, maxy = -INFINITY;
     for (uint64_t i = 0; i < v->n; ++i) {
@@ -279,6 +297,7 @@ void choose_geom(cb200_ctx* c, const cb200_state_view* v) {
     }
     if (!(maxx >= minx)) minx = maxx = miny = maxy = 0;
     const double cx = std::min((maxx - minx) / c->cell_width + 4.0, 1e9), cy = std::min((maxy - miny) / c->cell_width + 4.0, 1e9);
+    c->world_cells = cx * cy;
     int lw = std::max(ilog2_ceil((uint64_t)cx), 6), lh = std::max(ilog2_ceil((uint64_t)cy), 6);
     // cap the table at ~4 slots per hitbox (min 2^12, max 2^26): fold the larger axis
     const int max_bits = std::min(26, std::max(12, ilog2_ceil(std::max<uint64_t>(v->n, 1) * 4)));
@@ -353,6 +372,14 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaHostAlloc(&c->h_sort_big, (1 + 2 * kBsMaxBig) * sizeof(uint32_t), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer((void**)&c->d_sort_big, c->h_sort_big, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     if (const char* so = getenv("CB200_SORT")) c->sort_oneshot = strcmp(so, "slow") != 0;
+    if (const char* v = getenv("CB200_TILE")) c->tile_enabled = v[0] != '0';
+    if (const char* v = getenv("CB200_TILE_TARGET")) c->tile_target = (uint32_t)std::max(16, std::min(2048, atoi(v)));
+    if (const char* v = getenv("CB200_TILE_CAP")) {
+        c->tile_cap_rec = (uint32_t)std::max(32, std::min(1400, atoi(v)));
+        c->tile_cap_ent = 4 * c->tile_cap_rec;
+    }
+    if (const char* v = getenv("CB200_TILE_QUEUE")) c->tile_cap_q = (uint32_t)std::max(256, std::min(8192, atoi(v)));
+    if (const char* v = getenv("CB200_PER_SM_T")) c->per_sm_t = (uint32_t)std::max(1, std::min(16, atoi(v)));
     for (auto& ev : c->ev_t)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
     *out = c;
@@ -379,6 +406,7 @@ void cb200_destroy(cb200_ctx* c) {
     c->slots.release(); c->chunk_base.release(); c->entries.release(); c->work.release(); c->work_count.release(); c->dense.release();
     c->ov_pairs.release(); c->ov_table.release(); c->ov_bits.release(); c->ov_pair_bits.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
+    c->tile_rows.release(); c->home.release(); c->vis_count.release(); c->vis.release();
     c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); for (auto& b : c->bs_tab) b.release(); c->imm_pairs.release(); if (c->d_n_imm) cudaFree(c->d_n_imm); c->ev_out.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->d_key) cudaFree(c->d_key);
@@ -636,11 +664,41 @@ static int launch_scan(cb200_ctx* ctx, bool step) {
     return CB200_OK;
 }
 
+// Tile path: the tile size for this table — about tile_target home rows per tile at the scene's mean density — and the
+// buffers that depend on it.  Called at every re-sort (the density may have changed with the table).
+static int choose_tile_geom(cb200_ctx* ctx) {
+    const GridGeom g = ctx->geom;
+    const double n_slots = (double)g.n_slots();
+    const double cells = ctx->world_cells > 0 ? std::min(n_slots, ctx->world_cells) : n_slots;
+    const double per_cell = std::max(1e-9, (double)ctx->n / cells);
+    int tj = (int)lround(log2((double)ctx->tile_target / per_cell));
+    tj = std::max(4, std::min(std::min(11, g.lw + g.lh), tj));
+    if (const char* v = getenv("CB200_TILE_LOG2")) tj = std::max(1, std::min(std::min(11, g.lw + g.lh), atoi(v)));
+    ctx->tgeom = make_tile_geom(g, tj);
+    ctx->tile_vcap = std::max<uint32_t>(64, ctx->tile_cap_rec / 2 + 16);
+    if (const char* v = getenv("CB200_TILE_VCAP")) ctx->tile_vcap = (uint32_t)std::max(1, atoi(v));
+    const uint32_t nt = ctx->tgeom.n_tiles;
+    CU(ctx->tile_rows.reserve(nt));
+    CU(ctx->home.reserve(std::max<uint32_t>(ctx->n, 1)));
+    CU(ctx->vis_count.reserve(2 * (size_t)nt));
+    CU(ctx->vis.reserve((size_t)nt * ctx->tile_vcap));
+    CU(cudaMemsetAsync(ctx->vis_count.p, 0, 2 * (size_t)nt * 4, ctx->stream));
+    ctx->tile_smem = tile_smem_bytes(ctx->tile_cap_rec, ctx->tile_cap_ent, ctx->tile_cap_q, tj);
+    CU(cudaFuncSetAttribute(k_tile_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
+    CU(cudaFuncSetAttribute(k_tile_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
+    ctx->grid_t = (uint32_t)ctx->sm_count * ctx->per_sm_t;
+    if (getenv("CB200_VERBOSE"))
+        fprintf(stderr, "[cb200] tile path: 2^%d slots per tile (%d x %d cells), %u tiles, %.2f hitboxes per cell, record cap %u, visitor cap %u, %zu B smem, %u blocks\n", tj,
+                1 << ctx->tgeom.bx, 1 << ctx->tgeom.by, nt, per_cell, ctx->tile_cap_rec, ctx->tile_vcap, ctx->tile_smem, ctx->grid_t);
+    return CB200_OK;
+}
+
 // Put the table rows into grid-slot order of their centre cells (kernels.cuh "Table order").
 static int resort_rows(cb200_ctx* ctx) {
     const uint32_t n = ctx->n;
     ctx->need_resort = false;
     ctx->steps_since_resort = 0;
+    ctx->tile_ok = false;
     if (n < 2) return CB200_OK;
     const uint32_t n_slots = ctx->geom.n_slots();
     const uint32_t blocks = (n + kThreads - 1) / kThreads;
@@ -654,6 +712,15 @@ static int resort_rows(cb200_ctx* ctx) {
     int rc = launch_scan(ctx, false);
     if (rc != CB200_OK) return rc;
     k_resort_rank<<<blocks, kThreads, 0, ctx->stream>>>(n, ctx->sort_key.p, ctx->slots.p, ctx->src_row.p);
+    if (ctx->tile_enabled && !ctx->sharded && n_slots >= 16) {
+        // tile path: the row range of every tile and the home tile of every (new) row
+        if ((rc = choose_tile_geom(ctx)) != CB200_OK) return rc;
+        k_tile_rows<<<(ctx->tgeom.n_tiles + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(ctx->tgeom.n_tiles, ctx->tgeom.tj, ctx->slots.p, ctx->chunk_base.p, ctx->tile_rows.p);
+        k_tile_home<<<blocks, kThreads, 0, ctx->stream>>>(n, ctx->tgeom.tj, ctx->src_row.p, ctx->sort_key.p, ctx->home.p);
+        ctx->launches += 2;
+        ctx->tile_ok = true;
+        ctx->tile_suspended = false;
+    }
     ResortCols rc_{};
     for (int k = 0; k < 11; ++k) {
         rc_.in[k] = ctx->col[k].p;
@@ -716,7 +783,7 @@ static int prepare_buffers(cb200_ctx* ctx) {
     ctx->grid_p = ctx->sm_count * ctx->per_sm_p;
     ctx->grid_s = ctx->sm_count * ctx->per_sm_s;
     ctx->grid_d = ctx->sm_count * ctx->per_sm_d;
-    CU(ctx->partial.reserve(ctx->grid_a + ctx->grid_s + ctx->grid_d));
+    CU(ctx->partial.reserve((size_t)ctx->sm_count * 12 + ctx->grid_s + std::max(ctx->grid_d, (uint32_t)ctx->sm_count * ctx->per_sm_t) + 8));
     // the rows of the previous step's records move with a re-sort: only between steps, never on a re-run
     if (ctx->need_resort || (ctx->resort_period > 0 && ctx->steps_since_resort >= (uint32_t)ctx->resort_period)) {
         int rc = resort_rows(ctx);
@@ -731,7 +798,7 @@ static int prepare_buffers(cb200_ctx* ctx) {
 static int set_step_dyn(cb200_ctx* ctx, double time, double end_time) {
     ctx->h_dyn->T = time;
     ctx->h_dyn->end_scalar = end_time;
-    ctx->h_dyn->tag = ctx->p2p_step;
+    ctx->h_dyn->tag = ctx->sharded ? ctx->p2p_step : ctx->tile_steps;  // (tile path: the parity of its visitor counters)
     CU(cudaMemcpyAsync(ctx->d_dyn, ctx->h_dyn, sizeof(StepDyn), cudaMemcpyHostToDevice, ctx->stream));
     return CB200_OK;
 }
@@ -810,9 +877,48 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     return CB200_OK;
 }
 
+// The arguments of the solve-stage kernels (k_solve, k_solve_dense, k_tile_solve) for the current step.
+static SolveArgs solve_args_of(cb200_ctx* ctx, const ShardGeom& sh, const VisSpace& vs) {
+    const bool use_map = ctx->sharded && ctx->n_ov;
+    CandArgs cd{};
+    cd.geom = ctx->geom;
+    cd.col_lo = sh.col_lo;
+    cd.col_hi = sh.col_hi;
+    cd.ov = OverlapSet{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, ctx->n_ov, ctx->ov_pair_bits.p, ctx->ov_pair_mask};
+    SolveArgs sv{};
+    sv.cd = cd;
+    sv.work = work_lists_of(ctx);
+    sv.ov_pairs = ctx->ov_pairs.p;
+    sv.n_ov = ctx->n_ov;
+    sv.rec = ctx->rec.p;
+    sv.dyn = ctx->d_dyn;
+    sv.padding = ctx->padding;
+    sv.events = ctx->events.p;
+    sv.cap_events = (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu);
+    sv.ctr = ctx->d_ctr;
+    sv.partial = ctx->partial.p;
+    sv.n_partial_a = ctx->grid_a;
+    sv.n_partial_dense = 0;
+    sv.result = ctx->d_res;
+    sv.local_key = ctx->d_key;
+    sv.vmap = ctx->sharded ? (use_map ? ctx->vmap.p : nullptr) : ctx->row_of.p;
+    sv.id_space = ctx->sharded ? (uint32_t)ctx->id_space : ctx->n;
+    sv.sharded = ctx->sharded ? 1 : 0;
+    sv.ids = ctx->sharded ? nullptr : ctx->ids.p;
+    sv.dbg = getenv("CB200_DBG_S") ? (uint32_t)atoi(getenv("CB200_DBG_S")) : 0u;
+    sv.add_mode = ctx->add_mode ? 1 : 0;
+    sv.imm_pairs = ctx->imm_pairs.p;
+    sv.n_imm = ctx->d_n_imm;
+    sv.cap_imm = (uint32_t)std::min<size_t>(ctx->imm_pairs.cap, 0xffffffffu);
+    sv.vs = vs;
+    sv.col_lo = sh.col_lo;
+    sv.col_hi = sh.col_hi;
+    return sv;
+}
+
 // Back half over the visitor table: (index received records,) scan, scatter, candidates, solve + min-reduce + result.
 // recount = the own records' cells must be counted again (re-run after a buffer grew).
-static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
+static int enqueue_back(cb200_ctx* ctx, double time, bool recount, bool bin_only = false) {
     const GridGeom g = ctx->geom;
     const uint32_t n_slots = g.n_slots();
     const ShardGeom sh = ctx->sharded ? ctx->shard : whole_world();
@@ -843,48 +949,22 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     }
     DBG_SYNC("k_scatter");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_CAND], ctx->stream));
-    CandArgs cd{};
-    cd.geom = g;
-    cd.col_lo = sh.col_lo;
-    cd.col_hi = sh.col_hi;
-    cd.ov = OverlapSet{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, ctx->n_ov, ctx->ov_pair_bits.p, ctx->ov_pair_mask};
     EnumArgs en{};
     en.entries = ctx->entries.p;
     en.cap_entries = (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu);
     en.work = work_lists_of(ctx);
     en.dense = dense_list_of(ctx);
     en.ctr = ctx->d_ctr;
+    if (bin_only) {
+        // (the grid alone: the debug views and the incremental API after a tile step)
+        CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
+        return CB200_OK;
+    }
     k_enum_pairs<<<ctx->grid_p, kThreads, 0, ctx->stream>>>(en);
     DBG_SYNC("k_enum_pairs");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_SOLVE], ctx->stream));
-    SolveArgs sv{};
-    sv.cd = cd;
-    sv.work = en.work;
-    sv.ov_pairs = ctx->ov_pairs.p;
-    sv.n_ov = ctx->n_ov;
-    sv.rec = ctx->rec.p;
-    sv.dyn = ctx->d_dyn;
-    sv.padding = ctx->padding;
-    sv.events = ctx->events.p;
-    sv.cap_events = (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu);
-    sv.ctr = ctx->d_ctr;
-    sv.partial = ctx->partial.p;
-    sv.n_partial_a = ctx->grid_a;
+    SolveArgs sv = solve_args_of(ctx, sh, vs);
     sv.n_partial_dense = ctx->dense_rank == kDenseOff ? 0u : ctx->grid_d;
-    sv.result = ctx->d_res;
-    sv.local_key = ctx->d_key;
-    sv.vmap = ctx->sharded ? (use_map ? ctx->vmap.p : nullptr) : ctx->row_of.p;
-    sv.id_space = ctx->sharded ? (uint32_t)ctx->id_space : ctx->n;
-    sv.sharded = ctx->sharded ? 1 : 0;
-    sv.ids = ctx->sharded ? nullptr : ctx->ids.p;
-    sv.dbg = getenv("CB200_DBG_S") ? (uint32_t)atoi(getenv("CB200_DBG_S")) : 0u;
-    sv.add_mode = ctx->add_mode ? 1 : 0;
-    sv.imm_pairs = ctx->imm_pairs.p;
-    sv.n_imm = ctx->d_n_imm;
-    sv.cap_imm = (uint32_t)std::min<size_t>(ctx->imm_pairs.cap, 0xffffffffu);
-    sv.vs = vs;
-    sv.col_lo = sh.col_lo;
-    sv.col_hi = sh.col_hi;
     if (ctx->dense_rank != kDenseOff) {
         // long slot runs (dense cells) first: their minima and counts are folded in by the last block of the kernel below
         DenseArgs da{};
@@ -910,6 +990,95 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount) {
     return CB200_OK;
 }
 
+// The whole step on the tile path (tile.cuh): counters, stage A + visitor slabs, per-tile binning / enumeration / solve in
+// shared memory, then the overlapping pairs (separate_time) and the last-block min-reduction through k_solve.
+static int enqueue_tile_step(cb200_ctx* ctx, bool do_rebase, const double* const* nv) {
+    const uint32_t n = ctx->n;
+    k_step_zero<<<1, kThreads, 0, ctx->stream>>>(nullptr, 0u, ctx->d_ctr, nullptr, ctx->work_count.p, kWorkLists + 2, 0u);
+    ctx->launches += 1;
+    DBG_SYNC("k_step_zero");
+    if (ctx->collider_dirty && n) {
+        CU(cudaMemsetAsync(ctx->collider_dirty, 0, n, ctx->stream));
+        CU(cudaMemsetAsync(ctx->collider_dirty_count, 0, 4, ctx->stream));
+    }
+    if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_STAGE_A], ctx->stream));
+    StepArgs a{};
+    a.n = n;
+    a.rebase = do_rebase ? 1 : 0;
+    a.dyn = ctx->d_dyn;
+    a.cell_width = ctx->cell_width;
+    a.padding = ctx->padding;
+    a.s = cols_of(ctx);
+    a.nvx = do_rebase ? nv[0] : nullptr; a.nvy = do_rebase ? nv[1] : nullptr;
+    a.nrw = do_rebase ? nv[2] : nullptr; a.nrh = do_rebase ? nv[3] : nullptr;
+    a.nend = do_rebase ? nv[4] : ctx->col[10].p;  // re-run: the user end_time is the stored pub_end_time
+    a.label = ctx->label.p;
+    a.ord = ctx->label.p;
+    a.rec = ctx->rec.p;
+    a.bink = ctx->bink.p;
+    a.geom = ctx->geom;
+    a.ctr = ctx->d_ctr;
+    a.partial = ctx->partial.p;
+    a.partial_base = 0;
+    a.ov_bits = ctx->ov_bits.p;
+    TileTables tt{ctx->tile_rows.p, ctx->home.p, ctx->vis_count.p, ctx->vis.p, ctx->tile_vcap, ctx->tgeom.n_tiles};
+    TileStageArgs ta{ctx->tgeom, tt, ctx->n_ov ? 1u : 0u};
+    ctx->grid_a = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, ctx->sm_count * ctx->per_sm_a));
+    k_stage_a_tile<<<ctx->grid_a, kThreads, 0, ctx->stream>>>(a, ta);
+    ctx->launches += 1;
+    DBG_SYNC("k_stage_a_tile");
+    if (ctx->stage_timing) {
+        CU(cudaEventRecord(ctx->ev_t[ST_EXCH], ctx->stream));
+        CU(cudaEventRecord(ctx->ev_t[ST_SCAN], ctx->stream));
+        CU(cudaEventRecord(ctx->ev_t[ST_SCATTER], ctx->stream));
+        CU(cudaEventRecord(ctx->ev_t[ST_CAND], ctx->stream));
+    }
+    const ShardGeom sh = whole_world();
+    const VisSpace vs{n, n, 0u, 1, 0};
+    TileSolveArgs ts{};
+    ts.sv = solve_args_of(ctx, sh, vs);
+    ts.s = a.s;
+    ts.label = ctx->label.p;
+    ts.bink = ctx->bink.p;
+    ts.tg = ctx->tgeom;
+    ts.tt = tt;
+    ts.cap_rec = ctx->tile_cap_rec;
+    ts.cap_ent = ctx->tile_cap_ent;
+    ts.cap_q = ctx->tile_cap_q;
+    ts.partial_at = ctx->grid_a + ctx->grid_s;
+    k_tile_solve<false><<<ctx->grid_t, kTileThreads, ctx->tile_smem, ctx->stream>>>(ts);
+    ctx->launches += 1;
+    DBG_SYNC("k_tile_solve");
+    if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_SOLVE], ctx->stream));
+    // the overlapping pairs (separate_time) + the min-reduction and the step result; the work lists are empty (zeroed above).
+    // NET: the tile kernel counts the pairs that pass candidate_geom, this one takes the overlapping ones among them off again
+    SolveArgs sv = ts.sv;
+    sv.n_partial_dense = ctx->grid_t;
+    k_solve<false, true><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
+    ctx->launches += 1;
+    DBG_SYNC("k_solve");
+    if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
+    CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
+    return CB200_OK;
+}
+
+// After a tile step the global grid (slot table, entry array, records) is not built.  The debug views and the incremental
+// Collider API read it: rebuild it from the rebased table (the global path's stage A without the rebase, scan, scatter).
+static int rebuild_global_grid(cb200_ctx* ctx) {
+    if (ctx->global_grid_valid) return CB200_OK;
+    const double* nv[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    CU(ctx->slots.reserve(ctx->geom.n_slots()));
+    CU(ctx->chunk_base.reserve(ctx->geom.n_slots() / kScanChunk));
+    CU(ctx->entries.reserve(std::max<size_t>((size_t)ctx->last.ctr.n_entries + 1024, ctx->entries.cap)));
+    int rc = enqueue_front(ctx, ctx->last_T, false, nv, 0.0);
+    if (rc == CB200_OK) rc = enqueue_back(ctx, ctx->last_T, false, true);
+    if (rc != CB200_OK) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    ctx->global_grid_valid = true;
+    return CB200_OK;
+}
+
 // Wait for the step, grow any buffer that overflowed.  *again = the step must be re-run.
 static int complete_step(cb200_ctx* ctx, double time, bool* again) {
     CU(cudaStreamSynchronize(ctx->stream));
@@ -917,11 +1086,30 @@ static int complete_step(cb200_ctx* ctx, double time, bool* again) {
     ctx->last = *ctx->h_res;
     ctx->last_add_mode = ctx->add_mode;
     ctx->last_dense_rank = ctx->dense_rank;
+    ctx->last_step_tile = ctx->step_is_tile;
+    ctx->global_grid_valid = !ctx->step_is_tile;
     ctx->last_T = time;
     ctx->have_step = true;
     ctx->ev_sorted = false;
     const Counters& c = ctx->last.ctr;
     *again = false;
+    if (ctx->step_is_tile) {
+        if (c.tile_fail) {
+            // a visitor slab or a single cell did not fit: this step, and every step up to the next re-sort, takes the global path
+            ctx->tile_suspended = true;
+            ctx->tile_fallbacks += 1;
+            CU(cudaMemsetAsync(ctx->vis_count.p, 0, 2 * (size_t)ctx->tgeom.n_tiles * 4, ctx->stream));
+            if (getenv("CB200_VERBOSE")) fprintf(stderr, "[cb200] tile path: capacity exceeded, falling back to the global path until the next re-sort\n");
+            *again = true;
+            return CB200_OK;
+        }
+        if (c.n_pair_events > ctx->events.cap) {
+            CU(ctx->events.reserve((size_t)c.n_pair_events + c.n_pair_events / 4 + 1024));
+            CU(cudaMemsetAsync(ctx->vis_count.p, 0, 2 * (size_t)ctx->tgeom.n_tiles * 4, ctx->stream));
+            *again = true;
+        }
+        return CB200_OK;
+    }
     if (c.overflow_entries || c.n_entries > ctx->entries.cap) {
         CU(ctx->entries.reserve((size_t)c.n_entries + c.n_entries / 4 + 1024));
         CU(reserve_dense(ctx));
@@ -1032,6 +1220,11 @@ static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
     if (const char* d = getenv("CB200_DBG_S")) mix((uint64_t)atoi(d) + 31);
     mix(ctx->ld256 ? 257u : 129u);
     mix(ctx->solve_two_phase ? 2u : 1u);
+    if (ctx->step_is_tile) {
+        mix(0x711e); mix((uint64_t)ctx->tgeom.tj); mix(ctx->tile_vcap); mix(ctx->tile_cap_rec); mix(ctx->tile_cap_ent); mix(ctx->tile_cap_q); mix(ctx->grid_t);
+        const void* tp[] = {ctx->tile_rows.p, ctx->home.p, ctx->vis_count.p, ctx->vis.p};
+        for (const void* q : tp) mix((uint64_t)(uintptr_t)q);
+    }
     return h ? h : 1;
 }
 
@@ -1054,6 +1247,8 @@ static int launch_step_graph(cb200_ctx* ctx, double time, const double* const* n
         int rc;
         if (ctx->sharded) {
             rc = enqueue_direct_step(ctx, time, nv, end_time);
+        } else if (ctx->step_is_tile) {
+            rc = enqueue_tile_step(ctx, true, nv);
         } else {
             rc = enqueue_front(ctx, time, true, nv, end_time);
             if (rc == CB200_OK) rc = enqueue_back(ctx, time, false);
@@ -1104,17 +1299,24 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
     int rc = stage_vel(ctx, vel, nv);
     if (rc != CB200_OK) return rc;
     if ((rc = prepare_buffers(ctx)) != CB200_OK) return rc;
+    ctx->tile_steps += 1;
     if ((rc = set_step_dyn(ctx, time, end_time)) != CB200_OK) return rc;
-    // A step is re-run (without the rebase) when a buffer had to grow.
+    // A step is re-run (without the rebase) when a buffer had to grow — or, on the tile path, when a tile exceeded its
+    // shared-memory capacity (then on the global path).
     bool again = true;
-    for (int attempt = 0; attempt < 4 && again; ++attempt) {
+    for (int attempt = 0; attempt < 5 && again; ++attempt) {
+        ctx->step_is_tile = ctx->tile_enabled && ctx->tile_ok && !ctx->tile_suspended && !ctx->add_mode && ctx->n >= 2;
         bool replayed = false;
         if (attempt == 0 && ctx->use_graph && !ctx->stage_timing) {
             if ((rc = launch_step_graph(ctx, time, nv, end_time, &replayed)) != CB200_OK) return rc;
         }
         if (!replayed) {
-            if ((rc = enqueue_front(ctx, time, attempt == 0, nv, end_time)) != CB200_OK) return rc;
-            if ((rc = enqueue_back(ctx, time, false)) != CB200_OK) return rc;
+            if (ctx->step_is_tile) {
+                if ((rc = enqueue_tile_step(ctx, attempt == 0, nv)) != CB200_OK) return rc;
+            } else {
+                if ((rc = enqueue_front(ctx, time, attempt == 0, nv, end_time)) != CB200_OK) return rc;
+                if ((rc = enqueue_back(ctx, time, false)) != CB200_OK) return rc;
+            }
         }
         if ((rc = complete_step(ctx, time, &again)) != CB200_OK) return rc;
         if (ctx->last.ctr.err_flags) break;
@@ -1630,8 +1832,26 @@ int cb200_fetch_candidate_pairs(cb200_ctx* ctx, uint64_t* id_hi, uint64_t* id_lo
     CU(out.reserve(total));
     CU(cnt.reserve(1));
     CU(cudaMemsetAsync(cnt.p, 0, 8, ctx->stream));
+    if (ctx->last_step_tile) {
+        // the tile kernel again, listing instead of solving (state, visitor slabs and this step's counters are untouched)
+        const VisSpace vs{ctx->n, ctx->n, 0u, 1, 0};
+        TileSolveArgs ts{};
+        ts.sv = solve_args_of(ctx, sh, vs);
+        ts.s = cols_of(ctx);
+        ts.label = ctx->label.p;
+        ts.bink = ctx->bink.p;
+        ts.tg = ctx->tgeom;
+        ts.tt = TileTables{ctx->tile_rows.p, ctx->home.p, ctx->vis_count.p, ctx->vis.p, ctx->tile_vcap, ctx->tgeom.n_tiles};
+        ts.cap_rec = ctx->tile_cap_rec;
+        ts.cap_ent = ctx->tile_cap_ent;
+        ts.cap_q = ctx->tile_cap_q;
+        ts.list_out = out.p;
+        ts.n_list = cnt.p;
+        ts.cap_list = total;
+        k_tile_solve<true><<<ctx->grid_t, kTileThreads, ctx->tile_smem, ctx->stream>>>(ts);
+    } else
     k_list_candidates<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(cd, work_lists_of(ctx), ctx->rec.p, out.p, cnt.p, total);
-    if (ctx->last_dense_rank != kDenseOff) {
+    if (!ctx->last_step_tile && ctx->last_dense_rank != kDenseOff) {
         DenseArgs da{};
         da.list = dense_list_of(ctx);
         da.entries = reinterpret_cast<const uint2*>(ctx->entries.p);
@@ -1661,6 +1881,10 @@ int cb200_fetch_cell_entries(cb200_ctx* ctx, int32_t* cell_x, int32_t* cell_y, u
     const uint64_t total = ctx->last.ctr.n_entries;
     if (n_out) *n_out = total;
     if (cap == 0 || total == 0) return CB200_OK;
+    {
+        int rc = rebuild_global_grid(ctx);  // (after a tile step)
+        if (rc != CB200_OK) return rc;
+    }
     std::vector<CellEntry> h(total);
     std::vector<uint64_t> ids;
     int rc = gid_to_id_table(ctx, ids);
@@ -1690,6 +1914,10 @@ int cb200_fetch_index_rects(cb200_ctx* ctx, int32_t* rects, uint64_t cap_hitboxe
     if (ctx->sharded) return fail(ctx, CB200_E_STATE, "fetch_index_rects is a one-device debug view");
     if (cap_hitboxes < ctx->n) return fail(ctx, CB200_E_ARG, "rect buffer too small");
     CU(cudaSetDevice(ctx->device));
+    {
+        int rc = rebuild_global_grid(ctx);  // (after a tile step the records are not all there)
+        if (rc != CB200_OK) return rc;
+    }
     // strided D2H: first 16 bytes of every 96-byte record = sx, sy, span, label -> decode the span, place by label
     std::vector<int32_t> raw((size_t)ctx->n * 4);
     if (ctx->n) CU(cudaMemcpy2D(raw.data(), 16, ctx->rec.p, sizeof(HbRec), 16, ctx->n, cudaMemcpyDeviceToHost));
@@ -1752,6 +1980,15 @@ int cb200_separate_time_batch(cb200_ctx* ctx, uint64_t n, const double* a, const
 }
 
 uint64_t cb200_launch_count(const cb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int cb200_last_step_path(const cb200_ctx* ctx) { return ctx && ctx->have_step ? (ctx->last_step_tile ? 1 : 0) : -1; }
+uint64_t cb200_tile_fallbacks(const cb200_ctx* ctx) { return ctx ? ctx->tile_fallbacks : 0; }
+int cb200_get_tile(const cb200_ctx* ctx, int* log2_slots, int* cells_x, int* cells_y) {
+    if (!ctx) return CB200_E_ARG;
+    if (log2_slots) *log2_slots = ctx->tile_ok ? ctx->tgeom.tj : 0;
+    if (cells_x) *cells_x = ctx->tile_ok ? 1 << ctx->tgeom.bx : 0;
+    if (cells_y) *cells_y = ctx->tile_ok ? 1 << ctx->tgeom.by : 0;
+    return CB200_OK;
+}
 
 int cb200_last_step_timing(cb200_ctx* ctx, float* total_ms, float* stage_ms, int n_stages) {
     if (!ctx) return CB200_E_ARG;

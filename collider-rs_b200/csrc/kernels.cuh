@@ -1250,6 +1250,8 @@ __device__ __forceinline__ void solve_epilogue(const SolveArgs& a, MinKey best, 
         out.err_flags = c->err_flags; out.scan_ticket = c->scan_ticket; out.overflow_entries = c->overflow_entries;
         out.done_blocks = c->done_blocks; out.n_local = c->n_local; out.overflow_send = c->overflow_send;
         out.diff_hi = 0; out.diff_lo = 0; out.n_sort_keys = 0;
+        out.n_tile_pairs = c->n_tile_pairs; out.tile_fail = c->tile_fail; out.pad1 = 0;
+        out.n_work += out.n_tile_pairs;
         a.result->ctr = out;
         __threadfence_system();
     }

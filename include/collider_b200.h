@@ -332,6 +332,14 @@ cb200_ctx* cb200_collider_engine(cb200_collider* c); /* the underlying device co
 
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
 uint64_t cb200_launch_count(const cb200_ctx* ctx);
+/* Which device path the last bulk step took: 1 = tile path (binning, candidate enumeration and pair solve per block of grid
+ * cells in shared memory: k_stage_a_tile + k_tile_solve + k_solve for the overlapping pairs), 0 = global path (slot table,
+ * entry array, work lists: k_stage_a, k_scan_slots, k_scatter, k_enum_pairs, k_solve[_dense]); -1 = no step yet.  Both are
+ * exact; the tile path is taken by single-device bulk steps (environment CB200_TILE=0 disables it), and a step whose tiles
+ * exceed the shared-memory capacities is repeated on the global path (cb200_tile_fallbacks counts those). */
+int cb200_last_step_path(const cb200_ctx* ctx);
+uint64_t cb200_tile_fallbacks(const cb200_ctx* ctx);
+int cb200_get_tile(const cb200_ctx* ctx, int* log2_slots, int* cells_x, int* cells_y); /* tile size chosen at the last re-sort (0: none) */
 /* Device-side duration of cb200_bulk_update and of each of its stages in milliseconds (CUDA events on the
  * context's stream).  For bench.py's roofline. */
 /* Averages since the last cb200_reset_timing.  Stages: 0 pre (H2D velocities + table zeroing), 1 stage A (+ halo

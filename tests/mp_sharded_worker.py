@@ -31,7 +31,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--exchange", default="direct", choices=["direct", "nccl"])
     ap.add_argument("--scenario", default="parity", choices=["parity", "abort", "timeout"])
-    ap.add_argument("--n", type=int, default=6000)
+    ap.add_argument("--hitboxes", dest="n", type=int, default=6000)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--scene", default="uniform", choices=["uniform", "dense", "clustered"])
     args = ap.parse_args()

@@ -15,6 +15,16 @@ cb = importlib.import_module("collider-rs_b200")
 scenes = importlib.import_module("collider-rs_b200.scenes")
 
 CW, PAD = scenes.CELL_WIDTH, scenes.PADDING
+
+
+@pytest.fixture(autouse=True, params=["tile", "global"])
+def device_path(request, monkeypatch):
+    """Every case runs on both device paths of the bulk step: the tile path (tile.cuh: binning / enumeration / solve per
+    block of cells in shared memory; the default) and the global path (slot table, entry array, work lists)."""
+    monkeypatch.setenv("CB200_TILE", "1" if request.param == "tile" else "0")
+    return request.param
+
+
 STATE_COLS = ("pos_x", "pos_y", "dim_x", "dim_y", "vel_x", "vel_y", "rsz_x", "rsz_y", "start_time", "end_time", "pub_end_time")
 
 
@@ -303,6 +313,32 @@ def test_event_queue_heavy_ties_at_later_times(oracle):
     np.testing.assert_array_equal(ev2["kind"], kind2)
     np.testing.assert_array_equal(ev2["a"], a2)
     np.testing.assert_array_equal(bits(ev2["time"]), bits(t2))
+
+
+def test_tile_path_is_taken_and_splits_or_falls_back_when_a_tile_does_not_fit(oracle, device_path, monkeypatch):
+    """The tile path handles a tile whose records exceed the shared-memory capacity by splitting its cell range (tiny
+    CB200_TILE_CAP), and a visitor slab that overflows by repeating the step on the global path (tiny CB200_TILE_VCAP) —
+    results identical either way."""
+    if device_path != "tile":
+        pytest.skip("tile path only")
+    scene = scenes.uniform_density(20000, density=0.5, seed=scenes.SEED_BASE + 50)
+    for env, want_fallback in (({}, False), ({"CB200_TILE_CAP": "40"}, False), ({"CB200_TILE_VCAP": "2"}, True), ({"CB200_TILE_LOG2": "11", "CB200_TILE_CAP": "64"}, False),
+                               ({"CB200_TILE_QUEUE": "256", "CB200_TILE_LOG2": "8"}, False)):
+        for k in ("CB200_TILE_CAP", "CB200_TILE_VCAP", "CB200_TILE_LOG2", "CB200_TILE_QUEUE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        orc, eng = seeded(oracle, scene)
+        T = 0.0
+        for step in range(2):
+            orc.bulk_update(end_time=T + 0.1, record_candidates=True)
+            res = eng.bulk_update(T, end_time=T + 0.1)
+            assert_step_parity(orc, eng, res, check_grid=(step == 1))
+            T += 0.1
+            drain_until(orc, T)
+            eng.set_overlaps(*orc.dump_overlaps())
+        assert (eng.tile_fallbacks() > 0) == want_fallback, env
+        assert eng.last_step_path() == ("global" if want_fallback else "tile"), env
 
 
 def test_aliased_grid_is_still_exact(oracle):

@@ -45,7 +45,7 @@ def test_direct_exchange_between_processes(world):
 
 
 def test_direct_exchange_between_processes_dense():
-    rc, log = launch(2, "--exchange", "direct", "--steps", "2", "--scene", "dense", "--n", "4000")
+    rc, log = launch(2, "--exchange", "direct", "--steps", "2", "--scene", "dense", "--hitboxes", "4000")
     assert rc == 0 and log.count("MP_SHARDED_OK") == 2, log[-4000:]
 
 
