@@ -137,15 +137,16 @@ struct cb200_ctx {
     bool geom_forced = false;
     double world_cells = 0;  // cells of the uploaded extent (choose_geom): the density the tile size is chosen from
     // ---- tile path (tile.cuh): binning / enumeration / solve per block of cells in shared memory ----
-    bool tile_enabled = true;     // CB200_TILE=0: the global path only
+    bool tile_enabled = false;    // CB200_TILE=1: single-device bulk steps take the tile path
     bool tile_ok = false;         // the row-range / home tables match the current row order (written at the re-sort)
     bool tile_suspended = false;  // a tile step exceeded a capacity: global path until the next re-sort
     bool step_is_tile = false, last_step_tile = false;
     bool global_grid_valid = false;  // the slot table / entry array / records describe the last step (always after a global step)
     TileGeom tgeom{};
-    uint32_t tile_target = 160;   // home rows per tile the tile size is chosen for (CB200_TILE_TARGET)
-    uint32_t tile_cap_rec = 352, tile_cap_ent = 1408, tile_cap_q = 1024, tile_vcap = 0;  // CB200_TILE_CAP
-    uint32_t per_sm_t = 3, grid_t = 0;
+    uint32_t tile_target = 48;    // home rows per tile the tile size is chosen for (CB200_TILE_TARGET)
+    uint32_t tile_cap_rec = 96, tile_cap_ent = 384, tile_vcap = 0;  // per warp (CB200_TILE_CAP)
+    uint32_t per_sm_t = CB200_LB_TILE, grid_t = 0;
+    DevBuf<uint2> surv;           // survivors of the tile kernel's filter: (source hi, source lo) (tile.cuh SurvList)
     size_t tile_smem = 0;
     DevBuf<uint2> tile_rows;
     DevBuf<uint32_t> home, vis_count;
@@ -375,10 +376,9 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if (const char* v = getenv("CB200_TILE")) c->tile_enabled = v[0] != '0';
     if (const char* v = getenv("CB200_TILE_TARGET")) c->tile_target = (uint32_t)std::max(16, std::min(2048, atoi(v)));
     if (const char* v = getenv("CB200_TILE_CAP")) {
-        c->tile_cap_rec = (uint32_t)std::max(32, std::min(1400, atoi(v)));
+        c->tile_cap_rec = (uint32_t)std::max(16, std::min(512, atoi(v)));
         c->tile_cap_ent = 4 * c->tile_cap_rec;
     }
-    if (const char* v = getenv("CB200_TILE_QUEUE")) c->tile_cap_q = (uint32_t)std::max(256, std::min(8192, atoi(v)));
     if (const char* v = getenv("CB200_PER_SM_T")) c->per_sm_t = (uint32_t)std::max(1, std::min(16, atoi(v)));
     for (auto& ev : c->ev_t)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -406,7 +406,7 @@ void cb200_destroy(cb200_ctx* c) {
     c->slots.release(); c->chunk_base.release(); c->entries.release(); c->work.release(); c->work_count.release(); c->dense.release();
     c->ov_pairs.release(); c->ov_table.release(); c->ov_bits.release(); c->ov_pair_bits.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
-    c->tile_rows.release(); c->home.release(); c->vis_count.release(); c->vis.release();
+    c->tile_rows.release(); c->home.release(); c->vis_count.release(); c->vis.release(); c->surv.release();
     c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); for (auto& b : c->bs_tab) b.release(); c->imm_pairs.release(); if (c->d_n_imm) cudaFree(c->d_n_imm); c->ev_out.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->d_key) cudaFree(c->d_key);
@@ -675,7 +675,14 @@ static int choose_tile_geom(cb200_ctx* ctx) {
     tj = std::max(4, std::min(std::min(11, g.lw + g.lh), tj));
     if (const char* v = getenv("CB200_TILE_LOG2")) tj = std::max(1, std::min(std::min(11, g.lw + g.lh), atoi(v)));
     ctx->tgeom = make_tile_geom(g, tj);
-    ctx->tile_vcap = std::max<uint32_t>(64, ctx->tile_cap_rec / 2 + 16);
+    {
+        // visitors a tile can expect: the hitboxes whose rect (about 1.45 cells wide at these shape sizes) reaches in from the
+        // neighbouring tiles, plus the rows that drift out of their home tile between two re-sorts; twice that, plus slack
+        const double own = per_cell * (double)(1u << tj);
+        const double wx = (double)(1u << ctx->tgeom.bx), wy = (double)(1u << ctx->tgeom.by);
+        const double ratio = (1.0 + 0.6 / wx) * (1.0 + 0.6 / wy) - 1.0;
+        ctx->tile_vcap = (uint32_t)std::min(4096.0, std::max(32.0, 2.0 * own * ratio + 32.0));
+    }
     if (const char* v = getenv("CB200_TILE_VCAP")) ctx->tile_vcap = (uint32_t)std::max(1, atoi(v));
     const uint32_t nt = ctx->tgeom.n_tiles;
     CU(ctx->tile_rows.reserve(nt));
@@ -683,12 +690,13 @@ static int choose_tile_geom(cb200_ctx* ctx) {
     CU(ctx->vis_count.reserve(2 * (size_t)nt));
     CU(ctx->vis.reserve((size_t)nt * ctx->tile_vcap));
     CU(cudaMemsetAsync(ctx->vis_count.p, 0, 2 * (size_t)nt * 4, ctx->stream));
-    ctx->tile_smem = tile_smem_bytes(ctx->tile_cap_rec, ctx->tile_cap_ent, ctx->tile_cap_q, tj);
-    CU(cudaFuncSetAttribute(k_tile_solve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
-    CU(cudaFuncSetAttribute(k_tile_solve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
+    ctx->tile_smem = kTileWarps * tile_warp_smem_bytes(ctx->tile_cap_rec, ctx->tile_cap_ent, tj);
+    CU(cudaFuncSetAttribute(k_tile_bin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
+    CU(cudaFuncSetAttribute(k_tile_bin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->tile_smem));
+    if (ctx->surv.cap == 0) CU(ctx->surv.reserve((size_t)ctx->n + 4096));
     ctx->grid_t = (uint32_t)ctx->sm_count * ctx->per_sm_t;
     if (getenv("CB200_VERBOSE"))
-        fprintf(stderr, "[cb200] tile path: 2^%d slots per tile (%d x %d cells), %u tiles, %.2f hitboxes per cell, record cap %u, visitor cap %u, %zu B smem, %u blocks\n", tj,
+        fprintf(stderr, "[cb200] tile path: 2^%d slots per tile (%d x %d cells), %u tiles, %.2f hitboxes per cell, record cap %u per warp, visitor cap %u, %zu B smem per block, %u blocks\n", tj,
                 1 << ctx->tgeom.bx, 1 << ctx->tgeom.by, nt, per_cell, ctx->tile_cap_rec, ctx->tile_vcap, ctx->tile_smem, ctx->grid_t);
     return CB200_OK;
 }
@@ -1044,19 +1052,17 @@ static int enqueue_tile_step(cb200_ctx* ctx, bool do_rebase, const double* const
     ts.tt = tt;
     ts.cap_rec = ctx->tile_cap_rec;
     ts.cap_ent = ctx->tile_cap_ent;
-    ts.cap_q = ctx->tile_cap_q;
-    ts.partial_at = ctx->grid_a + ctx->grid_s;
-    k_tile_solve<false><<<ctx->grid_t, kTileThreads, ctx->tile_smem, ctx->stream>>>(ts);
+    ts.surv = SurvList{ctx->surv.p, (uint32_t)std::min<size_t>(ctx->surv.cap, 0x7fffffffu)};
+    ts.sv.n_partial_dense = 0;
+    k_tile_bin<false><<<ctx->grid_t, kTileThreads, ctx->tile_smem, ctx->stream>>>(ts);
     ctx->launches += 1;
-    DBG_SYNC("k_tile_solve");
+    DBG_SYNC("k_tile_bin");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_SOLVE], ctx->stream));
-    // the overlapping pairs (separate_time) + the min-reduction and the step result; the work lists are empty (zeroed above).
-    // NET: the tile kernel counts the pairs that pass candidate_geom, this one takes the overlapping ones among them off again
-    SolveArgs sv = ts.sv;
-    sv.n_partial_dense = ctx->grid_t;
-    k_solve<false, true><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
+    // the survivors (collide_time) and the overlapping pairs (separate_time), the min-reduction and the step result.  The tile
+    // kernel counted the pairs that pass candidate_geom; this one takes the overlapping ones among them off again
+    k_tile_finish<false><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(ts, nullptr, nullptr, 0ull);
     ctx->launches += 1;
-    DBG_SYNC("k_solve");
+    DBG_SYNC("k_tile_finish");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
     CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
     return CB200_OK;
@@ -1099,15 +1105,21 @@ static int complete_step(cb200_ctx* ctx, double time, bool* again) {
             ctx->tile_suspended = true;
             ctx->tile_fallbacks += 1;
             CU(cudaMemsetAsync(ctx->vis_count.p, 0, 2 * (size_t)ctx->tgeom.n_tiles * 4, ctx->stream));
-            if (getenv("CB200_VERBOSE")) fprintf(stderr, "[cb200] tile path: capacity exceeded, falling back to the global path until the next re-sort\n");
+            if (getenv("CB200_VERBOSE"))
+                fprintf(stderr, "[cb200] tile path: capacity exceeded (code %u: 1 visitor slab, 2 records of one cell, 4 entries of one cell, 8 split stack), global path until the next re-sort\n",
+                        c.tile_fail);
             *again = true;
             return CB200_OK;
         }
-        if (c.n_pair_events > ctx->events.cap) {
-            CU(ctx->events.reserve((size_t)c.n_pair_events + c.n_pair_events / 4 + 1024));
-            CU(cudaMemsetAsync(ctx->vis_count.p, 0, 2 * (size_t)ctx->tgeom.n_tiles * 4, ctx->stream));
+        if (c.n_surv > ctx->surv.cap) {
+            CU(ctx->surv.reserve((size_t)c.n_surv + c.n_surv / 4 + 1024));
             *again = true;
         }
+        if (c.n_pair_events > ctx->events.cap) {
+            CU(ctx->events.reserve((size_t)c.n_pair_events + c.n_pair_events / 4 + 1024));
+            *again = true;
+        }
+        if (*again) CU(cudaMemsetAsync(ctx->vis_count.p, 0, 2 * (size_t)ctx->tgeom.n_tiles * 4, ctx->stream));
         return CB200_OK;
     }
     if (c.overflow_entries || c.n_entries > ctx->entries.cap) {
@@ -1221,8 +1233,9 @@ static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
     mix(ctx->ld256 ? 257u : 129u);
     mix(ctx->solve_two_phase ? 2u : 1u);
     if (ctx->step_is_tile) {
-        mix(0x711e); mix((uint64_t)ctx->tgeom.tj); mix(ctx->tile_vcap); mix(ctx->tile_cap_rec); mix(ctx->tile_cap_ent); mix(ctx->tile_cap_q); mix(ctx->grid_t);
-        const void* tp[] = {ctx->tile_rows.p, ctx->home.p, ctx->vis_count.p, ctx->vis.p};
+        mix(0x711e); mix((uint64_t)ctx->tgeom.tj); mix(ctx->tile_vcap); mix(ctx->tile_cap_rec); mix(ctx->tile_cap_ent); mix(ctx->grid_t);
+        const void* tp[] = {ctx->tile_rows.p, ctx->home.p, ctx->vis_count.p, ctx->vis.p, ctx->surv.p};
+        mix(ctx->surv.cap);
         for (const void* q : tp) mix((uint64_t)(uintptr_t)q);
     }
     return h ? h : 1;
@@ -1844,11 +1857,18 @@ int cb200_fetch_candidate_pairs(cb200_ctx* ctx, uint64_t* id_hi, uint64_t* id_lo
         ts.tt = TileTables{ctx->tile_rows.p, ctx->home.p, ctx->vis_count.p, ctx->vis.p, ctx->tile_vcap, ctx->tgeom.n_tiles};
         ts.cap_rec = ctx->tile_cap_rec;
         ts.cap_ent = ctx->tile_cap_ent;
-        ts.cap_q = ctx->tile_cap_q;
-        ts.list_out = out.p;
-        ts.n_list = cnt.p;
-        ts.cap_list = total;
-        k_tile_solve<true><<<ctx->grid_t, kTileThreads, ctx->tile_smem, ctx->stream>>>(ts);
+        // every pair that passes candidate_geom becomes a listed survivor (no swept-bounds filter): the list may need more room
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            ts.surv = SurvList{ctx->surv.p, (uint32_t)std::min<size_t>(ctx->surv.cap, 0x7fffffffu)};
+            CU(cudaMemsetAsync(&ctx->d_ctr->n_surv, 0, 8, ctx->stream));
+            k_tile_bin<true><<<ctx->grid_t, kTileThreads, ctx->tile_smem, ctx->stream>>>(ts);
+            unsigned long long n_surv = 0;
+            CU(cudaMemcpyAsync(&n_surv, &ctx->d_ctr->n_surv, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (n_surv <= ts.surv.cap) break;
+            CU(ctx->surv.reserve((size_t)n_surv + 1024));
+        }
+        k_tile_finish<true><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(ts, out.p, cnt.p, total);
     } else
     k_list_candidates<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(cd, work_lists_of(ctx), ctx->rec.p, out.p, cnt.p, total);
     if (!ctx->last_step_tile && ctx->last_dense_rank != kDenseOff) {

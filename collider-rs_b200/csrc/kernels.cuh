@@ -204,10 +204,18 @@ __device__ __forceinline__ uint32_t hb_update_core(HbCore& h, double T, bool reb
         } else {
             const double min_x = bb.cx - bb.w * 0.5, max_x = bb.cx + bb.w * 0.5;
             const double min_y = bb.cy - bb.h * 0.5, max_y = bb.cy + bb.h * 0.5;
-            const int32_t sx = f64_as_i32(floor(min_x / cell_width));
-            const int32_t sy = f64_as_i32(floor(min_y / cell_width));
-            const int32_t ex = max(f64_as_i32(ceil(max_x / cell_width)), (int32_t)((uint32_t)sx + 1u));
-            const int32_t ey = max(f64_as_i32(ceil(max_y / cell_width)), (int32_t)((uint32_t)sy + 1u));
+            // Grid::index_bounds divides by cell_width (grid.rs:101-113).  When cell_width is a power of two the quotient is an
+            // exact scaling, so multiplying by the (exact) reciprocal gives the same bits for every input — including subnormal
+            // results, which both operations round from the same real value — at a fraction of the cost of four f64 divisions.
+            const long long cw_bits = __double_as_longlong(cell_width);
+            const bool cw_pow2 = (cw_bits & 0x000fffffffffffffLL) == 0 && cw_bits > (2LL << 52) && cw_bits < (2044LL << 52);
+            const double cw_inv = __longlong_as_double((2046LL << 52) - cw_bits);
+            const double qx0 = cw_pow2 ? min_x * cw_inv : min_x / cell_width, qy0 = cw_pow2 ? min_y * cw_inv : min_y / cell_width;
+            const double qx1 = cw_pow2 ? max_x * cw_inv : max_x / cell_width, qy1 = cw_pow2 ? max_y * cw_inv : max_y / cell_width;
+            const int32_t sx = f64_as_i32(floor(qx0));
+            const int32_t sy = f64_as_i32(floor(qy0));
+            const int32_t ex = max(f64_as_i32(ceil(qx1)), (int32_t)((uint32_t)sx + 1u));
+            const int32_t ey = max(f64_as_i32(ceil(qy1)), (int32_t)((uint32_t)sy + 1u));
             const int64_t nx = (int64_t)ex - sx, ny = (int64_t)ey - sy;
             if (nx <= 0 || ny <= 0) {
                 err |= kFEmptyRect;  // IndexRect::new (index_rect.rs:26-29)
@@ -1250,7 +1258,7 @@ __device__ __forceinline__ void solve_epilogue(const SolveArgs& a, MinKey best, 
         out.err_flags = c->err_flags; out.scan_ticket = c->scan_ticket; out.overflow_entries = c->overflow_entries;
         out.done_blocks = c->done_blocks; out.n_local = c->n_local; out.overflow_send = c->overflow_send;
         out.diff_hi = 0; out.diff_lo = 0; out.n_sort_keys = 0;
-        out.n_tile_pairs = c->n_tile_pairs; out.tile_fail = c->tile_fail; out.pad1 = 0;
+        out.n_tile_pairs = c->n_tile_pairs; out.n_surv = c->n_surv; out.tile_fail = c->tile_fail; out.pad1 = 0;
         out.n_work += out.n_tile_pairs;
         a.result->ctr = out;
         __threadfence_system();

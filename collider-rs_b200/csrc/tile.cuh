@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_A) k_stage_a_tile(const Ste
                     if (t == home) continue;
                     const uint32_t pos = atomicAdd(&vis_count[t], 1u);
                     if (pos < ta.tt.vcap) store_rec(ta.tt.vis + (size_t)t * ta.tt.vcap + pos, rec);
-                    else a.ctr->tile_fail = 1u;
+                    else atomicOr(&a.ctr->tile_fail, 1u);  // (1: a visitor slab is full)
                 }
         }
         if (h.reit) {
@@ -145,331 +145,442 @@ __global__ void __launch_bounds__(kThreads) k_tile_home(uint32_t n, int tj, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Survivors: the candidate pairs whose swept bounds touch, as (source of the higher id, source of the lower id).  A source
+// names where the hitbox's data lives: a table row, or kTileVisFlag | index into the visitor slabs.  8 bytes per pair; the
+// finish kernel gathers the two hitboxes (only the ~5-30 % of the candidate pairs that survive the filter are ever gathered).
+struct SurvList {
+    uint2* items;
+    uint32_t cap;
+};
+
 struct TileSolveArgs {
-    SolveArgs sv;           // cd, dyn, padding, events, ctr, partial, add_mode ... (rec / work unused here)
+    SolveArgs sv;           // cd, dyn, padding, events, ctr, partial, add_mode ... (work lists unused here)
     StateCols s;            // own rows: rebased state
     const uint32_t* label;
     const int4* bink;       // (sx, sy, span, kgb) per row, written by stage A
     TileGeom tg;
     TileTables tt;
-    uint32_t cap_rec, cap_ent, cap_q;  // shared-memory capacities: records, cell entries, queued survivors
-    uint32_t partial_at;    // first slot of this kernel's block minima in sv.partial
-    uint2* list_out;        // LIST: accepted candidate pairs (gid hi, gid lo) instead of solving them
-    unsigned long long* n_list;
-    unsigned long long cap_list;
+    SurvList surv;
+    uint32_t cap_rec, cap_ent;  // shared-memory capacities per warp: records, cell entries
 };
 
-constexpr uint32_t kTileThreads = 256;
-constexpr uint32_t kTileEvBuf = 2 * kTileThreads;  // events a block collects before it appends them with one atomic
+constexpr uint32_t kTileWarps = 4;                  // warps per block: every warp works on its own tile
+constexpr uint32_t kTileThreads = 32 * kTileWarps;
 constexpr uint32_t kTileVisFlag = 0x80000000u;
-constexpr int kTileStack = 12;
+constexpr int kTileStack = 24;
+constexpr uint32_t kTileIter = 3;                   // (entry, predecessor) pairs a lane tests per round
 
-__host__ __device__ inline size_t tile_smem_bytes(uint32_t cap_rec, uint32_t cap_ent, uint32_t cap_q, int tj) {
+// One record of a tile in shared memory: all the candidate test and the swept-bounds filter need (80 bytes).
+struct alignas(16) TileRec {
+    int32_t sx, sy;
+    uint32_t span, gid;
+    uint32_t kgb, mask, src, pad;
+    double l, r, b, t;  // swept edges over the record's own duration (narrowphase.cuh swept_edges)
+    double dur_key;
+    unsigned long long cells;  // tile_cell_list (valid when kgb bit 4 is set; bits 4.. of kgb are free in a record)
+};
+static_assert(sizeof(TileRec) == 80, "TileRec is five 16-byte chunks");
+
+__host__ __device__ inline size_t tile_warp_smem_bytes(uint32_t cap_rec, uint32_t cap_ent, int tj) {
     const size_t nc = (size_t)1 << tj;
-    return (size_t)cap_rec * (96 + 40 + 4) + (nc + 1) * 4 * 2 + (size_t)cap_ent * 4 + (size_t)cap_q * 4 + (size_t)kTileEvBuf * 16 + 64;
+    return ((size_t)cap_rec * sizeof(TileRec) + (nc + 1) * 4 * 2 + (size_t)cap_ent * 4 + 8 * kTileStack + 15) & ~(size_t)15;
 }
 
-// Does any cell of the rect fold into local cells [lo, hi) of the tile whose first slot is `base`?
-__device__ __forceinline__ bool rect_touches(const GridGeom& g, int32_t sx, int32_t sy, uint32_t span, uint32_t base, uint32_t lo, uint32_t hi) {
+// GridGeom::slot is separable: slot(x, y) = slot_x(x) | slot_y(y).
+__device__ __forceinline__ uint32_t slot_x(const GridGeom& g, int32_t x) {
+    const uint32_t ux = (uint32_t)x & ((1u << g.lw) - 1u);
+    const int a = g.tx(), b = g.ty();
+    return (ux & ((1u << a) - 1u)) | ((ux >> a) << (a + b));
+}
+__device__ __forceinline__ uint32_t slot_y(const GridGeom& g, int32_t y) {
+    const uint32_t uy = (uint32_t)y & ((1u << g.lh) - 1u);
+    const int a = g.tx(), b = g.ty();
+    return ((uy & ((1u << b) - 1u)) << a) | ((uy >> b) << (g.lw + b));
+}
+// The cells of a rect that fold into the tile whose first slot is `base` (NC slots), as up to four 16-bit local cell ids
+// (0xffff = none) — rects of at most 2 x 2 cells, i.e. nearly all of them; *complete = false for a larger rect (its cells are
+// then walked by for_tile_cells every time).
+__device__ __forceinline__ unsigned long long tile_cell_list(const GridGeom& g, int32_t sx, int32_t sy, uint32_t span, uint32_t base, uint32_t NC, bool* complete) {
+    const uint32_t nx = span & 0xffffu, ny = span >> 16;
+    *complete = nx <= 2u && ny <= 2u;
+    const uint32_t fx0 = slot_x(g, sx), fx1 = slot_x(g, sx + 1), fy0 = slot_y(g, sy), fy1 = slot_y(g, sy + 1);
+    uint32_t c[4] = {(fx0 | fy0) - base, (fx0 | fy1) - base, (fx1 | fy0) - base, (fx1 | fy1) - base};
+    const bool ok[4] = {nx >= 1u && ny >= 1u, nx >= 1u && ny >= 2u, nx >= 2u && ny >= 1u, nx >= 2u && ny >= 2u};
+    unsigned long long list = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) list |= (unsigned long long)((ok[k] && c[k] < NC) ? c[k] : 0xffffu) << (16 * k);
+    return list;
+}
+// The local cells of a rect inside a tile.  f(c) is called for every cell of the rect that folds into local cells
+// [lo, hi) of the tile whose first slot is `base`.
+template <class F>
+__device__ __forceinline__ void for_tile_cells(const GridGeom& g, int32_t sx, int32_t sy, uint32_t span, uint32_t base, uint32_t lo, uint32_t hi, F&& f) {
     const int32_t ex = sx + (int32_t)(span & 0xffffu), ey = sy + (int32_t)(span >> 16);
-    for (int32_t x = sx; x < ex; ++x)
+    for (int32_t x = sx; x < ex; ++x) {
+        const uint32_t fx = slot_x(g, x);
         for (int32_t y = sy; y != ey; ++y) {
-            const uint32_t c = g.slot(x, y) - base;  // (unsigned: slots below the tile wrap to huge values)
-            if (c >= lo && c < hi) return true;
+            const uint32_t c = (fx | slot_y(g, y)) - base;  // (unsigned: slots below the tile wrap to huge values)
+            if (c >= lo && c < hi) f(c - lo);
         }
-    return false;
+    }
+}
+// The same from a record's stored cell list when it is complete (kgb bit 4).
+template <class F>
+__device__ __forceinline__ void for_rec_cells(const GridGeom& g, int32_t sx, int32_t sy, uint32_t span, uint32_t kgb, unsigned long long list, uint32_t base, uint32_t lo,
+                                              uint32_t hi, F&& f) {
+    if (kgb & 16u) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t c = (uint32_t)(list >> (16 * k)) & 0xffffu;
+            if (c >= lo && c < hi) f(c - lo);  // (0xffff >= hi always: NC <= 2048)
+        }
+    } else {
+        for_tile_cells(g, sx, sy, span, base, lo, hi, f);
+    }
+}
+
+// The hitbox a source names, as the solve stage needs it.
+__device__ __forceinline__ void load_source(const TileSolveArgs& a, uint32_t src, double T, RecHead* h, DurHb* d) {
+    if (src & kTileVisFlag) {
+        const int4* p = reinterpret_cast<const int4*>(a.tt.vis + (src & ~kTileVisFlag));
+        decode_rec(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3), __ldg(p + 4), __ldg(p + 5), h, d);
+        return;
+    }
+    const int4 bk = __ldg(a.bink + src);
+    h->sx = bk.x; h->sy = bk.y;
+    h->ex = bk.x + (int32_t)((uint32_t)bk.z & 0xffffu);
+    h->ey = bk.y + (int32_t)((uint32_t)bk.z >> 16);
+    h->gid = __ldg(a.label + src);
+    h->kgb = (uint32_t)bk.w;
+    h->mask = __ldg(a.s.mask + src);
+    h->dur = __ldg(a.s.end + src) - T;  // (= r_time - T of stage A: the same operation on the same operands)
+    d->px = __ldg(a.s.px + src); d->py = __ldg(a.s.py + src); d->w = __ldg(a.s.w + src); d->h = __ldg(a.s.h + src);
+    d->vx = __ldg(a.s.vx + src); d->vy = __ldg(a.s.vy + src); d->rw = __ldg(a.s.rw + src); d->rh = __ldg(a.s.rh + src);
+    d->dur = h->dur;
+    d->kind = (int)(h->kgb & 1u);
 }
 
 #ifndef CB200_LB_TILE
-#define CB200_LB_TILE 2
+#define CB200_LB_TILE 5
 #endif
+// Binning + candidate enumeration + swept-bounds filter, one WARP per tile (no block-wide barrier anywhere); the survivors
+// leave as source pairs (SurvList).  LIST: the filter is skipped, i.e. the list holds every pair that passes candidate_geom
+// (the parity view).
 template <bool LIST>
-__global__ void __launch_bounds__(kTileThreads, CB200_LB_TILE) k_tile_solve(const TileSolveArgs a) {
+__global__ void __launch_bounds__(kTileThreads, CB200_LB_TILE) k_tile_bin(const TileSolveArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    // ---- shared-memory carve-up ----
-    int4* const s_rec = reinterpret_cast<int4*>(smem);                                         // [cap_rec * 6]
-    double* const s_edge = reinterpret_cast<double*>(smem + (size_t)a.cap_rec * 96);           // [cap_rec * 5]: l, r, b, t, dur_key
-    uint32_t* const s_src = reinterpret_cast<uint32_t*>(smem + (size_t)a.cap_rec * 136);       // [cap_rec]: row | visitor index
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t NC = 1u << a.tg.tj;
-    uint32_t* const s_off = s_src + a.cap_rec;   // [NC + 1] run starts
-    uint32_t* const s_cur = s_off + NC + 1;      // [NC + 1] counts, then cursors
-    uint32_t* const s_ent = s_cur + NC + 1;      // [cap_ent]: record index | local cell << 16
-    uint32_t* const s_q = s_ent + a.cap_ent;     // [cap_q]: record of the entry | record of its predecessor << 16
-    PairEvent* const s_ev = reinterpret_cast<PairEvent*>((reinterpret_cast<uintptr_t>(s_q + a.cap_q) + 15) & ~(uintptr_t)15);  // [kTileEvBuf]
-    __shared__ uint32_t s_nsel, s_nq, s_nev, s_sp, s_any;
-    __shared__ unsigned long long s_evbase;
-    __shared__ uint2 s_stack[kTileStack];
+    // ---- this warp's shared memory ----
+    unsigned char* const mine = smem + (size_t)warp * tile_warp_smem_bytes(a.cap_rec, a.cap_ent, a.tg.tj);
+    TileRec* const s_rec = reinterpret_cast<TileRec*>(mine);                 // [cap_rec]
+    uint2* const s_stack = reinterpret_cast<uint2*>(s_rec + a.cap_rec);      // [kTileStack]: cell ranges still to do
+    uint32_t* const s_off = reinterpret_cast<uint32_t*>(s_stack + kTileStack);  // [NC + 1] run starts
+    uint32_t* const s_cur = s_off + NC + 1;                                  // [NC + 1] counts, then cursors
+    uint32_t* const s_ent = s_cur + NC + 1;                                  // [cap_ent]: record index | local cell << 16
 
-    const int lane = threadIdx.x & 31;
     const StepDyn dyn = *a.sv.dyn;
     const double T = dyn.T;
     const uint32_t par = (uint32_t)(dyn.tag & 1ull);
-    uint32_t* const cnt_now = a.tt.vis_count + (size_t)par * a.tt.n_tiles;
+    const uint32_t* const cnt_now = a.tt.vis_count + (size_t)par * a.tt.n_tiles;
     uint32_t* const cnt_next = a.tt.vis_count + (size_t)(par ^ 1u) * a.tt.n_tiles;
     const GridGeom geom = a.sv.cd.geom;
+    const uint32_t fold_x = (1u << geom.lw) - 1u, fold_y = (1u << geom.lh) - 1u;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
-    MinKey best{kKeyMax, kKeyMax};
-    unsigned long long n_col = 0, n_entries = 0, n_cells = 0, n_pairs = 0;
+    unsigned long long n_col = 0, n_pairs = 0;
+    uint32_t n_entries = 0, n_cells = 0;  // (lane 0 / per lane)
 
-    auto flush_events = [&]() {  // all threads
-        __syncthreads();
-        const uint32_t n_ev = s_nev;
-        if (n_ev) {
-            if (threadIdx.x == 0) s_evbase = atomicAdd(&a.sv.ctr->n_pair_events, (unsigned long long)n_ev);
-            __syncthreads();
-            const unsigned long long pos = s_evbase;
-            for (uint32_t k = threadIdx.x; k < n_ev; k += blockDim.x)
-                if (pos + k < a.sv.cap_events) a.sv.events[pos + k] = s_ev[k];
-            __syncthreads();
-            if (threadIdx.x == 0) s_nev = 0;
-            __syncthreads();
-        }
-    };
-    if (threadIdx.x == 0) {
-        s_nev = 0;
-        s_nq = 0;
-    }
-    __syncthreads();
-
-    for (uint32_t t = blockIdx.x; t < a.tt.n_tiles; t += gridDim.x) {
+    const uint32_t n_warps = gridDim.x * kTileWarps;
+    for (uint32_t t = blockIdx.x * kTileWarps + warp; t < a.tt.n_tiles; t += n_warps) {
         const uint2 rows = __ldg(a.tt.rows + t);
         const uint32_t n_vis = min(cnt_now[t], a.tt.vcap);
-        if (!LIST && threadIdx.x == 0) cnt_next[t] = 0u;  // the slab counter the NEXT step appends to
+        if (!LIST && lane == 0) cnt_next[t] = 0u;  // the slab counter the NEXT step appends to
         if (rows.y == rows.x && n_vis == 0) continue;
         const uint32_t base = t << a.tg.tj;
-        const HbRec* const vis = a.tt.vis + (size_t)t * a.tt.vcap;
-        if (threadIdx.x == 0) {
-            s_stack[0] = make_uint2(0u, NC);
-            s_sp = 1;
-        }
-        __syncthreads();
-        while (s_sp) {  // (block-uniform: s_sp changes only between barriers)
-            const uint2 range = s_stack[s_sp - 1];
-            const uint32_t lo = range.x, hi = range.y;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                s_sp -= 1;
-                s_nsel = 0;
-            }
-            for (uint32_t c = threadIdx.x; c <= hi - lo; c += blockDim.x) s_cur[c] = 0u;
-            __syncthreads();
-            // ---- select: the rows / visitors with a cell in [lo, hi), in order (a warp's 32 consecutive rows stay together) ----
-            const uint32_t n_own = rows.y - rows.x, n_all = n_own + n_vis;
-            for (uint32_t b0 = (threadIdx.x & ~31u); b0 < n_all; b0 += blockDim.x) {
+        const size_t vis0 = (size_t)t * a.tt.vcap;
+        const uint32_t n_own = rows.y - rows.x, n_all = n_own + n_vis;
+        uint32_t sp = 1;  // (warp-uniform)
+        if (lane == 0) s_stack[0] = make_uint2(0u, NC);
+        __syncwarp();
+        while (sp) {
+            const uint2 range = s_stack[sp - 1];
+            sp -= 1;
+            const uint32_t lo = range.x, hi = range.y, n_c = hi - lo;
+            for (uint32_t c = lane; c <= n_c; c += 32) s_cur[c] = 0u;
+            __syncwarp();
+            // ---- load: every row / visitor with a cell in [lo, hi) becomes a record in shared memory, in order; its cells are
+            //      counted.  One round trip to global memory: all the columns of a row are requested before anything is known about it
+            uint32_t n_sel = 0;
+            for (uint32_t b0 = 0; b0 < n_all; b0 += 32) {
                 const uint32_t k = b0 + (uint32_t)lane;
                 bool take = false;
-                uint32_t src = 0;
+                TileRec r;
+                DurHb d;
                 if (k < n_own) {
-                    const int4 bk = __ldg(a.bink + rows.x + k);
-                    take = ((uint32_t)bk.w & 2u) && rect_touches(geom, bk.x, bk.y, (uint32_t)bk.z, base, lo, hi);
-                    src = rows.x + k;
-                } else if (k < n_all) {
-                    const int4 hd = __ldg(reinterpret_cast<const int4*>(vis + (k - n_own)));
-                    take = rect_touches(geom, hd.x, hd.y, (uint32_t)hd.z, base, lo, hi);
-                    src = kTileVisFlag | (k - n_own);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, take);
-                if (m) {
-                    uint32_t at = 0;
-                    if (lane == 0) at = atomicAdd(&s_nsel, (uint32_t)__popc(m));
-                    at = __shfl_sync(0xffffffffu, at, 0) + (uint32_t)__popc(m & ((1u << lane) - 1u));
-                    if (take && at < a.cap_rec) s_src[at] = src;
-                }
-            }
-            __syncthreads();
-            const uint32_t n_sel = s_nsel;
-            if (n_sel > a.cap_rec) {
-                // too many records for one pass: halve the cell range (a single cell that does not fit -> global path)
-                if (threadIdx.x == 0) {
-                    if (hi - lo < 2u || s_sp + 2 > kTileStack) {
-                        a.sv.ctr->tile_fail = 1u;
-                    } else {
-                        const uint32_t mid = lo + ((hi - lo) >> 1);
-                        s_stack[s_sp] = make_uint2(mid, hi);
-                        s_stack[s_sp + 1] = make_uint2(lo, mid);
-                        s_sp += 2;
-                    }
-                }
-                __syncthreads();
-                continue;
-            }
-            if (n_sel == 0) continue;
-            // ---- load the records (own rows: from the SoA columns; visitors: their 96 bytes), swept edges, cell counts ----
-            for (uint32_t k = threadIdx.x; k < n_sel; k += blockDim.x) {
-                const uint32_t src = s_src[k];
-                HbRec r;
-                if (src & kTileVisFlag) {
-                    const int4* p = reinterpret_cast<const int4*>(vis + (src & ~kTileVisFlag));
-                    int4* q = reinterpret_cast<int4*>(&r);
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) q[j] = __ldg(p + j);
-                } else {
+                    const uint32_t src = rows.x + k;
                     const int4 bk = __ldg(a.bink + src);
-                    r.sx = bk.x; r.sy = bk.y; r.span = (uint32_t)bk.z; r.kgb = (uint32_t)bk.w;
                     r.gid = __ldg(a.label + src);
                     r.mask = a.s.mask[src];
-                    r.dur = a.s.end[src] - T;  // (= r_time - T of stage A: the same operation on the same operands)
-                    r.px = a.s.px[src]; r.py = a.s.py[src]; r.w = a.s.w[src]; r.h = a.s.h[src];
-                    r.vx = a.s.vx[src]; r.vy = a.s.vy[src]; r.rw = a.s.rw[src]; r.rh = a.s.rh[src];
+                    const double end = a.s.end[src];
+                    d.px = a.s.px[src]; d.py = a.s.py[src]; d.w = a.s.w[src]; d.h = a.s.h[src];
+                    d.vx = a.s.vx[src]; d.vy = a.s.vy[src]; d.rw = a.s.rw[src]; d.rh = a.s.rh[src];
+                    r.sx = bk.x; r.sy = bk.y; r.span = (uint32_t)bk.z; r.kgb = (uint32_t)bk.w;
+                    r.src = src;
+                    d.dur = end - T;  // (= r_time - T of stage A: the same operation on the same operands)
+                    take = (r.kgb & 2u) != 0u;
+                } else if (k < n_all) {
+                    const int4* p = reinterpret_cast<const int4*>(a.tt.vis + vis0 + (k - n_own));
+                    const int4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3), q4 = __ldg(p + 4), q5 = __ldg(p + 5);
+                    RecHead h;
+                    decode_rec(q0, q1, q2, q3, q4, q5, &h, &d);
+                    r.sx = q0.x; r.sy = q0.y; r.span = (uint32_t)q0.z; r.gid = h.gid; r.kgb = h.kgb; r.mask = h.mask;
+                    r.src = kTileVisFlag | (uint32_t)(vis0 + (k - n_own));
+                    take = true;
                 }
-                const int4* q = reinterpret_cast<const int4*>(&r);
+                if (take) {
+                    bool complete;
+                    r.cells = tile_cell_list(geom, r.sx, r.sy, r.span, base, NC, &complete);
+                    r.kgb = (r.kgb & ~16u) | (complete ? 16u : 0u);
+                    bool any = false;
+                    for_rec_cells(geom, r.sx, r.sy, r.span, r.kgb, r.cells, base, lo, hi, [&](uint32_t) { any = true; });
+                    take = any;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, take);
+                const uint32_t at = n_sel + (uint32_t)__popc(m & lt_mask);
+                n_sel += (uint32_t)__popc(m);
+                if (take && at < a.cap_rec) {
+                    d.kind = (int)(r.kgb & 1u);
+                    const SweptEdges e = swept_edges(d);
+                    r.l = e.l; r.r = e.r; r.b = e.b; r.t = e.t; r.dur_key = e.dur_key;
+                    r.pad = 0u;
+                    const int4* q = reinterpret_cast<const int4*>(&r);
+                    int4* o = reinterpret_cast<int4*>(s_rec + at);
 #pragma unroll
-                for (int j = 0; j < 6; ++j) s_rec[k * 6 + j] = q[j];
-                DurHb d;
-                d.px = r.px; d.py = r.py; d.w = r.w; d.h = r.h; d.vx = r.vx; d.vy = r.vy; d.rw = r.rw; d.rh = r.rh; d.dur = r.dur; d.kind = (int)(r.kgb & 1u);
-                const SweptEdges e = swept_edges(d);
-                s_edge[k * 5 + 0] = e.l; s_edge[k * 5 + 1] = e.r; s_edge[k * 5 + 2] = e.b; s_edge[k * 5 + 3] = e.t; s_edge[k * 5 + 4] = e.dur_key;
-                const int32_t ex = r.sx + (int32_t)(r.span & 0xffffu), ey = r.sy + (int32_t)(r.span >> 16);
-                for (int32_t x = r.sx; x < ex; ++x)
-                    for (int32_t y = r.sy; y != ey; ++y) {
-                        const uint32_t c = geom.slot(x, y) - base;
-                        if (c >= lo && c < hi) atomicAdd(&s_cur[c - lo], 1u);
-                    }
+                    for (int j = 0; j < 5; ++j) o[j] = q[j];
+                    for_rec_cells(geom, r.sx, r.sy, r.span, r.kgb, r.cells, base, lo, hi, [&](uint32_t c) { atomicAdd(&s_cur[c], 1u); });
+                }
             }
-            __syncthreads();
+            __syncwarp();
             // ---- scan the cell counts: run starts ----
-            const uint32_t n_c = hi - lo;
-            uint32_t n_ent, nz = 0;
-            {
-                const uint32_t per = (n_c + blockDim.x - 1) / blockDim.x;
-                const uint32_t c0 = min(threadIdx.x * per, n_c), c1 = min(c0 + per, n_c);
+            uint32_t n_ent = 0, nz = 0;
+            if (n_sel <= a.cap_rec) {  // (warp-uniform)
+                const uint32_t per = (n_c + 31u) / 32u;
+                const uint32_t c0 = min((uint32_t)lane * per, n_c), c1 = min(c0 + per, n_c);
                 uint32_t sum = 0;
                 for (uint32_t c = c0; c < c1; ++c) {
                     sum += s_cur[c];
                     nz += s_cur[c] != 0u;
                 }
-                uint32_t run = block_excl_scan(sum, &n_ent);
+                uint32_t inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += u;
+                }
+                n_ent = __shfl_sync(0xffffffffu, inc, 31);
+                uint32_t run = inc - sum;
                 for (uint32_t c = c0; c < c1; ++c) {
                     const uint32_t v = s_cur[c];
                     s_off[c] = run;
                     s_cur[c] = run;
                     run += v;
                 }
-                if (c1 == n_c) s_off[n_c] = n_ent;
             }
-            __syncthreads();
-            if (n_ent > a.cap_ent) {
-                // too many cell entries for one pass: halve the cell range as above
-                if (threadIdx.x == 0) {
-                    if (hi - lo < 2u || s_sp + 2 > kTileStack) {
-                        a.sv.ctr->tile_fail = 1u;
-                    } else {
-                        const uint32_t mid = lo + ((hi - lo) >> 1);
-                        s_stack[s_sp] = make_uint2(mid, hi);
-                        s_stack[s_sp + 1] = make_uint2(lo, mid);
-                        s_sp += 2;
+            __syncwarp();
+            if (n_sel > a.cap_rec || n_ent > a.cap_ent) {
+                // too many records / cell entries for one pass: halve the cell range (a single cell that does not fit -> global path)
+                if (n_c < 2u || sp + 2 > (uint32_t)kTileStack) {
+                    if (lane == 0) atomicOr(&a.sv.ctr->tile_fail, n_c < 2u ? (n_sel > a.cap_rec ? 2u : 4u) : 8u);  // (2 / 4: one cell's records / entries do not fit; 8: stack)
+                } else {
+                    const uint32_t mid = lo + (n_c >> 1);
+                    if (lane == 0) {
+                        s_stack[sp] = make_uint2(mid, hi);
+                        s_stack[sp + 1] = make_uint2(lo, mid);
                     }
+                    sp += 2;
                 }
-                __syncthreads();
+                __syncwarp();
                 continue;
             }
+            if (n_sel == 0) continue;
             n_cells += nz;
-            if (threadIdx.x == 0) n_entries += n_ent;
+            if (lane == 0) n_entries += n_ent;
             // ---- scatter: 4-byte local entries (record index | local cell << 16) ----
-            for (uint32_t k = threadIdx.x; k < n_sel; k += blockDim.x) {
-                const int4 hd = s_rec[k * 6];
-                const int32_t ex = hd.x + (int32_t)((uint32_t)hd.z & 0xffffu), ey = hd.y + (int32_t)((uint32_t)hd.z >> 16);
-                for (int32_t x = hd.x; x < ex; ++x)
-                    for (int32_t y = hd.y; y != ey; ++y) {
-                        const uint32_t c = geom.slot(x, y) - base;
-                        if (c >= lo && c < hi) s_ent[atomicAdd(&s_cur[c - lo], 1u)] = k | ((c - lo) << 16);
-                    }
+            for (uint32_t k = lane; k < n_sel; k += 32) {
+                const int4 h0 = *reinterpret_cast<const int4*>(s_rec + k);
+                const uint32_t kgb = s_rec[k].kgb;
+                const unsigned long long cells = s_rec[k].cells;
+                for_rec_cells(geom, h0.x, h0.y, (uint32_t)h0.z, kgb, cells, base, lo, hi, [&](uint32_t c) { s_ent[atomicAdd(&s_cur[c], 1u)] = k | (c << 16); });
             }
-            __syncthreads();
-            // ---- enumerate + filter (each thread walks the predecessors of its entries), solve whenever the queue fills ----
-            uint32_t e = threadIdx.x;  // this thread's current entry
-            uint32_t p = 0;            // next predecessor position of that entry
-            bool fresh = true, done = e >= n_ent;
+            __syncwarp();
+            // ---- enumerate + filter: each lane walks the predecessors of its entries, at most kTileIter pairs per round; then the
+            //      round's survivors are appended to the global list with one atomic ----
+            uint32_t e = lane, p = 0, p_end = 0;
+            bool fresh = true;
             for (;;) {
-                while (!done) {
+                uint32_t budget = kTileIter, my_q = 0;
+                uint2 mine_q[kTileIter];
+                while (e < n_ent && budget) {
                     const uint32_t ent = s_ent[e];
                     const uint32_t ka = ent & 0xffffu, c = ent >> 16;
                     if (fresh) {
                         p = s_off[c];
+                        p_end = e;
                         fresh = false;
                     }
-                    if (p == e) {
-                        e += blockDim.x;
-                        fresh = true;
-                        done = e >= n_ent;
-                        continue;
-                    }
-                    const uint32_t kb = s_ent[p] & 0xffffu;
-                    // candidate test from the two record heads (candidate_geom: owner cell, column strip, interact groups)
-                    const int4 a0 = s_rec[ka * 6], a1 = s_rec[ka * 6 + 1], b0 = s_rec[kb * 6], b1 = s_rec[kb * 6 + 1];
-                    RecHead ha, hb;
-                    ha.sx = a0.x; ha.sy = a0.y; ha.ex = a0.x + (int32_t)((uint32_t)a0.z & 0xffffu); ha.ey = a0.y + (int32_t)((uint32_t)a0.z >> 16);
-                    ha.gid = (uint32_t)a0.w; ha.kgb = (uint32_t)a1.z; ha.mask = (uint32_t)a1.w;
-                    hb.sx = b0.x; hb.sy = b0.y; hb.ex = b0.x + (int32_t)((uint32_t)b0.z & 0xffffu); hb.ey = b0.y + (int32_t)((uint32_t)b0.z >> 16);
-                    hb.gid = (uint32_t)b0.w; hb.kgb = (uint32_t)b1.z; hb.mask = (uint32_t)b1.w;
-                    bool a_is_hi;
-                    bool pass = candidate_geom(a.sv.cd, ha, hb, base + lo + c, &a_is_hi);
-                    if (pass) {
-                        if (!LIST) {
-                            SweptEdges ea;
-                            ea.l = s_edge[ka * 5]; ea.r = s_edge[ka * 5 + 1]; ea.b = s_edge[ka * 5 + 2]; ea.t = s_edge[ka * 5 + 3]; ea.dur_key = s_edge[ka * 5 + 4];
-                            pass = swept_filter_pass(ea, s_edge[kb * 5], s_edge[kb * 5 + 1], s_edge[kb * 5 + 2], s_edge[kb * 5 + 3], s_edge[kb * 5 + 4]);
-                        }
-                        if (pass) {
-                            const uint32_t at = atomicAdd(&s_nq, 1u);
-                            if (at >= a.cap_q) break;  // queue full: this pair is retried after the solve round (p not advanced)
-                            s_q[at] = ka | (kb << 16);
-                        }
-                        n_col += 1;  // (counted when the pair leaves the filter, exactly once: a retried pair breaks before this)
-                    }
-                    n_pairs += 1;
-                    p += 1;
-                }
-                // ---- solve round ----
-                __syncthreads();
-                const uint32_t n_q = min(s_nq, a.cap_q);
-                for (uint32_t q0 = 0; q0 < n_q; q0 += blockDim.x) {
-                    if (s_nev + blockDim.x > kTileEvBuf) flush_events();  // (block-uniform: s_nev is stable between barriers)
-                    const uint32_t q = q0 + threadIdx.x;
-                    if (q < n_q) {
-                        const uint32_t pr = s_q[q];
-                        const int4* pa = s_rec + (pr & 0xffffu) * 6;
-                        const int4* pb = s_rec + (pr >> 16) * 6;
-                        RecHead h1, h2;
-                        DurHb d1, d2;
-                        decode_rec(pa[0], pa[1], pa[2], pa[3], pa[4], pa[5], &h1, &d1);
-                        decode_rec(pb[0], pb[1], pb[2], pb[3], pb[4], pb[5], &h2, &d2);
-                        const bool first_hi = h1.gid > h2.gid;
-                        if (!is_overlapping(a.sv.cd, h1, h2, first_hi)) {
-                            if (LIST) {
-                                const unsigned long long pos = atomicAdd(a.n_list, 1ull);
-                                if (pos < a.cap_list) a.list_out[pos] = first_hi ? make_uint2(h1.gid, h2.gid) : make_uint2(h2.gid, h1.gid);
-                            } else {
-                                PairEvent ev;
-                                if (solve_pair(a.sv, T, h1, d1, h2, d2, first_hi, &ev, &best)) s_ev[atomicAdd(&s_nev, 1u)] = ev;
+                    if (p < p_end) {
+                        const TileRec ra = s_rec[ka];
+                        const int32_t aex = ra.sx + (int32_t)(ra.span & 0xffffu), aey = ra.sy + (int32_t)(ra.span >> 16);
+                        uint32_t cell_x, cell_y;  // the folded cell of the run: a pair belongs to it iff its owner cell folds to the same
+                        geom.unslot(base + lo + c, &cell_x, &cell_y);
+                        for (; p < p_end && budget; ++p, --budget) {
+                            const uint32_t kb = s_ent[p] & 0xffffu;
+                            const int4 b0 = *reinterpret_cast<const int4*>(s_rec + kb), b1 = *(reinterpret_cast<const int4*>(s_rec + kb) + 1);
+                            const int32_t bex = b0.x + (int32_t)((uint32_t)b0.z & 0xffffu), bey = b0.y + (int32_t)((uint32_t)b0.z >> 16);
+                            const uint32_t bgid = (uint32_t)b0.w, bkgb = (uint32_t)b1.x, bmask = (uint32_t)b1.y, bsrc = (uint32_t)b1.z;
+                            // candidate_geom with the slot test written as "the owner cell folds to the run's cell"
+                            const int32_t ox = max(ra.sx, b0.x), oy = max(ra.sy, b0.y);
+                            const bool first_hi = ra.gid > bgid;
+                            const uint32_t mask_hi = first_hi ? ra.mask : bmask, group_lo = ((first_hi ? bkgb : ra.kgb) >> 8) & 31u;
+                            const bool geom_ok = (ox < min(aex, bex)) & (oy < min(aey, bey)) & (((uint32_t)ox & fold_x) == cell_x) & (((uint32_t)oy & fold_y) == cell_y) &
+                                                 (ox >= a.sv.cd.col_lo) & (ox < a.sv.cd.col_hi) & (((mask_hi >> group_lo) & 1u) != 0u);
+                            n_pairs += 1;
+                            if (!geom_ok) continue;
+                            n_col += 1;
+                            bool pass = true;
+                            if (!LIST) {
+                                const TileRec& rb = s_rec[kb];
+                                const bool touch = (ra.r - rb.l >= 0.0) & (ra.t - rb.b >= 0.0) & (rb.r - ra.l >= 0.0) & (rb.t - ra.b >= 0.0);
+                                pass = touch | !(ra.dur_key == rb.dur_key);  // swept_filter_pass (narrowphase.cuh)
                             }
+                            if (pass) mine_q[my_q++] = first_hi ? make_uint2(ra.src, bsrc) : make_uint2(bsrc, ra.src);
                         }
                     }
-                    __syncthreads();
+                    if (p == p_end) {
+                        e += 32;
+                        fresh = true;
+                    }
                 }
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    s_nq = 0;
-                    s_any = 0;
+                // ---- survivors of the round out: one reservation per warp, consecutive 8-byte items ----
+                uint32_t inc = my_q;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += u;
                 }
-                __syncthreads();
-                if (!done) s_any = 1u;
-                __syncthreads();
-                if (!s_any) break;
+                const uint32_t n_q = __shfl_sync(0xffffffffu, inc, 31);
+                if (n_q) {
+                    unsigned long long at = 0;
+                    if (lane == 0) at = atomicAdd(&a.sv.ctr->n_surv, (unsigned long long)n_q);
+                    at = __shfl_sync(0xffffffffu, at, 0) + (inc - my_q);
+#pragma unroll
+                    for (uint32_t j = 0; j < kTileIter; ++j)
+                        if (j < my_q && at + j < a.surv.cap) a.surv.items[at + j] = mine_q[j];
+                }
+                if (!__any_sync(0xffffffffu, e < n_ent)) break;
             }
+            __syncwarp();
         }
-        __syncthreads();
+        __syncwarp();
     }
-    flush_events();
-    best = block_min(best);
-    const unsigned long long col_tot = block_sum(n_col), ent_tot = block_sum(n_entries), cell_tot = block_sum(n_cells), pair_tot = block_sum(n_pairs);
+    const unsigned long long col_tot = block_sum(n_col), ent_tot = block_sum((unsigned long long)n_entries), cell_tot = block_sum((unsigned long long)n_cells),
+                             pair_tot = block_sum(n_pairs);
     if (threadIdx.x == 0 && !LIST) {
-        a.sv.partial[a.partial_at + blockIdx.x] = best;
         if (col_tot) atomicAdd(&a.sv.ctr->n_collide, col_tot);
         if (ent_tot) atomicAdd(&a.sv.ctr->n_entries, ent_tot);
         if (cell_tot) atomicAdd(&a.sv.ctr->n_cells, cell_tot);
         if (pair_tot) atomicAdd(&a.sv.ctr->n_tile_pairs, pair_tot);
     }
+}
+
+// The solve stage of the tile path: the survivors (collide_time), then the overlapping pairs (separate_time; their records
+// are gathered like in k_solve), then k_solve's epilogue: block minima, counters, and the last block reduces every partial
+// minimum of the step and publishes the result.
+// LIST: the survivors that are not overlapping already are listed as (gid hi, gid lo); nothing else happens.
+template <bool LIST>
+__global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_tile_finish(const TileSolveArgs ta, uint2* list_out, unsigned long long* n_list, unsigned long long cap_list) {
+    const SolveArgs& a = ta.sv;
+    __shared__ PairEvent s_ev[kSolveBuf];
+    __shared__ uint32_t s_n;
+    __shared__ unsigned long long s_base;
+    MinKey best{kKeyMax, kKeyMax};
+    uint32_t n_sep = 0;
+    int32_t n_col = 0;  // net: minus the overlapping pairs that are candidates (the tile kernel counted every pair passing candidate_geom)
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const uint32_t n_surv = (uint32_t)min(a.ctr->n_surv, (unsigned long long)ta.surv.cap);
+    const uint32_t total = n_surv + (LIST ? 0u : a.n_ov);
+    const uint32_t n_local = a.ctr->n_local;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    auto flush = [&]() {  // all threads
+        __syncthreads();
+        const uint32_t n_ev = s_n;
+        if (n_ev) {
+            if (threadIdx.x == 0) s_base = atomicAdd(&a.ctr->n_pair_events, (unsigned long long)n_ev);
+            __syncthreads();
+            const unsigned long long pos = s_base;
+            for (uint32_t k = threadIdx.x; k < n_ev; k += blockDim.x)
+                if (pos + k < a.cap_events) a.events[pos + k] = s_ev[k];
+            __syncthreads();
+            if (threadIdx.x == 0) s_n = 0;
+            __syncthreads();
+        }
+    };
+    uint32_t pending_rounds = 0;
+    const double T = a.dyn->T;
+    const uint64_t keep = l2_policy_evict_last();
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
+        const uint32_t p = base + threadIdx.x;
+        if (p < n_surv) {
+            const uint2 it = __ldg(ta.surv.items + p);
+            RecHead hh, hl;
+            DurHb dh, dl;
+            load_source(ta, it.x, T, &hh, &dh);
+            load_source(ta, it.y, T, &hl, &dl);
+            if (!is_overlapping(a.cd, hh, hl, true)) {
+                if (LIST) {
+                    const unsigned long long pos = warp_agg_claim(n_list);
+                    if (pos < cap_list) list_out[pos] = make_uint2(hh.gid, hl.gid);
+                } else {
+                    PairEvent ev;
+                    if (solve_pair(a, T, hh, dh, hl, dl, true, &ev, &best)) s_ev[atomicAdd(&s_n, 1u)] = ev;
+                }
+            }
+        } else if (p < total) {
+            // an overlapping pair (gid hi, gid lo): separate_time (collider.rs:329-339)
+            const uint2 pr = a.ov_pairs[p - n_surv];
+            uint32_t ia, ib;
+            if (gid_lookup(a, n_local, pr.x, &ia) && gid_lookup(a, n_local, pr.y, &ib)) {
+                RecHead ha, hb;
+                DurHb da, db;
+                load_rec_keep(a.rec, ia, keep, &ha, &da);
+                load_rec_keep(a.rec, ib, keep, &hb, &db);
+                const int32_t owner_col = max(ha.sx, hb.sx);
+                if (owner_col >= a.col_lo && owner_col < a.col_hi) {
+                    n_col -= overlap_pair_is_candidate(a.cd, ha, hb);
+                    const DurHb B = advanced(db, 0.0);  // the partner is `other.hitbox_at_time(T)` (collider.rs:478-486)
+                    const double delay = separate_time(da, B, a.padding);
+                    if (delay != delay) report_error(a.ctr, kFNan, ha.gid);
+                    n_sep += 1;
+                    const double t = T + delay;
+                    if (t < kHighTime) {
+                        const uint32_t low = hb.gid;  // Separate: no collide bit
+                        s_ev[atomicAdd(&s_n, 1u)] = PairEvent{t, ha.gid, low};
+                        const MinKey k{time_key(t), kPairClass | ((uint64_t)ha.gid << 32) | low};
+                        if (key_less(k, best)) best = k;
+                    }
+                }
+            }
+        }
+        if (++pending_rounds == kSolveBuf / kThreads) {
+            flush();
+            pending_rounds = 0;
+        }
+    }
+    if (LIST) return;
+    flush();
+    solve_epilogue(a, best, n_sep, n_col);
 }
 
 }  // namespace cb200

@@ -322,9 +322,9 @@ def test_tile_path_is_taken_and_splits_or_falls_back_when_a_tile_does_not_fit(or
     if device_path != "tile":
         pytest.skip("tile path only")
     scene = scenes.uniform_density(20000, density=0.5, seed=scenes.SEED_BASE + 50)
-    for env, want_fallback in (({}, False), ({"CB200_TILE_CAP": "40"}, False), ({"CB200_TILE_VCAP": "2"}, True), ({"CB200_TILE_LOG2": "11", "CB200_TILE_CAP": "64"}, False),
-                               ({"CB200_TILE_QUEUE": "256", "CB200_TILE_LOG2": "8"}, False)):
-        for k in ("CB200_TILE_CAP", "CB200_TILE_VCAP", "CB200_TILE_LOG2", "CB200_TILE_QUEUE"):
+    for env, want_fallback in (({}, False), ({"CB200_TILE_CAP": "40"}, False), ({"CB200_TILE_VCAP": "2"}, True), ({"CB200_TILE_LOG2": "11", "CB200_TILE_CAP": "64", "CB200_TILE_VCAP": "400"}, False),
+                               ({"CB200_TILE_LOG2": "6"}, False)):
+        for k in ("CB200_TILE_CAP", "CB200_TILE_VCAP", "CB200_TILE_LOG2"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
