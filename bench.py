@@ -213,8 +213,9 @@ def main():
 class Job:
     """One workload on this rank: engine (single or sharded), step function, overlap hand-over."""
 
-    def __init__(self, cb, scenes, sharding, dist, workload, n, rank, world, local_rank, grid="", slab=0):
+    def __init__(self, cb, scenes, sharding, dist, workload, n, rank, world, local_rank, grid="", slab=0, drain=False):
         self.cb, self.rank, self.world, self.n, self.dist = cb, rank, world, n, dist
+        self.drain = drain and world == 1
         self.scene = make_workload(scenes, workload, n, rank, world)
         self.sh = None
         if world == 1:
@@ -222,6 +223,8 @@ class Job:
             if grid:
                 self.eng.set_grid(*[int(v) for v in grid.split(",")])
             self.eng.upload_state(**self.scene)
+            if self.drain:
+                self.eng.set_window_drain(True)
             self.step = self.eng.bulk_update
         else:
             # spatial sharding: one column strip of the world per rank; halo records and next-event keys are pushed
@@ -470,6 +473,7 @@ def _main(out):
     ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--no-collider-rows", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--drain", action="store_true", help="window drain: pair events inside each step's window processed on the device, overlap set device-resident")
     ap.add_argument("--grid", default="", help="force the device grid period: log2_w,log2_h")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -501,7 +505,7 @@ def _main(out):
 
     parity = None if args.no_parity else parity_check(cb, scenes, sharding, dist, args.workload, rank, world, local_rank)
 
-    job = Job(cb, scenes, sharding, dist, args.workload, n, rank, world, local_rank, grid=args.grid)
+    job = Job(cb, scenes, sharding, dist, args.workload, n, rank, world, local_rank, grid=args.grid, drain=args.drain)
     eng = job.eng
     job.first_step()
     eng.set_stage_timing(False)  # the timed region carries two CUDA events per step (start / end), none between the kernels;

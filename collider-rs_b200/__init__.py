@@ -58,6 +58,7 @@ class Event(C.Structure):
     _fields_ = [("time", C.c_double), ("a", C.c_uint64), ("b", C.c_uint64), ("kind", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+EVENT16_DTYPE = np.dtype([("time", "<f8"), ("a", "<u4"), ("b", "<u4")])
 EVENT_DTYPE = np.dtype([("time", "<f8"), ("a", "<u8"), ("b", "<u8"), ("kind", "<u4"), ("_pad", "<u4")])
 
 
@@ -91,7 +92,7 @@ EXPORTS = (
     "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
     "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_shard_set_slab", "cb200_set_stream", "cb200_shard_begin", "cb200_shard_finish",
     "cb200_shard_result", "cb200_set_resort_period", "cb200_resort_count", "cb200_event_sort_fallbacks", "cb200_set_stage_timing",
-    "cb200_shard_p2p_export", "cb200_shard_p2p_import", "cb200_shard_step", "cb200_shard_global_next", "cb200_shard_local_key", "cb200_shard_abort", "cb200_last_step_path", "cb200_tile_fallbacks", "cb200_get_tile",
+    "cb200_shard_p2p_export", "cb200_shard_p2p_import", "cb200_shard_step", "cb200_shard_global_next", "cb200_shard_local_key", "cb200_shard_abort", "cb200_stage_velocities", "cb200_fetch_events_begin", "cb200_fetch_events_end", "cb200_set_window_drain", "cb200_fetch_overlaps", "cb200_last_drain", "cb200_last_step_path", "cb200_tile_fallbacks", "cb200_get_tile",
     "cb200_collider_new", "cb200_collider_free", "cb200_collider_last_error", "cb200_collider_set_can_interact", "cb200_collider_time",
     "cb200_collider_next_time", "cb200_collider_set_time", "cb200_collider_next", "cb200_collider_get_hitbox", "cb200_collider_add_hitbox",
     "cb200_collider_set_hitbox_vel", "cb200_collider_remove_hitbox", "cb200_collider_get_overlaps", "cb200_collider_is_overlapping",
@@ -153,6 +154,12 @@ def load_library() -> C.CDLL:
     L.cb200_shard_local_key.restype = vp
     L.cb200_shard_abort.argtypes = [vp]
     L.cb200_last_step_path.argtypes = [vp]
+    L.cb200_stage_velocities.argtypes = [vp, C.POINTER(VelView)]
+    L.cb200_fetch_events_begin.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.cb200_fetch_events_end.argtypes = [vp]
+    L.cb200_set_window_drain.argtypes = [vp, i32]
+    L.cb200_fetch_overlaps.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
+    L.cb200_last_drain.argtypes = [vp] + [C.POINTER(u64)] * 5
     L.cb200_tile_fallbacks.argtypes = [vp]
     L.cb200_tile_fallbacks.restype = u64
     L.cb200_get_tile.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
@@ -372,6 +379,38 @@ class Engine:
         self._check(self._L.cb200_fetch_events(self._h, _ptr(buf), cap, offset, C.byref(got)))
         return buf[: got.value]
 
+    # ---- pipelined I/O (cb200_stage_velocities / cb200_fetch_events_begin / _end) ----
+    def stage_velocities(self, vel_x=None, vel_y=None, rsz_x=None, rsz_y=None, end_time_arr=None):
+        """Start the H2D copy of the NEXT step's velocities (pinned arrays: PinnedArray.array); the next bulk_update() without
+        velocity arguments consumes them."""
+        arrs = [vel_x, vel_y, rsz_x, rsz_y, end_time_arr]
+        self._staged_keep = [None if a is None else _col(a, np.float64, self.n) for a in arrs]
+        v = VelView(*[None if a is None else a.ctypes.data for a in self._staged_keep])
+        self._check(self._L.cb200_stage_velocities(self._h, C.byref(v)))
+
+    def fetch_events_begin(self, buf: np.ndarray) -> int:
+        """Queue the sort + download of the last step's events as EVENT16_DTYPE records into `buf` (ideally pinned); returns the
+        number of events that will be there once fetch_events_end() has returned."""
+        got = C.c_uint64()
+        self._check(self._L.cb200_fetch_events_begin(self._h, _ptr(buf), buf.shape[0], C.byref(got)))
+        return int(got.value)
+
+    def fetch_events_end(self):
+        self._check(self._L.cb200_fetch_events_end(self._h))
+
+    @staticmethod
+    def decode_events16(ev16: np.ndarray, ids: np.ndarray) -> np.ndarray:
+        """EVENT16_DTYPE records -> EVENT_DTYPE records (ids looked up from the labels; `ids` = the uploaded ascending id array)."""
+        out = np.zeros(len(ev16), dtype=EVENT_DTYPE)
+        reit = (ev16["a"] >> np.uint32(31)).astype(bool)
+        collide = (ev16["b"] >> np.uint32(31)).astype(bool)
+        la, lb = ev16["a"] & np.uint32(0x7FFFFFFF), ev16["b"] & np.uint32(0x7FFFFFFF)
+        out["time"] = ev16["time"]
+        out["a"] = ids[la]
+        out["b"] = np.where(reit, 0, ids[np.where(reit, 0, lb)])
+        out["kind"] = np.where(reit, EV_REITERATE, np.where(collide, EV_COLLIDE, EV_SEPARATE))
+        return out
+
     def set_resort_period(self, steps: int):
         self._check(self._L.cb200_set_resort_period(self._h, steps))
 
@@ -422,6 +461,24 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self._L.cb200_launch_count(self._h))
+
+    def set_window_drain(self, on: bool = True):
+        """Process the pair events inside every step's own window on the device and keep the overlap set there (cb200_set_window_drain)."""
+        self._check(self._L.cb200_set_window_drain(self._h, 1 if on else 0))
+
+    def fetch_overlaps(self):
+        n = C.c_uint64()
+        self._check(self._L.cb200_fetch_overlaps(self._h, None, None, 0, C.byref(n)))
+        a = np.zeros(n.value, dtype=np.uint64)
+        b = np.zeros(n.value, dtype=np.uint64)
+        if n.value:
+            self._check(self._L.cb200_fetch_overlaps(self._h, _ptr(a), _ptr(b), n.value, C.byref(n)))
+        return a, b
+
+    def last_drain(self) -> dict:
+        v = [C.c_uint64() for _ in range(5)]
+        self._check(self._L.cb200_last_drain(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("followup_events", "pairs_added", "pairs_removed", "pairs_now", "reiterates_in_windows"), [x.value for x in v]))
 
     def last_step_path(self) -> str:
         return {1: "tile", 0: "global"}.get(self._L.cb200_last_step_path(self._h), "none")

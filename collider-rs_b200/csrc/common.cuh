@@ -271,6 +271,7 @@ struct Counters {
     unsigned long long diff_hi, diff_lo;  // sort: OR of key differences
     unsigned long long n_sort_keys;
     unsigned long long n_tile_pairs;   // tile path: (entry, predecessor) pairs walked in shared memory (the step result's work items)
+    unsigned long long n_first_events; // pair events when the solve stage finished (the window drain appends its follow-ups behind them)
     unsigned long long n_surv;         // tile path: survivors of the swept-bounds filter queued for k_tile_finish (may exceed the buffer: overflow)
     unsigned int tile_fail;            // tile path: a visitor slab or a single cell exceeded its capacity -> the host repeats the step on the global path
     unsigned int pad1;

@@ -20,6 +20,7 @@
 #include "single.cuh"
 #include "sort.cuh"
 #include "tile.cuh"
+#include "drain.cuh"
 
 using namespace cb200;
 
@@ -176,6 +177,13 @@ struct cb200_ctx {
     uint32_t ov_pair_mask = 0;            // its words - 1
     uint32_t n_ov = 0, ov_bucket_mask = 0;
     DevBuf<uint64_t> ov_ida, ov_idb;
+    // window drain (drain.cuh): the overlap set lives on the device from step to step
+    bool ov_track = false, ov_ready = false;
+    OvDyn* d_ov = nullptr;
+    DevBuf<uint2> ov_pairs_new;   // compaction target
+    uint32_t ov_cap_pairs = 0, ov_n_keys = 0, ov_bit_words = 0;
+    uint32_t ov_list_len = 0;     // host mirror of OvDyn.n_pairs (the list also holds the pairs that separated since the last rebuild)
+    uint64_t drain_reiterates = 0;  // Reiterate events that fell inside a drained window (the drain is exact only without them)
 
     DevBuf<PairEvent> events;
     DevBuf<MinKey> partial;
@@ -196,7 +204,21 @@ struct cb200_ctx {
     DevBuf<uint32_t> rs_hist;
     DevBuf<uint32_t> bs_tab[5];  // bucket sort, one per recursion depth: counts / offsets, cursors, oversized buckets, range
     DevBuf<EventOut> ev_out;
+    Key128* sorted_keys = nullptr;  // where the last sort left the sorted keys (keys_a or keys_b)
     bool ev_sorted = false;
+    // pipelined I/O: compact events leave on their own copy stream (double-buffered), staged velocities arrive on another
+    DevBuf<Event16> ev16[2];
+    int ev16_parity = 0;
+    cudaStream_t d2h_stream = nullptr, h2d_stream = nullptr;
+    cudaEvent_t ev_sorted_done = nullptr, ev_staged_done = nullptr, ev_step_done = nullptr;
+    bool fetch_pending = false, fetch_oneshot_pending = false;
+    Event16* fetch_dst = nullptr;
+    uint64_t fetch_take = 0;
+    uint32_t fetch_nt = 0, fetch_np = 0;
+    uint64_t fetch_ns = 0;
+    DevBuf<double> nvel_staged[5];
+    bool vel_staged = false;
+    bool staged_has[5] = {};
     bool sort_oneshot = true;        // CB200_SORT=slow: recursive bucket sort / radix sort only (A/B and tests)
     uint32_t* h_sort_big = nullptr;  // pinned, mapped: k_bs_scan8's oversized-bucket report [1 + 2 * kBsMaxBig]
     uint32_t* d_sort_big = nullptr;  // its device alias
@@ -404,9 +426,16 @@ void cb200_destroy(cb200_ctx* c) {
     for (auto& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     c->slots.release(); c->chunk_base.release(); c->entries.release(); c->work.release(); c->work_count.release(); c->dense.release();
+    c->ov_pairs_new.release(); if (c->d_ov) cudaFree(c->d_ov);
     c->ov_pairs.release(); c->ov_table.release(); c->ov_bits.release(); c->ov_pair_bits.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
     c->tile_rows.release(); c->home.release(); c->vis_count.release(); c->vis.release(); c->surv.release();
+    for (auto& b : c->ev16) b.release();
+    for (auto& b : c->nvel_staged) b.release();
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    for (cudaEvent_t e : {c->ev_sorted_done, c->ev_staged_done, c->ev_step_done})
+        if (e) cudaEventDestroy(e);
     c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); for (auto& b : c->bs_tab) b.release(); c->imm_pairs.release(); if (c->d_n_imm) cudaFree(c->d_n_imm); c->ev_out.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->d_key) cudaFree(c->d_key);
@@ -549,6 +578,75 @@ int cb200_download_state(cb200_ctx* ctx, const cb200_state_out* o) {
     return CB200_OK;
 }
 
+static int gid_to_id_table(cb200_ctx* ctx, std::vector<uint64_t>& ids);
+static int compact_overlaps(cb200_ctx* ctx);
+static inline uint64_t id_of(const std::vector<uint64_t>& ids, uint32_t gid);
+
+// (Re)build the overlap hash table, the per-hitbox bits and the pair Bloom bits from the np (hi, lo) label pairs in ov_pairs.
+// With the window drain on, everything is sized with head-room (the set changes on the device from step to step).
+static int build_overlap_tables(cb200_ctx* ctx, uint32_t np) {
+    // cap_pairs: pairs the hash table and the Bloom bits are sized for
+    const uint32_t cap_pairs = ctx->ov_track ? (uint32_t)std::max<uint64_t>({4ull * np, (uint64_t)ctx->n / 8, 4096ull}) : np;
+    if (ctx->ov_track) {
+        // the list can take every pair the table is sized for plus every pair one step can add (one per pair event)
+        if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)ctx->n * 2 + 1024));
+        const size_t cap_list = (size_t)cap_pairs + ctx->events.cap;
+        CU(ctx->ov_pairs.reserve(cap_list, true, ctx->stream));
+        CU(ctx->ov_pairs_new.reserve(cap_list));
+        if (!ctx->d_ov) CU(cudaMalloc(&ctx->d_ov, sizeof(OvDyn)));
+        OvDyn init{};
+        init.n_pairs = np;
+        init.n_live = np;
+        CU(cudaMemcpyAsync(ctx->d_ov, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));  // (init is a stack object)
+        ctx->ov_list_len = np;
+    }
+    uint32_t cap = 1024;
+    while (cap < 2 * cap_pairs) cap <<= 1;
+    CU(ctx->ov_table.reserve(cap));
+    const size_t gid_space = ctx->sharded ? (size_t)ctx->id_space : std::max<size_t>(ctx->row_of.cap, ctx->n);
+    const size_t n_words = (gid_space + 31) / 32 + 1;
+    CU(ctx->ov_bits.reserve(n_words));
+    CU(cudaMemsetAsync(ctx->ov_bits.p, 0, n_words * 4, ctx->stream));
+    uint32_t pair_words = 1024;
+    while (pair_words < cap_pairs / 2u + 1u) pair_words <<= 1;  // >= 16 bits per pair
+    CU(ctx->ov_pair_bits.reserve(pair_words));
+    CU(cudaMemsetAsync(ctx->ov_pair_bits.p, 0, (size_t)pair_words * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->ov_table.p, 0xff, (size_t)cap * 8, ctx->stream));
+    if (np) {
+        k_overlap_insert<<<(np + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, np, ctx->ov_table.p, cap / 4 - 1, ctx->ov_bits.p, ctx->ov_pair_bits.p, pair_words - 1);
+        ctx->launches += 1;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaGetLastError());
+    ctx->n_ov = np;
+    ctx->ov_bucket_mask = cap / 4 - 1;
+    ctx->ov_pair_mask = pair_words - 1;
+    ctx->ov_cap_pairs = cap_pairs;
+    ctx->ov_n_keys = cap;
+    ctx->ov_bit_words = (uint32_t)n_words;
+    ctx->ov_ready = ctx->ov_track;
+    return CB200_OK;
+}
+
+// Window drain housekeeping: drop the pairs that separated since the last rebuild from the list and rebuild the tables.
+static int compact_overlaps(cb200_ctx* ctx) {
+    if (!(ctx->ov_track && ctx->ov_ready)) return CB200_OK;
+    const uint32_t len = ctx->ov_list_len;
+    uint32_t n_live = 0;
+    if (len) {
+        uint32_t* d_n = &ctx->d_ov->n_add;  // (a scratch word: zero between steps)
+        CU(cudaMemsetAsync(d_n, 0, 4, ctx->stream));
+        const OverlapSet ov{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, 1u, ctx->ov_pair_bits.p, ctx->ov_pair_mask};
+        k_ov_compact<<<(uint32_t)ctx->sm_count * 4u, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, len, ov, ctx->ov_pairs_new.p, d_n);
+        ctx->launches += 1;
+        CU(cudaMemcpyAsync(&n_live, d_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (n_live) CU(cudaMemcpyAsync(ctx->ov_pairs.p, ctx->ov_pairs_new.p, (size_t)n_live * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return build_overlap_tables(ctx, n_live);
+}
+
 int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_b, uint64_t n_pairs) {
     if (!ctx) return CB200_E_ARG;
     if (!ctx->have_state) return fail(ctx, CB200_E_STATE, "set_overlaps before upload_state");
@@ -557,38 +655,68 @@ int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_
     CU(cudaSetDevice(ctx->device));
     ctx->n_ov = 0;
     ctx->ov_bucket_mask = 0;
-    if (n_pairs == 0) return CB200_OK;
+    ctx->ov_ready = false;
+    if (n_pairs == 0) return ctx->ov_track ? build_overlap_tables(ctx, 0) : CB200_OK;
     const uint32_t np = (uint32_t)n_pairs;
     CU(ctx->ov_ida.reserve(np)); CU(ctx->ov_idb.reserve(np)); CU(ctx->ov_pairs.reserve(np));
-    uint32_t cap = 1024;
-    while (cap < 2 * np) cap <<= 1;
-    CU(ctx->ov_table.reserve(cap));
-    const size_t gid_space = ctx->sharded ? (size_t)ctx->id_space : std::max<size_t>(ctx->row_of.cap, ctx->n);
-    const size_t n_words = (gid_space + 31) / 32 + 1;
-    CU(ctx->ov_bits.reserve(n_words));
-    CU(cudaMemsetAsync(ctx->ov_bits.p, 0, n_words * 4, ctx->stream));
-    uint32_t pair_words = 1024;
-    while (pair_words < np / 2u + 1u) pair_words <<= 1;  // >= 16 bits per pair
-    CU(ctx->ov_pair_bits.reserve(pair_words));
-    CU(cudaMemsetAsync(ctx->ov_pair_bits.p, 0, (size_t)pair_words * 4, ctx->stream));
     CU(cudaMemcpyAsync(ctx->ov_ida.p, id_a, (size_t)np * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->ov_idb.p, id_b, (size_t)np * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(ctx->ov_table.p, 0xff, (size_t)cap * 8, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_ctr, 0, sizeof(Counters), ctx->stream));
     const unsigned long long big = ~0ull;
     CU(cudaMemcpyAsync(&ctx->d_ctr->err_slot, &big, 8, cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t blocks = (np + kThreads - 1) / kThreads;
     k_overlap_map_ids<<<blocks, kThreads, 0, ctx->stream>>>(ctx->sharded ? nullptr : ctx->ids.p, ctx->n, ctx->ov_ida.p, ctx->ov_idb.p, np, ctx->ov_pairs.p, ctx->d_ctr);
-    k_overlap_insert<<<blocks, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, np, ctx->ov_table.p, cap / 4 - 1, ctx->ov_bits.p, ctx->ov_pair_bits.p, pair_words - 1);
-    ctx->launches += 2;
+    ctx->launches += 1;
     Counters h;
     CU(cudaMemcpyAsync(&h, ctx->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
     if (h.err_flags) return fail(ctx, CB200_E_ARG, "set_overlaps: hitbox id not found (pair " + std::to_string(h.err_slot) + ")");
-    ctx->n_ov = np;
-    ctx->ov_bucket_mask = cap / 4 - 1;
-    ctx->ov_pair_mask = pair_words - 1;
+    return build_overlap_tables(ctx, np);
+}
+
+int cb200_set_window_drain(cb200_ctx* ctx, int on) {
+    if (!ctx) return CB200_E_ARG;
+    if (on && ctx->sharded) return fail(ctx, CB200_E_STATE, "the window drain runs on one device");
+    CU(cudaSetDevice(ctx->device));
+    const bool was = ctx->ov_track;
+    ctx->ov_track = on != 0;
+    ctx->ov_ready = false;
+    if (ctx->ov_track && !was && ctx->have_state) return build_overlap_tables(ctx, ctx->n_ov);  // (the pairs uploaded so far stay)
+    return CB200_OK;
+}
+
+// The overlap set as the device holds it (with the window drain: as of the end of the last drained window).
+int cb200_fetch_overlaps(cb200_ctx* ctx, uint64_t* id_a, uint64_t* id_b, uint64_t cap, uint64_t* n_out) {
+    if (!ctx) return CB200_E_ARG;
+    if (ctx->sharded) return fail(ctx, CB200_E_STATE, "fetch_overlaps is a one-device view");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->ov_track && ctx->ov_ready && ctx->ov_list_len != ctx->n_ov) {
+        int rc = compact_overlaps(ctx);  // (the list also holds the pairs that separated since the last rebuild)
+        if (rc != CB200_OK) return rc;
+    }
+    const uint64_t total = ctx->n_ov;
+    if (n_out) *n_out = total;
+    if (cap == 0 || total == 0) return CB200_OK;
+    std::vector<uint2> h(total);
+    std::vector<uint64_t> ids;
+    int rc = gid_to_id_table(ctx, ids);
+    if (rc != CB200_OK) return rc;
+    CU(cudaMemcpy(h.data(), ctx->ov_pairs.p, total * sizeof(uint2), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < total && i < cap; ++i) {
+        if (id_a) id_a[i] = id_of(ids, h[i].x);
+        if (id_b) id_b[i] = id_of(ids, h[i].y);
+    }
+    return CB200_OK;
+}
+
+int cb200_last_drain(const cb200_ctx* ctx, uint64_t* followups, uint64_t* added, uint64_t* removed, uint64_t* pairs_now, uint64_t* reiterates_in_windows) {
+    if (!ctx) return CB200_E_ARG;
+    if (followups) *followups = ctx->last.n_followups;
+    if (added) *added = ctx->last.n_added;
+    if (removed) *removed = ctx->last.n_removed;
+    if (pairs_now) *pairs_now = ctx->n_ov;
+    if (reiterates_in_windows) *reiterates_in_windows = ctx->drain_reiterates;
     return CB200_OK;
 }
 
@@ -606,6 +734,16 @@ static int dbg_sync(cb200_ctx* ctx, const char* stage) {
 static int stage_vel(cb200_ctx* ctx, const cb200_vel_view* vel, const double** nv) {
     const uint32_t n = ctx->n;
     for (int k = 0; k < 5; ++k) nv[k] = nullptr;
+    if (!vel && ctx->vel_staged) {
+        // velocities staged ahead of time by cb200_stage_velocities (their H2D copy ran beside the previous step)
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_staged_done, 0));
+        for (int k = 0; k < 5; ++k) {
+            std::swap(ctx->nvel[k], ctx->nvel_staged[k]);
+            if (ctx->staged_has[k]) nv[k] = ctx->nvel[k].p;
+        }
+        ctx->vel_staged = false;
+        return CB200_OK;
+    }
     if (vel && n) {
         const double* src[5] = {vel->vel_x, vel->vel_y, vel->rsz_x, vel->rsz_y, vel->end_time};
         for (int k = 0; k < 5; ++k)
@@ -885,6 +1023,40 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     return CB200_OK;
 }
 
+// Window drain (drain.cuh) behind the solve stage: chains of the step's pair events up to the step's end time, the overlap
+// set updated in place — one launch, which does nothing if the step is going to be re-run.
+static int enqueue_drain(cb200_ctx* ctx, bool is_tile) {
+    if (!(ctx->ov_track && ctx->ov_ready) || ctx->sharded || ctx->add_mode) return CB200_OK;
+    DrainArgs d{};
+    d.s = cols_of(ctx);
+    d.row_of = ctx->row_of.p;
+    d.n_rows = ctx->n;
+    d.n_labels = (uint32_t)std::min<size_t>(ctx->row_of.cap, 0xffffffffu);
+    d.dyn = ctx->d_dyn;
+    d.padding = ctx->padding;
+    d.events = ctx->events.p;
+    d.cap_events = (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu);
+    d.ctr = ctx->d_ctr;
+    d.table = ctx->ov_table.p;
+    d.bucket_mask = ctx->ov_bucket_mask;
+    d.bits = ctx->ov_bits.p;
+    d.pair_bits = ctx->ov_pair_bits.p;
+    d.pair_mask = ctx->ov_pair_mask;
+    d.pairs = ctx->ov_pairs.p;
+    d.cap_pairs = (uint32_t)std::min<size_t>(ctx->ov_pairs.cap, 0x7fffffffu);
+    d.ov = ctx->d_ov;
+    d.result = ctx->d_res;
+    d.cap_entries = (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu);
+    d.seg_cap = (uint32_t)std::min<size_t>(ctx->work.cap / kWorkLists, 0x7fffffffu);
+    d.cap_surv = (uint32_t)std::min<size_t>(ctx->surv.cap, 0x7fffffffu);
+    d.is_tile = is_tile ? 1u : 0u;
+    d.work_count = ctx->work_count.p;
+    k_drain_chains<<<(uint32_t)ctx->sm_count * 2u, kThreads, 0, ctx->stream>>>(d);
+    ctx->launches += 1;
+    DBG_SYNC("drain");
+    return CB200_OK;
+}
+
 // The arguments of the solve-stage kernels (k_solve, k_solve_dense, k_tile_solve) for the current step.
 static SolveArgs solve_args_of(cb200_ctx* ctx, const ShardGeom& sh, const VisSpace& vs) {
     const bool use_map = ctx->sharded && ctx->n_ov;
@@ -892,12 +1064,15 @@ static SolveArgs solve_args_of(cb200_ctx* ctx, const ShardGeom& sh, const VisSpa
     cd.geom = ctx->geom;
     cd.col_lo = sh.col_lo;
     cd.col_hi = sh.col_hi;
-    cd.ov = OverlapSet{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, ctx->n_ov, ctx->ov_pair_bits.p, ctx->ov_pair_mask};
+    const bool track = ctx->ov_track && ctx->ov_ready;  // (the pair count lives on the device: the table is consulted whenever it exists)
+    cd.ov = OverlapSet{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, track ? 1u : ctx->n_ov, ctx->ov_pair_bits.p, ctx->ov_pair_mask};
     SolveArgs sv{};
     sv.cd = cd;
     sv.work = work_lists_of(ctx);
     sv.ov_pairs = ctx->ov_pairs.p;
-    sv.n_ov = ctx->n_ov;
+    sv.n_ov = track ? (uint32_t)std::min<size_t>(ctx->ov_pairs.cap, 0x7fffffffu) : ctx->n_ov;  // (tracked: the capacity; the length is on the device)
+    sv.n_ov_dev = track ? &ctx->d_ov->n_pairs : nullptr;
+    sv.ov_live_check = track ? 1 : 0;
     sv.rec = ctx->rec.p;
     sv.dyn = ctx->d_dyn;
     sv.padding = ctx->padding;
@@ -993,6 +1168,10 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount, bool bin_only
     else k_solve<false, false><<<ctx->grid_s, kThreads, 0, ctx->stream>>>(sv);
     DBG_SYNC("k_solve");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
+    {
+        int rc = enqueue_drain(ctx, false);
+        if (rc != CB200_OK) return rc;
+    }
     CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
     ctx->launches += 2;
     return CB200_OK;
@@ -1030,7 +1209,7 @@ static int enqueue_tile_step(cb200_ctx* ctx, bool do_rebase, const double* const
     a.partial_base = 0;
     a.ov_bits = ctx->ov_bits.p;
     TileTables tt{ctx->tile_rows.p, ctx->home.p, ctx->vis_count.p, ctx->vis.p, ctx->tile_vcap, ctx->tgeom.n_tiles};
-    TileStageArgs ta{ctx->tgeom, tt, ctx->n_ov ? 1u : 0u};
+    TileStageArgs ta{ctx->tgeom, tt, (ctx->n_ov || (ctx->ov_track && ctx->ov_ready)) ? 1u : 0u};
     ctx->grid_a = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, ctx->sm_count * ctx->per_sm_a));
     k_stage_a_tile<<<ctx->grid_a, kThreads, 0, ctx->stream>>>(a, ta);
     ctx->launches += 1;
@@ -1064,6 +1243,10 @@ static int enqueue_tile_step(cb200_ctx* ctx, bool do_rebase, const double* const
     ctx->launches += 1;
     DBG_SYNC("k_tile_finish");
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_TAIL], ctx->stream));
+    {
+        int rc = enqueue_drain(ctx, true);
+        if (rc != CB200_OK) return rc;
+    }
     CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
     return CB200_OK;
 }
@@ -1099,6 +1282,27 @@ static int complete_step(cb200_ctx* ctx, double time, bool* again) {
     ctx->ev_sorted = false;
     const Counters& c = ctx->last.ctr;
     *again = false;
+    if (ctx->ov_track && ctx->ov_ready && !ctx->sharded && !ctx->add_mode && (ctx->last.drain_flags & kDrainGo)) {
+        // the window drain ran: the overlap set now holds the pairs overlapping at the end of the window
+        ctx->n_ov = ctx->last.ov_live_now;
+        ctx->ov_list_len = ctx->last.ov_pairs_now;
+        ctx->drain_reiterates += c.n_solitaire;
+        if (ctx->last.drain_flags & (kDrainOverflow | kDrainLongChain))
+            return fail(ctx, CB200_E_STATE, ((ctx->last.drain_flags & kDrainOverflow)
+                                                 ? std::string("window drain: a buffer overflowed; the overlap set is no longer in step — call cb200_set_overlaps")
+                                                 : std::string("window drain: a pair changed state more than 16 times inside one window")) +
+                                                " (flags " + std::to_string(ctx->last.drain_flags) + ", list " + std::to_string(ctx->last.ov_pairs_now) + " of " +
+                                                std::to_string(ctx->ov_pairs.cap) + ", live " + std::to_string(ctx->last.ov_live_now) + ", added " + std::to_string(ctx->last.n_added) +
+                                                ", follow-ups " + std::to_string(ctx->last.n_followups) + ", pair events " + std::to_string(c.n_pair_events) + " of " +
+                                                std::to_string(ctx->events.cap) + ")");
+        // every pair ever listed holds a table slot: rebuild compactly when the table passes half load, when the dead pairs
+        // outnumber the live ones, or when the list could not take another step's worth of new pairs
+        const uint32_t dead = ctx->ov_list_len - ctx->n_ov;
+        if (ctx->ov_list_len > ctx->ov_cap_pairs || dead > std::max<uint32_t>(ctx->n_ov, 4096u) || (size_t)ctx->ov_list_len + ctx->events.cap > ctx->ov_pairs.cap) {
+            int rc = compact_overlaps(ctx);
+            if (rc != CB200_OK) return rc;
+        }
+    }
     if (ctx->step_is_tile) {
         if (c.tile_fail) {
             // a visitor slab or a single cell did not fit: this step, and every step up to the next re-sort, takes the global path
@@ -1120,6 +1324,10 @@ static int complete_step(cb200_ctx* ctx, double time, bool* again) {
             *again = true;
         }
         if (*again) CU(cudaMemsetAsync(ctx->vis_count.p, 0, 2 * (size_t)ctx->tgeom.n_tiles * 4, ctx->stream));
+        if (*again && ctx->ov_track && ctx->ov_ready) {  // (the drain's list is sized from the event buffer)
+            CU(ctx->ov_pairs.reserve((size_t)ctx->ov_cap_pairs + ctx->events.cap, true, ctx->stream));
+            CU(ctx->ov_pairs_new.reserve((size_t)ctx->ov_cap_pairs + ctx->events.cap));
+        }
         return CB200_OK;
     }
     if (c.overflow_entries || c.n_entries > ctx->entries.cap) {
@@ -1134,6 +1342,10 @@ static int complete_step(cb200_ctx* ctx, double time, bool* again) {
     if (c.n_pair_events > ctx->events.cap) {
         CU(ctx->events.reserve((size_t)c.n_pair_events + c.n_pair_events / 4 + 1024));
         *again = true;
+    }
+    if (*again && ctx->ov_track && ctx->ov_ready) {  // (the drain's list is sized from the event buffer)
+        CU(ctx->ov_pairs.reserve((size_t)ctx->ov_cap_pairs + ctx->events.cap, true, ctx->stream));
+        CU(ctx->ov_pairs_new.reserve((size_t)ctx->ov_cap_pairs + ctx->events.cap));
     }
     return CB200_OK;
 }
@@ -1211,7 +1423,7 @@ static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
             h *= 0x100000001b3ull;
         }
     };
-    mix(ctx->n); mix((uint64_t)ctx->geom.lw << 8 | (uint64_t)ctx->geom.lh); mix(ctx->n_ov); mix(ctx->ov_bucket_mask); mix(ctx->ov_pair_mask);
+    mix(ctx->n); mix((uint64_t)ctx->geom.lw << 8 | (uint64_t)ctx->geom.lh); mix((ctx->ov_track && ctx->ov_ready) ? 0xffffffffu : ctx->n_ov); mix(ctx->ov_bucket_mask); mix(ctx->ov_pair_mask);
     for (auto& b : ctx->col) mix((uint64_t)(uintptr_t)b.p);
     const void* ptrs[] = {ctx->kind.p, ctx->reit.p, ctx->group.p, ctx->mask.p, ctx->label.p, ctx->row_of.p, ctx->rec.p, ctx->bink.p, ctx->slots.p,
                           ctx->chunk_base.p, ctx->entries.p, ctx->work.p, ctx->work_count.p, ctx->events.p, ctx->partial.p, ctx->ov_pairs.p,
@@ -1232,6 +1444,11 @@ static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
     if (const char* d = getenv("CB200_DBG_S")) mix((uint64_t)atoi(d) + 31);
     mix(ctx->ld256 ? 257u : 129u);
     mix(ctx->solve_two_phase ? 2u : 1u);
+    if (ctx->ov_track && ctx->ov_ready) {
+        mix(0xd7a1); mix(ctx->ov_cap_pairs); mix(ctx->ov_n_keys); mix(ctx->ov_bit_words); mix(ctx->ov_pairs.cap);
+        const void* dp[] = {ctx->d_ov, ctx->surv.p};
+        for (const void* q : dp) mix((uint64_t)(uintptr_t)q);
+    }
     if (ctx->step_is_tile) {
         mix(0x711e); mix((uint64_t)ctx->tgeom.tj); mix(ctx->tile_vcap); mix(ctx->tile_cap_rec); mix(ctx->tile_cap_ent); mix(ctx->grid_t);
         const void* tp[] = {ctx->tile_rows.p, ctx->home.p, ctx->vis_count.p, ctx->vis.p, ctx->surv.p};
@@ -1312,6 +1529,8 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
     int rc = stage_vel(ctx, vel, nv);
     if (rc != CB200_OK) return rc;
     if ((rc = prepare_buffers(ctx)) != CB200_OK) return rc;
+    if (ctx->ov_track && !ctx->ov_ready && (rc = build_overlap_tables(ctx, ctx->n_ov)) != CB200_OK) return rc;
+    if (ctx->ov_track && vel && vel->end_time) return fail(ctx, CB200_E_ARG, "the window drain needs one end time for the whole step (vel->end_time must be NULL)");
     ctx->tile_steps += 1;
     if ((rc = set_step_dyn(ctx, time, end_time)) != CB200_OK) return rc;
     // A step is re-run (without the rebase) when a buffer had to grow — or, on the tile path, when a tile exceeded its
@@ -1714,6 +1933,7 @@ static int enqueue_sort_oneshot(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, u
     k_bs2_scatter<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, range, log2_buckets, cursor, tmp);
     k_bs_local<<<std::min<uint32_t>((n_buckets + 7) / 8, (uint32_t)ctx->sm_count * 8u), 256, 0, ctx->stream>>>(tmp, count, n_buckets, keys);
     k_decode_events<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p, ctx->last_add_mode ? 1 : 0);
+    ctx->sorted_keys = keys;
     ctx->launches += 6;
     CU(cudaGetLastError());
     return CB200_OK;
@@ -1748,6 +1968,7 @@ static int sort_events_slow(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, uint6
         }
     }
     k_decode_events<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(nt, in, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p, ctx->last_add_mode ? 1 : 0);
+    ctx->sorted_keys = in;
     ctx->launches += 1;
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
@@ -1810,6 +2031,104 @@ int cb200_fetch_events(cb200_ctx* ctx, cb200_event* buf, uint64_t cap, uint64_t 
     int rc = sort_events_to(ctx, reinterpret_cast<EventOut*>(buf), offset, cap, &take);
     if (rc != CB200_OK) return rc;
     if (n_out) *n_out = take;
+    return CB200_OK;
+}
+
+// ---- pipelined I/O -----------------------------------------------------------------------------------------
+static int ensure_io_streams(cb200_ctx* ctx) {
+    if (ctx->d2h_stream) return CB200_OK;
+    CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->ev_sorted_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_staged_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_step_done, cudaEventDisableTiming));
+    return CB200_OK;
+}
+
+// New velocities for the NEXT bulk step, copied host -> device on the context's upload stream while the current step (or
+// the event download of the previous one) is still running.  Consumed by the next cb200_bulk_update called with vel == NULL.
+int cb200_stage_velocities(cb200_ctx* ctx, const cb200_vel_view* vel) {
+    if (!ctx || !vel) return CB200_E_ARG;
+    if (!ctx->have_state) return fail(ctx, CB200_E_STATE, "stage_velocities before upload_state");
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_io_streams(ctx);
+    if (rc != CB200_OK) return rc;
+    const uint32_t n = ctx->n;
+    const double* src[5] = {vel->vel_x, vel->vel_y, vel->rsz_x, vel->rsz_y, vel->end_time};
+    for (int k = 0; k < 5; ++k) {
+        ctx->staged_has[k] = src[k] != nullptr;
+        if (!src[k] || !n) continue;
+        CU(ctx->nvel_staged[k].reserve(n));
+        CU(cudaMemcpyAsync(ctx->nvel_staged[k].p, src[k], (size_t)n * 8, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    }
+    CU(cudaEventRecord(ctx->ev_staged_done, ctx->h2d_stream));
+    ctx->vel_staged = true;
+    return CB200_OK;
+}
+
+// The sorted events of the last step in the compact form (cb200_event16), downloaded on the context's copy stream: returns
+// as soon as the sort and the copy are queued, so the caller can start the next bulk step; cb200_fetch_events_end waits for
+// the copy.  *n_out = events that will be in buf[0 .. *n_out) (at most cap).
+int cb200_fetch_events_begin(cb200_ctx* ctx, cb200_event16* buf, uint64_t cap, uint64_t* n_out) {
+    if (!ctx) return CB200_E_ARG;
+    if (!ctx->have_step) return fail(ctx, CB200_E_STATE, "fetch_events before bulk_update");
+    if (ctx->fetch_pending) return fail(ctx, CB200_E_STATE, "cb200_fetch_events_end the pending download first");
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_io_streams(ctx);
+    if (rc != CB200_OK) return rc;
+    static_assert(sizeof(cb200_event16) == sizeof(Event16), "compact event layout");
+    const Counters& c = ctx->last.ctr;
+    const uint64_t total = c.n_pair_events + c.n_solitaire;
+    if (total >= 0xffffffffull) return fail(ctx, CB200_E_STATE, "too many events to sort");
+    const uint32_t nt = (uint32_t)total;
+    const uint64_t take = buf ? std::min<uint64_t>(total, cap) : 0;
+    if (n_out) *n_out = take;
+    ctx->ev16_parity ^= 1;
+    DevBuf<Event16>& dst = ctx->ev16[ctx->ev16_parity];
+    ctx->fetch_oneshot_pending = false;
+    if (nt) {
+        CU(ctx->keys_a.reserve(nt)); CU(ctx->keys_b.reserve(nt)); CU(dst.reserve(nt));
+        if (!ctx->ev_sorted) {
+            ctx->n_ev_sorted = total;
+            ctx->h_sort_big[0] = 0;
+            if (ctx->sort_oneshot) {
+                CU(ctx->ev_out.reserve(nt));
+                if ((rc = enqueue_sort_oneshot(ctx, nt, (uint32_t)c.n_pair_events, c.n_solitaire)) != CB200_OK) return rc;
+                ctx->fetch_oneshot_pending = true;  // (whether it held is known once the stream has run: checked in _end)
+            } else {
+                CU(ctx->ev_out.reserve(nt));
+                if ((rc = sort_events_slow(ctx, nt, (uint32_t)c.n_pair_events, c.n_solitaire)) != CB200_OK) return rc;
+            }
+            ctx->ev_sorted = true;
+        }
+        // the sorted keys are in keys_a: decode them once more into the compact form
+        k_decode_events16<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(nt, ctx->sorted_keys, dst.p, ctx->last_add_mode ? 1 : 0);
+        ctx->launches += 1;
+    }
+    CU(cudaEventRecord(ctx->ev_sorted_done, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_sorted_done, 0));
+    if (take) CU(cudaMemcpyAsync(buf, dst.p, take * sizeof(Event16), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    ctx->fetch_pending = true;
+    ctx->fetch_dst = reinterpret_cast<Event16*>(buf);
+    ctx->fetch_take = take;
+    ctx->fetch_nt = nt;
+    ctx->fetch_np = (uint32_t)c.n_pair_events;
+    ctx->fetch_ns = c.n_solitaire;
+    return CB200_OK;
+}
+
+int cb200_fetch_events_end(cb200_ctx* ctx) {
+    if (!ctx) return CB200_E_ARG;
+    if (!ctx->fetch_pending) return CB200_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->d2h_stream));
+    ctx->fetch_pending = false;
+    if (ctx->fetch_oneshot_pending && ctx->h_sort_big[0] != 0) {
+        // the one-shot sort met an oversized bucket: the download holds a partially sorted list.  This can only be repaired
+        // while the step's events are still the last step's — the caller must not have started another step
+        ctx->sort_fallbacks += 1;
+        return fail(ctx, CB200_E_STATE, "the one-shot event sort met an oversized bucket (a heavy tie at a later time): fetch this step's events with cb200_fetch_events instead");
+    }
     return CB200_OK;
 }
 

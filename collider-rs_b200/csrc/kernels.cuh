@@ -1151,13 +1151,18 @@ struct StepResultDev {
     uint64_t next_tie;  // MinKey.tie of the minimum (kKeyMax if none)
     uint64_t next_id_a, next_id_b;  // its HbIds (label -> id), so the host needs no further copy
     Counters ctr;
+    // window drain (drain.cuh), written by k_drain_commit
+    unsigned long long n_followups;
+    uint32_t ov_pairs_now, drain_flags, n_removed, n_added, ov_live_now, pad;
 };
 
 struct SolveArgs {
     CandArgs cd;             // the candidate test of a work item
     WorkLists work;          // k_enum_pairs' lists
     const uint2* ov_pairs;
-    uint32_t n_ov;
+    uint32_t n_ov;             // overlapping pairs (with n_ov_dev: the capacity of the list)
+    const uint32_t* n_ov_dev;  // window drain: the pair count lives on the device (drain.cuh OvDyn.n_pairs); null = n_ov
+    int ov_live_check;         // window drain: the list also holds pairs that separated since the last rebuild — skip those (table lookup)
     const HbRec* rec;
     const StepDyn* dyn;
     double padding;
@@ -1232,6 +1237,7 @@ __device__ __forceinline__ void solve_epilogue(const SolveArgs& a, MinKey best, 
     }
     best = block_min(best);
     if (threadIdx.x == 0) {
+        a.ctr->n_first_events = a.ctr->n_pair_events;  // (every block of the solve stage has flushed its events)
         a.result->next_time = (best.t == kKeyMax && best.tie == kKeyMax) ? cb_inf() : key_time(best.t);
         a.result->next_tie = best.tie;
         {
@@ -1258,7 +1264,7 @@ __device__ __forceinline__ void solve_epilogue(const SolveArgs& a, MinKey best, 
         out.err_flags = c->err_flags; out.scan_ticket = c->scan_ticket; out.overflow_entries = c->overflow_entries;
         out.done_blocks = c->done_blocks; out.n_local = c->n_local; out.overflow_send = c->overflow_send;
         out.diff_hi = 0; out.diff_lo = 0; out.n_sort_keys = 0;
-        out.n_tile_pairs = c->n_tile_pairs; out.n_surv = c->n_surv; out.tile_fail = c->tile_fail; out.pad1 = 0;
+        out.n_tile_pairs = c->n_tile_pairs; out.n_surv = c->n_surv; out.tile_fail = c->tile_fail; out.pad1 = 0; out.n_first_events = c->n_pair_events;
         out.n_work += out.n_tile_pairs;
         a.result->ctr = out;
         __threadfence_system();
@@ -1288,7 +1294,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
     if (threadIdx.x == 0) s_n = 0;
     work_index_build(a.work, &s_idx);
     const uint32_t n_cand = s_idx.first[kWorkLists];
-    const uint32_t total = n_cand + a.n_ov;
+    const uint32_t total = n_cand + (a.n_ov_dev ? min(*a.n_ov_dev, a.n_ov) : a.n_ov);
     const uint32_t n_local = a.ctr->n_local;
     const uint32_t stride = gridDim.x * blockDim.x;
     auto flush = [&]() {  // all threads
@@ -1316,7 +1322,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
             bool present = true;
             if (sep) {
                 const uint2 pr = a.ov_pairs[p - n_cand];
-                present = gid_lookup(a, n_local, pr.x, &ia) && gid_lookup(a, n_local, pr.y, &ib);
+                present = (!a.ov_live_check || overlap_contains(a.cd.ov, pr.x, pr.y)) && gid_lookup(a, n_local, pr.x, &ia) && gid_lookup(a, n_local, pr.y, &ib);
             } else {
                 const WorkItem it = work_item_at(a.work, &s_idx, p);
                 ia = it.a; ib = it.b; slot = it.slot;
@@ -1414,7 +1420,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve2(const Solve
     }
     work_index_build(a.work, &s_idx);  // (barriers inside)
     const uint32_t n_cand = s_idx.first[kWorkLists];
-    const uint32_t total = n_cand + a.n_ov;
+    const uint32_t total = n_cand + (a.n_ov_dev ? min(*a.n_ov_dev, a.n_ov) : a.n_ov);
     const uint32_t n_local = a.ctr->n_local;
     const uint32_t stride = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
@@ -1480,7 +1486,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve2(const Solve
                 // an overlapping pair (hi, lo): solved by the rank that owns its cell column
                 const uint2 pr = a.ov_pairs[p - n_cand];
                 uint32_t ia, ib;
-                if (gid_lookup(a, n_local, pr.x, &ia) && gid_lookup(a, n_local, pr.y, &ib)) {
+                if ((!a.ov_live_check || overlap_contains(a.cd.ov, pr.x, pr.y)) && gid_lookup(a, n_local, pr.x, &ia) && gid_lookup(a, n_local, pr.y, &ib)) {
                     const RecHead ha = load_head(a.rec, ia), hb = load_head(a.rec, ib);
                     const int32_t owner_col = max(ha.sx, hb.sx);
                     if (owner_col >= a.col_lo && owner_col < a.col_hi) {

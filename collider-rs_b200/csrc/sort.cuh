@@ -507,4 +507,28 @@ __global__ void k_decode_events(uint32_t n, const Key128* __restrict__ keys, con
     out[i] = e;
 }
 
+// The compact form (cb200_event16): labels instead of ids, the kind in the two spare top bits.
+struct Event16 {
+    double time;
+    uint32_t a, b;
+};
+__global__ void k_decode_events16(uint32_t n, const Key128* __restrict__ keys, Event16* out, int add_mode) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Key128 k = keys[i];
+    Event16 e;
+    e.time = key_time(k.hi);
+    if (k.lo & kPairClass) {
+        const uint32_t hi = (uint32_t)((k.lo >> 32) & 0x7fffffffu);
+        const uint32_t lo = add_mode ? (uint32_t)((k.lo & 0xffffffffu) >> 1) : (uint32_t)(k.lo & 0x7fffffffu);
+        const bool collide = (add_mode ? (k.lo & 1ull) : (k.lo & kCollideBit)) != 0;
+        e.a = hi;
+        e.b = lo | (collide ? 0x80000000u : 0u);
+    } else {
+        e.a = (uint32_t)k.lo | 0x80000000u;  // Reiterate
+        e.b = 0u;
+    }
+    out[i] = e;
+}
+
 }  // namespace cb200

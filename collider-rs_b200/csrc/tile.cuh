@@ -147,7 +147,9 @@ __global__ void __launch_bounds__(kThreads) k_tile_home(uint32_t n, int tj, cons
 // ---------------------------------------------------------------------------------------------------------
 // Survivors: the candidate pairs whose swept bounds touch, as (source of the higher id, source of the lower id).  A source
 // names where the hitbox's data lives: a table row, or kTileVisFlag | index into the visitor slabs.  8 bytes per pair; the
-// finish kernel gathers the two hitboxes (only the ~5-30 % of the candidate pairs that survive the filter are ever gathered).
+// finish kernel gathers the two hitboxes (only the few per cent of the candidate pairs that survive the filter are ever
+// gathered).  (Measured alternative: the tile kernel assembling both 96-byte records per survivor so that the finish kernel
+// streams them — the lane-serial assembly cost the tile kernel 35 us for 40k survivors and saved the finish kernel 3.)
 struct SurvList {
     uint2* items;
     uint32_t cap;
@@ -510,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_tile_finish(const 
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     const uint32_t n_surv = (uint32_t)min(a.ctr->n_surv, (unsigned long long)ta.surv.cap);
-    const uint32_t total = n_surv + (LIST ? 0u : a.n_ov);
+    const uint32_t total = n_surv + (LIST ? 0u : (a.n_ov_dev ? min(*a.n_ov_dev, a.n_ov) : a.n_ov));
     const uint32_t n_local = a.ctr->n_local;
     const uint32_t stride = gridDim.x * blockDim.x;
     auto flush = [&]() {  // all threads
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_tile_finish(const 
             // an overlapping pair (gid hi, gid lo): separate_time (collider.rs:329-339)
             const uint2 pr = a.ov_pairs[p - n_surv];
             uint32_t ia, ib;
-            if (gid_lookup(a, n_local, pr.x, &ia) && gid_lookup(a, n_local, pr.y, &ib)) {
+            if ((!a.ov_live_check || overlap_contains(a.cd.ov, pr.x, pr.y)) && gid_lookup(a, n_local, pr.x, &ia) && gid_lookup(a, n_local, pr.y, &ib)) {
                 RecHead ha, hb;
                 DurHb da, db;
                 load_rec_keep(a.rec, ia, keep, &ha, &da);

@@ -164,6 +164,20 @@ int cb200_download_state(cb200_ctx* ctx, const cb200_state_out* out);
 /* Replace the set of currently-overlapping pairs (HitboxInfo.overlaps, collider.rs:463) as id pairs. */
 int cb200_set_overlaps(cb200_ctx* ctx, const uint64_t* id_a, const uint64_t* id_b, uint64_t n_pairs);
 
+/* Window drain: process, on the device, the pair events of every bulk step that fall inside the step's own window
+ * [time, end_time] — exactly as Collider::next / process_event / process_collision (collider.rs:113-197) would for a caller
+ * that pops every event up to end_time WITHOUT reacting to it (no set_hitbox_vel in between): Collide -> the pair joins the
+ * overlap set and its Separate is computed at the event time, Separate -> it leaves and its next Collide is computed; every
+ * follow-up event with time <= end_time is appended to the step's event list (cb200_fetch_events then holds every event the
+ * reference delivers up to end_time), and the overlap set — kept on the device from step to step, no cb200_set_overlaps
+ * between steps — is the set at end_time.  Exact as long as no Reiterate event falls inside a window (a hitbox crossing a
+ * whole cell within one step); cb200_last_drain reports how many did.  One device only; the step takes one scalar end_time.
+ * cb200_fetch_overlaps reads the set back (id pairs, higher id first). */
+int cb200_set_window_drain(cb200_ctx* ctx, int on);
+int cb200_fetch_overlaps(cb200_ctx* ctx, uint64_t* id_a, uint64_t* id_b, uint64_t cap, uint64_t* n_out);
+int cb200_last_drain(const cb200_ctx* ctx, uint64_t* followup_events, uint64_t* pairs_added, uint64_t* pairs_removed, uint64_t* pairs_now,
+                     uint64_t* reiterates_in_windows);
+
 /* The bulk advance/rebuild entry point.  Reference-equivalent definition: at `time`,
  *   for id in ascending HbId: Collider::internal_update_hitbox(id, Some(vel_id))   (collider.rs:231-250)
  * i.e. rebase, clear every queued event, solitaire_event_check, re-bin into the grid, candidate pairs,
@@ -239,6 +253,27 @@ int cb200_shard_abort(cb200_ctx* ctx);
 /* Events queued by the last bulk step, sorted by the canonical order (time, class, hi id, kind, lo id)
  * (events.rs:60-68 with SURVEY.md §8c tie-break).  Copies events [offset, offset+cap) into buf. */
 int cb200_fetch_events(cb200_ctx* ctx, cb200_event* buf, uint64_t cap, uint64_t offset, uint64_t* n_out);
+
+/* ---- Pipelined host I/O ----------------------------------------------------------------------------------------------
+ * A bulk step is bound by PCIe when its inputs and outputs cross the host boundary every step.  These three calls let the
+ * transfers run beside the compute (each direction on its own CUDA stream of the context, double-buffered):
+ *   cb200_stage_velocities   starts the host -> device copy of the NEXT step's velocities and returns; the next
+ *                            cb200_bulk_update called with vel == NULL consumes them (the host arrays must stay valid and
+ *                            unchanged until that call returns; pinned memory — cb200_host_alloc — for a truly asynchronous copy)
+ *   cb200_fetch_events_begin sorts the last step's events on the device (as cb200_fetch_events) and starts their download
+ *                            in the 16-byte compact form; returns without waiting, so the next step can be started
+ *   cb200_fetch_events_end   waits for that download
+ * cb200_event16: `a` = label of the first hitbox (bit 31 set: the event is a Reiterate), `b` = label of the second hitbox
+ * (bit 31 set: Collide, clear: Separate).  A label is the rank of the HbId in the uploaded (ascending) id array — the host
+ * holds that array — or the id itself in sharded mode. */
+typedef struct cb200_event16 {
+    double time;
+    uint32_t a;
+    uint32_t b;
+} cb200_event16;
+int cb200_stage_velocities(cb200_ctx* ctx, const cb200_vel_view* vel);
+int cb200_fetch_events_begin(cb200_ctx* ctx, cb200_event16* buf, uint64_t cap, uint64_t* n_out);
+int cb200_fetch_events_end(cb200_ctx* ctx);
 
 /* Parity/debug views of the last bulk step.
  * Candidate pairs: (hi id, lo id) for every collide_time evaluated (unsorted).  Grid::overlapping_ids, grid.rs:115-135. */

@@ -341,6 +341,86 @@ def test_tile_path_is_taken_and_splits_or_falls_back_when_a_tile_does_not_fit(or
         assert eng.last_step_path() == ("global" if want_fallback else "tile"), env
 
 
+def drain_recording(orc, t_stop):
+    """drain_until, keeping what the reference delivers: (time, kind, id_1, id_2) of every user-visible event up to t_stop."""
+    out = []
+    while True:
+        t = min(orc.next_time(), t_stop)
+        orc.set_time(t)
+        while True:
+            ev = orc.next()
+            if ev is None:
+                break
+            out.append((t, ev[0], ev[1], ev[2]))
+        if t >= t_stop:
+            return out
+
+
+@pytest.mark.parametrize("scene_name", ["sparse", "dense"])
+def test_window_drain_keeps_the_overlap_set_on_the_device(oracle, scene_name):
+    """cb200_set_window_drain: the pair events inside every step's window are processed on the device (chains included) and the
+    overlap set stays there — no set_overlaps between the steps.  Per step: the events up to the end of the window equal what
+    the oracle delivers through next() (times bit-equal), and the device overlap set equals the oracle's at the window's end."""
+    scene = scenes.uniform_density(30000, seed=scenes.SEED_BASE + 60) if scene_name == "sparse" else scenes.uniform_density(4000, density=1.0, seed=scenes.SEED_BASE + 61)
+    orc, eng = seeded(oracle, scene)
+    eng.set_window_drain(True)
+    T, dt, followups = 0.0, 0.1, 0
+    for step in range(6):
+        orc.bulk_update(end_time=T + dt)
+        res = eng.bulk_update(T, end_time=T + dt)
+        assert res.n_solitaire == 0  # (no Reiterate inside a window: the drain is exact)
+        want = drain_recording(orc, T + dt)
+        ev = eng.fetch_events()
+        assert len(ev) == res.n_events
+        ev = ev[ev["time"] <= T + dt]
+        got = sorted((bits([t])[0], int(k), int(min(a, b)), int(max(a, b))) for t, k, a, b in zip(ev["time"], ev["kind"], ev["a"], ev["b"]))
+        assert got == sorted((bits([t])[0], k, a, b) for t, k, a, b in want), step
+        assert np.all(np.diff(ev["time"]) >= 0)
+        followups += eng.last_drain()["followup_events"]
+        oa, ob = orc.dump_overlaps()
+        da, db = eng.fetch_overlaps()
+        key = lambda p, q: np.sort(np.maximum(p, q).astype(np.uint64) << np.uint64(32) | np.minimum(p, q).astype(np.uint64))
+        np.testing.assert_array_equal(key(da, db), key(oa, ob))
+        assert eng.last_drain()["pairs_now"] == len(oa)
+        T += dt
+    assert eng.last_drain()["reiterates_in_windows"] == 0
+    if scene_name == "dense":
+        assert followups > 0, "the dense case must contain chains (a pair that collides and separates inside one window)"
+
+
+def test_pipelined_io_matches_plain_calls(oracle):
+    """cb200_stage_velocities + cb200_fetch_events_begin / _end (transfers on their own streams, compact 16-byte events)
+    give exactly what the plain calls give: same events in the same order, same state."""
+    n = 8000
+    scene = scenes.uniform_density(n, seed=scenes.SEED_BASE + 70)
+    orc, eng = seeded(oracle, scene)
+    ids = np.ascontiguousarray(orc.dump_state()["id"], dtype=np.uint64)
+    pin = cb.PinnedArray(4 * n, cb.EVENT16_DTYPE)
+    pv = [(cb.PinnedArray(n, np.float64), cb.PinnedArray(n, np.float64)) for _ in range(2)]
+    T = 0.0
+    for step in range(4):
+        vx = scenes.uniform(900 + step, n, 1, -3.0, 3.0)
+        vy = scenes.uniform(900 + step, n, 2, -3.0, 3.0)
+        pv[step & 1][0].array[:] = vx
+        pv[step & 1][1].array[:] = vy
+        eng.stage_velocities(vel_x=pv[step & 1][0].array, vel_y=pv[step & 1][1].array)
+        orc.bulk_update(end_time=T + 0.2, vx=vx, vy=vy, record_candidates=True)
+        res = eng.bulk_update(T, end_time=T + 0.2)  # consumes the staged velocities
+        got = eng.fetch_events_begin(pin.array)
+        eng.fetch_events_end()
+        assert got == res.n_events
+        ev = cb.Engine.decode_events16(pin.array[:got], ids)
+        t, kind, a, b = oracle_events(orc)
+        np.testing.assert_array_equal(ev["kind"], kind)
+        np.testing.assert_array_equal(ev["a"], a)
+        np.testing.assert_array_equal(ev["b"], np.where(kind == 0, 0, b))
+        np.testing.assert_array_equal(bits(ev["time"]), bits(t))
+        assert_step_parity(orc, eng, res, check_grid=False)  # (the plain fetch after the pipelined one: the same list)
+        T += 0.2
+        drain_until(orc, T)
+        eng.set_overlaps(*orc.dump_overlaps())
+
+
 def test_aliased_grid_is_still_exact(oracle):
     """Force a tiny grid period so that many cells share a slot: results must not change."""
     scene = scenes.uniform_density(5000)
