@@ -335,8 +335,9 @@ def parity_check(cb, scenes, sharding, dist, workload, rank, world, local_rank, 
             "bit_identical_to_oracle": ok}
 
 
-def timed_passes(job, barrier, steps, repeats, body):
-    """`repeats` runs of `steps` calls of body(); returns (per-run wall seconds, accumulated dict of body's counters)."""
+def timed_passes(job, barrier, steps, repeats, body, tail=None):
+    """`repeats` runs of `steps` calls of body() (+ tail(): whatever the last call left in flight); returns (per-run wall
+    seconds, accumulated dict of body's counters)."""
     walls, acc = [], {}
     for _ in range(repeats):
         barrier()
@@ -344,9 +345,36 @@ def timed_passes(job, barrier, steps, repeats, body):
         for _ in range(steps):
             for k, v in body().items():
                 acc[k] = acc.get(k, 0) + v
+        if tail is not None:
+            tail()
         barrier()
         walls.append(time.perf_counter() - t0)
     return walls, acc
+
+
+class EventPins:
+    """Two page-locked buffers for the pipelined event download (one is being filled while the other is read)."""
+
+    def __init__(self, cb):
+        self.cb, self.bufs, self.k, self.last_n = cb, [None, None], 0, 0
+
+    def next(self, n_events):
+        self.k ^= 1
+        b = self.bufs[self.k]
+        if b is None or b.array.shape[0] < n_events:
+            b = self.bufs[self.k] = self.cb.PinnedArray(max(int(n_events * 1.3) + 1024, 4096), self.cb.EVENT16_DTYPE)
+        self.last_n = int(n_events)
+        return b.array
+
+    def last(self):
+        return self.bufs[self.k].array
+
+
+def events_digest16(ev):
+    h = hashlib.sha256()
+    for k in ("time", "a", "b"):
+        h.update(np.ascontiguousarray(ev[k]).tobytes())
+    return h.hexdigest()
 
 
 def collider_rows(cb, scenes, device):
@@ -434,15 +462,20 @@ def config4_block(cb, scenes, sharding, dist, rank, world, local_rank, barrier, 
     walls, _ = timed_passes(job, barrier, steps, 1, body)
     dev_ms, _ = job.eng.step_timing()
     ev_bytes = [0]
+    pins = EventPins(cb)
+    failures = [0]
 
     def body_fetch():
-        job.device_step()
-        evs = job.eng.fetch_events(pinned=True)
-        ev_bytes[0] += evs.nbytes
+        r = job.device_step()
+        try:
+            job.eng.fetch_events_end()
+        except cb.ColliderError:
+            failures[0] += 1
+        ev_bytes[0] += 16 * job.eng.fetch_events_begin(pins.next(r.n_events))
         return {}
 
     body_fetch()
-    walls_t, _ = timed_passes(job, barrier, steps, 1, body_fetch)
+    walls_t, _ = timed_passes(job, barrier, steps, 1, body_fetch, tail=job.eng.fetch_events_end)
     t = torch.tensor([walls[0], walls_t[0], dev_ms], dtype=torch.float64, device="cuda")
     s = torch.tensor([float(solves[0])], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -455,7 +488,47 @@ def config4_block(cb, scenes, sharding, dist, rank, world, local_rank, barrier, 
             "n_gpus": world, "hitboxes_total": C4_TOTAL, "steps": steps, "warmup": warmup,
             "device_ms_per_step": dev, "ms_per_step_device_resident": wall / steps * 1e3, "hitbox_updates_per_s": C4_TOTAL * steps / wall,
             "pair_solves_per_s": s.item() / wall, "t_step_ms_with_event_list": wall_t / steps * 1e3, "d2h_bytes_per_step_rank0": int(ev_bytes[0] / (steps + 1)),
-            "event_sort_fallbacks": fallbacks, "scaling": "strong (fixed 16,777,216 hitboxes; compare with the n_gpus=1 line's block)"}
+            "event_sort_fallbacks": fallbacks, "pipelined_fetch_failures": failures[0], "scaling": "strong (fixed 16,777,216 hitboxes; compare with the n_gpus=1 line's block)"}
+
+
+def steady_state_block(cb, scenes, sharding, dist, args, rank, world, local_rank, barrier, K):
+    """The same workload with the window drain on (cb200_set_window_drain): the pair events inside each step's window are
+    processed on the device (chains included) and the overlap set stays device-resident, as in a run whose caller pops every
+    event before the next step.  The headline run never processes events, so pairs that came into contact keep returning as
+    zero-delay Collide events (12x the event volume); this block is the steady state."""
+    job = Job(cb, scenes, sharding, dist, args.workload, args.n, rank, world, local_rank, grid=args.grid, drain=True)
+    eng = job.eng
+    job.first_step()
+    eng.set_stage_timing(False)
+    for _ in range(max(args.warmup, 17)):
+        job.device_step()
+    eng.reset_timing()
+    acc = {"events": 0, "solves": 0, "followups": 0}
+
+    def body():
+        r = job.device_step()
+        acc["events"] += r.n_events
+        acc["solves"] += r.n_collide_solves + r.n_separate_solves
+        acc["followups"] += eng.last_drain()["followup_events"]
+        return {}
+
+    walls, _ = timed_passes(job, barrier, K, 1, body)
+    dev_ms, _ = eng.step_timing()
+    pins = EventPins(cb)
+
+    def body_t():
+        r = job.device_step()
+        eng.fetch_events_end()
+        eng.fetch_events_begin(pins.next(r.n_events))
+        return {}
+
+    body_t()
+    walls_t, _ = timed_passes(job, barrier, K, 1, body_t, tail=eng.fetch_events_end)
+    d = eng.last_drain()
+    return {"what": "window drain on: events of each step's window processed on the device, overlap set device-resident (cb200_set_window_drain)",
+            "device_ms_per_step": dev_ms, "t_step_ms": walls_t[0] / K * 1e3, "hitbox_updates_per_s": args.n * K / walls_t[0],
+            "events_per_step": acc["events"] / K, "followup_events_per_step": acc["followups"] / K, "pair_solves_per_step": acc["solves"] / K,
+            "overlapping_pairs": d["pairs_now"], "reiterates_inside_windows": d["reiterates_in_windows"], "path": eng.last_step_path()}
 
 
 def _main(out):
@@ -473,6 +546,7 @@ def _main(out):
     ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--no-collider-rows", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-steady-state", dest="steady_state", action="store_false", help="skip the window-drain (steady-state) block of the N=1 line")
     ap.add_argument("--drain", action="store_true", help="window drain: pair events inside each step's window processed on the device, overlap set device-resident")
     ap.add_argument("--grid", default="", help="force the device grid period: log2_w,log2_h")
     args = ap.parse_args()
@@ -529,19 +603,28 @@ def _main(out):
     launches = (eng.launch_count() - launches0) // R
     dev_ms, _ = eng.step_timing()  # average over all R*K steps
 
-    # (2) t_step of SURVEY 8(d): step + ordered queue (device sort) + D2H of the event list into pinned memory
+    # (2) t_step of SURVEY 8(d): step + ordered queue (device sort) + D2H of the event list into pinned host memory.  The
+    # download of step k's list (16-byte events, own copy stream) runs beside step k+1: cb200_fetch_events_begin / _end
+    pins = EventPins(cb)
     digest = [None]
+    fetch_failures = [0]
+
+    def fetch_pipelined(n_events):
+        try:
+            eng.fetch_events_end()  # the previous step's download
+        except cb.ColliderError:
+            fetch_failures[0] += 1
+        return eng.fetch_events_begin(pins.next(n_events))
 
     def body_tstep():
-        job.device_step()
-        evs = eng.fetch_events(pinned=True)
-        if digest[0] is None:
-            digest[0] = events_digest(evs)
-        return {"ev_bytes": evs.nbytes}
+        r = job.device_step()
+        got = fetch_pipelined(r.n_events)
+        return {"ev_bytes": got * 16}
 
     body_tstep()
-    digest[0] = None
-    walls_t, acc_t = timed_passes(job, barrier, K, R, body_tstep)
+    eng.fetch_events_end()
+    digest[0] = events_digest16(pins.last()[: pins.last_n])
+    walls_t, acc_t = timed_passes(job, barrier, K, R, body_tstep, tail=eng.fetch_events_end)
 
     # (3) per-kernel durations: K steps with CUDA events between the stages (each event adds ~2 us of stream time, so these are
     # upper bounds and their sum exceeds device_ms_per_step)
@@ -551,21 +634,27 @@ def _main(out):
     _, stage_ms = eng.step_timing()
     eng.set_stage_timing(False)
 
-    # (4) e2e: new velocities arrive from pinned host arrays every step, sorted events are read back
+    # (4) e2e: new velocities arrive from pinned host arrays every step, sorted events are read back.  Both transfers are
+    # pipelined against the compute: the upload of step k+1's velocities (cb200_stage_velocities, own stream) and the download of
+    # step k-1's events run beside step k
     pvx, pvy = cb.PinnedArray(n, np.float64), cb.PinnedArray(n, np.float64)
     pvx.array[:] = job.scene["vel_x"]
     pvy.array[:] = job.scene["vel_y"]
+    eng.stage_velocities(vel_x=pvx.array, vel_y=pvy.array)
 
     def body_e2e():
+        eng.stage_velocities(vel_x=pvx.array, vel_y=pvy.array)  # the NEXT step's velocities
         T = job.clock
         job.clock = T + DT
-        job.step(T, end_time=job.clock, vel_x=pvx.array, vel_y=pvy.array)
-        evs = eng.fetch_events(pinned=True)  # sorted queue of the step, D2H into page-locked memory
-        return {"d2h": evs.nbytes + C_sizeof_result(cb)}
+        r = job.step(T, end_time=job.clock)                      # consumes the set staged one iteration ago
+        got = fetch_pipelined(r.n_events)
+        return {"d2h": got * 16 + C_sizeof_result(cb)}
 
     for _ in range(3):
         body_e2e()
-    walls_e, acc_e = timed_passes(job, barrier, K, R, body_e2e)
+    walls_e, acc_e = timed_passes(job, barrier, K, R, body_e2e, tail=eng.fetch_events_end)
+    job.step(job.clock, end_time=job.clock + DT)  # (consume the set that is still staged)
+    job.clock += DT
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -582,9 +671,14 @@ def _main(out):
     solves_all = sums.tolist()[0]
 
     sort_fallbacks = eng.event_sort_fallbacks()
+    steady = None
+    if args.steady_state and world == 1:
+        del job, eng
+        steady = steady_state_block(cb, scenes, sharding, dist, args, rank, world, local_rank, barrier, K)
+        job = eng = None
     c4 = None
     if not args.no_config4 and args.workload == "c3":
-        del job, eng
+        job = eng = None
         c4 = config4_block(cb, scenes, sharding, dist, rank, world, local_rank, barrier)
 
     if rank == 0:
@@ -618,8 +712,9 @@ def _main(out):
             "ms_per_step": wall_t / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_of(args),
             "timing": {"repeats": R, "reported": "median run of `repeats` runs of K steps, max over ranks",
-                       "value": "t_step of SURVEY 8(d): device-resident state; bulk step + ordered event queue (device sort) + D2H of the event list into pinned "
-                                "host memory; wall clock around the synchronous C-ABI calls, bracketed by barrier + cuda sync",
+                       "value": "t_step of SURVEY 8(d): device-resident state; bulk step + ordered event queue (device sort) + D2H of the event list (16-byte "
+                                "events) into pinned host memory, the download of step k overlapping step k+1; wall clock around the C-ABI calls, bracketed by "
+                                "barrier + cuda sync",
                        "t_step_ms_min_max_over_runs": [wall_t_min / K * 1e3, wall_t_max / K * 1e3],
                        "l2": "working set per step (SoA state + records + slot table + entries, > 300 MB) exceeds the 126 MB L2; no flush needed"},
             "device_ms_per_step": dev_ms_max,
@@ -630,7 +725,8 @@ def _main(out):
             "per_step": {"cell_entries": E, "cells": Cc, "work_items": W, "pair_solves": P, "events": V, "event_list_bytes": acc_t["ev_bytes"] / KR},
             "gpu_launches": int(launches),
             "e2e": {"value": n * world * K / wall_e, "unit": UNIT, "h2d_bytes_per_step": int(16 * n), "d2h_bytes_per_step": int(acc_e["d2h"] / KR),
-                    "ms_per_step": wall_e / K * 1e3, "event_sort_fallbacks": sort_fallbacks},
+                    "ms_per_step": wall_e / K * 1e3, "event_sort_fallbacks": sort_fallbacks, "pipelined_fetch_failures": fetch_failures[0],
+                    "pipeline": "velocities of step k+1 staged (H2D stream) and events of step k-1 downloaded as 16-byte records (D2H stream) beside step k"},
             "roofline": {"bound": "hbm", "kernel": "bulk step (all kernels of one cb200_bulk_update)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
                          "bytes_model": "SURVEY 8(d): B_step = 184 N + 104 E + 16 C + 24 V", "b_step_bytes": b_step,
@@ -647,6 +743,8 @@ def _main(out):
             line["config"]["parallelism"] = (f"spatial sharding: {world} column strips; halo records (96 B) and next-event keys "
                                              + ("pushed into the peers' memory over NVLink by the step kernels (cudaIpc), one host sync per step, no collective on the data path"
                                                 if os.environ.get("CB200_EXCHANGE", "direct") != "nccl" else "exchanged by two NCCL all-gathers"))
+        if steady is not None:
+            line["steady_state_window_drain"] = steady
         if c4 is not None:
             line["config4"] = c4
         if not args.no_cpu_baseline and world == 1:

@@ -210,15 +210,15 @@ struct cb200_ctx {
     DevBuf<Event16> ev16[2];
     int ev16_parity = 0;
     cudaStream_t d2h_stream = nullptr, h2d_stream = nullptr;
-    cudaEvent_t ev_sorted_done = nullptr, ev_staged_done = nullptr, ev_step_done = nullptr;
+    cudaEvent_t ev_sorted_done = nullptr, ev_staged_done[2] = {nullptr, nullptr};
     bool fetch_pending = false, fetch_oneshot_pending = false;
     Event16* fetch_dst = nullptr;
     uint64_t fetch_take = 0;
     uint32_t fetch_nt = 0, fetch_np = 0;
     uint64_t fetch_ns = 0;
-    DevBuf<double> nvel_staged[5];
-    bool vel_staged = false;
-    bool staged_has[5] = {};
+    DevBuf<double> nvel_staged[2][5];  // two staged sets: one can be uploaded while the step consumes the other
+    bool staged_has[2][5] = {};
+    int staged_count = 0, staged_head = 0;  // FIFO over the two sets
     bool sort_oneshot = true;        // CB200_SORT=slow: recursive bucket sort / radix sort only (A/B and tests)
     uint32_t* h_sort_big = nullptr;  // pinned, mapped: k_bs_scan8's oversized-bucket report [1 + 2 * kBsMaxBig]
     uint32_t* d_sort_big = nullptr;  // its device alias
@@ -431,10 +431,11 @@ void cb200_destroy(cb200_ctx* c) {
     c->events.release(); c->partial.release();
     c->tile_rows.release(); c->home.release(); c->vis_count.release(); c->vis.release(); c->surv.release();
     for (auto& b : c->ev16) b.release();
-    for (auto& b : c->nvel_staged) b.release();
+    for (auto& set : c->nvel_staged)
+        for (auto& b : set) b.release();
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
-    for (cudaEvent_t e : {c->ev_sorted_done, c->ev_staged_done, c->ev_step_done})
+    for (cudaEvent_t e : {c->ev_sorted_done, c->ev_staged_done[0], c->ev_staged_done[1]})
         if (e) cudaEventDestroy(e);
     c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); for (auto& b : c->bs_tab) b.release(); c->imm_pairs.release(); if (c->d_n_imm) cudaFree(c->d_n_imm); c->ev_out.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
@@ -734,14 +735,14 @@ static int dbg_sync(cb200_ctx* ctx, const char* stage) {
 static int stage_vel(cb200_ctx* ctx, const cb200_vel_view* vel, const double** nv) {
     const uint32_t n = ctx->n;
     for (int k = 0; k < 5; ++k) nv[k] = nullptr;
-    if (!vel && ctx->vel_staged) {
-        // velocities staged ahead of time by cb200_stage_velocities (their H2D copy ran beside the previous step)
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_staged_done, 0));
-        for (int k = 0; k < 5; ++k) {
-            std::swap(ctx->nvel[k], ctx->nvel_staged[k]);
-            if (ctx->staged_has[k]) nv[k] = ctx->nvel[k].p;
-        }
-        ctx->vel_staged = false;
+    if (!vel && ctx->staged_count) {
+        // velocities staged ahead of time by cb200_stage_velocities (their H2D copy ran beside the previous step): oldest set first
+        const int slot = ctx->staged_head;
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_staged_done[slot], 0));
+        for (int k = 0; k < 5; ++k)
+            if (ctx->staged_has[slot][k]) nv[k] = ctx->nvel_staged[slot][k].p;
+        ctx->staged_head ^= 1;
+        ctx->staged_count -= 1;
         return CB200_OK;
     }
     if (vel && n) {
@@ -1911,7 +1912,7 @@ static int build_sort_keys(cb200_ctx* ctx, uint32_t n_pairs, uint64_t n_solitair
 // been synchronised; the caller checks it and falls back to sort_events_slow.
 static int enqueue_sort_oneshot(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, uint64_t n_solitaire) {
     int log2_buckets = 6;
-    while ((1u << log2_buckets) * 12u < nt && log2_buckets < 22) ++log2_buckets;
+    while ((1u << log2_buckets) * 8u < nt && log2_buckets < 24) ++log2_buckets;  // ~8 keys per bucket (a warp sorts up to 256)
     const uint32_t nb = 1u << log2_buckets, n_buckets = 2 * nb;  // region A (ties at the first time) + region B (by time)
     const uint32_t scan_blocks = (n_buckets + kBs2Chunk - 1) / kBs2Chunk;
     DevBuf<uint32_t>& tab = ctx->bs_tab[0];
@@ -2040,29 +2041,32 @@ static int ensure_io_streams(cb200_ctx* ctx) {
     CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&ctx->ev_sorted_done, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&ctx->ev_staged_done, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&ctx->ev_step_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_staged_done[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_staged_done[1], cudaEventDisableTiming));
     return CB200_OK;
 }
 
-// New velocities for the NEXT bulk step, copied host -> device on the context's upload stream while the current step (or
-// the event download of the previous one) is still running.  Consumed by the next cb200_bulk_update called with vel == NULL.
+// New velocities for a coming bulk step, copied host -> device on the context's upload stream while the current step (or
+// the event download of the previous one) is running.  Up to two sets can be staged; each cb200_bulk_update called with
+// vel == NULL consumes the oldest one.
 int cb200_stage_velocities(cb200_ctx* ctx, const cb200_vel_view* vel) {
     if (!ctx || !vel) return CB200_E_ARG;
     if (!ctx->have_state) return fail(ctx, CB200_E_STATE, "stage_velocities before upload_state");
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_io_streams(ctx);
     if (rc != CB200_OK) return rc;
+    if (ctx->staged_count >= 2) return fail(ctx, CB200_E_STATE, "two velocity sets are staged already: run a bulk step (vel == NULL) first");
     const uint32_t n = ctx->n;
+    const int slot = (ctx->staged_head + ctx->staged_count) & 1;
     const double* src[5] = {vel->vel_x, vel->vel_y, vel->rsz_x, vel->rsz_y, vel->end_time};
     for (int k = 0; k < 5; ++k) {
-        ctx->staged_has[k] = src[k] != nullptr;
+        ctx->staged_has[slot][k] = src[k] != nullptr;
         if (!src[k] || !n) continue;
-        CU(ctx->nvel_staged[k].reserve(n));
-        CU(cudaMemcpyAsync(ctx->nvel_staged[k].p, src[k], (size_t)n * 8, cudaMemcpyHostToDevice, ctx->h2d_stream));
+        CU(ctx->nvel_staged[slot][k].reserve(n));
+        CU(cudaMemcpyAsync(ctx->nvel_staged[slot][k].p, src[k], (size_t)n * 8, cudaMemcpyHostToDevice, ctx->h2d_stream));
     }
-    CU(cudaEventRecord(ctx->ev_staged_done, ctx->h2d_stream));
-    ctx->vel_staged = true;
+    CU(cudaEventRecord(ctx->ev_staged_done[slot], ctx->h2d_stream));
+    ctx->staged_count += 1;
     return CB200_OK;
 }
 

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_scatter(const Key128* __restr
 // into 2^b equal ranges (~12 events each), the keys are counting-sorted into those buckets, and every bucket is finished by
 // one warp with a rank sort on the full 128-bit key in shared memory.  Six launches instead of ~70 for the LSD radix sort
 // above, which remains the fallback when some bucket is too large (many events at exactly the same time).
-constexpr int kBsMaxBucket = 128;  // keys a warp sorts in shared memory
+constexpr int kBsMaxBucket = 256;  // keys a warp sorts in shared memory (8 warps x 256 x 16 B = 32 KB per block)
 
 // The buckets are cut on ONE 64-bit field of the key: the time key (field 1), or — for a set of keys that all carry the
 // same time, e.g. everything that happens exactly at T — the tie word (field 0).  Buckets that come out too large for a warp

@@ -257,9 +257,10 @@ int cb200_fetch_events(cb200_ctx* ctx, cb200_event* buf, uint64_t cap, uint64_t 
 /* ---- Pipelined host I/O ----------------------------------------------------------------------------------------------
  * A bulk step is bound by PCIe when its inputs and outputs cross the host boundary every step.  These three calls let the
  * transfers run beside the compute (each direction on its own CUDA stream of the context, double-buffered):
- *   cb200_stage_velocities   starts the host -> device copy of the NEXT step's velocities and returns; the next
- *                            cb200_bulk_update called with vel == NULL consumes them (the host arrays must stay valid and
- *                            unchanged until that call returns; pinned memory — cb200_host_alloc — for a truly asynchronous copy)
+ *   cb200_stage_velocities   starts the host -> device copy of a coming step's velocities and returns; up to two sets may
+ *                            be staged, and each cb200_bulk_update called with vel == NULL consumes the oldest (the host
+ *                            arrays must stay valid and unchanged until that step has returned; pinned memory —
+ *                            cb200_host_alloc — for a truly asynchronous copy).  So the upload of step k+1 runs beside step k.
  *   cb200_fetch_events_begin sorts the last step's events on the device (as cb200_fetch_events) and starts their download
  *                            in the 16-byte compact form; returns without waiting, so the next step can be started
  *   cb200_fetch_events_end   waits for that download
