@@ -98,7 +98,7 @@ EXPORTS = (
     "cb200_collider_set_hitbox_vel", "cb200_collider_remove_hitbox", "cb200_collider_get_overlaps", "cb200_collider_is_overlapping",
     "cb200_collider_query_overlaps", "cb200_collider_bulk_update", "cb200_collider_len", "cb200_collider_set_rebin_threshold",
     "cb200_collider_rebin_count", "cb200_collider_engine", "cb200_collider_add_hitboxes", "cb200_collider_prefetch_count",
-    "cb200_collider_hitbox_cache_hits", "cb200_collider_run_halving_loop",
+    "cb200_collider_hitbox_cache_hits", "cb200_collider_run_halving_loop", "cb200_collider_query_overlaps_batch", "cb200_collider_group_index",
 )
 
 _lib = None

@@ -140,6 +140,8 @@ def _bind(L):
     L.cb200_collider_hitbox_cache_hits.argtypes = [vp]
     L.cb200_collider_hitbox_cache_hits.restype = u64
     L.cb200_collider_run_halving_loop.argtypes = [vp, C.c_double, C.POINTER(u64), C.POINTER(u64)]
+    L.cb200_collider_query_overlaps_batch.argtypes = [vp, u64, vp, vp, u64, vp]
+    L.cb200_collider_group_index.argtypes = [vp, u32, C.POINTER(u32)]
     L.cb200_collider_engine.argtypes = [vp]
     L.cb200_collider_engine.restype = vp
     L._collider_bound = True
@@ -277,6 +279,39 @@ class Collider:
         p = self._profile(id, group, interact_mask)
         return self._ids(lambda out, cap, n: self._L.cb200_collider_query_overlaps(self._h, shape.shape.kind, shape.x, shape.y, shape.shape.w, shape.shape.h,
                                                                                   C.byref(p), out, cap, n))
+
+    def query_overlaps_batch(self, shapes, ids, interact_masks=None):
+        """query_overlaps for many shapes in one device launch.  shapes: PlacedShape list; ids: the querying profiles' ids;
+        returns a list of ascending id lists."""
+        n = len(shapes)
+        qd = np.zeros(n, dtype=np.dtype([("kind", "<u4"), ("_pad", "<u4"), ("pos_x", "<f8"), ("pos_y", "<f8"), ("dim_x", "<f8"), ("dim_y", "<f8"),
+                                         ("id", "<u8"), ("group", "<u4"), ("interact_mask", "<u4")]))
+        assert qd.dtype.itemsize == 56
+        for k, sh in enumerate(shapes):
+            qd[k] = (sh.shape.kind, 0, sh.x, sh.y, sh.shape.w, sh.shape.h, ids[k], 0, 1 if interact_masks is None else interact_masks[k])
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        cap = max(64, 8 * n)
+        while True:
+            out = np.zeros(cap, dtype=np.uint64)
+            self._check(self._L.cb200_collider_query_overlaps_batch(self._h, n, qd.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), cap,
+                                                                    offsets.ctypes.data_as(C.c_void_p)))
+            if int(offsets[n]) <= cap:
+                return [out[int(offsets[k]):int(offsets[k + 1])].tolist() for k in range(n)]
+            cap = int(offsets[n])
+
+    def group_index(self, group_value: int) -> int:
+        """Device group index (0..31) of an arbitrary HbGroup value (cb200_collider_group_index)."""
+        i = C.c_uint32()
+        self._check(self._L.cb200_collider_group_index(self._h, group_value, C.byref(i)))
+        return i.value
+
+    def profile_of(self, group, interact_groups):
+        """(group index or None, interact mask) for arbitrary HbGroup values — what add_hitbox / query_overlaps take."""
+        g = None if group is None else self.group_index(group)
+        m = 0
+        for v in interact_groups:
+            m |= 1 << self.group_index(v)
+        return g, m
 
     def len(self):
         return int(self._L.cb200_collider_len(self._h))

@@ -106,6 +106,10 @@ struct cb200_collider {
     Mapped<OneHeader> head;
     Mapped<OneItem> items;
     Mapped<uint32_t> ov, qout;
+    Mapped<QueryItem> bq_items;   // batched queries
+    Mapped<OneHeader> bq_heads;
+    Mapped<uint32_t> bq_out;
+    std::unordered_map<uint32_t, uint32_t> group_index;  // HbGroup value -> device group index (0..31), in order of first use
     DevBuf<uint8_t> dirty;
     DevBuf<uint32_t> dirty_list;
     uint32_t* d_dirty_count = nullptr;
@@ -660,6 +664,7 @@ void cb200_collider_free(cb200_collider* c) {
         cudaStreamSynchronize(c->ctx->stream);
     }
     c->head.release(); c->items.release(); c->ov.release(); c->qout.release(); c->jobs.release(); c->job_out.release();
+    c->bq_items.release(); c->bq_heads.release(); c->bq_out.release();
     c->dirty.release(); c->dirty_list.release();
     if (c->d_dirty_count) cudaFree(c->d_dirty_count);
     cb200_destroy(c->ctx);
@@ -1132,6 +1137,85 @@ int cb200_collider_query_overlaps(cb200_collider* c, uint32_t kind, double pos_x
         return CB200_OK;
     }
     return cfail(c, CB200_E_STATE, "query buffer failed to converge");
+}
+
+// Collider::query_overlaps (collider.rs:309-318) for a batch of shapes: one device launch, one block per query.
+// ids of query q: out_ids[offsets[q] .. offsets[q + 1]), ascending.  offsets[n] = total; if it exceeds cap_ids only the
+// queries that fit completely were written (call again with a larger buffer).
+int cb200_collider_query_overlaps_batch(cb200_collider* c, uint64_t n, const cb200_query* queries, uint64_t* out_ids, uint64_t cap_ids, uint64_t* offsets) {
+    if (!c || !offsets || (n && !queries)) return CB200_E_ARG;
+    for (uint64_t q = 0; q <= n; ++q) offsets[q] = 0;
+    if (n == 0) return CB200_OK;
+    if (n > 0x3fffffffull) return cfail(c, CB200_E_ARG, "too many queries in one batch");
+    cb200_ctx* x = c->ctx;
+    cudaSetDevice(x->device);
+    for (uint64_t q = 0; q < n; ++q) {
+        const cb200_query& qu = queries[q];
+        if (qu.kind > 1) return cfail(c, CB200_E_ARG, "bad shape kind");
+        if (!(qu.dim_x >= 0.0 && qu.dim_y >= 0.0)) return cfail(c, CB200_E_CONTRACT, "dims must be non-negative");
+        if (qu.kind == CB200_KIND_CIRCLE && !(qu.dim_x == qu.dim_y)) return cfail(c, CB200_E_CONTRACT, "circle width must equal height");
+    }
+    if (x->n == 0) return CB200_OK;
+    int rc = maybe_rebin(c);
+    if (rc != CB200_OK) return rc;
+    CCU(c->bq_items.reserve(n));
+    CCU(c->bq_heads.reserve(n));
+    for (uint64_t q = 0; q < n; ++q)
+        c->bq_items.h[q] = QueryItem{PShape{queries[q].pos_x, queries[q].pos_y, queries[q].dim_x, queries[q].dim_y, (int)queries[q].kind}, queries[q].profile.interact_mask};
+    uint32_t cap_each = 32;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        CCU(c->bq_out.reserve((size_t)n * cap_each));
+        QueryBatchArgs a{};
+        a.t = table_of(c);
+        a.g = grid_of(c);
+        a.items = c->bq_items.d;
+        a.T = c->time;
+        a.cell_width = x->cell_width;
+        a.heads = c->bq_heads.d;
+        a.out = c->bq_out.d;
+        a.cap_each = cap_each;
+        k_query_batch<<<(uint32_t)n, kThreads, 0, x->stream>>>(a);
+        x->launches += 1;
+        if ((rc = wait_head(c)) != CB200_OK) return rc;
+        uint32_t need = 0;
+        for (uint64_t q = 0; q < n; ++q) {
+            if (c->bq_heads.h[q].err_flags) return cfail(c, CB200_E_CONTRACT, flags_message(c->bq_heads.h[q].err_flags) + " (query " + std::to_string(q) + ")");
+            need = std::max(need, c->bq_heads.h[q].n_items);
+        }
+        if (need <= cap_each) break;
+        cap_each = need + need / 4;
+        if (attempt == 3) return cfail(c, CB200_E_STATE, "query buffers failed to converge");
+    }
+    uint64_t total = 0;
+    std::vector<uint64_t> ids;
+    for (uint64_t q = 0; q < n; ++q) {
+        ids.clear();
+        const uint32_t m = c->bq_heads.h[q].n_items;
+        for (uint32_t k = 0; k < m; ++k) {
+            const uint64_t other = c->id_of_label[c->bq_out.h[(size_t)q * cap_each + k]];
+            if (interacts(c, other, queries[q].profile.id)) ids.push_back(other);
+        }
+        std::sort(ids.begin(), ids.end());
+        offsets[q] = total;
+        if (out_ids && total + ids.size() <= cap_ids) std::copy(ids.begin(), ids.end(), out_ids + total);
+        total += ids.size();
+    }
+    offsets[n] = total;
+    return CB200_OK;
+}
+
+// HbGroup is an arbitrary u32 in the reference (core/mod.rs:199); the device keys its grid by a group INDEX 0..31 and takes
+// interact_groups as a bit mask over those indices.  This maps a group value to its index, assigning indices in order of
+// first use — a wrapper builds cb200_profile.group / .interact_mask from it (at most 32 distinct groups per collider).
+int cb200_collider_group_index(cb200_collider* c, uint32_t group_value, uint32_t* index_out) {
+    if (!c || !index_out) return CB200_E_ARG;
+    auto it = c->group_index.find(group_value);
+    if (it == c->group_index.end()) {
+        if (c->group_index.size() >= 32) return cfail(c, CB200_E_ARG, "more than 32 distinct HbGroup values (the device grid key holds 32 group indices)");
+        it = c->group_index.emplace(group_value, (uint32_t)c->group_index.size()).first;
+    }
+    *index_out = it->second;
+    return CB200_OK;
 }
 
 // Benchmark driver: the user loop of the reference's README (README.md:66-80) run natively over this API — advance to the

@@ -390,50 +390,73 @@ struct QueryArgs {
     uint32_t* out;  // mapped pinned
     uint32_t cap;
 };
-__global__ void __launch_bounds__(kThreads) k_query(const QueryArgs a) {
+// One query, run by one block (all threads call; barriers inside).  Results: labels (unordered) in out[0 .. min(count, cap)).
+__device__ __forceinline__ void query_block(const TableView& t, const GridView& g, const PShape& q, uint32_t mask, double T, double cell_width, uint32_t* out,
+                                            uint32_t cap, OneHeader* head) {
     __shared__ uint32_t s_count, s_err;
     __shared__ int32_t s_rect[4];
     if (threadIdx.x == 0) {
         s_count = 0;
         s_err = 0;
         // Grid::index_bounds (grid.rs:101-113)
-        const double min_x = a.q.px - a.q.w * 0.5, max_x = a.q.px + a.q.w * 0.5, min_y = a.q.py - a.q.h * 0.5, max_y = a.q.py + a.q.h * 0.5;
-        const int32_t sx = f64_as_i32(floor(min_x / a.cell_width)), sy = f64_as_i32(floor(min_y / a.cell_width));
-        const int32_t ex = max(f64_as_i32(ceil(max_x / a.cell_width)), (int32_t)((uint32_t)sx + 1u));
-        const int32_t ey = max(f64_as_i32(ceil(max_y / a.cell_width)), (int32_t)((uint32_t)sy + 1u));
+        const double min_x = q.px - q.w * 0.5, max_x = q.px + q.w * 0.5, min_y = q.py - q.h * 0.5, max_y = q.py + q.h * 0.5;
+        const int32_t sx = f64_as_i32(floor(min_x / cell_width)), sy = f64_as_i32(floor(min_y / cell_width));
+        const int32_t ex = max(f64_as_i32(ceil(max_x / cell_width)), (int32_t)((uint32_t)sx + 1u));
+        const int32_t ey = max(f64_as_i32(ceil(max_y / cell_width)), (int32_t)((uint32_t)sy + 1u));
         s_rect[0] = sx; s_rect[1] = sy; s_rect[2] = ex; s_rect[3] = ey;
         const int64_t nx = (int64_t)ex - sx, ny = (int64_t)ey - sy;
         if (nx <= 0 || ny <= 0) s_err = kFEmptyRect;
-        else if (nx > (1ll << a.g.geom.lw) || ny > (1ll << a.g.geom.lh) || nx > 0xffff || ny > 0xffff) s_err = kFRectSpan;
+        else if (nx > (1ll << g.geom.lw) || ny > (1ll << g.geom.lh) || nx > 0xffff || ny > 0xffff) s_err = kFRectSpan;
     }
     __syncthreads();
     if (!s_err) {
-        for_each_cellmate(a.t, a.g, s_rect[0], s_rect[1], s_rect[2], s_rect[3], kRowNone, [&](uint32_t j, const RecHead& hj) {
+        for_each_cellmate(t, g, s_rect[0], s_rect[1], s_rect[2], s_rect[3], kRowNone, [&](uint32_t j, const RecHead& hj) {
             const uint32_t group_j = (hj.kgb >> 8) & 0xffu;
-            if (group_j > 31u || !((a.mask >> group_j) & 1u)) return;
+            if (group_j > 31u || !((mask >> group_j) & 1u)) return;
             uint32_t err = 0;
-            const double start = a.t.s.start[j], pub_end = a.t.s.pub_end[j];
-            if (!(a.T >= start && a.T <= pub_end)) err |= kFInvalidTime;
-            const double dt = a.T - start;
+            const double start = t.s.start[j], pub_end = t.s.pub_end[j];
+            if (!(T >= start && T <= pub_end)) err |= kFInvalidTime;
+            const double dt = T - start;
             if (!(dt < kHighTime)) err |= kFHighTime;
             PShape p;
-            p.px = a.t.s.px[j] + a.t.s.vx[j] * dt;
-            p.py = a.t.s.py[j] + a.t.s.vy[j] * dt;
-            p.w = a.t.s.w[j] + a.t.s.rw[j] * dt;
-            p.h = a.t.s.h[j] + a.t.s.rh[j] * dt;
-            p.kind = (int)(a.t.s.kind[j] & 1u);
+            p.px = t.s.px[j] + t.s.vx[j] * dt;
+            p.py = t.s.py[j] + t.s.vy[j] * dt;
+            p.w = t.s.w[j] + t.s.rw[j] * dt;
+            p.h = t.s.h[j] + t.s.rh[j] * dt;
+            p.kind = (int)(t.s.kind[j] & 1u);
             if (err) atomicOr(&s_err, err);
-            if (!shapes_overlap(p, a.q)) return;
+            if (!shapes_overlap(p, q)) return;
             const uint32_t pos = atomicAdd(&s_count, 1u);
-            if (pos < a.cap) a.out[pos] = hj.gid;
+            if (pos < cap) out[pos] = hj.gid;
         });
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        a.head->n_items = s_count;
-        a.head->err_flags = s_err;
+        head->n_items = s_count;
+        head->err_flags = s_err;
         __threadfence_system();
     }
+}
+__global__ void __launch_bounds__(kThreads) k_query(const QueryArgs a) { query_block(a.t, a.g, a.q, a.mask, a.T, a.cell_width, a.out, a.cap, a.head); }
+
+// Many queries in one launch, one block each (Collider::query_overlaps for a batch of shapes): query b reads items[b] and
+// writes its labels to out[b * cap_each ...] and its count / flags to heads[b].
+struct QueryItem {
+    PShape q;
+    uint32_t mask;
+};
+struct QueryBatchArgs {
+    TableView t;
+    GridView g;
+    const QueryItem* items;
+    double T, cell_width;
+    OneHeader* heads;  // mapped pinned
+    uint32_t* out;     // mapped pinned, [n * cap_each]
+    uint32_t cap_each;
+};
+__global__ void __launch_bounds__(kThreads) k_query_batch(const QueryBatchArgs a) {
+    const QueryItem it = a.items[blockIdx.x];
+    query_block(a.t, a.g, it.q, it.mask, a.T, a.cell_width, a.out + (size_t)blockIdx.x * a.cap_each, a.cap_each, a.heads + blockIdx.x);
 }
 
 // Collider::remove_hitbox, table part: the last row moves into the hole (its sorted-array entries go stale, so it

@@ -346,6 +346,20 @@ int cb200_collider_get_overlaps(cb200_collider* c, uint64_t id, uint64_t* out, u
 int cb200_collider_is_overlapping(cb200_collider* c, uint64_t id_1, uint64_t id_2, int* out);                        /* :300-305 */
 int cb200_collider_query_overlaps(cb200_collider* c, uint32_t kind, double pos_x, double pos_y, double dim_x, double dim_y,
                                   const cb200_profile* profile, uint64_t* out, uint64_t cap, uint64_t* n_out);       /* :309-318 */
+/* Collider::query_overlaps for a batch of shapes in ONE device launch (one thread block per query).  ids of query q:
+ * out_ids[offsets[q] .. offsets[q + 1]), ascending; offsets has n + 1 entries and offsets[n] is the total — if it exceeds
+ * cap_ids, only the queries that fit completely were written. */
+typedef struct cb200_query {
+    uint32_t kind; /* CB200_KIND_* */
+    uint32_t _pad;
+    double pos_x, pos_y, dim_x, dim_y;
+    cb200_profile profile; /* id (for can_interact), interact_mask */
+} cb200_query;
+int cb200_collider_query_overlaps_batch(cb200_collider* c, uint64_t n, const cb200_query* queries, uint64_t* out_ids, uint64_t cap_ids, uint64_t* offsets);
+/* HbGroup is an arbitrary u32 in the reference (core/mod.rs:199); the device takes group INDICES 0..31 (cb200_profile.group)
+ * and interact_groups as a bit mask over them.  Maps a group value to its index (assigned in order of first use; at most 32
+ * distinct values per collider) so that a wrapper can accept any HbGroup. */
+int cb200_collider_group_index(cb200_collider* c, uint32_t group_value, uint32_t* index_out);
 /* The bulk advance/rebuild entry point on a Collider: at the current time, for id ascending,
  * internal_update_hitbox(id, Some(vel_id)) — one device pass (cb200_bulk_update).  `vel` arrays are in ascending-id order. */
 int cb200_collider_bulk_update(cb200_collider* c, const cb200_vel_view* vel, double end_time, cb200_step_result* out);

@@ -388,6 +388,42 @@ def test_adds_removes_groups_and_queries(oracle):
         c.get_overlaps(id)
 
 
+def test_batched_queries_and_arbitrary_group_values(oracle):
+    """cb200_collider_query_overlaps_batch answers many queries in one launch (same answers as one call each and as the
+    oracle), and cb200_collider_group_index lets a wrapper use ANY u32 HbGroup value (core/mod.rs:199): the device sees dense
+    indices in order of first use, the oracle is driven with those indices."""
+    rng = np.random.default_rng(11)
+    c = Lockstep(oracle, 4.0, 0.05)
+    values = [4_000_000_000, 7, 1_000_000_007]                      # arbitrary HbGroup values
+    wants = {4_000_000_000: [7, 4_000_000_000], 7: [1_000_000_007], 1_000_000_007: [4_000_000_000, 7, 1_000_000_007]}
+    index = {}
+    for id in range(600):
+        v = values[id % 3]
+        g, m = c.d.profile_of(v, wants[v])
+        index[v] = g
+        kind = int(rng.integers(0, 2))
+        w = float(rng.uniform(0.5, 3.0))
+        hb = oracle.Hitbox(oracle.PlacedShape(rng.uniform(-40, 40), rng.uniform(-40, 40), oracle.Shape(kind, w, w if kind == 0 else float(rng.uniform(0.5, 3.0)))),
+                           oracle.HbVel(rng.uniform(-2, 2), rng.uniform(-2, 2)))
+        c.add_hitbox(id, hb, g, m)
+    assert sorted(index.values()) == [0, 1, 2] and c.d.group_index(7) == index[7]
+    readme_loop(c, 1.5, lambda a, b: None)
+    shapes, ids, masks = [], [], []
+    for k in range(200):
+        kind = int(rng.integers(0, 2))
+        w = float(rng.uniform(1, 15))
+        shapes.append(oracle.PlacedShape(rng.uniform(-40, 40), rng.uniform(-40, 40), oracle.Shape(kind, w, w if kind == 0 else float(rng.uniform(1, 15)))))
+        ids.append(10_000 + k)
+        masks.append(int(rng.integers(1, 8)))
+    got = c.d.query_overlaps_batch(shapes, ids, masks)
+    assert sum(len(g) for g in got) > 100
+    for k in range(200):
+        assert got[k] == sorted(c.o.query_overlaps(shapes[k], ids[k], 0, masks[k])) == sorted(c.d.query_overlaps(shapes[k], ids[k], 0, masks[k]))
+    with pytest.raises(col.ColliderError):
+        for v in range(100, 140):
+            c.d.group_index(v)  # the 33rd distinct value
+
+
 def test_can_interact_filter(oracle):
     s = scenes.make_scene(200, 90.0, seed=scenes.SEED_BASE + 21, squares=True)
     c = Lockstep(oracle, scenes.CELL_WIDTH, scenes.PADDING)

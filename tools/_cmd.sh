@@ -1,9 +1,7 @@
 mkdir -p gpurun_out
-bash tools/gpu_kickoff.sh r2m tests
-timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/r2m_c3.json 2> gpurun_out/r2m_c3.err || { echo "c3 FAILED"; tail -c 2500 gpurun_out/r2m_c3.err; }
-python profiles/bench_summary.py gpurun_out/r2m_c3.json
-python - <<'PY'
-import json
-d=json.load(open("gpurun_out/r2m_c3.json"))
-print("value", d["value"], "e2e", d["e2e"], "\nsteady", d.get("steady_state_window_drain"))
-PY
+nvidia-smi --query-gpu=name --format=csv,noheader | wc -l
+timeout 900 python -m pytest tests/test_sharded_multiprocess_gpu.py -x -q -m gpu --timeout 600 --timeout-method thread > gpurun_out/r2n_mp_tests.log 2>&1; echo "mp tests rc=$?"; tail -5 gpurun_out/r2n_mp_tests.log
+for N in 8 4; do
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/r2n_g$N.json 2> gpurun_out/r2n_g$N.err || { echo "bench g$N FAILED"; tail -c 2500 gpurun_out/r2n_g$N.err; }
+python profiles/bench_summary.py gpurun_out/r2n_g$N.json
+done
