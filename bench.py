@@ -446,8 +446,18 @@ def collider_rows(cb, scenes, device):
     for _ in range(reps):
         d1.bulk_update(end_time=DT, vx=p1[0].array, vy=p1[1].array)
     t_api = (time.perf_counter() - t0) / reps * 1e3
-    rows["collider_api_bulk_update_1m"] = {"workload": "cb200_collider_bulk_update on 1,000,000 hitboxes (config 3 scene), new velocities from page-locked host arrays, queue reset to the device-sorted run",
-                                           "ms_per_call": t_api, "hitbox_updates_per_s": 1_000_000 / (t_api * 1e-3)}
+    # the same with the upload of call k+1's velocities staged beside call k (cb200_stage_velocities on the collider's context)
+    d1.stage_velocities(vx=p1[0].array, vy=p1[1].array)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        d1.stage_velocities(vx=p1[0].array, vy=p1[1].array)
+        d1.bulk_update(end_time=DT)
+    t_api_staged = (time.perf_counter() - t0) / reps * 1e3
+    d1.bulk_update(end_time=DT)
+    rows["collider_api_bulk_update_1m"] = {"workload": "cb200_collider_bulk_update on 1,000,000 hitboxes (config 3 scene), new velocities from page-locked host arrays (16 MB H2D per call), "
+                                                       "queue reset to the device-sorted run",
+                                           "ms_per_call": t_api, "ms_per_call_velocities_staged_ahead": t_api_staged,
+                                           "hitbox_updates_per_s": 1_000_000 / (t_api_staged * 1e-3)}
     del d1
     rows["config2"] = {"workload": f"100k mixed circles/rects, bulk update every {DT} with new velocities (host arrays), events between the steps "
                                    f"processed through next() with velocity halving on Collide, {steps} steps",
@@ -761,6 +771,19 @@ def _main(out):
             "events_sha256_first_timed_step": digests,
             "clocks": sampler.summary(),
         }
+        fpath = os.path.join(ROOT, "profiles", "fp64_peak.json")
+        if args.workload == "c3_dense" and os.path.exists(fpath):
+            # dense scenes: the pair math dominates — state the FP64 bound next to the HBM one.  FP64 arithmetic
+            # instructions (DADD + DMUL + 2 DFMA) per pair solve come from the committed ncu capture of this workload
+            # (profiles/r2/dense_fp64.txt); the peak is the box's measured separate-DMUL+DADD rate (the engine is built -fmad=false)
+            with open(fpath) as f:
+                fp = json.load(f)
+            flop_per_solve = fp["fp64_flop_per_step_1m_dense"] / 29_154_750.0
+            ach = flop_per_solve * P / t_dev / 1e12
+            line["roofline_fp64"] = {"bound": "fp64 (DMUL + DADD, no contraction)", "achieved": ach, "peak": fp["fp64_peak_dmul_dadd_tflops"], "unit": "TFLOP/s",
+                                     "frac": ach / fp["fp64_peak_dmul_dadd_tflops"], "fp64_flop_per_pair_solve": flop_per_solve,
+                                     "note": "neither roofline binds the dense step: the FP64 pipe is 34 % busy (comparisons, min/max, conversions and the "
+                                             "division / sqrt sequences share it) and the kernel is issue- and latency-bound (profiles/r2/dense_fp64.txt, DESIGN 4)"}
         if parity is not None:
             line["parity"] = parity
         if world > 1:

@@ -337,6 +337,16 @@ class Collider:
         self._check(self._L.cb200_collider_run_halving_loop(self._h, t_end, C.byref(ne), C.byref(nc)))
         return ne.value, nc.value
 
+    def stage_velocities(self, vx=None, vy=None):
+        """Start the upload of the NEXT bulk_update's velocities on the engine's upload stream (cb200_stage_velocities on the
+        collider's context); the next bulk_update() without velocity arguments consumes them.  Arrays: ascending-id order, pinned."""
+        n = self.len()
+        self._staged_keep = [None if a is None else _col(a, np.float64, n) for a in (vx, vy, None, None, None)]
+        v = VelView(*[None if a is None else a.ctypes.data for a in self._staged_keep])
+        rc = self._L.cb200_stage_velocities(self._L.cb200_collider_engine(self._h), C.byref(v))
+        if rc != 0:
+            raise ColliderError(rc, self._L.cb200_last_error(self._L.cb200_collider_engine(self._h)).decode())
+
     def set_rebin_threshold(self, rows: int):
         self._check(self._L.cb200_collider_set_rebin_threshold(self._h, rows))
 

@@ -52,7 +52,8 @@ struct DrainArgs {
     uint32_t* pair_bits;
     uint32_t pair_mask;
     uint2* pairs;       // the list the solve stage walks
-    uint32_t cap_pairs;
+    uint32_t cap_pairs;        // capacity of the list
+    uint32_t cap_table_pairs;  // list length up to which new pairs also get a table slot (the table has 2 slots per such pair)
     OvDyn* ov;
     StepResultDev* result;  // mapped host memory
     // the step is complete (will not be re-run with larger buffers) iff ...
@@ -88,27 +89,37 @@ __device__ __forceinline__ bool overlap_kill(unsigned long long* table, uint32_t
         b = (b + 1) & bucket_mask;
     }
 }
-// The pair overlaps now: revive its dead slot (it is in the list already: returns false) or claim a free one (returns true:
-// the caller appends it to the list).
-__device__ __forceinline__ bool overlap_join(unsigned long long* table, uint32_t bucket_mask, unsigned long long key) {
-    uint32_t b = (uint32_t)mix64(key) & bucket_mask;
+// The pair overlaps now.  Its dead slot is revived (it is in the list already), or it is appended to the list and — while
+// the table has room for it (the list length counts the slots ever claimed, so the table stays at most half full and every
+// probe sequence ends) — given a slot.  A pair that found no room is in the list only: the host sees the list outgrow the
+// table (ov_pairs_now > cap_table_pairs) and rebuilds everything larger before the next step; the compaction keeps listed
+// pairs that are absent from the table (k_ov_compact).
+__device__ __forceinline__ void overlap_join(const DrainArgs& a, unsigned long long key, uint32_t hi, uint32_t lo) {
+    uint32_t b = (uint32_t)mix64(key) & a.bucket_mask;
+    bool listed = false;
     for (;;) {
         for (int k = 0; k < 4; ++k) {
-            unsigned long long* slot = &table[4 * (size_t)b + k];
+            unsigned long long* slot = &a.table[4 * (size_t)b + k];
             const unsigned long long q = *slot;
             if (q == (key | kOvDead)) {
                 *slot = key;  // (one thread per pair: no race on this slot)
-                return false;
+                return;
             }
-            if (q == key) return false;
+            if (q == key) return;
             if (q == kKeyMax) {
+                if (!listed) {
+                    const uint32_t pos = atomicAdd(&a.ov->n_pairs, 1u);
+                    if (pos < a.cap_pairs) a.pairs[pos] = make_uint2(hi, lo);
+                    else atomicOr(&a.ov->flags, kDrainOverflow);
+                    listed = true;
+                    if (pos >= a.cap_table_pairs) return;  // no room in the table: listed only
+                }
                 const unsigned long long prev = atomicCAS(slot, kKeyMax, key);
-                if (prev == kKeyMax) return true;
-                if (prev == key) return false;
+                if (prev == kKeyMax) return;
                 // another pair took the slot in the meantime: keep probing from the next slot
             }
         }
-        b = (b + 1) & bucket_mask;
+        b = (b + 1) & a.bucket_mask;
     }
 }
 
@@ -161,11 +172,7 @@ __global__ void __launch_bounds__(kThreads) k_drain_chains(const DrainArgs a) {
             atomicOr(a.bits + (lo >> 5), 1u << (lo & 31u));
             const uint32_t pb = pair_bit_index(mix64(key));
             atomicOr(a.pair_bits + ((pb >> 5) & a.pair_mask), 1u << (pb & 31u));
-            if (overlap_join(a.table, a.bucket_mask, key)) {
-                const uint32_t pos = atomicAdd(&a.ov->n_pairs, 1u);
-                if (pos < a.cap_pairs) a.pairs[pos] = make_uint2(hi, lo);
-                else atomicOr(&a.ov->flags, kDrainOverflow);
-            }
+            overlap_join(a, key, hi, lo);
             atomicAdd(&a.ov->n_add, 1u);
         } else if (!first_collide && !overlapping) {
             if (overlap_kill(a.table, a.bucket_mask, key)) atomicAdd(&a.ov->n_removed, 1u);
@@ -204,11 +211,28 @@ __global__ void __launch_bounds__(kThreads) k_drain_chains(const DrainArgs a) {
     ov->done_blocks = 0u;
 }
 
-// Host-triggered compaction (engine.cu compact_overlaps): the live pairs of the list, in list order.
-__global__ void __launch_bounds__(kThreads) k_ov_compact(const uint2* __restrict__ pairs, uint32_t n_pairs, const OverlapSet ov, uint2* out, uint32_t* n_out) {
+// Host-triggered compaction (engine.cu compact_overlaps): the pairs of the list that are not marked dead in the table — live,
+// or listed without a slot (overlap_join) — in list order.
+__global__ void __launch_bounds__(kThreads) k_ov_compact(const uint2* __restrict__ pairs, uint32_t n_pairs, const unsigned long long* __restrict__ table,
+                                                         uint32_t bucket_mask, uint2* out, uint32_t* n_out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
         const uint2 pr = pairs[i];
-        if (!overlap_contains(ov, pr.x, pr.y)) continue;
+        const unsigned long long key = ((unsigned long long)pr.x << 32) | pr.y;
+        bool dead = false;
+        uint32_t b = (uint32_t)mix64(key) & bucket_mask;
+        for (bool done = false; !done;) {
+            for (int k = 0; k < 4 && !done; ++k) {
+                const unsigned long long q = table[4 * (size_t)b + k];
+                if (q == (key | kOvDead)) {
+                    dead = true;
+                    done = true;
+                } else if (q == key || q == kKeyMax) {
+                    done = true;
+                }
+            }
+            b = (b + 1) & bucket_mask;
+        }
+        if (dead) continue;
         out[warp_agg_claim32(n_out)] = pr;
     }
 }

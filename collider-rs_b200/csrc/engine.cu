@@ -638,8 +638,7 @@ static int compact_overlaps(cb200_ctx* ctx) {
     if (len) {
         uint32_t* d_n = &ctx->d_ov->n_add;  // (a scratch word: zero between steps)
         CU(cudaMemsetAsync(d_n, 0, 4, ctx->stream));
-        const OverlapSet ov{reinterpret_cast<const ulonglong2*>(ctx->ov_table.p), ctx->ov_bits.p, ctx->ov_bucket_mask, 1u, ctx->ov_pair_bits.p, ctx->ov_pair_mask};
-        k_ov_compact<<<(uint32_t)ctx->sm_count * 4u, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, len, ov, ctx->ov_pairs_new.p, d_n);
+        k_ov_compact<<<(uint32_t)ctx->sm_count * 4u, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, len, ctx->ov_table.p, ctx->ov_bucket_mask, ctx->ov_pairs_new.p, d_n);
         ctx->launches += 1;
         CU(cudaMemcpyAsync(&n_live, d_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -1045,6 +1044,7 @@ static int enqueue_drain(cb200_ctx* ctx, bool is_tile) {
     d.pair_mask = ctx->ov_pair_mask;
     d.pairs = ctx->ov_pairs.p;
     d.cap_pairs = (uint32_t)std::min<size_t>(ctx->ov_pairs.cap, 0x7fffffffu);
+    d.cap_table_pairs = ctx->ov_cap_pairs;
     d.ov = ctx->d_ov;
     d.result = ctx->d_res;
     d.cap_entries = (uint32_t)std::min<size_t>(ctx->entries.cap, 0xffffffffu);

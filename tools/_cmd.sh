@@ -1,7 +1,9 @@
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name --format=csv,noheader | wc -l
-timeout 900 python -m pytest tests/test_sharded_multiprocess_gpu.py -x -q -m gpu --timeout 600 --timeout-method thread > gpurun_out/r2n_mp_tests.log 2>&1; echo "mp tests rc=$?"; tail -5 gpurun_out/r2n_mp_tests.log
-for N in 8 4; do
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$N bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/r2n_g$N.json 2> gpurun_out/r2n_g$N.err || { echo "bench g$N FAILED"; tail -c 2500 gpurun_out/r2n_g$N.err; }
-python profiles/bench_summary.py gpurun_out/r2n_g$N.json
-done
+bash tools/gpu_kickoff.sh r2p bench
+bash tools/gpu_kickoff.sh r2p ncu
+NOX="--no-cpu-baseline --no-collider-rows --no-parity --no-config4 --no-steady-state --repeats 1"
+timeout 300 ncu --metrics gpu__time_duration.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active \
+  --clock-control none -k regex:'k_solve' --launch-skip 40 -c 4 --csv --log-file gpurun_out/r2p_dense_fp64.csv \
+  python bench.py --steps 5 --warmup 5 $NOX --workload c3_dense > gpurun_out/r2p_dense_fp64.log 2>&1; echo "ncu fp64 rc=$?"
+./tools/fp64_peak > gpurun_out/r2p_fp64_peak.json; cat gpurun_out/r2p_fp64_peak.json
+timeout 300 python -m pytest tests/test_collider_gpu.py -x -q -m gpu -k "batched_queries" 2>&1 | tail -3
