@@ -180,7 +180,9 @@ struct cb200_ctx {
     // window drain (drain.cuh): the overlap set lives on the device from step to step
     bool ov_track = false, ov_ready = false;
     OvDyn* d_ov = nullptr;
-    DevBuf<uint2> ov_pairs_new;   // compaction target
+    DevBuf<uint2> ov_pairs_new;   // compaction target / sort scratch
+    DevBuf<uint32_t> ov_sort_hist;
+    bool ov_sort = false;         // CB200_OV_SORT=1: keep the overlapping-pair list in the row order of its first hitbox (measured: 1 % on the dense solve stage)
     uint32_t ov_cap_pairs = 0, ov_n_keys = 0, ov_bit_words = 0;
     uint32_t ov_list_len = 0;     // host mirror of OvDyn.n_pairs (the list also holds the pairs that separated since the last rebuild)
     uint64_t drain_reiterates = 0;  // Reiterate events that fell inside a drained window (the drain is exact only without them)
@@ -396,6 +398,7 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaHostGetDevicePointer((void**)&c->d_sort_big, c->h_sort_big, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     if (const char* so = getenv("CB200_SORT")) c->sort_oneshot = strcmp(so, "slow") != 0;
     if (const char* v = getenv("CB200_TILE")) c->tile_enabled = v[0] != '0';
+    if (const char* v = getenv("CB200_OV_SORT")) c->ov_sort = v[0] != '0';
     if (const char* v = getenv("CB200_TILE_TARGET")) c->tile_target = (uint32_t)std::max(16, std::min(2048, atoi(v)));
     if (const char* v = getenv("CB200_TILE_CAP")) {
         c->tile_cap_rec = (uint32_t)std::max(16, std::min(512, atoi(v)));
@@ -426,7 +429,7 @@ void cb200_destroy(cb200_ctx* c) {
     for (auto& g : c->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     c->slots.release(); c->chunk_base.release(); c->entries.release(); c->work.release(); c->work_count.release(); c->dense.release();
-    c->ov_pairs_new.release(); if (c->d_ov) cudaFree(c->d_ov);
+    c->ov_pairs_new.release(); c->ov_sort_hist.release(); if (c->d_ov) cudaFree(c->d_ov);
     c->ov_pairs.release(); c->ov_table.release(); c->ov_bits.release(); c->ov_pair_bits.release(); c->ov_ida.release(); c->ov_idb.release();
     c->events.release(); c->partial.release();
     c->tile_rows.release(); c->home.release(); c->vis_count.release(); c->vis.release(); c->surv.release();
@@ -580,6 +583,22 @@ int cb200_download_state(cb200_ctx* ctx, const cb200_state_out* o) {
 }
 
 static int gid_to_id_table(cb200_ctx* ctx, std::vector<uint64_t>& ids);
+// Put the overlapping-pair list into the row order of its first hitbox (kernels.cuh "Order of the overlapping-pair list").
+static int sort_overlap_pairs(cb200_ctx* ctx, uint32_t n_list) {
+    if (!ctx->ov_sort || ctx->sharded || n_list < 65536u || ctx->n < 2) return CB200_OK;
+    const int shift = 8;
+    const uint32_t n_buckets = (ctx->n >> shift) + 2u;
+    CU(ctx->ov_sort_hist.reserve(n_buckets));
+    CU(ctx->ov_pairs_new.reserve(std::max<size_t>(n_list, ctx->ov_pairs_new.cap)));
+    CU(cudaMemsetAsync(ctx->ov_sort_hist.p, 0, (size_t)n_buckets * 4, ctx->stream));
+    const uint32_t g = (uint32_t)ctx->sm_count * 8u, n_labels = (uint32_t)std::min<size_t>(ctx->row_of.cap, 0xffffffffu);
+    k_ovsort_count<<<g, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, n_list, ctx->row_of.p, n_labels, shift, n_buckets, ctx->ov_sort_hist.p);
+    k_ovsort_scan<<<1, 1024, 0, ctx->stream>>>(ctx->ov_sort_hist.p, n_buckets);
+    k_ovsort_scatter<<<g, kThreads, 0, ctx->stream>>>(ctx->ov_pairs.p, n_list, ctx->row_of.p, n_labels, shift, n_buckets, ctx->ov_sort_hist.p, ctx->ov_pairs_new.p);
+    CU(cudaMemcpyAsync(ctx->ov_pairs.p, ctx->ov_pairs_new.p, (size_t)n_list * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->launches += 3;
+    return CB200_OK;
+}
 static int compact_overlaps(cb200_ctx* ctx);
 static inline uint64_t id_of(const std::vector<uint64_t>& ids, uint32_t gid);
 
@@ -627,7 +646,7 @@ static int build_overlap_tables(cb200_ctx* ctx, uint32_t np) {
     ctx->ov_n_keys = cap;
     ctx->ov_bit_words = (uint32_t)n_words;
     ctx->ov_ready = ctx->ov_track;
-    return CB200_OK;
+    return ctx->need_resort ? CB200_OK : sort_overlap_pairs(ctx, np);  // (before the first re-sort the rows are still in upload order)
 }
 
 // Window drain housekeeping: drop the pairs that separated since the last rebuild from the list and rebuild the tables.
@@ -886,6 +905,11 @@ static int resort_rows(cb200_ctx* ctx) {
     std::swap(ctx->mask, ctx->mask_alt); std::swap(ctx->label, ctx->label_alt);
     if (ctx->sharded) std::swap(ctx->ord, ctx->ord_alt);
     ctx->resorts += 1;
+    {
+        const uint32_t n_list = (ctx->ov_track && ctx->ov_ready) ? ctx->ov_list_len : ctx->n_ov;
+        int rc2 = sort_overlap_pairs(ctx, n_list);  // (the rows moved: the pair list follows)
+        if (rc2 != CB200_OK) return rc2;
+    }
     return CB200_OK;
 }
 

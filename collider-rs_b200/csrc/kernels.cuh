@@ -832,6 +832,43 @@ __global__ void k_overlap_insert(const uint2* __restrict__ pairs, uint32_t n_pai
         b = (b + 1) & bucket_mask;
     }
 }
+// Order of the overlapping-pair list.  The solve stage gathers both records of every listed pair; rows are kept in grid-slot
+// order, and two overlapping hitboxes are neighbours, so a list ordered by the ROW of its first hitbox turns those gathers into
+// near-sequential reads (config-4 density: 3.4 M pairs per million hitboxes, 650 MB of gathers per step).  A counting sort on
+// row >> shift (buckets of 2^shift rows; the order inside a bucket does not matter), redone after every re-sort of the table.
+__global__ void __launch_bounds__(kThreads) k_ovsort_count(const uint2* __restrict__ pairs, uint32_t n_pairs, const uint32_t* __restrict__ row_of, uint32_t n_labels,
+                                                           int shift, uint32_t n_buckets, uint32_t* hist) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
+        const uint32_t hi = pairs[i].x;
+        const uint32_t row = hi < n_labels ? row_of[hi] : 0xffffffffu;
+        atomicAdd(&hist[min(row >> shift, n_buckets - 1u)], 1u);
+    }
+}
+__global__ void __launch_bounds__(1024) k_ovsort_scan(uint32_t* hist, uint32_t n_buckets) {  // one block: hist -> exclusive prefix (cursors)
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_buckets; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_buckets ? hist[i] : 0u;
+        uint32_t total;
+        const uint32_t excl = block_excl_scan(v, &total);
+        const uint32_t carry = s_carry;
+        if (i < n_buckets) hist[i] = carry + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_ovsort_scatter(const uint2* __restrict__ pairs, uint32_t n_pairs, const uint32_t* __restrict__ row_of, uint32_t n_labels,
+                                                             int shift, uint32_t n_buckets, uint32_t* cursor, uint2* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
+        const uint2 pr = pairs[i];
+        const uint32_t row = pr.x < n_labels ? row_of[pr.x] : 0xffffffffu;
+        out[atomicAdd(&cursor[min(row >> shift, n_buckets - 1u)], 1u)] = pr;
+    }
+}
+
 // ids -> slots (binary search in the ascending id column); pairs out as (hi slot, lo slot).
 __global__ void k_overlap_map_ids(const uint64_t* __restrict__ ids, uint32_t n, const uint64_t* __restrict__ id_a,
                                   const uint64_t* __restrict__ id_b, uint32_t n_pairs, uint2* pairs, Counters* ctr) {

@@ -1,9 +1,16 @@
-mkdir -p gpurun_out
-bash tools/gpu_kickoff.sh r2p bench
-bash tools/gpu_kickoff.sh r2p ncu
-NOX="--no-cpu-baseline --no-collider-rows --no-parity --no-config4 --no-steady-state --repeats 1"
-timeout 300 ncu --metrics gpu__time_duration.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active \
-  --clock-control none -k regex:'k_solve' --launch-skip 40 -c 4 --csv --log-file gpurun_out/r2p_dense_fp64.csv \
-  python bench.py --steps 5 --warmup 5 $NOX --workload c3_dense > gpurun_out/r2p_dense_fp64.log 2>&1; echo "ncu fp64 rc=$?"
-./tools/fp64_peak > gpurun_out/r2p_fp64_peak.json; cat gpurun_out/r2p_fp64_peak.json
-timeout 300 python -m pytest tests/test_collider_gpu.py -x -q -m gpu -k "batched_queries" 2>&1 | tail -3
+timeout 100 python - <<'PY'
+import importlib, time, sys, numpy as np
+sys.path.insert(0, ".")
+cb = importlib.import_module("collider-rs_b200"); scenes = importlib.import_module("collider-rs_b200.scenes")
+s = scenes.c3_dense(1_000_000)
+eng = cb.Engine(4.0, 0.01); eng.upload_state(**s); eng.set_window_drain(True); eng.set_stage_timing(False)
+pin = cb.PinnedArray(4_000_000, cb.EVENT16_DTYPE)
+T = 0.0
+for k in range(24):
+    t0 = time.perf_counter(); r = eng.bulk_update(T, end_time=T + 0.1); t1 = time.perf_counter()
+    got = eng.fetch_events_begin(pin.array); t2 = time.perf_counter(); eng.fetch_events_end(); t3 = time.perf_counter()
+    T += 0.1
+    d = eng.last_drain()
+    if k % 3 == 0 or k > 18:
+        print(k, "step %.2f ms  begin %.2f  end %.2f" % ((t1-t0)*1e3, (t2-t1)*1e3, (t3-t2)*1e3), "events", r.n_events, "live", d["pairs_now"], "added", d["pairs_added"], "removed", d["pairs_removed"], "launches", eng.launch_count(), "fallbacks", eng.event_sort_fallbacks(), flush=True)
+PY
