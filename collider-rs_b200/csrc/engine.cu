@@ -207,6 +207,8 @@ struct cb200_ctx {
     DevBuf<uint32_t> bs_tab[5];  // bucket sort, one per recursion depth: counts / offsets, cursors, oversized buckets, range
     DevBuf<EventOut> ev_out;
     Key128* sorted_keys = nullptr;  // where the last sort left the sorted keys (keys_a or keys_b)
+    bool ev_out_valid = false;      // ev_out holds the 32-byte records of the sorted keys
+    cudaEvent_t ev_keys_done = nullptr;
     bool ev_sorted = false;
     // pipelined I/O: compact events leave on their own copy stream (double-buffered), staged velocities arrive on another
     DevBuf<Event16> ev16[2];
@@ -438,7 +440,7 @@ void cb200_destroy(cb200_ctx* c) {
         for (auto& b : set) b.release();
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
-    for (cudaEvent_t e : {c->ev_sorted_done, c->ev_staged_done[0], c->ev_staged_done[1]})
+    for (cudaEvent_t e : {c->ev_sorted_done, c->ev_staged_done[0], c->ev_staged_done[1], c->ev_keys_done})
         if (e) cudaEventDestroy(e);
     c->keys_a.release(); c->keys_b.release(); c->rs_hist.release(); for (auto& b : c->bs_tab) b.release(); c->imm_pairs.release(); if (c->d_n_imm) cudaFree(c->d_n_imm); c->ev_out.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
@@ -1934,7 +1936,11 @@ static int build_sort_keys(cb200_ctx* ctx, uint32_t n_pairs, uint64_t n_solitair
 // One-shot bucket sort (sort.cuh): everything is queued without a host round trip — keys, two-region bucket cut, rank sort,
 // decode into ev_out.  Whether it succeeded (no bucket too large for a warp) is in ctx->h_sort_big[0] once the stream has
 // been synchronised; the caller checks it and falls back to sort_events_slow.
-static int enqueue_sort_oneshot(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, uint64_t n_solitaire) {
+// `st`: the stream the sort itself runs on.  The order keys are always built on the context's stream (they read the step's
+// event buffer and state columns, which the next step overwrites); with st != ctx->stream the bucket sort then runs beside
+// whatever the context's stream does next (cb200_fetch_events_begin: beside the next bulk step).  decode32: also decode the
+// sorted keys into the 32-byte cb200_event records (ev_out).
+static int enqueue_sort_oneshot(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, uint64_t n_solitaire, cudaStream_t st, bool decode32) {
     int log2_buckets = 6;
     while ((1u << log2_buckets) * 8u < nt && log2_buckets < 24) ++log2_buckets;  // ~8 keys per bucket (a warp sorts up to 256)
     const uint32_t nb = 1u << log2_buckets, n_buckets = 2 * nb;  // region A (ties at the first time) + region B (by time)
@@ -1950,16 +1956,21 @@ static int enqueue_sort_oneshot(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, u
     CU(cudaMemcpyAsync(range, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     int rc = build_sort_keys(ctx, n_pairs, n_solitaire, range, range + 1);
     if (rc != CB200_OK) return rc;
+    if (st != ctx->stream) {
+        CU(cudaEventRecord(ctx->ev_keys_done, ctx->stream));
+        CU(cudaStreamWaitEvent(st, ctx->ev_keys_done, 0));
+    }
     const uint32_t blocks = (nt + kThreads - 1) / kThreads;
     Key128 *keys = ctx->keys_a.p, *tmp = ctx->keys_b.p;
-    k_bs2_count<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, range, log2_buckets, count);
-    k_bs2_scan_local<<<scan_blocks, 256, 0, ctx->stream>>>(count, n_buckets, cursor, block_total);
-    k_bs2_scan_add<<<scan_blocks, 256, 0, ctx->stream>>>(count, n_buckets, cursor, block_total, ctx->d_sort_big);
-    k_bs2_scatter<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, range, log2_buckets, cursor, tmp);
-    k_bs_local<<<std::min<uint32_t>((n_buckets + 7) / 8, (uint32_t)ctx->sm_count * 8u), 256, 0, ctx->stream>>>(tmp, count, n_buckets, keys);
-    k_decode_events<<<blocks, kThreads, 0, ctx->stream>>>(nt, keys, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p, ctx->last_add_mode ? 1 : 0);
+    k_bs2_count<<<blocks, kThreads, 0, st>>>(nt, keys, range, log2_buckets, count);
+    k_bs2_scan_local<<<scan_blocks, 256, 0, st>>>(count, n_buckets, cursor, block_total);
+    k_bs2_scan_add<<<scan_blocks, 256, 0, st>>>(count, n_buckets, cursor, block_total, ctx->d_sort_big);
+    k_bs2_scatter<<<blocks, kThreads, 0, st>>>(nt, keys, range, log2_buckets, cursor, tmp);
+    k_bs_local<<<std::min<uint32_t>((n_buckets + 7) / 8, (uint32_t)ctx->sm_count * 8u), 256, 0, st>>>(tmp, count, n_buckets, keys);
+    if (decode32) k_decode_events<<<blocks, kThreads, 0, st>>>(nt, keys, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p, ctx->last_add_mode ? 1 : 0);
+    ctx->ev_out_valid = decode32;
     ctx->sorted_keys = keys;
-    ctx->launches += 6;
+    ctx->launches += decode32 ? 6 : 5;
     CU(cudaGetLastError());
     return CB200_OK;
 }
@@ -1994,6 +2005,7 @@ static int sort_events_slow(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, uint6
     }
     k_decode_events<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(nt, in, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p, ctx->last_add_mode ? 1 : 0);
     ctx->sorted_keys = in;
+    ctx->ev_out_valid = true;
     ctx->launches += 1;
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaGetLastError());
@@ -2004,6 +2016,22 @@ static int sort_events_slow(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, uint6
 // behind the sort, so a fetch costs one synchronisation.
 static int sort_events_to(cb200_ctx* ctx, EventOut* copy_to, uint64_t offset, uint64_t cap, uint64_t* taken) {
     if (taken) *taken = 0;
+    if (ctx->fetch_pending) {  // (a pipelined download may still be sorting on the copy stream: it shares the key buffers)
+        CU(cudaStreamSynchronize(ctx->d2h_stream));
+    }
+    if (ctx->ev_sorted && !ctx->ev_out_valid && ctx->n_ev_sorted) {
+        // sorted by a pipelined fetch, which only produced the compact records: decode the 32-byte ones now
+        if (ctx->d2h_stream) CU(cudaStreamSynchronize(ctx->d2h_stream));
+        if (ctx->sort_oneshot && ctx->h_sort_big[0] != 0) {
+            ctx->ev_sorted = false;  // (that sort met an oversized bucket: sort again below, with the fallback)
+        } else {
+            const uint32_t n = (uint32_t)ctx->n_ev_sorted;
+            CU(ctx->ev_out.reserve(n));
+            k_decode_events<<<(n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(n, ctx->sorted_keys, ctx->sharded ? nullptr : ctx->ids.p, ctx->ev_out.p, ctx->last_add_mode ? 1 : 0);
+            ctx->launches += 1;
+            ctx->ev_out_valid = true;
+        }
+    }
     const bool was_sorted = ctx->ev_sorted;
     uint32_t nt = 0, n_pairs = 0;
     uint64_t n_solitaire = 0;
@@ -2018,7 +2046,7 @@ static int sort_events_to(cb200_ctx* ctx, EventOut* copy_to, uint64_t offset, ui
         if (nt) {
             CU(ctx->keys_a.reserve(nt)); CU(ctx->keys_b.reserve(nt)); CU(ctx->ev_out.reserve(nt));
             ctx->h_sort_big[0] = 0;
-            int rc = ctx->sort_oneshot ? enqueue_sort_oneshot(ctx, nt, n_pairs, n_solitaire) : sort_events_slow(ctx, nt, n_pairs, n_solitaire);
+            int rc = ctx->sort_oneshot ? enqueue_sort_oneshot(ctx, nt, n_pairs, n_solitaire, ctx->stream, true) : sort_events_slow(ctx, nt, n_pairs, n_solitaire);
             if (rc != CB200_OK) return rc;
         }
     }
@@ -2065,6 +2093,7 @@ static int ensure_io_streams(cb200_ctx* ctx) {
     CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&ctx->ev_sorted_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_keys_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_staged_done[0], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_staged_done[1], cudaEventDisableTiming));
     return CB200_OK;
@@ -2116,21 +2145,25 @@ int cb200_fetch_events_begin(cb200_ctx* ctx, cb200_event16* buf, uint64_t cap, u
     ctx->fetch_oneshot_pending = false;
     if (nt) {
         CU(ctx->keys_a.reserve(nt)); CU(ctx->keys_b.reserve(nt)); CU(dst.reserve(nt));
+        bool on_copy_stream = false;
         if (!ctx->ev_sorted) {
             ctx->n_ev_sorted = total;
             ctx->h_sort_big[0] = 0;
             if (ctx->sort_oneshot) {
-                CU(ctx->ev_out.reserve(nt));
-                if ((rc = enqueue_sort_oneshot(ctx, nt, (uint32_t)c.n_pair_events, c.n_solitaire)) != CB200_OK) return rc;
+                // keys on the context's stream (a few microseconds), the bucket sort on the copy stream: the next bulk step does
+                // not wait for it
+                if ((rc = enqueue_sort_oneshot(ctx, nt, (uint32_t)c.n_pair_events, c.n_solitaire, ctx->d2h_stream, false)) != CB200_OK) return rc;
                 ctx->fetch_oneshot_pending = true;  // (whether it held is known once the stream has run: checked in _end)
+                on_copy_stream = true;
             } else {
                 CU(ctx->ev_out.reserve(nt));
                 if ((rc = sort_events_slow(ctx, nt, (uint32_t)c.n_pair_events, c.n_solitaire)) != CB200_OK) return rc;
             }
             ctx->ev_sorted = true;
         }
-        // the sorted keys are in keys_a: decode them once more into the compact form
-        k_decode_events16<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(nt, ctx->sorted_keys, dst.p, ctx->last_add_mode ? 1 : 0);
+        // the sorted keys -> compact records, on the stream that sorted them
+        cudaStream_t ds = on_copy_stream ? ctx->d2h_stream : ctx->stream;
+        k_decode_events16<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ds>>>(nt, ctx->sorted_keys, dst.p, ctx->last_add_mode ? 1 : 0);
         ctx->launches += 1;
     }
     CU(cudaEventRecord(ctx->ev_sorted_done, ctx->stream));
