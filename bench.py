@@ -8,7 +8,7 @@ density 0.025/unit^2, cell 4, padding 0.01, bulk step every 0.1 time units).  N>
 per GPU; the same line carries a `config4` block (16,777,216 shapes in 4096^2 split over the N strips — strong scaling; the
 N=1 line carries the one-GPU anchor).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n HITBOXES] [--workload c3|c3_dense|c5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n HITBOXES] [--workload c3|c3_dense|c5|c3_groups]
 
 ONE JSON line on stdout (rank 0):
   value / ms_per_step   t_step of SURVEY 8(d): device-resident state, bulk step + queue materialisation + D2H of the sorted
@@ -46,7 +46,7 @@ METRIC = "hitbox updates/sec (full re-bin + pair TOI solve + next-event min + or
 UNIT = "hitbox updates/s"
 C4_TOTAL = 16_777_216
 C4_SIDE = 4096.0
-DENSITY = {"c3": 0.025, "c3_dense": 1.0, "c5": 0.025}
+DENSITY = {"c3": 0.025, "c3_dense": 1.0, "c5": 0.025, "c3_groups": 0.025}
 
 
 def load_peaks():
@@ -69,6 +69,8 @@ def make_workload(scenes, name: str, n: int, rank: int, world: int):
     if name in ("c3", "c3_dense"):
         side = math.sqrt(n / DENSITY[name])
         s = scenes.make_scene(n, side, side, seed=scenes.SEED_BASE + 3 + 1000 * rank, x0=side * rank)
+    elif name == "c3_groups":  # f-4: resizing shapes in four groups (single GPU)
+        s = scenes.c3_groups(n)
     elif name == "c5":
         s = scenes.c5(n)
         s["pos_x"] = s["pos_x"] + math.sqrt(n / 0.025) * rank
@@ -523,6 +525,43 @@ def config4_block(cb, scenes, sharding, dist, rank, world, local_rank, barrier, 
             "event_sort_fallbacks": fallbacks, "pipelined_fetch_failures": failures[0], "scaling": "strong (fixed 16,777,216 hitboxes; compare with the n_gpus=1 line's block)"}
 
 
+def migration_block(cb, scenes, sharding, dist, args, rank, world, local_rank, barrier, steps=64, every=16):
+    """N > 1: a run in which the residents follow their strips (SURVEY.md 8e owner migration): every `every` steps each rank
+    hands the rows whose centre left its strip by more than one column to the rank that holds them (ShardedEngine.migrate —
+    collective, through the host).  Hitboxes keep their velocities, so they drift up to 0.2 units per step."""
+    import torch
+
+    job = Job(cb, scenes, sharding, dist, args.workload, args.n, rank, world, local_rank, grid=args.grid)
+    job.first_step()
+    job.eng.set_stage_timing(False)
+    for _ in range(args.warmup):
+        job.device_step()
+    acc = {"out": 0, "in": 0, "mig_s": 0.0}
+
+    def body():
+        for _ in range(every):
+            job.device_step()
+        t0 = time.perf_counter()
+        o, i = job.sh.migrate(1)
+        acc["mig_s"] += time.perf_counter() - t0
+        acc["out"] += o
+        acc["in"] += i
+        return {}
+
+    walls, _ = timed_passes(job, barrier, steps // every, 1, body)
+    rows = job.eng.shard_rows()
+    t = torch.tensor([walls[0], acc["mig_s"]], dtype=torch.float64, device="cuda")
+    c = torch.tensor([float(acc["out"]), float(acc["in"]), float(rows["rows"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    wall, mig = t.tolist()
+    n_out, n_in, n_rows = c.tolist()
+    calls = steps // every
+    return {"what": f"device-resident steps with owner migration every {every} steps (margin 1 column): rows whose centre left their rank's strip move to the rank that holds them",
+            "steps": calls * every, "migrations": calls, "rows_moved_all_ranks": int(n_out), "rows_received_all_ranks": int(n_in), "rows_resident_all_ranks": int(n_rows),
+            "ms_per_migration_max_rank": mig / calls * 1e3, "ms_per_step_including_migration": wall / (calls * every) * 1e3}
+
+
 def steady_state_block(cb, scenes, sharding, dist, args, rank, world, local_rank, barrier, K):
     """The same workload with the window drain on (cb200_set_window_drain): the pair events inside each step's window are
     processed on the device (chains included) and the overlap set stays device-resident, as in a run whose caller pops every
@@ -570,7 +609,7 @@ def _main(out):
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", "--hitboxes", dest="n", type=int, default=1_000_000, help="hitboxes per GPU")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c3_dense", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c3_dense", "c5", "c3_groups"])
     ap.add_argument("--repeats", type=int, default=3, help="runs of K steps; the median run is reported")
     ap.add_argument("--ref-sample", type=int, default=500_000, help="hitboxes in the cpu_baseline sample of the GPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -578,6 +617,7 @@ def _main(out):
     ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--no-collider-rows", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-migration", action="store_true", help="skip the owner-migration block of the N>1 lines")
     ap.add_argument("--no-steady-state", dest="steady_state", action="store_false", help="skip the window-drain (steady-state) block of the N=1 line")
     ap.add_argument("--drain", action="store_true", help="window drain: pair events inside each step's window processed on the device, overlap set device-resident")
     ap.add_argument("--grid", default="", help="force the device grid period: log2_w,log2_h")
@@ -710,6 +750,10 @@ def _main(out):
         del job, eng
         steady = steady_state_block(cb, scenes, sharding, dist, args, rank, world, local_rank, barrier, K)
         job = eng = None
+    migration = None
+    if world > 1 and not args.no_migration:
+        job = eng = None
+        migration = migration_block(cb, scenes, sharding, dist, args, rank, world, local_rank, barrier)
     c4 = None
     if not args.no_config4 and args.workload == "c3":
         job = eng = None
@@ -792,6 +836,8 @@ def _main(out):
                                                 if os.environ.get("CB200_EXCHANGE", "direct") != "nccl" else "exchanged by two NCCL all-gathers"))
         if steady is not None:
             line["steady_state_window_drain"] = steady
+        if migration is not None:
+            line["owner_migration"] = migration
         if c4 is not None:
             line["config4"] = c4
         if not args.no_cpu_baseline and world == 1:

@@ -50,6 +50,15 @@ class StateOut(C.Structure):
     ]
 
 
+ROW_F64 = ("pos_x", "pos_y", "dim_x", "dim_y", "vel_x", "vel_y", "rsz_x", "rsz_y", "start_time", "end_time", "pub_end_time")
+
+
+class RowsOut(C.Structure):
+    """cb200_rows_out"""
+    _fields_ = [("cap", C.c_uint64), ("id", C.c_void_p)] + [(k, C.c_void_p) for k in ROW_F64] + [
+        ("kind", C.c_void_p), ("group", C.c_void_p), ("interact_mask", C.c_void_p), ("dest", C.c_void_p)]
+
+
 class VelView(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("vel_x", "vel_y", "rsz_x", "rsz_y", "end_time")]
 
@@ -92,7 +101,7 @@ EXPORTS = (
     "cb200_fetch_index_rects", "cb200_collide_time_batch", "cb200_separate_time_batch", "cb200_launch_count",
     "cb200_last_step_timing", "cb200_reset_timing", "cb200_shard_configure", "cb200_shard_set_slab", "cb200_set_stream", "cb200_shard_begin", "cb200_shard_finish",
     "cb200_shard_result", "cb200_set_resort_period", "cb200_resort_count", "cb200_event_sort_fallbacks", "cb200_set_stage_timing",
-    "cb200_shard_p2p_export", "cb200_shard_p2p_import", "cb200_shard_step", "cb200_shard_global_next", "cb200_shard_local_key", "cb200_shard_abort", "cb200_stage_velocities", "cb200_fetch_events_begin", "cb200_fetch_events_end", "cb200_set_window_drain", "cb200_fetch_overlaps", "cb200_last_drain", "cb200_last_step_path", "cb200_tile_fallbacks", "cb200_get_tile",
+    "cb200_shard_p2p_export", "cb200_shard_p2p_import", "cb200_shard_step", "cb200_shard_global_next", "cb200_shard_local_key", "cb200_shard_abort", "cb200_shard_set_row_capacity", "cb200_shard_rows", "cb200_shard_take_movers", "cb200_shard_add_rows", "cb200_stage_velocities", "cb200_fetch_events_begin", "cb200_fetch_events_end", "cb200_set_window_drain", "cb200_fetch_overlaps", "cb200_last_drain", "cb200_last_step_path", "cb200_tile_fallbacks", "cb200_get_tile",
     "cb200_collider_new", "cb200_collider_free", "cb200_collider_last_error", "cb200_collider_set_can_interact", "cb200_collider_time",
     "cb200_collider_next_time", "cb200_collider_set_time", "cb200_collider_next", "cb200_collider_get_hitbox", "cb200_collider_add_hitbox",
     "cb200_collider_set_hitbox_vel", "cb200_collider_remove_hitbox", "cb200_collider_get_overlaps", "cb200_collider_is_overlapping",
@@ -153,6 +162,10 @@ def load_library() -> C.CDLL:
     L.cb200_shard_local_key.argtypes = [vp]
     L.cb200_shard_local_key.restype = vp
     L.cb200_shard_abort.argtypes = [vp]
+    L.cb200_shard_set_row_capacity.argtypes = [vp, u64]
+    L.cb200_shard_rows.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+    L.cb200_shard_take_movers.argtypes = [vp, i32, C.POINTER(RowsOut), C.POINTER(u64)]
+    L.cb200_shard_add_rows.argtypes = [vp, C.POINTER(StateView)]
     L.cb200_last_step_path.argtypes = [vp]
     L.cb200_stage_velocities.argtypes = [vp, C.POINTER(VelView)]
     L.cb200_fetch_events_begin.argtypes = [vp, vp, u64, C.POINTER(u64)]
@@ -303,6 +316,53 @@ class Engine:
 
     def shard_set_slab(self, records: int):
         self._check(self._L.cb200_shard_set_slab(self._h, records))
+
+    def shard_set_row_capacity(self, rows: int):
+        self._check(self._L.cb200_shard_set_row_capacity(self._h, rows))
+
+    def shard_rows(self) -> dict:
+        v = [C.c_uint64(0) for _ in range(4)]
+        self._check(self._L.cb200_shard_rows(self._h, *[C.byref(x) for x in v]))
+        return dict(rows=v[0].value, capacity=v[1].value, migrated_out=v[2].value, migrated_in=v[3].value)
+
+    def shard_take_movers(self, margin_cols: int = 1):
+        """Owner migration, sending side: (rows, dest) — `rows` a dict of columns (id, the 11 state columns, kind, group,
+        interact_mask) of the rows that left this rank's strip, dest[i] the rank that should take row i.  They are removed here."""
+        need = C.c_uint64(0)
+        rc = self._L.cb200_shard_take_movers(self._h, margin_cols, None, C.byref(need))
+        m = need.value
+        rows = {"id": np.zeros(m, np.uint64), **{k: np.zeros(m) for k in ROW_F64}, "kind": np.zeros(m, np.uint8),
+                "group": np.zeros(m, np.uint32), "interact_mask": np.zeros(m, np.uint32)}
+        dest = np.zeros(m, np.int32)
+        if m == 0:
+            self._check(rc)
+            return rows, dest
+        o = RowsOut()
+        o.cap = m
+        for k, a in rows.items():
+            setattr(o, k, a.ctypes.data)
+        o.dest = dest.ctypes.data
+        self._check(self._L.cb200_shard_take_movers(self._h, margin_cols, C.byref(o), C.byref(need)))
+        assert need.value == m
+        self.n -= m
+        return rows, dest
+
+    def shard_add_rows(self, rows: dict):
+        """Owner migration, receiving side: append rows (a dict like shard_take_movers returns; any order)."""
+        m = len(rows["id"])
+        if m == 0:
+            return 0
+        o = np.argsort(np.asarray(rows["id"], dtype=np.uint64), kind="stable")
+        cols = {"id": _col(np.asarray(rows["id"])[o], np.uint64, m), **{k: _col(np.asarray(rows[k])[o], np.float64, m) for k in ROW_F64},
+                "kind": _col(np.asarray(rows["kind"])[o], np.uint8, m), "group": _col(np.asarray(rows["group"])[o], np.uint32, m),
+                "interact_mask": _col(np.asarray(rows["interact_mask"])[o], np.uint32, m)}
+        v = StateView()
+        v.n = m
+        for k, a in cols.items():
+            setattr(v, k, a.ctypes.data)
+        self._check(self._L.cb200_shard_add_rows(self._h, C.byref(v)))
+        self.n += m
+        return m
 
     def set_stream(self, cuda_stream: int):
         self._check(self._L.cb200_set_stream(self._h, C.c_void_p(cuda_stream)))

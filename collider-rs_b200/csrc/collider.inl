@@ -212,7 +212,7 @@ int rebin(cb200_collider* c) {
     CCU(x->chunk_base.reserve(n_slots / kScanChunk));
     if (x->entries.cap == 0) CCU(x->entries.reserve((size_t)n * 4 + 1024));
     for (int attempt = 0; attempt < 3; ++attempt) {
-        k_step_zero<<<x->sm_count * 4, kThreads, 0, x->stream>>>(reinterpret_cast<uint4*>(x->slots.p), n_slots / 4, x->d_ctr, nullptr, nullptr, 0, 0);
+        k_step_zero<<<x->sm_count * 4, kThreads, 0, x->stream>>>(reinterpret_cast<uint4*>(x->slots.p), n_slots / 4, x->d_ctr, nullptr, nullptr, 0, 0, 0);
         if (n) k_rebin_count<<<(n + kThreads - 1) / kThreads, kThreads, 0, x->stream>>>(n, x->rec.p, x->slots.p, x->geom, c->dirty.p, c->d_dirty_count);
         int rc = launch_scan(x, true);
         if (rc != CB200_OK) return cfail(c, rc, x->err);

@@ -21,6 +21,7 @@
 #include "sort.cuh"
 #include "tile.cuh"
 #include "drain.cuh"
+#include "migrate.cuh"
 
 using namespace cb200;
 
@@ -114,6 +115,12 @@ struct cb200_ctx {
     ShardGeom shard{};
     DevBuf<HbRec> send;      // [slab]: the outgoing halo slab, record 0 is its header
     DevBuf<uint32_t> send_count;
+    // owner migration: the own records of the visitor table have room for own_cap rows (the receive area starts there, so that
+    // rows can arrive without moving what the peers have mapped)
+    uint32_t own_cap = 0, own_cap_request = 0;
+    DevBuf<unsigned char> mig_stage;
+    DevBuf<uint32_t> mig_u32;
+    uint64_t rows_migrated_out = 0, rows_migrated_in = 0;
     uint32_t slab = 0;       // records per slab, header included
     MinKey* d_key = nullptr; // local minimum of the last step (device), input of the all-gather min
     bool own_stream = true;
@@ -421,7 +428,7 @@ void cb200_destroy(cb200_ctx* c) {
     for (auto& b : c->col) b.release();
     for (auto& b : c->nvel) b.release();
     c->kind.release(); c->reit.release(); c->group.release(); c->mask.release(); c->ids.release(); c->rec.release(); c->bink.release();
-    c->label.release(); c->ord.release(); c->row_of.release(); c->send.release(); c->send_count.release(); c->vmap.release();
+    c->label.release(); c->ord.release(); c->row_of.release(); c->send.release(); c->send_count.release(); c->vmap.release(); c->mig_stage.release(); c->mig_u32.release();
     for (auto& b : c->col_alt) b.release();
     c->kind_alt.release(); c->reit_alt.release(); c->group_alt.release(); c->mask_alt.release(); c->label_alt.release(); c->ord_alt.release();
     c->sort_key.release(); c->src_row.release(); c->tmp_col.release();
@@ -507,7 +514,14 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
     for (uint64_t i = 0; i < v->n; ++i)
         if (v->group[i] != CB200_GROUP_NONE && v->group[i] > 31) return fail(ctx, CB200_E_ARG, "group must be 0..31 or CB200_GROUP_NONE");
     CU(cudaSetDevice(ctx->device));
-    const size_t n = (size_t)v->n, cap = std::max<size_t>(n, 1);
+    const size_t n = (size_t)v->n;
+    if (ctx->sharded) {
+        // room for rows that migrate in later (cb200_shard_add_rows): 1/4 more than the residents of now, or what the host asked for
+        const size_t want = ctx->own_cap_request ? (size_t)ctx->own_cap_request : n + std::max<size_t>(n / 4, 4096);
+        if (want < n || want >= 0x7fffffffull) return fail(ctx, CB200_E_ARG, "row capacity (cb200_shard_set_row_capacity) smaller than the uploaded table");
+        ctx->own_cap = (uint32_t)want;
+    }
+    const size_t cap = ctx->sharded ? (size_t)ctx->own_cap : std::max<size_t>(n, 1);
     const double* src[11] = {v->pos_x, v->pos_y, v->dim_x, v->dim_y, v->vel_x, v->vel_y, v->rsz_x, v->rsz_y, v->start_time, v->end_time, v->pub_end_time};
     for (int k = 0; k < 11; ++k) {
         CU(ctx->col[k].reserve(cap));
@@ -538,14 +552,15 @@ int cb200_upload_state(cb200_ctx* ctx, const cb200_state_view* v) {
         // visitor table holds the n own records followed by one received slab per rank
         if (ctx->slab == 0) ctx->slab = (uint32_t)std::max<size_t>(n / 64, 4095) + 1;
         // (two receive areas: the direct exchange double-buffers them by step parity)
-        CU(ctx->rec.reserve(n + 2 * (size_t)ctx->slab * ctx->shard.world));
-        CU(ctx->bink.reserve(n + 2 * (size_t)ctx->slab * ctx->shard.world));
+        CU(ctx->rec.reserve(cap + 2 * (size_t)ctx->slab * ctx->shard.world));
+        CU(ctx->bink.reserve(cap + 2 * (size_t)ctx->slab * ctx->shard.world));
         ctx->p2p = false;  // peers must be re-imported: the receive area moved
-        CU(ctx->send.reserve(ctx->slab));
-        CU(ctx->send_count.reserve(1));
+        CU(ctx->send.reserve((size_t)ctx->slab * ctx->shard.world));  // one slab per destination
+        CU(ctx->send_count.reserve(kMaxWorld));
+        CU(cudaMemsetAsync(ctx->send.p, 0, (size_t)ctx->slab * ctx->shard.world * sizeof(HbRec), ctx->stream));
         CU(ctx->vmap.reserve(ctx->id_space));
         CU(cudaMemsetAsync(ctx->vmap.p, 0xff, ctx->id_space * 4, ctx->stream));
-        CU(cudaMemsetAsync(ctx->rec.p + n, 0, 2 * (size_t)ctx->slab * ctx->shard.world * sizeof(HbRec), ctx->stream));
+        CU(cudaMemsetAsync(ctx->rec.p + cap, 0, 2 * (size_t)ctx->slab * ctx->shard.world * sizeof(HbRec), ctx->stream));
     } else {
         CU(ctx->row_of.reserve(cap));
         if (n) k_iota_rows<<<((uint32_t)n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>((uint32_t)n, ctx->label.p, ctx->row_of.p);
@@ -929,13 +944,14 @@ static int reserve_step_buffers(cb200_ctx* ctx) {
     CU(reserve_dense(ctx));
     if (ctx->events.cap == 0) CU(ctx->events.reserve((size_t)n * 2 + 1024));
     CU(ctx->partial.reserve((size_t)ctx->sm_count * (32 + 32 + 32 + 8)));  // worst case of the CB200_PER_SM_* overrides
-    for (auto& b : ctx->nvel) CU(b.reserve(std::max<uint32_t>(n, 1)));       // (stage_vel must not allocate while a peer waits in a kernel)
-    if (n >= 2) {
+    const uint32_t row_cap = ctx->sharded ? std::max(n, ctx->own_cap) : n;  // (rows may migrate in: cb200_shard_add_rows)
+    for (auto& b : ctx->nvel) CU(b.reserve(std::max<uint32_t>(row_cap, 1)));  // (stage_vel must not allocate while a peer waits in a kernel)
+    if (row_cap >= 2) {
         for (int k = 0; k < 11; ++k) CU(ctx->col_alt[k].reserve(ctx->col[k].cap));
         CU(ctx->kind_alt.reserve(ctx->kind.cap)); CU(ctx->reit_alt.reserve(ctx->reit.cap)); CU(ctx->group_alt.reserve(ctx->group.cap));
         CU(ctx->mask_alt.reserve(ctx->mask.cap)); CU(ctx->label_alt.reserve(ctx->label.cap));
         if (ctx->sharded) CU(ctx->ord_alt.reserve(ctx->ord.cap));
-        CU(ctx->sort_key.reserve(n)); CU(ctx->src_row.reserve(n));
+        CU(ctx->sort_key.reserve(row_cap)); CU(ctx->src_row.reserve(row_cap));
     }
     return CB200_OK;
 }
@@ -980,7 +996,8 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     const GridGeom g = ctx->geom;
     const uint32_t n_slots = g.n_slots();
     k_step_zero<<<ctx->sm_count * 4, kThreads, 0, ctx->stream>>>(reinterpret_cast<uint4*>(ctx->slots.p), n_slots / 4, ctx->d_ctr,
-                                                                  ctx->sharded ? ctx->send_count.p : nullptr, ctx->work_count.p, kWorkLists + 2, ctx->sharded ? n : 0u);
+                                                                  ctx->sharded ? ctx->send_count.p : nullptr, ctx->work_count.p, kWorkLists + 2, ctx->sharded ? n : 0u,
+                                                                  ctx->sharded ? (uint32_t)ctx->shard.world : 0u);
     ctx->launches += 1;
     DBG_SYNC("k_step_zero");
     if (ctx->collider_dirty && n) {
@@ -1042,7 +1059,7 @@ static int enqueue_front(cb200_ctx* ctx, double time, bool do_rebase, const doub
     }
     DBG_SYNC("k_stage_a");
     if (ctx->sharded) {
-        k_slab_header<<<1, 1, 0, ctx->stream>>>(ctx->send.p, ctx->send_count.p, ctx->slab);
+        k_slab_header<<<1, kMaxWorld, 0, ctx->stream>>>(ctx->send.p, ctx->send_count.p, ctx->slab, ctx->shard.world);
         ctx->launches += 1;
     }
     if (ctx->stage_timing) CU(cudaEventRecord(ctx->ev_t[ST_EXCH], ctx->stream));
@@ -1132,7 +1149,8 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount, bool bin_only
     const GridGeom g = ctx->geom;
     const uint32_t n_slots = g.n_slots();
     const ShardGeom sh = ctx->sharded ? ctx->shard : whole_world();
-    const VisSpace vs{ctx->n, ctx->n + (ctx->p2p ? (uint32_t)ctx->p2p_parity * (uint32_t)sh.world * ctx->slab : 0u), ctx->slab, sh.world, sh.rank};
+    const uint32_t recv_base = ctx->sharded ? ctx->own_cap : ctx->n;
+    const VisSpace vs{ctx->n, recv_base + (ctx->p2p ? (uint32_t)ctx->p2p_parity * (uint32_t)sh.world * ctx->slab : 0u), ctx->slab, sh.world, sh.rank};
     const uint32_t n_vis_max = ctx->sharded ? ctx->n + ctx->slab * (uint32_t)sh.world : ctx->n;
     const uint32_t grid_v = std::max<uint32_t>(1, std::min<uint32_t>((n_vis_max + kThreads - 1) / kThreads, ctx->sm_count * 8));
     const bool use_map = ctx->sharded && ctx->n_ov;
@@ -1208,7 +1226,7 @@ static int enqueue_back(cb200_ctx* ctx, double time, bool recount, bool bin_only
 // shared memory, then the overlapping pairs (separate_time) and the last-block min-reduction through k_solve.
 static int enqueue_tile_step(cb200_ctx* ctx, bool do_rebase, const double* const* nv) {
     const uint32_t n = ctx->n;
-    k_step_zero<<<1, kThreads, 0, ctx->stream>>>(nullptr, 0u, ctx->d_ctr, nullptr, ctx->work_count.p, kWorkLists + 2, 0u);
+    k_step_zero<<<1, kThreads, 0, ctx->stream>>>(nullptr, 0u, ctx->d_ctr, nullptr, ctx->work_count.p, kWorkLists + 2, 0u, 0u);
     ctx->launches += 1;
     DBG_SYNC("k_step_zero");
     if (ctx->collider_dirty && n) {
@@ -1458,7 +1476,7 @@ static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
     for (const void* p : ptrs) mix((uint64_t)(uintptr_t)p);
     mix(ctx->entries.cap); mix(ctx->work.cap); mix(ctx->events.cap); mix((uint64_t)(uintptr_t)ctx->dense.p); mix(ctx->dense.cap); mix(ctx->dense_rank); mix(ctx->dense_lockstep ? 3 : 5); mix(ctx->stage_a_tma ? 1 : 0);
     if (ctx->sharded) {
-        mix(0x5aa5); mix(ctx->peer_timeout_ns); mix((uint64_t)ctx->p2p_parity); mix(ctx->slab); mix((uint64_t)ctx->shard.world << 8 | (uint64_t)ctx->shard.rank);
+        mix(0x5aa5); mix(ctx->own_cap); mix(ctx->peer_timeout_ns); mix((uint64_t)ctx->p2p_parity); mix(ctx->slab); mix((uint64_t)ctx->shard.world << 8 | (uint64_t)ctx->shard.rank);
         const void* sp[] = {ctx->ord.p, ctx->send.p, ctx->send_count.p, ctx->vmap.p, ctx->d_mail, ctx->d_key, ctx->d_gkey};
         for (const void* q : sp) mix((uint64_t)(uintptr_t)q);
         for (int d = 0; d < ctx->shard.world; ++d) {
@@ -1617,6 +1635,175 @@ int cb200_shard_set_slab(cb200_ctx* ctx, uint64_t records) {
     return CB200_OK;
 }
 
+int cb200_shard_set_row_capacity(cb200_ctx* ctx, uint64_t rows) {
+    if (!ctx) return CB200_E_ARG;
+    if (rows >= 0x7fffffffull) return fail(ctx, CB200_E_ARG, "bad row capacity");
+    ctx->own_cap_request = (uint32_t)rows;  // 0 = default (residents + 25 %)
+    ctx->have_state = false;                // buffers are sized at upload_state
+    return CB200_OK;
+}
+
+int cb200_shard_rows(const cb200_ctx* ctx, uint64_t* rows, uint64_t* capacity, uint64_t* migrated_out, uint64_t* migrated_in) {
+    if (!ctx) return CB200_E_ARG;
+    if (rows) *rows = ctx->n;
+    if (capacity) *capacity = ctx->sharded ? ctx->own_cap : ctx->n;
+    if (migrated_out) *migrated_out = ctx->rows_migrated_out;
+    if (migrated_in) *migrated_in = ctx->rows_migrated_in;
+    return CB200_OK;
+}
+
+static MigCols mig_cols_of(cb200_ctx* ctx) {
+    MigCols c{};
+    for (int k = 0; k < 11; ++k) c.col[k] = ctx->col[k].p;
+    c.kind = ctx->kind.p; c.reit = ctx->reit.p; c.group = ctx->group.p; c.mask = ctx->mask.p; c.label = ctx->label.p; c.ord = ctx->ord.p;
+    return c;
+}
+static int mig_check(cb200_ctx* ctx, const char* what) {
+    if (!ctx->sharded) return fail(ctx, CB200_E_STATE, std::string(what) + ": cb200_shard_configure first");
+    if (!ctx->have_state) return fail(ctx, CB200_E_STATE, std::string(what) + " before upload_state");
+    if (ctx->shard_phase != 0) return fail(ctx, CB200_E_STATE, std::string(what) + " inside a step (cb200_shard_result first)");
+    if (ctx->fetch_pending) return fail(ctx, CB200_E_STATE, std::string(what) + ": cb200_fetch_events_end the pending download first");
+    return CB200_OK;
+}
+static void mig_invalidate(cb200_ctx* ctx) {
+    ctx->have_step = false;  // the event list of the last step named rows that may be gone
+    ctx->ev_sorted = false;
+    ctx->tile_ok = false;
+    set_l2_window(ctx);
+}
+
+// Owner migration, sending side (migrate.cuh): the rows whose centre column lies more than margin_cols columns outside this
+// rank's strip are copied out — every column, plus the rank whose strip holds them — and removed from the table.
+int cb200_shard_take_movers(cb200_ctx* ctx, int32_t margin_cols, const cb200_rows_out* out, uint64_t* n_out) {
+    if (!ctx) return CB200_E_ARG;
+    if (n_out) *n_out = 0;
+    int rc = mig_check(ctx, "shard_take_movers");
+    if (rc != CB200_OK) return rc;
+    if (margin_cols < 0) return fail(ctx, CB200_E_ARG, "margin_cols must be >= 0");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = ctx->n;
+    if (!n) return CB200_OK;
+    CU(ctx->sort_key.reserve(n)); CU(ctx->src_row.reserve(n)); CU(ctx->mig_u32.reserve(4096));
+    uint32_t* rows = ctx->sort_key.p;
+    int32_t* dest = reinterpret_cast<int32_t*>(ctx->src_row.p);
+    uint32_t* count = ctx->mig_u32.p;
+    const uint32_t blocks = (n + kThreads - 1) / kThreads;
+    CU(cudaMemsetAsync(count, 0, 4, ctx->stream));
+    k_mig_mark<<<blocks, kThreads, 0, ctx->stream>>>(n, ctx->col[0].p, ctx->cell_width, ctx->shard, margin_cols, rows, dest, count, n);
+    ctx->launches += 1;
+    uint32_t m = 0;
+    CU(cudaMemcpyAsync(&m, count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (n_out) *n_out = m;
+    if (!m) return CB200_OK;
+    if (!out || out->cap < m) return fail(ctx, CB200_E_ARG, "shard_take_movers: output capacity too small (nothing was removed; *n_out = rows that would move)");
+    const void* need[] = {out->id, out->pos_x, out->pos_y, out->dim_x, out->dim_y, out->vel_x, out->vel_y, out->rsz_x, out->rsz_y, out->start_time,
+                          out->end_time, out->pub_end_time, out->kind, out->group, out->interact_mask, out->dest};
+    for (const void* q : need)
+        if (!q) return fail(ctx, CB200_E_ARG, "null column in rows_out");
+    // pack + download
+    const size_t bytes = mig_stage_bytes(m);
+    CU(ctx->mig_stage.reserve(bytes));
+    const MigCols mc = mig_cols_of(ctx);
+    const uint32_t mblocks = (m + kThreads - 1) / kThreads;
+    k_mig_pack<<<mblocks, kThreads, 0, ctx->stream>>>(m, rows, mc, ctx->mig_stage.p, ctx->vmap.p, (uint32_t)ctx->id_space);
+    ctx->launches += 1;
+    std::vector<unsigned char> hs(bytes);
+    std::vector<uint32_t> hrows(m);
+    CU(cudaMemcpyAsync(hs.data(), ctx->mig_stage.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(hrows.data(), rows, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out->dest, dest, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    double* oc[11] = {out->pos_x, out->pos_y, out->dim_x, out->dim_y, out->vel_x, out->vel_y, out->rsz_x, out->rsz_y, out->start_time, out->end_time, out->pub_end_time};
+    const double* hd = reinterpret_cast<const double*>(hs.data());
+    for (int k = 0; k < 11; ++k) memcpy(oc[k], hd + (size_t)k * m, (size_t)m * 8);
+    const uint32_t* hu = reinterpret_cast<const uint32_t*>(hd + (size_t)11 * m);
+    for (uint32_t j = 0; j < m; ++j) out->id[j] = hu[j];
+    std::vector<uint32_t> gone(hu + m, hu + 2 * (size_t)m);  // the movers' positions in the caller's array order
+    memcpy(out->group, hu + 2 * (size_t)m, (size_t)m * 4);
+    memcpy(out->interact_mask, hu + 3 * (size_t)m, (size_t)m * 4);
+    memcpy(out->kind, reinterpret_cast<const unsigned char*>(hu + 4 * (size_t)m), m);
+    // holes among the first n - m rows <- the surviving rows of the tail
+    const uint32_t n_left = n - m;
+    std::sort(hrows.begin(), hrows.end());
+    std::sort(gone.begin(), gone.end());
+    std::vector<uint32_t> up;  // [moves: (dst, src) pairs][gone ords]
+    {
+        size_t t = std::lower_bound(hrows.begin(), hrows.end(), n_left) - hrows.begin();  // movers inside the tail start here
+        uint32_t src = n_left;
+        for (size_t h = 0; h < hrows.size() && hrows[h] < n_left; ++h) {
+            while (t < hrows.size() && hrows[t] == src) { ++t; ++src; }  // (skip tail rows that move away themselves)
+            up.push_back(hrows[h]);
+            up.push_back(src++);
+        }
+    }
+    const uint32_t n_moves = (uint32_t)(up.size() / 2);
+    up.insert(up.end(), gone.begin(), gone.end());
+    CU(ctx->mig_u32.reserve(up.size() + 16));
+    CU(cudaMemcpyAsync(ctx->mig_u32.p, up.data(), up.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_moves) k_mig_fill<<<(n_moves + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(n_moves, ctx->mig_u32.p, mc);
+    if (n_left) k_mig_ord_out<<<(n_left + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(n_left, ctx->ord.p, ctx->mig_u32.p + 2 * (size_t)n_moves, m);
+    ctx->launches += 2;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->n = n_left;
+    ctx->rows_migrated_out += m;
+    mig_invalidate(ctx);
+    return CB200_OK;
+}
+
+// Owner migration, receiving side: the rows are appended to the table (ids strictly ascending, none of them resident here).
+int cb200_shard_add_rows(cb200_ctx* ctx, const cb200_state_view* v) {
+    if (!ctx || !v) return CB200_E_ARG;
+    int rc = mig_check(ctx, "shard_add_rows");
+    if (rc != CB200_OK) return rc;
+    const uint64_t m64 = v->n;
+    if (!m64) return CB200_OK;
+    const void* need[] = {v->id, v->pos_x, v->pos_y, v->dim_x, v->dim_y, v->vel_x, v->vel_y, v->rsz_x, v->rsz_y,
+                          v->start_time, v->end_time, v->pub_end_time, v->kind, v->group, v->interact_mask};
+    for (const void* q : need)
+        if (!q) return fail(ctx, CB200_E_ARG, "null column in state view");
+    const uint32_t n = ctx->n;
+    if ((uint64_t)n + m64 > ctx->own_cap) return fail(ctx, CB200_E_STATE, "shard_add_rows: the strip's row capacity is exhausted (cb200_shard_set_row_capacity before upload_state)");
+    const uint32_t m = (uint32_t)m64;
+    std::vector<uint32_t> up(m);
+    for (uint32_t j = 0; j < m; ++j) {
+        if (j && !(v->id[j - 1] < v->id[j])) return fail(ctx, CB200_E_ARG, "ids must be strictly ascending");
+        if (v->id[j] >= ctx->id_space) return fail(ctx, CB200_E_ARG, "sharded mode requires ids < id_space");
+        if (v->group[j] != CB200_GROUP_NONE && v->group[j] > 31) return fail(ctx, CB200_E_ARG, "group must be 0..31 or CB200_GROUP_NONE");
+        up[j] = (uint32_t)v->id[j];
+    }
+    CU(cudaSetDevice(ctx->device));
+    const double* src[11] = {v->pos_x, v->pos_y, v->dim_x, v->dim_y, v->vel_x, v->vel_y, v->rsz_x, v->rsz_y, v->start_time, v->end_time, v->pub_end_time};
+    for (int k = 0; k < 11; ++k) CU(cudaMemcpyAsync(ctx->col[k].p + n, src[k], (size_t)m * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->kind.p + n, v->kind, m, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->group.p + n, v->group, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->mask.p + n, v->interact_mask, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->label.p + n, up.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->reit.p + n, 0, m, ctx->stream));
+    // the caller's array order is the ascending-id order of the residents: shift the residents' positions, place the arrivals
+    CU(ctx->mig_u32.reserve(2 * (size_t)m + 16));
+    uint32_t* d_ids = ctx->mig_u32.p;
+    uint32_t* d_below = ctx->mig_u32.p + m;  // [m + 1]
+    CU(cudaMemcpyAsync(d_ids, up.data(), (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d_below, 0, ((size_t)m + 1) * 4, ctx->stream));
+    if (n) k_mig_ord_in<<<(n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(n, ctx->ord.p, ctx->label.p, d_ids, m, d_below);
+    ctx->launches += 1;
+    std::vector<uint32_t> below((size_t)m + 1);
+    CU(cudaMemcpyAsync(below.data(), d_below, ((size_t)m + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint32_t run = 0;
+    for (uint32_t j = 0; j < m; ++j) {
+        run += below[j];
+        up[j] = run + j;
+    }
+    CU(cudaMemcpy(ctx->ord.p + n, up.data(), (size_t)m * 4, cudaMemcpyHostToDevice));
+    ctx->n = n + m;
+    ctx->rows_migrated_in += m;
+    if ((uint64_t)m * 16 > ctx->n) ctx->need_resort = true;  // (many new rows at the end of the table: put them into slot order)
+    mig_invalidate(ctx);
+    return CB200_OK;
+}
+
 int cb200_set_stream(cb200_ctx* ctx, void* cuda_stream) {
     if (!ctx) return CB200_E_ARG;
     CU(cudaSetDevice(ctx->device));
@@ -1645,7 +1832,7 @@ int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
     ctx->shard_phase = 1;
     ctx->shard_T = time;
     if (send_base) *send_base = ctx->send.p;
-    if (recv_base) *recv_base = ctx->rec.p + ctx->n;
+    if (recv_base) *recv_base = ctx->rec.p + ctx->own_cap;
     if (slab_bytes) *slab_bytes = (uint64_t)ctx->slab * sizeof(HbRec);
     return CB200_OK;
 }
@@ -1737,7 +1924,7 @@ int cb200_shard_p2p_export(cb200_ctx* ctx, cb200_p2p_info* out) {
     else cudaGetLastError();
     out->rec_ptr = (uint64_t)(uintptr_t)ctx->rec.p;
     out->mail_ptr = (uint64_t)(uintptr_t)ctx->d_mail;
-    out->recv_offset_bytes = (uint64_t)ctx->n * sizeof(HbRec);
+    out->recv_offset_bytes = (uint64_t)ctx->own_cap * sizeof(HbRec);
     out->pid = (uint64_t)getpid();
     out->device = ctx->device;
     out->slab_records = ctx->slab;
@@ -1756,7 +1943,7 @@ int cb200_shard_p2p_import(cb200_ctx* ctx, const cb200_p2p_info* infos /* world 
     for (int d = 0; d < world; ++d) {
         if (infos[d].slab_records != ctx->slab) return fail(ctx, CB200_E_ARG, "peers must use the same halo slab size (cb200_shard_set_slab)");
         if (d == rank) {
-            pt.recv[d] = ctx->rec.p + ctx->n;
+            pt.recv[d] = ctx->rec.p + ctx->own_cap;
             pt.mail[d] = ctx->d_mail;
             continue;
         }

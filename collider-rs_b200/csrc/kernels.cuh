@@ -59,10 +59,11 @@ struct StepArgs {
     MinKey* partial;  // solitaire minima, one per block of the stage-A launches
     uint32_t partial_base;  // first slot of this launch
     uint32_t dbg;           // timing experiments only (CB200_DBG_A): 1 skip the cell count, 2 skip the record store, 4 skip the state write-back
-    // sharded only: ONE outgoing slab of `slab` records; record 0 is its header (first word = count).  It is
-    // all-gathered: every rank receives every slab and simply bins what falls into its own strip.
-    HbRec* send;           // [slab]
-    uint32_t* send_count;  // [1]
+    // sharded only: one outgoing slab of `slab` records PER DESTINATION rank; record 0 of a slab is its header (first word =
+    // count).  A record goes into the slab of every other strip its columns touch (usually one neighbour), so a rank
+    // receives only what it has to bin.
+    HbRec* send;           // [world][slab]
+    uint32_t* send_count;  // [world]
     uint32_t slab;
     uint32_t* vmap;        // gid -> record index of this step (direct-addressed; null when there are no overlapping pairs)
     const uint32_t* ov_bits;  // one bit per gid: the hitbox has an overlap — only those are looked up through vmap
@@ -74,7 +75,7 @@ struct VisSpace {
     uint32_t n_own;  // capacity of the own region (= residents)
     uint32_t recv0;  // first record of this step's received slabs (n_own; direct exchange: + parity * world * slab)
     uint32_t slab;   // records per slab including the header
-    int world, rank; // slab `rank` is this rank's own halo slab coming back from the all-gather: ignored
+    int world, rank; // slab `rank` (this rank's own slot) is never filled: ignored
 };
 __device__ __forceinline__ uint32_t slab_count(const HbRec* rec, const VisSpace& vs, int d) {
     return __ldg(reinterpret_cast<const unsigned int*>(rec + vs.recv0 + (size_t)d * vs.slab));
@@ -289,13 +290,16 @@ __device__ __forceinline__ HbRec stage_a_row(const StepArgs& a, const ShardGeom&
     if (SHARDED && h.binned) {
         // The record is needed by every rank whose strip intersects columns [sx, ex + 1): the extra column keeps
         // a partner that is within `padding` across a cell line (an overlapping pair whose rects do not
-        // intersect) visible.  Any strip other than the own one -> the halo slab.
+        // intersect) visible.  Every strip other than the own one -> that rank's halo slab (sharding.py strips_touched).
         const int64_t hi_col = (int64_t)h.ex + 1;
         const bool leaves = (int64_t)rec.sx < (int64_t)sh.col_lo || hi_col > (int64_t)sh.col_hi;
         if (leaves) {
-            const uint32_t pos = warp_agg_claim32(a.send_count);
-            if (pos + 1 < a.slab) store_rec(a.send + 1 + pos, rec);
-            else a.ctr->overflow_send = 1u;
+            for (int d = 0; d < sh.world; ++d) {
+                if (d == sh.rank || !((int64_t)sh.bounds[d + 1] > (int64_t)rec.sx && (int64_t)sh.bounds[d] < hi_col)) continue;
+                const uint32_t pos = atomicAdd(a.send_count + d, 1u);
+                if (pos + 1 < a.slab) store_rec(a.send + (size_t)d * a.slab + 1 + pos, rec);
+                else a.ctr->overflow_send = 1u;
+            }
         }
     }
     if (h.reit) {
@@ -433,9 +437,10 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_A) k_stage_a_tma(const Step
     }
 }
 
-// Sharded: publish the record count in the halo slab's header before the all-gather.
-__global__ void k_slab_header(HbRec* send, const uint32_t* __restrict__ send_count, uint32_t slab) {
-    *reinterpret_cast<unsigned int*>(send) = min(send_count[0], slab - 1u);
+// Sharded: publish the record counts in the headers of the halo slabs before the exchange (one thread per destination).
+__global__ void k_slab_header(HbRec* send, const uint32_t* __restrict__ send_count, uint32_t slab, int world) {
+    const int d = threadIdx.x;
+    if (d < world) *reinterpret_cast<unsigned int*>(send + (size_t)d * slab) = min(send_count[d], slab - 1u);
 }
 
 // Sharded, after the exchange: count the strip cells of the RECEIVED records (the own ones were counted in stage A;
@@ -464,8 +469,8 @@ __global__ void __launch_bounds__(kThreads) k_index_visitors(const HbRec* __rest
 // ---------------------------------------------------------------------------------------------------------
 // Direct halo exchange over peer memory (NVLink / NVSwitch): every rank's visitor table and mailbox are mapped into its
 // peers (cudaIpc or same-process pointers), so the exchange is two tiny kernels instead of two NCCL collectives —
-//   k_push_halo   copies the rank's halo slab (header + the records that are actually there) straight into slot `rank` of
-//                 every peer's receive area for this step's parity, then raises flag_halo[rank] = tag on that peer
+//   k_push_halo   copies the rank's halo slab for peer d (header + the records that are actually there) straight into slot
+//                 `rank` of that peer's receive area for this step's parity, then raises flag_halo[rank] = tag on the peer
 //   k_wait_halo   spins (on local memory) until every peer has raised its flag for this step
 // and the same pattern for the 24-byte next-event keys after the solve stage (k_push_key / k_reduce_keys).  Slab areas and
 // key rows are double-buffered by step parity; a rank can run at most one step ahead of a peer, because its next back half
@@ -487,6 +492,7 @@ __global__ void __launch_bounds__(1024) k_push_halo(const HbRec* __restrict__ se
     const unsigned long long tag = dyn->tag;
     const int d = blockIdx.x + (blockIdx.x >= (unsigned)rank ? 1 : 0);  // blocks enumerate the peers
     if (d >= world) return;
+    send += (size_t)d * slab;  // the slab addressed to peer d
     const uint32_t count = min(*reinterpret_cast<const unsigned int*>(send), slab - 1u);
     const int4* src = reinterpret_cast<const int4*>(send);
     int4* dst = reinterpret_cast<int4*>(peers.recv[d] + ((size_t)parity * world + rank) * slab);
@@ -597,7 +603,7 @@ __global__ void k_raise_abort(PeerTable peers, int world, int rank) {
 // ---------------------------------------------------------------------------------------------------------
 // Step prologue: one kernel zeroes everything a step accumulates into (slot table, counters, halo count).
 __global__ void __launch_bounds__(kThreads) k_step_zero(uint4* slots4, uint32_t n4, Counters* ctr, uint32_t* send_count, uint32_t* work_count,
-                                                        uint32_t n_work_lists, uint32_t n_local) {
+                                                        uint32_t n_work_lists, uint32_t n_local, uint32_t n_send) {
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) slots4[i] = z;
     if (blockIdx.x == 0) {
@@ -610,8 +616,9 @@ __global__ void __launch_bounds__(kThreads) k_step_zero(uint4* slots4, uint32_t 
         if (threadIdx.x == 0) {
             ctr->err_slot = ~0ull;
             ctr->n_local = n_local;  // sharded: the own records occupy rows [0, n) of the visitor table
-            if (send_count) *send_count = 0u;
         }
+        if (send_count)
+            for (uint32_t d = threadIdx.x; d < n_send; d += blockDim.x) send_count[d] = 0u;
     }
 }
 

@@ -72,6 +72,26 @@ def c3_dense(n: int = 1_000_000) -> dict:
     return uniform_density(n, density=1.0, seed=SEED_BASE + 3)
 
 
+def with_groups_and_resizing(s: dict, seed: int) -> dict:
+    """The rows the reference's own tests leave out: resize velocities (circles keep rsz_x == rsz_y),
+    four groups with asymmetric interact_groups lists and one of them HbGroup None, coordinates centred on the origin."""
+    n = len(s["id"])
+    s["pos_x"] = s["pos_x"] - 0.5 * (s["pos_x"].max() + s["pos_x"].min())
+    s["pos_y"] = s["pos_y"] - 0.5 * (s["pos_y"].max() + s["pos_y"].min())
+    r = uniform(seed, n, 20, -0.05, 0.3)
+    s["rsz_x"] = r
+    s["rsz_y"] = np.where(s["kind"] == 0, r, uniform(seed, n, 21, -0.05, 0.3))
+    g = (splitmix64(seed, n, 22) % np.uint64(4)).astype(np.uint32)
+    s["group"] = np.where(g == 3, np.uint32(0xFFFFFFFF), g)  # CB200_GROUP_NONE
+    s["interact_mask"] = np.array([0b011, 0b101, 0b110, 0b111], dtype=np.uint32)[g]
+    return s
+
+
+def c3_groups(n: int = 1_000_000) -> dict:
+    """Config 3's density with resizing shapes in several groups (f-4 at the benchmark's size)."""
+    return with_groups_and_resizing(uniform_density(n, seed=SEED_BASE + 6), SEED_BASE + 6)
+
+
 def c4(n: int = 16_777_216) -> dict:
     """Config 4: n shapes at 1 per unit^2 (16M -> 4096 x 4096)."""
     return uniform_density(n, density=1.0, seed=SEED_BASE + 4)

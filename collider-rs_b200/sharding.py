@@ -67,6 +67,12 @@ def min_key(rows):
     return min(((int(a) & KEY_MAX), (int(b) & KEY_MAX)) for a, b in rows)
 
 
+def rows_for(parts, rank: int) -> dict:
+    """Of the (rows, dest) every rank took out of its table, the rows addressed to `rank`, as one dict of columns."""
+    picks = [{k: v[dest == rank] for k, v in rows.items()} for rows, dest in parts]
+    return {k: np.concatenate([p[k] for p in picks]) for k in picks[0]}
+
+
 class DevMem:
     """A raw device allocation exposed through __cuda_array_interface__ so torch can wrap it without copying."""
 
@@ -82,7 +88,7 @@ def wrap(ptr: int, nbytes: int, device):
 
 class Exchange:
     """The two collectives of a sharded step over a torch.distributed process group (NCCL on GPUs, gloo in CPU tests):
-    an all-gather of the per-rank halo slabs and an all-gather of the 16-byte per-rank minimum keys."""
+    an all-to-all of the per-destination halo slabs and an all-gather of the 16-byte per-rank minimum keys."""
 
     def __init__(self, group=None):
         import torch.distributed as dist
@@ -92,16 +98,18 @@ class Exchange:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
-    def all_gather_slabs(self, recv_buf, send_buf):
-        """send_buf: uint8 tensor of one slab; recv_buf: world slabs.  Slot d of recv_buf receives rank d's slab."""
+    def exchange_slabs(self, recv_buf, send_buf):
+        """send_buf: uint8 tensor of `world` slabs, slab d addressed to rank d; recv_buf: world slabs.  Slot d of recv_buf
+        receives the slab rank d addressed to this rank (the slot of the own rank is not meaningful)."""
         if send_buf.device.type == "cuda":
-            self.dist.all_gather_into_tensor(recv_buf, send_buf, group=self.group)
+            self.dist.all_to_all_single(recv_buf, send_buf, group=self.group)
             return
         import torch
 
+        per = send_buf.numel() // self.world
         rows = [torch.empty_like(send_buf) for _ in range(self.world)]
-        self.dist.all_gather(rows, send_buf, group=self.group)
-        recv_buf.copy_(torch.cat(rows))
+        self.dist.all_gather(rows, send_buf, group=self.group)  # (gloo: no all-to-all on every build; tests only)
+        recv_buf.copy_(torch.cat([rows[d][self.rank * per:(self.rank + 1) * per] for d in range(self.world)]))
 
     def all_gather_keys(self, key_local):
         """key_local: int64 tensor [2] (time key, tie).  Returns an int64 tensor [world, 2]."""
@@ -119,7 +127,7 @@ class Exchange:
 
 class ShardedEngine:
     """One rank of a sharded `Collider`: a device context on torch's current stream + the two collectives of its step.
-    Per step the host enqueues: stage A + halo pack -> all-gather of the halo slabs -> binning / candidates / solve / local min
+    Per step the host enqueues: stage A + halo pack -> all-to-all of the halo slabs -> binning / candidates / solve / local min
     -> all-gather of the keys, and synchronises once at the end."""
 
 
@@ -164,6 +172,16 @@ class ShardedEngine:
     def set_overlaps(self, a, b):
         self.eng.set_overlaps(a, b)
 
+    def migrate(self, margin_cols: int = 1):
+        """Owner migration, collective, between two steps: every rank hands the rows whose centre column left its
+        strip (by more than margin_cols columns — hysteresis against ping-pong at an edge) to the rank whose strip holds them.
+        Returns (rows sent, rows received).  The rows travel through the host (they are few: a row crosses an edge only after
+        moving a whole strip margin); the step's halo exchange is untouched — the receive areas do not move."""
+        rows, dest = self.eng.shard_take_movers(margin_cols)
+        parts = [None] * self.ex.world
+        self.ex.dist.all_gather_object(parts, (rows, dest), group=self.ex.group)
+        return len(dest), self.eng.shard_add_rows(rows_for(parts, self.ex.rank))
+
     def bulk_update(self, time: float, end_time: float, **vel):
         import torch
 
@@ -185,9 +203,9 @@ class ShardedEngine:
         st = self.eng.shard_begin(time, end_time=end_time, **vel)
         key = (st["send_ptr"], st["recv_ptr"], st["slab_bytes"])
         if self._bufs is None or self._bufs[0] != key:
-            self._bufs = (key, wrap(st["send_ptr"], st["slab_bytes"], self.device), wrap(st["recv_ptr"], st["slab_bytes"] * self.ex.world, self.device))
+            self._bufs = (key, wrap(st["send_ptr"], st["slab_bytes"] * self.ex.world, self.device), wrap(st["recv_ptr"], st["slab_bytes"] * self.ex.world, self.device))
         _, send, recv = self._bufs
-        self.ex.all_gather_slabs(recv, send)
+        self.ex.exchange_slabs(recv, send)
         key_ptr = self.eng.shard_finish()
         # shard_result may re-run the back half after growing a buffer that overflowed, and the re-run rewrites the local
         # key (the first run dropped candidate pairs): the keys are gathered only after it, from the final value

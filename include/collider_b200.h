@@ -187,22 +187,21 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
 
 /* ---- Spatial sharding across the GPUs of one box — one context per GPU / process ----------------
  * Cell columns are split into `world` contiguous strips: rank d owns columns [col_bounds[d], col_bounds[d+1])
- * (the first and last strips are open-ended).  Each rank keeps a fixed set of resident hitboxes (upload_state;
- * ids must be < 2^31 - 1 and globally unique) and, every step, hands the 96-byte record of each resident to every
- * rank whose strip its index rect touches (one all-gather of small per-rank halo slabs).  A pair is solved by exactly one rank: the one whose strip holds the
- * pair's owner cell (max of the two rect starts), so records only ever need to reach ranks at or right of their
- * start column.  The exchange itself is done by the caller between the two halves (NCCL over NVLink:
- * torch.distributed in this repo, ncclSend/ncclRecv from a Rust host); the global next event is the minimum of the
- * per-rank keys.
+ * (the first and last strips are open-ended).  Each rank keeps a set of resident hitboxes (upload_state; ids must be
+ * < 2^31 - 1 and globally unique; residents change only through the owner migration below) and, every step, hands the
+ * 96-byte record of each resident to every other rank whose strip its index rect touches: one halo slab per destination,
+ * so a rank receives only what it has to bin.  A pair is solved by exactly one rank: the one whose strip holds the pair's
+ * owner cell (max of the two rect starts).  With the collective exchange the caller moves the slabs between the two halves
+ * (NCCL over NVLink: torch.distributed in this repo, ncclSend/ncclRecv from a Rust host); the global next event is the
+ * minimum of the per-rank keys.
  * All three calls below are asynchronous on the context's stream except cb200_shard_result:
  *   cb200_set_stream  : run the context on the caller's CUDA stream (e.g. torch's current stream) so that the
  *                       exchange collectives are stream-ordered between the two halves — no host sync mid-step.
- *   cb200_shard_begin : stage A on the residents + halo pack.  Every record whose rect (+1 column) leaves the own
- *                       strip is appended once to the rank's halo slab at *send_base (slab_bytes bytes: a 96-byte
- *                       header whose first word is the record count, then the records).  The caller all-gathers the
- *                       slabs: slab of rank d -> slot d of every rank's *recv_base (ncclAllGather;
- *                       torch.distributed.all_gather_into_tensor) — ONE collective, NVLS-capable on NVSwitch.
- *                       Receivers bin whatever falls into their strip; the rest produces no cell entries.
+ *   cb200_shard_begin : stage A on the residents + halo pack.  Every record whose rect (+1 column) touches another strip is
+ *                       appended to the halo slab of that strip's rank: *send_base holds `world` slabs of slab_bytes bytes,
+ *                       slab d addressed to rank d (a 96-byte header whose first word is the record count, then the
+ *                       records).  The caller exchanges them all-to-all: slab d of rank r -> slot r of rank d's
+ *                       *recv_base (ncclSend/ncclRecv pairs; torch.distributed.all_to_all_single) — ONE collective.
  *   cb200_shard_finish: bins own + received records restricted to the own strip, candidate pairs, solves, min.
  *                       *local_key = device address of this rank's (time key, tie) minimum, 2 x u64: all-gather it and
  *                       take the lexicographic minimum for the global next event.
@@ -212,6 +211,34 @@ int cb200_shard_configure(cb200_ctx* ctx, int rank, int world, const int32_t* co
                           uint64_t id_space /* every HbId of every rank is < id_space < 2^31 - 1 */);
 int cb200_set_stream(cb200_ctx* ctx, void* cuda_stream);
 int cb200_shard_set_slab(cb200_ctx* ctx, uint64_t records); /* capacity of the halo slab; default max(4095, n/64): the direct exchange only moves the records that are there; before upload_state */
+
+/* Owner migration ("hitboxes migrate owners when `start` crosses a strip edge"; the reference keeps one grid,
+ * grid.rs:37-70, so there is nothing to cite beyond the cell rule of index_bounds, dur_hitbox/mod.rs:83-102).  Between two
+ * steps of a sharded context:
+ *   cb200_shard_take_movers  every row whose centre column (floor(pos_x / cell_width)) lies more than margin_cols columns
+ *                            outside this rank's strip is copied into `out` — every state column, its profile and dest[i] = the
+ *                            rank whose strip holds it — and removed from the table.  *n_out = rows moved.  If out is NULL or
+ *                            out->cap is too small, nothing is removed, *n_out = the rows that qualify and CB200_E_ARG is
+ *                            returned (out == NULL, cap 0: a pure count, CB200_OK when nothing qualifies)
+ *   cb200_shard_add_rows     appends rows (ids strictly ascending, none resident here) — what the peers' take_movers addressed
+ *                            to this rank.  The table has room for cb200_shard_set_row_capacity rows (default: 25 % more than
+ *                            were uploaded); the receive area of the halo exchange does not move, the peers' mappings stay valid
+ * Afterwards the caller's array order (new velocities of cb200_vel_view, cb200_download_state) is the ascending-id order of
+ * the rank's residents, as after cb200_upload_state.  Which rank solves a pair never depended on residence (owner-cell rule):
+ * results are unchanged; the last step's events can no longer be fetched. */
+typedef struct cb200_rows_out {
+    uint64_t cap; /* capacity of every array below, in rows */
+    uint64_t* id;
+    double *pos_x, *pos_y, *dim_x, *dim_y, *vel_x, *vel_y, *rsz_x, *rsz_y, *start_time, *end_time, *pub_end_time;
+    uint8_t* kind;
+    uint32_t* group;
+    uint32_t* interact_mask;
+    int32_t* dest;
+} cb200_rows_out;
+int cb200_shard_set_row_capacity(cb200_ctx* ctx, uint64_t rows); /* 0 = default; before upload_state */
+int cb200_shard_rows(const cb200_ctx* ctx, uint64_t* rows, uint64_t* capacity, uint64_t* migrated_out, uint64_t* migrated_in);
+int cb200_shard_take_movers(cb200_ctx* ctx, int32_t margin_cols, const cb200_rows_out* out, uint64_t* n_out);
+int cb200_shard_add_rows(cb200_ctx* ctx, const cb200_state_view* rows);
 int cb200_shard_begin(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, void** send_base, void** recv_base,
                       uint64_t* slab_bytes);
 int cb200_shard_finish(cb200_ctx* ctx, void** local_key);

@@ -7,6 +7,8 @@ kernels are time-sliced, so a waiting kernel of one rank is preempted for the pe
 
   --exchange direct   cb200_shard_step (peer memory); host plumbing over gloo
   --exchange nccl     cb200_shard_begin / finish with all_gather_into_tensor over NCCL (needs one GPU per rank)
+  --migrate           owner migration (ShardedEngine.migrate: take_movers -> all_gather_object -> add_rows) after every step,
+                      with new fast velocities each step: rows cross strip edges and change rank between the steps
   --scenario abort    rank 1 stops after the first step and raises its peers' abort words: rank 0's next step must FAIL with
                       CB200_F_PEER_LOST instead of hanging
   --scenario timeout  the same without the abort call: rank 0's wait ends by the timeout (CB200_PEER_TIMEOUT_MS)
@@ -34,6 +36,7 @@ def main():
     ap.add_argument("--hitboxes", dest="n", type=int, default=6000)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--scene", default="uniform", choices=["uniform", "dense", "clustered"])
+    ap.add_argument("--migrate", action="store_true")
     args = ap.parse_args()
 
     import torch
@@ -64,7 +67,12 @@ def main():
     owner = np.clip(np.searchsorted(bounds[1:-1], np.floor(scene["pos_x"] / CW), side="right"), 0, world - 1)
     sh = sharding.ShardedEngine(cb, CW, PAD, device, bounds, n, sharding.Exchange(), direct=args.exchange == "direct")
     m = owner == rank
+    if args.migrate:
+        m = (st["id"] % np.uint64(world)) == np.uint64(rank)  # residents unrelated to position: the first migration re-homes most rows
+        sh.eng.shard_set_row_capacity(n)
     sh.upload_state(**{k: v[m] for k, v in st.items()})
+    my_ids = st["id"][m].astype(np.int64)
+    moved = 0
     assert sh.direct == (args.exchange == "direct"), getattr(sh, "direct_error", "direct exchange was not established")
 
     T, dt = 0.0, 0.1
@@ -85,8 +93,14 @@ def main():
                 dist.barrier()
                 break
             raise AssertionError("the step of a rank whose peer stopped must fail, not succeed")
-        orc.bulk_update(end_time=T + dt, record_candidates=True)
-        res = sh.bulk_update(T, end_time=T + dt)
+        vel = {}
+        if args.migrate:
+            vx, vy = scenes.uniform(9000 + step, n, 1, -30.0, 30.0), scenes.uniform(9000 + step, n, 2, -30.0, 30.0)
+            orc.bulk_update(end_time=T + dt, vx=vx, vy=vy, record_candidates=True)
+            vel = dict(vel_x=vx[my_ids], vel_y=vy[my_ids])
+        else:
+            orc.bulk_update(end_time=T + dt, record_candidates=True)
+        res = sh.bulk_update(T, end_time=T + dt, **vel)
         ev = sh.eng.fetch_events()
         hi, lo = sh.eng.fetch_candidate_pairs()
         parts = [None] * world
@@ -109,6 +123,19 @@ def main():
             np.testing.assert_array_equal(dkey, np.sort(ohi.astype(np.uint64) << np.uint64(32) | olo))  # disjoint union == the oracle's set
             assert sum(p[3] for p in parts) == len(ov_a)
             assert all(p[5] == 0 for p in parts), "the one-shot event sort must hold on every rank"
+        if args.migrate:
+            st_after = orc.dump_state()
+            before = sh.eng.shard_rows()
+            sent, got = sh.migrate(0)
+            info = sh.eng.shard_rows()
+            assert info["rows"] == before["rows"] - sent + got
+            moved += sent
+            col = np.floor(st_after["pos_x"] / CW)
+            my_ids = np.nonzero((col >= float(bounds[rank])) & (col < float(bounds[rank + 1])))[0]  # residence follows space now
+            assert info["rows"] == len(my_ids), (info, len(my_ids))
+            mine = sh.eng.download_state()
+            for k, colv in mine.items():
+                np.testing.assert_array_equal(bits(colv), bits(st_after[k][my_ids]), err_msg=f"rank {rank} {k}")
         T += dt
         while True:  # drain the oracle's events up to the next step (no velocity changes)
             tt = min(orc.next_time(), T)
@@ -118,7 +145,8 @@ def main():
             if tt >= T:
                 break
     else:
-        print(f"MP_SHARDED_OK rank {rank}: {args.steps} steps, world {world}, exchange {args.exchange}, device {device}", flush=True)
+        assert not args.migrate or moved > 0
+        print(f"MP_SHARDED_OK rank {rank}: {args.steps} steps, world {world}, exchange {args.exchange}, device {device}, rows migrated out {moved}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -6,6 +6,8 @@
              with the overlap set re-uploaded, i.e. exactly the state a config-2/3 run is in.
   config 5   1,000,000 clustered shapes with fast small ones, long slot runs through k_solve_dense
   config 4   its density (1 shape per unit^2) at 1,000,000 hitboxes, through k_solve_dense
+  f-4        config 3's density with resize velocities, four groups (one HbGroup None, asymmetric interact lists) and
+             coordinates centred on the origin, 1,000,000 hitboxes
              Both against the TILED oracle (tests/tiled_oracle.py: 16 independent oracle colliders on the host threads,
              proven equal to the single oracle by tests/test_tiled_oracle.py) — the single oracle needs minutes for them.
   config 2   100,000 shapes through the `Collider` API only: batched add, bulk steps every 0.1 with the Collide events in
@@ -52,17 +54,18 @@ def test_config3_one_million_two_chained_steps(oracle):
     assert eng.event_sort_fallbacks() == 0
 
 
-@pytest.mark.parametrize("name", ["config5_clustered", "config4_density"])
+@pytest.mark.parametrize("name", ["config5_clustered", "config4_density", "config3_groups_resizing"])
 def test_one_million_dense_scenes(oracle, name, monkeypatch):
-    monkeypatch.setenv("CB200_DENSE_RANK", "4")  # the dense kernel from the first step (a run reaches it from its second step)
-    scene = scenes.c5(1_000_000) if name == "config5_clustered" else scenes.c3_dense(1_000_000)
+    if name != "config3_groups_resizing":
+        monkeypatch.setenv("CB200_DENSE_RANK", "4")  # the dense kernel from the first step (a run reaches it from its second step)
+    scene = {"config5_clustered": scenes.c5, "config4_density": scenes.c3_dense, "config3_groups_resizing": scenes.c3_groups}[name](1_000_000)
     want = tiled_bulk_step(oracle, scene, CW, PAD, 0.1, tiles=4)
     eng = cb.Engine(CW, PAD)
     eng.upload_state(**want["state"])
     eng.set_overlaps(*want["overlaps"])
     res = eng.bulk_update(0.0, end_time=0.1)
     t, kind, a, b = want["events"]
-    assert res.n_events == len(t) and res.n_collide_solves > (20_000_000 if name == "config4_density" else 5_000_000)
+    assert res.n_events == len(t) and res.n_collide_solves > {"config4_density": 20_000_000, "config5_clustered": 5_000_000, "config3_groups_resizing": 150_000}[name]
     ev = eng.fetch_events()
     np.testing.assert_array_equal(ev["kind"], kind)
     np.testing.assert_array_equal(ev["a"], a)

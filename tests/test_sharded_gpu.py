@@ -21,7 +21,7 @@ def bits(a):
 
 
 def exchange_on_one_gpu(engs, states):
-    """The all-gather of the halo slabs, done with device-to-device copies between the contexts of one GPU."""
+    """The all-to-all of the per-destination halo slabs, done with device-to-device copies between the contexts of one GPU."""
     import torch
 
     dev = torch.device("cuda", 0)
@@ -30,7 +30,7 @@ def exchange_on_one_gpu(engs, states):
     for r in range(R):
         per = states[r]["slab_bytes"]
         for d in range(R):
-            src = sharding.wrap(states[d]["send_ptr"], per, dev)
+            src = sharding.wrap(states[d]["send_ptr"] + r * per, per, dev)  # the slab rank d addressed to rank r
             dst = sharding.wrap(states[r]["recv_ptr"] + d * per, per, dev)
             dst.copy_(src)
     torch.cuda.synchronize()
@@ -42,7 +42,10 @@ def key_of(ev):
     return np.lexsort((ev["b"], kbit, ev["a"], cls, ev["time"]))
 
 
-def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space", direct=False):
+def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space", direct=False, migrate_margin=None, speed=None):
+    """migrate_margin: after every step the rows that left their rank's strip (by more than that many columns) migrate to
+    the rank that holds them (cb200_shard_take_movers / cb200_shard_add_rows), and every rank's table is compared with the
+    oracle's.  speed: every step installs new random velocities in [-speed, speed]^2 (arrays in the ranks' ascending-id order)."""
     n = len(scene["id"])
     orc = oracle.Collider(CW, PAD)
     orc.add_hitboxes(scene)
@@ -53,13 +56,17 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
         owner = np.clip(np.searchsorted(bounds[1:-1], np.floor(scene["pos_x"] / CW), side="right"), 0, world - 1)
     else:  # residents unrelated to position: every record may have to travel
         owner = (scene["id"] % np.uint64(world)).astype(np.int64)
-    engs = []
+    engs, ids_of = [], []
     for r in range(world):
         e = cb.Engine(CW, PAD)
         e.shard_configure(r, world, bounds, n)
+        if migrate_margin is not None:
+            e.shard_set_row_capacity(n)
         m = owner == r
         e.upload_state(**{k: v[m] for k, v in st.items()})
         engs.append(e)
+        ids_of.append(st["id"][m].astype(np.int64))
+    moved = 0
     if direct:
         # direct exchange over peer memory: here the "peers" are contexts of this process, addressed by raw pointers
         infos = [e.p2p_export() for e in engs]
@@ -72,13 +79,20 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
         for e in engs:
             e.set_overlaps(ov_a, ov_b)
         end = np.inf if end_dt is None else T + end_dt
-        orc.bulk_update(end_time=end, record_candidates=True)
+        vel = [{} for _ in engs]
+        if speed is None:
+            orc.bulk_update(end_time=end, record_candidates=True)
+        else:  # (ids are 0 .. n-1: the oracle's ascending-id arrays are indexed by id)
+            vx, vy = scenes.uniform(9000 + step, n, 1, -speed, speed), scenes.uniform(9000 + step, n, 2, -speed, speed)
+            orc.bulk_update(end_time=end, vx=vx, vy=vy, record_candidates=True)
+            vel = [dict(vel_x=vx[ids], vel_y=vy[ids]) for ids in ids_of]
+        st_after = orc.dump_state()
         import torch
 
         dev = torch.device("cuda", 0)
         if direct:
-            for e in engs:  # every rank's step is enqueued before any is waited for: the kernels wait for each other's flags
-                e.shard_step(T, end_time=end)
+            for e, v in zip(engs, vel):  # every rank's step is enqueued before any is waited for: the kernels wait for each other's flags
+                e.shard_step(T, end_time=end, **v)
             results = [e.shard_result() for e in engs]
             gk = [e.shard_global_next() for e in engs]
             rows = [sharding.wrap(e.shard_local_key_ptr(), 16, dev).view(torch.int64).tolist() for e in engs]
@@ -89,12 +103,13 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
             global_event = sharding.decode_key(*want)
             total_halo += 1
         else:
-            states = [e.shard_begin(T, end_time=end) for e in engs]
+            states = [e.shard_begin(T, end_time=end, **v) for e, v in zip(engs, vel)]
             exchange_on_one_gpu(engs, states)
             key_ptrs = [e.shard_finish() for e in engs]
             results = [e.shard_result() for e in engs]
             for st in states:  # records that actually travelled: the slab headers
-                total_halo += int(sharding.wrap(st["send_ptr"], 4, dev).view(torch.int32).item())
+                for d in range(world):
+                    total_halo += int(sharding.wrap(st["send_ptr"] + d * st["slab_bytes"], 4, dev).view(torch.int32).item())
             # the device-side local keys, all-gathered and min-reduced like sharding.ShardedEngine does
             rows = [sharding.wrap(p, 16, dev).view(torch.int64).tolist() for p in key_ptrs]
             global_event = sharding.decode_key(*sharding.min_key(rows))
@@ -119,6 +134,28 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
         dkey = np.sort(np.concatenate([hi << np.uint64(32) | lo for hi, lo in pairs]))
         np.testing.assert_array_equal(dkey, np.sort(ohi.astype(np.uint64) << np.uint64(32) | olo))
         assert sum(r.n_separate_solves for r in results) == len(ov_a)
+        if migrate_margin is not None:
+            parts = [e.shard_take_movers(migrate_margin) for e in engs]
+            for r, e in enumerate(engs):
+                mine = sharding.rows_for(parts, r)
+                e.shard_add_rows(mine)
+                gone = parts[r][0]["id"].astype(np.int64)
+                ids_of[r] = np.sort(np.concatenate([np.setdiff1d(ids_of[r], gone), mine["id"].astype(np.int64)]))
+                moved += len(gone)
+                info = e.shard_rows()
+                assert info["rows"] == len(ids_of[r]) == e.n
+            assert np.array_equal(np.sort(np.concatenate(ids_of)), np.arange(n)), "every hitbox is resident on exactly one rank"
+            # residence follows space now: the centre column of every row lies in (or within the margin of) its rank's strip
+            col = np.floor(st_after["pos_x"] / CW)
+            for r in range(world):
+                c = col[ids_of[r]]
+                assert np.all(c >= float(bounds[r]) - migrate_margin) and np.all(c < float(bounds[r + 1]) + migrate_margin)
+        if migrate_margin is not None or speed is not None:
+            # every rank's table, in its ascending-id order, is the oracle's table of those hitboxes
+            for r, e in enumerate(engs):
+                got = e.download_state()
+                for k, colv in got.items():
+                    np.testing.assert_array_equal(bits(colv), bits(st_after[k][ids_of[r]]), err_msg=f"rank {r} {k}")
         T = T + dt
         # drain the oracle's events up to the next step (no velocity changes)
         while True:
@@ -128,7 +165,7 @@ def run_sharded_case(oracle, scene, world, steps, dt, end_dt, resident_by="space
                 pass
             if tt >= T:
                 break
-    return total_halo
+    return moved if migrate_margin is not None else total_halo
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -166,3 +203,23 @@ def test_sharded_dense_cells(oracle, direct):
     """Config 4's density across 2 ranks: the long slot runs go through k_solve_dense, pairs straddling the strip edge are
     still solved by exactly one rank."""
     run_sharded_case(oracle, scenes.uniform_density(4000, density=1.0, seed=scenes.SEED_BASE + 41), 2, steps=2, dt=0.1, end_dt=0.1, direct=direct)
+
+
+@pytest.mark.parametrize("direct", [False, True])
+def test_sharded_owner_migration(oracle, direct):
+    """SURVEY.md 8e owner migration: residents start out unrelated to position (id mod world), so the first migration moves
+    about two thirds of all rows to the rank whose strip holds them; later steps install fast new velocities and rows keep
+    crossing strip edges.  After every migration: each hitbox is resident exactly once, residence follows space, every rank's
+    table equals the oracle's, and the following steps (new velocities in the ranks' new array order) still match the oracle
+    event for event.  direct: the peers' mapped receive areas stay where they were."""
+    moved = run_sharded_case(oracle, scenes.uniform_density(6000), 3, steps=5, dt=0.1, end_dt=0.1, resident_by="id", direct=direct,
+                             migrate_margin=0, speed=30.0)
+    assert moved > 4000 + 100, "the first migration re-homes ~2/3 of the rows, later ones move rows that crossed an edge"
+
+
+def test_sharded_migration_hysteresis(oracle):
+    """With a margin of one column, rows whose centre is in the column next to the strip stay where they are."""
+    moved = run_sharded_case(oracle, scenes.uniform_density(6000), 2, steps=8, dt=0.1, end_dt=0.1, migrate_margin=1, speed=30.0)
+    moved0 = run_sharded_case(oracle, scenes.uniform_density(6000), 2, steps=8, dt=0.1, end_dt=0.1, migrate_margin=0, speed=30.0)
+    assert 0 < moved < moved0
+

@@ -49,6 +49,16 @@ def test_direct_exchange_between_processes_dense():
     assert rc == 0 and log.count("MP_SHARDED_OK") == 2, log[-4000:]
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_owner_migration_between_processes(world):
+    """Rows change rank between the steps (ShardedEngine.migrate) while the peers keep writing halo records into the mapped
+    receive areas: residents start unrelated to position, every step installs fast new velocities."""
+    if world > 2 and gpu_count() < world:
+        pytest.skip("more than two ranks only with one GPU per rank")
+    rc, log = launch(world, "--exchange", "direct", "--steps", "4", "--migrate")
+    assert rc == 0 and log.count("MP_SHARDED_OK") == world, log[-4000:]
+
+
 @pytest.mark.parametrize("world", [2, 8])
 def test_nccl_exchange_between_processes(world):
     if gpu_count() < world:

@@ -48,12 +48,13 @@ def _worker(rank, world, port, out):
     try:
         ex = sharding.Exchange()
         per = 3 * sharding.RECORD_BYTES
-        # rank r's halo slab is filled with the tag 16 + r; after the all-gather slot d of every rank must hold 16 + d
-        send = torch.full((per,), 16 + rank, dtype=torch.uint8)
+        # rank r's halo slab for rank d is filled with the tag 16 * (r + 1) + d; after the exchange slot d of rank r must hold
+        # what rank d addressed to r
+        send = torch.cat([torch.full((per,), 16 * (rank + 1) + d, dtype=torch.uint8) for d in range(world)])
         recv = torch.zeros(world * per, dtype=torch.uint8)
-        ex.all_gather_slabs(recv, send)
+        ex.exchange_slabs(recv, send)
         for d in range(world):
-            assert bool((recv[d * per:(d + 1) * per] == 16 + d).all())
+            assert bool((recv[d * per:(d + 1) * per] == 16 * (d + 1) + rank).all())
         # all-gather of the per-rank (time key, tie) minima + lexicographic min, in the device's u64 encoding
         def enc(t, tie):
             bits = struct.unpack("<Q", struct.pack("<d", t))[0]
