@@ -689,15 +689,31 @@ def _main(out):
             fetch_failures[0] += 1
         return eng.fetch_events_begin(pins.next(n_events))
 
+    phase = {"step": 0.0, "fetch_end": 0.0, "fetch_begin": 0.0}  # host seconds of rank-local phases of the t_step loop
+
     def body_tstep():
+        t0 = time.perf_counter()
         r = job.device_step()
-        got = fetch_pipelined(r.n_events)
+        t1 = time.perf_counter()
+        try:
+            eng.fetch_events_end()  # the previous step's download
+        except cb.ColliderError:
+            fetch_failures[0] += 1
+        t2 = time.perf_counter()
+        got = eng.fetch_events_begin(pins.next(r.n_events))
+        t3 = time.perf_counter()
+        phase["step"] += t1 - t0
+        phase["fetch_end"] += t2 - t1
+        phase["fetch_begin"] += t3 - t2
         return {"ev_bytes": got * 16}
 
     body_tstep()
     eng.fetch_events_end()
     digest[0] = events_digest16(pins.last()[: pins.last_n])
+    for k in phase:
+        phase[k] = 0.0
     walls_t, acc_t = timed_passes(job, barrier, K, R, body_tstep, tail=eng.fetch_events_end)
+    phase_ms = {k: v / (K * R) * 1e3 for k, v in phase.items()}
 
     # (3) per-kernel durations: K steps with CUDA events between the stages (each event adds ~2 us of stream time, so these are
     # upper bounds and their sum exceeds device_ms_per_step)
@@ -733,7 +749,8 @@ def _main(out):
         sampler.join(timeout=2)
 
     med = lambda w: float(np.median(w))
-    times = torch.tensor([med(walls_dev), med(walls_t), med(walls_e), dev_ms, min(walls_t), max(walls_t)], dtype=torch.float64, device="cuda")
+    times = torch.tensor([med(walls_dev), med(walls_t), med(walls_e), dev_ms, min(walls_t), max(walls_t), phase_ms["step"], phase_ms["fetch_end"], phase_ms["fetch_begin"]],
+                         dtype=torch.float64, device="cuda")
     sums = torch.tensor([float(acc["solves"]), float(acc["entries"]), float(acc["cells"]), float(acc["events"])], dtype=torch.float64, device="cuda")
     digests = [digest[0]]
     if world > 1:
@@ -741,7 +758,7 @@ def _main(out):
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         digests = [None] * world
         dist.all_gather_object(digests, digest[0])
-    wall_dev, wall_t, wall_e, dev_ms_max, wall_t_min, wall_t_max = times.tolist()
+    wall_dev, wall_t, wall_e, dev_ms_max, wall_t_min, wall_t_max, ph_step, ph_end, ph_begin = times.tolist()
     solves_all = sums.tolist()[0]
 
     sort_fallbacks = eng.event_sort_fallbacks()
@@ -794,6 +811,7 @@ def _main(out):
                                 "events) into pinned host memory, the download of step k overlapping step k+1; wall clock around the C-ABI calls, bracketed by "
                                 "barrier + cuda sync",
                        "t_step_ms_min_max_over_runs": [wall_t_min / K * 1e3, wall_t_max / K * 1e3],
+                       "t_step_host_phases_ms_max_rank": {"bulk_step_until_result": ph_step, "fetch_events_end": ph_end, "fetch_events_begin": ph_begin},
                        "l2": "working set per step (SoA state + records + slot table + entries, > 300 MB) exceeds the 126 MB L2; no flush needed"},
             "device_ms_per_step": dev_ms_max,
             "device_resident_step_only": {"value": n * world * K / wall_dev, "unit": UNIT, "ms_per_step": wall_dev / K * 1e3,

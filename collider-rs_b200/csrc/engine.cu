@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <map>
 #include <set>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -215,6 +216,7 @@ struct cb200_ctx {
     DevBuf<EventOut> ev_out;
     Key128* sorted_keys = nullptr;  // where the last sort left the sorted keys (keys_a or keys_b)
     bool ev_out_valid = false;      // ev_out holds the 32-byte records of the sorted keys
+    int prio_low = 0;
     cudaEvent_t ev_keys_done = nullptr;
     bool ev_sorted = false;
     // pipelined I/O: compact events leave on their own copy stream (double-buffered), staged velocities arrive on another
@@ -233,6 +235,22 @@ struct cb200_ctx {
     bool sort_oneshot = true;        // CB200_SORT=slow: recursive bucket sort / radix sort only (A/B and tests)
     uint32_t* h_sort_big = nullptr;  // pinned, mapped: k_bs_scan8's oversized-bucket report [1 + 2 * kBsMaxBig]
     uint32_t* d_sort_big = nullptr;  // its device alias
+    // pipelined fetch: the one-shot sort as two replayed graphs (keys on the context's stream, sort + decode on the copy stream)
+    SortIn* h_sort_in = nullptr;     // pinned, mapped: the step's counts, written by the host before the launch
+    SortIn* d_sort_in = nullptr;
+    DevBuf<SortDyn> sort_dyn;
+    struct FetchGraph {
+        uint64_t sig = 0;
+        cudaGraphExec_t keys = nullptr, sort = nullptr;
+    };
+    static constexpr int kFetchGraphs = 8;  // column-buffer set x destination buffer (+ re-captures after a buffer grew)
+    FetchGraph fetch_graphs[kFetchGraphs];
+    int fetch_graph_next = 0;
+    bool fetch_graph_enabled = true;
+    // the copy-stream half of a pipelined fetch (sort graph + download) is launched AFTER the next step has been queued, so
+    // that the host's driver calls for it are off the step-to-step critical path (flush_deferred_fetch)
+    cudaGraphExec_t fetch_deferred_sort = nullptr;
+    const Event16* fetch_deferred_src = nullptr;
     uint64_t sort_fallbacks = 0;
     uint64_t n_ev_sorted = 0;
 
@@ -373,7 +391,15 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
         delete c;
         return fail(nullptr, CB200_E_CUDA, m);
     };
-    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    {
+        // the step runs at the highest stream priority, the event sort / download stream (ensure_io_streams) at the lowest: when
+        // both have blocks pending, the step's kernels — the critical path, and in sharded mode what the peers wait for — go first
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) least = greatest = 0;
+        if (getenv("CB200_NO_PRIORITY")) least = greatest = 0;
+        c->prio_low = least;
+        if ((e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, greatest)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    }
     if ((e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return bail("cudaDeviceGetAttribute", e);
     if ((e = cudaMalloc(&c->d_ctr, sizeof(Counters))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&c->d_key, sizeof(MinKey))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -405,6 +431,9 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaHostGetDevicePointer((void**)&c->d_res, c->h_res, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     if ((e = cudaHostAlloc(&c->h_sort_big, (1 + 2 * kBsMaxBig) * sizeof(uint32_t), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer((void**)&c->d_sort_big, c->h_sort_big, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
+    if ((e = cudaHostAlloc(&c->h_sort_in, sizeof(SortIn), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
+    if ((e = cudaHostGetDevicePointer((void**)&c->d_sort_in, c->h_sort_in, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
+    if (const char* v = getenv("CB200_FETCH_GRAPH")) c->fetch_graph_enabled = v[0] != '0';
     if (const char* so = getenv("CB200_SORT")) c->sort_oneshot = strcmp(so, "slow") != 0;
     if (const char* v = getenv("CB200_TILE")) c->tile_enabled = v[0] != '0';
     if (const char* v = getenv("CB200_OV_SORT")) c->ov_sort = v[0] != '0';
@@ -457,6 +486,12 @@ void cb200_destroy(cb200_ctx* c) {
     if (c->h_gkey) cudaFreeHost(c->h_gkey);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_sort_big) cudaFreeHost(c->h_sort_big);
+    if (c->h_sort_in) cudaFreeHost(c->h_sort_in);
+    for (auto& g : c->fetch_graphs) {
+        if (g.keys) cudaGraphExecDestroy(g.keys);
+        if (g.sort) cudaGraphExecDestroy(g.sort);
+    }
+    c->sort_dyn.release();
     if (c->pinned_stage) cudaFreeHost(c->pinned_stage);
     for (auto& ev : c->ev_t)
         if (ev) cudaEventDestroy(ev);
@@ -1563,6 +1598,7 @@ static int launch_step_graph(cb200_ctx* ctx, double time, const double* const* n
     return CB200_OK;
 }
 
+static int flush_deferred_fetch(cb200_ctx* ctx);
 int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, double end_time, cb200_step_result* out) {
     if (!ctx) return CB200_E_ARG;
     if (!ctx->have_state) return fail(ctx, CB200_E_STATE, "bulk_update before upload_state");
@@ -1595,6 +1631,7 @@ int cb200_bulk_update(cb200_ctx* ctx, double time, const cb200_vel_view* vel, do
                 if ((rc = enqueue_back(ctx, time, false)) != CB200_OK) return rc;
             }
         }
+        if ((rc = flush_deferred_fetch(ctx)) != CB200_OK) return rc;  // (the previous step's event download: behind this step's launch)
         if ((rc = complete_step(ctx, time, &again)) != CB200_OK) return rc;
         if (ctx->last.ctr.err_flags) break;
     }
@@ -1847,7 +1884,7 @@ int cb200_shard_finish(cb200_ctx* ctx, void** local_key) {
     if (rc != CB200_OK) return rc;
     ctx->shard_phase = 2;
     if (local_key) *local_key = ctx->d_key;
-    return CB200_OK;
+    return flush_deferred_fetch(ctx);
 }
 
 // Synchronous: waits for the step; re-runs the back half if a buffer had to grow; fills the (local) result.
@@ -2016,7 +2053,7 @@ int cb200_shard_step(cb200_ctx* ctx, double time, const cb200_vel_view* vel, dou
     if (!replayed && (rc = enqueue_direct_step(ctx, time, nv, end_time)) != CB200_OK) return rc;
     CU(cudaEventRecord(ctx->ev_t[ST_COUNT], ctx->stream));
     ctx->shard_phase = 2;
-    return CB200_OK;
+    return flush_deferred_fetch(ctx);  // (the previous step's event download: behind this step's launch)
 }
 
 // After cb200_shard_result of a direct-exchange step: the global next event (minimum over all ranks).  *complete == 0:
@@ -2204,6 +2241,8 @@ static int sort_events_slow(cb200_ctx* ctx, uint32_t nt, uint32_t n_pairs, uint6
 static int sort_events_to(cb200_ctx* ctx, EventOut* copy_to, uint64_t offset, uint64_t cap, uint64_t* taken) {
     if (taken) *taken = 0;
     if (ctx->fetch_pending) {  // (a pipelined download may still be sorting on the copy stream: it shares the key buffers)
+        int rc = flush_deferred_fetch(ctx);
+        if (rc != CB200_OK) return rc;
         CU(cudaStreamSynchronize(ctx->d2h_stream));
     }
     if (ctx->ev_sorted && !ctx->ev_out_valid && ctx->n_ev_sorted) {
@@ -2277,8 +2316,8 @@ int cb200_fetch_events(cb200_ctx* ctx, cb200_event* buf, uint64_t cap, uint64_t 
 // ---- pipelined I/O -----------------------------------------------------------------------------------------
 static int ensure_io_streams(cb200_ctx* ctx) {
     if (ctx->d2h_stream) return CB200_OK;
-    CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithPriority(&ctx->d2h_stream, cudaStreamNonBlocking, ctx->prio_low));
+    CU(cudaStreamCreateWithPriority(&ctx->h2d_stream, cudaStreamNonBlocking, ctx->prio_low));
     CU(cudaEventCreateWithFlags(&ctx->ev_sorted_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_keys_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_staged_done[0], cudaEventDisableTiming));
@@ -2310,6 +2349,109 @@ int cb200_stage_velocities(cb200_ctx* ctx, const cb200_vel_view* vel) {
     return CB200_OK;
 }
 
+// The pipelined fetch's sort as two replayed CUDA graphs (sort.cuh "sizes in DEVICE memory"): the order keys on the context's
+// stream, then — beside whatever that stream does next — bucket sort and decode into `dst` on the copy stream.
+static int capture_to_exec(cb200_ctx* ctx, cudaStream_t st, cudaGraphExec_t* exec, const std::function<void()>& body) {
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        cudaGetLastError();
+        return CB200_E_CUDA;
+    }
+    body();
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (e != cudaSuccess || !graph) {
+        cudaGetLastError();
+        return CB200_E_CUDA;
+    }
+    e = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return CB200_E_CUDA;
+    }
+    return CB200_OK;
+}
+// Second half of a pipelined fetch: the sort graph and the download, on the copy stream.  Called once the next step has been
+// queued (cb200_bulk_update / cb200_shard_step / cb200_shard_finish) or when the caller waits for the fetch / reads the queue.
+static int flush_deferred_fetch(cb200_ctx* ctx) {
+    if (!ctx->fetch_deferred_sort) return CB200_OK;
+    cudaGraphExec_t g = ctx->fetch_deferred_sort;
+    ctx->fetch_deferred_sort = nullptr;
+    CU(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_keys_done, 0));
+    CU(cudaGraphLaunch(g, ctx->d2h_stream));
+    if (ctx->fetch_take) CU(cudaMemcpyAsync(ctx->fetch_dst, ctx->fetch_deferred_src, ctx->fetch_take * sizeof(Event16), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    return CB200_OK;
+}
+
+static int enqueue_sort_graph(cb200_ctx* ctx, uint32_t n_pairs, uint64_t n_solitaire, Event16* dst, size_t cap_keys) {
+    int log2_cap = 6;
+    while ((1ull << log2_cap) * 8ull < cap_keys && log2_cap < 24) ++log2_cap;
+    const uint32_t nb_max = 2u << log2_cap;
+    const uint32_t scan_blocks = (nb_max + kBs2Chunk - 1) / kBs2Chunk;
+    DevBuf<uint32_t>& tab = ctx->bs_tab[0];
+    CU(tab.reserve(2 * (size_t)nb_max + 16 + scan_blocks));
+    CU(ctx->sort_dyn.reserve(1));
+    uint32_t* count = tab.p;                // [n_buckets + 1] then: offsets
+    uint32_t* cursor = tab.p + nb_max + 4;  // [n_buckets]
+    BsRange* range = reinterpret_cast<BsRange*>(tab.p + 2 * (size_t)nb_max + 4);  // [2]: time keys, first labels
+    uint32_t* block_total = tab.p + 2 * (size_t)nb_max + 12;
+    Key128 *keys = ctx->keys_a.p, *tmp = ctx->keys_b.p;
+    SortDyn* dyn = ctx->sort_dyn.p;
+    const uint32_t n = ctx->n;
+    const uint32_t g_rows = std::max<uint32_t>(1, std::min<uint32_t>((n + kThreads - 1) / kThreads, (uint32_t)ctx->sm_count * 8u));
+    const uint32_t g_keys = (uint32_t)std::max<size_t>(1, std::min<size_t>((cap_keys + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 16u));
+    // signature of everything the captured launches carry
+    uint64_t h = 0xcbf29ce484222325ull;
+    auto mix = [&h](uint64_t v) {
+        h ^= v;
+        h *= 0x100000001b3ull;
+        h ^= h >> 29;
+    };
+    const void* ptrs[] = {count, keys, tmp, dyn, dst, ctx->events.p, ctx->reit.p, ctx->col[9].p, ctx->label.p, ctx->d_ctr, ctx->d_sort_in, ctx->d_sort_big};
+    for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
+    mix(n); mix(nb_max); mix(g_keys); mix((uint64_t)log2_cap);
+    if (!h) h = 1;
+    cb200_ctx::FetchGraph* slot = nullptr;
+    for (auto& g : ctx->fetch_graphs)
+        if (g.sig == h && g.keys && g.sort) slot = &g;
+    if (!slot) {
+        cb200_ctx::FetchGraph& g = ctx->fetch_graphs[ctx->fetch_graph_next];
+        ctx->fetch_graph_next = (ctx->fetch_graph_next + 1) % cb200_ctx::kFetchGraphs;
+        if (g.keys) cudaGraphExecDestroy(g.keys);
+        if (g.sort) cudaGraphExecDestroy(g.sort);
+        g = cb200_ctx::FetchGraph{};
+        int rc = capture_to_exec(ctx, ctx->stream, &g.keys, [&]() {
+            k_sortdyn_init<<<1, 1, 0, ctx->stream>>>(ctx->d_sort_in, dyn, range, ctx->d_ctr, log2_cap);
+            k_sortdyn_zero<<<(uint32_t)ctx->sm_count * 2u, kThreads, 0, ctx->stream>>>(dyn, count);
+            if (n) k_keys_solitaire<<<g_rows, kThreads, 0, ctx->stream>>>(n, ctx->reit.p, ctx->col[9].p, ctx->label.p, keys, ctx->d_ctr, range, range + 1);
+            k_keys_pairs_dyn<<<g_keys, kThreads, 0, ctx->stream>>>(dyn, ctx->events.p, keys, range, range + 1);
+        });
+        if (rc != CB200_OK) return fail(ctx, rc, "capture of the event-key graph failed");
+        cudaStream_t st = ctx->d2h_stream;
+        rc = capture_to_exec(ctx, st, &g.sort, [&]() {
+            k_bs2_count_dyn<<<g_keys, kThreads, 0, st>>>(dyn, keys, range, count);
+            k_bs2_scan_local_dyn<<<scan_blocks, 256, 0, st>>>(count, dyn, cursor, block_total);
+            k_bs2_scan_add_dyn<<<scan_blocks, 256, 0, st>>>(count, dyn, cursor, block_total, ctx->d_sort_big);
+            k_bs2_scatter_dyn<<<g_keys, kThreads, 0, st>>>(dyn, keys, range, cursor, tmp);
+            k_bs_local_dyn<<<(uint32_t)ctx->sm_count * 8u, 256, 0, st>>>(tmp, count, dyn, keys);
+            k_decode_events16_dyn<<<g_keys, kThreads, 0, st>>>(dyn, keys, dst);
+        });
+        if (rc != CB200_OK) return fail(ctx, rc, "capture of the event-sort graph failed");
+        g.sig = h;
+        slot = &g;
+    }
+    ctx->h_sort_in->n_pairs = n_pairs;
+    ctx->h_sort_in->n_sol = n_solitaire;
+    ctx->h_sort_in->add_mode = ctx->last_add_mode ? 1u : 0u;
+    CU(cudaGraphLaunch(slot->keys, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_keys_done, ctx->stream));
+    ctx->fetch_deferred_sort = slot->sort;  // (launched by flush_deferred_fetch)
+    ctx->ev_out_valid = false;
+    ctx->sorted_keys = keys;
+    ctx->launches += 10;
+    return CB200_OK;
+}
+
 // The sorted events of the last step in the compact form (cb200_event16), downloaded on the context's copy stream: returns
 // as soon as the sort and the copy are queued, so the caller can start the next bulk step; cb200_fetch_events_end waits for
 // the copy.  *n_out = events that will be in buf[0 .. *n_out) (at most cap).
@@ -2331,12 +2473,18 @@ int cb200_fetch_events_begin(cb200_ctx* ctx, cb200_event16* buf, uint64_t cap, u
     DevBuf<Event16>& dst = ctx->ev16[ctx->ev16_parity];
     ctx->fetch_oneshot_pending = false;
     if (nt) {
-        CU(ctx->keys_a.reserve(nt)); CU(ctx->keys_b.reserve(nt)); CU(dst.reserve(nt));
-        bool on_copy_stream = false;
+        // (sized for everything a step can queue, so that the buffers — and the graphs that carry their addresses — stay put)
+        const size_t cap_keys = std::max<size_t>(nt, ctx->events.cap + (size_t)ctx->n);
+        CU(ctx->keys_a.reserve(cap_keys)); CU(ctx->keys_b.reserve(cap_keys)); CU(dst.reserve(cap_keys));
+        bool on_copy_stream = false, decoded = false;
         if (!ctx->ev_sorted) {
             ctx->n_ev_sorted = total;
             ctx->h_sort_big[0] = 0;
-            if (ctx->sort_oneshot) {
+            if (ctx->sort_oneshot && ctx->fetch_graph_enabled && !ctx->capturing) {
+                if ((rc = enqueue_sort_graph(ctx, (uint32_t)c.n_pair_events, c.n_solitaire, dst.p, cap_keys)) != CB200_OK) return rc;
+                ctx->fetch_oneshot_pending = true;
+                on_copy_stream = decoded = true;
+            } else if (ctx->sort_oneshot) {
                 // keys on the context's stream (a few microseconds), the bucket sort on the copy stream: the next bulk step does
                 // not wait for it
                 if ((rc = enqueue_sort_oneshot(ctx, nt, (uint32_t)c.n_pair_events, c.n_solitaire, ctx->d2h_stream, false)) != CB200_OK) return rc;
@@ -2350,15 +2498,20 @@ int cb200_fetch_events_begin(cb200_ctx* ctx, cb200_event16* buf, uint64_t cap, u
         }
         // the sorted keys -> compact records, on the stream that sorted them
         cudaStream_t ds = on_copy_stream ? ctx->d2h_stream : ctx->stream;
-        k_decode_events16<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ds>>>(nt, ctx->sorted_keys, dst.p, ctx->last_add_mode ? 1 : 0);
-        ctx->launches += 1;
+        if (!decoded) {
+            k_decode_events16<<<(nt + kThreads - 1) / kThreads, kThreads, 0, ds>>>(nt, ctx->sorted_keys, dst.p, ctx->last_add_mode ? 1 : 0);
+            ctx->launches += 1;
+        }
+        if (!on_copy_stream) {
+            CU(cudaEventRecord(ctx->ev_sorted_done, ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_sorted_done, 0));
+        }
     }
-    CU(cudaEventRecord(ctx->ev_sorted_done, ctx->stream));
-    CU(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_sorted_done, 0));
-    if (take) CU(cudaMemcpyAsync(buf, dst.p, take * sizeof(Event16), cudaMemcpyDeviceToHost, ctx->d2h_stream));
-    ctx->fetch_pending = true;
     ctx->fetch_dst = reinterpret_cast<Event16*>(buf);
     ctx->fetch_take = take;
+    ctx->fetch_deferred_src = dst.p;
+    if (!ctx->fetch_deferred_sort && take) CU(cudaMemcpyAsync(buf, dst.p, take * sizeof(Event16), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    ctx->fetch_pending = true;
     ctx->fetch_nt = nt;
     ctx->fetch_np = (uint32_t)c.n_pair_events;
     ctx->fetch_ns = c.n_solitaire;
@@ -2369,6 +2522,10 @@ int cb200_fetch_events_end(cb200_ctx* ctx) {
     if (!ctx) return CB200_E_ARG;
     if (!ctx->fetch_pending) return CB200_OK;
     CU(cudaSetDevice(ctx->device));
+    {
+        int rc = flush_deferred_fetch(ctx);
+        if (rc != CB200_OK) return rc;
+    }
     CU(cudaStreamSynchronize(ctx->d2h_stream));
     ctx->fetch_pending = false;
     if (ctx->fetch_oneshot_pending && ctx->h_sort_big[0] != 0) {

@@ -63,7 +63,8 @@ __global__ void k_keys_solitaire(uint32_t n, const uint8_t* __restrict__ reit, c
     if (range) block_range_reduce(lo, hi, range);
     if (lab_range) block_range_reduce(llo, lhi, lab_range);
 }
-__global__ void k_keys_pairs(uint32_t n_ev, const PairEvent* __restrict__ ev, Key128* keys, unsigned long long base, BsRange* range, BsRange* lab_range) {
+__device__ __forceinline__ void keys_pairs_body(uint32_t n_ev, const PairEvent* __restrict__ ev, Key128* keys, unsigned long long base, BsRange* range,
+                                                BsRange* lab_range) {
     unsigned long long lo = ~0ull, hi = 0ull, llo = ~0ull, lhi = 0ull;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ev; i += gridDim.x * blockDim.x) {
         const PairEvent e = ev[i];
@@ -76,6 +77,9 @@ __global__ void k_keys_pairs(uint32_t n_ev, const PairEvent* __restrict__ ev, Ke
     }
     if (range) block_range_reduce(lo, hi, range);
     if (lab_range) block_range_reduce(llo, lhi, lab_range);
+}
+__global__ void k_keys_pairs(uint32_t n_ev, const PairEvent* __restrict__ ev, Key128* keys, unsigned long long base, BsRange* range, BsRange* lab_range) {
+    keys_pairs_body(n_ev, ev, keys, base, range, lab_range);
 }
 __global__ void k_key_diff(uint32_t n, const Key128* __restrict__ keys, Counters* ctr) {
     const Key128 k0 = keys[0];
@@ -337,7 +341,7 @@ __global__ void k_bs_scatter(uint32_t n, const Key128* __restrict__ keys, int fi
 }
 __device__ __forceinline__ bool key128_less(const Key128& a, const Key128& b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
 // one warp per bucket: rank sort in shared memory; larger buckets are left in `in` (the host sorts them there next)
-__global__ void __launch_bounds__(256) k_bs_local(const Key128* __restrict__ in, const uint32_t* __restrict__ offsets, uint32_t n_buckets, Key128* out) {
+__device__ __forceinline__ void bs_local_body(const Key128* __restrict__ in, const uint32_t* __restrict__ offsets, uint32_t n_buckets, Key128* out) {
     __shared__ Key128 s_keys[8][kBsMaxBucket];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t b = blockIdx.x * 8 + warp; b < n_buckets; b += gridDim.x * 8) {
@@ -361,6 +365,9 @@ __global__ void __launch_bounds__(256) k_bs_local(const Key128* __restrict__ in,
         }
         __syncwarp();
     }
+}
+__global__ void __launch_bounds__(256) k_bs_local(const Key128* __restrict__ in, const uint32_t* __restrict__ offsets, uint32_t n_buckets, Key128* out) {
+    bs_local_body(in, offsets, n_buckets, out);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -402,8 +409,8 @@ __global__ void k_bs2_scatter(uint32_t n, const Key128* __restrict__ keys, const
 // accesses) and leaves the block totals; k_bs2_scan_add gives every block the sum of the totals before it (there are at
 // most a few thousand), writes offsets and cursors, and reports the buckets that are too large for a warp.
 constexpr int kBs2Chunk = 256 * 8;
-__global__ void __launch_bounds__(256) k_bs2_scan_local(const uint32_t* __restrict__ count, uint32_t n_buckets, uint32_t* __restrict__ local,
-                                                        uint32_t* __restrict__ block_total) {
+__device__ __forceinline__ void bs2_scan_local_body(const uint32_t* __restrict__ count, uint32_t n_buckets, uint32_t* __restrict__ local,
+                                                    uint32_t* __restrict__ block_total) {
     __shared__ uint32_t s_w[8];
     const uint32_t i0 = blockIdx.x * kBs2Chunk + threadIdx.x * 8u;
     uint32_t v[8], sum = 0;
@@ -447,9 +454,13 @@ __global__ void __launch_bounds__(256) k_bs2_scan_local(const uint32_t* __restri
     }
     if (threadIdx.x == 0) block_total[blockIdx.x] = total;
 }
+__global__ void __launch_bounds__(256) k_bs2_scan_local(const uint32_t* __restrict__ count, uint32_t n_buckets, uint32_t* __restrict__ local,
+                                                        uint32_t* __restrict__ block_total) {
+    bs2_scan_local_body(count, n_buckets, local, block_total);
+}
 // count -> offsets in place (offsets[n_buckets] = total); cursor = the block-local scan on entry, a copy of offsets on exit
-__global__ void __launch_bounds__(256) k_bs2_scan_add(uint32_t* count_offsets, uint32_t n_buckets, uint32_t* cursor, const uint32_t* __restrict__ block_total,
-                                                      uint32_t* big /* mapped host memory; big[0] zeroed by the host */) {
+__device__ __forceinline__ void bs2_scan_add_body(uint32_t* count_offsets, uint32_t n_buckets, uint32_t* cursor, const uint32_t* __restrict__ block_total,
+                                                  uint32_t* big /* mapped host memory; big[0] zeroed by the host */) {
     __shared__ uint32_t s_w[8];
     uint32_t part = 0;
     for (uint32_t b = threadIdx.x; b < blockIdx.x; b += blockDim.x) part += block_total[b];
@@ -478,6 +489,10 @@ __global__ void __launch_bounds__(256) k_bs2_scan_add(uint32_t* count_offsets, u
             if (i == n_buckets - 1) count_offsets[n_buckets] = off + v;
         }
     }
+}
+__global__ void __launch_bounds__(256) k_bs2_scan_add(uint32_t* count_offsets, uint32_t n_buckets, uint32_t* cursor, const uint32_t* __restrict__ block_total,
+                                                      uint32_t* big) {
+    bs2_scan_add_body(count_offsets, n_buckets, cursor, block_total, big);
 }
 
 // Decode sorted keys to the C-ABI event records (layout of cb200_event: f64 time, u64 a, u64 b, u32 kind, u32 pad).
@@ -512,10 +527,7 @@ struct Event16 {
     double time;
     uint32_t a, b;
 };
-__global__ void k_decode_events16(uint32_t n, const Key128* __restrict__ keys, Event16* out, int add_mode) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const Key128 k = keys[i];
+__device__ __forceinline__ Event16 decode_event16(const Key128& k, int add_mode) {
     Event16 e;
     e.time = key_time(k.hi);
     if (k.lo & kPairClass) {
@@ -528,7 +540,86 @@ __global__ void k_decode_events16(uint32_t n, const Key128* __restrict__ keys, E
         e.a = (uint32_t)k.lo | 0x80000000u;  // Reiterate
         e.b = 0u;
     }
-    out[i] = e;
+    return e;
+}
+__global__ void k_decode_events16(uint32_t n, const Key128* __restrict__ keys, Event16* out, int add_mode) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = decode_event16(keys[i], add_mode);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The one-shot sort with its sizes in DEVICE memory: the same kernel bodies, launched with grids sized for the buffers'
+// capacity, so that the whole sequence is one pair of CUDA graphs replayed every step (engine.cu cb200_fetch_events_begin:
+// sixteen driver calls per step became four).  The host writes the step's counts into a mapped struct (SortIn) before it
+// launches the first graph; k_sortdyn_init turns them into the sort's parameters.
+struct SortIn {  // pinned, mapped host memory
+    unsigned long long n_pairs, n_sol;
+    uint32_t add_mode, pad;
+};
+struct SortDyn {
+    uint32_t nt, n_pairs, n_buckets;
+    int log2_buckets;
+    unsigned long long n_sol;
+    uint32_t add_mode, pad;
+};
+__host__ __device__ inline int bs2_log2_buckets(uint32_t nt, int log2_cap) {
+    int l = 6;
+    while ((1u << l) * 8u < nt && l < log2_cap) ++l;  // ~8 keys per bucket (a warp sorts up to kBsMaxBucket)
+    return l;
+}
+__global__ void k_sortdyn_init(const volatile SortIn* in, SortDyn* d, BsRange* range /* [2] */, Counters* ctr, int log2_cap) {
+    SortDyn v;
+    v.n_pairs = (uint32_t)in->n_pairs;
+    v.n_sol = in->n_sol;
+    v.nt = v.n_pairs + (uint32_t)v.n_sol;
+    v.log2_buckets = bs2_log2_buckets(v.nt, log2_cap);
+    v.n_buckets = 2u << v.log2_buckets;  // region A + region B
+    v.add_mode = in->add_mode;
+    v.pad = 0;
+    *d = v;
+    range[0] = BsRange{~0ull, 0ull};
+    range[1] = BsRange{~0ull, 0ull};
+    ctr->n_sort_keys = 0ull;
+}
+__global__ void k_sortdyn_zero(const SortDyn* d, uint32_t* count) {
+    const uint32_t m = d->n_buckets + 1u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) count[i] = 0u;
+}
+__global__ void k_keys_pairs_dyn(const SortDyn* d, const PairEvent* __restrict__ ev, Key128* keys, BsRange* range, BsRange* lab_range) {
+    keys_pairs_body(d->n_pairs, ev, keys, d->n_sol, range, lab_range);
+}
+__global__ void k_bs2_count_dyn(const SortDyn* d, const Key128* __restrict__ keys, const BsRange* r, uint32_t* count) {
+    const uint32_t n = d->nt;
+    const int l = d->log2_buckets;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&count[bs2_bucket(keys[i], r[0], l, r[1])], 1u);
+}
+__global__ void k_bs2_scatter_dyn(const SortDyn* d, const Key128* __restrict__ keys, const BsRange* r, uint32_t* cursor, Key128* out) {
+    const uint32_t n = d->nt;
+    const int l = d->log2_buckets;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Key128 k = keys[i];
+        out[atomicAdd(&cursor[bs2_bucket(k, r[0], l, r[1])], 1u)] = k;
+    }
+}
+__global__ void __launch_bounds__(256) k_bs2_scan_local_dyn(const uint32_t* __restrict__ count, const SortDyn* d, uint32_t* __restrict__ local,
+                                                            uint32_t* __restrict__ block_total) {
+    const uint32_t n_buckets = d->n_buckets;
+    if (blockIdx.x * (uint32_t)kBs2Chunk >= n_buckets) return;  // (the grid is sized for the largest table)
+    bs2_scan_local_body(count, n_buckets, local, block_total);
+}
+__global__ void __launch_bounds__(256) k_bs2_scan_add_dyn(uint32_t* count_offsets, const SortDyn* d, uint32_t* cursor, const uint32_t* __restrict__ block_total,
+                                                          uint32_t* big) {
+    const uint32_t n_buckets = d->n_buckets;
+    if (blockIdx.x * (uint32_t)kBs2Chunk >= n_buckets) return;
+    bs2_scan_add_body(count_offsets, n_buckets, cursor, block_total, big);
+}
+__global__ void __launch_bounds__(256) k_bs_local_dyn(const Key128* __restrict__ in, const uint32_t* __restrict__ offsets, const SortDyn* d, Key128* out) {
+    bs_local_body(in, offsets, d->n_buckets, out);
+}
+__global__ void k_decode_events16_dyn(const SortDyn* d, const Key128* __restrict__ keys, Event16* out) {
+    const uint32_t n = d->nt;
+    const int add_mode = (int)d->add_mode;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = decode_event16(keys[i], add_mode);
 }
 
 }  // namespace cb200

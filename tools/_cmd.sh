@@ -1,0 +1,5 @@
+timeout 400 python -m pytest tests/test_sharded_multiprocess_gpu.py -x -q -m gpu --timeout 300 2>&1 | tail -4
+for g in 8 4; do
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 2951$g bench.py --gpus $g --steps 50 --warmup 5 > gpurun_out/r3d_g$g.json 2> gpurun_out/r3d_g$g.err || tail -5 gpurun_out/r3d_g$g.err
+python profiles/bench_summary.py gpurun_out/r3d_g$g.json 2>/dev/null | head -1 | cut -c1-330
+done
