@@ -247,6 +247,7 @@ struct cb200_ctx {
     FetchGraph fetch_graphs[kFetchGraphs];
     int fetch_graph_next = 0;
     bool fetch_graph_enabled = true;
+    bool solve_prefetch = false;  // CB200_SOLVE_PREFETCH=1
     // the copy-stream half of a pipelined fetch (sort graph + download) is launched AFTER the next step has been queued, so
     // that the host's driver calls for it are off the step-to-step critical path (flush_deferred_fetch)
     cudaGraphExec_t fetch_deferred_sort = nullptr;
@@ -434,6 +435,7 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaHostAlloc(&c->h_sort_in, sizeof(SortIn), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer((void**)&c->d_sort_in, c->h_sort_in, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     if (const char* v = getenv("CB200_FETCH_GRAPH")) c->fetch_graph_enabled = v[0] != '0';
+    if (const char* v = getenv("CB200_SOLVE_PREFETCH")) c->solve_prefetch = v[0] != '0';
     if (const char* so = getenv("CB200_SORT")) c->sort_oneshot = strcmp(so, "slow") != 0;
     if (const char* v = getenv("CB200_TILE")) c->tile_enabled = v[0] != '0';
     if (const char* v = getenv("CB200_OV_SORT")) c->ov_sort = v[0] != '0';
@@ -1168,6 +1170,7 @@ static SolveArgs solve_args_of(cb200_ctx* ctx, const ShardGeom& sh, const VisSpa
     sv.sharded = ctx->sharded ? 1 : 0;
     sv.ids = ctx->sharded ? nullptr : ctx->ids.p;
     sv.dbg = getenv("CB200_DBG_S") ? (uint32_t)atoi(getenv("CB200_DBG_S")) : 0u;
+    sv.prefetch = ctx->solve_prefetch ? 1u : 0u;
     sv.add_mode = ctx->add_mode ? 1 : 0;
     sv.imm_pairs = ctx->imm_pairs.p;
     sv.n_imm = ctx->d_n_imm;
@@ -1524,6 +1527,7 @@ static uint64_t step_signature(cb200_ctx* ctx, const double* const* nv) {
     if (const char* d = getenv("CB200_DBG_S")) mix((uint64_t)atoi(d) + 31);
     mix(ctx->ld256 ? 257u : 129u);
     mix(ctx->solve_two_phase ? 2u : 1u);
+    mix(ctx->solve_prefetch ? 7u : 3u);
     if (ctx->ov_track && ctx->ov_ready) {
         mix(0xd7a1); mix(ctx->ov_cap_pairs); mix(ctx->ov_n_keys); mix(ctx->ov_bit_words); mix(ctx->ov_pairs.cap);
         const void* dp[] = {ctx->d_ov, ctx->surv.p};

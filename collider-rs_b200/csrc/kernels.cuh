@@ -1226,6 +1226,7 @@ struct SolveArgs {
     int32_t col_lo, col_hi;
     const uint64_t* ids;     // label -> HbId (null: the label is the id)
     uint32_t dbg;            // timing experiments only (CB200_DBG_S): 1 skip the narrowphase, 2 skip the event append, 4 skip the candidate test
+    uint32_t prefetch;       // k_solve: request the next work item's records into L2 one iteration ahead (CB200_SOLVE_PREFETCH)
     // add mode (batched Collider::add_hitbox, collider.rs:214-222 + 355-365): a candidate whose collide delay is exactly 0.0
     // overlaps NOW — its pair is reported in imm_pairs and its event is the Separate; simultaneous events of one hitbox are
     // ordered by partner id alone (they were created in one ascending loop), so the kind bit sits below the partner label
@@ -1234,6 +1235,14 @@ struct SolveArgs {
     unsigned long long* n_imm;
     uint32_t cap_imm;
 };
+
+// The three 32-byte sectors of a 96-byte record, requested into L2 (no register, no scoreboard entry).
+__device__ __forceinline__ void prefetch_rec_l2(const HbRec* rec, uint32_t v) {
+    const char* q = reinterpret_cast<const char*>(rec + v);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 32));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 64));
+}
 
 // A map entry is trusted only if it names a record slot that is live in THIS step and that record carries the gid.
 // One device: vmap = row_of (label -> row; record index == row).  Sharded: vmap = gid -> visitor index.
@@ -1358,6 +1367,14 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
     uint32_t pending_rounds = 0;
     const double T = a.dyn->T;
     const uint64_t keep = l2_policy_evict_last();
+    // Software prefetch (SolveArgs.prefetch): the work item of the thread's NEXT iteration is loaded one iteration early and its
+    // two records are requested into L2 while this iteration's records are in flight and its narrowphase runs.
+    const bool pf = a.prefetch != 0u;
+    WorkItem nxt{0u, 0u, 0u, 0u};
+    {
+        const uint32_t p0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (pf && p0 < n_cand) nxt = work_item_at(a.work, &s_idx, p0);
+    }
     for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
         const uint32_t p = base + threadIdx.x;
         if (p < total) {
@@ -1368,8 +1385,13 @@ __global__ void __launch_bounds__(kThreads, CB200_LB_SOLVE) k_solve(const SolveA
                 const uint2 pr = a.ov_pairs[p - n_cand];
                 present = (!a.ov_live_check || overlap_contains(a.cd.ov, pr.x, pr.y)) && gid_lookup(a, n_local, pr.x, &ia) && gid_lookup(a, n_local, pr.y, &ib);
             } else {
-                const WorkItem it = work_item_at(a.work, &s_idx, p);
+                const WorkItem it = pf ? nxt : work_item_at(a.work, &s_idx, p);
                 ia = it.a; ib = it.b; slot = it.slot;
+                if (pf && p + stride < n_cand) {
+                    nxt = work_item_at(a.work, &s_idx, p + stride);
+                    prefetch_rec_l2(a.rec, nxt.a);
+                    prefetch_rec_l2(a.rec, nxt.b);
+                }
             }
             if (present) {
                 // all twelve 16-byte loads of the two records are issued before anything depends on them

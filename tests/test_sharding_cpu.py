@@ -23,6 +23,19 @@ def test_strip_bounds_and_destinations():
         sharding.strip_bounds(64, 0.0, 8.0, 4.0)
 
 
+def test_migration_routing():
+    """ShardedEngine.migrate: of the (rows, dest) every rank took out of its table, rank r keeps the rows addressed to r."""
+    def part(ids, dest):
+        ids = np.asarray(ids, dtype=np.uint64)
+        return ({"id": ids, "pos_x": ids.astype(np.float64) * 0.5, "kind": (ids % np.uint64(2)).astype(np.uint8)}, np.asarray(dest, dtype=np.int32))
+
+    parts = [part([5, 9, 11], [1, 2, 1]), part([], []), part([3, 40], [0, 1])]
+    got = sharding.rows_for(parts, 1)
+    assert got["id"].tolist() == [5, 11, 40] and got["pos_x"].tolist() == [2.5, 5.5, 20.0] and got["kind"].dtype == np.uint8
+    assert sharding.rows_for(parts, 0)["id"].tolist() == [3] and sharding.rows_for(parts, 2)["id"].tolist() == [9]
+    assert len(sharding.rows_for([part([], []), part([], [])], 0)["id"]) == 0
+
+
 def test_event_key_order():
     k = sharding.event_key
     assert k(1.0, 0, 7, 0) < k(1.0, 2, 3, 1) < k(1.0, 1, 3, 1) < k(1.0, 2, 4, 0) < k(1.5, 0, 0, 0) < k(float("inf"), 0, 0, 0)
