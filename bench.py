@@ -95,6 +95,27 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
 
     def run(self):
+        # NVML in this process (nvidia_ml_py) — forking nvidia-smi several times a second takes driver locks and CPU time away
+        # from the run it is watching; the subprocess is the fallback when the module is missing
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            while not self.stop_flag:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = int(reasons_fn(h))
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         while not self.stop_flag:
             try:
@@ -110,7 +131,8 @@ class ClockSampler(threading.Thread):
             time.sleep(0.25)
 
     def summary(self):
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "source": getattr(self, "source", None)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU side (oracle port)
@@ -342,17 +364,24 @@ def parity_check(cb, scenes, sharding, dist, workload, rank, world, local_rank, 
 def timed_passes(job, barrier, steps, repeats, body, tail=None):
     """`repeats` runs of `steps` calls of body() (+ tail(): whatever the last call left in flight); returns (per-run wall
     seconds, accumulated dict of body's counters)."""
+    import gc
+
     walls, acc = [], {}
     for _ in range(repeats):
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            for k, v in body().items():
-                acc[k] = acc.get(k, 0) + v
-        if tail is not None:
-            tail()
-        barrier()
-        walls.append(time.perf_counter() - t0)
+        gc.collect()
+        gc.disable()  # (a collection pause on one rank is paid by every rank of a sharded step)
+        try:
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                for k, v in body().items():
+                    acc[k] = acc.get(k, 0) + v
+            if tail is not None:
+                tail()
+            barrier()
+            walls.append(time.perf_counter() - t0)
+        finally:
+            gc.enable()
     return walls, acc
 
 
