@@ -628,7 +628,8 @@ def steady_state_block(cb, scenes, sharding, dist, args, rank, world, local_rank
         return {}
 
     body_t()
-    walls_t, _ = timed_passes(job, barrier, K, 1, body_t, tail=eng.fetch_events_end)
+    walls_t, _ = timed_passes(job, barrier, K, 3, body_t, tail=eng.fetch_events_end)
+    walls_t = [sorted(walls_t)[1]]  # (median of three runs: a run in which the overlap list is compacted re-captures the step graph)
     d = eng.last_drain()
     return {"what": "window drain on: events of each step's window processed on the device, overlap set device-resident (cb200_set_window_drain)",
             "device_ms_per_step": dev_ms, "t_step_ms": walls_t[0] / K * 1e3, "hitbox_updates_per_s": args.n * K / walls_t[0],

@@ -98,7 +98,7 @@ struct cb200_ctx {
         uint64_t sig = 0;
         cudaGraphExec_t exec = nullptr;
     };
-    static constexpr int kGraphSlots = 8;  // column-buffer set x step parity (sharded) x dense path on / off
+    static constexpr int kGraphSlots = 32;  // column-buffer set x step parity (sharded) x dense path on / off x (window drain) overlap-list buffer
     GraphSlot graphs[kGraphSlots];
     int graph_next = 0;
     bool capturing = false;
@@ -236,8 +236,6 @@ struct cb200_ctx {
     uint32_t* h_sort_big = nullptr;  // pinned, mapped: k_bs_scan8's oversized-bucket report [1 + 2 * kBsMaxBig]
     uint32_t* d_sort_big = nullptr;  // its device alias
     // pipelined fetch: the one-shot sort as two replayed graphs (keys on the context's stream, sort + decode on the copy stream)
-    SortIn* h_sort_in = nullptr;     // pinned, mapped: the step's counts, written by the host before the launch
-    SortIn* d_sort_in = nullptr;
     DevBuf<SortDyn> sort_dyn;
     struct FetchGraph {
         uint64_t sig = 0;
@@ -432,8 +430,6 @@ int cb200_create(double cell_width, double padding, int device, cb200_ctx** out)
     if ((e = cudaHostGetDevicePointer((void**)&c->d_res, c->h_res, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     if ((e = cudaHostAlloc(&c->h_sort_big, (1 + 2 * kBsMaxBig) * sizeof(uint32_t), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
     if ((e = cudaHostGetDevicePointer((void**)&c->d_sort_big, c->h_sort_big, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
-    if ((e = cudaHostAlloc(&c->h_sort_in, sizeof(SortIn), cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc", e);
-    if ((e = cudaHostGetDevicePointer((void**)&c->d_sort_in, c->h_sort_in, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     if (const char* v = getenv("CB200_FETCH_GRAPH")) c->fetch_graph_enabled = v[0] != '0';
     if (const char* v = getenv("CB200_SOLVE_PREFETCH")) c->solve_prefetch = v[0] != '0';
     if (const char* so = getenv("CB200_SORT")) c->sort_oneshot = strcmp(so, "slow") != 0;
@@ -488,7 +484,6 @@ void cb200_destroy(cb200_ctx* c) {
     if (c->h_gkey) cudaFreeHost(c->h_gkey);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->h_sort_big) cudaFreeHost(c->h_sort_big);
-    if (c->h_sort_in) cudaFreeHost(c->h_sort_in);
     for (auto& g : c->fetch_graphs) {
         if (g.keys) cudaGraphExecDestroy(g.keys);
         if (g.sort) cudaGraphExecDestroy(g.sort);
@@ -2411,28 +2406,30 @@ static int enqueue_sort_graph(cb200_ctx* ctx, uint32_t n_pairs, uint64_t n_solit
         h *= 0x100000001b3ull;
         h ^= h >> 29;
     };
-    const void* ptrs[] = {count, keys, tmp, dyn, dst, ctx->events.p, ctx->reit.p, ctx->col[9].p, ctx->label.p, ctx->d_ctr, ctx->d_sort_in, ctx->d_sort_big};
+    const void* ptrs[] = {count, keys, tmp, dyn, dst, ctx->events.p, ctx->reit.p, ctx->col[9].p, ctx->label.p, ctx->d_ctr, ctx->d_sort_big};
     for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
-    mix(n); mix(nb_max); mix(g_keys); mix((uint64_t)log2_cap);
+    const uint32_t cap_events = (uint32_t)std::min<size_t>(ctx->events.cap, 0xffffffffu), add_mode = ctx->last_add_mode ? 1u : 0u;
+    mix(n); mix(nb_max); mix(g_keys); mix((uint64_t)log2_cap); mix(cap_events); mix(add_mode);
     if (!h) h = 1;
     cb200_ctx::FetchGraph* slot = nullptr;
     for (auto& g : ctx->fetch_graphs)
         if (g.sig == h && g.keys && g.sort) slot = &g;
     if (!slot) {
+        if (getenv("CB200_VERBOSE")) fprintf(stderr, "[cb200] capturing the event-sort graphs (sig %016llx, n %u, cap_keys %zu)\n", (unsigned long long)h, n, cap_keys);
         cb200_ctx::FetchGraph& g = ctx->fetch_graphs[ctx->fetch_graph_next];
         ctx->fetch_graph_next = (ctx->fetch_graph_next + 1) % cb200_ctx::kFetchGraphs;
         if (g.keys) cudaGraphExecDestroy(g.keys);
         if (g.sort) cudaGraphExecDestroy(g.sort);
         g = cb200_ctx::FetchGraph{};
         int rc = capture_to_exec(ctx, ctx->stream, &g.keys, [&]() {
-            k_sortdyn_init<<<1, 1, 0, ctx->stream>>>(ctx->d_sort_in, dyn, range, ctx->d_ctr, log2_cap);
-            k_sortdyn_zero<<<(uint32_t)ctx->sm_count * 2u, kThreads, 0, ctx->stream>>>(dyn, count);
-            if (n) k_keys_solitaire<<<g_rows, kThreads, 0, ctx->stream>>>(n, ctx->reit.p, ctx->col[9].p, ctx->label.p, keys, ctx->d_ctr, range, range + 1);
-            k_keys_pairs_dyn<<<g_keys, kThreads, 0, ctx->stream>>>(dyn, ctx->events.p, keys, range, range + 1);
+            k_sortdyn_init<<<1, 1, 0, ctx->stream>>>(ctx->d_ctr, cap_events, add_mode, dyn, range, log2_cap);
+            k_keys_all_dyn<<<g_rows + g_keys, kThreads, 0, ctx->stream>>>(dyn, g_rows, n, ctx->reit.p, ctx->col[9].p, ctx->label.p, ctx->events.p, keys, ctx->d_ctr, range,
+                                                                         range + 1);
         });
         if (rc != CB200_OK) return fail(ctx, rc, "capture of the event-key graph failed");
         cudaStream_t st = ctx->d2h_stream;
         rc = capture_to_exec(ctx, st, &g.sort, [&]() {
+            k_sortdyn_zero<<<(uint32_t)ctx->sm_count * 2u, kThreads, 0, st>>>(dyn, count);
             k_bs2_count_dyn<<<g_keys, kThreads, 0, st>>>(dyn, keys, range, count);
             k_bs2_scan_local_dyn<<<scan_blocks, 256, 0, st>>>(count, dyn, cursor, block_total);
             k_bs2_scan_add_dyn<<<scan_blocks, 256, 0, st>>>(count, dyn, cursor, block_total, ctx->d_sort_big);
@@ -2444,15 +2441,13 @@ static int enqueue_sort_graph(cb200_ctx* ctx, uint32_t n_pairs, uint64_t n_solit
         g.sig = h;
         slot = &g;
     }
-    ctx->h_sort_in->n_pairs = n_pairs;
-    ctx->h_sort_in->n_sol = n_solitaire;
-    ctx->h_sort_in->add_mode = ctx->last_add_mode ? 1u : 0u;
+    (void)n_pairs; (void)n_solitaire;  // (the graphs read the counts where the step left them: Counters on the device)
     CU(cudaGraphLaunch(slot->keys, ctx->stream));
     CU(cudaEventRecord(ctx->ev_keys_done, ctx->stream));
     ctx->fetch_deferred_sort = slot->sort;  // (launched by flush_deferred_fetch)
     ctx->ev_out_valid = false;
     ctx->sorted_keys = keys;
-    ctx->launches += 10;
+    ctx->launches += 9;
     return CB200_OK;
 }
 

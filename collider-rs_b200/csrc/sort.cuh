@@ -46,10 +46,11 @@ __device__ __forceinline__ void block_range_reduce(unsigned long long lo, unsign
         }
     }
 }
-__global__ void k_keys_solitaire(uint32_t n, const uint8_t* __restrict__ reit, const double* __restrict__ end, const uint32_t* __restrict__ gid,
-                                 Key128* keys, Counters* ctr, BsRange* range, BsRange* lab_range) {
+// (bid / nblk: the block's index and the number of blocks that share the loop — a kernel may run both key loops side by side)
+__device__ __forceinline__ void keys_solitaire_body(uint32_t bid, uint32_t nblk, uint32_t n, const uint8_t* __restrict__ reit, const double* __restrict__ end,
+                                                    const uint32_t* __restrict__ gid, Key128* keys, Counters* ctr, BsRange* range, BsRange* lab_range) {
     unsigned long long lo = ~0ull, hi = 0ull, llo = ~0ull, lhi = 0ull;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n; i += nblk * blockDim.x) {
         if (!reit[i]) continue;
         const unsigned long long pos = warp_agg_claim(&ctr->n_sort_keys);
         const unsigned long long t = time_key(end[i]);
@@ -63,10 +64,14 @@ __global__ void k_keys_solitaire(uint32_t n, const uint8_t* __restrict__ reit, c
     if (range) block_range_reduce(lo, hi, range);
     if (lab_range) block_range_reduce(llo, lhi, lab_range);
 }
-__device__ __forceinline__ void keys_pairs_body(uint32_t n_ev, const PairEvent* __restrict__ ev, Key128* keys, unsigned long long base, BsRange* range,
-                                                BsRange* lab_range) {
+__global__ void k_keys_solitaire(uint32_t n, const uint8_t* __restrict__ reit, const double* __restrict__ end, const uint32_t* __restrict__ gid,
+                                 Key128* keys, Counters* ctr, BsRange* range, BsRange* lab_range) {
+    keys_solitaire_body(blockIdx.x, gridDim.x, n, reit, end, gid, keys, ctr, range, lab_range);
+}
+__device__ __forceinline__ void keys_pairs_body(uint32_t bid, uint32_t nblk, uint32_t n_ev, const PairEvent* __restrict__ ev, Key128* keys, unsigned long long base,
+                                                BsRange* range, BsRange* lab_range) {
     unsigned long long lo = ~0ull, hi = 0ull, llo = ~0ull, lhi = 0ull;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ev; i += gridDim.x * blockDim.x) {
+    for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n_ev; i += nblk * blockDim.x) {
         const PairEvent e = ev[i];
         const unsigned long long t = time_key(e.time);
         keys[base + i] = Key128{kPairClass | ((unsigned long long)e.a << 32) | e.b_kind, t};
@@ -79,7 +84,7 @@ __device__ __forceinline__ void keys_pairs_body(uint32_t n_ev, const PairEvent* 
     if (lab_range) block_range_reduce(llo, lhi, lab_range);
 }
 __global__ void k_keys_pairs(uint32_t n_ev, const PairEvent* __restrict__ ev, Key128* keys, unsigned long long base, BsRange* range, BsRange* lab_range) {
-    keys_pairs_body(n_ev, ev, keys, base, range, lab_range);
+    keys_pairs_body(blockIdx.x, gridDim.x, n_ev, ev, keys, base, range, lab_range);
 }
 __global__ void k_key_diff(uint32_t n, const Key128* __restrict__ keys, Counters* ctr) {
     const Key128 k0 = keys[0];
@@ -550,12 +555,10 @@ __global__ void k_decode_events16(uint32_t n, const Key128* __restrict__ keys, E
 // ---------------------------------------------------------------------------------------------------------
 // The one-shot sort with its sizes in DEVICE memory: the same kernel bodies, launched with grids sized for the buffers'
 // capacity, so that the whole sequence is one pair of CUDA graphs replayed every step (engine.cu cb200_fetch_events_begin:
-// sixteen driver calls per step became four).  The host writes the step's counts into a mapped struct (SortIn) before it
-// launches the first graph; k_sortdyn_init turns them into the sort's parameters.
-struct SortIn {  // pinned, mapped host memory
-    unsigned long long n_pairs, n_sol;
-    uint32_t add_mode, pad;
-};
+// sixteen driver calls per step became a handful).  k_sortdyn_init reads the step's counters where the step left them (the
+// device copy of Counters) and turns them into the sort's parameters.  Only two launches sit on the step's stream — the init
+// and ONE kernel that builds both kinds of keys — everything else, the zeroing of the bucket counters included, runs on the
+// copy stream beside the next step.
 struct SortDyn {
     uint32_t nt, n_pairs, n_buckets;
     int log2_buckets;
@@ -567,14 +570,14 @@ __host__ __device__ inline int bs2_log2_buckets(uint32_t nt, int log2_cap) {
     while ((1u << l) * 8u < nt && l < log2_cap) ++l;  // ~8 keys per bucket (a warp sorts up to kBsMaxBucket)
     return l;
 }
-__global__ void k_sortdyn_init(const volatile SortIn* in, SortDyn* d, BsRange* range /* [2] */, Counters* ctr, int log2_cap) {
+__global__ void k_sortdyn_init(Counters* ctr, uint32_t cap_events, uint32_t add_mode, SortDyn* d, BsRange* range /* [2] */, int log2_cap) {
     SortDyn v;
-    v.n_pairs = (uint32_t)in->n_pairs;
-    v.n_sol = in->n_sol;
+    v.n_pairs = (uint32_t)min(ctr->n_pair_events, (unsigned long long)cap_events);
+    v.n_sol = ctr->n_solitaire;
     v.nt = v.n_pairs + (uint32_t)v.n_sol;
     v.log2_buckets = bs2_log2_buckets(v.nt, log2_cap);
     v.n_buckets = 2u << v.log2_buckets;  // region A + region B
-    v.add_mode = in->add_mode;
+    v.add_mode = add_mode;
     v.pad = 0;
     *d = v;
     range[0] = BsRange{~0ull, 0ull};
@@ -585,8 +588,14 @@ __global__ void k_sortdyn_zero(const SortDyn* d, uint32_t* count) {
     const uint32_t m = d->n_buckets + 1u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) count[i] = 0u;
 }
-__global__ void k_keys_pairs_dyn(const SortDyn* d, const PairEvent* __restrict__ ev, Key128* keys, BsRange* range, BsRange* lab_range) {
-    keys_pairs_body(d->n_pairs, ev, keys, d->n_sol, range, lab_range);
+// blocks [0, g_rows): the Reiterate keys of the table rows; blocks [g_rows, gridDim.x): the pair-event keys
+__global__ void k_keys_all_dyn(const SortDyn* d, uint32_t g_rows, uint32_t n, const uint8_t* __restrict__ reit, const double* __restrict__ end,
+                               const uint32_t* __restrict__ gid, const PairEvent* __restrict__ ev, Key128* keys, Counters* ctr, BsRange* range, BsRange* lab_range) {
+    if (blockIdx.x < g_rows) {
+        if (d->n_sol) keys_solitaire_body(blockIdx.x, g_rows, n, reit, end, gid, keys, ctr, range, lab_range);
+    } else {
+        keys_pairs_body(blockIdx.x - g_rows, gridDim.x - g_rows, d->n_pairs, ev, keys, d->n_sol, range, lab_range);
+    }
 }
 __global__ void k_bs2_count_dyn(const SortDyn* d, const Key128* __restrict__ keys, const BsRange* r, uint32_t* count) {
     const uint32_t n = d->nt;
