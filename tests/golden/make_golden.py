@@ -30,6 +30,8 @@ CASES = [
     # config 4's density (1 shape per unit^2, ~30 entries per slot run): from its second step on the device takes the
     # dense-run path (k_solve_dense), chosen from the first step's counters
     dict(name="dense_250", scene="uniform", n=250, density=1.0, end=0.1, dt=0.1, steps=3),
+    # resizing shapes in several groups
+    dict(name="groups_resizing_600", scene="groups", n=600, density=0.2, end=0.1, dt=0.1, steps=3),
 ]
 
 
@@ -38,6 +40,8 @@ def make_scene(case):
         return scenes.c1(case["n"])
     if case["scene"] == "c5":
         return scenes.c5(case["n"])
+    if case["scene"] == "groups":  # resize velocities, four groups (one HbGroup None, asymmetric interact lists), origin-centred
+        return scenes.with_groups_and_resizing(scenes.uniform_density(case["n"], density=case["density"], seed=scenes.SEED_BASE + 6), scenes.SEED_BASE + 6)
     return scenes.uniform_density(case["n"], density=case.get("density", 0.025))
 
 

@@ -22,6 +22,8 @@ def make_scene(case):
         return scenes.c1(case["n"])
     if case["scene"] == "c5":
         return scenes.c5(case["n"])
+    if case["scene"] == "groups":  # resize velocities, four groups (one HbGroup None, asymmetric interact lists), origin-centred
+        return scenes.with_groups_and_resizing(scenes.uniform_density(case["n"], density=case["density"], seed=scenes.SEED_BASE + 6), scenes.SEED_BASE + 6)
     return scenes.uniform_density(case["n"], density=case.get("density", 0.025))
 
 

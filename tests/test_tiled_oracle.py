@@ -14,10 +14,13 @@ def bits(a):
     return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
 
 
-@pytest.mark.parametrize("name", ["sparse", "clustered", "dense"])
+@pytest.mark.parametrize("name", ["sparse", "clustered", "dense", "groups_resizing"])
 def test_tiled_equals_single(oracle, name):
     scene = {"sparse": lambda: scenes.uniform_density(20000), "clustered": lambda: scenes.c5(20000),
-             "dense": lambda: scenes.uniform_density(6000, density=1.0, seed=scenes.SEED_BASE + 40)}[name]()
+             "dense": lambda: scenes.uniform_density(6000, density=1.0, seed=scenes.SEED_BASE + 40),
+             # (f-4: resize velocities, four groups with asymmetric interact lists, coordinates around the origin — at a density
+             # that gives this small scene enough events)
+             "groups_resizing": lambda: scenes.with_groups_and_resizing(scenes.uniform_density(20000, density=0.1, seed=scenes.SEED_BASE + 6), scenes.SEED_BASE + 6)}[name]()
     orc = oracle.Collider(scenes.CELL_WIDTH, scenes.PADDING)
     orc.add_hitboxes(scene)
     st0 = orc.dump_state()
