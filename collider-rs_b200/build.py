@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "engine.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("engine.cu", "kernels.cuh", "common.cuh", "narrowphase.cuh", "sort.cuh", "single.cuh", "tile.cuh", "drain.cuh", "migrate.cuh", "collider.inl")] + [
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("engine.cu", "kernels.cuh", "common.cuh", "narrowphase.cuh", "sort.cuh", "single.cuh", "tile.cuh", "drain.cuh", "migrate.cuh", "sort_cut.cuh", "collider.inl")] + [
     os.path.join(ROOT, "include", "collider_b200.h")
 ]
 OUT = os.path.join(HERE, "lib", "libcollider_b200.so")

@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "narrowphase.cuh"
+#include "sort_cut.cuh"
 
 namespace cb200 {
 
@@ -18,8 +19,6 @@ constexpr uint32_t kFInvalidTime = 1u << 0, kFEndTime = 1u << 1, kFCircleResize 
                    kFIdNotFound = 1u << 8, kFPeerLost = 1u << 9;
 
 constexpr uint32_t kGroupNone = 0xFFFFFFFFu;
-constexpr uint32_t kCollideBit = 0x80000000u;  // in PairEvent.b_kind: 1 = Collide, 0 = Separate
-constexpr uint64_t kPairClass = 0x8000000000000000ull;
 
 // The DurHitbox a hitbox presents to the pair stage at the step time (core/dur_hitbox/mod.rs:27-70)
 // plus its IndexRect (index_rect.rs:17-31) and profile bits: 96 B = three 32-B sectors.  Sector 0 is
@@ -180,26 +179,6 @@ struct MinKey {
     uint64_t t, tie;
 };
 __device__ __forceinline__ bool key_less(const MinKey& a, const MinKey& b) { return a.t < b.t || (a.t == b.t && a.tie < b.tie); }
-__host__ __device__ __forceinline__ uint64_t time_key(double t) {
-    t = t + 0.0;  // -0.0 -> +0.0 (round-to-nearest; every other value unchanged): the two zeros are one time in the reference's order (N64's Ord is partial_cmp, float.rs:36-42)
-#if defined(__CUDA_ARCH__)
-    const uint64_t b = (uint64_t)__double_as_longlong(t);
-#else
-    uint64_t b;
-    memcpy(&b, &t, 8);
-#endif
-    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__host__ __device__ __forceinline__ double key_time(uint64_t k) {
-    const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
-#if defined(__CUDA_ARCH__)
-    return __longlong_as_double((long long)b);
-#else
-    double t;
-    memcpy(&t, &b, 8);
-    return t;
-#endif
-}
 constexpr uint64_t kKeyMax = 0xFFFFFFFFFFFFFFFFull;
 
 __device__ __forceinline__ MinKey warp_min(MinKey k) {

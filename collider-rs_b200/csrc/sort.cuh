@@ -7,17 +7,9 @@
 
 namespace cb200 {
 
-struct alignas(16) Key128 {
-    unsigned long long lo;  // tie: class | hi << 32 | kind << 31 | lo     (solitaire: slot)
-    unsigned long long hi;  // time_key(time)
-};
-
 // Reiterate events live in the state columns (reit flag + internal end_time); append their keys.
 // Both key kernels also reduce the range of the time keys they produce into *range (min, max; null: not wanted): one
 // atomic pair per block instead of a separate pass over the keys.
-struct BsRange {
-    unsigned long long lo, hi;  // min / max of a key field
-};
 __device__ __forceinline__ void block_range_reduce(unsigned long long lo, unsigned long long hi, BsRange* range) {
     __shared__ unsigned long long s_lo[32], s_hi[32];
     __syncthreads();  // (called twice per kernel: time range, label range)
@@ -247,7 +239,6 @@ constexpr int kBsMaxBucket = 256;  // keys a warp sorts in shared memory (8 warp
 // The buckets are cut on ONE 64-bit field of the key: the time key (field 1), or — for a set of keys that all carry the
 // same time, e.g. everything that happens exactly at T — the tie word (field 0).  Buckets that come out too large for a warp
 // are sorted again on their own range (the host recurses, sort_range in engine.cu).
-__device__ __forceinline__ unsigned long long bs_field(const Key128& k, int field) { return field ? k.hi : k.lo; }
 __global__ void k_bs_minmax(uint32_t n, const Key128* __restrict__ keys, int field, BsRange* r) {
     unsigned long long lo = ~0ull, hi = 0ull;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -264,21 +255,6 @@ __global__ void k_bs_minmax(uint32_t n, const Key128* __restrict__ keys, int fie
         atomicMin(&r->lo, lo);
         atomicMax(&r->hi, hi);
     }
-}
-// Bucket of a field value: monotone non-decreasing in the value (that is all the sort needs).  Times are cut linearly in
-// the time itself — the bit pattern of a double is linear only inside one binade, and a step starting at T = 0 spans all of
-// them; the tie word is an integer and is cut on its leading bits.
-__device__ __forceinline__ uint32_t bs_bucket(unsigned long long t, const BsRange& r, int log2_buckets, int field) {
-    if (field == 1) {
-        const double lo = key_time(r.lo), hi = key_time(r.hi), x = key_time(t);
-        const double scaled = (x - lo) * ((double)(1u << log2_buckets) / (hi - lo));  // hi > lo here; finite (times < 1e50)
-        const uint32_t last = (1u << log2_buckets) - 1u;
-        return scaled >= (double)last ? last : (uint32_t)scaled;
-    }
-    const unsigned long long span = r.hi - r.lo;
-    const int bits = span ? 64 - __clzll((long long)span) : 0;  // span < 2^bits
-    const int shift = bits > log2_buckets ? bits - log2_buckets : 0;
-    return (uint32_t)((t - r.lo) >> shift);
 }
 __global__ void k_bs_count(uint32_t n, const Key128* __restrict__ keys, int field, const BsRange* r, int log2_buckets, uint32_t* count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -386,18 +362,6 @@ __global__ void __launch_bounds__(256) k_bs_local(const Key128* __restrict__ in,
 // The labels are cut over the range [lab.lo, lab.hi] the step's keys actually carry (reduced by the key kernels next to the
 // time range): a sharded rank's labels (= ids) cover about 1 / world of the id space, and cutting over the whole id space
 // left most of region A's buckets empty and the rest oversized (every fetch then fell back to the recursive sort).
-__device__ __forceinline__ uint32_t bs2_bucket(const Key128& k, const BsRange& r, int log2_buckets, const BsRange& lab) {
-    const uint32_t nb = 1u << log2_buckets;
-    if (k.hi == r.lo) {
-        const uint32_t half = nb >> 1;
-        const bool pair = (k.lo & kPairClass) != 0;
-        const unsigned long long label = pair ? ((k.lo >> 32) & 0x7fffffffull) : min(k.lo, 0xffffffffull);
-        const unsigned long long bound = lab.hi - lab.lo + 1ull;                      // (lab.lo <= label <= lab.hi)
-        const unsigned long long rel = min(label - min(label, lab.lo), bound - 1ull);
-        return (pair ? half : 0u) + (uint32_t)((rel * half) / bound);
-    }
-    return nb + bs_bucket(k.hi, r, log2_buckets, 1);  // (r.hi > r.lo here)
-}
 __global__ void k_bs2_count(uint32_t n, const Key128* __restrict__ keys, const BsRange* r /* [2]: time range, label range */, int log2_buckets, uint32_t* count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) atomicAdd(&count[bs2_bucket(keys[i], r[0], log2_buckets, r[1])], 1u);
@@ -527,26 +491,6 @@ __global__ void k_decode_events(uint32_t n, const Key128* __restrict__ keys, con
     out[i] = e;
 }
 
-// The compact form (cb200_event16): labels instead of ids, the kind in the two spare top bits.
-struct Event16 {
-    double time;
-    uint32_t a, b;
-};
-__device__ __forceinline__ Event16 decode_event16(const Key128& k, int add_mode) {
-    Event16 e;
-    e.time = key_time(k.hi);
-    if (k.lo & kPairClass) {
-        const uint32_t hi = (uint32_t)((k.lo >> 32) & 0x7fffffffu);
-        const uint32_t lo = add_mode ? (uint32_t)((k.lo & 0xffffffffu) >> 1) : (uint32_t)(k.lo & 0x7fffffffu);
-        const bool collide = (add_mode ? (k.lo & 1ull) : (k.lo & kCollideBit)) != 0;
-        e.a = hi;
-        e.b = lo | (collide ? 0x80000000u : 0u);
-    } else {
-        e.a = (uint32_t)k.lo | 0x80000000u;  // Reiterate
-        e.b = 0u;
-    }
-    return e;
-}
 __global__ void k_decode_events16(uint32_t n, const Key128* __restrict__ keys, Event16* out, int add_mode) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = decode_event16(keys[i], add_mode);
@@ -565,11 +509,6 @@ struct SortDyn {
     unsigned long long n_sol;
     uint32_t add_mode, pad;
 };
-__host__ __device__ inline int bs2_log2_buckets(uint32_t nt, int log2_cap) {
-    int l = 6;
-    while ((1u << l) * 8u < nt && l < log2_cap) ++l;  // ~8 keys per bucket (a warp sorts up to kBsMaxBucket)
-    return l;
-}
 __global__ void k_sortdyn_init(Counters* ctr, uint32_t cap_events, uint32_t add_mode, SortDyn* d, BsRange* range /* [2] */, int log2_cap) {
     SortDyn v;
     v.n_pairs = (uint32_t)min(ctr->n_pair_events, (unsigned long long)cap_events);
