@@ -61,7 +61,9 @@ def config_of(args):
     """Identical for both arms (the driver compares them)."""
     return {"workload": f"{args.workload}: {args.n} mixed circles/rects per GPU, uniform density {DENSITY[args.workload]}/unit^2, cell_width 4, padding 0.01, "
                         f"bulk step every {DT} (full re-bin + pair TOI solve + next-event min + ordered event list)",
-            "hitboxes_per_gpu": args.n, "scaling_unit": "one column strip of the world per GPU"}
+            "hitboxes_per_gpu": args.n, "scaling_unit": "one column strip of the world per GPU",
+            "l2": "inputs larger than L2 (GPU arm): the working set of a step — SoA state, records, slot table, cell entries — is > 300 MB per "
+                  "million hitboxes against the 126 MB L2; nothing is flushed between iterations"}
 
 
 def make_workload(scenes, name: str, n: int, rank: int, world: int):
